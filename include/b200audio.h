@@ -1,0 +1,223 @@
+/*
+ * b200audio.h -- C ABI of the B200-native STFT-family DSP path.
+ *
+ * Drop-in boundary for the DSP helpers of smdesai/mlx-swift-audio (the reference has no
+ * FFI layer of its own: the seam is its set of Swift free functions, SURVEY.md section
+ * 8b).  Every entry point below names the reference function it replaces (paths relative
+ * to the reference's package/ directory).  Plain pointers and sizes only; no torch / MLX
+ * types.  INTEGRATION.md shows the Swift-side binding.
+ *
+ * Conventions
+ *  - All arithmetic is IEEE fp32 on the GPU (sm_100a CUDA kernels).  There is NO CPU
+ *    fallback: every compute entry point fails with B2A_E_CUDA when no device is usable.
+ *  - `space` says where the caller's buffers live: B2A_DEVICE (device pointers; work is
+ *    enqueued on the context's stream and the call returns immediately) or B2A_HOST
+ *    (host pointers, pinned preferred: the call stages clips through device memory in
+ *    overlapped chunks and returns after the result is in the caller's buffer).
+ *  - The reference helpers take ONE clip (T,).  Here every entry point takes `batch`
+ *    independent clips of equal length laid out (batch, n_samples) row-major; batch = 1
+ *    is exactly the reference call.  Outputs are (batch, ...reference shape...).
+ *  - Output buffers are caller-allocated; the *_shape functions are pure integer code.
+ *  - The reference calls fatalError on bad input; here a non-zero status is returned and
+ *    b2a_last_error(ctx) describes it (the Swift shim turns it back into fatalError).
+ *  - A context owns a stream, device tables (windows, sparse filterbanks, twiddles) and
+ *    scratch.  One context per host thread / stream; contexts share no mutable state.
+ */
+#ifndef B200AUDIO_H_
+#define B200AUDIO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B2A_API
+#else
+#define B2A_API __attribute__((visibility("default")))
+#endif
+
+typedef struct b2a_ctx b2a_ctx;
+
+enum b2a_status {
+  B2A_OK = 0,
+  B2A_E_BAD_ARG = 1,     /* null pointer, non-positive size, unsupported parameter value        */
+  B2A_E_TOO_SHORT = 2,   /* reference: fatalError("Input is too short for STFT")                */
+  B2A_E_CUDA = 3,        /* CUDA runtime / launch failure, or no sm_100 device                  */
+  B2A_E_UNSUPPORTED = 4, /* valid in the reference but not built here (e.g. n_fft outside set)  */
+  B2A_E_NOMEM = 5
+};
+
+enum b2a_space { B2A_HOST = 0, B2A_DEVICE = 1 };
+
+/* window generators of the reference */
+enum b2a_window_kind {
+  B2A_WIN_WHISPER_HANN = 0,  /* whisperHannWindow        STT/Whisper/WhisperAudio.swift:32-44 (symmetric)         */
+  B2A_WIN_HANNING = 1,       /* hanningWindow / hanning  Codec/S3Tokenizer/S3TokenizerUtils.swift:213-221,
+                                                         TTS/Kokoro/Decoder/MLXSTFT.swift:12-20 (np.hanning)      */
+  B2A_WIN_HAMMING = 2,       /* hammingWindow            STT/FunASR/FunASRAudio.swift:35-45                       */
+  B2A_WIN_POVEY = 3,         /* poveyWindow              Codec/S3Gen/CAMPPlus.swift:15-19                         */
+  B2A_WIN_HANN_PERIODIC = 4  /* hannWindowPeriodic       Codec/S3Gen/HiFiGAN.swift:15-20,
+                                cosyVoice3HannWindowPeriodic TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:429-432 */
+};
+
+/* ---------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------- */
+B2A_API const char* b2a_version(void);
+/* Creates a context on `device` with its own non-blocking stream. */
+B2A_API int b2a_ctx_create(b2a_ctx** ctx, int device);
+/* Same, but enqueues on the caller's stream (a cudaStream_t passed as void*; NULL = legacy default). */
+B2A_API int b2a_ctx_create_on_stream(b2a_ctx** ctx, int device, void* cuda_stream);
+B2A_API int b2a_ctx_destroy(b2a_ctx* ctx);
+B2A_API int b2a_ctx_sync(b2a_ctx* ctx);
+B2A_API const char* b2a_last_error(const b2a_ctx* ctx);
+/* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
+B2A_API int64_t b2a_ctx_launch_count(const b2a_ctx* ctx);
+/* Pinned host memory for B2A_HOST buffers (optional; pageable pointers also work, slower). */
+B2A_API int b2a_host_alloc(void** ptr, uint64_t bytes);
+B2A_API int b2a_host_free(void* ptr);
+
+/* ---------------------------------------------------------------------------------------
+ * host-side pure functions (no GPU needed): windows, filterbanks, index and shape rules
+ * ------------------------------------------------------------------------------------- */
+B2A_API int b2a_window(int kind, int length, float* out);                       /* see enum b2a_window_kind */
+/* melFilters (Slaney)      Codec/S3Tokenizer/S3TokenizerUtils.swift:301-375.  out (n_mels, n_fft/2+1).  f_max < 0 = nil (sr/2). */
+B2A_API int b2a_mel_filters(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out);
+/* funASRMelFilters (HTK)   STT/FunASR/FunASRAudio.swift:322-396.  out (n_mels, n_fft/2) -- 200-point linspace grid. */
+B2A_API int b2a_funasr_mel_filters(int sample_rate, int n_fft, int n_mels, float* out);
+/* melFiltersHTK            Codec/S3Gen/CAMPPlus.swift:134-175.  out (n_fft/2+1, n_mels) -- integer-bin triangles. */
+B2A_API int b2a_mel_filters_htk(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out);
+/* Source index of padded position i (0 <= i < n + 2*pad) under reflectPad / reflectPad1D
+ * (S3TokenizerUtils.swift:266-298, FunASRAudio.swift:280-310), incl. the short-input loops. */
+B2A_API int64_t b2a_reflect_pad_index(int64_t i, int64_t n, int64_t pad);
+/* nextPowerOf2             Codec/S3Gen/CAMPPlus.swift:22-29 */
+B2A_API int b2a_next_power_of_2(int n);
+/* computeFeatureLength     STT/FunASR/FunASRAudio.swift:225-235 */
+B2A_API int64_t b2a_funasr_compute_feature_length(int64_t audio_length, int hop_length, int lfr_n);
+
+/* frame-count rules (all return < 0 for "too short") */
+B2A_API int64_t b2a_stft_num_frames(int64_t n_samples, int n_fft, int hop, int center);  /* stft: 1 + (T + 2*(n_fft/2)*center - n_fft) / hop */
+B2A_API int64_t b2a_whisper_num_frames(int64_t n_samples, int64_t padding);               /* stft frames - 1 */
+B2A_API int64_t b2a_funasr_num_frames(int64_t n_samples);                                 /* 1 + T/160 */
+B2A_API int64_t b2a_lfr_num_rows(int64_t n_frames, int lfr_n);                             /* ceil(T / lfr_n) */
+B2A_API int64_t b2a_kaldi_num_frames(int64_t n_samples, int win_length, int hop);          /* max(1, (T - win)/hop + 1) */
+B2A_API int64_t b2a_s3gen_num_frames(int64_t n_samples, int n_fft, int hop);               /* on reflectPad2D'ed signal, center=false */
+B2A_API int64_t b2a_vocoder_stft_num_frames(int64_t n_samples, int n_fft, int hop);        /* (T + 2*(n_fft/2) - n_fft)/hop + 1 */
+B2A_API int64_t b2a_istft_out_length(int64_t n_frames, int hop);                           /* (frames - 1) * hop */
+
+/* ---------------------------------------------------------------------------------------
+ * log-mel / fbank front ends
+ * ------------------------------------------------------------------------------------- */
+
+/* padOrTrim                STT/Whisper/WhisperAudio.swift:54-67.  out (batch, length). */
+B2A_API int b2a_pad_or_trim(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int64_t length,
+                            float* out, int space);
+
+/* whisperLogMelSpectrogram STT/Whisper/WhisperAudio.swift:78-137.
+ * audio (batch, n_samples) -> out (batch, T', n_mels), T' = b2a_whisper_num_frames(n_samples, padding).
+ * The max-8 clamp uses each clip's own global maximum, as the single-clip reference does. */
+B2A_API int b2a_whisper_log_mel_spectrogram(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
+                                            int n_mels, int64_t padding, float* out, int space);
+
+/* logMelSpectrogramChatterbox Codec/S3Tokenizer/S3TokenizerUtils.swift:160-208 (and the wrapper
+ * logMelSpectrogramCAMPPlus TTS/CosyVoice2/CosyVoice2TTS.swift:787-795).  out (batch, n_mels, T'). */
+B2A_API int b2a_log_mel_spectrogram_chatterbox(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
+                                               int n_mels, int64_t padding, float* out, int space);
+
+/* funASRLogMelSpectrogram  STT/FunASR/FunASRAudio.swift:57-94 (n_fft 400, hop 160).  out (batch, T', n_mels). */
+B2A_API int b2a_funasr_log_mel_spectrogram(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
+                                           int n_mels, float* out, int space);
+/* applyLFR                 STT/FunASR/FunASRAudio.swift:108-154.  features (batch, T, n_mels) -> (batch, ceil(T/lfr_n), lfr_m*n_mels). */
+B2A_API int b2a_apply_lfr(b2a_ctx* ctx, const float* features, int64_t batch, int64_t n_frames, int n_mels,
+                          int lfr_m, int lfr_n, float* out, int space);
+/* applyCMVN                STT/FunASR/FunASRAudio.swift:165-180.  cmvn_mean/cmvn_istd (dim,) or both NULL (per-utterance). */
+B2A_API int b2a_apply_cmvn(b2a_ctx* ctx, const float* features, int64_t batch, int64_t n_rows, int dim,
+                           const float* cmvn_mean, const float* cmvn_istd, float* out, int space);
+/* preprocessAudio          STT/FunASR/FunASRAudio.swift:197-216.  out (batch, ceil(T'/lfr_n), lfr_m*n_mels). */
+B2A_API int b2a_funasr_preprocess_audio(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
+                                        int n_mels, int lfr_m, int lfr_n, int apply_normalization,
+                                        float* out, int space);
+
+/* kaldiFbankCAMPPlus       Codec/S3Gen/CAMPPlus.swift:32-106.  out (batch, T', num_mel_bins).
+ * mean_norm != 0 additionally applies the caller-side `fbank - mean(fbank, axis: 0)` of
+ * CAMPPlus.inference (CAMPPlus.swift:797-802), per clip. */
+B2A_API int b2a_kaldi_fbank_campplus(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
+                                     int sample_rate, int num_mel_bins, float frame_length_ms, float frame_shift_ms,
+                                     int mean_norm, float* out, int space);
+
+/* s3genMelSpectrogram      Codec/S3Gen/Mel/S3GenMel.swift:43-102 (wrappers computeMelSpectrogram80
+ * CosyVoice2TTS.swift:754-770, CosyVoice3TTS.swift:770-787, melSpectrogramS3Gen ChatterboxTurboModel.swift:545-572).
+ * y (batch, n_samples) -> out (batch, num_mels, T').  Built for n_fft=win_size=1920, hop=480. */
+B2A_API int b2a_s3gen_mel_spectrogram(b2a_ctx* ctx, const float* y, int64_t batch, int64_t n_samples, int n_fft,
+                                      int num_mels, int sampling_rate, int hop_size, int win_size, int fmin, int fmax,
+                                      float* out, int space);
+
+/* voiceEncoderMelspectrogram TTS/Chatterbox/VoiceEncoder/VoiceEncoderMelspec.swift:17-68 with VoiceEncConfig
+ * (Config/ChatterboxConfig.swift:139-156).  out (batch, num_mels, T'). */
+typedef struct b2a_voice_enc_config {
+  int num_mels;            /* 40    */
+  int sample_rate;         /* 16000 */
+  int n_fft;               /* 400   */
+  int hop_size;            /* 160   */
+  int win_size;            /* 400   */
+  int fmin;                /* 0     */
+  int fmax;                /* 8000  */
+  float mel_power;         /* 2.0 (1.0 and 2.0 are built) */
+  int mel_type_db;         /* 0 = "amp" (default), 1 = "db" */
+  int normalized_mels;     /* 0 */
+  float stft_magnitude_min;/* 1e-4 */
+} b2a_voice_enc_config;
+B2A_API void b2a_voice_enc_config_default(b2a_voice_enc_config* cfg);
+B2A_API int b2a_voice_encoder_melspectrogram(b2a_ctx* ctx, const float* wav, int64_t batch, int64_t n_samples,
+                                             const b2a_voice_enc_config* cfg, float* out, int space);
+
+/* stft                     Codec/S3Tokenizer/S3TokenizerUtils.swift:224-263 (== funASRSTFT FunASRAudio.swift:240-277).
+ * window (win_len,) host pointer, zero-extended to n_fft; out (batch, T', n_fft/2+1) complex64 interleaved (re, im).
+ * Built for n_fft in {400, 512, 1920} with hop {160, 160, 480}. */
+B2A_API int b2a_stft(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, const float* window, int win_len,
+                     int n_fft, int hop, int center, float* out_complex, int space);
+
+/* ---------------------------------------------------------------------------------------
+ * vocoder STFT / iSTFT (n_fft 16 hop 4, n_fft 20 hop 5)
+ * ------------------------------------------------------------------------------------- */
+
+/* stftHiFiGAN              Codec/S3Gen/HiFiGAN.swift:257-295.  x (batch, T) -> real, imag (batch, n_fft/2+1, frames).
+ * window (n_fft,) host pointer. */
+B2A_API int b2a_stft_hifigan(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int n_fft, int hop,
+                             const float* window, float* real_out, float* imag_out, int space);
+/* istftHiFiGAN             Codec/S3Gen/HiFiGAN.swift:298-367.  magnitude, phase (batch, n_fft/2+1, frames)
+ * -> out (batch, (frames-1)*hop). */
+B2A_API int b2a_istft_hifigan(b2a_ctx* ctx, const float* magnitude, const float* phase, int64_t batch,
+                              int64_t n_frames, int n_fft, int hop, const float* window, float* out, int space);
+/* cosyVoice3Stft           TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:435-460 (zero padding). */
+B2A_API int b2a_cosyvoice3_stft(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int n_fft, int hop,
+                                const float* window, float* real_out, float* imag_out, int space);
+/* cosyVoice3Istft          TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:463-514 (clip magnitude to [0, 100]). */
+B2A_API int b2a_cosyvoice3_istft(b2a_ctx* ctx, const float* magnitude, const float* phase, int64_t batch,
+                                 int64_t n_frames, int n_fft, int hop, const float* window, float* out, int space);
+/* MLXSTFT.transform        TTS/Kokoro/Decoder/MLXSTFT.swift:181-209 (mlxStft :69-113, "hann", center, reflect).
+ * x (batch, T) -> magnitude, phase (batch, filter_length/2+1, frames). */
+B2A_API int b2a_kokoro_stft_transform(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples,
+                                      int filter_length, int hop_length, int win_length,
+                                      float* magnitude_out, float* phase_out, int space);
+/* MLXSTFT.inverse          TTS/Kokoro/Decoder/MLXSTFT.swift:211-235 (unwrap :23-46, mlxIstft :115-163).
+ * magnitude, phase (batch, F, frames) -> out (batch, 1, (frames-1)*hop). */
+B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const float* phase, int64_t batch,
+                                    int64_t n_frames, int filter_length, int hop_length, int win_length,
+                                    float* out, int space);
+
+/* ---------------------------------------------------------------------------------------
+ * instrumentation used by bench.py (device-side timing of the last call's kernels)
+ * ------------------------------------------------------------------------------------- */
+/* When enabled, every compute entry point brackets its kernels with CUDA events on the
+ * context's stream; b2a_ctx_last_kernel_ms returns the elapsed time of the last call
+ * (synchronises the two events).  Off by default. */
+B2A_API int b2a_ctx_enable_timing(b2a_ctx* ctx, int on);
+B2A_API int b2a_ctx_last_kernel_ms(b2a_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AUDIO_H_ */

@@ -1,0 +1,538 @@
+"""Host-side mirror of the reference's Swift DSP helpers over the C ABI (ctypes).
+
+Function names and argument meaning follow the Swift free functions they replace (SURVEY.md
+section 8b); the Swift labels become keyword arguments.  Inputs may be
+
+  * NumPy float32 arrays  -> B2A_HOST  (the library stages them through the GPU), or
+  * torch CUDA tensors    -> B2A_DEVICE (kernels run on the current torch stream, async).
+
+and the result comes back as the same kind.  Where the reference takes one clip ``(T,)``, a
+leading batch axis ``(B, T)`` is also accepted (independent clips; per-clip statistics).
+
+Error behaviour: the reference ``fatalError``s on bad input; here ``B2AError`` is raised
+(``B2ATooShort`` for "Input is too short for STFT").  There is no CPU fallback: every call
+reaches a CUDA kernel or raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib as L
+
+
+class B2AError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"b200audio {L.STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class B2ATooShort(B2AError):
+    pass
+
+
+def _raise(status: int, msg: str):
+    raise (B2ATooShort if status == L.B2A_E_TOO_SHORT else B2AError)(status, msg)
+
+
+class Context:
+    """Owns a b2a_ctx (stream, device tables, scratch).  One per host thread / stream."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = L.load()
+        h = C.c_void_p()
+        if stream is None:
+            rc = self.lib.b2a_ctx_create(C.byref(h), device)
+        else:
+            rc = self.lib.b2a_ctx_create_on_stream(C.byref(h), device, C.c_void_p(stream))
+        if rc != L.B2A_OK:
+            _raise(rc, "cannot create a context (no sm_100 CUDA device?)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2a_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self.check(self.lib.b2a_ctx_sync(self.h))
+
+    def check(self, rc: int):
+        if rc != L.B2A_OK:
+            _raise(rc, self.lib.b2a_last_error(self.h).decode())
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b2a_ctx_launch_count(self.h))
+
+    def enable_timing(self, on: bool = True):
+        self.check(self.lib.b2a_ctx_enable_timing(self.h, int(on)))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self.check(self.lib.b2a_ctx_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+
+_tls = threading.local()
+
+
+def default_context(device: int = 0, stream: int | None = None) -> Context:
+    key = (device, stream)
+    cache = getattr(_tls, "ctx", None)
+    if cache is None:
+        cache = _tls.ctx = {}
+    if key not in cache:
+        cache[key] = Context(device, stream)
+    return cache[key]
+
+
+# ---- array plumbing -------------------------------------------------------------------------------
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Arr:
+    """Uniform view of a NumPy array (host) or a torch CUDA tensor (device)."""
+
+    def __init__(self, x):
+        if _is_torch(x):
+            import torch
+            if not x.is_cuda:
+                raise B2AError(L.B2A_E_BAD_ARG, "torch tensors must live on a CUDA device (use NumPy arrays for host data)")
+            self.t = x.detach().to(torch.float32).contiguous()
+            self.space = L.B2A_DEVICE
+            self.shape = tuple(self.t.shape)
+            self.ptr = C.c_void_p(self.t.data_ptr())
+            self.device = self.t.device.index or 0
+        else:
+            self.t = np.ascontiguousarray(x, dtype=np.float32)
+            self.space = L.B2A_HOST
+            self.shape = self.t.shape
+            self.ptr = C.c_void_p(self.t.ctypes.data)
+            self.device = None
+
+    def empty(self, shape):
+        if self.space == L.B2A_DEVICE:
+            import torch
+            return torch.empty(shape, dtype=torch.float32, device=self.t.device)
+        return np.empty(shape, np.float32)
+
+
+def _ptr(a):
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _ctx_for(a: _Arr, ctx: Context | None) -> Context:
+    if ctx is not None:
+        return ctx
+    if a.space == L.B2A_DEVICE:
+        import torch
+        return default_context(a.device, torch.cuda.current_stream(a.device).cuda_stream)
+    return default_context(0, None)
+
+
+def _batched(a: _Arr, base_ndim: int):
+    """-> (batch, n, had_batch_axis)"""
+    if len(a.shape) == base_ndim:
+        return 1, a.shape[-1], False
+    if len(a.shape) == base_ndim + 1:
+        return a.shape[0], a.shape[-1], True
+    raise B2AError(L.B2A_E_BAD_ARG, f"expected {base_ndim}-D input (or one leading batch axis), got shape {a.shape}")
+
+
+def _fptr(w: np.ndarray):
+    return w.ctypes.data_as(C.POINTER(C.c_float))
+
+
+# ---- host-only helpers (windows, filterbanks, shape rules) --------------------------------------------
+
+def _window(kind: int, length: int) -> np.ndarray:
+    out = np.empty(length, np.float32)
+    rc = L.load().b2a_window(kind, length, _fptr(out))
+    if rc != L.B2A_OK:
+        _raise(rc, "bad window parameters")
+    return out
+
+
+def whisperHannWindow(length: int) -> np.ndarray:
+    """STT/Whisper/WhisperAudio.swift:32-44"""
+    return _window(L.WIN_WHISPER_HANN, length)
+
+
+def hanningWindow(length: int) -> np.ndarray:
+    """Codec/S3Tokenizer/S3TokenizerUtils.swift:213-221 (== Kokoro ``hanning``, MLXSTFT.swift:12-20)"""
+    return _window(L.WIN_HANNING, length)
+
+
+hanning = hanningWindow
+
+
+def hammingWindow(length: int) -> np.ndarray:
+    """STT/FunASR/FunASRAudio.swift:35-45"""
+    return _window(L.WIN_HAMMING, length)
+
+
+def poveyWindow(size: int) -> np.ndarray:
+    """Codec/S3Gen/CAMPPlus.swift:15-19"""
+    return _window(L.WIN_POVEY, size)
+
+
+def hannWindowPeriodic(size: int) -> np.ndarray:
+    """Codec/S3Gen/HiFiGAN.swift:15-20"""
+    return _window(L.WIN_HANN_PERIODIC, size)
+
+
+cosyVoice3HannWindowPeriodic = hannWindowPeriodic  # CausalHiFTGenerator.swift:429-432
+
+
+def melFilters(sampleRate: int, nFft: int, nMels: int, fMin: float = 0.0, fMax: float | None = None) -> np.ndarray:
+    """Codec/S3Tokenizer/S3TokenizerUtils.swift:301-375 -> (nMels, nFft/2+1)"""
+    out = np.empty((nMels, nFft // 2 + 1), np.float32)
+    rc = L.load().b2a_mel_filters(sampleRate, nFft, nMels, fMin, -1.0 if fMax is None else fMax, _fptr(out))
+    if rc != L.B2A_OK:
+        _raise(rc, "bad filterbank parameters")
+    return out
+
+
+def funASRMelFilters(sampleRate: int = 16000, nFft: int = 400, nMels: int = 80) -> np.ndarray:
+    """STT/FunASR/FunASRAudio.swift:322-396 -> (nMels, nFft/2)"""
+    out = np.empty((nMels, nFft // 2), np.float32)
+    rc = L.load().b2a_funasr_mel_filters(sampleRate, nFft, nMels, _fptr(out))
+    if rc != L.B2A_OK:
+        _raise(rc, "bad filterbank parameters")
+    return out
+
+
+def melFiltersHTK(sampleRate: int, nFft: int, nMels: int, fMin: float, fMax: float) -> np.ndarray:
+    """Codec/S3Gen/CAMPPlus.swift:134-175 -> (nFft/2+1, nMels)"""
+    out = np.empty((nFft // 2 + 1, nMels), np.float32)
+    rc = L.load().b2a_mel_filters_htk(sampleRate, nFft, nMels, fMin, fMax, _fptr(out))
+    if rc != L.B2A_OK:
+        _raise(rc, "bad filterbank parameters")
+    return out
+
+
+def nextPowerOf2(n: int) -> int:
+    """Codec/S3Gen/CAMPPlus.swift:22-29"""
+    return int(L.load().b2a_next_power_of_2(n))
+
+
+def computeFeatureLength(audioLength: int, hopLength: int = 160, lfrN: int = 6) -> int:
+    """STT/FunASR/FunASRAudio.swift:225-235"""
+    return int(L.load().b2a_funasr_compute_feature_length(audioLength, hopLength, lfrN))
+
+
+def reflectPadIndex(i: int, n: int, padding: int) -> int:
+    """Source index of padded position i under reflectPad (S3TokenizerUtils.swift:266-298)."""
+    return int(L.load().b2a_reflect_pad_index(i, n, padding))
+
+
+# ---- front ends ------------------------------------------------------------------------------------
+
+def padOrTrim(array, length: int = 480000, ctx: Context | None = None):
+    """STT/Whisper/WhisperAudio.swift:54-67"""
+    a = _Arr(array)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    out = a.empty((b, length))
+    c.check(c.lib.b2a_pad_or_trim(c.h, a.ptr, b, n, length, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def whisperLogMelSpectrogram(audio, nMels: int, padding: int = 0, ctx: Context | None = None):
+    """STT/Whisper/WhisperAudio.swift:78-137 -> (T', nMels)"""
+    a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_whisper_num_frames(n, padding))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, frames, nMels))
+    c.check(c.lib.b2a_whisper_log_mel_spectrogram(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def logMelSpectrogramChatterbox(audio, nMels: int = 128, padding: int = 0, ctx: Context | None = None):
+    """Codec/S3Tokenizer/S3TokenizerUtils.swift:160-208 -> (nMels, T')"""
+    a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_whisper_num_frames(n, padding))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, nMels, frames))
+    c.check(c.lib.b2a_log_mel_spectrogram_chatterbox(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def logMelSpectrogramCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 128, ctx: Context | None = None):
+    """TTS/CosyVoice2/CosyVoice2TTS.swift:787-795 (thin wrapper over logMelSpectrogramChatterbox)"""
+    return logMelSpectrogramChatterbox(audio, nMels=numMelBins, padding=0, ctx=ctx)
+
+
+def funASRLogMelSpectrogram(audio, nMels: int = 80, nFft: int = 400, hopLength: int = 160, ctx: Context | None = None):
+    """STT/FunASR/FunASRAudio.swift:57-94 -> (T', nMels)"""
+    if (nFft, hopLength) != (400, 160):
+        _raise(L.B2A_E_UNSUPPORTED, "Fun-ASR log-mel is built for nFft 400 / hopLength 160")
+    a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_funasr_num_frames(n))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, frames, nMels))
+    c.check(c.lib.b2a_funasr_log_mel_spectrogram(c.h, a.ptr, b, n, nMels, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def applyLFR(features, lfrM: int = 7, lfrN: int = 6, ctx: Context | None = None):
+    """STT/FunASR/FunASRAudio.swift:108-154 : (T, M) -> (ceil(T/lfrN), lfrM*M)"""
+    a = _Arr(features)
+    if len(a.shape) == 2:
+        b, had = 1, False
+    elif len(a.shape) == 3:
+        b, had = a.shape[0], True
+    else:
+        raise B2AError(L.B2A_E_BAD_ARG, "applyLFR expects (T, M) or (B, T, M)")
+    t, m = a.shape[-2], a.shape[-1]
+    c = _ctx_for(a, ctx)
+    rows = int(c.lib.b2a_lfr_num_rows(t, lfrN))
+    out = a.empty((b, rows, lfrM * m))
+    c.check(c.lib.b2a_apply_lfr(c.h, a.ptr, b, t, m, lfrM, lfrN, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def applyCMVN(features, cmvnMean=None, cmvnIstd=None, ctx: Context | None = None):
+    """STT/FunASR/FunASRAudio.swift:165-180"""
+    a = _Arr(features)
+    if len(a.shape) == 2:
+        b, had = 1, False
+    elif len(a.shape) == 3:
+        b, had = a.shape[0], True
+    else:
+        raise B2AError(L.B2A_E_BAD_ARG, "applyCMVN expects (T, D) or (B, T, D)")
+    t, d = a.shape[-2], a.shape[-1]
+    c = _ctx_for(a, ctx)
+    out = a.empty((b, t, d))
+    pm = pi = None
+    keep = []
+    if cmvnMean is not None or cmvnIstd is not None:
+        if cmvnMean is None or cmvnIstd is None:
+            raise B2AError(L.B2A_E_BAD_ARG, "cmvnMean and cmvnIstd must both be given")
+        if a.space == L.B2A_DEVICE:
+            import torch
+            m_ = torch.as_tensor(cmvnMean, dtype=torch.float32, device=a.t.device).contiguous()
+            i_ = torch.as_tensor(cmvnIstd, dtype=torch.float32, device=a.t.device).contiguous()
+        else:
+            m_ = np.ascontiguousarray(cmvnMean, np.float32)
+            i_ = np.ascontiguousarray(cmvnIstd, np.float32)
+        keep = [m_, i_]
+        pm, pi = _ptr(m_), _ptr(i_)
+    c.check(c.lib.b2a_apply_cmvn(c.h, a.ptr, b, t, d, pm, pi, _ptr(out), a.space))
+    del keep
+    return out if had else out[0]
+
+
+def preprocessAudio(audio, nMels: int = 80, lfrM: int = 7, lfrN: int = 6, applyNormalization: bool = True,
+                    ctx: Context | None = None):
+    """STT/FunASR/FunASRAudio.swift:197-216 -> (ceil(T'/lfrN), nMels*lfrM)"""
+    a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_funasr_num_frames(n))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    rows = int(c.lib.b2a_lfr_num_rows(frames, lfrN))
+    out = a.empty((b, rows, nMels * lfrM))
+    c.check(c.lib.b2a_funasr_preprocess_audio(c.h, a.ptr, b, n, nMels, lfrM, lfrN, int(applyNormalization), _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def kaldiFbankCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 80, frameLength: float = 25.0,
+                       frameShift: float = 10.0, meanNorm: bool = False, ctx: Context | None = None):
+    """Codec/S3Gen/CAMPPlus.swift:32-106 -> (T', numMelBins).  ``meanNorm`` adds the caller-side
+    ``fbank - mean(fbank, axis: 0)`` of CAMPPlus.inference (:797-802)."""
+    a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    win = int(np.float32(sampleRate) * np.float32(frameLength) / np.float32(1000))
+    hop = int(np.float32(sampleRate) * np.float32(frameShift) / np.float32(1000))
+    frames = int(c.lib.b2a_kaldi_num_frames(n, win, hop))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "signal shorter than one analysis window")
+    out = a.empty((b, frames, numMelBins))
+    c.check(c.lib.b2a_kaldi_fbank_campplus(c.h, a.ptr, b, n, sampleRate, numMelBins, frameLength, frameShift, int(meanNorm),
+                                           _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def s3genMelSpectrogram(y, nFft: int = 1920, numMels: int = 80, samplingRate: int = 24000, hopSize: int = 480,
+                        winSize: int = 1920, fmin: int = 0, fmax: int = 8000, center: bool = False,
+                        ctx: Context | None = None):
+    """Codec/S3Gen/Mel/S3GenMel.swift:43-102 : (B, T) or (T,) -> (B, numMels, T') or (numMels, T')"""
+    a = _Arr(y)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_s3gen_num_frames(n, nFft, hopSize))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, numMels, frames))
+    c.check(c.lib.b2a_s3gen_mel_spectrogram(c.h, a.ptr, b, n, nFft, numMels, samplingRate, hopSize, winSize, fmin, fmax,
+                                            _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def voiceEncoderMelspectrogram(wav, config: L.VoiceEncConfig | None = None, pad: bool = True, ctx: Context | None = None):
+    """TTS/Chatterbox/VoiceEncoder/VoiceEncoderMelspec.swift:17-68 -> (numMels, T')"""
+    cfg = config
+    if cfg is None:
+        cfg = L.VoiceEncConfig()
+        L.load().b2a_voice_enc_config_default(C.byref(cfg))
+    a = _Arr(wav)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_stft_num_frames(n, cfg.n_fft, cfg.hop_size, 1))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, cfg.num_mels, frames))
+    c.check(c.lib.b2a_voice_encoder_melspectrogram(c.h, a.ptr, b, n, C.byref(cfg), _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def stft(x, window, nFft: int, hopLength: int, winLength: int | None = None, center: bool = True,
+         padMode: str = "reflect", ctx: Context | None = None):
+    """Codec/S3Tokenizer/S3TokenizerUtils.swift:224-263 -> complex64 (T', nFft/2+1).
+    ``winLength`` and ``padMode`` are ignored, as in the reference (:229,231)."""
+    a = _Arr(x)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    w = np.ascontiguousarray(window, np.float32)
+    frames = int(c.lib.b2a_stft_num_frames(n, nFft, hopLength, int(center)))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, frames, nFft // 2 + 1, 2))
+    c.check(c.lib.b2a_stft(c.h, a.ptr, b, n, _fptr(w), w.shape[0], nFft, hopLength, int(center), _ptr(out), a.space))
+    if a.space == L.B2A_DEVICE:
+        import torch
+        z = torch.view_as_complex(out)
+    else:
+        z = out.view(np.complex64)[..., 0]
+    return z if had else z[0]
+
+
+# ---- vocoder STFT / iSTFT ----------------------------------------------------------------------------
+
+def _small_stft(fn_name, x, nFft, hopLength, window, ctx):
+    a = _Arr(x)
+    if len(a.shape) != 2:
+        raise B2AError(L.B2A_E_BAD_ARG, "expected (B, T)")
+    b, n = a.shape
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_vocoder_stft_num_frames(n, nFft, hopLength))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short")
+    o0 = a.empty((b, nFft // 2 + 1, frames))
+    o1 = a.empty((b, nFft // 2 + 1, frames))
+    w = np.ascontiguousarray(window, np.float32)
+    c.check(getattr(c.lib, fn_name)(c.h, a.ptr, b, n, nFft, hopLength, _fptr(w), _ptr(o0), _ptr(o1), a.space))
+    return o0, o1
+
+
+def stftHiFiGAN(x, nFft: int, hopLength: int, window, ctx: Context | None = None):
+    """Codec/S3Gen/HiFiGAN.swift:257-295 : (B, T) -> (real, imag) each (B, nFft/2+1, frames)"""
+    return _small_stft("b2a_stft_hifigan", x, nFft, hopLength, window, ctx)
+
+
+def cosyVoice3Stft(x, nFft: int, hopLength: int, window, ctx: Context | None = None):
+    """TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:435-460"""
+    return _small_stft("b2a_cosyvoice3_stft", x, nFft, hopLength, window, ctx)
+
+
+def _istft(fn_name, magnitude, phase, nFft, hopLength, window, ctx):
+    m = _Arr(magnitude)
+    p = _Arr(phase)
+    if len(m.shape) != 3 or m.shape != p.shape or m.space != p.space:
+        raise B2AError(L.B2A_E_BAD_ARG, "magnitude and phase must both be (B, F, frames) in the same memory space")
+    b, f, frames = m.shape
+    if f != nFft // 2 + 1:
+        raise B2AError(L.B2A_E_BAD_ARG, f"expected {nFft // 2 + 1} frequency bins, got {f}")
+    c = _ctx_for(m, ctx)
+    if frames < 2:
+        _raise(L.B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames")
+    out = m.empty((b, (frames - 1) * hopLength))
+    w = np.ascontiguousarray(window, np.float32)
+    c.check(getattr(c.lib, fn_name)(c.h, m.ptr, p.ptr, b, frames, nFft, hopLength, _fptr(w), _ptr(out), m.space))
+    return out
+
+
+def istftHiFiGAN(magnitude, phase, nFft: int, hopLength: int, window, ctx: Context | None = None):
+    """Codec/S3Gen/HiFiGAN.swift:298-367 -> (B, (frames-1)*hop)"""
+    return _istft("b2a_istft_hifigan", magnitude, phase, nFft, hopLength, window, ctx)
+
+
+def cosyVoice3Istft(magnitude, phase, nFft: int, hopLength: int, window, ctx: Context | None = None):
+    """TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:463-514"""
+    return _istft("b2a_cosyvoice3_istft", magnitude, phase, nFft, hopLength, window, ctx)
+
+
+class MLXSTFT:
+    """TTS/Kokoro/Decoder/MLXSTFT.swift:165-235 (``transform`` / ``inverse`` / call)."""
+
+    def __init__(self, filterLength: int = 800, hopLength: int = 200, winLength: int = 800, window: str = "hann",
+                 ctx: Context | None = None):
+        if window.lower() != "hann":
+            raise B2AError(L.B2A_E_BAD_ARG, f"Only hanning is supported for window, not {window}")  # MLXSTFT.swift:54
+        self.filterLength, self.hopLength, self.winLength, self.window = filterLength, hopLength, winLength, window
+        self.ctx = ctx
+        self.magnitude = None
+        self.phase = None
+
+    def transform(self, inputData):
+        a = _Arr(inputData)
+        if len(a.shape) == 1:
+            if a.space == L.B2A_DEVICE:
+                a = _Arr(a.t[None])
+            else:
+                a = _Arr(a.t[None])
+        b, n = a.shape
+        c = _ctx_for(a, self.ctx)
+        frames = int(c.lib.b2a_vocoder_stft_num_frames(n, self.filterLength, self.hopLength))
+        if frames <= 0:
+            _raise(L.B2A_E_TOO_SHORT, "Input is too short")
+        f = self.filterLength // 2 + 1
+        mag, ph = a.empty((b, f, frames)), a.empty((b, f, frames))
+        c.check(c.lib.b2a_kokoro_stft_transform(c.h, a.ptr, b, n, self.filterLength, self.hopLength, self.winLength,
+                                                _ptr(mag), _ptr(ph), a.space))
+        return mag, ph
+
+    def inverse(self, magnitude, phase):
+        m, p = _Arr(magnitude), _Arr(phase)
+        if len(m.shape) != 3 or m.shape != p.shape or m.space != p.space:
+            raise B2AError(L.B2A_E_BAD_ARG, "magnitude and phase must both be (B, F, frames)")
+        b, f, frames = m.shape
+        c = _ctx_for(m, self.ctx)
+        if frames < 2:
+            _raise(L.B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames")
+        out = m.empty((b, 1, (frames - 1) * self.hopLength))
+        c.check(c.lib.b2a_kokoro_stft_inverse(c.h, m.ptr, p.ptr, b, frames, self.filterLength, self.hopLength, self.winLength,
+                                              _ptr(out), m.space))
+        return out
+
+    def __call__(self, inputData):
+        mag, ph = self.transform(inputData)
+        self.magnitude, self.phase = mag, ph
+        rec = self.inverse(mag, ph)
+        return rec[..., None, :] if not _is_torch(rec) else rec.unsqueeze(-2)

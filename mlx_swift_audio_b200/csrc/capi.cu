@@ -1,0 +1,786 @@
+// C ABI of the B200 STFT-family DSP path (include/b200audio.h): context, device-table caches,
+// scratch, the overlapped host<->device chunk pipeline for B2A_HOST buffers, and one entry point
+// per reference helper.  There is no CPU fallback anywhere in this file: every compute entry
+// point ends in a CUDA kernel launch or fails with B2A_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200audio.h"
+#include "internal.h"
+
+using namespace b2a;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct BankStorage {
+  SparseBank host;
+  int* start = nullptr;
+  int* count = nullptr;
+  int* offset = nullptr;
+  float* weights = nullptr;
+};
+
+constexpr int kSlots = 3;  // chunk ring depth of the host pipeline
+
+}  // namespace
+
+struct b2a_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_comp[kSlots] = {}, ev_d2h[kSlots] = {};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool timing = false, timed = false;
+  std::string err;
+  int64_t launches = 0;
+  std::mutex mu;
+  std::map<std::string, BankStorage> banks;      // like the reference's MelFilterCache (CAMPPlus.swift:111-131), per context
+  std::map<std::string, std::vector<float>> windows;
+  DevBuf in[kSlots][2], out[kSlots][2];          // host-pipeline staging
+  DevBuf scratch[kSlots][3];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase
+  int* h_flag = nullptr;                         // pinned
+};
+
+namespace {
+
+int fail(b2a_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+int cu(b2a_ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return B2A_OK;
+  return fail(c, B2A_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int ensure(b2a_ctx* c, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return B2A_OK;
+  if (b.p) {
+    cudaError_t e = cudaFree(b.p);  // synchronises the device: no kernel still reads the old buffer
+    b.p = nullptr;
+    b.bytes = 0;
+    if (e != cudaSuccess) return cu(c, e, "cudaFree");
+  }
+  size_t want = std::max<size_t>(bytes, 256);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    b.p = nullptr;
+    return fail(c, e == cudaErrorMemoryAllocation ? B2A_E_NOMEM : B2A_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  b.bytes = want;
+  return B2A_OK;
+}
+
+const std::vector<float>& cached_window(b2a_ctx* c, const std::string& key, const std::function<void(std::vector<float>&)>& make) {
+  auto it = c->windows.find(key);
+  if (it != c->windows.end()) return it->second;
+  std::vector<float> w;
+  make(w);
+  return c->windows.emplace(key, std::move(w)).first->second;
+}
+
+int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool bin_major,
+                const std::function<int(float*)>& make_dense, DeviceBank* out) {
+  auto it = c->banks.find(key);
+  if (it == c->banks.end()) {
+    std::vector<float> dense(size_t(n_mels) * n_bins);
+    int rc = make_dense(dense.data());
+    if (rc != B2A_OK) return fail(c, rc, "bad filterbank parameters");
+    BankStorage bs;
+    build_sparse_bank(dense.data(), n_mels, n_bins, bin_major, bs.host);
+    const size_t nw = std::max<size_t>(bs.host.weights.size(), 1);
+    cudaError_t e;
+    if ((e = cudaMalloc(&bs.start, sizeof(int) * n_mels)) != cudaSuccess) return cu(c, e, "cudaMalloc");
+    if ((e = cudaMalloc(&bs.count, sizeof(int) * n_mels)) != cudaSuccess) return cu(c, e, "cudaMalloc");
+    if ((e = cudaMalloc(&bs.offset, sizeof(int) * n_mels)) != cudaSuccess) return cu(c, e, "cudaMalloc");
+    if ((e = cudaMalloc(&bs.weights, sizeof(float) * nw)) != cudaSuccess) return cu(c, e, "cudaMalloc");
+    // synchronous uploads (once per configuration), ordered before any later launch
+    if ((e = cudaMemcpy(bs.start, bs.host.start.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
+    if ((e = cudaMemcpy(bs.count, bs.host.count.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
+    if ((e = cudaMemcpy(bs.offset, bs.host.offset.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
+    if (!bs.host.weights.empty())
+      if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cu(c, e, "bank upload");
+    it = c->banks.emplace(key, std::move(bs)).first;
+  }
+  const BankStorage& bs = it->second;
+  out->start = bs.start;
+  out->count = bs.count;
+  out->offset = bs.offset;
+  out->weights = bs.weights;
+  out->n_mels = n_mels;
+  out->n_bins_used = bs.host.max_bin + 1;
+  return B2A_OK;
+}
+
+struct Guard {
+  b2a_ctx* c;
+  std::unique_lock<std::mutex> lk;
+  int prev_dev = -1;
+  bool ok = true;
+  explicit Guard(b2a_ctx* ctx) : c(ctx), lk(ctx->mu) {
+    cudaGetDevice(&prev_dev);
+    if (prev_dev != c->device) ok = cudaSetDevice(c->device) == cudaSuccess;
+    c->err.clear();
+  }
+  ~Guard() {
+    if (prev_dev >= 0 && prev_dev != c->device) cudaSetDevice(prev_dev);
+  }
+};
+
+// Runs `body(d_in0, d_in1, d_out0, d_out1, n_clips, slot)` over the batch.
+//  B2A_DEVICE: a single call on the caller's pointers.
+//  B2A_HOST  : clips are streamed through device staging buffers in chunks; H2D of chunk i+1, the
+//              kernels of chunk i and D2H of chunk i-1 overlap on three streams.
+using Body = std::function<int(const float*, const float*, float*, float*, int64_t, int)>;
+
+int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t in0_per_clip, const float* in1,
+                size_t in1_per_clip, float* out0, size_t out0_per_clip, float* out1, size_t out1_per_clip, const Body& body) {
+  if (space == B2A_DEVICE) {
+    if (c->timing) cudaEventRecord(c->ev_t0, c->stream);
+    int rc = body(in0, in1, out0, out1, batch, 0);
+    if (c->timing) {
+      cudaEventRecord(c->ev_t1, c->stream);
+      c->timed = true;
+    }
+    return rc;
+  }
+  if (space != B2A_HOST) return fail(c, B2A_E_BAD_ARG, "space must be B2A_HOST or B2A_DEVICE");
+  const size_t per_clip = sizeof(float) * (in0_per_clip + in1_per_clip + out0_per_clip + out1_per_clip);
+  const size_t target = size_t(192) << 20;  // bytes per chunk (inputs + outputs)
+  int64_t chunk = std::max<int64_t>(1, int64_t(target / std::max<size_t>(per_clip, 1)));
+  chunk = std::min(chunk, batch);
+  const int64_t n_chunks = (batch + chunk - 1) / chunk;
+  const int slots = int(std::min<int64_t>(kSlots, n_chunks));
+  for (int s = 0; s < slots; ++s) {
+    int rc;
+    if ((rc = ensure(c, c->in[s][0], sizeof(float) * in0_per_clip * chunk)) != B2A_OK) return rc;
+    if (in1 && (rc = ensure(c, c->in[s][1], sizeof(float) * in1_per_clip * chunk)) != B2A_OK) return rc;
+    if ((rc = ensure(c, c->out[s][0], sizeof(float) * out0_per_clip * chunk)) != B2A_OK) return rc;
+    if (out1 && (rc = ensure(c, c->out[s][1], sizeof(float) * out1_per_clip * chunk)) != B2A_OK) return rc;
+  }
+  cudaError_t e;
+  // order the copy streams after whatever is already queued on the compute stream
+  if ((e = cudaEventRecord(c->ev_comp[0], c->stream)) != cudaSuccess) return cu(c, e, "event record");
+  if ((e = cudaStreamWaitEvent(c->s_h2d, c->ev_comp[0], 0)) != cudaSuccess) return cu(c, e, "stream wait");
+  for (int64_t i = 0; i < n_chunks; ++i) {
+    const int s = int(i % kSlots);
+    const int64_t c0 = i * chunk, n = std::min(chunk, batch - c0);
+    if (i >= kSlots) {  // slot reuse: its previous D2H must have drained
+      if ((e = cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
+    }
+    if ((e = cudaMemcpyAsync(c->in[s][0].p, in0 + c0 * in0_per_clip, sizeof(float) * in0_per_clip * n, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+      return cu(c, e, "H2D copy");
+    if (in1 && (e = cudaMemcpyAsync(c->in[s][1].p, in1 + c0 * in1_per_clip, sizeof(float) * in1_per_clip * n, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+      return cu(c, e, "H2D copy");
+    if ((e = cudaEventRecord(c->ev_h2d[s], c->s_h2d)) != cudaSuccess) return cu(c, e, "event record");
+    if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
+    int rc = body(static_cast<const float*>(c->in[s][0].p), static_cast<const float*>(c->in[s][1].p),
+                  static_cast<float*>(c->out[s][0].p), static_cast<float*>(c->out[s][1].p), n, s);
+    if (rc != B2A_OK) {
+      cudaStreamSynchronize(c->s_h2d);
+      cudaStreamSynchronize(c->stream);
+      cudaStreamSynchronize(c->s_d2h);
+      return rc;
+    }
+    if ((e = cudaEventRecord(c->ev_comp[s], c->stream)) != cudaSuccess) return cu(c, e, "event record");
+    if ((e = cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
+    if ((e = cudaMemcpyAsync(out0 + c0 * out0_per_clip, c->out[s][0].p, sizeof(float) * out0_per_clip * n, cudaMemcpyDeviceToHost, c->s_d2h)) != cudaSuccess)
+      return cu(c, e, "D2H copy");
+    if (out1 && (e = cudaMemcpyAsync(out1 + c0 * out1_per_clip, c->out[s][1].p, sizeof(float) * out1_per_clip * n, cudaMemcpyDeviceToHost, c->s_d2h)) != cudaSuccess)
+      return cu(c, e, "D2H copy");
+    if ((e = cudaEventRecord(c->ev_d2h[s], c->s_d2h)) != cudaSuccess) return cu(c, e, "event record");
+  }
+  if ((e = cudaStreamSynchronize(c->s_d2h)) != cudaSuccess) return cu(c, e, "sync");
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return cu(c, e, "sync");
+  return B2A_OK;
+}
+
+int check_common(b2a_ctx* c, const void* in, const void* out, int64_t batch, int64_t n) {
+  if (!c) return B2A_E_BAD_ARG;
+  if (!in || !out) return fail(c, B2A_E_BAD_ARG, "null buffer");
+  if (batch <= 0 || n <= 0) return fail(c, B2A_E_BAD_ARG, "batch and sizes must be positive");
+  return B2A_OK;
+}
+
+// One preset of the fused front-end.
+struct Preset {
+  int n_fft = 400, hop = 160, win_len = 400;
+  const std::vector<float>* window = nullptr;  // zero-extended to n_fft
+  int pad_mode = PAD_REFLECT;
+  int64_t pad_left = 200;
+  int64_t zero_tail = 0;
+  int pre_mode = PRE_NONE;
+  int spec_mode = SPEC_POWER;
+  DeviceBank bank;
+  int log_mode = LOG_NONE;
+  float log_floor = 0.0f;
+  int whisper_norm = 0;
+  int post_affine = 0;
+  float post_sub = 0.0f, post_div = 1.0f;
+  int out_mode = OUT_TM;
+  int64_t n_frames = 0;
+  int lfr_m = 7, lfr_n = 6;
+  int64_t lfr_rows = 0;
+  int post_cmvn = 0;       // Fun-ASR per-utterance CMVN on the LFR features
+  int post_mean_norm = 0;  // CAM++ time-mean removal
+};
+
+int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, int64_t n_samples, float* out, int space) {
+  size_t out_per_clip;
+  switch (p.out_mode) {
+    case OUT_LFR: out_per_clip = size_t(p.lfr_rows) * p.lfr_m * p.bank.n_mels; break;
+    case OUT_COMPLEX: out_per_clip = size_t(p.n_frames) * (p.n_fft / 2 + 1) * 2; break;
+    default: out_per_clip = size_t(p.n_frames) * p.bank.n_mels; break;
+  }
+  const int tiles = frontend_tiles_per_clip(p.n_fft, p.n_frames);
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int slot) -> int {
+    FrontendArgs a;
+    a.n_fft = p.n_fft; a.hop = p.hop; a.win_len = p.win_len;
+    a.x = d_in; a.batch = n; a.n_samples = n_samples; a.zero_tail = p.zero_tail;
+    a.pad_mode = p.pad_mode; a.pad_left = p.pad_left; a.pre_mode = p.pre_mode;
+    a.window = p.window->data();
+    a.spec_mode = p.spec_mode; a.bank = p.bank; a.log_mode = p.log_mode; a.log_floor = p.log_floor;
+    a.whisper_norm = p.whisper_norm; a.post_affine = p.post_affine; a.post_sub = p.post_sub; a.post_div = p.post_div;
+    a.out_mode = p.out_mode; a.n_frames = p.n_frames; a.out = d_out; a.lfr_m = p.lfr_m; a.lfr_n = p.lfr_n; a.lfr_rows = p.lfr_rows;
+    if (p.whisper_norm) {
+      int rc;
+      if ((rc = ensure(c, c->scratch[slot][0], sizeof(int) * size_t(n))) != B2A_OK) return rc;
+      if ((rc = ensure(c, c->scratch[slot][1], sizeof(float) * size_t(n) * tiles)) != B2A_OK) return rc;
+      a.clip_max = static_cast<int*>(c->scratch[slot][0].p);
+      a.tile_min = static_cast<float*>(c->scratch[slot][1].p);
+    }
+    int launches = 0;
+    std::string err;
+    int rc = launch_frontend(a, c->stream, &launches, &err);
+    if (rc == B2A_OK && p.post_cmvn)
+      rc = launch_cmvn(d_out, d_out, n, p.lfr_rows, p.lfr_m * p.bank.n_mels, nullptr, nullptr, c->stream, &launches, &err);
+    if (rc == B2A_OK && p.post_mean_norm) rc = launch_mean_norm(d_out, n, p.n_frames, p.bank.n_mels, c->stream, &launches, &err);
+    c->launches += launches;
+    if (rc != B2A_OK) c->err = err;
+    return rc;
+  };
+  return run_batched(c, space, batch, audio, size_t(n_samples), nullptr, 0, out, out_per_clip, nullptr, 0, body);
+}
+
+std::string key_of(const char* tag, std::initializer_list<double> v) {
+  std::string k = tag;
+  for (double d : v) {
+    k += '_';
+    k += std::to_string(d);
+  }
+  return k;
+}
+
+int slaney_bank(b2a_ctx* c, int sr, int n_fft, int n_mels, float fmin, float fmax, DeviceBank* out) {
+  if (n_mels <= 0) return fail(c, B2A_E_BAD_ARG, "n_mels must be positive");
+  return cached_bank(c, key_of("slaney", {double(sr), double(n_fft), double(n_mels), fmin, fmax}), n_mels, n_fft / 2 + 1, false,
+                     [&](float* d) { return mel_filters_slaney(sr, n_fft, n_mels, fmin, fmax, d); }, out);
+}
+
+const std::vector<float>& window_of(b2a_ctx* c, int kind, int length, int n_fft, bool via_plus_one) {
+  return cached_window(c, key_of("win", {double(kind), double(length), double(n_fft), double(via_plus_one)}), [&](std::vector<float>& w) {
+    if (via_plus_one) hann_periodic_via_hanning(length, w);
+    else {
+      w.resize(length);
+      make_window(kind, length, w.data());
+    }
+    w.resize(n_fft, 0.0f);  // zero-extend (S3TokenizerUtils.swift:235-239)
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- context ------------------------------------------------------------------------------------
+static int ctx_create(b2a_ctx** out, int device, void* stream, bool own) {
+  if (!out) return B2A_E_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return B2A_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2A_E_CUDA;
+  if (prop.major != 10) return B2A_E_CUDA;  // kernels are built for sm_100a only
+  int prev = 0;
+  cudaGetDevice(&prev);
+  if (cudaSetDevice(device) != cudaSuccess) return B2A_E_CUDA;
+  b2a_ctx* c = new b2a_ctx();
+  c->device = device;
+  int rc = B2A_OK;
+  do {
+    if (own) {
+      if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = B2A_E_CUDA; break; }
+      c->own_stream = true;
+    } else {
+      c->stream = static_cast<cudaStream_t>(stream);
+    }
+    if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) { rc = B2A_E_CUDA; break; }
+    if (cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { rc = B2A_E_CUDA; break; }
+    for (int s = 0; s < kSlots && rc == B2A_OK; ++s) {
+      if (cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming) != cudaSuccess) rc = B2A_E_CUDA;
+      if (cudaEventCreateWithFlags(&c->ev_comp[s], cudaEventDisableTiming) != cudaSuccess) rc = B2A_E_CUDA;
+      if (cudaEventCreateWithFlags(&c->ev_d2h[s], cudaEventDisableTiming) != cudaSuccess) rc = B2A_E_CUDA;
+    }
+    if (rc != B2A_OK) break;
+    if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) { rc = B2A_E_CUDA; break; }
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_flag), sizeof(int), cudaHostAllocDefault) != cudaSuccess) { rc = B2A_E_CUDA; break; }
+    std::string err;
+    rc = init_frontend_tables(&err);
+  } while (false);
+  cudaSetDevice(prev);
+  if (rc != B2A_OK) {
+    b2a_ctx_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return B2A_OK;
+}
+
+int b2a_ctx_create(b2a_ctx** ctx, int device) { return ctx_create(ctx, device, nullptr, true); }
+int b2a_ctx_create_on_stream(b2a_ctx** ctx, int device, void* cuda_stream) { return ctx_create(ctx, device, cuda_stream, false); }
+
+int b2a_ctx_destroy(b2a_ctx* c) {
+  if (!c) return B2A_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int s = 0; s < kSlots; ++s) {
+    for (int j = 0; j < 2; ++j) {
+      if (c->in[s][j].p) cudaFree(c->in[s][j].p);
+      if (c->out[s][j].p) cudaFree(c->out[s][j].p);
+    }
+    for (int j = 0; j < 3; ++j)
+      if (c->scratch[s][j].p) cudaFree(c->scratch[s][j].p);
+    if (c->ev_h2d[s]) cudaEventDestroy(c->ev_h2d[s]);
+    if (c->ev_comp[s]) cudaEventDestroy(c->ev_comp[s]);
+    if (c->ev_d2h[s]) cudaEventDestroy(c->ev_d2h[s]);
+  }
+  for (auto& kv : c->banks) {
+    cudaFree(kv.second.start);
+    cudaFree(kv.second.count);
+    cudaFree(kv.second.offset);
+    cudaFree(kv.second.weights);
+  }
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  cudaSetDevice(prev);
+  delete c;
+  return B2A_OK;
+}
+
+int b2a_ctx_sync(b2a_ctx* c) {
+  if (!c) return B2A_E_BAD_ARG;
+  return cu(c, cudaStreamSynchronize(c->stream), "sync");
+}
+
+const char* b2a_last_error(const b2a_ctx* c) { return c ? c->err.c_str() : "null context"; }
+int64_t b2a_ctx_launch_count(const b2a_ctx* c) { return c ? c->launches : 0; }
+
+int b2a_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return B2A_E_BAD_ARG;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? B2A_OK : B2A_E_NOMEM;
+}
+int b2a_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? B2A_OK : B2A_E_CUDA; }
+
+int b2a_ctx_enable_timing(b2a_ctx* c, int on) {
+  if (!c) return B2A_E_BAD_ARG;
+  c->timing = on != 0;
+  c->timed = false;
+  return B2A_OK;
+}
+
+int b2a_ctx_last_kernel_ms(b2a_ctx* c, float* ms) {
+  if (!c || !ms) return B2A_E_BAD_ARG;
+  if (!c->timed) return fail(c, B2A_E_BAD_ARG, "no timed B2A_DEVICE call yet");
+  cudaError_t e = cudaEventSynchronize(c->ev_t1);
+  if (e != cudaSuccess) return cu(c, e, "event sync");
+  return cu(c, cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1), "elapsed");
+}
+
+// ---- front ends -----------------------------------------------------------------------------------
+int b2a_pad_or_trim(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int64_t length, float* out, int space) {
+  int rc = check_common(c, x, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (length <= 0) return fail(c, B2A_E_BAD_ARG, "length must be positive");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r = launch_pad_or_trim(d_in, d_out, n, n_samples, length, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(length), nullptr, 0, body);
+}
+
+static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding, float* out,
+                        int space, bool chatterbox) {
+  int rc = check_common(c, audio, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (padding < 0) return fail(c, B2A_E_BAD_ARG, "padding must be >= 0");
+  const int64_t frames = b2a_whisper_num_frames(n_samples, padding);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Preset p;
+  // Whisper: symmetric Hann (WhisperAudio.swift:89); S3Tokenizer/Chatterbox: hanningWindow(401)[0..<400] (S3TokenizerUtils.swift:172)
+  p.window = chatterbox ? &window_of(c, B2A_WIN_HANNING, 400, 400, true) : &window_of(c, B2A_WIN_WHISPER_HANN, 400, 400, false);
+  p.zero_tail = padding;
+  // Whisper passes fMax 8000 explicitly (WhisperAudio.swift:113-119); Chatterbox leaves it nil = sr/2 (S3TokenizerUtils.swift:190-194)
+  if ((rc = slaney_bank(c, 16000, 400, n_mels, 0.0f, chatterbox ? -1.0f : 8000.0f, &p.bank)) != B2A_OK) return rc;
+  p.log_mode = LOG_LOG10;
+  p.log_floor = 1e-10f;
+  p.whisper_norm = 1;
+  p.out_mode = chatterbox ? OUT_MT : OUT_TM;
+  p.n_frames = frames;  // the last STFT frame is dropped (WhisperAudio.swift:105, S3TokenizerUtils.swift:184)
+  return run_preset(c, p, audio, batch, n_samples, out, space);
+}
+
+int b2a_whisper_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
+                                    float* out, int space) {
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, false);
+}
+
+int b2a_log_mel_spectrogram_chatterbox(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
+                                       float* out, int space) {
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, true);
+}
+
+static int funasr_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
+                         int lfr, int norm, float* out, int space) {
+  int rc = check_common(c, audio, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (n_mels <= 0) return fail(c, B2A_E_BAD_ARG, "n_mels must be positive");
+  if (lfr && (lfr_m <= 0 || lfr_n <= 0)) return fail(c, B2A_E_BAD_ARG, "lfr_m and lfr_n must be positive");
+  const int64_t frames = b2a_funasr_num_frames(n_samples);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Preset p;
+  p.window = &window_of(c, B2A_WIN_HAMMING, 400, 400, false);
+  if ((rc = cached_bank(c, key_of("funasr", {16000.0, 400.0, double(n_mels)}), n_mels, 200, false,
+                        [&](float* d) { return mel_filters_funasr(16000, 400, n_mels, d); }, &p.bank)) != B2A_OK)
+    return rc;
+  p.log_mode = LOG_LN;
+  p.log_floor = 1e-10f;
+  p.n_frames = frames;
+  if (lfr) {
+    p.out_mode = OUT_LFR;
+    p.lfr_m = lfr_m;
+    p.lfr_n = lfr_n;
+    p.lfr_rows = b2a_lfr_num_rows(frames, lfr_n);
+    p.post_cmvn = norm;
+  }
+  return run_preset(c, p, audio, batch, n_samples, out, space);
+}
+
+int b2a_funasr_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, float* out, int space) {
+  return funasr_common(c, audio, batch, n_samples, n_mels, 0, 0, 0, 0, out, space);
+}
+
+int b2a_funasr_preprocess_audio(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
+                                int apply_normalization, float* out, int space) {
+  return funasr_common(c, audio, batch, n_samples, n_mels, lfr_m, lfr_n, 1, apply_normalization != 0, out, space);
+}
+
+int b2a_apply_lfr(b2a_ctx* c, const float* features, int64_t batch, int64_t n_frames, int n_mels, int lfr_m, int lfr_n, float* out,
+                  int space) {
+  int rc = check_common(c, features, out, batch, n_frames);
+  if (rc != B2A_OK) return rc;
+  if (n_mels <= 0 || lfr_m <= 0 || lfr_n <= 0) return fail(c, B2A_E_BAD_ARG, "n_mels, lfr_m, lfr_n must be positive");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  const int64_t rows = b2a_lfr_num_rows(n_frames, lfr_n);
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r = launch_lfr(d_in, d_out, n, n_frames, n_mels, lfr_m, lfr_n, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, batch, features, size_t(n_frames) * n_mels, nullptr, 0, out, size_t(rows) * lfr_m * n_mels, nullptr, 0, body);
+}
+
+int b2a_apply_cmvn(b2a_ctx* c, const float* features, int64_t batch, int64_t n_rows, int dim, const float* cmvn_mean,
+                   const float* cmvn_istd, float* out, int space) {
+  int rc = check_common(c, features, out, batch, n_rows);
+  if (rc != B2A_OK) return rc;
+  if (dim <= 0) return fail(c, B2A_E_BAD_ARG, "dim must be positive");
+  if ((cmvn_mean == nullptr) != (cmvn_istd == nullptr)) return fail(c, B2A_E_BAD_ARG, "cmvn_mean and cmvn_istd must both be given or both be NULL");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  const float* d_mean = nullptr;
+  const float* d_istd = nullptr;
+  if (cmvn_mean) {
+    // statistics always come from the host side of the boundary (model config); upload per call
+    if ((rc = ensure(c, c->scratch[0][2], sizeof(float) * 2 * size_t(dim))) != B2A_OK) return rc;
+    float* d = static_cast<float*>(c->scratch[0][2].p);
+    cudaError_t e;
+    if (space == B2A_DEVICE) {
+      if ((e = cudaMemcpyAsync(d, cmvn_mean, sizeof(float) * dim, cudaMemcpyDeviceToDevice, c->stream)) != cudaSuccess) return cu(c, e, "copy");
+      if ((e = cudaMemcpyAsync(d + dim, cmvn_istd, sizeof(float) * dim, cudaMemcpyDeviceToDevice, c->stream)) != cudaSuccess) return cu(c, e, "copy");
+    } else {
+      if ((e = cudaMemcpy(d, cmvn_mean, sizeof(float) * dim, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "copy");
+      if ((e = cudaMemcpy(d + dim, cmvn_istd, sizeof(float) * dim, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "copy");
+    }
+    d_mean = d;
+    d_istd = d + dim;
+  }
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r = launch_cmvn(d_in, d_out, n, n_rows, dim, d_mean, d_istd, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, batch, features, size_t(n_rows) * dim, nullptr, 0, out, size_t(n_rows) * dim, nullptr, 0, body);
+}
+
+int b2a_kaldi_fbank_campplus(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
+                             float frame_length_ms, float frame_shift_ms, int mean_norm, float* out, int space) {
+  int rc = check_common(c, audio, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (sample_rate <= 0 || num_mel_bins <= 0) return fail(c, B2A_E_BAD_ARG, "sample_rate and num_mel_bins must be positive");
+  const int win_length = int(float(sample_rate) * frame_length_ms / 1000.0f);  // CAMPPlus.swift:40-42
+  const int hop = int(float(sample_rate) * frame_shift_ms / 1000.0f);
+  const int n_fft = b2a_next_power_of_2(win_length);
+  if (!frontend_plan_exists(n_fft, hop, win_length)) return fail(c, B2A_E_UNSUPPORTED, "Kaldi fbank is built for 25 ms / 10 ms at 16 kHz (win 400, hop 160, n_fft 512)");
+  const int64_t frames = b2a_kaldi_num_frames(n_samples, win_length, hop);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "signal shorter than one analysis window");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Preset p;
+  p.n_fft = n_fft; p.hop = hop; p.win_len = win_length;
+  p.window = &window_of(c, B2A_WIN_POVEY, win_length, n_fft, false);
+  p.pad_mode = PAD_NONE;
+  p.pad_left = 0;
+  p.pre_mode = PRE_KALDI;
+  if ((rc = cached_bank(c, key_of("htkint", {double(sample_rate), double(n_fft), double(num_mel_bins), 20.0, double(sample_rate) / 2}),
+                        num_mel_bins, n_fft / 2 + 1, true,
+                        [&](float* d) { return mel_filters_htk_int(sample_rate, n_fft, num_mel_bins, 20.0f, float(sample_rate) / 2, d); },
+                        &p.bank)) != B2A_OK)
+    return rc;
+  p.log_mode = LOG_LN;
+  p.log_floor = 1.1920929e-07f;
+  p.n_frames = frames;
+  p.post_mean_norm = mean_norm != 0;
+  return run_preset(c, p, audio, batch, n_samples, out, space);
+}
+
+int b2a_s3gen_mel_spectrogram(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
+                              int hop_size, int win_size, int fmin, int fmax, float* out, int space) {
+  int rc = check_common(c, y, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (win_size > n_fft || win_size <= 0) return fail(c, B2A_E_BAD_ARG, "win_size must be in (0, n_fft]");
+  if (!frontend_plan_exists(n_fft, hop_size, n_fft)) return fail(c, B2A_E_UNSUPPORTED, "s3gen mel is built for n_fft 1920 / hop 480 (and 400 / 160)");
+  const int64_t frames = b2a_s3gen_num_frames(n_samples, n_fft, hop_size);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Preset p;
+  p.n_fft = n_fft; p.hop = hop_size; p.win_len = n_fft;
+  p.window = &window_of(c, B2A_WIN_HANNING, win_size, n_fft, true);
+  p.pad_mode = PAD_REFLECT;
+  const int64_t pad = (n_fft - hop_size) / 2;
+  p.pad_left = std::min<int64_t>(pad, n_samples - 1);  // reflectPad2D truncates, no loop (S3GenMel.swift:17-25)
+  p.spec_mode = SPEC_MAGNITUDE;
+  if ((rc = slaney_bank(c, sampling_rate, n_fft, num_mels, float(fmin), float(fmax), &p.bank)) != B2A_OK) return rc;
+  p.log_mode = LOG_LN;
+  p.log_floor = 1e-5f;
+  p.out_mode = OUT_MT;
+  p.n_frames = frames;
+  return run_preset(c, p, y, batch, n_samples, out, space);
+}
+
+int b2a_voice_encoder_melspectrogram(b2a_ctx* c, const float* wav, int64_t batch, int64_t n_samples, const b2a_voice_enc_config* cfg_in,
+                                     float* out, int space) {
+  int rc = check_common(c, wav, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  b2a_voice_enc_config cfg;
+  if (cfg_in) cfg = *cfg_in;
+  else b2a_voice_enc_config_default(&cfg);
+  if (cfg.win_size > cfg.n_fft || cfg.win_size <= 0) return fail(c, B2A_E_BAD_ARG, "win_size must be in (0, n_fft]");
+  if (!frontend_plan_exists(cfg.n_fft, cfg.hop_size, cfg.n_fft)) return fail(c, B2A_E_UNSUPPORTED, "voice-encoder mel is built for n_fft 400 / hop 160");
+  if (cfg.mel_power != 1.0f && cfg.mel_power != 2.0f) return fail(c, B2A_E_UNSUPPORTED, "mel_power 1.0 and 2.0 are built");
+  const int64_t frames = b2a_stft_num_frames(n_samples, cfg.n_fft, cfg.hop_size, 1);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Preset p;
+  p.n_fft = cfg.n_fft; p.hop = cfg.hop_size; p.win_len = cfg.n_fft;
+  p.window = &window_of(c, B2A_WIN_HANNING, cfg.win_size, cfg.n_fft, true);
+  p.pad_left = cfg.n_fft / 2;
+  p.spec_mode = cfg.mel_power == 2.0f ? SPEC_POWER : SPEC_MAGNITUDE;
+  if ((rc = slaney_bank(c, cfg.sample_rate, cfg.n_fft, cfg.num_mels, float(cfg.fmin), float(cfg.fmax), &p.bank)) != B2A_OK) return rc;
+  if (cfg.mel_type_db) {
+    p.log_mode = LOG_DB20;
+    p.log_floor = cfg.stft_magnitude_min;
+  }
+  if (cfg.normalized_mels) {  // VoiceEncoderMelspec.swift:61-65
+    const float min_level_db = 20.0f * log10f(cfg.stft_magnitude_min);
+    p.post_affine = 1;
+    p.post_sub = min_level_db;
+    p.post_div = -min_level_db + 15.0f;
+  }
+  p.out_mode = OUT_MT;
+  p.n_frames = frames;
+  return run_preset(c, p, wav, batch, n_samples, out, space);
+}
+
+int b2a_stft(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, const float* window, int win_len, int n_fft, int hop,
+             int center, float* out_complex, int space) {
+  int rc = check_common(c, x, out_complex, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (!window || win_len <= 0 || win_len > n_fft) return fail(c, B2A_E_BAD_ARG, "window must have 1..n_fft taps");
+  int plan_win = n_fft;
+  if (!frontend_plan_exists(n_fft, hop, plan_win)) {
+    plan_win = 400;
+    if (!(n_fft == 512 && win_len <= 400 && frontend_plan_exists(n_fft, hop, plan_win)))
+      return fail(c, B2A_E_UNSUPPORTED, "stft is built for (n_fft, hop) = (400, 160), (1920, 480), and (512, 160) with <= 400 taps");
+  }
+  const int64_t frames = b2a_stft_num_frames(n_samples, n_fft, hop, center);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  std::vector<float> w(window, window + win_len);
+  w.resize(n_fft, 0.0f);
+  Preset p;
+  p.n_fft = n_fft; p.hop = hop; p.win_len = plan_win;
+  p.window = &w;
+  p.pad_mode = center ? PAD_REFLECT : PAD_NONE;
+  p.pad_left = center ? n_fft / 2 : 0;
+  p.out_mode = OUT_COMPLEX;
+  p.n_frames = frames;
+  return run_preset(c, p, x, batch, n_samples, out_complex, space);
+}
+
+// ---- vocoder --------------------------------------------------------------------------------------
+static int small_stft_common(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int n_fft, int hop, const float* window,
+                             int pad_mode, int out_kind, float* o0, float* o1, int space) {
+  int rc = check_common(c, x, o0, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (!o1 || !window) return fail(c, B2A_E_BAD_ARG, "null buffer");
+  const int64_t frames = b2a_vocoder_stft_num_frames(n_samples, n_fft, hop);
+  if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  const size_t per = size_t(n_fft / 2 + 1) * frames;
+  Body body = [&](const float* d_in, const float*, float* d0, float* d1, int64_t n, int) -> int {
+    SmallStftArgs a;
+    a.n_fft = n_fft; a.hop = hop; a.x = d_in; a.batch = n; a.n_samples = n_samples; a.n_frames = frames;
+    a.pad_mode = pad_mode; a.window = window; a.out_kind = out_kind; a.out0 = d0; a.out1 = d1;
+    int launches = 0;
+    std::string err;
+    int r = launch_small_stft(a, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, o0, per, o1, per, body);
+}
+
+int b2a_stft_hifigan(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int n_fft, int hop, const float* window,
+                     float* real_out, float* imag_out, int space) {
+  return small_stft_common(c, x, batch, n_samples, n_fft, hop, window, PAD_REFLECT, SOUT_REAL_IMAG, real_out, imag_out, space);
+}
+
+int b2a_cosyvoice3_stft(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int n_fft, int hop, const float* window,
+                        float* real_out, float* imag_out, int space) {
+  if (c && n_samples > 0 && n_samples <= n_fft / 2) {
+    // zero padding has no minimum length beyond one frame (CausalHiFTGenerator.swift:438-440)
+    if (n_samples + 2 * (n_fft / 2) < n_fft) return fail(c, B2A_E_TOO_SHORT, "Input is too short");
+  }
+  return small_stft_common(c, x, batch, n_samples, n_fft, hop, window, PAD_ZERO, SOUT_REAL_IMAG, real_out, imag_out, space);
+}
+
+int b2a_kokoro_stft_transform(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int filter_length, int hop_length,
+                              int win_length, float* magnitude_out, float* phase_out, int space) {
+  if (!c) return B2A_E_BAD_ARG;
+  if (win_length <= 0 || win_length > filter_length) return fail(c, B2A_E_BAD_ARG, "win_length must be in (0, filter_length]");
+  std::vector<float> w;
+  hann_periodic_via_hanning(win_length, w);  // getWindow "hann" (MLXSTFT.swift:48-67)
+  w.resize(filter_length, 0.0f);
+  return small_stft_common(c, x, batch, n_samples, filter_length, hop_length, w.data(), PAD_REFLECT, SOUT_MAG_PHASE, magnitude_out,
+                           phase_out, space);
+}
+
+static int istft_common(b2a_ctx* c, const float* mag, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,
+                        const float* window, int use_clip_lo, float clip_hi, int norm, int unwrap, float* out, int space) {
+  int rc = check_common(c, mag, out, batch, n_frames);
+  if (rc != B2A_OK) return rc;
+  if (!phase || !window) return fail(c, B2A_E_BAD_ARG, "null buffer");
+  if (n_frames < 2) return fail(c, B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  const size_t per_in = size_t(n_fft / 2 + 1) * n_frames;
+  const size_t per_out = size_t(n_frames - 1) * hop;
+  Body body = [&](const float* d_mag, const float* d_phase, float* d_out, float*, int64_t n, int slot) -> int {
+    IstftArgs a;
+    a.n_fft = n_fft; a.hop = hop; a.mag = d_mag; a.phase = d_phase; a.batch = n; a.n_frames = n_frames; a.window = window;
+    a.use_clip_lo = use_clip_lo; a.clip_lo = 0.0f; a.clip_hi = clip_hi; a.norm = norm; a.out = d_out;
+    if (unwrap) {
+      int r;
+      if ((r = ensure(c, c->scratch[slot][0], sizeof(int))) != B2A_OK) return r;
+      if ((r = ensure(c, c->scratch[slot][2], sizeof(float) * per_in * size_t(n))) != B2A_OK) return r;
+      a.unwrap = 2;
+      a.d_flag = static_cast<int*>(c->scratch[slot][0].p);
+      a.h_flag = c->h_flag;
+      a.scratch_phase = static_cast<float*>(c->scratch[slot][2].p);
+    }
+    int launches = 0;
+    std::string err;
+    int r = launch_istft(a, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, batch, mag, per_in, phase, per_in, out, per_out, nullptr, 0, body);
+}
+
+int b2a_istft_hifigan(b2a_ctx* c, const float* magnitude, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,
+                      const float* window, float* out, int space) {
+  // clip(magnitude, max: 1e2) only (HiFiGAN.swift:300)
+  return istft_common(c, magnitude, phase, batch, n_frames, n_fft, hop, window, 0, 100.0f, NORM_WSQ_FLOOR, 0, out, space);
+}
+
+int b2a_cosyvoice3_istft(b2a_ctx* c, const float* magnitude, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,
+                         const float* window, float* out, int space) {
+  // clip(magnitude, min: 0, max: 1e2) (CausalHiFTGenerator.swift:464)
+  return istft_common(c, magnitude, phase, batch, n_frames, n_fft, hop, window, 1, 100.0f, NORM_WSQ_FLOOR, 0, out, space);
+}
+
+int b2a_kokoro_stft_inverse(b2a_ctx* c, const float* magnitude, const float* phase, int64_t batch, int64_t n_frames, int filter_length,
+                            int hop_length, int win_length, float* out, int space) {
+  if (!c) return B2A_E_BAD_ARG;
+  if (win_length != filter_length) return fail(c, B2A_E_UNSUPPORTED, "Kokoro inverse is built for win_length == filter_length");
+  std::vector<float> w;
+  hann_periodic_via_hanning(win_length, w);
+  // no magnitude clip; plain window-sum normalisation with != 0 guard; unwrap first (MLXSTFT.swift:143-155,215)
+  return istft_common(c, magnitude, phase, batch, n_frames, filter_length, hop_length, w.data(), 0, 3.402823466e+38f, NORM_WSUM_NONZERO, 1,
+                      out, space);
+}
+
+}  // extern "C"

@@ -1,0 +1,625 @@
+// Fused STFT -> |X|^2 / |X| -> sparse mel projection -> log / clamp / normalise for sm_100a.
+//
+// One kernel replaces the reference's chain of ~10 lazily evaluated MLX ops
+// (reflectPad -> asStrided -> * window -> rfft -> abs -> pow -> matmul -> log10 -> max -> scale;
+// Codec/S3Tokenizer/S3TokenizerUtils.swift:224-263, STT/Whisper/WhisperAudio.swift:78-137 and the
+// other front ends listed in include/b200audio.h).  Nothing here is derived from MLX source.
+//
+// Design (see DESIGN.md "frontend kernel"):
+//   * a CTA owns a tile of FT = 32 consecutive frames of one clip; LANE == FRAME in every stage, so
+//     twiddles / window values / filter weights are warp-uniform operands and every shared-memory
+//     access is stride-1 across lanes (conflict-free by construction);
+//   * PCM for the tile is loaded once from HBM with coalesced float4 loads into shared memory
+//     (row pitch HOP+1 so that the stride-HOP frame starts fall in distinct banks) -- the 2.5x
+//     (or 4x) frame overlap is served from shared memory, never from HBM;
+//   * real FFT of size N = N1*N2 as two register-resident stages of generated straight-line
+//     codelets (tools/gen_codelets.py): stage A = N2 real DFTs of size N1 (+ inter-stage twiddle),
+//     one shared-memory exchange, stage B = N1/2+1 DFTs of size N2 (complex / real / odd-real);
+//     warps split the items of each stage;
+//   * mel projection is sparse (each triangular filter is a short contiguous run of bins), fused
+//     with log/floor/scale; output tile is staged and written with coalesced stores;
+//   * the per-clip max-8 clamp of Whisper / S3Tokenizer needs a clip-global maximum: the main
+//     kernel writes normalised values, tracks per-clip max and per-tile min, and a second tiny
+//     kernel rewrites only tiles whose minimum is below the clamp threshold.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200audio.h"
+#include "codelets.h"
+#include "internal.h"
+
+namespace b2a {
+
+// ------------------------------------------------------------------------------------------------
+// codelet dispatch by array size
+// ------------------------------------------------------------------------------------------------
+#define B2A_DEV __device__ __forceinline__
+B2A_DEV void rdft(const float (&x)[16], float (&yr)[9], float (&yi)[9]) { b2a_rdft16(x, yr, yi); }
+B2A_DEV void rdft(const float (&x)[25], float (&yr)[13], float (&yi)[13]) { b2a_rdft25(x, yr, yi); }
+B2A_DEV void rdft(const float (&x)[32], float (&yr)[17], float (&yi)[17]) { b2a_rdft32(x, yr, yi); }
+B2A_DEV void rdft(const float (&x)[60], float (&yr)[31], float (&yi)[31]) { b2a_rdft60(x, yr, yi); }
+B2A_DEV void rdftodd(const float (&x)[25], float (&yr)[13], float (&yi)[13]) { b2a_rdftodd25(x, yr, yi); }
+B2A_DEV void rdftodd(const float (&x)[32], float (&yr)[16], float (&yi)[16]) { b2a_rdftodd32(x, yr, yi); }
+B2A_DEV void cdft(const float (&xr)[25], const float (&xi)[25], float (&yr)[25], float (&yi)[25]) { b2a_cdft25(xr, xi, yr, yi); }
+B2A_DEV void cdft(const float (&xr)[32], const float (&xi)[32], float (&yr)[32], float (&yi)[32]) { b2a_cdft32(xr, xi, yr, yi); }
+
+// inter-stage twiddles W_N^{n2*k1}, k1 = 1..N1/2-1, as (cos, -sin); filled once per device
+__constant__ float2 c_tw400[25 * 7];
+__constant__ float2 c_tw512[32 * 7];
+__constant__ float2 c_tw1920[32 * 29];
+
+template <int N_, int WIN_, int N1_, int N2_, int HOP_, int FT_, int NWARPS_, int MINB_>
+struct Plan {
+  static constexpr int N = N_, WIN = WIN_, N1 = N1_, N2 = N2_, HOP = HOP_, FT = FT_, NWARPS = NWARPS_, MINB = MINB_;
+  static constexpr int H1 = N1 / 2;
+  static constexpr int NBINS = N / 2 + 1;
+  static constexpr int NTHREADS = NWARPS * 32;
+  static constexpr int TS = (FT - 1) * HOP + WIN;  // samples per tile
+  static constexpr int PITCH = HOP + 1;            // skewed row pitch
+  static constexpr int PCM_WORDS = ((TS - 1) + (TS - 1) / HOP + 1 + 3) & ~3;
+  static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT
+  static constexpr int P_PITCH = FT + 1;
+  static constexpr int P_WORDS_REAL = NBINS * FT;
+  static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
+  static constexpr int R0_WORDS_REAL = PCM_WORDS > P_WORDS_REAL ? PCM_WORDS : P_WORDS_REAL;
+  static constexpr int R0_WORDS_CPLX = PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX;
+  static_assert(N1 * N2 == N, "N = N1*N2");
+  static_assert(HOP % 4 == 0 && TS % 4 == 0, "float4 staging");
+  static_assert(FT == 32, "lane == frame");
+};
+using Plan400 = Plan<400, 400, 16, 25, 160, 32, 9, 2>;
+using Plan512 = Plan<512, 400, 16, 32, 160, 32, 9, 2>;
+
+template <class P> struct TwTable;
+template <> struct TwTable<Plan400> { static B2A_DEV const float2* get() { return c_tw400; } };
+template <> struct TwTable<Plan512> { static B2A_DEV const float2* get() { return c_tw512; } };
+
+struct WinTabEntry {
+  float w;   // window value at sample offset o
+  int off;   // skewed shared-memory word offset of sample o relative to the lane's frame start
+};
+
+template <class P>
+struct FrontendParams {
+  const float* x;
+  long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, lfr_rows;
+  int pad_mode, pre_mode, spec_mode, log_mode, whisper_norm, post_affine, out_mode, tiles_per_clip, lfr_m, lfr_n;
+  float log_floor, post_sub, post_div;
+  const int* fb_start;
+  const int* fb_count;
+  const int* fb_offset;
+  const float* fb_w;
+  int n_mels, n_bins_used;
+  float* out;
+  int* clip_max;
+  float* tile_min;
+  WinTabEntry tab[P::WIN];
+};
+
+B2A_DEV int enc_ordered(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+B2A_DEV float dec_ordered(int e) { return __int_as_float(e >= 0 ? e : e ^ 0x7fffffff); }
+
+// value of padded coordinate p of one clip (generic / edge path)
+B2A_DEV float fetch_padded(const float* __restrict__ xc, long long p, long long pad_left, long long n_samples,
+                           long long n_eff, int pad_mode) {
+  long long j = p - pad_left;
+  if (j < 0 || j >= n_eff) {
+    if (pad_mode != PAD_REFLECT) return 0.0f;
+    if (n_eff == 1) j = 0;
+    else if (j < 0) j = ((-j - 1) % (n_eff - 1)) + 1;
+    else j = n_eff - 2 - ((j - n_eff) % (n_eff - 1));
+  }
+  return j < n_samples ? __ldg(xc + j) : 0.0f;
+}
+
+template <class P>
+__global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
+  constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
+  extern __shared__ __align__(16) float smem[];
+  const bool cplx = prm.out_mode == OUT_COMPLEX;
+  float* s_r0 = smem;                                       // PCM tile, later the spectrum tile
+  float2* s_y = reinterpret_cast<float2*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL));
+  float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
+  __shared__ int s_tile_min;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x % prm.tiles_per_clip;
+  const long long clip = blockIdx.x / prm.tiles_per_clip;
+  const long long f0 = (long long)tile * FT;
+  const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
+  if (tid == 0) s_tile_min = 0x7fffffff;
+
+  // ---- 1. stage the tile's PCM (coalesced, skewed rows) -----------------------------------------
+  {
+    const long long p0 = f0 * HOP;
+    const long long j0 = p0 - prm.pad_left;
+    const bool interior = j0 >= 0 && j0 + P::TS <= prm.n_samples && ((reinterpret_cast<uintptr_t>(xc + j0) & 15) == 0);
+    if (interior) {
+      const float4* __restrict__ src = reinterpret_cast<const float4*>(xc + j0);
+      for (int s4 = tid; s4 < P::TS / 4; s4 += P::NTHREADS) {
+        const float4 v = __ldg(src + s4);
+        const int s = s4 * 4;
+        float* d = s_r0 + s + s / HOP;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    } else {
+      for (int s = tid; s < P::TS; s += P::NTHREADS)
+        s_r0[s + s / HOP] = fetch_padded(xc, p0 + s, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode);
+    }
+  }
+  __syncthreads();
+
+  // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
+  float mu = 0.0f;
+  if (prm.pre_mode == PRE_KALDI) {
+    float part = 0.0f;
+    for (int o = warp; o < WIN; o += NW) part += s_r0[lane * P::PITCH + prm.tab[o].off];
+    s_o[warp * FT + lane] = part;
+    __syncthreads();
+    float tot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) tot += s_o[w * FT + lane];
+    mu = tot / float(WIN);
+    __syncthreads();
+  }
+
+  // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
+  {
+    const float* lane_pcm = s_r0 + lane * P::PITCH;
+    const float2* __restrict__ tw = TwTable<P>::get();
+    for (int n2 = warp; n2 < N2; n2 += NW) {
+      float in[N1];
+#pragma unroll
+      for (int n1 = 0; n1 < N1; ++n1) {
+        const int o = N2 * n1 + n2;
+        if (N2 * n1 < WIN && o < WIN) {
+          const WinTabEntry e = prm.tab[o];
+          float v = lane_pcm[e.off];
+          if (prm.pre_mode == PRE_KALDI) {
+            // (x[o]-mu) - 0.97*(x[o-1]-mu), first sample only DC-removed (CAMPPlus.swift:66-72)
+            v = v - mu;
+            if (o > 0) v = v - 0.97f * (lane_pcm[prm.tab[o - 1].off] - mu);
+          }
+          in[n1] = v * e.w;
+        } else {
+          in[n1] = 0.0f;
+        }
+      }
+      float yr[H1 + 1], yi[H1 + 1];
+      rdft(in, yr, yi);
+      float2* yb = s_y + n2 * FT + lane;
+      yb[0] = make_float2(yr[0], yr[H1]);
+#pragma unroll
+      for (int k1 = 1; k1 < H1; ++k1) {
+        const float2 t = tw[n2 * (H1 - 1) + (k1 - 1)];
+        yb[k1 * N2 * FT] = make_float2(yr[k1] * t.x - yi[k1] * t.y, yr[k1] * t.y + yi[k1] * t.x);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
+  {
+    const int spec_mode = prm.spec_mode;
+    auto put = [&](int k, float re, float im) {
+      if (cplx) {
+        reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + lane] = make_float2(re, im);
+      } else {
+        const float pw = re * re + im * im;
+        s_r0[k * FT + lane] = spec_mode == SPEC_POWER ? pw : sqrtf(pw);
+      }
+    };
+    for (int it = warp; it <= H1; it += NW) {
+      if (it == 0) {
+        float in[N2];
+#pragma unroll
+        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + lane].x;
+        float ur[N2 / 2 + 1], ui[N2 / 2 + 1];
+        rdft(in, ur, ui);
+#pragma unroll
+        for (int k2 = 0; k2 <= N2 / 2; ++k2) put(N1 * k2, ur[k2], ui[k2]);
+      } else if (it == H1) {
+        float in[N2];
+#pragma unroll
+        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + lane].y;
+        float ur[(N2 - 1) / 2 + 1], ui[(N2 - 1) / 2 + 1];
+        rdftodd(in, ur, ui);
+#pragma unroll
+        for (int k2 = 0; k2 <= (N2 - 1) / 2; ++k2) put(H1 + N1 * k2, ur[k2], ui[k2]);
+      } else {
+        float xr[N2], xi[N2], ur[N2], ui[N2];
+        const float2* yb = s_y + it * N2 * FT + lane;
+#pragma unroll
+        for (int n2 = 0; n2 < N2; ++n2) {
+          const float2 v = yb[n2 * FT];
+          xr[n2] = v.x;
+          xi[n2] = v.y;
+        }
+        cdft(xr, xi, ur, ui);
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) {
+          const int kc = N1 * k2;  // k = it + kc
+          if (kc + H1 <= N / 2) put(it + kc, ur[k2], ui[k2]);       // it < H1  =>  it + kc <= N/2
+          else put(N - kc - it, ur[k2], -ui[k2]);                    // conjugate mirror
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const bool frame_ok = f0 + lane < prm.n_frames;
+
+  // ---- 4a. plain stft(): write the complex spectrum tile ------------------------------------------
+  if (cplx) {
+    const int nb = P::NBINS;
+    float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride) + f0 * nb;
+    const long long rows = prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT;
+    const float2* sp = reinterpret_cast<const float2*>(s_r0);
+    for (int e = tid; e < rows * nb; e += P::NTHREADS) {
+      const int r = e / nb, k = e - r * nb;
+      dst[e] = sp[k * P::P_PITCH + r];
+    }
+    return;
+  }
+
+  // ---- 4b. sparse mel projection + log / floor / scale ---------------------------------------------
+  const int M = prm.n_mels;
+  const int opitch = M + 1;
+  float lmax = -3.0e38f, vmin = 3.0e38f;
+  {
+    const int* __restrict__ fst = prm.fb_start;
+    const int* __restrict__ fcn = prm.fb_count;
+    const int* __restrict__ fof = prm.fb_offset;
+    const float* __restrict__ fw = prm.fb_w;
+    float* __restrict__ out_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
+    for (int m = warp; m < M; m += NW) {
+      const int st = __ldg(fst + m), cn = __ldg(fcn + m);
+      const float* __restrict__ w = fw + __ldg(fof + m);
+      const float* pp = s_r0 + st * FT + lane;
+      float acc = 0.0f;
+      for (int i = 0; i < cn; ++i) acc = fmaf(__ldg(w + i), pp[i * FT], acc);
+      float v = acc;
+      if (prm.log_mode == LOG_LOG10) v = log10f(fmaxf(v, prm.log_floor));
+      else if (prm.log_mode == LOG_LN) v = logf(fmaxf(v, prm.log_floor));
+      else if (prm.log_mode == LOG_DB20) v = 20.0f * log10f(fmaxf(v, prm.log_floor));
+      if (prm.whisper_norm) {
+        if (frame_ok) lmax = fmaxf(lmax, v);
+        v = (v + 4.0f) / 4.0f;
+        if (frame_ok) vmin = fminf(vmin, v);
+      }
+      if (prm.post_affine) v = (v - prm.post_sub) / prm.post_div;
+      if (prm.out_mode == OUT_MT) {
+        if (frame_ok) out_mt[(long long)m * prm.n_frames] = v;
+      } else {
+        s_o[lane * opitch + m] = v;
+      }
+    }
+  }
+  if (prm.whisper_norm) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+    }
+    if (lane == 0) {
+      atomicMax(prm.clip_max + clip, enc_ordered(lmax));
+      atomicMin(&s_tile_min, enc_ordered(vmin));
+    }
+  }
+  if (prm.out_mode == OUT_MT && !prm.whisper_norm) return;
+  __syncthreads();
+  if (prm.whisper_norm && tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
+  if (prm.out_mode == OUT_MT) return;
+
+  // ---- 5. coalesced store of the staged (frames x M) tile -------------------------------------------
+  const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
+  if (prm.out_mode == OUT_TM) {
+    float* __restrict__ dst = prm.out + clip * prm.out_clip_stride + f0 * M;
+    if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const int m4 = M >> 2;
+      for (int e = tid; e < rows * m4; e += P::NTHREADS) {
+        const int r = e / m4, c = (e - r * m4) * 4;
+        const float* s = s_o + r * opitch + c;
+        reinterpret_cast<float4*>(dst)[e] = make_float4(s[0], s[1], s[2], s[3]);
+      }
+    } else {
+      for (int e = tid; e < rows * M; e += P::NTHREADS) {
+        const int r = e / M, c = e - r * M;
+        dst[e] = s_o[r * opitch + c];
+      }
+    }
+  } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
+    const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
+    const long long T = prm.n_frames;
+    long long i_lo = (f0 + left - (lm - 1)) / ln;
+    if (f0 + left - (lm - 1) < 0) i_lo = 0;
+    long long i_hi = (f0 + rows - 1 + left) / ln;
+    if (f0 + rows >= T) i_hi = prm.lfr_rows - 1;
+    if (i_hi > prm.lfr_rows - 1) i_hi = prm.lfr_rows - 1;
+    const int nseg = int(i_hi - i_lo + 1) * lm;
+    float* __restrict__ dst = prm.out + clip * prm.out_clip_stride;
+    for (int sg = warp; sg < nseg; sg += NW) {
+      const long long i = i_lo + sg / lm;
+      const int j = sg % lm;
+      long long t = i * ln + j - left;
+      t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+      if (t < f0 || t >= f0 + rows) continue;
+      const float* s = s_o + int(t - f0) * opitch;
+      float* d = dst + (i * lm + j) * (long long)M;
+      for (int c = lane; c < M; c += 32) d[c] = s[c];
+    }
+  }
+}
+
+// Rewrites only the tiles whose minimum lies below the clip's clamp threshold:
+//   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, ((Lmax - 8) + 4) / 4)   (x -> (x+4)/4 is monotone in fp32)
+// WhisperAudio.swift:130-134, S3TokenizerUtils.swift:203-205.
+__global__ void whisper_clamp_kernel(float* out, const int* clip_max, const float* tile_min, int tiles_per_clip,
+                                     long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
+  const long long clip = blockIdx.x;
+  const float lm = dec_ordered(clip_max[clip]);
+  const float thr = ((lm - 8.0f) + 4.0f) / 4.0f;
+  float* o = out + clip * out_clip_stride;
+  for (int t = 0; t < tiles_per_clip; ++t) {
+    if (!(tile_min[clip * tiles_per_clip + t] < thr)) continue;
+    const long long f0 = (long long)t * ft;
+    const int rows = int(n_frames - f0 < ft ? n_frames - f0 : ft);
+    if (out_mode == OUT_TM) {
+      float* d = o + f0 * n_mels;
+      for (int e = threadIdx.x; e < rows * n_mels; e += blockDim.x) d[e] = fmaxf(d[e], thr);
+    } else {  // OUT_MT
+      for (int e = threadIdx.x; e < rows * n_mels; e += blockDim.x) {
+        const int m = e / rows, r = e - m * rows;
+        float* d = o + (long long)m * n_frames + f0 + r;
+        *d = fmaxf(*d, thr);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-clip column statistics: CMVN (FunASRAudio.swift:165-180) and time-mean removal (CAMPPlus.swift:800)
+// block = 32 columns x 8 row groups; grid = (column chunks, batch)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows,
+                                                      int dim, const float* __restrict__ gmean, const float* __restrict__ gistd,
+                                                      int do_var) {
+  __shared__ float s_red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long clip = blockIdx.y;
+  const float* src = in + clip * rows * dim;
+  float* dst = out + clip * rows * dim;
+  const bool ok = col < dim;
+  if (gmean != nullptr) {  // (x + mean) * istd with precomputed statistics
+    if (ok) {
+      const float a = gmean[col], b = gistd[col];
+      for (long long r = ry; r < rows; r += 8) dst[r * dim + col] = (src[r * dim + col] + a) * b;
+    }
+    return;
+  }
+  float s = 0.0f;
+  if (ok) for (long long r = ry; r < rows; r += 8) s += src[r * dim + col];
+  s_red[ry][cx] = s;
+  __syncthreads();
+  float mean = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += s_red[i][cx];
+  mean = mean / float(rows);
+  __syncthreads();
+  float denom = 1.0f;
+  if (do_var) {
+    float q = 0.0f;
+    if (ok) for (long long r = ry; r < rows; r += 8) { const float d = src[r * dim + col] - mean; q = fmaf(d, d, q); }
+    s_red[ry][cx] = q;
+    __syncthreads();
+    float var = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) var += s_red[i][cx];
+    var = var / float(rows);
+    denom = sqrtf(var) + 1e-6f;
+  }
+  if (ok) {
+    if (do_var) for (long long r = ry; r < rows; r += 8) dst[r * dim + col] = (src[r * dim + col] - mean) / denom;
+    else for (long long r = ry; r < rows; r += 8) dst[r * dim + col] = src[r * dim + col] - mean;
+  }
+}
+
+// standalone applyLFR (FunASRAudio.swift:108-154): one warp per (row, slot) segment
+__global__ void lfr_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_frames, int n_mels, int lfr_m,
+                           int lfr_n, long long lfr_rows) {
+  const long long clip = blockIdx.y;
+  const int left = (lfr_m - 1) / 2;
+  const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (seg >= lfr_rows * lfr_m) return;
+  const long long i = seg / lfr_m;
+  const int j = int(seg - i * lfr_m);
+  long long t = i * lfr_n + j - left;
+  t = t < 0 ? 0 : (t > n_frames - 1 ? n_frames - 1 : t);
+  const float* s = in + (clip * n_frames + t) * n_mels;
+  float* d = out + (clip * lfr_rows * lfr_m + seg) * n_mels;
+  for (int c = threadIdx.x & 31; c < n_mels; c += 32) d[c] = s[c];
+}
+
+// padOrTrim (WhisperAudio.swift:54-67)
+__global__ void pad_or_trim_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, long long length) {
+  const long long clip = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < length) out[clip * length + i] = i < n ? in[clip * n + i] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int cuda_fail(cudaError_t e, const char* what, std::string* err) {
+  if (err) *err = std::string(what) + ": " + cudaGetErrorString(e);
+  return B2A_E_CUDA;
+}
+
+static void fill_tw(std::vector<float2>& v, int N, int N1, int N2) {
+  const int H1 = N1 / 2;
+  v.resize(size_t(N2) * (H1 - 1));
+  for (int n2 = 0; n2 < N2; ++n2)
+    for (int k1 = 1; k1 < H1; ++k1) {
+      const double a = -2.0 * M_PI * double((long long)n2 * k1 % N) / double(N);
+      v[size_t(n2) * (H1 - 1) + (k1 - 1)] = make_float2(float(cos(a)), float(sin(a)));
+    }
+}
+
+int init_frontend_tables(std::string* err) {
+  std::vector<float2> t;
+  cudaError_t e;
+  fill_tw(t, 400, 16, 25);
+  if ((e = cudaMemcpyToSymbol(c_tw400, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
+  fill_tw(t, 512, 16, 32);
+  if ((e = cudaMemcpyToSymbol(c_tw512, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
+  fill_tw(t, 1920, 60, 32);
+  if ((e = cudaMemcpyToSymbol(c_tw1920, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
+  return B2A_OK;
+}
+
+bool frontend_plan_exists(int n_fft, int hop, int win_len) {
+  return (n_fft == 400 && hop == 160 && win_len == 400) || (n_fft == 512 && hop == 160 && win_len == 400);
+}
+
+int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
+  (void)n_fft;
+  return int((n_frames + 31) / 32);
+}
+
+template <class P>
+static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
+  static FrontendParams<P> prm;  // large (window table); filled per call under the context's lock
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  prm.x = a.x;
+  prm.clip_stride = a.n_samples;
+  prm.n_samples = a.n_samples;
+  prm.n_eff = a.n_samples + a.zero_tail;
+  prm.pad_left = a.pad_left;
+  prm.n_frames = a.n_frames;
+  prm.pad_mode = a.pad_mode;
+  prm.pre_mode = a.pre_mode;
+  prm.spec_mode = a.spec_mode;
+  prm.log_mode = a.log_mode;
+  prm.whisper_norm = a.whisper_norm;
+  prm.post_affine = a.post_affine;
+  prm.post_sub = a.post_sub;
+  prm.post_div = a.post_div;
+  prm.out_mode = a.out_mode;
+  prm.log_floor = a.log_floor;
+  prm.lfr_m = a.lfr_m;
+  prm.lfr_n = a.lfr_n;
+  prm.lfr_rows = a.lfr_rows;
+  prm.fb_start = a.bank.start;
+  prm.fb_count = a.bank.count;
+  prm.fb_offset = a.bank.offset;
+  prm.fb_w = a.bank.weights;
+  prm.n_mels = a.bank.n_mels;
+  prm.n_bins_used = a.bank.n_bins_used;
+  prm.out = a.out;
+  prm.clip_max = a.clip_max;
+  prm.tile_min = a.tile_min;
+  prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
+  switch (a.out_mode) {
+    case OUT_TM: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
+    case OUT_MT: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
+    case OUT_LFR: prm.out_clip_stride = a.lfr_rows * (long long)a.lfr_m * a.bank.n_mels; break;
+    default: prm.out_clip_stride = a.n_frames * (long long)P::NBINS * 2; break;
+  }
+  for (int o = 0; o < P::WIN; ++o) {
+    prm.tab[o].w = a.window[o];
+    prm.tab[o].off = o + o / P::HOP;
+  }
+  if (a.out_mode != OUT_COMPLEX) {
+    if (a.bank.n_mels <= 0 || a.bank.n_mels + 1 > P::N) {
+      if (err) *err = "n_mels out of range for this plan";
+      return B2A_E_BAD_ARG;
+    }
+  }
+  const size_t smem = sizeof(float) * size_t((a.out_mode == OUT_COMPLEX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(sizeof(float) * size_t(P::R0_WORDS_CPLX + P::Y_WORDS)));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
+    attr_set = true;
+  }
+  const long long nblocks = (long long)prm.tiles_per_clip * a.batch;
+  if (nblocks <= 0 || nblocks > 0x7fffffffLL) {
+    if (err) *err = "grid too large";
+    return B2A_E_BAD_ARG;
+  }
+  cudaError_t e;
+  if (a.whisper_norm) {
+    if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+  }
+  frontend_kernel<P><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
+  *launches += 1;
+  if (a.whisper_norm) {
+    whisper_clamp_kernel<<<unsigned(a.batch), 256, 0, st>>>(a.out, a.clip_max, a.tile_min, prm.tiles_per_clip, a.n_frames,
+                                                             a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
+    *launches += 1;
+  }
+  return B2A_OK;
+}
+
+int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400) return launch_plan<Plan400>(a, st, launches, err);
+  if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) return launch_plan<Plan512>(a, st, launches, err);
+  if (err) *err = "no FFT plan built for this (n_fft, hop, win_length)";
+  return B2A_E_UNSUPPORTED;
+}
+
+int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
+                void* stream, int* launches, std::string* err) {
+  dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));
+  colstat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, dim, mean, istd, 1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "colstat_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err) {
+  dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));
+  colstat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(inout, inout, rows, dim, nullptr, nullptr, 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "colstat_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+int launch_lfr(const float* in, float* out, int64_t batch, int64_t n_frames, int n_mels, int lfr_m, int lfr_n, void* stream,
+               int* launches, std::string* err) {
+  const long long rows = (n_frames + lfr_n - 1) / lfr_n;
+  const long long segs = rows * lfr_m;
+  dim3 grid(unsigned((segs + 7) / 8), unsigned(batch));
+  lfr_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n_frames, n_mels, lfr_m, lfr_n, rows);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "lfr_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream, int* launches,
+                       std::string* err) {
+  dim3 grid(unsigned((length + 255) / 256), unsigned(batch));
+  pad_or_trim_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, length);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pad_or_trim_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+}  // namespace b2a

@@ -1,0 +1,291 @@
+// Host-side tables and integer rules of the STFT-family DSP path: window generators,
+// mel filterbanks, reflect-pad index map, frame-count rules.  Pure C++ (no CUDA), so the
+// CPU test-suite can check every one of them against the oracle through the C ABI.
+//
+// Each function restates (does not copy) the fp32 scalar arithmetic of the reference
+// helper it names; paths are relative to the reference's package/ directory.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "../../include/b200audio.h"
+#include "internal.h"
+
+namespace b2a {
+
+static const float kPi = 3.14159265358979323846f;  // Swift Float.pi rounds to the same fp32 value
+
+// ---- windows -----------------------------------------------------------------------------
+int make_window(int kind, int length, float* out) {
+  if (length <= 0 || out == nullptr) return B2A_E_BAD_ARG;
+  if (length == 1 && kind != B2A_WIN_POVEY && kind != B2A_WIN_HANN_PERIODIC) {
+    out[0] = 1.0f;  // the `length == 1` early return of WhisperAudio.swift:33, S3TokenizerUtils.swift:214, FunASRAudio.swift:36
+    return B2A_OK;
+  }
+  switch (kind) {
+    case B2A_WIN_WHISPER_HANN: {  // STT/Whisper/WhisperAudio.swift:32-44
+      const float factor = 2.0f * kPi / float(length - 1);
+      for (int n = 0; n < length; ++n) out[n] = 0.5f * (1.0f - cosf(float(n) * factor));
+      return B2A_OK;
+    }
+    case B2A_WIN_HANNING: {  // Codec/S3Tokenizer/S3TokenizerUtils.swift:213-221, TTS/Kokoro/Decoder/MLXSTFT.swift:12-20
+      const float factor = kPi / float(length - 1);
+      for (int i = 0; i < length; ++i) {
+        const float n = float(1 - length) + 2.0f * float(i);
+        out[i] = 0.5f + 0.5f * cosf(n * factor);
+      }
+      return B2A_OK;
+    }
+    case B2A_WIN_HAMMING: {  // STT/FunASR/FunASRAudio.swift:35-45
+      const float factor = 2.0f * kPi / float(length - 1);
+      for (int n = 0; n < length; ++n) out[n] = 0.54f - 0.46f * cosf(float(n) * factor);
+      return B2A_OK;
+    }
+    case B2A_WIN_POVEY: {  // Codec/S3Gen/CAMPPlus.swift:15-19
+      for (int n = 0; n < length; ++n) {
+        const float hann = 0.5f - 0.5f * cosf(2.0f * kPi * float(n) / float(length - 1));
+        out[n] = powf(hann, 0.85f);
+      }
+      return B2A_OK;
+    }
+    case B2A_WIN_HANN_PERIODIC: {  // Codec/S3Gen/HiFiGAN.swift:15-20, CosyVoice3 CausalHiFTGenerator.swift:429-432
+      for (int n = 0; n < length; ++n) out[n] = 0.5f * (1.0f - cosf(2.0f * kPi * float(n) / float(length)));
+      return B2A_OK;
+    }
+    default:
+      return B2A_E_BAD_ARG;
+  }
+}
+
+// hanningWindow(length: n + 1)[0 ..< n]  (S3TokenizerUtils.swift:172, S3GenMel.swift:66, MLXSTFT.swift:52)
+void hann_periodic_via_hanning(int n, std::vector<float>& w) {
+  std::vector<float> full(n + 1);
+  make_window(B2A_WIN_HANNING, n + 1, full.data());
+  w.assign(full.begin(), full.begin() + n);
+}
+
+// ---- Slaney filterbank: S3TokenizerUtils.swift:301-375 -------------------------------------
+int mel_filters_slaney(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out) {
+  if (sample_rate <= 0 || n_fft <= 0 || n_mels <= 0 || out == nullptr) return B2A_E_BAD_ARG;
+  const float actual_fmax = f_max >= 0.0f ? f_max : float(sample_rate) / 2.0f;
+  const float f_sp = 200.0f / 3.0f;
+  const float min_log_hz = 1000.0f;
+  const float min_log_mel = min_log_hz / f_sp;
+  const float logstep = logf(6.4f) / 27.0f;
+  auto hz_to_mel = [&](float hz) { return hz >= min_log_hz ? min_log_mel + logf(hz / min_log_hz) / logstep : hz / f_sp; };
+  auto mel_to_hz = [&](float mel) { return mel >= min_log_mel ? min_log_hz * expf(logstep * (mel - min_log_mel)) : f_sp * mel; };
+  const float mel_min = hz_to_mel(f_min), mel_max = hz_to_mel(actual_fmax);
+  std::vector<float> pts(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i) pts[i] = mel_to_hz(mel_min + float(i) * (mel_max - mel_min) / float(n_mels + 1));
+  const int nb = n_fft / 2 + 1;
+  std::vector<float> freqs(nb);
+  for (int i = 0; i < nb; ++i) freqs[i] = float(i) * float(sample_rate) / float(n_fft);
+  for (int m = 0; m < n_mels; ++m) {
+    const float fl = pts[m], fc = pts[m + 1], fr = pts[m + 2];
+    const float enorm = 2.0f / (pts[m + 2] - pts[m]);
+    for (int k = 0; k < nb; ++k) {
+      const float f = freqs[k];
+      float v = 0.0f;
+      if (f >= fl && f <= fc) v = (f - fl) / (fc - fl);
+      else if (f > fc && f <= fr) v = (fr - f) / (fr - fc);
+      out[size_t(m) * nb + k] = v * enorm;
+    }
+  }
+  return B2A_OK;
+}
+
+// ---- Fun-ASR HTK filterbank on the 200-point linspace grid: FunASRAudio.swift:322-396 -------
+static void linspace_f32(float a, float b, int num, std::vector<float>& v) {
+  // MLX linspace evaluates (1 - t) * start + t * stop with t = arange(num) / (num - 1) in fp32
+  v.resize(num);
+  for (int i = 0; i < num; ++i) {
+    const float t = float(i) / float(num - 1);
+    v[i] = (1.0f - t) * a + t * b;
+  }
+}
+
+int mel_filters_funasr(int sample_rate, int n_fft, int n_mels, float* out) {
+  if (sample_rate <= 0 || n_fft < 4 || n_mels <= 0 || out == nullptr) return B2A_E_BAD_ARG;
+  const int n_freqs = n_fft / 2;
+  std::vector<float> all_freqs, m_pts;
+  linspace_f32(0.0f, float(sample_rate) / 2.0f, n_freqs, all_freqs);
+  const float m_min = 2595.0f * log10f(1.0f + 0.0f / 700.0f);
+  const float m_max = 2595.0f * log10f(1.0f + (float(sample_rate) / 2.0f) / 700.0f);
+  linspace_f32(m_min, m_max, n_mels + 2, m_pts);
+  std::vector<float> f_pts(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i) f_pts[i] = 700.0f * (powf(10.0f, m_pts[i] / 2595.0f) - 1.0f);
+  for (int m = 0; m < n_mels; ++m) {
+    const float enorm = 2.0f / (f_pts[m + 2] - f_pts[m]);
+    const float d0 = f_pts[m + 1] - f_pts[m], d1 = f_pts[m + 2] - f_pts[m + 1];
+    for (int k = 0; k < n_freqs; ++k) {
+      const float down = -(f_pts[m] - all_freqs[k]) / d0;   // rising edge
+      const float up = (f_pts[m + 2] - all_freqs[k]) / d1;  // falling edge
+      out[size_t(m) * n_freqs + k] = fmaxf(0.0f, fminf(down, up)) * enorm;
+    }
+  }
+  return B2A_OK;
+}
+
+// ---- integer-bin HTK triangles: CAMPPlus.swift:134-175 ---------------------------------------
+int mel_filters_htk_int(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out) {
+  if (sample_rate <= 0 || n_fft <= 0 || n_mels <= 0 || out == nullptr) return B2A_E_BAD_ARG;
+  auto hz_to_mel = [](float hz) { return 2595.0f * log10f(1.0f + hz / 700.0f); };
+  auto mel_to_hz = [](float mel) { return 700.0f * (powf(10.0f, mel / 2595.0f) - 1.0f); };
+  const float mel_min = hz_to_mel(f_min), mel_max = hz_to_mel(f_max);
+  std::vector<long> bins(n_mels + 2);
+  for (int i = 0; i < n_mels + 2; ++i) {
+    const float mel = mel_min + float(i) * (mel_max - mel_min) / float(n_mels + 1);
+    bins[i] = lroundf(mel_to_hz(mel) * float(n_fft) / float(sample_rate));  // Swift round(): half away from zero
+  }
+  const int nb = n_fft / 2 + 1;
+  for (size_t i = 0; i < size_t(nb) * n_mels; ++i) out[i] = 0.0f;
+  for (int m = 1; m <= n_mels; ++m) {
+    const long lo = bins[m - 1], ce = bins[m], hi = bins[m + 1];
+    for (long k = lo; k < ce; ++k)
+      if (k >= 0 && k < nb && ce != lo) out[size_t(k) * n_mels + (m - 1)] = float(k - lo) / float(ce - lo);
+    for (long k = ce; k < hi; ++k)
+      if (k >= 0 && k < nb && hi != ce) out[size_t(k) * n_mels + (m - 1)] = float(hi - k) / float(hi - ce);
+  }
+  return B2A_OK;
+}
+
+// ---- reflect index map: S3TokenizerUtils.swift:266-298 == FunASRAudio.swift:280-310 -----------
+// The while-loops there prepend / append chunks x[1..a] reversed, so walking outwards from the
+// signal edge the source index cycles 1, 2, ..., n-1, 1, 2, ... (left) and n-2, ..., 0, n-2, ... (right).
+int64_t reflect_pad_index(int64_t i, int64_t n, int64_t pad) {
+  const int64_t j = i - pad;  // position relative to the signal
+  if (j >= 0 && j < n) return j;
+  if (n == 1) return 0;
+  if (j < 0) return ((-j - 1) % (n - 1)) + 1;
+  return n - 2 - ((j - n) % (n - 1));
+}
+
+// ---- sparse filterbank: each filter = contiguous run of bins with non-zero weight ----------
+// bank is (n_mels, n_bins) row-major when !bin_major, else (n_bins, n_mels).
+void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major, SparseBank& sb) {
+  sb.n_mels = n_mels;
+  sb.n_bins = n_bins;
+  sb.start.assign(n_mels, 0);
+  sb.count.assign(n_mels, 0);
+  sb.offset.assign(n_mels, 0);
+  sb.weights.clear();
+  sb.max_bin = -1;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < n_bins; ++k) {
+      const float v = bin_major ? bank[size_t(k) * n_mels + m] : bank[size_t(m) * n_bins + k];
+      if (v != 0.0f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    }
+    sb.offset[m] = int(sb.weights.size());
+    if (first >= 0) {
+      sb.start[m] = first;
+      sb.count[m] = last - first + 1;
+      for (int k = first; k <= last; ++k)
+        sb.weights.push_back(bin_major ? bank[size_t(k) * n_mels + m] : bank[size_t(m) * n_bins + k]);
+      if (last > sb.max_bin) sb.max_bin = last;
+    }
+  }
+}
+
+}  // namespace b2a
+
+// ---- C ABI (host-only part) ------------------------------------------------------------------
+extern "C" {
+
+int b2a_window(int kind, int length, float* out) { return b2a::make_window(kind, length, out); }
+
+int b2a_mel_filters(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out) {
+  return b2a::mel_filters_slaney(sample_rate, n_fft, n_mels, f_min, f_max, out);
+}
+
+int b2a_funasr_mel_filters(int sample_rate, int n_fft, int n_mels, float* out) {
+  return b2a::mel_filters_funasr(sample_rate, n_fft, n_mels, out);
+}
+
+int b2a_mel_filters_htk(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out) {
+  return b2a::mel_filters_htk_int(sample_rate, n_fft, n_mels, f_min, f_max, out);
+}
+
+int64_t b2a_reflect_pad_index(int64_t i, int64_t n, int64_t pad) {
+  if (n <= 0 || pad < 0 || i < 0 || i >= n + 2 * pad) return -1;
+  return b2a::reflect_pad_index(i, n, pad);
+}
+
+int b2a_next_power_of_2(int n) {  // CAMPPlus.swift:22-29
+  if (n <= 1) return 1;
+  int p = 1;
+  while (p < n) p *= 2;
+  return p;
+}
+
+int64_t b2a_funasr_compute_feature_length(int64_t audio_length, int hop_length, int lfr_n) {  // FunASRAudio.swift:225-235
+  if (hop_length <= 0 || lfr_n <= 0) return -1;
+  return (audio_length / hop_length + lfr_n - 1) / lfr_n;
+}
+
+// stft: numFrames = 1 + (T + 2*(nFft/2)*center - nFft) / hop   (S3TokenizerUtils.swift:245-251)
+int64_t b2a_stft_num_frames(int64_t n_samples, int n_fft, int hop, int center) {
+  if (n_samples <= 0 || n_fft <= 0 || hop <= 0) return -1;
+  const int64_t len = n_samples + (center ? 2 * int64_t(n_fft / 2) : 0);
+  if (len < n_fft) return -1;
+  return 1 + (len - n_fft) / hop;
+}
+
+int64_t b2a_whisper_num_frames(int64_t n_samples, int64_t padding) {  // WhisperAudio.swift:91-105
+  if (padding < 0) return -1;
+  const int64_t f = b2a_stft_num_frames(n_samples + padding, 400, 160, 1);
+  return f < 0 ? -1 : f - 1;
+}
+
+int64_t b2a_funasr_num_frames(int64_t n_samples) { return b2a_stft_num_frames(n_samples, 400, 160, 1); }
+
+int64_t b2a_lfr_num_rows(int64_t n_frames, int lfr_n) {  // FunASRAudio.swift:117
+  if (n_frames <= 0 || lfr_n <= 0) return -1;
+  return (n_frames + lfr_n - 1) / lfr_n;
+}
+
+int64_t b2a_kaldi_num_frames(int64_t n_samples, int win_length, int hop) {  // CAMPPlus.swift:51-54
+  if (n_samples < win_length || win_length <= 0 || hop <= 0) return -1;  // shorter than one window: MLX.take would read out of bounds
+  return (n_samples - win_length) / hop + 1;
+}
+
+int64_t b2a_s3gen_num_frames(int64_t n_samples, int n_fft, int hop) {  // S3GenMel.swift:10-28,61-77
+  if (n_samples <= 0 || n_fft <= 0 || hop <= 0) return -1;
+  const int64_t pad = (n_fft - hop) / 2;
+  const int64_t eff = pad < n_samples - 1 ? pad : n_samples - 1;  // reflectPad2D truncates the reflection, no loop
+  const int64_t len = n_samples + 2 * eff;
+  if (len < n_fft) return -1;
+  return 1 + (len - n_fft) / hop;
+}
+
+int64_t b2a_vocoder_stft_num_frames(int64_t n_samples, int n_fft, int hop) {  // HiFiGAN.swift:262-270
+  if (n_samples <= n_fft / 2 || n_fft <= 0 || hop <= 0) return -1;  // needs x[1 ..< pad+1]
+  return (n_samples + 2 * int64_t(n_fft / 2) - n_fft) / hop + 1;
+}
+
+int64_t b2a_istft_out_length(int64_t n_frames, int hop) {  // HiFiGAN.swift:331,362-364
+  if (n_frames <= 0 || hop <= 0) return -1;
+  return (n_frames - 1) * hop;
+}
+
+void b2a_voice_enc_config_default(b2a_voice_enc_config* c) {  // Config/ChatterboxConfig.swift:139-156
+  if (!c) return;
+  c->num_mels = 40;
+  c->sample_rate = 16000;
+  c->n_fft = 400;
+  c->hop_size = 160;
+  c->win_size = 400;
+  c->fmin = 0;
+  c->fmax = 8000;
+  c->mel_power = 2.0f;
+  c->mel_type_db = 0;
+  c->normalized_mels = 0;
+  c->stft_magnitude_min = 1e-4f;
+}
+
+const char* b2a_version(void) { return "b200audio 0.1 (sm_100a)"; }
+
+}  // extern "C"

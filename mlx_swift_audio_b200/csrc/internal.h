@@ -1,0 +1,123 @@
+// Internal declarations shared by the host tables, the CUDA kernels and the C ABI.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b2a {
+
+// ---- host tables (host_tables.cpp) ---------------------------------------------------------
+struct SparseBank {
+  int n_mels = 0, n_bins = 0, max_bin = -1;
+  std::vector<int> start, count, offset;  // per filter: first bin, number of bins, offset into weights
+  std::vector<float> weights;
+};
+int make_window(int kind, int length, float* out);
+void hann_periodic_via_hanning(int n, std::vector<float>& w);
+int mel_filters_slaney(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out);
+int mel_filters_funasr(int sample_rate, int n_fft, int n_mels, float* out);
+int mel_filters_htk_int(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out);
+int64_t reflect_pad_index(int64_t i, int64_t n, int64_t pad);
+void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major, SparseBank& sb);
+
+// ---- fused STFT -> (power | magnitude) -> mel -> log front-end (frontend.cu) -----------------
+enum PadMode { PAD_NONE = 0, PAD_REFLECT = 1, PAD_ZERO = 2 };
+enum PreMode { PRE_NONE = 0, PRE_KALDI = 1 };            // per-frame DC removal + 0.97 pre-emphasis
+enum SpecMode { SPEC_POWER = 0, SPEC_MAGNITUDE = 1 };     // |X|^2 or |X|
+enum LogMode { LOG_NONE = 0, LOG_LOG10 = 1, LOG_LN = 2, LOG_DB20 = 3 };
+enum OutMode {
+  OUT_TM = 0,       // (batch, T', M)            Whisper, Fun-ASR log-mel, Kaldi fbank
+  OUT_MT = 1,       // (batch, M, T')            S3Tokenizer/Chatterbox 128-mel, S3Gen 80-mel, voice encoder
+  OUT_LFR = 2,      // (batch, ceil(T'/n), m*M)  Fun-ASR preprocessAudio (LFR stacking fused into the store)
+  OUT_COMPLEX = 3   // (batch, T', F) complex64  plain stft()
+};
+
+struct DeviceBank {  // sparse filterbank in device memory
+  const int* start = nullptr;
+  const int* count = nullptr;
+  const int* offset = nullptr;
+  const float* weights = nullptr;
+  int n_mels = 0;
+  int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
+};
+
+struct FrontendArgs {
+  // plan selection
+  int n_fft = 0, hop = 0, win_len = 0;
+  // input
+  const float* x = nullptr;       // device, (batch, n_samples)
+  int64_t batch = 0;
+  int64_t n_samples = 0;          // real samples per clip
+  int64_t zero_tail = 0;          // Whisper `padding`: virtual zeros appended before the reflect pad
+  int pad_mode = PAD_NONE;
+  int64_t pad_left = 0;           // padded coordinate p maps to signal index p - pad_left
+  int pre_mode = PRE_NONE;
+  const float* window = nullptr;  // HOST pointer, n_fft floats (already zero-extended)
+  // spectrum -> mel -> log
+  int spec_mode = SPEC_POWER;
+  DeviceBank bank;
+  int log_mode = LOG_NONE;
+  float log_floor = 0.0f;
+  int whisper_norm = 0;           // (x + 4) / 4 and per-clip max-8 clamp (needs clip_max / tile_min scratch)
+  float post_sub = 0.0f, post_div = 1.0f;  // optional (x - post_sub) / post_div   (voice-encoder normalized_mels)
+  int post_affine = 0;
+  // output
+  int out_mode = OUT_TM;
+  int64_t n_frames = 0;           // frames to emit per clip
+  float* out = nullptr;           // device
+  int lfr_m = 7, lfr_n = 6;       // OUT_LFR only
+  int64_t lfr_rows = 0;
+  // scratch for the Whisper clamp (device): clip_max (batch) ordered-int encoded, tile_min (batch * tiles)
+  int* clip_max = nullptr;
+  float* tile_min = nullptr;
+};
+
+// Returns 0 or a b2a_status; sets *launches to the number of kernels enqueued.
+int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err);
+int frontend_tiles_per_clip(int n_fft, int64_t n_frames);
+bool frontend_plan_exists(int n_fft, int hop, int win_len);
+int init_frontend_tables(std::string* err);  // once per device: twiddle tables into __constant__ memory
+
+// per-clip column statistics kernels (frontend.cu)
+int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
+                void* stream, int* launches, std::string* err);
+int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err);
+int launch_lfr(const float* in, float* out, int64_t batch, int64_t n_frames, int n_mels, int lfr_m, int lfr_n,
+               void* stream, int* launches, std::string* err);
+int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
+                       int* launches, std::string* err);
+
+// ---- vocoder STFT / iSTFT (vocoder.cu) -------------------------------------------------------
+enum IstftNorm { NORM_WSQ_FLOOR = 0 /* HiFT, CosyVoice3: / max(sum w^2, 1e-8) */, NORM_WSUM_NONZERO = 1 /* Kokoro */ };
+struct IstftArgs {
+  int n_fft = 0, hop = 0;
+  const float* mag = nullptr;     // device (batch, F, frames)
+  const float* phase = nullptr;
+  int64_t batch = 0, n_frames = 0;
+  const float* window = nullptr;  // HOST, n_fft floats
+  float clip_lo = 0.0f;
+  int use_clip_lo = 0;            // CosyVoice3 clips below at 0; HiFT does not
+  float clip_hi = 100.0f;
+  int norm = NORM_WSQ_FLOOR;
+  int unwrap = 0;                 // Kokoro: 0 none, 1 always unwrap (numpy-style, along time), 2 optimistic (flag + redo)
+  int* d_flag = nullptr;          // unwrap == 2: device flag and pinned host mirror
+  int* h_flag = nullptr;
+  float* out = nullptr;           // device (batch, (frames-1)*hop)
+  float* scratch_phase = nullptr; // device, same size as phase, when unwrap != 0
+};
+int launch_istft(const IstftArgs& a, void* stream, int* launches, std::string* err);
+
+enum SmallStftOut { SOUT_REAL_IMAG = 0, SOUT_MAG_PHASE = 1 };
+struct SmallStftArgs {
+  int n_fft = 0, hop = 0;
+  const float* x = nullptr;       // device (batch, n_samples)
+  int64_t batch = 0, n_samples = 0, n_frames = 0;
+  int pad_mode = PAD_REFLECT;     // reflect (HiFT, Kokoro) or zero (CosyVoice3); pad = n_fft / 2
+  const float* window = nullptr;  // HOST, n_fft floats
+  int out_kind = SOUT_REAL_IMAG;
+  float* out0 = nullptr;          // device (batch, F, frames): real or magnitude
+  float* out1 = nullptr;          //                            imag or phase
+};
+int launch_small_stft(const SmallStftArgs& a, void* stream, int* launches, std::string* err);
+
+}  // namespace b2a

@@ -1,0 +1,415 @@
+// Vocoder-side STFT / iSTFT kernels for sm_100a: n_fft 16 / hop 4 (HiFT, CosyVoice3) and
+// n_fft 20 / hop 5 (Kokoro iSTFTNet).
+//
+// Replaces istftHiFiGAN (Codec/S3Gen/HiFiGAN.swift:298-367), cosyVoice3Istft
+// (TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:463-514), MLXSTFT.inverse
+// (TTS/Kokoro/Decoder/MLXSTFT.swift:115-163,211-235) and the matching forward transforms
+// (HiFiGAN.swift:257-295, CausalHiFTGenerator.swift:435-460, MLXSTFT.swift:69-113,181-209).
+//
+// iSTFT design: THREAD == FRAME, lanes are consecutive frames, so the (batch, F, frames) inputs are
+// read with perfectly coalesced 128-byte warp loads.  Each thread clips, converts polar->rectangular
+// with an in-register sincos (Cody-Waite + minimax polynomials, ~1 ulp), runs a generated
+// straight-line half-complex-to-real codelet, applies window/N, and the overlap-add is a GATHER:
+// output segment s (hop samples) = y_s[0:h] + y_{s-1}[h:2h] + y_{s-2}[2h:3h] + y_{s-3}[3h:4h], fetched
+// from the neighbouring lanes with warp shuffles (cross-warp halo through shared memory).  No
+// atomics, no index tensors, deterministic summation order (the frame order of the reference's
+// scatter-add), window-envelope normalisation folded into the same pass.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <string>
+
+#include "../../include/b200audio.h"
+#include "codelets.h"
+#include "internal.h"
+
+namespace b2a {
+
+#define B2A_DEV __device__ __forceinline__
+
+B2A_DEV void c2r(const float (&xr)[9], const float (&xi)[9], float (&y)[16]) { b2a_c2r16(xr, xi, y); }
+B2A_DEV void c2r(const float (&xr)[11], const float (&xi)[11], float (&y)[20]) { b2a_c2r20(xr, xi, y); }
+B2A_DEV void rdft_small(const float (&x)[16], float (&yr)[9], float (&yi)[9]) { b2a_rdft16(x, yr, yi); }
+B2A_DEV void rdft_small(const float (&x)[20], float (&yr)[11], float (&yi)[11]) { b2a_rdft20(x, yr, yi); }
+
+// sin and cos of x, ~1 ulp for |x| < 4.8e4 (3-term Cody-Waite reduction by pi/2 with FMA, cephes-style
+// minimax polynomials on [-pi/4, pi/4]); larger arguments take the libdevice slow path.
+B2A_DEV void sincos_f32(float x, float* s, float* c) {
+  if (!(fabsf(x) < 48000.0f)) {
+    sincosf(x, s, c);
+    return;
+  }
+  const float q = rintf(x * 0.636619772f);
+  float r = fmaf(q, -1.57079601e+00f, x);
+  r = fmaf(q, -3.13916473e-07f, r);
+  r = fmaf(q, -5.39030253e-15f, r);
+  const int i = __float2int_rn(q);
+  const float r2 = r * r;
+  float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, r2, -1.6666654611e-1f);
+  ps = fmaf(ps * r2, r, r);
+  float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, r2, 4.166664568298827e-2f);
+  pc = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const float ss = (i & 1) ? pc : ps;
+  const float cc = (i & 1) ? ps : pc;
+  *s = (i & 2) ? -ss : ss;
+  *c = ((i + 1) & 2) ? -cc : cc;
+}
+
+template <int NFFT, int HOP>
+struct IstftParams {
+  const float* mag;
+  const float* phase;
+  float* out;
+  long long n_frames, out_len;
+  float clip_lo, clip_hi;
+  int use_clip_lo, norm;
+  int* unwrap_flag;       // set to 1 if any |dphi| >= pi was seen (Kokoro optimistic path); may be null
+  float wn[NFFT];         // window[n] / NFFT
+  float wenv[NFFT];       // window^2 (HiFT/CosyVoice3) or window (Kokoro): envelope contributions
+  float inv_env[HOP];     // interior 1 / envelope
+};
+
+constexpr int kIstftThreads = 256;
+
+template <int NFFT, int HOP>
+__global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_constant__ IstftParams<NFFT, HOP> prm) {
+  constexpr int F = NFFT / 2 + 1;
+  constexpr int R = NFFT / HOP;          // overlapping frames per output segment
+  constexpr int HALO = R - 1;
+  constexpr int SEG_PER_BLOCK = kIstftThreads - HALO;
+  static_assert(NFFT % HOP == 0 && R == 4, "built for 4x overlap");
+  __shared__ float s_halo[kIstftThreads / 32][HALO][HALO * HOP];  // [warp][lane 29..31][tail parts]
+  __shared__ float s_stage[(HOP == 4) ? 1 : SEG_PER_BLOCK * HOP];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long clip = blockIdx.y;
+  const long long nF = prm.n_frames;
+  const long long nSeg = nF + HALO;                      // segments of the untrimmed OLA buffer
+  const long long seg0 = (long long)blockIdx.x * SEG_PER_BLOCK;  // first segment this block emits
+  const long long f = seg0 - HALO + tid;                 // frame (== segment) of this thread
+  const bool has_frame = f >= 0 && f < nF;
+
+  // ---- per-frame inverse real FFT, windowed ------------------------------------------------------
+  float y[NFFT];
+  {
+    const float* __restrict__ mp = prm.mag + clip * F * nF + f;
+    const float* __restrict__ pp = prm.phase + clip * F * nF + f;
+    float xr[F], xi[F], ph[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+      float m = has_frame ? __ldg(mp + k * nF) : 0.0f;
+      ph[k] = has_frame ? __ldg(pp + k * nF) : 0.0f;
+      m = fminf(m, prm.clip_hi);
+      if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
+      xr[k] = m;
+    }
+    if (prm.unwrap_flag != nullptr) {
+      // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.
+      // (warp-uniform branch; every lane takes part in the shuffles)
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        float prev = __shfl_up_sync(0xffffffffu, ph[k], 1);
+        if (has_frame && f > 0) {
+          if (lane == 0) prev = __ldg(pp + k * nF - 1);
+          bad |= !(fabsf(ph[k] - prev) < 3.14159274f);
+        }
+      }
+      if (bad) *prm.unwrap_flag = 1;
+    }
+    if (has_frame) {
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        float s, c;
+        sincos_f32(ph[k], &s, &c);
+        const float m = xr[k];
+        xr[k] = m * c;
+        xi[k] = m * s;  // imaginary parts of DC / Nyquist are ignored by the codelet, as by irfft
+      }
+      c2r(xr, xi, y);
+#pragma unroll
+      for (int n = 0; n < NFFT; ++n) y[n] *= prm.wn[n];
+    } else {
+#pragma unroll
+      for (int n = 0; n < NFFT; ++n) y[n] = 0.0f;
+    }
+  }
+
+  // ---- overlap-add as a gather from the 3 previous frames ----------------------------------------
+  if (lane >= 32 - HALO) {
+    const int h = lane - (32 - HALO);  // 0 -> lane 29
+#pragma unroll
+    for (int i = 0; i < HALO * HOP; ++i) s_halo[warp][h][i] = y[HOP + i];
+  }
+  __syncthreads();
+  float acc[HOP];
+#pragma unroll
+  for (int i = 0; i < HOP; ++i) acc[i] = y[i];
+#pragma unroll
+  for (int r = 1; r <= HALO; ++r) {
+#pragma unroll
+    for (int i = 0; i < HOP; ++i) {
+      float v = __shfl_up_sync(0xffffffffu, y[r * HOP + i], r);
+      if (lane < r) v = warp > 0 ? s_halo[warp - 1][HALO - r + lane][(r - 1) * HOP + i] : 0.0f;
+      acc[i] += v;
+    }
+  }
+
+  // ---- envelope normalisation, trim, store ---------------------------------------------------------
+  const long long s = f;                           // this thread's segment index
+  const bool emit = tid >= HALO && s >= R / 2 && s < nSeg - R / 2 && s >= 0;
+  float o[HOP];
+  if (emit) {
+    const bool interior = s >= HALO && s <= nF - 1;
+#pragma unroll
+    for (int i = 0; i < HOP; ++i) {
+      if (interior) {
+        o[i] = acc[i] * prm.inv_env[i];
+      } else {
+        float e = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (s - r >= 0 && s - r < nF) e += prm.wenv[r * HOP + i];
+        if (prm.norm == NORM_WSQ_FLOOR) o[i] = acc[i] / fmaxf(e, 1e-8f);
+        else o[i] = e != 0.0f ? acc[i] / e : acc[i];
+      }
+    }
+  }
+  float* __restrict__ dst = prm.out + clip * prm.out_len;
+  if (HOP == 4) {
+    if (emit) {
+      float* d = dst + (s - R / 2) * HOP;
+      if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < HOP; ++i) d[i] = o[i];
+      }
+    }
+  } else {
+    // hop 5: stage the block's segments and write them out contiguously
+    if (emit) {
+#pragma unroll
+      for (int i = 0; i < HOP; ++i) s_stage[(tid - HALO) * HOP + i] = o[i];
+    }
+    __syncthreads();
+    // block emits segments [max(seg0, R/2), min(seg0 + SEG_PER_BLOCK, nSeg - R/2))
+    const long long a = seg0 > R / 2 ? seg0 : R / 2;
+    long long b = seg0 + SEG_PER_BLOCK;
+    if (b > nSeg - R / 2) b = nSeg - R / 2;
+    const long long n = (b - a) * HOP;
+    const float* src = s_stage + (a - seg0) * HOP;
+    float* d = dst + (a - R / 2) * HOP;
+    for (long long i = tid; i < n; i += kIstftThreads) d[i] = src[i];
+  }
+}
+
+// ---- Kokoro slow path: numpy-style unwrap along time (MLXSTFT.swift:23-46), one warp per (clip, bin) row
+__global__ void unwrap_kernel(const float* __restrict__ phase, float* __restrict__ out, long long n_frames, long long n_rows) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = phase + row * n_frames;
+  float* o = out + row * n_frames;
+  const float period = 6.28318548f, hi = 3.14159274f, lo = -3.14159274f;
+  float carry = 0.0f;   // running sum of corrections
+  float prev_last = 0.0f;
+  for (long long t0 = 0; t0 < n_frames; t0 += 32) {
+    const long long t = t0 + lane;
+    const float v = t < n_frames ? p[t] : 0.0f;
+    float prev = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) prev = prev_last;
+    float corr = 0.0f;
+    if (t > 0 && t < n_frames) {
+      const float d = v - prev;
+      float dm = d - lo;
+      dm = fmodf(fmodf(dm, period) + period, period) + lo;
+      if (dm == lo && d > 0.0f) dm = hi;
+      corr = fabsf(d) < hi ? 0.0f : dm - d;
+    }
+    // inclusive warp scan of the corrections
+    float sc = corr;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, sc, d);
+      if (lane >= d) sc += n;
+    }
+    sc += carry;
+    if (t < n_frames) o[t] = t == 0 ? v : v + sc;
+    carry = __shfl_sync(0xffffffffu, sc, 31);
+    prev_last = __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small forward STFT: thread == frame
+// ------------------------------------------------------------------------------------------------
+template <int NFFT, int HOP>
+struct SmallStftParams {
+  const float* x;
+  float* out0;
+  float* out1;
+  long long n_samples, n_frames;
+  int pad_mode, out_kind;
+  float w[NFFT];
+};
+
+template <int NFFT, int HOP>
+__global__ void __launch_bounds__(256) small_stft_kernel(const __grid_constant__ SmallStftParams<NFFT, HOP> prm) {
+  constexpr int F = NFFT / 2 + 1;
+  constexpr int PAD = NFFT / 2;
+  const long long clip = blockIdx.y;
+  const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= prm.n_frames) return;
+  const long long T = prm.n_samples;
+  const float* __restrict__ xc = prm.x + clip * T;
+  float in[NFFT];
+  const long long j0 = f * HOP - PAD;
+  if (j0 >= 0 && j0 + NFFT <= T) {
+#pragma unroll
+    for (int n = 0; n < NFFT; ++n) in[n] = __ldg(xc + j0 + n) * prm.w[n];
+  } else {
+#pragma unroll
+    for (int n = 0; n < NFFT; ++n) {
+      long long j = j0 + n;
+      float v = 0.0f;
+      if (j >= 0 && j < T) v = __ldg(xc + j);
+      else if (prm.pad_mode == PAD_REFLECT) {
+        j = j < 0 ? -j : 2 * (T - 1) - j;   // T > PAD is checked on the host
+        v = __ldg(xc + j);
+      }
+      in[n] = v * prm.w[n];
+    }
+  }
+  float yr[F], yi[F];
+  rdft_small(in, yr, yi);
+  float* o0 = prm.out0 + clip * F * prm.n_frames + f;
+  float* o1 = prm.out1 + clip * F * prm.n_frames + f;
+#pragma unroll
+  for (int k = 0; k < F; ++k) {
+    if (prm.out_kind == SOUT_REAL_IMAG) {
+      o0[k * prm.n_frames] = yr[k];
+      o1[k * prm.n_frames] = yi[k];
+    } else {
+      o0[k * prm.n_frames] = sqrtf(yr[k] * yr[k] + yi[k] * yi[k]);
+      o1[k * prm.n_frames] = atan2f(yi[k], yr[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int cuda_fail2(cudaError_t e, const char* what, std::string* err) {
+  if (err) *err = std::string(what) + ": " + cudaGetErrorString(e);
+  return B2A_E_CUDA;
+}
+
+template <int NFFT, int HOP>
+static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, std::string* err, const float* phase,
+                          int* unwrap_flag) {
+  constexpr int R = NFFT / HOP;
+  IstftParams<NFFT, HOP> prm;
+  prm.mag = a.mag;
+  prm.phase = phase;
+  prm.out = a.out;
+  prm.n_frames = a.n_frames;
+  prm.out_len = (a.n_frames - 1) * HOP;
+  prm.clip_lo = a.clip_lo;
+  prm.clip_hi = a.clip_hi;
+  prm.use_clip_lo = a.use_clip_lo;
+  prm.norm = a.norm;
+  prm.unwrap_flag = unwrap_flag;
+  for (int n = 0; n < NFFT; ++n) {
+    prm.wn[n] = a.window[n] / float(NFFT);
+    prm.wenv[n] = a.norm == NORM_WSQ_FLOOR ? a.window[n] * a.window[n] : a.window[n];
+  }
+  for (int i = 0; i < HOP; ++i) {
+    float e = 0.0f;
+    for (int r = 0; r < R; ++r) e += prm.wenv[r * HOP + i];  // same order as the scatter-add by frame
+    if (a.norm == NORM_WSQ_FLOOR) e = e > 1e-8f ? e : 1e-8f;
+    prm.inv_env[i] = e != 0.0f ? 1.0f / e : 1.0f;
+  }
+  const long long n_seg = a.n_frames + R - 1;
+  const int per_block = kIstftThreads - (R - 1);
+  dim3 grid(unsigned((n_seg + per_block - 1) / per_block), unsigned(a.batch));
+  istft_kernel<NFFT, HOP><<<grid, kIstftThreads, 0, st>>>(prm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail2(e, "istft_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+int launch_istft(const IstftArgs& a, void* stream, int* launches, std::string* err) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a.n_frames < 2) {
+    if (err) *err = "iSTFT needs at least 2 frames";
+    return B2A_E_TOO_SHORT;
+  }
+  auto run = [&](const float* phase, int* flag) -> int {
+    if (a.n_fft == 16 && a.hop == 4) return launch_istft_t<16, 4>(a, st, launches, err, phase, flag);
+    if (a.n_fft == 20 && a.hop == 5) return launch_istft_t<20, 5>(a, st, launches, err, phase, flag);
+    return -1;
+  };
+  auto run_unwrapped = [&]() -> int {
+    const long long rows = a.batch * (a.n_fft / 2 + 1);
+    unwrap_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a.phase, a.scratch_phase, a.n_frames, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail2(e, "unwrap_kernel launch", err);
+    *launches += 1;
+    return run(a.scratch_phase, nullptr);
+  };
+  int rc;
+  if (a.unwrap == 0) {
+    rc = run(a.phase, nullptr);
+  } else if (a.unwrap == 2 && a.d_flag != nullptr && a.h_flag != nullptr) {
+    // Optimistic: unwrap is the identity unless a phase step >= pi exists.  The kernel raises a flag when it
+    // sees one; only then is the slow path (fp32 cumsum of corrections, then iSTFT again) taken.  The host
+    // reads the flag, i.e. this entry point synchronises -- as the reference's own eval() calls do
+    // (MLXSTFT.swift:219,229).
+    cudaError_t e = cudaMemsetAsync(a.d_flag, 0, sizeof(int), st);
+    if (e != cudaSuccess) return cuda_fail2(e, "memset", err);
+    rc = run(a.phase, a.d_flag);
+    if (rc != B2A_OK) goto done;
+    if ((e = cudaMemcpyAsync(a.h_flag, a.d_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail2(e, "flag copy", err);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail2(e, "sync", err);
+    if (*a.h_flag != 0) rc = run_unwrapped();
+  } else {
+    rc = run_unwrapped();
+  }
+done:
+  if (rc >= 0) return rc;
+  if (err) *err = "iSTFT built for (n_fft, hop) = (16, 4) and (20, 5)";
+  return B2A_E_UNSUPPORTED;
+}
+
+template <int NFFT, int HOP>
+static int launch_small_stft_t(const SmallStftArgs& a, cudaStream_t st, int* launches, std::string* err) {
+  SmallStftParams<NFFT, HOP> prm;
+  prm.x = a.x;
+  prm.out0 = a.out0;
+  prm.out1 = a.out1;
+  prm.n_samples = a.n_samples;
+  prm.n_frames = a.n_frames;
+  prm.pad_mode = a.pad_mode;
+  prm.out_kind = a.out_kind;
+  for (int n = 0; n < NFFT; ++n) prm.w[n] = a.window[n];
+  dim3 grid(unsigned((a.n_frames + 255) / 256), unsigned(a.batch));
+  small_stft_kernel<NFFT, HOP><<<grid, 256, 0, st>>>(prm);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail2(e, "small_stft_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+int launch_small_stft(const SmallStftArgs& a, void* stream, int* launches, std::string* err) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a.n_fft == 16 && a.hop == 4) return launch_small_stft_t<16, 4>(a, st, launches, err);
+  if (a.n_fft == 20 && a.hop == 5) return launch_small_stft_t<20, 5>(a, st, launches, err);
+  if (err) *err = "vocoder STFT built for (n_fft, hop) = (16, 4) and (20, 5)";
+  return B2A_E_UNSUPPORTED;
+}
+
+}  // namespace b2a

@@ -363,7 +363,27 @@ def gen_c2r(n):
     return emit(g, "b2a_c2r%d" % n, "const float (&xr)[%d], const float (&xi)[%d], float (&y)[%d]" % (h, h, n), outs)
 
 
+def gen_rdft_odd(n):
+    """Odd-frequency DFT of a real sequence: U[k] = sum_j y[j] e^{-2 pi i j (k + 1/2)/n}, k = 0..(n-1)//2.
+    This is the stage-B item k1 = N1/2 of the two-stage real FFT (inputs are real after stage A;
+    the inter-stage twiddle e^{-pi i j/n} is folded in here as compile-time constants).  The other
+    bins are conjugate mirrors: U[n-1-k] = conj(U[k])."""
+    g = G()
+    xs = []
+    for j in range(n):
+        ang = -math.pi * j / n
+        xs.append(C(g, g.inp("x[%d]" % j), g.ZERO).mul_const(math.cos(ang), math.sin(ang)))
+    ys = dft(g, xs, -1)
+    h = (n - 1) // 2 + 1
+    outs = []
+    for k in range(h):
+        outs.append(("yr[%d]" % k, ys[k].re))
+        outs.append(("yi[%d]" % k, ys[k].im))
+    return emit(g, "b2a_rdftodd%d" % n, "const float (&x)[%d], float (&yr)[%d], float (&yi)[%d]" % (n, h, h), outs)
+
+
 RDFT = [16, 20, 25, 32, 40, 60, 64]
+RDFT_ODD = [25, 32]
 CDFT = [16, 20, 25, 30, 32]
 C2R = [16, 20]
 
@@ -380,6 +400,10 @@ def main():
         code, st = gen_rdft(n)
         out.append(code)
         stats.append(("rdft%d" % n, st))
+    for n in RDFT_ODD:
+        code, st = gen_rdft_odd(n)
+        out.append(code)
+        stats.append(("rdftodd%d" % n, st))
     for n in CDFT:
         code, st = gen_cdft(n)
         out.append(code)
