@@ -26,9 +26,7 @@ struct DevBuf {
 
 struct BankStorage {
   SparseBank host;
-  int* start = nullptr;
-  int* count = nullptr;
-  int* offset = nullptr;
+  int* desc = nullptr;
   float* weights = nullptr;
 };
 
@@ -103,23 +101,23 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
     build_sparse_bank(dense.data(), n_mels, n_bins, bin_major, bs.host);
     const size_t nw = std::max<size_t>(bs.host.weights.size(), 1);
     cudaError_t e;
-    if ((e = cudaMalloc(&bs.start, sizeof(int) * n_mels)) != cudaSuccess) return cu(c, e, "cudaMalloc");
-    if ((e = cudaMalloc(&bs.count, sizeof(int) * n_mels)) != cudaSuccess) return cu(c, e, "cudaMalloc");
-    if ((e = cudaMalloc(&bs.offset, sizeof(int) * n_mels)) != cudaSuccess) return cu(c, e, "cudaMalloc");
+    std::vector<int> desc(size_t(n_mels) * 4, 0);
+    for (int m = 0; m < n_mels; ++m) {
+      desc[4 * m + 0] = bs.host.start[m];
+      desc[4 * m + 1] = bs.host.count[m];
+      desc[4 * m + 2] = bs.host.offset[m];
+    }
+    if ((e = cudaMalloc(&bs.desc, sizeof(int) * desc.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
     if ((e = cudaMalloc(&bs.weights, sizeof(float) * nw)) != cudaSuccess) return cu(c, e, "cudaMalloc");
     // synchronous uploads (once per configuration), ordered before any later launch
-    if ((e = cudaMemcpy(bs.start, bs.host.start.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
-    if ((e = cudaMemcpy(bs.count, bs.host.count.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
-    if ((e = cudaMemcpy(bs.offset, bs.host.offset.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
+    if ((e = cudaMemcpy(bs.desc, desc.data(), sizeof(int) * desc.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
     if (!bs.host.weights.empty())
       if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
     it = c->banks.emplace(key, std::move(bs)).first;
   }
   const BankStorage& bs = it->second;
-  out->start = bs.start;
-  out->count = bs.count;
-  out->offset = bs.offset;
+  out->desc = bs.desc;
   out->weights = bs.weights;
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
@@ -371,9 +369,7 @@ int b2a_ctx_destroy(b2a_ctx* c) {
     if (c->ev_d2h[s]) cudaEventDestroy(c->ev_d2h[s]);
   }
   for (auto& kv : c->banks) {
-    cudaFree(kv.second.start);
-    cudaFree(kv.second.count);
-    cudaFree(kv.second.offset);
+    cudaFree(kv.second.desc);
     cudaFree(kv.second.weights);
   }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);

@@ -25,6 +25,7 @@
 
 #include <cmath>
 #include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -78,26 +79,21 @@ template <class P> struct TwTable;
 template <> struct TwTable<Plan400> { static B2A_DEV const float2* get() { return c_tw400; } };
 template <> struct TwTable<Plan512> { static B2A_DEV const float2* get() { return c_tw512; } };
 
-struct WinTabEntry {
-  float w;   // window value at sample offset o
-  int off;   // skewed shared-memory word offset of sample o relative to the lane's frame start
-};
+enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
 
 template <class P>
 struct FrontendParams {
   const float* x;
   long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, lfr_rows;
-  int pad_mode, pre_mode, spec_mode, log_mode, whisper_norm, post_affine, out_mode, tiles_per_clip, lfr_m, lfr_n;
+  int pad_mode, log_mode, whisper_norm, post_affine, out_mode, tiles_per_clip, lfr_m, lfr_n;
   float log_floor, post_sub, post_div;
-  const int* fb_start;
-  const int* fb_count;
-  const int* fb_offset;
+  const int4* fb_desc;    // per filter: (first bin, number of bins, offset into fb_w, 0)
   const float* fb_w;
-  int n_mels, n_bins_used;
+  int n_mels;
   float* out;
   int* clip_max;
   float* tile_min;
-  WinTabEntry tab[P::WIN];
+  float window[P::WIN];
 };
 
 B2A_DEV int enc_ordered(float f) {
@@ -119,14 +115,52 @@ B2A_DEV float fetch_padded(const float* __restrict__ xc, long long p, long long 
   return j < n_samples ? __ldg(xc + j) : 0.0f;
 }
 
-template <class P>
+// Shared-memory word offset (relative to the lane's frame start) of sample o = N2*n1 + n2 in the skewed
+// PCM tile: o + o / HOP.  With n1 a compile-time constant this is (immediate) + n2 + carry, and the carry
+// can only be non-zero for the few n1 whose row remainder is within N2 of the row end.
+template <class P, int n1>
+B2A_DEV int pcm_off(int n2) {
+  constexpr int base = P::N2 * n1;
+  constexpr int c = base / P::HOP, r = base % P::HOP;
+  if (r + P::N2 - 1 >= P::HOP) return base + c + n2 + (n2 >= P::HOP - r ? 1 : 0);
+  return base + c + n2;
+}
+
+template <class P, int PRE, int n1>
+B2A_DEV float load_sample(const float* lane_pcm, int n2, float mu) {
+  constexpr int base = P::N2 * n1;
+  if (base >= P::WIN) return 0.0f;
+  const int off = pcm_off<P, n1>(n2);
+  float v = lane_pcm[off];
+  if (PRE == PRE_KALDI) {
+    // (x[o]-mu) - 0.97*(x[o-1]-mu), first sample only DC-removed (CAMPPlus.swift:66-72)
+    v = v - mu;
+    const int o = base + n2;
+    if (o > 0) {
+      const int poff = off - 1 - ((o % P::HOP) == 0 ? 1 : 0);  // previous sample may sit before the row's pad word
+      v = v - 0.97f * (lane_pcm[poff] - mu);
+    }
+  }
+  if (base + P::N2 - 1 >= P::WIN && base + n2 >= P::WIN) v = 0.0f;  // zero-extended window (win_length < n_fft)
+  return v;
+}
+
+template <class P, int PRE, int... I>
+B2A_DEV void load_item(const float* lane_pcm, int n2, float mu, const float* wrow, float (&in)[P::N1], std::integer_sequence<int, I...>) {
+  ((in[I] = load_sample<P, PRE, I>(lane_pcm, n2, mu) * wrow[I]), ...);
+}
+
+template <class P, int PRE, int SPEC>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
+  constexpr bool cplx = SPEC == SK_CPLX;
+  constexpr int OP = FT + 1;  // output staging pitch ([m][frame], conflict-free both ways)
   extern __shared__ __align__(16) float smem[];
-  const bool cplx = prm.out_mode == OUT_COMPLEX;
   float* s_r0 = smem;                                       // PCM tile, later the spectrum tile
   float2* s_y = reinterpret_cast<float2*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL));
   float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
+  float* s_wt = smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS;  // window, item-major [n2][n1]
+  float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   __shared__ int s_tile_min;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -136,19 +170,25 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
   if (tid == 0) s_tile_min = 0x7fffffff;
 
-  // ---- 1. stage the tile's PCM (coalesced, skewed rows) -----------------------------------------
+  // ---- 0. per-block tables: window in item-major order, twiddles ---------------------------------
+  for (int i = tid; i < N; i += P::NTHREADS) {
+    const int n2 = i / N1, n1 = i - n2 * N1;
+    const int o = N2 * n1 + n2;
+    s_wt[i] = o < WIN ? prm.window[o] : 0.0f;
+  }
+  {
+    const float2* __restrict__ tw = TwTable<P>::get();
+    for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) s_tw[i] = tw[i];
+  }
+
+  // ---- 1. stage the tile's PCM: coalesced scalar loads, skewed rows (pitch HOP+1) -------------------
   {
     const long long p0 = f0 * HOP;
     const long long j0 = p0 - prm.pad_left;
-    const bool interior = j0 >= 0 && j0 + P::TS <= prm.n_samples && ((reinterpret_cast<uintptr_t>(xc + j0) & 15) == 0);
-    if (interior) {
-      const float4* __restrict__ src = reinterpret_cast<const float4*>(xc + j0);
-      for (int s4 = tid; s4 < P::TS / 4; s4 += P::NTHREADS) {
-        const float4 v = __ldg(src + s4);
-        const int s = s4 * 4;
-        float* d = s_r0 + s + s / HOP;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-      }
+    if (j0 >= 0 && j0 + P::TS <= prm.n_samples) {
+      const float* __restrict__ src = xc + j0;
+#pragma unroll 4
+      for (int s = tid; s < P::TS; s += P::NTHREADS) s_r0[s + s / HOP] = __ldg(src + s);
     } else {
       for (int s = tid; s < P::TS; s += P::NTHREADS)
         s_r0[s + s / HOP] = fetch_padded(xc, p0 + s, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode);
@@ -158,9 +198,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
   // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
   float mu = 0.0f;
-  if (prm.pre_mode == PRE_KALDI) {
+  if (PRE == PRE_KALDI) {
     float part = 0.0f;
-    for (int o = warp; o < WIN; o += NW) part += s_r0[lane * P::PITCH + prm.tab[o].off];
+    for (int o = warp; o < WIN; o += NW) part += s_r0[lane * P::PITCH + o + o / HOP];
     s_o[warp * FT + lane] = part;
     __syncthreads();
     float tot = 0.0f;
@@ -173,32 +213,23 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
   {
     const float* lane_pcm = s_r0 + lane * P::PITCH;
-    const float2* __restrict__ tw = TwTable<P>::get();
     for (int n2 = warp; n2 < N2; n2 += NW) {
-      float in[N1];
+      float wrow[N1];
 #pragma unroll
-      for (int n1 = 0; n1 < N1; ++n1) {
-        const int o = N2 * n1 + n2;
-        if (N2 * n1 < WIN && o < WIN) {
-          const WinTabEntry e = prm.tab[o];
-          float v = lane_pcm[e.off];
-          if (prm.pre_mode == PRE_KALDI) {
-            // (x[o]-mu) - 0.97*(x[o-1]-mu), first sample only DC-removed (CAMPPlus.swift:66-72)
-            v = v - mu;
-            if (o > 0) v = v - 0.97f * (lane_pcm[prm.tab[o - 1].off] - mu);
-          }
-          in[n1] = v * e.w;
-        } else {
-          in[n1] = 0.0f;
-        }
+      for (int q = 0; q < N1 / 4; ++q) {
+        const float4 w4 = reinterpret_cast<const float4*>(s_wt + n2 * N1)[q];
+        wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
       }
+      float in[N1];
+      load_item<P, PRE>(lane_pcm, n2, mu, wrow, in, std::make_integer_sequence<int, N1>{});
       float yr[H1 + 1], yi[H1 + 1];
       rdft(in, yr, yi);
       float2* yb = s_y + n2 * FT + lane;
       yb[0] = make_float2(yr[0], yr[H1]);
+      const float2* twr = s_tw + n2 * (H1 - 1);
 #pragma unroll
       for (int k1 = 1; k1 < H1; ++k1) {
-        const float2 t = tw[n2 * (H1 - 1) + (k1 - 1)];
+        const float2 t = twr[k1 - 1];
         yb[k1 * N2 * FT] = make_float2(yr[k1] * t.x - yi[k1] * t.y, yr[k1] * t.y + yi[k1] * t.x);
       }
     }
@@ -207,13 +238,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
   // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
   {
-    const int spec_mode = prm.spec_mode;
     auto put = [&](int k, float re, float im) {
       if (cplx) {
         reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + lane] = make_float2(re, im);
       } else {
         const float pw = re * re + im * im;
-        s_r0[k * FT + lane] = spec_mode == SPEC_POWER ? pw : sqrtf(pw);
+        s_r0[k * FT + lane] = SPEC == SK_POWER ? pw : sqrtf(pw);
       }
     };
     for (int it = warp; it <= H1; it += NW) {
@@ -255,12 +285,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   __syncthreads();
 
   const bool frame_ok = f0 + lane < prm.n_frames;
+  const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
 
   // ---- 4a. plain stft(): write the complex spectrum tile ------------------------------------------
   if (cplx) {
     const int nb = P::NBINS;
     float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride) + f0 * nb;
-    const long long rows = prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT;
     const float2* sp = reinterpret_cast<const float2*>(s_r0);
     for (int e = tid; e < rows * nb; e += P::NTHREADS) {
       const int r = e / nb, k = e - r * nb;
@@ -271,34 +301,35 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
   // ---- 4b. sparse mel projection + log / floor / scale ---------------------------------------------
   const int M = prm.n_mels;
-  const int opitch = M + 1;
   float lmax = -3.0e38f, vmin = 3.0e38f;
   {
-    const int* __restrict__ fst = prm.fb_start;
-    const int* __restrict__ fcn = prm.fb_count;
-    const int* __restrict__ fof = prm.fb_offset;
+    const int4* __restrict__ fdesc = prm.fb_desc;
     const float* __restrict__ fw = prm.fb_w;
+    const int log_mode = prm.log_mode;
+    const float log_floor = prm.log_floor;
     float* __restrict__ out_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
     for (int m = warp; m < M; m += NW) {
-      const int st = __ldg(fst + m), cn = __ldg(fcn + m);
-      const float* __restrict__ w = fw + __ldg(fof + m);
-      const float* pp = s_r0 + st * FT + lane;
+      const int4 d = __ldg(fdesc + m);
+      const float* __restrict__ w = fw + d.z;
+      const float* pp = s_r0 + d.x * FT + lane;
       float acc = 0.0f;
-      for (int i = 0; i < cn; ++i) acc = fmaf(__ldg(w + i), pp[i * FT], acc);
+#pragma unroll 4
+      for (int i = 0; i < d.y; ++i) acc = fmaf(__ldg(w + i), pp[i * FT], acc);
       float v = acc;
-      if (prm.log_mode == LOG_LOG10) v = log10f(fmaxf(v, prm.log_floor));
-      else if (prm.log_mode == LOG_LN) v = logf(fmaxf(v, prm.log_floor));
-      else if (prm.log_mode == LOG_DB20) v = 20.0f * log10f(fmaxf(v, prm.log_floor));
+      // log2-based logs: MUFU.LG2 is accurate to ~1e-7 absolute on the log value, far inside the 1e-4 tolerance
+      if (log_mode == LOG_LOG10) v = __log2f(fmaxf(v, log_floor)) * 0.30102999566398120f;
+      else if (log_mode == LOG_LN) v = __log2f(fmaxf(v, log_floor)) * 0.69314718055994531f;
+      else if (log_mode == LOG_DB20) v = __log2f(fmaxf(v, log_floor)) * 6.0205999132796239f;
       if (prm.whisper_norm) {
         if (frame_ok) lmax = fmaxf(lmax, v);
-        v = (v + 4.0f) / 4.0f;
+        v = (v + 4.0f) * 0.25f;
         if (frame_ok) vmin = fminf(vmin, v);
       }
       if (prm.post_affine) v = (v - prm.post_sub) / prm.post_div;
       if (prm.out_mode == OUT_MT) {
         if (frame_ok) out_mt[(long long)m * prm.n_frames] = v;
       } else {
-        s_o[lane * opitch + m] = v;
+        s_o[m * OP + lane] = v;
       }
     }
   }
@@ -318,22 +349,17 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   if (prm.whisper_norm && tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
   if (prm.out_mode == OUT_MT) return;
 
-  // ---- 5. coalesced store of the staged (frames x M) tile -------------------------------------------
-  const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
+  // ---- 5. coalesced store of the staged (M x frames) tile as (frames, M) rows ------------------------
   if (prm.out_mode == OUT_TM) {
     float* __restrict__ dst = prm.out + clip * prm.out_clip_stride + f0 * M;
-    if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      const int m4 = M >> 2;
-      for (int e = tid; e < rows * m4; e += P::NTHREADS) {
-        const int r = e / m4, c = (e - r * m4) * 4;
-        const float* s = s_o + r * opitch + c;
-        reinterpret_cast<float4*>(dst)[e] = make_float4(s[0], s[1], s[2], s[3]);
-      }
-    } else {
-      for (int e = tid; e < rows * M; e += P::NTHREADS) {
-        const int r = e / M, c = e - r * M;
-        dst[e] = s_o[r * opitch + c];
-      }
+    const int total = rows * M;
+    int r = tid / M, c = tid - r * M;
+    const int dr = P::NTHREADS / M, dc = P::NTHREADS - dr * M;
+    for (int e = tid; e < total; e += P::NTHREADS) {
+      dst[e] = s_o[c * OP + r];
+      r += dr;
+      c += dc;
+      if (c >= M) { c -= M; r += 1; }
     }
   } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
     const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
@@ -351,9 +377,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       long long t = i * ln + j - left;
       t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
       if (t < f0 || t >= f0 + rows) continue;
-      const float* s = s_o + int(t - f0) * opitch;
+      const float* s = s_o + int(t - f0);
       float* d = dst + (i * lm + j) * (long long)M;
-      for (int c = lane; c < M; c += 32) d[c] = s[c];
+      for (int c = lane; c < M; c += 32) d[c] = s[c * OP];
     }
   }
 }
@@ -494,9 +520,9 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + 31) / 32);
 }
 
-template <class P>
+template <class P, int PRE, int SPEC>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
-  static FrontendParams<P> prm;  // large (window table); filled per call under the context's lock
+  static FrontendParams<P> prm;  // large (window table); filled and launched under the lock
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
   prm.x = a.x;
@@ -506,8 +532,6 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.pad_left = a.pad_left;
   prm.n_frames = a.n_frames;
   prm.pad_mode = a.pad_mode;
-  prm.pre_mode = a.pre_mode;
-  prm.spec_mode = a.spec_mode;
   prm.log_mode = a.log_mode;
   prm.whisper_norm = a.whisper_norm;
   prm.post_affine = a.post_affine;
@@ -518,12 +542,9 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.lfr_m = a.lfr_m;
   prm.lfr_n = a.lfr_n;
   prm.lfr_rows = a.lfr_rows;
-  prm.fb_start = a.bank.start;
-  prm.fb_count = a.bank.count;
-  prm.fb_offset = a.bank.offset;
+  prm.fb_desc = reinterpret_cast<const int4*>(a.bank.desc);
   prm.fb_w = a.bank.weights;
   prm.n_mels = a.bank.n_mels;
-  prm.n_bins_used = a.bank.n_bins_used;
   prm.out = a.out;
   prm.clip_max = a.clip_max;
   prm.tile_min = a.tile_min;
@@ -534,34 +555,27 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     case OUT_LFR: prm.out_clip_stride = a.lfr_rows * (long long)a.lfr_m * a.bank.n_mels; break;
     default: prm.out_clip_stride = a.n_frames * (long long)P::NBINS * 2; break;
   }
-  for (int o = 0; o < P::WIN; ++o) {
-    prm.tab[o].w = a.window[o];
-    prm.tab[o].off = o + o / P::HOP;
-  }
-  if (a.out_mode != OUT_COMPLEX) {
-    if (a.bank.n_mels <= 0 || a.bank.n_mels + 1 > P::N) {
+  for (int o = 0; o < P::WIN; ++o) prm.window[o] = a.window[o];
+  if (SPEC != SK_CPLX) {
+    // the (M x frames) staging tile aliases the exchange buffer
+    if (a.bank.n_mels <= 0 || a.bank.n_mels * (P::FT + 1) > P::Y_WORDS) {
       if (err) *err = "n_mels out of range for this plan";
       return B2A_E_BAD_ARG;
     }
   }
-  const size_t smem = sizeof(float) * size_t((a.out_mode == OUT_COMPLEX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(sizeof(float) * size_t(P::R0_WORDS_CPLX + P::Y_WORDS)));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
-    attr_set = true;
-  }
+  const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS + P::N +
+                                             2 * P::N2 * (P::H1 - 1));
+  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   const long long nblocks = (long long)prm.tiles_per_clip * a.batch;
   if (nblocks <= 0 || nblocks > 0x7fffffffLL) {
     if (err) *err = "grid too large";
     return B2A_E_BAD_ARG;
   }
-  cudaError_t e;
   if (a.whisper_norm) {
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
-  frontend_kernel<P><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
@@ -575,9 +589,17 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
 
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400) return launch_plan<Plan400>(a, st, launches, err);
-  if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) return launch_plan<Plan512>(a, st, launches, err);
-  if (err) *err = "no FFT plan built for this (n_fft, hop, win_length)";
+  const int spec = a.out_mode == OUT_COMPLEX ? SK_CPLX : (a.spec_mode == SPEC_POWER ? SK_POWER : SK_MAG);
+  if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE) {
+    if (spec == SK_POWER) return launch_plan<Plan400, PRE_NONE, SK_POWER>(a, st, launches, err);
+    if (spec == SK_MAG) return launch_plan<Plan400, PRE_NONE, SK_MAG>(a, st, launches, err);
+    return launch_plan<Plan400, PRE_NONE, SK_CPLX>(a, st, launches, err);
+  }
+  if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) {
+    if (a.pre_mode == PRE_KALDI && spec == SK_POWER) return launch_plan<Plan512, PRE_KALDI, SK_POWER>(a, st, launches, err);
+    if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
+  }
+  if (err) *err = "no FFT plan built for this (n_fft, hop, win_length, mode)";
   return B2A_E_UNSUPPORTED;
 }
 

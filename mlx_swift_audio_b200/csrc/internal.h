@@ -33,9 +33,7 @@ enum OutMode {
 };
 
 struct DeviceBank {  // sparse filterbank in device memory
-  const int* start = nullptr;
-  const int* count = nullptr;
-  const int* offset = nullptr;
+  const int* desc = nullptr;      // 4 ints per filter: first bin, number of bins, offset into weights, 0
   const float* weights = nullptr;
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
