@@ -28,6 +28,7 @@ struct BankStorage {
   SparseBank host;
   int* desc = nullptr;
   float* weights = nullptr;
+  float* bins = nullptr;
 };
 
 constexpr int kSlots = 3;  // chunk ring depth of the host pipeline
@@ -114,11 +115,18 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
     if (!bs.host.weights.empty())
       if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
+    if (bs.host.two_adjacent) {
+      if ((e = cudaMalloc(&bs.bins, sizeof(float) * bs.host.bins.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
+      if ((e = cudaMemcpy(bs.bins, bs.host.bins.data(), sizeof(float) * bs.host.bins.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return cu(c, e, "bank upload");
+    }
     it = c->banks.emplace(key, std::move(bs)).first;
   }
   const BankStorage& bs = it->second;
   out->desc = bs.desc;
   out->weights = bs.weights;
+  out->bins = bs.bins;
+  out->host_count = bs.host.count.data();
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
   return B2A_OK;
@@ -371,6 +379,7 @@ int b2a_ctx_destroy(b2a_ctx* c) {
   for (auto& kv : c->banks) {
     cudaFree(kv.second.desc);
     cudaFree(kv.second.weights);
+    if (kv.second.bins) cudaFree(kv.second.bins);
   }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);

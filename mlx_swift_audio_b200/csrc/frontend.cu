@@ -89,7 +89,9 @@ struct FrontendParams {
   float log_floor, post_sub, post_div;
   const int4* fb_desc;    // per filter: (first bin, number of bins, offset into fb_w, 0)
   const float* fb_w;
-  int n_mels;
+  const float4* fb_bins;  // per bin: (w_lo, w_hi, bits(m_lo), 0): bin feeds filters m_lo and m_lo+1; null = generic path
+  int n_mels, n_bins_used;
+  int chunk_m[P::NWARPS + 1];  // filters [chunk_m[w], chunk_m[w+1]) belong to warp w
   float* out;
   int* clip_max;
   float* tile_min;
@@ -159,7 +161,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float* s_r0 = smem;                                       // PCM tile, later the spectrum tile
   float2* s_y = reinterpret_cast<float2*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL));
   float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
-  float* s_wt = smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS;  // window, item-major [n2][n1]
+  float4* s_bins = reinterpret_cast<float4*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS);  // per-bin mel weights
+  float* s_wt = reinterpret_cast<float*>(s_bins) + (cplx ? 0 : 4 * P::NBINS);  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   __shared__ int s_tile_min;
 
@@ -179,6 +182,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   {
     const float2* __restrict__ tw = TwTable<P>::get();
     for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) s_tw[i] = tw[i];
+    if (!cplx && prm.fb_bins != nullptr)
+      for (int i = tid; i < prm.n_bins_used; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_bins + i);
   }
 
   // ---- 1. stage the tile's PCM: coalesced scalar loads, skewed rows (pitch HOP+1) -------------------
@@ -303,33 +308,74 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   const int M = prm.n_mels;
   float lmax = -3.0e38f, vmin = 3.0e38f;
   {
-    const int4* __restrict__ fdesc = prm.fb_desc;
-    const float* __restrict__ fw = prm.fb_w;
     const int log_mode = prm.log_mode;
     const float log_floor = prm.log_floor;
-    float* __restrict__ out_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
-    for (int m = warp; m < M; m += NW) {
-      const int4 d = __ldg(fdesc + m);
-      const float* __restrict__ w = fw + d.z;
-      const float* pp = s_r0 + d.x * FT + lane;
-      float acc = 0.0f;
-#pragma unroll 4
-      for (int i = 0; i < d.y; ++i) acc = fmaf(__ldg(w + i), pp[i * FT], acc);
-      float v = acc;
+    const bool wnorm = prm.whisper_norm != 0, post = prm.post_affine != 0, out_mt = prm.out_mode == OUT_MT;
+    float* __restrict__ dst_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
+    auto emit = [&](int m, float v) {
       // log2-based logs: MUFU.LG2 is accurate to ~1e-7 absolute on the log value, far inside the 1e-4 tolerance
       if (log_mode == LOG_LOG10) v = __log2f(fmaxf(v, log_floor)) * 0.30102999566398120f;
       else if (log_mode == LOG_LN) v = __log2f(fmaxf(v, log_floor)) * 0.69314718055994531f;
       else if (log_mode == LOG_DB20) v = __log2f(fmaxf(v, log_floor)) * 6.0205999132796239f;
-      if (prm.whisper_norm) {
-        if (frame_ok) lmax = fmaxf(lmax, v);
+      if (wnorm) {
+        lmax = fmaxf(lmax, frame_ok ? v : -3.0e38f);
         v = (v + 4.0f) * 0.25f;
-        if (frame_ok) vmin = fminf(vmin, v);
+        vmin = fminf(vmin, frame_ok ? v : 3.0e38f);
       }
-      if (prm.post_affine) v = (v - prm.post_sub) / prm.post_div;
-      if (prm.out_mode == OUT_MT) {
-        if (frame_ok) out_mt[(long long)m * prm.n_frames] = v;
+      if (post) v = (v - prm.post_sub) / prm.post_div;
+      if (out_mt) {
+        if (frame_ok) dst_mt[(long long)m * prm.n_frames] = v;
       } else {
         s_o[m * OP + lane] = v;
+      }
+    };
+    const int ma = prm.chunk_m[warp], mb = prm.chunk_m[warp + 1];
+    const int4* __restrict__ fdesc = prm.fb_desc;
+    if (prm.fb_bins != nullptr) {
+      // bin-major: every spectrum bin is read once and feeds two running accumulators (a bin touches at most
+      // two adjacent triangular filters); filters are emitted as the bin index passes their last bin
+      if (ma < mb) {
+        const int k_begin = __ldg(fdesc + ma).x;
+        const int4 dl = __ldg(fdesc + (mb - 1));
+        const int k_end = dl.x + dl.y;  // one past the last bin of the chunk's last filter
+        int cur = ma;
+        float acc0 = 0.0f, acc1 = 0.0f;
+        const float* pp = s_r0 + lane;
+        for (int k = k_begin; k < k_end; ++k) {
+          const float4 t = s_bins[k];
+          const int ml = __float_as_int(t.z);
+          const float pk = pp[k * FT];
+          while (cur < ml) {  // warp-uniform
+            emit(cur, acc0);
+            acc0 = acc1;
+            acc1 = 0.0f;
+            ++cur;
+          }
+          // cur >= ml; cur == ml + 1 only at the start of a chunk whose first bin is shared with filter ma - 1
+          if (cur == ml) {
+            acc0 = fmaf(t.x, pk, acc0);
+            acc1 = fmaf(t.y, pk, acc1);
+          } else {
+            acc0 = fmaf(t.y, pk, acc0);
+          }
+        }
+        while (cur < mb) {
+          emit(cur, acc0);
+          acc0 = acc1;
+          acc1 = 0.0f;
+          ++cur;
+        }
+      }
+    } else {
+      // generic path: arbitrary filterbank, one short loop per filter
+      const float* __restrict__ fw = prm.fb_w;
+      for (int m = ma; m < mb; ++m) {
+        const int4 d = __ldg(fdesc + m);
+        const float* __restrict__ w = fw + d.z;
+        const float* pp = s_r0 + d.x * FT + lane;
+        float acc = 0.0f;
+        for (int i = 0; i < d.y; ++i) acc = fmaf(__ldg(w + i), pp[i * FT], acc);
+        emit(m, acc);
       }
     }
   }
@@ -544,7 +590,24 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.lfr_rows = a.lfr_rows;
   prm.fb_desc = reinterpret_cast<const int4*>(a.bank.desc);
   prm.fb_w = a.bank.weights;
+  prm.fb_bins = reinterpret_cast<const float4*>(a.bank.bins);
   prm.n_mels = a.bank.n_mels;
+  prm.n_bins_used = a.bank.n_bins_used;
+  for (int w = 0; w <= P::NWARPS; ++w) prm.chunk_m[w] = 0;
+  if (SPEC != SK_CPLX) {
+    // balance (bins + per-filter emit cost) across the warps
+    const int M = a.bank.n_mels;
+    long long total = 0;
+    for (int m = 0; m < M; ++m) total += a.bank.host_count[m] + 4;
+    long long run = 0;
+    int w = 1;
+    for (int m = 0; m < M && w < P::NWARPS; ++m) {
+      run += a.bank.host_count[m] + 4;
+      while (w < P::NWARPS && run * P::NWARPS >= total * w) prm.chunk_m[w++] = m + 1;
+    }
+    for (; w <= P::NWARPS; ++w) prm.chunk_m[w] = M;
+    prm.chunk_m[P::NWARPS] = M;
+  }
   prm.out = a.out;
   prm.clip_max = a.clip_max;
   prm.tile_min = a.tile_min;
@@ -564,7 +627,9 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     }
   }
   const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS + P::N +
-                                             2 * P::N2 * (P::H1 - 1));
+                                             2 * P::N2 * (P::H1 - 1) + (SPEC == SK_CPLX ? 0 : 4 * P::NBINS));
+  static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 2) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0,
+                "shared-memory tables must stay 16-byte (bins, window rows) / 8-byte (twiddles) aligned");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   const long long nblocks = (long long)prm.tiles_per_clip * a.batch;

@@ -6,6 +6,7 @@
 // helper it names; paths are relative to the reference's package/ directory.
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "../../include/b200audio.h"
@@ -188,6 +189,43 @@ void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major
       if (last > sb.max_bin) sb.max_bin = last;
     }
   }
+  // per-bin form: bin k feeds filters m_lo(k) and m_lo(k)+1 only, with m_lo non-decreasing in k.
+  // (True for every triangular bank of the reference; checked by reconstructing the dense bank.)
+  auto at = [&](int m, int k) -> float {
+    if (m < 0 || m >= n_mels) return 0.0f;
+    return bin_major ? bank[size_t(k) * n_mels + m] : bank[size_t(m) * n_bins + k];
+  };
+  sb.two_adjacent = true;
+  sb.bins.assign(size_t(n_bins) * 4, 0.0f);
+  int prev_m = 0;
+  for (int k = 0; k < n_bins && sb.two_adjacent; ++k) {
+    int first = -1, last = -1;
+    for (int m = 0; m < n_mels; ++m)
+      if (at(m, k) != 0.0f) {
+        if (first < 0) first = m;
+        last = m;
+      }
+    int m_lo = prev_m;
+    if (first >= 0) {
+      if (last - first > 1) { sb.two_adjacent = false; break; }
+      if (last == first && first - 1 >= prev_m) m_lo = first - 1;  // single filter: keep the lower one open as long as possible
+      else m_lo = first;
+      if (m_lo < prev_m) { sb.two_adjacent = false; break; }
+    }
+    for (int m = 0; m < n_mels; ++m) {  // reconstruction check
+      const float want = at(m, k);
+      const float got = m == m_lo ? at(m_lo, k) : (m == m_lo + 1 ? at(m_lo + 1, k) : 0.0f);
+      if (want != got) { sb.two_adjacent = false; break; }
+    }
+    sb.bins[size_t(k) * 4 + 0] = at(m_lo, k);
+    sb.bins[size_t(k) * 4 + 1] = at(m_lo + 1, k);
+    float fbits;
+    static_assert(sizeof(int) == sizeof(float), "bit cast");
+    memcpy(&fbits, &m_lo, sizeof(float));
+    sb.bins[size_t(k) * 4 + 2] = fbits;
+    prev_m = m_lo;
+  }
+  if (!sb.two_adjacent) sb.bins.clear();
 }
 
 }  // namespace b2a

@@ -11,6 +11,8 @@ struct SparseBank {
   int n_mels = 0, n_bins = 0, max_bin = -1;
   std::vector<int> start, count, offset;  // per filter: first bin, number of bins, offset into weights
   std::vector<float> weights;
+  bool two_adjacent = false;       // every bin feeds at most two filters, and they are adjacent (m, m+1), m non-decreasing
+  std::vector<float> bins;         // then: 4 floats per bin (w_lo, w_hi, bits(m_lo), 0)
 };
 int make_window(int kind, int length, float* out);
 void hann_periodic_via_hanning(int n, std::vector<float>& w);
@@ -35,6 +37,8 @@ enum OutMode {
 struct DeviceBank {  // sparse filterbank in device memory
   const int* desc = nullptr;      // 4 ints per filter: first bin, number of bins, offset into weights, 0
   const float* weights = nullptr;
+  const float* bins = nullptr;    // 4 floats per bin (w_lo, w_hi, bits(m_lo), 0) or null when a bin feeds > 2 filters
+  const int* host_count = nullptr;  // HOST copy of the per-filter bin counts (work balancing)
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
 };

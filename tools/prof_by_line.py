@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""Join an `ncu --page source --print-source sass --csv` dump with nvdisasm line info and aggregate
+executed instructions / stall samples per CUDA source line (and per file).
+
+usage: prof_by_line.py <src_sass.csv> <nvdisasm -g -c output> <kernel substring> [top]
+"""
+import csv, re, sys
+from collections import Counter, defaultdict
+
+src_csv, dis, kname = sys.argv[1], sys.argv[2], sys.argv[3]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+rows = list(csv.reader(open(src_csv)))
+hdr = rows[1]; data = rows[2:]
+ia = hdr.index('Source'); ie = hdr.index('Instructions Executed'); isamp = hdr.index('# Samples')
+
+# parse nvdisasm: find the function section, then sequence of (line info, instruction)
+lines = open(dis).read().split('\n')
+in_fn = False; cur = ('?', 0); seq = []
+stack_re = re.compile(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?')
+for ln in lines:
+    if ln.startswith('.text.') or ln.strip().startswith('.section'):
+        in_fn = (kname in ln)
+        continue
+    if not in_fn:
+        continue
+    m = stack_re.search(ln)
+    if m:
+        f = m.group(1).split('/')[-1]
+        cur = (f, int(m.group(2)), (m.group(3) or '').split('/')[-1], int(m.group(4) or 0))
+        continue
+    m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', ln)
+    if m:
+        seq.append((cur, m.group(2)))
+print('sass instr in dis:', len(seq), ' in ncu:', len(data))
+n = min(len(seq), len(data))
+by_line = Counter(); by_line_s = Counter(); by_file = Counter()
+for i in range(n):
+    cur, _ = seq[i]
+    ex = int(data[i][ie]); sm = int(data[i][isamp])
+    # attribute inlined codelet code to the outermost frontend.cu line if available
+    key = (cur[0], cur[1]) if cur[0] != 'codelets.h' or not cur[2] else (cur[2], cur[3])
+    by_line[key] += ex; by_line_s[key] += sm; by_file[cur[0]] += ex
+tot = sum(by_line.values())
+print('by file:', {k: round(100 * v / tot, 1) for k, v in by_file.items()})
+for key, v in by_line.most_common(top):
+    print(f"{key[0]:16s}:{key[1]:5d}  {100*v/tot:5.1f}%  samples {by_line_s[key]}")
