@@ -127,6 +127,7 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
   out->weights = bs.weights;
   out->bins = bs.bins;
   out->host_count = bs.host.count.data();
+  out->host_start = bs.host.start.data();
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
   return B2A_OK;

@@ -23,6 +23,7 @@
 //     kernel rewrites only tiles whose minimum is below the clamp threshold.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 #include <utility>
@@ -67,7 +68,7 @@ struct Plan {
   static constexpr int P_WORDS_REAL = NBINS * FT;
   static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
   static constexpr int R0_WORDS_REAL = PCM_WORDS > P_WORDS_REAL ? PCM_WORDS : P_WORDS_REAL;
-  static constexpr int R0_WORDS_CPLX = PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX;
+  static constexpr int R0_WORDS_CPLX = ((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3;
   static_assert(N1 * N2 == N, "N = N1*N2");
   static_assert(HOP % 4 == 0 && TS % 4 == 0, "float4 staging");
   static_assert(FT == 32, "lane == frame");
@@ -92,6 +93,7 @@ struct FrontendParams {
   const float4* fb_bins;  // per bin: (w_lo, w_hi, bits(m_lo), 0): bin feeds filters m_lo and m_lo+1; null = generic path
   int n_mels, n_bins_used;
   int chunk_m[P::NWARPS + 1];  // filters [chunk_m[w], chunk_m[w+1]) belong to warp w
+  int chunk_k0[P::NWARPS], chunk_k1[P::NWARPS];  // bins [k0, k1) cover every non-zero weight of the chunk's filters
   float* out;
   int* clip_max;
   float* tile_min;
@@ -152,6 +154,58 @@ B2A_DEV void load_item(const float* lane_pcm, int n2, float mu, const float* wro
   ((in[I] = load_sample<P, PRE, I>(lane_pcm, n2, mu) * wrow[I]), ...);
 }
 
+B2A_DEV float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Bin-major sparse mel projection for one warp's chunk of filters [ma, mb): every spectrum bin is read once
+// and feeds two running accumulators (a bin touches at most two adjacent triangular filters, s_bins[k] =
+// (w_lo, w_hi, bits(m_lo))); filters are emitted as the bin index passes their last bin.  LANE == FRAME.
+// Output goes either straight to the (M, T') global layout (coalesced over lanes) or to the [m][frame]
+// staging tile.  log2-based logs: MUFU.LG2 is accurate to ~1e-7 absolute on the log value.
+template <int FT, int OP, int LOGM, bool WNORM, bool MT>
+B2A_DEV void mel_chunk(const float* __restrict__ pp, const float4* __restrict__ s_bins, int k_begin, int k_end, int ma, int mb,
+                       float log_floor, bool frame_ok, float* __restrict__ so, float* __restrict__ dm, long long nfr,
+                       float& lmax, float& vmin) {
+  constexpr float kLog = LOGM == LOG_LOG10 ? 0.30102999566398120f : (LOGM == LOG_LN ? 0.69314718055994531f : 6.0205999132796239f);
+  int cur = __float_as_int(s_bins[k_begin].z);  // ma or ma - 1 (first bin shared with the previous filter)
+  so += cur * OP;
+  dm += cur * nfr;
+  float acc0 = 0.0f, acc1 = 0.0f;
+  auto emit = [&]() {
+    if (cur >= ma) {
+      float v = acc0;
+      if (LOGM != LOG_NONE) v = lg2_ftz(fmaxf(v, log_floor)) * kLog;
+      if (WNORM) {
+        lmax = fmaxf(lmax, v);
+        v = (v + 4.0f) * 0.25f;
+        vmin = fminf(vmin, v);
+      }
+      if (MT) {
+        if (frame_ok) *dm = v;
+      } else {
+        *so = v;
+      }
+    }
+    so += OP;
+    dm += nfr;
+    acc0 = acc1;
+    acc1 = 0.0f;
+    ++cur;
+  };
+  for (int k = k_begin; k < k_end; ++k) {
+    const float4 t = s_bins[k];
+    const float pk = pp[k * FT];
+    const int ml = __float_as_int(t.z);
+    while (cur < ml) emit();  // warp-uniform
+    acc0 = fmaf(t.x, pk, acc0);
+    acc1 = fmaf(t.y, pk, acc1);
+  }
+  while (cur < mb) emit();
+}
+
 template <class P, int PRE, int SPEC>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
@@ -186,14 +240,26 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       for (int i = tid; i < prm.n_bins_used; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_bins + i);
   }
 
-  // ---- 1. stage the tile's PCM: coalesced scalar loads, skewed rows (pitch HOP+1) -------------------
+  // ---- 1. stage the tile's PCM: one skewed row (HOP samples, pitch HOP+1) per warp iteration, coalesced ----
   {
     const long long p0 = f0 * HOP;
     const long long j0 = p0 - prm.pad_left;
+    constexpr int NROWS = (P::TS + HOP - 1) / HOP, CPR = (HOP + 31) / 32;
     if (j0 >= 0 && j0 + P::TS <= prm.n_samples) {
       const float* __restrict__ src = xc + j0;
-#pragma unroll 4
-      for (int s = tid; s < P::TS; s += P::NTHREADS) s_r0[s + s / HOP] = __ldg(src + s);
+      for (int r = warp; r < NROWS; r += NW) {
+        float v[CPR];
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+          const int col = j * 32 + lane;
+          v[j] = (col < HOP && r * HOP + col < P::TS) ? __ldg(src + r * HOP + col) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+          const int col = j * 32 + lane;
+          if (col < HOP && r * HOP + col < P::TS) s_r0[r * P::PITCH + col] = v[j];
+        }
+      }
     } else {
       for (int s = tid; s < P::TS; s += P::NTHREADS)
         s_r0[s + s / HOP] = fetch_padded(xc, p0 + s, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode);
@@ -205,7 +271,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float mu = 0.0f;
   if (PRE == PRE_KALDI) {
     float part = 0.0f;
-    for (int o = warp; o < WIN; o += NW) part += s_r0[lane * P::PITCH + o + o / HOP];
+    const int fl = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
+    for (int o = warp; o < WIN; o += NW) part += s_r0[fl * P::PITCH + o + o / HOP];
     s_o[warp * FT + lane] = part;
     __syncthreads();
     float tot = 0.0f;
@@ -215,9 +282,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     __syncthreads();
   }
 
+  // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
+  // not a conflict), so that per-tile max / min need no lane masking.
+  const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
+  const int flane = lane < rows ? lane : rows - 1;
+
   // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
   {
-    const float* lane_pcm = s_r0 + lane * P::PITCH;
+    const float* lane_pcm = s_r0 + flane * P::PITCH;
     for (int n2 = warp; n2 < N2; n2 += NW) {
       float wrow[N1];
 #pragma unroll
@@ -289,8 +361,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   }
   __syncthreads();
 
-  const bool frame_ok = f0 + lane < prm.n_frames;
-  const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
+  const bool frame_ok = lane < rows;
 
   // ---- 4a. plain stft(): write the complex spectrum tile ------------------------------------------
   if (cplx) {
@@ -310,72 +381,51 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   {
     const int log_mode = prm.log_mode;
     const float log_floor = prm.log_floor;
-    const bool wnorm = prm.whisper_norm != 0, post = prm.post_affine != 0, out_mt = prm.out_mode == OUT_MT;
-    float* __restrict__ dst_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
-    auto emit = [&](int m, float v) {
-      // log2-based logs: MUFU.LG2 is accurate to ~1e-7 absolute on the log value, far inside the 1e-4 tolerance
-      if (log_mode == LOG_LOG10) v = __log2f(fmaxf(v, log_floor)) * 0.30102999566398120f;
-      else if (log_mode == LOG_LN) v = __log2f(fmaxf(v, log_floor)) * 0.69314718055994531f;
-      else if (log_mode == LOG_DB20) v = __log2f(fmaxf(v, log_floor)) * 6.0205999132796239f;
-      if (wnorm) {
-        lmax = fmaxf(lmax, frame_ok ? v : -3.0e38f);
-        v = (v + 4.0f) * 0.25f;
-        vmin = fminf(vmin, frame_ok ? v : 3.0e38f);
-      }
-      if (post) v = (v - prm.post_sub) / prm.post_div;
-      if (out_mt) {
-        if (frame_ok) dst_mt[(long long)m * prm.n_frames] = v;
-      } else {
-        s_o[m * OP + lane] = v;
-      }
-    };
+    const bool wnorm = prm.whisper_norm != 0, out_mt = prm.out_mode == OUT_MT;
     const int ma = prm.chunk_m[warp], mb = prm.chunk_m[warp + 1];
     const int4* __restrict__ fdesc = prm.fb_desc;
-    if (prm.fb_bins != nullptr) {
-      // bin-major: every spectrum bin is read once and feeds two running accumulators (a bin touches at most
-      // two adjacent triangular filters); filters are emitted as the bin index passes their last bin
-      if (ma < mb) {
-        const int k_begin = __ldg(fdesc + ma).x;
-        const int4 dl = __ldg(fdesc + (mb - 1));
-        const int k_end = dl.x + dl.y;  // one past the last bin of the chunk's last filter
-        int cur = ma;
-        float acc0 = 0.0f, acc1 = 0.0f;
+    float* __restrict__ dst_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
+    if (ma < mb) {
+      if (prm.fb_bins != nullptr && !prm.post_affine && log_mode != LOG_DB20) {
+        const int k_begin = prm.chunk_k0[warp], k_end = prm.chunk_k1[warp];
         const float* pp = s_r0 + lane;
-        for (int k = k_begin; k < k_end; ++k) {
-          const float4 t = s_bins[k];
-          const int ml = __float_as_int(t.z);
-          const float pk = pp[k * FT];
-          while (cur < ml) {  // warp-uniform
-            emit(cur, acc0);
-            acc0 = acc1;
-            acc1 = 0.0f;
-            ++cur;
+        float* so = s_o + lane;
+        const long long nfr = prm.n_frames;
+#define B2A_MEL(LOGM, WN, MT_) mel_chunk<FT, OP, LOGM, WN, MT_>(pp, s_bins, k_begin, k_end, ma, mb, log_floor, frame_ok, so, dst_mt, nfr, lmax, vmin)
+        if (wnorm) {  // Whisper / S3Tokenizer: log10 + per-clip clamp bookkeeping
+          if (out_mt) B2A_MEL(LOG_LOG10, true, true); else B2A_MEL(LOG_LOG10, true, false);
+        } else if (log_mode == LOG_LN) {
+          if (out_mt) B2A_MEL(LOG_LN, false, true); else B2A_MEL(LOG_LN, false, false);
+        } else if (log_mode == LOG_LOG10) {
+          if (out_mt) B2A_MEL(LOG_LOG10, false, true); else B2A_MEL(LOG_LOG10, false, false);
+        } else {
+          if (out_mt) B2A_MEL(LOG_NONE, false, true); else B2A_MEL(LOG_NONE, false, false);
+        }
+#undef B2A_MEL
+      } else {
+        // generic path: arbitrary filterbank / rarely used epilogues, one short loop per filter
+        const float* __restrict__ fw = prm.fb_w;
+        for (int m = ma; m < mb; ++m) {
+          const int4 d = __ldg(fdesc + m);
+          const float* __restrict__ w = fw + d.z;
+          const float* pp = s_r0 + d.x * FT + lane;
+          float v = 0.0f;
+          for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
+          if (log_mode == LOG_LOG10) v = lg2_ftz(fmaxf(v, log_floor)) * 0.30102999566398120f;
+          else if (log_mode == LOG_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
+          else if (log_mode == LOG_DB20) v = lg2_ftz(fmaxf(v, log_floor)) * 6.0205999132796239f;
+          if (wnorm) {
+            lmax = fmaxf(lmax, v);
+            v = (v + 4.0f) * 0.25f;
+            vmin = fminf(vmin, v);
           }
-          // cur >= ml; cur == ml + 1 only at the start of a chunk whose first bin is shared with filter ma - 1
-          if (cur == ml) {
-            acc0 = fmaf(t.x, pk, acc0);
-            acc1 = fmaf(t.y, pk, acc1);
+          if (prm.post_affine) v = (v - prm.post_sub) / prm.post_div;
+          if (out_mt) {
+            if (frame_ok) dst_mt[(long long)m * prm.n_frames] = v;
           } else {
-            acc0 = fmaf(t.y, pk, acc0);
+            s_o[m * OP + lane] = v;
           }
         }
-        while (cur < mb) {
-          emit(cur, acc0);
-          acc0 = acc1;
-          acc1 = 0.0f;
-          ++cur;
-        }
-      }
-    } else {
-      // generic path: arbitrary filterbank, one short loop per filter
-      const float* __restrict__ fw = prm.fb_w;
-      for (int m = ma; m < mb; ++m) {
-        const int4 d = __ldg(fdesc + m);
-        const float* __restrict__ w = fw + d.z;
-        const float* pp = s_r0 + d.x * FT + lane;
-        float acc = 0.0f;
-        for (int i = 0; i < d.y; ++i) acc = fmaf(__ldg(w + i), pp[i * FT], acc);
-        emit(m, acc);
       }
     }
   }
@@ -398,14 +448,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   // ---- 5. coalesced store of the staged (M x frames) tile as (frames, M) rows ------------------------
   if (prm.out_mode == OUT_TM) {
     float* __restrict__ dst = prm.out + clip * prm.out_clip_stride + f0 * M;
-    const int total = rows * M;
-    int r = tid / M, c = tid - r * M;
-    const int dr = P::NTHREADS / M, dc = P::NTHREADS - dr * M;
-    for (int e = tid; e < total; e += P::NTHREADS) {
-      dst[e] = s_o[c * OP + r];
-      r += dr;
-      c += dc;
-      if (c >= M) { c -= M; r += 1; }
+    for (int r = warp; r < rows; r += NW) {
+      float* d = dst + r * M;
+      const float* sr = s_o + r;
+      for (int c = lane; c < M; c += 32) d[c] = sr[c * OP];
     }
   } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
     const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
@@ -607,6 +653,17 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     }
     for (; w <= P::NWARPS; ++w) prm.chunk_m[w] = M;
     prm.chunk_m[P::NWARPS] = M;
+    for (int c = 0; c < P::NWARPS; ++c) {
+      int k0 = 1 << 30, k1 = 0;
+      for (int m = prm.chunk_m[c]; m < prm.chunk_m[c + 1]; ++m)
+        if (a.bank.host_count[m] > 0) {
+          k0 = std::min(k0, a.bank.host_start[m]);
+          k1 = std::max(k1, a.bank.host_start[m] + a.bank.host_count[m]);
+        }
+      if (k1 == 0) k0 = 0;  // no weights at all: nothing to accumulate, the flush emits zeros
+      prm.chunk_k0[c] = k0;
+      prm.chunk_k1[c] = k1;
+    }
   }
   prm.out = a.out;
   prm.clip_max = a.clip_max;

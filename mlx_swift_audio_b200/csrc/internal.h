@@ -38,7 +38,8 @@ struct DeviceBank {  // sparse filterbank in device memory
   const int* desc = nullptr;      // 4 ints per filter: first bin, number of bins, offset into weights, 0
   const float* weights = nullptr;
   const float* bins = nullptr;    // 4 floats per bin (w_lo, w_hi, bits(m_lo), 0) or null when a bin feeds > 2 filters
-  const int* host_count = nullptr;  // HOST copy of the per-filter bin counts (work balancing)
+  const int* host_count = nullptr;  // HOST copies of the per-filter bin counts / first bins (work balancing)
+  const int* host_start = nullptr;
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
 };

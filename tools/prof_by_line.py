@@ -44,3 +44,17 @@ tot = sum(by_line.values())
 print('by file:', {k: round(100 * v / tot, 1) for k, v in by_file.items()})
 for key, v in by_line.most_common(top):
     print(f"{key[0]:16s}:{key[1]:5d}  {100*v/tot:5.1f}%  samples {by_line_s[key]}")
+
+# ---- opcode mix per source-line range (frontend.cu outermost line) ----
+if len(sys.argv) > 5:
+    ranges = [tuple(map(int, r.split('-'))) for r in sys.argv[5].split(',')]
+    for lo, hi in ranges:
+        c = Counter(); t = 0
+        for i in range(n):
+            cur, ins = seq[i]
+            key = (cur[0], cur[1]) if cur[0] != 'codelets.h' or not cur[2] else (cur[2], cur[3])
+            if key[0] == 'frontend.cu' and lo <= key[1] <= hi:
+                tk = ins.split()
+                op = tk[1] if tk[0].startswith('@') else tk[0]
+                c[op.split('.')[0]] += int(data[i][ie]); t += int(data[i][ie])
+        print(f"lines {lo}-{hi}: {100*t/tot:5.1f}% of all; per tile {t/24000:.0f}: " + ', '.join(f"{k}:{v/24000:.0f}" for k, v in c.most_common(14)))
