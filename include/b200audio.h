@@ -208,6 +208,11 @@ B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const 
                                     int64_t n_frames, int filter_length, int hop_length, int win_length,
                                     float* out, int space);
 
+/* Test hook (host only, no GPU): compiles a dense filterbank ((n_mels, n_bins), or (n_bins, n_mels) when
+ * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
+ * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */
+B2A_API int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out);
+
 /* ---------------------------------------------------------------------------------------
  * instrumentation used by bench.py (device-side timing of the last call's kernels)
  * ------------------------------------------------------------------------------------- */

@@ -28,7 +28,7 @@ struct BankStorage {
   SparseBank host;
   int* desc = nullptr;
   float* weights = nullptr;
-  float* bins = nullptr;
+  float* steps = nullptr;
 };
 
 constexpr int kSlots = 3;  // chunk ring depth of the host pipeline
@@ -115,9 +115,10 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
     if (!bs.host.weights.empty())
       if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
-    if (bs.host.two_adjacent) {
-      if ((e = cudaMalloc(&bs.bins, sizeof(float) * bs.host.bins.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
-      if ((e = cudaMemcpy(bs.bins, bs.host.bins.data(), sizeof(float) * bs.host.bins.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+    build_mel_program(dense.data(), n_mels, n_bins, bin_major, kFrontendFrameTile, kFrontendFrameTile + 1, kFrontendWarps, bs.host);
+    if (!bs.host.steps.empty()) {
+      if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
+      if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
     }
     it = c->banks.emplace(key, std::move(bs)).first;
@@ -125,9 +126,10 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
   const BankStorage& bs = it->second;
   out->desc = bs.desc;
   out->weights = bs.weights;
-  out->bins = bs.bins;
-  out->host_count = bs.host.count.data();
-  out->host_start = bs.host.start.data();
+  out->steps = bs.steps;
+  out->n_steps = int(bs.host.steps.size() / 4);
+  out->host_chunk_m = bs.host.chunk_m.data();
+  out->host_chunk_s = bs.host.chunk_s.data();
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
   return B2A_OK;
@@ -380,7 +382,7 @@ int b2a_ctx_destroy(b2a_ctx* c) {
   for (auto& kv : c->banks) {
     cudaFree(kv.second.desc);
     cudaFree(kv.second.weights);
-    if (kv.second.bins) cudaFree(kv.second.bins);
+    if (kv.second.steps) cudaFree(kv.second.steps);
   }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);

@@ -65,6 +65,7 @@ struct Plan {
   static constexpr int PCM_WORDS = ((TS - 1) + (TS - 1) / HOP + 1 + 3) & ~3;
   static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT
   static constexpr int P_PITCH = FT + 1;
+  static constexpr int MAX_STEPS = NBINS + 256;    // mel step program: one step per bin (+ chunk-boundary repeats, empty filters)
   static constexpr int P_WORDS_REAL = NBINS * FT;
   static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
   static constexpr int R0_WORDS_REAL = PCM_WORDS > P_WORDS_REAL ? PCM_WORDS : P_WORDS_REAL;
@@ -90,10 +91,10 @@ struct FrontendParams {
   float log_floor, post_sub, post_div;
   const int4* fb_desc;    // per filter: (first bin, number of bins, offset into fb_w, 0)
   const float* fb_w;
-  const float4* fb_bins;  // per bin: (w_lo, w_hi, bits(m_lo), 0): bin feeds filters m_lo and m_lo+1; null = generic path
-  int n_mels, n_bins_used;
+  const float4* fb_steps; // mel step program (see mel_steps); null = generic per-filter path
+  int n_mels, n_steps;
   int chunk_m[P::NWARPS + 1];  // filters [chunk_m[w], chunk_m[w+1]) belong to warp w
-  int chunk_k0[P::NWARPS], chunk_k1[P::NWARPS];  // bins [k0, k1) cover every non-zero weight of the chunk's filters
+  int chunk_s[P::NWARPS + 1];  // steps   [chunk_s[w], chunk_s[w+1]) of the program belong to warp w
   float* out;
   int* clip_max;
   float* tile_min;
@@ -160,50 +161,39 @@ B2A_DEV float lg2_ftz(float x) {
   return y;
 }
 
-// Bin-major sparse mel projection for one warp's chunk of filters [ma, mb): every spectrum bin is read once
-// and feeds two running accumulators (a bin touches at most two adjacent triangular filters, s_bins[k] =
-// (w_lo, w_hi, bits(m_lo))); filters are emitted as the bin index passes their last bin.  LANE == FRAME.
-// Output goes either straight to the (M, T') global layout (coalesced over lanes) or to the [m][frame]
-// staging tile.  log2-based logs: MUFU.LG2 is accurate to ~1e-7 absolute on the log value.
-template <int FT, int OP, int LOGM, bool WNORM, bool MT>
-B2A_DEV void mel_chunk(const float* __restrict__ pp, const float4* __restrict__ s_bins, int k_begin, int k_end, int ma, int mb,
-                       float log_floor, bool frame_ok, float* __restrict__ so, float* __restrict__ dm, long long nfr,
-                       float& lmax, float& vmin) {
-  constexpr float kLog = LOGM == LOG_LOG10 ? 0.30102999566398120f : (LOGM == LOG_LN ? 0.69314718055994531f : 6.0205999132796239f);
-  int cur = __float_as_int(s_bins[k_begin].z);  // ma or ma - 1 (first bin shared with the previous filter)
-  so += cur * OP;
-  dm += cur * nfr;
+// Branch-free sparse mel projection for one warp's chunk of filters.  The filterbank is compiled on the host
+// into a "step program": step = (w_lo, w_hi, byte offset of the spectrum bin, emit stride).  Each step adds
+// w_lo*P to the open filter and w_hi*P to the next one; a non-zero emit stride stores the open filter's sum
+// to the [m][frame] staging tile, advances the output pointer and shifts the accumulators.  A bin touches at
+// most two adjacent triangular filters; filters without bins get a zero-weight step.  LANE == FRAME.
+B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* __restrict__ so) {
   float acc0 = 0.0f, acc1 = 0.0f;
-  auto emit = [&]() {
-    if (cur >= ma) {
-      float v = acc0;
-      if (LOGM != LOG_NONE) v = lg2_ftz(fmaxf(v, log_floor)) * kLog;
-      if (WNORM) {
-        lmax = fmaxf(lmax, v);
-        v = (v + 4.0f) * 0.25f;
-        vmin = fminf(vmin, v);
-      }
-      if (MT) {
-        if (frame_ok) *dm = v;
-      } else {
-        *so = v;
-      }
-    }
-    so += OP;
-    dm += nfr;
-    acc0 = acc1;
-    acc1 = 0.0f;
-    ++cur;
-  };
-  for (int k = k_begin; k < k_end; ++k) {
-    const float4 t = s_bins[k];
-    const float pk = pp[k * FT];
-    const int ml = __float_as_int(t.z);
-    while (cur < ml) emit();  // warp-uniform
+#pragma unroll 2
+  for (int s = s0; s < s1; ++s) {
+    const float4 t = steps[s];
+    const float pk = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(p_lane) + __float_as_int(t.z));
+    const int adv = __float_as_int(t.w);
     acc0 = fmaf(t.x, pk, acc0);
     acc1 = fmaf(t.y, pk, acc1);
+    const bool e = adv != 0;
+    if (e) *so = acc0;
+    so = reinterpret_cast<float*>(reinterpret_cast<char*>(so) + adv);
+    acc0 = e ? acc1 : acc0;
+    acc1 = e ? 0.0f : acc1;
   }
-  while (cur < mb) emit();
+}
+
+template <int LOGM, bool WNORM>
+B2A_DEV float mel_post(float v, float log_floor, float& lmax, float& vmin) {
+  // log2-based logs: MUFU.LG2 is accurate to ~1e-7 absolute on the log value, far inside the 1e-4 tolerance
+  constexpr float kLog = LOGM == LOG_LOG10 ? 0.30102999566398120f : (LOGM == LOG_LN ? 0.69314718055994531f : 6.0205999132796239f);
+  if (LOGM != LOG_NONE) v = lg2_ftz(fmaxf(v, log_floor)) * kLog;
+  if (WNORM) {
+    lmax = fmaxf(lmax, v);
+    v = (v + 4.0f) * 0.25f;
+    vmin = fminf(vmin, v);
+  }
+  return v;
 }
 
 template <class P, int PRE, int SPEC>
@@ -216,7 +206,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float2* s_y = reinterpret_cast<float2*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL));
   float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
   float4* s_bins = reinterpret_cast<float4*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS);  // per-bin mel weights
-  float* s_wt = reinterpret_cast<float*>(s_bins) + (cplx ? 0 : 4 * P::NBINS);  // window, item-major [n2][n1]
+  float* s_wt = reinterpret_cast<float*>(s_bins) + (cplx ? 0 : 4 * P::MAX_STEPS);  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   __shared__ int s_tile_min;
 
@@ -236,8 +226,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   {
     const float2* __restrict__ tw = TwTable<P>::get();
     for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) s_tw[i] = tw[i];
-    if (!cplx && prm.fb_bins != nullptr)
-      for (int i = tid; i < prm.n_bins_used; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_bins + i);
+    if (!cplx && prm.fb_steps != nullptr)
+      for (int i = tid; i < prm.n_steps; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_steps + i);
   }
 
   // ---- 1. stage the tile's PCM: one skewed row (HOP samples, pitch HOP+1) per warp iteration, coalesced ----
@@ -375,56 +365,89 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     return;
   }
 
-  // ---- 4b. sparse mel projection + log / floor / scale ---------------------------------------------
+  // ---- 4b. sparse mel projection into the [m][frame] staging tile ------------------------------------
   const int M = prm.n_mels;
+  {
+    const int ma = prm.chunk_m[warp], mb = prm.chunk_m[warp + 1];
+    if (prm.fb_steps != nullptr) {
+      mel_steps(s_r0 + lane, s_bins, prm.chunk_s[warp], prm.chunk_s[warp + 1], s_o + ma * OP + lane);
+    } else {
+      // generic path: arbitrary filterbank, one short loop per filter
+      const int4* __restrict__ fdesc = prm.fb_desc;
+      const float* __restrict__ fw = prm.fb_w;
+      for (int m = ma; m < mb; ++m) {
+        const int4 d = __ldg(fdesc + m);
+        const float* __restrict__ w = fw + d.z;
+        const float* pp = s_r0 + d.x * FT + lane;
+        float v = 0.0f;
+        for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
+        s_o[m * OP + lane] = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. log / floor / scale fused into the coalesced store of the staged tile -----------------------
   float lmax = -3.0e38f, vmin = 3.0e38f;
   {
     const int log_mode = prm.log_mode;
     const float log_floor = prm.log_floor;
-    const bool wnorm = prm.whisper_norm != 0, out_mt = prm.out_mode == OUT_MT;
-    const int ma = prm.chunk_m[warp], mb = prm.chunk_m[warp + 1];
-    const int4* __restrict__ fdesc = prm.fb_desc;
-    float* __restrict__ dst_mt = prm.out + clip * prm.out_clip_stride + f0 + lane;
-    if (ma < mb) {
-      if (prm.fb_bins != nullptr && !prm.post_affine && log_mode != LOG_DB20) {
-        const int k_begin = prm.chunk_k0[warp], k_end = prm.chunk_k1[warp];
-        const float* pp = s_r0 + lane;
-        float* so = s_o + lane;
-        const long long nfr = prm.n_frames;
-#define B2A_MEL(LOGM, WN, MT_) mel_chunk<FT, OP, LOGM, WN, MT_>(pp, s_bins, k_begin, k_end, ma, mb, log_floor, frame_ok, so, dst_mt, nfr, lmax, vmin)
-        if (wnorm) {  // Whisper / S3Tokenizer: log10 + per-clip clamp bookkeeping
-          if (out_mt) B2A_MEL(LOG_LOG10, true, true); else B2A_MEL(LOG_LOG10, true, false);
-        } else if (log_mode == LOG_LN) {
-          if (out_mt) B2A_MEL(LOG_LN, false, true); else B2A_MEL(LOG_LN, false, false);
-        } else if (log_mode == LOG_LOG10) {
-          if (out_mt) B2A_MEL(LOG_LOG10, false, true); else B2A_MEL(LOG_LOG10, false, false);
-        } else {
-          if (out_mt) B2A_MEL(LOG_NONE, false, true); else B2A_MEL(LOG_NONE, false, false);
+    const bool wnorm = prm.whisper_norm != 0;
+    float* __restrict__ dst = prm.out + clip * prm.out_clip_stride;
+    if (prm.out_mode == OUT_TM) {
+      // (T', M) rows: lanes run over m
+      dst += f0 * M;
+      auto store_tm = [&](auto post) {
+        for (int r = warp; r < rows; r += NW) {
+          float* d = dst + r * M;
+          const float* sr = s_o + r;
+          for (int c = lane; c < M; c += 32) d[c] = post(sr[c * OP]);
         }
-#undef B2A_MEL
-      } else {
-        // generic path: arbitrary filterbank / rarely used epilogues, one short loop per filter
-        const float* __restrict__ fw = prm.fb_w;
-        for (int m = ma; m < mb; ++m) {
-          const int4 d = __ldg(fdesc + m);
-          const float* __restrict__ w = fw + d.z;
-          const float* pp = s_r0 + d.x * FT + lane;
-          float v = 0.0f;
-          for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
-          if (log_mode == LOG_LOG10) v = lg2_ftz(fmaxf(v, log_floor)) * 0.30102999566398120f;
-          else if (log_mode == LOG_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
-          else if (log_mode == LOG_DB20) v = lg2_ftz(fmaxf(v, log_floor)) * 6.0205999132796239f;
-          if (wnorm) {
-            lmax = fmaxf(lmax, v);
-            v = (v + 4.0f) * 0.25f;
-            vmin = fminf(vmin, v);
-          }
-          if (prm.post_affine) v = (v - prm.post_sub) / prm.post_div;
-          if (out_mt) {
-            if (frame_ok) dst_mt[(long long)m * prm.n_frames] = v;
-          } else {
-            s_o[m * OP + lane] = v;
-          }
+      };
+      if (wnorm) store_tm([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
+      else if (log_mode == LOG_LN) store_tm([&](float v) { return mel_post<LOG_LN, false>(v, log_floor, lmax, vmin); });
+      else if (log_mode == LOG_LOG10) store_tm([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
+      else if (log_mode == LOG_DB20) store_tm([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
+      else store_tm([&](float v) { return v; });
+    } else if (prm.out_mode == OUT_MT) {
+      // (M, T') rows: lanes run over frames
+      dst += f0 + lane;
+      const long long nfr = prm.n_frames;
+      const bool post = prm.post_affine != 0;
+      auto store_mt = [&](auto fn) {
+        for (int m = warp; m < M; m += NW) {
+          float v = fn(s_o[m * OP + lane]);
+          if (post) v = (v - prm.post_sub) / prm.post_div;
+          if (frame_ok) dst[m * nfr] = v;
+        }
+      };
+      if (wnorm) store_mt([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
+      else if (log_mode == LOG_LN) store_mt([&](float v) { return mel_post<LOG_LN, false>(v, log_floor, lmax, vmin); });
+      else if (log_mode == LOG_LOG10) store_mt([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
+      else if (log_mode == LOG_DB20) store_mt([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
+      else store_mt([&](float v) { return v; });
+    } else {  // OUT_LFR: out[i][j*M + m] = ln(feat)[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
+      const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
+      const long long T = prm.n_frames;
+      long long i_lo = (f0 + left - (lm - 1)) / ln;
+      if (f0 + left - (lm - 1) < 0) i_lo = 0;
+      long long i_hi = (f0 + rows - 1 + left) / ln;
+      if (f0 + rows >= T) i_hi = prm.lfr_rows - 1;
+      if (i_hi > prm.lfr_rows - 1) i_hi = prm.lfr_rows - 1;
+      const int nseg = int(i_hi - i_lo + 1) * lm;
+      for (int sg = warp; sg < nseg; sg += NW) {
+        const long long i = i_lo + sg / lm;
+        const int j = sg % lm;
+        long long t = i * ln + j - left;
+        t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+        if (t < f0 || t >= f0 + rows) continue;
+        const float* sr = s_o + int(t - f0);
+        float* d = dst + (i * lm + j) * (long long)M;
+        for (int c = lane; c < M; c += 32) {
+          float v = sr[c * OP];
+          if (log_mode == LOG_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
+          else if (log_mode == LOG_LOG10) v = lg2_ftz(fmaxf(v, log_floor)) * 0.30102999566398120f;
+          d[c] = v;
         }
       }
     }
@@ -439,40 +462,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       atomicMax(prm.clip_max + clip, enc_ordered(lmax));
       atomicMin(&s_tile_min, enc_ordered(vmin));
     }
-  }
-  if (prm.out_mode == OUT_MT && !prm.whisper_norm) return;
-  __syncthreads();
-  if (prm.whisper_norm && tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
-  if (prm.out_mode == OUT_MT) return;
-
-  // ---- 5. coalesced store of the staged (M x frames) tile as (frames, M) rows ------------------------
-  if (prm.out_mode == OUT_TM) {
-    float* __restrict__ dst = prm.out + clip * prm.out_clip_stride + f0 * M;
-    for (int r = warp; r < rows; r += NW) {
-      float* d = dst + r * M;
-      const float* sr = s_o + r;
-      for (int c = lane; c < M; c += 32) d[c] = sr[c * OP];
-    }
-  } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
-    const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
-    const long long T = prm.n_frames;
-    long long i_lo = (f0 + left - (lm - 1)) / ln;
-    if (f0 + left - (lm - 1) < 0) i_lo = 0;
-    long long i_hi = (f0 + rows - 1 + left) / ln;
-    if (f0 + rows >= T) i_hi = prm.lfr_rows - 1;
-    if (i_hi > prm.lfr_rows - 1) i_hi = prm.lfr_rows - 1;
-    const int nseg = int(i_hi - i_lo + 1) * lm;
-    float* __restrict__ dst = prm.out + clip * prm.out_clip_stride;
-    for (int sg = warp; sg < nseg; sg += NW) {
-      const long long i = i_lo + sg / lm;
-      const int j = sg % lm;
-      long long t = i * ln + j - left;
-      t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-      if (t < f0 || t >= f0 + rows) continue;
-      const float* s = s_o + int(t - f0);
-      float* d = dst + (i * lm + j) * (long long)M;
-      for (int c = lane; c < M; c += 32) d[c] = s[c * OP];
-    }
+    __syncthreads();
+    if (tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
   }
 }
 
@@ -636,33 +627,20 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.lfr_rows = a.lfr_rows;
   prm.fb_desc = reinterpret_cast<const int4*>(a.bank.desc);
   prm.fb_w = a.bank.weights;
-  prm.fb_bins = reinterpret_cast<const float4*>(a.bank.bins);
+  prm.fb_steps = reinterpret_cast<const float4*>(a.bank.steps);
   prm.n_mels = a.bank.n_mels;
-  prm.n_bins_used = a.bank.n_bins_used;
-  for (int w = 0; w <= P::NWARPS; ++w) prm.chunk_m[w] = 0;
+  prm.n_steps = a.bank.n_steps;
+  for (int w = 0; w <= P::NWARPS; ++w) prm.chunk_m[w] = prm.chunk_s[w] = 0;
   if (SPEC != SK_CPLX) {
-    // balance (bins + per-filter emit cost) across the warps
     const int M = a.bank.n_mels;
-    long long total = 0;
-    for (int m = 0; m < M; ++m) total += a.bank.host_count[m] + 4;
-    long long run = 0;
-    int w = 1;
-    for (int m = 0; m < M && w < P::NWARPS; ++m) {
-      run += a.bank.host_count[m] + 4;
-      while (w < P::NWARPS && run * P::NWARPS >= total * w) prm.chunk_m[w++] = m + 1;
-    }
-    for (; w <= P::NWARPS; ++w) prm.chunk_m[w] = M;
-    prm.chunk_m[P::NWARPS] = M;
-    for (int c = 0; c < P::NWARPS; ++c) {
-      int k0 = 1 << 30, k1 = 0;
-      for (int m = prm.chunk_m[c]; m < prm.chunk_m[c + 1]; ++m)
-        if (a.bank.host_count[m] > 0) {
-          k0 = std::min(k0, a.bank.host_start[m]);
-          k1 = std::max(k1, a.bank.host_start[m] + a.bank.host_count[m]);
-        }
-      if (k1 == 0) k0 = 0;  // no weights at all: nothing to accumulate, the flush emits zeros
-      prm.chunk_k0[c] = k0;
-      prm.chunk_k1[c] = k1;
+    static_assert(P::NWARPS == kFrontendWarps && P::FT == kFrontendFrameTile, "mel programs are compiled for this CTA shape");
+    if (a.bank.steps != nullptr) {
+      for (int w = 0; w <= P::NWARPS; ++w) {
+        prm.chunk_m[w] = a.bank.host_chunk_m[w];
+        prm.chunk_s[w] = a.bank.host_chunk_s[w];
+      }
+    } else {
+      for (int w = 0; w <= P::NWARPS; ++w) prm.chunk_m[w] = int((long long)M * w / P::NWARPS);
     }
   }
   prm.out = a.out;
@@ -678,13 +656,13 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   for (int o = 0; o < P::WIN; ++o) prm.window[o] = a.window[o];
   if (SPEC != SK_CPLX) {
     // the (M x frames) staging tile aliases the exchange buffer
-    if (a.bank.n_mels <= 0 || a.bank.n_mels * (P::FT + 1) > P::Y_WORDS) {
+    if (a.bank.n_mels <= 0 || a.bank.n_mels * (P::FT + 1) > P::Y_WORDS || a.bank.n_steps > P::MAX_STEPS) {
       if (err) *err = "n_mels out of range for this plan";
       return B2A_E_BAD_ARG;
     }
   }
   const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS + P::N +
-                                             2 * P::N2 * (P::H1 - 1) + (SPEC == SK_CPLX ? 0 : 4 * P::NBINS));
+                                             2 * P::N2 * (P::H1 - 1) + (SPEC == SK_CPLX ? 0 : 4 * P::MAX_STEPS));
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 2) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0,
                 "shared-memory tables must stay 16-byte (bins, window rows) / 8-byte (twiddles) aligned");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -4,6 +4,7 @@
 //
 // Each function restates (does not copy) the fp32 scalar arithmetic of the reference
 // helper it names; paths are relative to the reference's package/ directory.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -196,7 +197,7 @@ void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major
     return bin_major ? bank[size_t(k) * n_mels + m] : bank[size_t(m) * n_bins + k];
   };
   sb.two_adjacent = true;
-  sb.bins.assign(size_t(n_bins) * 4, 0.0f);
+  sb.bin_mlo.assign(n_bins, 0);
   int prev_m = 0;
   for (int k = 0; k < n_bins && sb.two_adjacent; ++k) {
     int first = -1, last = -1;
@@ -217,15 +218,74 @@ void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major
       const float got = m == m_lo ? at(m_lo, k) : (m == m_lo + 1 ? at(m_lo + 1, k) : 0.0f);
       if (want != got) { sb.two_adjacent = false; break; }
     }
-    sb.bins[size_t(k) * 4 + 0] = at(m_lo, k);
-    sb.bins[size_t(k) * 4 + 1] = at(m_lo + 1, k);
-    float fbits;
-    static_assert(sizeof(int) == sizeof(float), "bit cast");
-    memcpy(&fbits, &m_lo, sizeof(float));
-    sb.bins[size_t(k) * 4 + 2] = fbits;
+    sb.bin_mlo[k] = m_lo;
     prev_m = m_lo;
   }
-  if (!sb.two_adjacent) sb.bins.clear();
+  if (!sb.two_adjacent) sb.bin_mlo.clear();
+}
+
+// Compiles the bank into the frontend kernel's mel "step program" (see mel_steps in frontend.cu) for
+// n_chunks warps.  Filter m owns the bins whose lower filter is m (m_lo == m); each of its steps adds
+// W[m][k]*P[k] to the open accumulator and W[m+1][k]*P[k] to the next one, and its last step emits.  A chunk
+// (the filters of one warp) starts with zero-emit steps for the bins its first filter shares with the
+// previous chunk's last filter.  Chunks are cut at filter boundaries, balanced by step count.
+void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
+                       SparseBank& sb) {
+  sb.steps.clear();
+  sb.chunk_m.assign(n_chunks + 1, 0);
+  sb.chunk_s.assign(n_chunks + 1, 0);
+  if (!sb.two_adjacent) return;
+  auto at = [&](int m, int k) -> float {
+    if (m < 0 || m >= n_mels) return 0.0f;
+    return bin_major ? bank[size_t(k) * n_mels + m] : bank[size_t(m) * n_bins + k];
+  };
+  auto bits = [](int v) {
+    float f;
+    memcpy(&f, &v, sizeof(float));
+    return f;
+  };
+  std::vector<std::vector<int>> own(n_mels);  // bins whose lower filter is m
+  for (int k = 0; k < n_bins; ++k) {
+    const int m = sb.bin_mlo[k];
+    if (m >= 0 && m < n_mels && (at(m, k) != 0.0f || at(m + 1, k) != 0.0f)) own[m].push_back(k);
+  }
+  // balance: cost of a filter = number of its steps (at least one: the emit)
+  long long total = 0;
+  for (int m = 0; m < n_mels; ++m) total += std::max<size_t>(own[m].size(), 1);
+  {
+    long long run = 0;
+    int w = 1;
+    for (int m = 0; m < n_mels && w < n_chunks; ++m) {
+      run += std::max<size_t>(own[m].size(), 1);
+      while (w < n_chunks && run * n_chunks >= total * w) sb.chunk_m[w++] = m + 1;
+    }
+    for (; w <= n_chunks; ++w) sb.chunk_m[w] = n_mels;
+    sb.chunk_m[n_chunks] = n_mels;
+  }
+  auto push = [&](float wlo, float whi, int k, bool emit) {
+    sb.steps.push_back(wlo);
+    sb.steps.push_back(whi);
+    sb.steps.push_back(bits(k * frame_tile * int(sizeof(float))));
+    sb.steps.push_back(bits(emit ? out_pitch * int(sizeof(float)) : 0));
+  };
+  for (int c = 0; c < n_chunks; ++c) {
+    sb.chunk_s[c] = int(sb.steps.size() / 4);
+    const int ma = sb.chunk_m[c], mb = sb.chunk_m[c + 1];
+    if (ma < mb && ma > 0)
+      for (int k : own[ma - 1])
+        if (at(ma, k) != 0.0f) push(at(ma, k), 0.0f, k, false);
+    for (int m = ma; m < mb; ++m) {
+      if (own[m].empty()) {
+        push(0.0f, 0.0f, 0, true);
+        continue;
+      }
+      for (size_t i = 0; i < own[m].size(); ++i) {
+        const int k = own[m][i];
+        push(at(m, k), at(m + 1, k), k, i + 1 == own[m].size());
+      }
+    }
+  }
+  sb.chunk_s[n_chunks] = int(sb.steps.size() / 4);
 }
 
 }  // namespace b2a
@@ -325,5 +385,36 @@ void b2a_voice_enc_config_default(b2a_voice_enc_config* c) {  // Config/Chatterb
 }
 
 const char* b2a_version(void) { return "b200audio 0.1 (sm_100a)"; }
+
+// Test hook (host only): compiles `bank` into the frontend kernel's mel step program and interprets it on the
+// host exactly as the kernel does (per-chunk accumulators, emit-on-flag), for one spectrum `p` (n_bins).
+// Returns the number of steps, or -1 when the bank is not of the two-adjacent-filters form.
+int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out) {
+  b2a::SparseBank sb;
+  b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, 1, b2a::kFrontendWarps, sb);
+  if (sb.steps.empty()) return -1;
+  for (int c = 0; c < b2a::kFrontendWarps; ++c) {
+    float acc0 = 0.0f, acc1 = 0.0f;
+    float* so = out + sb.chunk_m[c];
+    for (int s = sb.chunk_s[c]; s < sb.chunk_s[c + 1]; ++s) {
+      const float* t = &sb.steps[size_t(s) * 4];
+      int off, adv;
+      memcpy(&off, t + 2, 4);
+      memcpy(&adv, t + 3, 4);
+      const float pk = p[off / 4];
+      acc0 = fmaf(t[0], pk, acc0);
+      acc1 = fmaf(t[1], pk, acc1);
+      if (adv != 0) {
+        *so = acc0;
+        so += adv / 4;
+        acc0 = acc1;
+        acc1 = 0.0f;
+      }
+    }
+    if (so != out + sb.chunk_m[c + 1]) return -2;  // every filter of the chunk must have been emitted exactly once
+  }
+  return int(sb.steps.size() / 4);
+}
 
 }  // extern "C"

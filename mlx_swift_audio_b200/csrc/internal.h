@@ -12,7 +12,9 @@ struct SparseBank {
   std::vector<int> start, count, offset;  // per filter: first bin, number of bins, offset into weights
   std::vector<float> weights;
   bool two_adjacent = false;       // every bin feeds at most two filters, and they are adjacent (m, m+1), m non-decreasing
-  std::vector<float> bins;         // then: 4 floats per bin (w_lo, w_hi, bits(m_lo), 0)
+  std::vector<int> bin_mlo;        // then: m_lo per bin
+  std::vector<float> steps;        // mel step program for the frontend kernel (see build_mel_program), 4 floats per step
+  std::vector<int> chunk_m, chunk_s;  // per warp: first filter / first step (n_chunks + 1 entries)
 };
 int make_window(int kind, int length, float* out);
 void hann_periodic_via_hanning(int n, std::vector<float>& w);
@@ -21,6 +23,10 @@ int mel_filters_funasr(int sample_rate, int n_fft, int n_mels, float* out);
 int mel_filters_htk_int(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out);
 int64_t reflect_pad_index(int64_t i, int64_t n, int64_t pad);
 void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major, SparseBank& sb);
+void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
+                       SparseBank& sb);
+constexpr int kFrontendWarps = 9;      // warps per CTA of every frontend plan (mel programs are chunked for it)
+constexpr int kFrontendFrameTile = 32; // frames per CTA (lane == frame)
 
 // ---- fused STFT -> (power | magnitude) -> mel -> log front-end (frontend.cu) -----------------
 enum PadMode { PAD_NONE = 0, PAD_REFLECT = 1, PAD_ZERO = 2 };
@@ -37,9 +43,10 @@ enum OutMode {
 struct DeviceBank {  // sparse filterbank in device memory
   const int* desc = nullptr;      // 4 ints per filter: first bin, number of bins, offset into weights, 0
   const float* weights = nullptr;
-  const float* bins = nullptr;    // 4 floats per bin (w_lo, w_hi, bits(m_lo), 0) or null when a bin feeds > 2 filters
-  const int* host_count = nullptr;  // HOST copies of the per-filter bin counts / first bins (work balancing)
-  const int* host_start = nullptr;
+  const float* steps = nullptr;   // mel step program, 4 floats per step (w_lo, w_hi, bits(bin*FT*4), bits(emit stride)); null = generic path
+  int n_steps = 0;
+  const int* host_chunk_m = nullptr;  // HOST: per-warp first filter / first step of the program (kFrontendWarps + 1 entries)
+  const int* host_chunk_s = nullptr;
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
 };
