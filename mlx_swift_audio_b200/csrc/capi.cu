@@ -91,8 +91,11 @@ const std::vector<float>& cached_window(b2a_ctx* c, const std::string& key, cons
   return c->windows.emplace(key, std::move(w)).first->second;
 }
 
-int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool bin_major,
+int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int n_bins, bool bin_major,
                 const std::function<int(float*)>& make_dense, DeviceBank* out) {
+  int frame_tile = 32, n_chunks = 9;
+  frontend_plan_shape(n_fft, &frame_tile, &n_chunks);
+  const std::string key = key0 + "_ft" + std::to_string(frame_tile) + "_c" + std::to_string(n_chunks);
   auto it = c->banks.find(key);
   if (it == c->banks.end()) {
     std::vector<float> dense(size_t(n_mels) * n_bins);
@@ -115,7 +118,7 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
     if (!bs.host.weights.empty())
       if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
-    build_mel_program(dense.data(), n_mels, n_bins, bin_major, kFrontendFrameTile, kFrontendFrameTile + 1, kFrontendWarps, bs.host);
+    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, frame_tile + 1, n_chunks, bs.host);
     if (!bs.host.steps.empty()) {
       if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
       if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -128,6 +131,8 @@ int cached_bank(b2a_ctx* c, const std::string& key, int n_mels, int n_bins, bool
   out->weights = bs.weights;
   out->steps = bs.steps;
   out->n_steps = int(bs.host.steps.size() / 4);
+  out->n_chunks = n_chunks;
+  out->frame_tile = frame_tile;
   out->host_chunk_m = bs.host.chunk_m.data();
   out->host_chunk_s = bs.host.chunk_s.data();
   out->n_mels = n_mels;
@@ -296,7 +301,7 @@ std::string key_of(const char* tag, std::initializer_list<double> v) {
 
 int slaney_bank(b2a_ctx* c, int sr, int n_fft, int n_mels, float fmin, float fmax, DeviceBank* out) {
   if (n_mels <= 0) return fail(c, B2A_E_BAD_ARG, "n_mels must be positive");
-  return cached_bank(c, key_of("slaney", {double(sr), double(n_fft), double(n_mels), fmin, fmax}), n_mels, n_fft / 2 + 1, false,
+  return cached_bank(c, key_of("slaney", {double(sr), double(n_fft), double(n_mels), fmin, fmax}), n_fft, n_mels, n_fft / 2 + 1, false,
                      [&](float* d) { return mel_filters_slaney(sr, n_fft, n_mels, fmin, fmax, d); }, out);
 }
 
@@ -487,7 +492,7 @@ static int funasr_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t 
   if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
   Preset p;
   p.window = &window_of(c, B2A_WIN_HAMMING, 400, 400, false);
-  if ((rc = cached_bank(c, key_of("funasr", {16000.0, 400.0, double(n_mels)}), n_mels, 200, false,
+  if ((rc = cached_bank(c, key_of("funasr", {16000.0, 400.0, double(n_mels)}), 400, n_mels, 200, false,
                         [&](float* d) { return mel_filters_funasr(16000, 400, n_mels, d); }, &p.bank)) != B2A_OK)
     return rc;
   p.log_mode = LOG_LN;
@@ -587,7 +592,7 @@ int b2a_kaldi_fbank_campplus(b2a_ctx* c, const float* audio, int64_t batch, int6
   p.pad_left = 0;
   p.pre_mode = PRE_KALDI;
   if ((rc = cached_bank(c, key_of("htkint", {double(sample_rate), double(n_fft), double(num_mel_bins), 20.0, double(sample_rate) / 2}),
-                        num_mel_bins, n_fft / 2 + 1, true,
+                        n_fft, num_mel_bins, n_fft / 2 + 1, true,
                         [&](float* d) { return mel_filters_htk_int(sample_rate, n_fft, num_mel_bins, 20.0f, float(sample_rate) / 2, d); },
                         &p.bank)) != B2A_OK)
     return rc;

@@ -65,21 +65,26 @@ struct Plan {
   static constexpr int PCM_WORDS = ((TS - 1) + (TS - 1) / HOP + 1 + 3) & ~3;
   static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT
   static constexpr int P_PITCH = FT + 1;
-  static constexpr int MAX_STEPS = NBINS + 256;    // mel step program: one step per bin (+ chunk-boundary repeats, empty filters)
+  static constexpr bool CPLX_DIRECT = (N / 2 + 1) * (FT + 1) * 2 * 4 > 64 * 1024;  // complex tile would not fit: stft() stores directly
+  static constexpr int MAX_STEPS = NBINS + 32 * NWARPS * (32 / FT);    // mel step program: one step per bin (+ chunk-boundary repeats, empty filters)
   static constexpr int P_WORDS_REAL = NBINS * FT;
   static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
   static constexpr int R0_WORDS_REAL = PCM_WORDS > P_WORDS_REAL ? PCM_WORDS : P_WORDS_REAL;
-  static constexpr int R0_WORDS_CPLX = ((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3;
+  static constexpr int R0_WORDS_CPLX = CPLX_DIRECT ? ((PCM_WORDS + 3) & ~3) : (((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3);
+  static constexpr int SUB = 32 / FT;               // a warp covers FT frames x SUB items (lane = sub * FT + frame)
+  static constexpr int NCHUNK = NWARPS * SUB;       // mel-program chunks
   static_assert(N1 * N2 == N, "N = N1*N2");
-  static_assert(HOP % 4 == 0 && TS % 4 == 0, "float4 staging");
-  static_assert(FT == 32, "lane == frame");
+  static_assert(FT == 32 || FT == 16, "lane == (item, frame)");
 };
 using Plan400 = Plan<400, 400, 16, 25, 160, 32, 9, 2>;
 using Plan512 = Plan<512, 400, 16, 32, 160, 32, 9, 2>;
+// n_fft 1920 (S3Gen 24 kHz mel): the exchange buffer only fits 16 frames, so half-warps take different items
+using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1>;
 
 template <class P> struct TwTable;
 template <> struct TwTable<Plan400> { static B2A_DEV const float2* get() { return c_tw400; } };
 template <> struct TwTable<Plan512> { static B2A_DEV const float2* get() { return c_tw512; } };
+template <> struct TwTable<Plan1920> { static B2A_DEV const float2* get() { return c_tw1920; } };
 
 enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
 
@@ -93,8 +98,8 @@ struct FrontendParams {
   const float* fb_w;
   const float4* fb_steps; // mel step program (see mel_steps); null = generic per-filter path
   int n_mels, n_steps;
-  int chunk_m[P::NWARPS + 1];  // filters [chunk_m[w], chunk_m[w+1]) belong to warp w
-  int chunk_s[P::NWARPS + 1];  // steps   [chunk_s[w], chunk_s[w+1]) of the program belong to warp w
+  int chunk_m[P::NCHUNK + 1];  // filters [chunk_m[c], chunk_m[c+1]) belong to chunk c = warp * SUB + sub
+  int chunk_s[P::NCHUNK + 1];  // steps   [chunk_s[c], chunk_s[c+1]) of the program belong to chunk c
   float* out;
   int* clip_max;
   float* tile_min;
@@ -210,7 +215,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   __shared__ int s_tile_min;
 
+  constexpr int SUB = P::SUB, NIT = NW * SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
   const int tile = blockIdx.x % prm.tiles_per_clip;
   const long long clip = blockIdx.x / prm.tiles_per_clip;
   const long long f0 = (long long)tile * FT;
@@ -261,13 +268,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float mu = 0.0f;
   if (PRE == PRE_KALDI) {
     float part = 0.0f;
-    const int fl = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
-    for (int o = warp; o < WIN; o += NW) part += s_r0[fl * P::PITCH + o + o / HOP];
-    s_o[warp * FT + lane] = part;
+    static_assert(PRE != PRE_KALDI || SUB == 1, "Kaldi pre-processing is built for 32-frame tiles");
+    const int fk = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
+    for (int o = warp; o < WIN; o += NW) part += s_r0[fk * P::PITCH + o + o / HOP];
+    s_o[warp * FT + fl] = part;
     __syncthreads();
     float tot = 0.0f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) tot += s_o[w * FT + lane];
+    for (int w = 0; w < NW; ++w) tot += s_o[w * FT + fl];
     mu = tot / float(WIN);
     __syncthreads();
   }
@@ -275,12 +283,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
   // not a conflict), so that per-tile max / min need no lane masking.
   const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
-  const int flane = lane < rows ? lane : rows - 1;
+  const int flane = fl < rows ? fl : rows - 1;
 
   // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
   {
     const float* lane_pcm = s_r0 + flane * P::PITCH;
-    for (int n2 = warp; n2 < N2; n2 += NW) {
+    for (int n2 = wsub; n2 < N2; n2 += NIT) {
       float wrow[N1];
 #pragma unroll
       for (int q = 0; q < N1 / 4; ++q) {
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       load_item<P, PRE>(lane_pcm, n2, mu, wrow, in, std::make_integer_sequence<int, N1>{});
       float yr[H1 + 1], yi[H1 + 1];
       rdft(in, yr, yi);
-      float2* yb = s_y + n2 * FT + lane;
+      float2* yb = s_y + n2 * FT + fl;
       yb[0] = make_float2(yr[0], yr[H1]);
       const float2* twr = s_tw + n2 * (H1 - 1);
 #pragma unroll
@@ -307,17 +315,22 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   {
     auto put = [&](int k, float re, float im) {
       if (cplx) {
-        reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + lane] = make_float2(re, im);
+        if (P::CPLX_DIRECT) {
+          // tile too large for a staged complex spectrum: store straight to (T', F) global memory
+          if (fl < rows) reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride)[(f0 + fl) * P::NBINS + k] = make_float2(re, im);
+        } else {
+          reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + fl] = make_float2(re, im);
+        }
       } else {
         const float pw = re * re + im * im;
-        s_r0[k * FT + lane] = SPEC == SK_POWER ? pw : sqrtf(pw);
+        s_r0[k * FT + fl] = SPEC == SK_POWER ? pw : sqrtf(pw);
       }
     };
-    for (int it = warp; it <= H1; it += NW) {
+    for (int it = wsub; it <= H1; it += NIT) {
       if (it == 0) {
         float in[N2];
 #pragma unroll
-        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + lane].x;
+        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].x;
         float ur[N2 / 2 + 1], ui[N2 / 2 + 1];
         rdft(in, ur, ui);
 #pragma unroll
@@ -325,14 +338,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       } else if (it == H1) {
         float in[N2];
 #pragma unroll
-        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + lane].y;
+        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].y;
         float ur[(N2 - 1) / 2 + 1], ui[(N2 - 1) / 2 + 1];
         rdftodd(in, ur, ui);
 #pragma unroll
         for (int k2 = 0; k2 <= (N2 - 1) / 2; ++k2) put(H1 + N1 * k2, ur[k2], ui[k2]);
       } else {
         float xr[N2], xi[N2], ur[N2], ui[N2];
-        const float2* yb = s_y + it * N2 * FT + lane;
+        const float2* yb = s_y + it * N2 * FT + fl;
 #pragma unroll
         for (int n2 = 0; n2 < N2; ++n2) {
           const float2 v = yb[n2 * FT];
@@ -351,10 +364,11 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   }
   __syncthreads();
 
-  const bool frame_ok = lane < rows;
+  const bool frame_ok = fl < rows;
 
   // ---- 4a. plain stft(): write the complex spectrum tile ------------------------------------------
   if (cplx) {
+    if (P::CPLX_DIRECT) return;
     const int nb = P::NBINS;
     float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride) + f0 * nb;
     const float2* sp = reinterpret_cast<const float2*>(s_r0);
@@ -368,9 +382,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   // ---- 4b. sparse mel projection into the [m][frame] staging tile ------------------------------------
   const int M = prm.n_mels;
   {
-    const int ma = prm.chunk_m[warp], mb = prm.chunk_m[warp + 1];
+    const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
     if (prm.fb_steps != nullptr) {
-      mel_steps(s_r0 + lane, s_bins, prm.chunk_s[warp], prm.chunk_s[warp + 1], s_o + ma * OP + lane);
+      mel_steps(s_r0 + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
     } else {
       // generic path: arbitrary filterbank, one short loop per filter
       const int4* __restrict__ fdesc = prm.fb_desc;
@@ -378,10 +392,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       for (int m = ma; m < mb; ++m) {
         const int4 d = __ldg(fdesc + m);
         const float* __restrict__ w = fw + d.z;
-        const float* pp = s_r0 + d.x * FT + lane;
+        const float* pp = s_r0 + d.x * FT + fl;
         float v = 0.0f;
         for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
-        s_o[m * OP + lane] = v;
+        s_o[m * OP + fl] = v;
       }
     }
   }
@@ -411,12 +425,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       else store_tm([&](float v) { return v; });
     } else if (prm.out_mode == OUT_MT) {
       // (M, T') rows: lanes run over frames
-      dst += f0 + lane;
+      dst += f0 + fl;
       const long long nfr = prm.n_frames;
       const bool post = prm.post_affine != 0;
       auto store_mt = [&](auto fn) {
-        for (int m = warp; m < M; m += NW) {
-          float v = fn(s_o[m * OP + lane]);
+        for (int m = wsub; m < M; m += NIT) {
+          float v = fn(s_o[m * OP + fl]);
           if (post) v = (v - prm.post_sub) / prm.post_div;
           if (frame_ok) dst[m * nfr] = v;
         }
@@ -595,12 +609,24 @@ int init_frontend_tables(std::string* err) {
 }
 
 bool frontend_plan_exists(int n_fft, int hop, int win_len) {
-  return (n_fft == 400 && hop == 160 && win_len == 400) || (n_fft == 512 && hop == 160 && win_len == 400);
+  return (n_fft == 400 && hop == 160 && win_len == 400) || (n_fft == 512 && hop == 160 && win_len == 400) ||
+         (n_fft == 1920 && hop == 480 && win_len == 1920);
+}
+
+void frontend_plan_shape(int n_fft, int* frame_tile, int* n_chunks) {
+  if (n_fft == 1920) {
+    *frame_tile = Plan1920::FT;
+    *n_chunks = Plan1920::NCHUNK;
+  } else {
+    *frame_tile = Plan400::FT;
+    *n_chunks = Plan400::NCHUNK;
+  }
 }
 
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
-  (void)n_fft;
-  return int((n_frames + 31) / 32);
+  int ft, nc;
+  frontend_plan_shape(n_fft, &ft, &nc);
+  return int((n_frames + ft - 1) / ft);
 }
 
 template <class P, int PRE, int SPEC>
@@ -630,17 +656,20 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.fb_steps = reinterpret_cast<const float4*>(a.bank.steps);
   prm.n_mels = a.bank.n_mels;
   prm.n_steps = a.bank.n_steps;
-  for (int w = 0; w <= P::NWARPS; ++w) prm.chunk_m[w] = prm.chunk_s[w] = 0;
+  for (int w = 0; w <= P::NCHUNK; ++w) prm.chunk_m[w] = prm.chunk_s[w] = 0;
   if (SPEC != SK_CPLX) {
     const int M = a.bank.n_mels;
-    static_assert(P::NWARPS == kFrontendWarps && P::FT == kFrontendFrameTile, "mel programs are compiled for this CTA shape");
     if (a.bank.steps != nullptr) {
-      for (int w = 0; w <= P::NWARPS; ++w) {
+      if (a.bank.n_chunks != P::NCHUNK || a.bank.frame_tile != P::FT) {
+        if (err) *err = "mel program was compiled for another CTA shape";
+        return B2A_E_BAD_ARG;
+      }
+      for (int w = 0; w <= P::NCHUNK; ++w) {
         prm.chunk_m[w] = a.bank.host_chunk_m[w];
         prm.chunk_s[w] = a.bank.host_chunk_s[w];
       }
     } else {
-      for (int w = 0; w <= P::NWARPS; ++w) prm.chunk_m[w] = int((long long)M * w / P::NWARPS);
+      for (int w = 0; w <= P::NCHUNK; ++w) prm.chunk_m[w] = int((long long)M * w / P::NCHUNK);
     }
   }
   prm.out = a.out;
@@ -680,7 +709,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   *launches += 1;
   if (a.whisper_norm) {
     whisper_clamp_kernel<<<unsigned(a.batch), 256, 0, st>>>(a.out, a.clip_max, a.tile_min, prm.tiles_per_clip, a.n_frames,
-                                                             a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);
+                                                             a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);  // tiles of FT frames
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
     *launches += 1;
   }
@@ -698,6 +727,11 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) {
     if (a.pre_mode == PRE_KALDI && spec == SK_POWER) return launch_plan<Plan512, PRE_KALDI, SK_POWER>(a, st, launches, err);
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
+  }
+  if (a.n_fft == 1920 && a.hop == 480 && a.win_len == 1920 && a.pre_mode == PRE_NONE) {
+    if (spec == SK_POWER) return launch_plan<Plan1920, PRE_NONE, SK_POWER>(a, st, launches, err);
+    if (spec == SK_MAG) return launch_plan<Plan1920, PRE_NONE, SK_MAG>(a, st, launches, err);
+    return launch_plan<Plan1920, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (err) *err = "no FFT plan built for this (n_fft, hop, win_length, mode)";
   return B2A_E_UNSUPPORTED;

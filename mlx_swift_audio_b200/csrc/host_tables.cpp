@@ -392,9 +392,10 @@ const char* b2a_version(void) { return "b200audio 0.1 (sm_100a)"; }
 int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out) {
   b2a::SparseBank sb;
   b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
-  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, 1, b2a::kFrontendWarps, sb);
+  const int kChunks = 9;
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, 1, kChunks, sb);
   if (sb.steps.empty()) return -1;
-  for (int c = 0; c < b2a::kFrontendWarps; ++c) {
+  for (int c = 0; c < kChunks; ++c) {
     float acc0 = 0.0f, acc1 = 0.0f;
     float* so = out + sb.chunk_m[c];
     for (int s = sb.chunk_s[c]; s < sb.chunk_s[c + 1]; ++s) {

@@ -25,8 +25,7 @@ int64_t reflect_pad_index(int64_t i, int64_t n, int64_t pad);
 void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major, SparseBank& sb);
 void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
                        SparseBank& sb);
-constexpr int kFrontendWarps = 9;      // warps per CTA of every frontend plan (mel programs are chunked for it)
-constexpr int kFrontendFrameTile = 32; // frames per CTA (lane == frame)
+void frontend_plan_shape(int n_fft, int* frame_tile, int* n_chunks);  // CTA shape the mel program must be compiled for
 
 // ---- fused STFT -> (power | magnitude) -> mel -> log front-end (frontend.cu) -----------------
 enum PadMode { PAD_NONE = 0, PAD_REFLECT = 1, PAD_ZERO = 2 };
@@ -45,7 +44,8 @@ struct DeviceBank {  // sparse filterbank in device memory
   const float* weights = nullptr;
   const float* steps = nullptr;   // mel step program, 4 floats per step (w_lo, w_hi, bits(bin*FT*4), bits(emit stride)); null = generic path
   int n_steps = 0;
-  const int* host_chunk_m = nullptr;  // HOST: per-warp first filter / first step of the program (kFrontendWarps + 1 entries)
+  int n_chunks = 0, frame_tile = 0;  // CTA shape the program was compiled for
+  const int* host_chunk_m = nullptr;  // HOST: per-warp first filter / first step of the program (n_chunks + 1 entries)
   const int* host_chunk_s = nullptr;
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage

@@ -105,6 +105,36 @@ def test_kaldi_fbank(api, ctx, n):
     assert_feat_close(got_n, want_n, tol=2e-4, what="kaldi mean norm")
 
 
+@pytest.mark.parametrize("n", [24000 * 2, 24000 + 333, 1000, 700])
+def test_s3gen_mel(api, ctx, n):
+    # n = 700 < pad + 1 exercises reflectPad2D's truncated reflection (S3GenMel.swift:17-25)
+    x = synth.pcm(3, n, sample_rate=24000, seed=1008)
+    got = api.s3genMelSpectrogram(x, ctx=ctx)
+    want = R.s3gen_mel_spectrogram(x)
+    assert_feat_close(got, want, what="s3gen mel")
+    got1 = api.s3genMelSpectrogram(x[0], ctx=ctx)
+    assert got1.shape == want[0].shape
+    assert_feat_close(got1, want[0], what="s3gen mel 1-D")
+
+
+def test_s3gen_too_short(api, ctx):
+    from mlx_swift_audio_b200.api import B2ATooShort
+    with pytest.raises(B2ATooShort):
+        api.s3genMelSpectrogram(np.zeros(600, np.float32), ctx=ctx)
+
+
+def test_stft_complex_1920(api, ctx):
+    x = synth.pcm(2, 24000, sample_rate=24000, seed=1009)
+    w = R.hann_periodic_via_hanning(1920)
+    got = api.stft(x, w, 1920, 480, center=False, ctx=ctx)
+    want = np.stack([R.stft(c, w, 1920, 480, center=False) for c in x])
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+    got_c = api.stft(x[0], w, 1920, 480, ctx=ctx)
+    want_c = R.stft(x[0], w, 1920, 480)
+    assert np.abs(got_c - want_c).max() <= 1e-4 * np.abs(want_c).max()
+
+
 def test_voice_encoder_mel(api, ctx):
     x = synth.pcm(2, 24000, seed=1006)
     got = api.voiceEncoderMelspectrogram(x, ctx=ctx)
