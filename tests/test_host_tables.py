@@ -1,0 +1,123 @@
+"""CPU: the C-ABI library loads, exports every symbol include/b200audio.h declares, and its host-side
+tables / integer rules agree with the oracle.  No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import reference_dsp as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def api(built_lib):
+    from mlx_swift_audio_b200 import api as A
+    return A
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "b200audio.h")).read()
+    names = set(re.findall(r"B2A_API\s+[\w\s\*]+?\b(b2a_\w+)\s*\(", hdr))
+    assert len(names) >= 40
+    from mlx_swift_audio_b200 import _lib
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    for n in names:
+        assert hasattr(built_lib, n), n
+
+
+def test_no_gpu_means_an_error_not_a_fallback(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert built_lib.b2a_ctx_create(C.byref(h), 0) != 0
+    from mlx_swift_audio_b200 import api as A
+    with pytest.raises(A.B2AError):
+        A.whisperLogMelSpectrogram(np.zeros(16000, np.float32), nMels=80)
+
+
+def test_windows(api):
+    for got, want in [(api.whisperHannWindow(400), R.whisper_hann_window(400)), (api.hanningWindow(401), R.hanning_window(401)),
+                      (api.hanningWindow(1921), R.hanning_window(1921)), (api.hammingWindow(400), R.hamming_window(400)),
+                      (api.poveyWindow(400), R.povey_window(400)), (api.hannWindowPeriodic(16), R.hann_window_periodic(16)),
+                      (api.hannWindowPeriodic(20), R.hann_window_periodic(20)), (api.hanningWindow(21), R.hanning_window(21))]:
+        assert np.abs(got - want).max() <= 2.5e-7
+    assert api.whisperHannWindow(1).tolist() == [1.0] and api.hammingWindow(1).tolist() == [1.0]
+
+
+@pytest.mark.parametrize("args", [(16000, 400, 80, 0.0, 8000.0), (16000, 400, 128, 0.0, 8000.0), (16000, 400, 128, 0.0, None),
+                                  (16000, 400, 40, 0.0, 8000.0), (24000, 1920, 80, 0.0, 8000.0)])
+def test_slaney_bank(api, args):
+    got, want = api.melFilters(*args), R.mel_filters(*args)
+    assert got.shape == want.shape
+    assert np.array_equal(got != 0, want != 0), "support of every triangle must be identical"
+    assert np.abs(got - want).max() <= 1e-5 * want.max()
+
+
+def test_funasr_and_htk_banks(api):
+    got, want = api.funASRMelFilters(), R.funasr_mel_filters()
+    assert got.shape == (80, 200)
+    assert np.abs(got - want).max() <= 1e-5 * want.max()
+    got, want = api.melFiltersHTK(16000, 512, 80, 20.0, 8000.0), R.mel_filters_htk(16000, 512, 80, 20.0, 8000.0)
+    assert np.array_equal(got, want), "integer-bin triangles are exact rationals"
+
+
+def test_reflect_index_is_bit_exact(api):
+    for n, p in [(5, 8), (3, 7), (1, 4), (2, 5), (300, 200), (1000, 200), (201, 200), (200, 200), (199, 200), (1441, 720)]:
+        got = np.array([api.reflectPadIndex(i, n, p) for i in range(n + 2 * p)])
+        assert np.array_equal(got, R.reflect_pad_index(n, p)), (n, p)
+
+
+def test_frame_count_rules(built_lib):
+    L = built_lib
+    for n in (161, 200, 399, 400, 401, 16000, 479999, 480000, 480001, 960000):
+        x = np.zeros(n, np.float32) + 1e-3
+        assert L.b2a_whisper_num_frames(n, 0) == R.stft(x, R.whisper_hann_window(400), 400, 160).shape[0] - 1
+        assert L.b2a_funasr_num_frames(n) == 1 + n // 160
+        assert L.b2a_stft_num_frames(n, 400, 160, 1) == R.stft(x, R.whisper_hann_window(400), 400, 160).shape[0]
+    assert L.b2a_whisper_num_frames(480000, 0) == 3000 and L.b2a_whisper_num_frames(480000, 480000) == 6000
+    assert L.b2a_lfr_num_rows(2001, 6) == 334
+    assert L.b2a_kaldi_num_frames(320000, 400, 160) == 1998 and L.b2a_kaldi_num_frames(399, 400, 160) < 0
+    assert L.b2a_s3gen_num_frames(240000, 1920, 480) == 500 and L.b2a_s3gen_num_frames(600, 1920, 480) < 0
+    assert L.b2a_s3gen_num_frames(700, 1920, 480) == R.s3gen_mel_spectrogram(np.zeros(700, np.float32)).shape[1]
+    assert L.b2a_vocoder_stft_num_frames(720000, 16, 4) == 180001 and L.b2a_vocoder_stft_num_frames(720000, 20, 5) == 144001
+    assert L.b2a_istft_out_length(180001, 4) == 720000
+    assert L.b2a_stft_num_frames(100, 400, 160, 0) < 0
+    assert L.b2a_next_power_of_2(400) == 512 and L.b2a_next_power_of_2(512) == 512 and L.b2a_next_power_of_2(1) == 1
+    for a in (0, 159, 160, 16000, 320000):
+        assert L.b2a_funasr_compute_feature_length(a, 160, 6) == R.compute_feature_length(a)
+
+
+def test_mel_step_program_reproduces_dense_projection(built_lib, api):
+    P = C.POINTER(C.c_float)
+    rng = np.random.default_rng(0)
+    banks = [(api.melFilters(16000, 400, 80, 0, 8000), False), (api.melFilters(16000, 400, 128, 0, 8000), False),
+             (api.melFilters(16000, 400, 40, 0, 8000), False), (api.melFilters(24000, 1920, 80, 0, 8000), False),
+             (api.funASRMelFilters(), False), (api.melFiltersHTK(16000, 512, 80, 20, 8000), True),
+             (api.melFilters(16000, 400, 17, 300.0, 5000.0), False)]
+    for bank, bin_major in banks:
+        nm, nb = (bank.shape[1], bank.shape[0]) if bin_major else bank.shape
+        p = rng.random(nb).astype(np.float32)
+        out = np.full(nm, -1, np.float32)
+        b = np.ascontiguousarray(bank)
+        n = built_lib.b2a_debug_mel_program_apply(b.ctypes.data_as(P), nm, nb, int(bin_major), p.ctypes.data_as(P), out.ctypes.data_as(P))
+        assert n > 0
+        ref = (bank.T if bin_major else bank).astype(np.float64) @ p.astype(np.float64)
+        assert np.abs(out - ref).max() <= 1e-6 * max(ref.max(), 1e-30)
+    dense = rng.random((10, 50)).astype(np.float32)  # a bin feeding >2 filters: the generic kernel path is used instead
+    out = np.zeros(10, np.float32)
+    assert built_lib.b2a_debug_mel_program_apply(dense.ctypes.data_as(P), 10, 50, 0, rng.random(50).astype(np.float32).ctypes.data_as(P),
+                                                 out.ctypes.data_as(P)) == -1
+
+
+def test_bad_arguments_are_rejected_without_a_gpu(built_lib):
+    L = built_lib
+    out = np.zeros(4, np.float32)
+    P = C.POINTER(C.c_float)
+    assert L.b2a_window(99, 4, out.ctypes.data_as(P)) != 0
+    assert L.b2a_window(0, 0, out.ctypes.data_as(P)) != 0
+    assert L.b2a_reflect_pad_index(100, 5, 8) == -1
+    assert L.b2a_whisper_log_mel_spectrogram(None, None, 1, 16000, 80, 0, None, 0) != 0  # null context

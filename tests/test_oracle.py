@@ -1,0 +1,130 @@
+"""CPU: the oracle against its frozen golden vectors, against independent implementations
+(torch.stft / torch.istft) and against the only assertions the reference's own tests make for this
+path (shapes: Tests/FunASRTests.swift:141-186, Tests/WhisperTests.swift:85-96)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import reference_dsp as R
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_fp32_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def close(a, b, tol=2e-5):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape
+    assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) <= tol
+
+
+def test_reference_unit_test_shapes(gold):
+    # FunASRTests.funASRAudioPreprocessing: 1 s 440 Hz sine
+    sine = gold["in_sine"]
+    mel = R.funasr_log_mel_spectrogram(sine)
+    assert mel.ndim == 2 and mel.shape[1] == 80
+    lfr = R.apply_lfr(mel)
+    assert lfr.shape[1] == 560 and lfr.shape[0] == (mel.shape[0] + 5) // 6
+    # WhisperTests.whisperAudioPreprocessing: constant 0.5 arrays
+    assert R.pad_or_trim(np.full(1000, 0.5, np.float32)).shape == (480000,)
+    assert R.pad_or_trim(np.full(600000, 0.5, np.float32)).shape == (480000,)
+    assert R.compute_feature_length(16000) == (100 + 5) // 6
+
+
+def test_frame_counts():
+    assert R.whisper_log_mel_spectrogram(np.zeros(480000, np.float32) + 1e-3, 80).shape == (3000, 80)
+    assert R.funasr_log_mel_spectrogram(np.ones(320000, np.float32)).shape == (2001, 80)
+    assert R.apply_lfr(np.zeros((2001, 80), np.float32)).shape == (334, 560)
+    assert R.kaldi_fbank_camp_plus(np.ones(320000, np.float32)).shape == (1998, 80)
+    assert R.s3gen_mel_spectrogram(np.ones((1, 240000), np.float32)).shape == (1, 80, 500)
+    assert R.voice_encoder_melspectrogram(np.ones(96000, np.float32)).shape == (40, 601)
+
+
+def test_golden_frontends(gold):
+    x16, x24 = gold["in_x16"], gold["in_x24"]
+    close(np.stack([R.whisper_log_mel_spectrogram(c, 80) for c in x16]), gold["whisper80"])
+    close(np.stack([R.whisper_log_mel_spectrogram(c, 128) for c in x16]), gold["whisper128"])
+    close(np.stack([R.log_mel_spectrogram_chatterbox(c, 128) for c in x16]), gold["chatterbox128"])
+    close(np.stack([R.preprocess_audio(c) for c in x16]), gold["funasr_preprocess"], 1e-4)
+    close(np.stack([R.kaldi_fbank_camp_plus(c) for c in x16]), gold["kaldi_fbank"])
+    close(R.s3gen_mel_spectrogram(x24), gold["s3gen_mel"])
+    close(R.preprocess_audio(gold["in_sine"]), gold["sine_funasr_preprocess"], 1e-3)  # pure tone: CMVN divides by tiny std
+    close(R.whisper_log_mel_spectrogram(gold["in_sine"], 80), gold["sine_whisper80"])
+
+
+def test_golden_vocoder(gold):
+    w16 = R.hann_window_periodic(16)
+    assert np.abs(R.istft_hifigan(gold["in_mag16"], gold["in_ph16"], 16, 4, w16) - gold["istft_hifigan"]).max() <= 2e-6
+    assert np.abs(R.cosyvoice3_istft(gold["in_mag16"], gold["in_ph16"], 16, 4, w16) - gold["cv3_istft"]).max() <= 2e-6
+    assert np.abs(R.kokoro_inverse(gold["in_mag20"], gold["in_ph20"]) - gold["kokoro_inverse"]).max() <= 2e-6
+    re, im = R.stft_hifigan(gold["in_x24"][:, :2000], 16, 4, w16)
+    assert np.abs(re - gold["stft_hifigan_re"]).max() <= 2e-6 and np.abs(im - gold["stft_hifigan_im"]).max() <= 2e-6
+
+
+def test_fp32_oracle_close_to_fp64(gold):
+    x = gold["in_x16"][0]
+    a = R.whisper_log_mel_spectrogram(x, 128)
+    b = R.whisper_log_mel_spectrogram(x, 128, dt=np.float64)
+    assert np.abs(a - b).max() <= 2e-5
+    w = R.hann_window_periodic(16)
+    y32 = R.istft_hifigan(gold["in_mag16"], gold["in_ph16"], 16, 4, w)
+    y64 = R.istft_hifigan(gold["in_mag16"], gold["in_ph16"], 16, 4, w, dt=np.float64)
+    assert np.abs(y32 - y64).max() <= 5e-6
+
+
+def test_against_torch(gold):
+    torch = pytest.importorskip("torch")
+    x = gold["in_x16"][0]
+    st = torch.stft(torch.from_numpy(x), 400, 160, window=torch.hann_window(400, periodic=False), return_complex=True).numpy().T
+    mine = R.stft(x, R.whisper_hann_window(400), 400, 160)
+    assert np.abs(st - mine).max() <= 2e-4 * np.abs(st).max()
+    # iSTFT: inverse of the forward transform is the identity (window-sum-square normalisation)
+    w16 = R.hann_window_periodic(16)
+    sig = gold["in_x24"][:, :2000]
+    re, im = R.stft_hifigan(sig, 16, 4, w16)
+    rec = R.istft_hifigan(np.sqrt(re ** 2 + im ** 2), np.arctan2(im, re), 16, 4, w16)
+    assert np.abs(rec - sig).max() <= 1e-6
+    ti = torch.istft(torch.complex(torch.from_numpy(re), torch.from_numpy(im)), 16, 4, window=torch.from_numpy(w16)).numpy()
+    assert np.abs(ti - rec).max() <= 1e-6
+    # Kokoro normalises by sum(w) instead of sum(w^2): interior gain 1.5 / 2.0
+    m, p = R.kokoro_transform(sig)
+    rk = R.kokoro_inverse(m, p)[:, 0]
+    assert np.abs(rk[:, 40:-40] - 0.75 * sig[:, 40:-40]).max() <= 1e-4
+
+
+def test_unwrap_matches_numpy():
+    rng = np.random.default_rng(0)
+    p = rng.uniform(-np.pi, np.pi, (7, 300)).astype(np.float32)
+    assert np.abs(R.unwrap(p) - np.unwrap(p.astype(np.float64), axis=1)).max() <= 1e-4
+    q = np.sin(rng.normal(0, 2, (7, 300))).astype(np.float32)  # vocoder phases: unwrap is the identity
+    assert np.array_equal(R.unwrap(q), q)
+
+
+def test_reflect_pad_short_inputs():
+    # numpy-style reflect where it is defined ...
+    x = np.arange(10, dtype=np.float32)
+    assert np.array_equal(R.reflect_pad(x, 4), np.pad(x, 4, mode="reflect"))
+    # ... and the reference's own looped variant below that (S3TokenizerUtils.swift:287-295)
+    assert R.reflect_pad_index(5, 8).tolist() == [4, 3, 2, 1, 4, 3, 2, 1, 0, 1, 2, 3, 4, 3, 2, 1, 0, 3, 2, 1, 0]
+    assert R.reflect_pad(np.array([7.0], np.float32), 3).tolist() == [7.0] * 7
+
+
+def test_too_short_raises():
+    with pytest.raises(ValueError):
+        R.stft(np.zeros(100, np.float32), R.whisper_hann_window(400), 400, 160, center=False)
+    with pytest.raises(ValueError):
+        R.s3gen_mel_spectrogram(np.zeros(600, np.float32))
+
+
+def test_htk_bank_has_the_all_zero_filter():
+    # one integer-bin HTK triangle is identically zero; reproduce, do not fix
+    fb = R.mel_filters_htk(16000, 512, 80, 20.0, 8000.0)
+    assert (np.abs(fb).sum(axis=0) == 0).sum() == 1
+    for nm in (80, 128, 40):
+        f = R.mel_filters(16000, 400, nm, 0.0, 8000.0)
+        assert ((f != 0).sum(axis=0) <= 2).all()
