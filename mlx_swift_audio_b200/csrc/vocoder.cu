@@ -32,18 +32,18 @@ B2A_DEV void c2r(const float (&xr)[11], const float (&xi)[11], float (&y)[20]) {
 B2A_DEV void rdft_small(const float (&x)[16], float (&yr)[9], float (&yi)[9]) { b2a_rdft16(x, yr, yi); }
 B2A_DEV void rdft_small(const float (&x)[20], float (&yr)[11], float (&yi)[11]) { b2a_rdft20(x, yr, yi); }
 
-// sin and cos of x, ~1 ulp for |x| < 4.8e4 (3-term Cody-Waite reduction by pi/2 with FMA, cephes-style
-// minimax polynomials on [-pi/4, pi/4]); larger arguments take the libdevice slow path.
-B2A_DEV void sincos_f32(float x, float* s, float* c) {
-  if (!(fabsf(x) < 48000.0f)) {
-    sincosf(x, s, c);
-    return;
-  }
-  const float q = rintf(x * 0.636619772f);
+// sin and cos of x, ~1 ulp for |x| < 4.8e4: 3-term Cody-Waite reduction by pi/2 with FMA (quadrant taken
+// from the mantissa of the magic-number rounding, no float->int conversion), cephes-style minimax
+// polynomials on [-pi/4, pi/4], quadrant fix-up with sign-bit arithmetic.  Branch-free; the caller checks
+// the argument range once per frame and uses the libdevice slow path otherwise.
+template <bool WANT_SIN>
+B2A_DEV void sincos_fast(float x, float* s, float* c) {
+  float q = fmaf(x, 0.636619772f, 12582912.0f);  // 1.5 * 2^23: round-to-nearest integer lands in the mantissa
+  const int i = __float_as_int(q);
+  q -= 12582912.0f;
   float r = fmaf(q, -1.57079601e+00f, x);
   r = fmaf(q, -3.13916473e-07f, r);
   r = fmaf(q, -5.39030253e-15f, r);
-  const int i = __float2int_rn(q);
   const float r2 = r * r;
   float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
   ps = fmaf(ps, r2, -1.6666654611e-1f);
@@ -51,10 +51,13 @@ B2A_DEV void sincos_f32(float x, float* s, float* c) {
   float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
   pc = fmaf(pc, r2, 4.166664568298827e-2f);
   pc = fmaf(pc * r2, r2, fmaf(r2, -0.5f, 1.0f));
-  const float ss = (i & 1) ? pc : ps;
-  const float cc = (i & 1) ? ps : pc;
-  *s = (i & 2) ? -ss : ss;
-  *c = ((i + 1) & 2) ? -cc : cc;
+  const bool odd = (i & 1) != 0;
+  const float cc = odd ? ps : pc;
+  *c = __int_as_float(__float_as_int(cc) ^ (((i + 1) & 2) << 30));
+  if (WANT_SIN) {
+    const float ss = odd ? pc : ps;
+    *s = __int_as_float(__float_as_int(ss) ^ ((i & 2) << 30));
+  }
 }
 
 template <int NFFT, int HOP>
@@ -79,11 +82,13 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
   constexpr int R = NFFT / HOP;          // overlapping frames per output segment
   constexpr int HALO = R - 1;
   constexpr int SEG_PER_BLOCK = kIstftThreads - HALO;
-  static_assert(NFFT % HOP == 0 && R == 4, "built for 4x overlap");
-  __shared__ float s_halo[kIstftThreads / 32][HALO][HALO * HOP];  // [warp][lane 29..31][tail parts]
-  __shared__ float s_stage[(HOP == 4) ? 1 : SEG_PER_BLOCK * HOP];
+  // row pitch of the frame tile: hop 4 uses 128-bit accesses (pitch odd in 16-byte units), hop 5 scalar ones (odd pitch)
+  constexpr bool VEC = HOP == 4;
+  constexpr int YP = VEC ? (((NFFT / 4) % 2 == 1) ? NFFT : NFFT + 4) : NFFT + 1;
+  static_assert(NFFT % HOP == 0 && R == 4 && NFFT % 4 == 0, "built for 4x overlap");
+  __shared__ __align__(16) float s_y[kIstftThreads * YP];  // windowed frames of the block, later the staged output
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const long long clip = blockIdx.y;
   const long long nF = prm.n_frames;
   const long long nSeg = nF + HALO;                      // segments of the untrimmed OLA buffer
@@ -92,11 +97,12 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
   const bool has_frame = f >= 0 && f < nF;
 
   // ---- per-frame inverse real FFT, windowed ------------------------------------------------------
-  float y[NFFT];
   {
+    float y[NFFT];
     const float* __restrict__ mp = prm.mag + clip * F * nF + f;
     const float* __restrict__ pp = prm.phase + clip * F * nF + f;
     float xr[F], xi[F], ph[F];
+    float amax = 0.0f;
 #pragma unroll
     for (int k = 0; k < F; ++k) {
       float m = has_frame ? __ldg(mp + k * nF) : 0.0f;
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       m = fminf(m, prm.clip_hi);
       if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
       xr[k] = m;
+      amax = fmaxf(amax, fabsf(ph[k]));
     }
     if (prm.unwrap_flag != nullptr) {
       // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.
@@ -119,61 +126,81 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       }
       if (bad) *prm.unwrap_flag = 1;
     }
-    if (has_frame) {
+    if (amax < 48000.0f) {  // false for NaN too
+      // imaginary parts of DC / Nyquist are ignored by the codelet, as by irfft: no sine needed there
+      float sn, cs;
+      sincos_fast<false>(ph[0], &sn, &cs);
+      xr[0] *= cs; xi[0] = 0.0f;
+      sincos_fast<false>(ph[F - 1], &sn, &cs);
+      xr[F - 1] *= cs; xi[F - 1] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < F; ++k) {
-        float s, c;
-        sincos_f32(ph[k], &s, &c);
+      for (int k = 1; k < F - 1; ++k) {
+        sincos_fast<true>(ph[k], &sn, &cs);
         const float m = xr[k];
-        xr[k] = m * c;
-        xi[k] = m * s;  // imaginary parts of DC / Nyquist are ignored by the codelet, as by irfft
+        xr[k] = m * cs;
+        xi[k] = m * sn;
       }
-      c2r(xr, xi, y);
-#pragma unroll
-      for (int n = 0; n < NFFT; ++n) y[n] *= prm.wn[n];
     } else {
 #pragma unroll
-      for (int n = 0; n < NFFT; ++n) y[n] = 0.0f;
+      for (int k = 0; k < F; ++k) {  // rare: huge / non-finite phases (fully unrolled: keeps the arrays in registers)
+        float sn, cs;
+        sincosf(ph[k], &sn, &cs);
+        const float m = xr[k];
+        xr[k] = m * cs;
+        xi[k] = m * sn;
+      }
     }
-  }
-
-  // ---- overlap-add as a gather from the 3 previous frames ----------------------------------------
-  if (lane >= 32 - HALO) {
-    const int h = lane - (32 - HALO);  // 0 -> lane 29
+    c2r(xr, xi, y);
+    // frames outside [0, nF) have magnitude 0 -> exact zeros
+    if (VEC) {
+      float4* row = reinterpret_cast<float4*>(s_y + tid * YP);
 #pragma unroll
-    for (int i = 0; i < HALO * HOP; ++i) s_halo[warp][h][i] = y[HOP + i];
+      for (int q = 0; q < NFFT / 4; ++q)
+        row[q] = make_float4(y[4 * q] * prm.wn[4 * q], y[4 * q + 1] * prm.wn[4 * q + 1], y[4 * q + 2] * prm.wn[4 * q + 2],
+                             y[4 * q + 3] * prm.wn[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int n = 0; n < NFFT; ++n) s_y[tid * YP + n] = y[n] * prm.wn[n];
+    }
   }
   __syncthreads();
-  float acc[HOP];
-#pragma unroll
-  for (int i = 0; i < HOP; ++i) acc[i] = y[i];
-#pragma unroll
-  for (int r = 1; r <= HALO; ++r) {
-#pragma unroll
-    for (int i = 0; i < HOP; ++i) {
-      float v = __shfl_up_sync(0xffffffffu, y[r * HOP + i], r);
-      if (lane < r) v = warp > 0 ? s_halo[warp - 1][HALO - r + lane][(r - 1) * HOP + i] : 0.0f;
-      acc[i] += v;
-    }
-  }
 
-  // ---- envelope normalisation, trim, store ---------------------------------------------------------
-  const long long s = f;                           // this thread's segment index
-  const bool emit = tid >= HALO && s >= R / 2 && s < nSeg - R / 2 && s >= 0;
+  // ---- overlap-add as a gather: segment s = y_s[0:h] + y_{s-1}[h:2h] + y_{s-2}[2h:3h] + y_{s-3}[3h:4h] -------------
+  // (added in that order: the frame order of the reference's scatter-add)
+  const long long s = f;
+  const bool emit = tid >= HALO && s >= R / 2 && s < nSeg - R / 2;
   float o[HOP];
   if (emit) {
-    const bool interior = s >= HALO && s <= nF - 1;
+    if (VEC) {
+      const float4 a0 = *reinterpret_cast<const float4*>(s_y + tid * YP);
+      o[0] = a0.x; o[1] = a0.y; o[2] = a0.z; o[3] = a0.w;
 #pragma unroll
-    for (int i = 0; i < HOP; ++i) {
-      if (interior) {
-        o[i] = acc[i] * prm.inv_env[i];
-      } else {
+      for (int r = 1; r <= HALO; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(s_y + (tid - r) * YP + r * HOP);
+        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < HOP; ++i) o[i] = s_y[tid * YP + i];
+#pragma unroll
+      for (int r = 1; r <= HALO; ++r) {
+#pragma unroll
+        for (int i = 0; i < HOP; ++i) o[i] += s_y[(tid - r) * YP + r * HOP + i];
+      }
+    }
+    const bool interior = s >= HALO && s <= nF - 1;
+    if (interior) {
+#pragma unroll
+      for (int i = 0; i < HOP; ++i) o[i] *= prm.inv_env[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < HOP; ++i) {
         float e = 0.0f;
 #pragma unroll
         for (int r = 0; r < R; ++r)
           if (s - r >= 0 && s - r < nF) e += prm.wenv[r * HOP + i];
-        if (prm.norm == NORM_WSQ_FLOOR) o[i] = acc[i] / fmaxf(e, 1e-8f);
-        else o[i] = e != 0.0f ? acc[i] / e : acc[i];
+        if (prm.norm == NORM_WSQ_FLOOR) o[i] = o[i] / fmaxf(e, 1e-8f);
+        else o[i] = e != 0.0f ? o[i] / e : o[i];
       }
     }
   }
@@ -190,6 +217,8 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
     }
   } else {
     // hop 5: stage the block's segments and write them out contiguously
+    __syncthreads();
+    float* s_stage = s_y;
     if (emit) {
 #pragma unroll
       for (int i = 0; i < HOP; ++i) s_stage[(tid - HALO) * HOP + i] = o[i];
