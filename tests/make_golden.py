@@ -45,6 +45,9 @@ def main():
     g["sine_funasr_lfr"] = R.apply_lfr(g["sine_funasr_logmel"])
     g["sine_funasr_preprocess"] = R.preprocess_audio(sine)
     g["sine_whisper80"] = R.whisper_log_mel_spectrogram(sine, 80)
+    # fp64 truth for the pure tone: its un-clamped log-mel spans 29 nepers, so bins ~100 dB below the peak carry
+    # nothing but fp32 rounding noise and two fp32 implementations differ there by ~1e-3 ("tolerances")
+    g["sine_funasr_logmel_f64"] = R.funasr_log_mel_spectrogram(sine, dt=np.float64).astype(np.float64)
     # seeded synthetic clips
     g["whisper80"] = np.stack([R.whisper_log_mel_spectrogram(c, 80) for c in x16])
     g["whisper128"] = np.stack([R.whisper_log_mel_spectrogram(c, 128) for c in x16])
