@@ -1,0 +1,139 @@
+// b200audio.hpp -- header-only C++ mirror of the reference's Swift DSP helpers over the C ABI.
+//
+// The reference is Swift (a compiled language) and no Swift toolchain exists in the build image, so the
+// compiled-language host layer is C++: same function names, argument meaning, defaults and return shapes
+// as the Swift helpers; a non-zero status throws b2a::Error where the reference
+// calls fatalError.  Host buffers (std::vector<float>) go through B2A_HOST; device pointers can be passed
+// to the C ABI directly with B2A_DEVICE.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "b200audio.h"
+
+namespace b2a {
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+struct Array {  // contiguous fp32, row-major
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  Array() = default;
+  explicit Array(std::vector<int64_t> s) : shape(std::move(s)) {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    data.assign(size_t(n), 0.0f);
+  }
+};
+
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    if (b2a_ctx_create(&c_, device) != B2A_OK) throw Error(B2A_E_CUDA, "b200audio: no sm_100 CUDA device");
+  }
+  ~Context() { b2a_ctx_destroy(c_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  b2a_ctx* raw() const { return c_; }
+  void check(int rc) const {
+    if (rc != B2A_OK) throw Error(rc, b2a_last_error(c_));
+  }
+
+  // STT/Whisper/WhisperAudio.swift:54-67
+  Array padOrTrim(const Array& array, int64_t length = 480000) const {
+    Array out({length});
+    check(b2a_pad_or_trim(c_, array.data.data(), 1, array.shape[0], length, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // STT/Whisper/WhisperAudio.swift:78-137 -> (T', nMels); a leading batch axis is accepted
+  Array whisperLogMelSpectrogram(const Array& audio, int nMels, int64_t padding = 0) const {
+    const int64_t b = audio.shape.size() == 2 ? audio.shape[0] : 1, n = audio.shape.back();
+    const int64_t frames = b2a_whisper_num_frames(n, padding);
+    if (frames <= 0) throw Error(B2A_E_TOO_SHORT, "Input is too short for STFT");
+    Array out(audio.shape.size() == 2 ? std::vector<int64_t>{b, frames, nMels} : std::vector<int64_t>{frames, nMels});
+    check(b2a_whisper_log_mel_spectrogram(c_, audio.data.data(), b, n, nMels, padding, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Codec/S3Tokenizer/S3TokenizerUtils.swift:160-208 -> (nMels, T')
+  Array logMelSpectrogramChatterbox(const Array& audio, int nMels = 128, int64_t padding = 0) const {
+    const int64_t n = audio.shape.back(), frames = b2a_whisper_num_frames(n, padding);
+    if (frames <= 0) throw Error(B2A_E_TOO_SHORT, "Input is too short for STFT");
+    Array out({nMels, frames});
+    check(b2a_log_mel_spectrogram_chatterbox(c_, audio.data.data(), 1, n, nMels, padding, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // STT/FunASR/FunASRAudio.swift:197-216
+  Array preprocessAudio(const Array& audio, int nMels = 80, int lfrM = 7, int lfrN = 6, bool applyNormalization = true) const {
+    const int64_t n = audio.shape.back(), frames = b2a_funasr_num_frames(n);
+    if (frames <= 0) throw Error(B2A_E_TOO_SHORT, "Input is too short for STFT");
+    Array out({b2a_lfr_num_rows(frames, lfrN), int64_t(nMels) * lfrM});
+    check(b2a_funasr_preprocess_audio(c_, audio.data.data(), 1, n, nMels, lfrM, lfrN, applyNormalization, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Codec/S3Gen/CAMPPlus.swift:32-106
+  Array kaldiFbankCAMPPlus(const Array& audio, int sampleRate = 16000, int numMelBins = 80, float frameLength = 25.0f,
+                           float frameShift = 10.0f) const {
+    const int64_t n = audio.shape.back();
+    const int win = int(float(sampleRate) * frameLength / 1000), hop = int(float(sampleRate) * frameShift / 1000);
+    const int64_t frames = b2a_kaldi_num_frames(n, win, hop);
+    if (frames <= 0) throw Error(B2A_E_TOO_SHORT, "signal shorter than one analysis window");
+    Array out({frames, numMelBins});
+    check(b2a_kaldi_fbank_campplus(c_, audio.data.data(), 1, n, sampleRate, numMelBins, frameLength, frameShift, 0, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Codec/S3Gen/Mel/S3GenMel.swift:43-102: (B, T) -> (B, numMels, T')
+  Array s3genMelSpectrogram(const Array& y, int nFft = 1920, int numMels = 80, int samplingRate = 24000, int hopSize = 480,
+                            int winSize = 1920, int fmin = 0, int fmax = 8000) const {
+    const bool was1d = y.shape.size() == 1;
+    const int64_t b = was1d ? 1 : y.shape[0], n = y.shape.back(), frames = b2a_s3gen_num_frames(n, nFft, hopSize);
+    if (frames <= 0) throw Error(B2A_E_TOO_SHORT, "Input is too short for STFT");
+    Array out(was1d ? std::vector<int64_t>{numMels, frames} : std::vector<int64_t>{b, numMels, frames});
+    check(b2a_s3gen_mel_spectrogram(c_, y.data.data(), b, n, nFft, numMels, samplingRate, hopSize, winSize, fmin, fmax, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Codec/S3Gen/HiFiGAN.swift:298-367
+  Array istftHiFiGAN(const Array& magnitude, const Array& phase, int nFft, int hopLength, const std::vector<float>& window) const {
+    const int64_t b = magnitude.shape[0], frames = magnitude.shape[2];
+    Array out({b, (frames - 1) * hopLength});
+    check(b2a_istft_hifigan(c_, magnitude.data.data(), phase.data.data(), b, frames, nFft, hopLength, window.data(), out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Codec/S3Gen/HiFiGAN.swift:257-295
+  std::pair<Array, Array> stftHiFiGAN(const Array& x, int nFft, int hopLength, const std::vector<float>& window) const {
+    const int64_t b = x.shape[0], n = x.shape[1], frames = b2a_vocoder_stft_num_frames(n, nFft, hopLength);
+    if (frames <= 0) throw Error(B2A_E_TOO_SHORT, "Input is too short");
+    Array re({b, nFft / 2 + 1, frames}), im({b, nFft / 2 + 1, frames});
+    check(b2a_stft_hifigan(c_, x.data.data(), b, n, nFft, hopLength, window.data(), re.data.data(), im.data.data(), B2A_HOST));
+    return {std::move(re), std::move(im)};
+  }
+  // TTS/Kokoro/Decoder/MLXSTFT.swift:211-235
+  Array mlxStftInverse(const Array& magnitude, const Array& phase, int filterLength = 20, int hopLength = 5, int winLength = 20) const {
+    const int64_t b = magnitude.shape[0], frames = magnitude.shape[2];
+    Array out({b, 1, (frames - 1) * hopLength});
+    check(b2a_kokoro_stft_inverse(c_, magnitude.data.data(), phase.data.data(), b, frames, filterLength, hopLength, winLength, out.data.data(), B2A_HOST));
+    return out;
+  }
+
+ private:
+  b2a_ctx* c_ = nullptr;
+};
+
+// host-only helpers
+inline std::vector<float> hannWindowPeriodic(int size) {  // Codec/S3Gen/HiFiGAN.swift:15-20
+  std::vector<float> w(size);
+  b2a_window(B2A_WIN_HANN_PERIODIC, size, w.data());
+  return w;
+}
+inline std::vector<float> melFilters(int sampleRate, int nFft, int nMels, float fMin = 0.0f, float fMax = -1.0f) {  // S3TokenizerUtils.swift:301-375
+  std::vector<float> f(size_t(nMels) * (nFft / 2 + 1));
+  if (b2a_mel_filters(sampleRate, nFft, nMels, fMin, fMax, f.data()) != B2A_OK) throw Error(B2A_E_BAD_ARG, "bad filterbank parameters");
+  return f;
+}
+
+}  // namespace b2a
