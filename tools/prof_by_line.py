@@ -58,3 +58,27 @@ if len(sys.argv) > 5:
                 op = tk[1] if tk[0].startswith('@') else tk[0]
                 c[op.split('.')[0]] += int(data[i][ie]); t += int(data[i][ie])
         print(f"lines {lo}-{hi}: {100*t/tot:5.1f}% of all; per tile {t/24000:.0f}: " + ', '.join(f"{k}:{v/24000:.0f}" for k, v in c.most_common(14)))
+    # time share (warp-stall samples) and stall reasons per range, codelets separately
+    stall_idx = [(i, h) for i, h in enumerate(hdr) if h.startswith('stall_')]
+    tot_s = sum(int(r[isamp]) for r in data[:n])
+    def region(i):
+        cur, _ = seq[i]
+        if cur[0] == 'codelets.h':
+            return 'codelets(' + str(cur[3]) + ')'
+        key = (cur[0], cur[1])
+        if key[0] == 'frontend.cu':
+            for lo, hi in ranges:
+                if lo <= key[1] <= hi:
+                    return f'{lo}-{hi}'
+        return 'other'
+    agg = defaultdict(lambda: Counter())
+    for i in range(n):
+        rg = region(i)
+        agg[rg]['samples'] += int(data[i][isamp]); agg[rg]['inst'] += int(data[i][ie])
+        for j, h in stall_idx:
+            try: agg[rg][h] += int(data[i][j])
+            except ValueError: pass
+    print('--- time share by region (samples), issue efficiency proxy = inst/sample, top stall reasons')
+    for rg, c in sorted(agg.items(), key=lambda kv: -kv[1]['samples']):
+        st = sorted(((v, k) for k, v in c.items() if k.startswith('stall_')), reverse=True)[:4]
+        print(f"{rg:16s} time {100*c['samples']/tot_s:5.1f}%  inst {100*c['inst']/tot:5.1f}%  " + ', '.join(f"{k[6:]}:{100*v/max(c['samples'],1):.0f}%" for v, k in st))
