@@ -71,6 +71,8 @@ struct Plan {
   static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
   static constexpr int R0_WORDS_REAL = PCM_WORDS > P_WORDS_REAL ? PCM_WORDS : P_WORDS_REAL;
   static constexpr int R0_WORDS_CPLX = CPLX_DIRECT ? ((PCM_WORDS + 3) & ~3) : (((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3);
+  static constexpr int TW_WORDS = (2 * N2 * (N1 / 2 - 1) + 3) & ~3;  // padded so that the mel program behind it stays 16-byte aligned
+  static constexpr bool DOUBLE_BUF = MINB_ > 1;       // second PCM/spectrum buffer: prefetch the next tile with cp.async
   static constexpr int SUB = 32 / FT;               // a warp covers FT frames x SUB items (lane = sub * FT + frame)
   static constexpr int NCHUNK = NWARPS * SUB;       // mel-program chunks
   static_assert(N1 * N2 == N, "N = N1*N2");
@@ -91,7 +93,7 @@ enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
 template <class P>
 struct FrontendParams {
   const float* x;
-  long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, lfr_rows;
+  long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, lfr_rows, total_tiles;
   int pad_mode, log_mode, whisper_norm, post_affine, out_mode, tiles_per_clip, lfr_m, lfr_n;
   float log_floor, post_sub, post_div;
   const int4* fb_desc;    // per filter: (first bin, number of bins, offset into fb_w, 0)
@@ -171,20 +173,37 @@ B2A_DEV float lg2_ftz(float x) {
 // w_lo*P to the open filter and w_hi*P to the next one; a non-zero emit stride stores the open filter's sum
 // to the [m][frame] staging tile, advances the output pointer and shifts the accumulators.  A bin touches at
 // most two adjacent triangular filters; filters without bins get a zero-weight step.  LANE == FRAME.
-B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* __restrict__ so) {
+B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, float*& so) {
+  const int adv = __float_as_int(t.w);
+  acc0 = fmaf(t.x, pk, acc0);
+  acc1 = fmaf(t.y, pk, acc1);
+  const bool e = adv != 0;
+  if (e) *so = acc0;
+  so = reinterpret_cast<float*>(reinterpret_cast<char*>(so) + adv);
+  acc0 = e ? acc1 : acc0;
+  acc1 = e ? 0.0f : acc1;
+}
+
+B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_in) {
+  float* so = so_in;
   float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 2
-  for (int s = s0; s < s1; ++s) {
+  const char* pb = reinterpret_cast<const char*>(p_lane);
+  int s = s0;
+  // four steps per iteration, all shared-memory loads issued before the (serial) accumulator updates
+  for (; s + 4 <= s1; s += 4) {
+    const float4 t0 = steps[s], t1 = steps[s + 1], t2 = steps[s + 2], t3 = steps[s + 3];
+    const float p0 = *reinterpret_cast<const float*>(pb + __float_as_int(t0.z));
+    const float p1 = *reinterpret_cast<const float*>(pb + __float_as_int(t1.z));
+    const float p2 = *reinterpret_cast<const float*>(pb + __float_as_int(t2.z));
+    const float p3 = *reinterpret_cast<const float*>(pb + __float_as_int(t3.z));
+    mel_step_apply(t0, p0, acc0, acc1, so);
+    mel_step_apply(t1, p1, acc0, acc1, so);
+    mel_step_apply(t2, p2, acc0, acc1, so);
+    mel_step_apply(t3, p3, acc0, acc1, so);
+  }
+  for (; s < s1; ++s) {
     const float4 t = steps[s];
-    const float pk = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(p_lane) + __float_as_int(t.z));
-    const int adv = __float_as_int(t.w);
-    acc0 = fmaf(t.x, pk, acc0);
-    acc1 = fmaf(t.y, pk, acc1);
-    const bool e = adv != 0;
-    if (e) *so = acc0;
-    so = reinterpret_cast<float*>(reinterpret_cast<char*>(so) + adv);
-    acc0 = e ? acc1 : acc0;
-    acc1 = e ? 0.0f : acc1;
+    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so);
   }
 }
 
@@ -201,30 +220,60 @@ B2A_DEV float mel_post(float v, float log_floor, float& lmax, float& vmin) {
   return v;
 }
 
+B2A_DEV void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src));
+}
+B2A_DEV void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Stages the PCM of tile (clip, f0) into `buf` (skewed rows, pitch HOP+1).  Interior tiles use cp.async so that
+// the copy overlaps with the previous tile's FFT stages; edge tiles (reflect / zero padding) go through the index map.
+template <class P>
+B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, long long clip, long long f0, int tid, int lane, int warp) {
+  constexpr int HOP = P::HOP, NW = P::NWARPS;
+  constexpr int NROWS = (P::TS + HOP - 1) / HOP, CPR = (HOP + 31) / 32;
+  const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
+  const long long p0 = f0 * HOP;
+  const long long j0 = p0 - prm.pad_left;
+  if (j0 >= 0 && j0 + P::TS <= prm.n_samples) {
+    const float* __restrict__ src = xc + j0;
+    for (int r = warp; r < NROWS; r += NW) {
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) {
+        const int col = j * 32 + lane;
+        if (col < HOP && r * HOP + col < P::TS) cp_async4(buf + r * P::PITCH + col, src + r * HOP + col);
+      }
+    }
+  } else {
+    for (int s = tid; s < P::TS; s += P::NTHREADS)
+      buf[s + s / HOP] = fetch_padded(xc, p0 + s, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode);
+  }
+}
+
+// Persistent kernel: grid = MINB CTAs per SM; every CTA loads its tables once and walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; with DOUBLE_BUF the next tile's PCM is prefetched (cp.async)
+// into the other spectrum/PCM buffer while the current tile is in its FFT / mel / store stages.
 template <class P, int PRE, int SPEC>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
+  constexpr bool DB = P::DOUBLE_BUF;
   constexpr int OP = FT + 1;  // output staging pitch ([m][frame], conflict-free both ways)
+  constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
   extern __shared__ __align__(16) float smem[];
-  float* s_r0 = smem;                                       // PCM tile, later the spectrum tile
-  float2* s_y = reinterpret_cast<float2*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL));
+  float2* s_y = reinterpret_cast<float2*>(smem + (DB ? 2 : 1) * R0W);
   float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
-  float4* s_bins = reinterpret_cast<float4*>(smem + (cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS);  // per-bin mel weights
-  float* s_wt = reinterpret_cast<float*>(s_bins) + (cplx ? 0 : 4 * P::MAX_STEPS);  // window, item-major [n2][n1]
+  float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
+  float4* s_bins = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);  // mel step program
   __shared__ int s_tile_min;
 
   constexpr int SUB = P::SUB, NIT = NW * SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
-  const int tile = blockIdx.x % prm.tiles_per_clip;
-  const long long clip = blockIdx.x / prm.tiles_per_clip;
-  const long long f0 = (long long)tile * FT;
-  const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
-  if (tid == 0) s_tile_min = 0x7fffffff;
 
-  // ---- 0. per-block tables: window in item-major order, twiddles ---------------------------------
+  // ---- 0. per-CTA tables (once): window in item-major order, twiddles, mel step program -------------
   for (int i = tid; i < N; i += P::NTHREADS) {
     const int n2 = i / N1, n1 = i - n2 * N1;
     const int o = N2 * n1 + n2;
@@ -237,247 +286,247 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       for (int i = tid; i < prm.n_steps; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_steps + i);
   }
 
-  // ---- 1. stage the tile's PCM: one skewed row (HOP samples, pitch HOP+1) per warp iteration, coalesced ----
-  {
-    const long long p0 = f0 * HOP;
-    const long long j0 = p0 - prm.pad_left;
-    constexpr int NROWS = (P::TS + HOP - 1) / HOP, CPR = (HOP + 31) / 32;
-    if (j0 >= 0 && j0 + P::TS <= prm.n_samples) {
-      const float* __restrict__ src = xc + j0;
-      for (int r = warp; r < NROWS; r += NW) {
-        float v[CPR];
-#pragma unroll
-        for (int j = 0; j < CPR; ++j) {
-          const int col = j * 32 + lane;
-          v[j] = (col < HOP && r * HOP + col < P::TS) ? __ldg(src + r * HOP + col) : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < CPR; ++j) {
-          const int col = j * 32 + lane;
-          if (col < HOP && r * HOP + col < P::TS) s_r0[r * P::PITCH + col] = v[j];
-        }
-      }
-    } else {
-      for (int s = tid; s < P::TS; s += P::NTHREADS)
-        s_r0[s + s / HOP] = fetch_padded(xc, p0 + s, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode);
+  long long t_idx = blockIdx.x;
+  if (t_idx < prm.total_tiles) stage_pcm<P>(prm, smem, t_idx / prm.tiles_per_clip, (t_idx % prm.tiles_per_clip) * FT, tid, lane, warp);
+
+  for (int iter = 0; t_idx < prm.total_tiles; ++iter, t_idx += gridDim.x) {
+    const int tile = int(t_idx % prm.tiles_per_clip);
+    const long long clip = t_idx / prm.tiles_per_clip;
+    const long long f0 = (long long)tile * FT;
+    float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile, later the spectrum tile
+    if (tid == 0) s_tile_min = 0x7fffffff;
+
+    // ---- 1. this tile's PCM has landed; prefetch the next tile into the other buffer ------------------
+    cp_async_commit_wait_all();
+    __syncthreads();
+    if (DB) {
+      const long long nxt = t_idx + gridDim.x;
+      if (nxt < prm.total_tiles)
+        stage_pcm<P>(prm, smem + ((iter & 1) ? 0 : R0W), nxt / prm.tiles_per_clip, (nxt % prm.tiles_per_clip) * FT, tid, lane, warp);
     }
-  }
-  __syncthreads();
 
-  // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
-  float mu = 0.0f;
-  if (PRE == PRE_KALDI) {
-    float part = 0.0f;
-    static_assert(PRE != PRE_KALDI || SUB == 1, "Kaldi pre-processing is built for 32-frame tiles");
-    const int fk = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
-    for (int o = warp; o < WIN; o += NW) part += s_r0[fk * P::PITCH + o + o / HOP];
-    s_o[warp * FT + fl] = part;
-    __syncthreads();
-    float tot = 0.0f;
+    // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
+    float mu = 0.0f;
+    if (PRE == PRE_KALDI) {
+      float part = 0.0f;
+      static_assert(PRE != PRE_KALDI || SUB == 1, "Kaldi pre-processing is built for 32-frame tiles");
+      const int fk = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
+      for (int o = warp; o < WIN; o += NW) part += s_r0[fk * P::PITCH + o + o / HOP];
+      s_o[warp * FT + fl] = part;
+      __syncthreads();
+      float tot = 0.0f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) tot += s_o[w * FT + fl];
-    mu = tot / float(WIN);
-    __syncthreads();
-  }
+      for (int w = 0; w < NW; ++w) tot += s_o[w * FT + fl];
+      mu = tot / float(WIN);
+      __syncthreads();
+    }
 
-  // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
-  // not a conflict), so that per-tile max / min need no lane masking.
-  const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
-  const int flane = fl < rows ? fl : rows - 1;
+    // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
+    // not a conflict), so that per-tile max / min need no lane masking.
+    const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
+    const int flane = fl < rows ? fl : rows - 1;
 
-  // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
-  {
-    const float* lane_pcm = s_r0 + flane * P::PITCH;
-    for (int n2 = wsub; n2 < N2; n2 += NIT) {
-      float wrow[N1];
+    // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
+    {
+      const float* lane_pcm = s_r0 + flane * P::PITCH;
+      for (int n2 = wsub; n2 < N2; n2 += NIT) {
+        float wrow[N1];
 #pragma unroll
-      for (int q = 0; q < N1 / 4; ++q) {
-        const float4 w4 = reinterpret_cast<const float4*>(s_wt + n2 * N1)[q];
-        wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
-      }
-      float in[N1];
-      load_item<P, PRE>(lane_pcm, n2, mu, wrow, in, std::make_integer_sequence<int, N1>{});
-      float yr[H1 + 1], yi[H1 + 1];
-      rdft(in, yr, yi);
-      float2* yb = s_y + n2 * FT + fl;
-      yb[0] = make_float2(yr[0], yr[H1]);
-      const float2* twr = s_tw + n2 * (H1 - 1);
+        for (int q = 0; q < N1 / 4; ++q) {
+          const float4 w4 = reinterpret_cast<const float4*>(s_wt + n2 * N1)[q];
+          wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
+        }
+        float in[N1];
+        load_item<P, PRE>(lane_pcm, n2, mu, wrow, in, std::make_integer_sequence<int, N1>{});
+        float yr[H1 + 1], yi[H1 + 1];
+        rdft(in, yr, yi);
+        float2* yb = s_y + n2 * FT + fl;
+        yb[0] = make_float2(yr[0], yr[H1]);
+        const float2* twr = s_tw + n2 * (H1 - 1);
 #pragma unroll
-      for (int k1 = 1; k1 < H1; ++k1) {
-        const float2 t = twr[k1 - 1];
-        yb[k1 * N2 * FT] = make_float2(yr[k1] * t.x - yi[k1] * t.y, yr[k1] * t.y + yi[k1] * t.x);
+        for (int k1 = 1; k1 < H1; ++k1) {
+          const float2 t = twr[k1 - 1];
+          yb[k1 * N2 * FT] = make_float2(yr[k1] * t.x - yi[k1] * t.y, yr[k1] * t.y + yi[k1] * t.x);
+        }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
-  {
-    auto put = [&](int k, float re, float im) {
-      if (cplx) {
-        if (P::CPLX_DIRECT) {
-          // tile too large for a staged complex spectrum: store straight to (T', F) global memory
-          if (fl < rows) reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride)[(f0 + fl) * P::NBINS + k] = make_float2(re, im);
+    // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
+    {
+      auto put = [&](int k, float re, float im) {
+        if (cplx) {
+          if (P::CPLX_DIRECT) {
+            // tile too large for a staged complex spectrum: store straight to (T', F) global memory
+            if (fl < rows) reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride)[(f0 + fl) * P::NBINS + k] = make_float2(re, im);
+          } else {
+            reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + fl] = make_float2(re, im);
+          }
         } else {
-          reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + fl] = make_float2(re, im);
-        }
-      } else {
-        const float pw = re * re + im * im;
-        s_r0[k * FT + fl] = SPEC == SK_POWER ? pw : sqrtf(pw);
-      }
-    };
-    for (int it = wsub; it <= H1; it += NIT) {
-      if (it == 0) {
-        float in[N2];
-#pragma unroll
-        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].x;
-        float ur[N2 / 2 + 1], ui[N2 / 2 + 1];
-        rdft(in, ur, ui);
-#pragma unroll
-        for (int k2 = 0; k2 <= N2 / 2; ++k2) put(N1 * k2, ur[k2], ui[k2]);
-      } else if (it == H1) {
-        float in[N2];
-#pragma unroll
-        for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].y;
-        float ur[(N2 - 1) / 2 + 1], ui[(N2 - 1) / 2 + 1];
-        rdftodd(in, ur, ui);
-#pragma unroll
-        for (int k2 = 0; k2 <= (N2 - 1) / 2; ++k2) put(H1 + N1 * k2, ur[k2], ui[k2]);
-      } else {
-        float xr[N2], xi[N2], ur[N2], ui[N2];
-        const float2* yb = s_y + it * N2 * FT + fl;
-#pragma unroll
-        for (int n2 = 0; n2 < N2; ++n2) {
-          const float2 v = yb[n2 * FT];
-          xr[n2] = v.x;
-          xi[n2] = v.y;
-        }
-        cdft(xr, xi, ur, ui);
-#pragma unroll
-        for (int k2 = 0; k2 < N2; ++k2) {
-          const int kc = N1 * k2;  // k = it + kc
-          if (kc + H1 <= N / 2) put(it + kc, ur[k2], ui[k2]);       // it < H1  =>  it + kc <= N/2
-          else put(N - kc - it, ur[k2], -ui[k2]);                    // conjugate mirror
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  const bool frame_ok = fl < rows;
-
-  // ---- 4a. plain stft(): write the complex spectrum tile ------------------------------------------
-  if (cplx) {
-    if (P::CPLX_DIRECT) return;
-    const int nb = P::NBINS;
-    float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride) + f0 * nb;
-    const float2* sp = reinterpret_cast<const float2*>(s_r0);
-    for (int e = tid; e < rows * nb; e += P::NTHREADS) {
-      const int r = e / nb, k = e - r * nb;
-      dst[e] = sp[k * P::P_PITCH + r];
-    }
-    return;
-  }
-
-  // ---- 4b. sparse mel projection into the [m][frame] staging tile ------------------------------------
-  const int M = prm.n_mels;
-  {
-    const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
-    if (prm.fb_steps != nullptr) {
-      mel_steps(s_r0 + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
-    } else {
-      // generic path: arbitrary filterbank, one short loop per filter
-      const int4* __restrict__ fdesc = prm.fb_desc;
-      const float* __restrict__ fw = prm.fb_w;
-      for (int m = ma; m < mb; ++m) {
-        const int4 d = __ldg(fdesc + m);
-        const float* __restrict__ w = fw + d.z;
-        const float* pp = s_r0 + d.x * FT + fl;
-        float v = 0.0f;
-        for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
-        s_o[m * OP + fl] = v;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- 5. log / floor / scale fused into the coalesced store of the staged tile -----------------------
-  float lmax = -3.0e38f, vmin = 3.0e38f;
-  {
-    const int log_mode = prm.log_mode;
-    const float log_floor = prm.log_floor;
-    const bool wnorm = prm.whisper_norm != 0;
-    float* __restrict__ dst = prm.out + clip * prm.out_clip_stride;
-    if (prm.out_mode == OUT_TM) {
-      // (T', M) rows: lanes run over m
-      dst += f0 * M;
-      auto store_tm = [&](auto post) {
-        for (int r = warp; r < rows; r += NW) {
-          float* d = dst + r * M;
-          const float* sr = s_o + r;
-          for (int c = lane; c < M; c += 32) d[c] = post(sr[c * OP]);
+          const float pw = re * re + im * im;
+          s_r0[k * FT + fl] = SPEC == SK_POWER ? pw : sqrtf(pw);
         }
       };
-      if (wnorm) store_tm([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
-      else if (log_mode == LOG_LN) store_tm([&](float v) { return mel_post<LOG_LN, false>(v, log_floor, lmax, vmin); });
-      else if (log_mode == LOG_LOG10) store_tm([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
-      else if (log_mode == LOG_DB20) store_tm([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
-      else store_tm([&](float v) { return v; });
-    } else if (prm.out_mode == OUT_MT) {
-      // (M, T') rows: lanes run over frames
-      dst += f0 + fl;
-      const long long nfr = prm.n_frames;
-      const bool post = prm.post_affine != 0;
-      auto store_mt = [&](auto fn) {
-        for (int m = wsub; m < M; m += NIT) {
-          float v = fn(s_o[m * OP + fl]);
-          if (post) v = (v - prm.post_sub) / prm.post_div;
-          if (frame_ok) dst[m * nfr] = v;
-        }
-      };
-      if (wnorm) store_mt([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
-      else if (log_mode == LOG_LN) store_mt([&](float v) { return mel_post<LOG_LN, false>(v, log_floor, lmax, vmin); });
-      else if (log_mode == LOG_LOG10) store_mt([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
-      else if (log_mode == LOG_DB20) store_mt([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
-      else store_mt([&](float v) { return v; });
-    } else {  // OUT_LFR: out[i][j*M + m] = ln(feat)[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
-      const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
-      const long long T = prm.n_frames;
-      long long i_lo = (f0 + left - (lm - 1)) / ln;
-      if (f0 + left - (lm - 1) < 0) i_lo = 0;
-      long long i_hi = (f0 + rows - 1 + left) / ln;
-      if (f0 + rows >= T) i_hi = prm.lfr_rows - 1;
-      if (i_hi > prm.lfr_rows - 1) i_hi = prm.lfr_rows - 1;
-      const int nseg = int(i_hi - i_lo + 1) * lm;
-      for (int sg = warp; sg < nseg; sg += NW) {
-        const long long i = i_lo + sg / lm;
-        const int j = sg % lm;
-        long long t = i * ln + j - left;
-        t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-        if (t < f0 || t >= f0 + rows) continue;
-        const float* sr = s_o + int(t - f0);
-        float* d = dst + (i * lm + j) * (long long)M;
-        for (int c = lane; c < M; c += 32) {
-          float v = sr[c * OP];
-          if (log_mode == LOG_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
-          else if (log_mode == LOG_LOG10) v = lg2_ftz(fmaxf(v, log_floor)) * 0.30102999566398120f;
-          d[c] = v;
+      for (int it = wsub; it <= H1; it += NIT) {
+        if (it == 0) {
+          float in[N2];
+#pragma unroll
+          for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].x;
+          float ur[N2 / 2 + 1], ui[N2 / 2 + 1];
+          rdft(in, ur, ui);
+#pragma unroll
+          for (int k2 = 0; k2 <= N2 / 2; ++k2) put(N1 * k2, ur[k2], ui[k2]);
+        } else if (it == H1) {
+          float in[N2];
+#pragma unroll
+          for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].y;
+          float ur[(N2 - 1) / 2 + 1], ui[(N2 - 1) / 2 + 1];
+          rdftodd(in, ur, ui);
+#pragma unroll
+          for (int k2 = 0; k2 <= (N2 - 1) / 2; ++k2) put(H1 + N1 * k2, ur[k2], ui[k2]);
+        } else {
+          float xr[N2], xi[N2], ur[N2], ui[N2];
+          const float2* yb = s_y + it * N2 * FT + fl;
+#pragma unroll
+          for (int n2 = 0; n2 < N2; ++n2) {
+            const float2 v = yb[n2 * FT];
+            xr[n2] = v.x;
+            xi[n2] = v.y;
+          }
+          cdft(xr, xi, ur, ui);
+#pragma unroll
+          for (int k2 = 0; k2 < N2; ++k2) {
+            const int kc = N1 * k2;  // k = it + kc
+            if (kc + H1 <= N / 2) put(it + kc, ur[k2], ui[k2]);       // it < H1  =>  it + kc <= N/2
+            else put(N - kc - it, ur[k2], -ui[k2]);                    // conjugate mirror
+          }
         }
       }
-    }
-  }
-  if (prm.whisper_norm) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
-      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
-    }
-    if (lane == 0) {
-      atomicMax(prm.clip_max + clip, enc_ordered(lmax));
-      atomicMin(&s_tile_min, enc_ordered(vmin));
     }
     __syncthreads();
-    if (tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
+
+    const bool frame_ok = fl < rows;
+
+    // ---- 4a. plain stft(): write the complex spectrum tile ------------------------------------------
+    if (cplx) {
+      if (!P::CPLX_DIRECT) {
+        const int nb = P::NBINS;
+        float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride) + f0 * nb;
+        const float2* sp = reinterpret_cast<const float2*>(s_r0);
+        for (int e = tid; e < rows * nb; e += P::NTHREADS) {
+          const int r = e / nb, k = e - r * nb;
+          dst[e] = sp[k * P::P_PITCH + r];
+        }
+      }
+      continue;  // the loop-top barrier orders this tile's reads before the next tile's writes
+    }
+
+    // ---- 4b. sparse mel projection into the [m][frame] staging tile ------------------------------------
+    const int M = prm.n_mels;
+    {
+      const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
+      if (prm.fb_steps != nullptr) {
+        mel_steps(s_r0 + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
+      } else {
+        // generic path: arbitrary filterbank, one short loop per filter
+        const int4* __restrict__ fdesc = prm.fb_desc;
+        const float* __restrict__ fw = prm.fb_w;
+        for (int m = ma; m < mb; ++m) {
+          const int4 d = __ldg(fdesc + m);
+          const float* __restrict__ w = fw + d.z;
+          const float* pp = s_r0 + d.x * FT + fl;
+          float v = 0.0f;
+          for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
+          s_o[m * OP + fl] = v;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- 5. log / floor / scale fused into the coalesced store of the staged tile -----------------------
+    float lmax = -3.0e38f, vmin = 3.0e38f;
+    {
+      const int log_mode = prm.log_mode;
+      const float log_floor = prm.log_floor;
+      const bool wnorm = prm.whisper_norm != 0;
+      float* __restrict__ dst = prm.out + clip * prm.out_clip_stride;
+      if (prm.out_mode == OUT_TM) {
+        // (T', M) rows: lanes run over m
+        dst += f0 * M;
+        auto store_tm = [&](auto post) {
+          for (int r = warp; r < rows; r += NW) {
+            float* d = dst + r * M;
+            const float* sr = s_o + r;
+            for (int c = lane; c < M; c += 32) d[c] = post(sr[c * OP]);
+          }
+        };
+        if (wnorm) store_tm([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
+        else if (log_mode == LOG_LN) store_tm([&](float v) { return mel_post<LOG_LN, false>(v, log_floor, lmax, vmin); });
+        else if (log_mode == LOG_LOG10) store_tm([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
+        else if (log_mode == LOG_DB20) store_tm([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
+        else store_tm([&](float v) { return v; });
+      } else if (prm.out_mode == OUT_MT) {
+        // (M, T') rows: lanes run over frames
+        dst += f0 + fl;
+        const long long nfr = prm.n_frames;
+        const bool post = prm.post_affine != 0;
+        auto store_mt = [&](auto fn) {
+          for (int m = wsub; m < M; m += NIT) {
+            float v = fn(s_o[m * OP + fl]);
+            if (post) v = (v - prm.post_sub) / prm.post_div;
+            if (frame_ok) dst[m * nfr] = v;
+          }
+        };
+        if (wnorm) store_mt([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
+        else if (log_mode == LOG_LN) store_mt([&](float v) { return mel_post<LOG_LN, false>(v, log_floor, lmax, vmin); });
+        else if (log_mode == LOG_LOG10) store_mt([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
+        else if (log_mode == LOG_DB20) store_mt([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
+        else store_mt([&](float v) { return v; });
+      } else {  // OUT_LFR: out[i][j*M + m] = ln(feat)[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
+        const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
+        const long long T = prm.n_frames;
+        long long i_lo = (f0 + left - (lm - 1)) / ln;
+        if (f0 + left - (lm - 1) < 0) i_lo = 0;
+        long long i_hi = (f0 + rows - 1 + left) / ln;
+        if (f0 + rows >= T) i_hi = prm.lfr_rows - 1;
+        if (i_hi > prm.lfr_rows - 1) i_hi = prm.lfr_rows - 1;
+        const int nseg = int(i_hi - i_lo + 1) * lm;
+        for (int sg = warp; sg < nseg; sg += NW) {
+          const long long i = i_lo + sg / lm;
+          const int j = sg % lm;
+          long long t = i * ln + j - left;
+          t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+          if (t < f0 || t >= f0 + rows) continue;
+          const float* sr = s_o + int(t - f0);
+          float* d = dst + (i * lm + j) * (long long)M;
+          for (int c = lane; c < M; c += 32) {
+            float v = sr[c * OP];
+            if (log_mode == LOG_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
+            else if (log_mode == LOG_LOG10) v = lg2_ftz(fmaxf(v, log_floor)) * 0.30102999566398120f;
+            d[c] = v;
+          }
+        }
+      }
+    }
+    if (prm.whisper_norm) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+      }
+      if (lane == 0) {
+        atomicMax(prm.clip_max + clip, enc_ordered(lmax));
+        atomicMin(&s_tile_min, enc_ordered(vmin));
+      }
+      __syncthreads();
+      if (tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
+    }
+    if (!DB) {
+      // single buffer: the next tile's PCM can only be staged once every warp is done with the spectrum tile
+      __syncthreads();
+      const long long nxt = t_idx + gridDim.x;
+      if (nxt < prm.total_tiles) stage_pcm<P>(prm, smem, nxt / prm.tiles_per_clip, (nxt % prm.tiles_per_clip) * FT, tid, lane, warp);
+    }
   }
 }
 
@@ -690,17 +739,29 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       return B2A_E_BAD_ARG;
     }
   }
-  const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS + P::N +
-                                             2 * P::N2 * (P::H1 - 1) + (SPEC == SK_CPLX ? 0 : 4 * P::MAX_STEPS));
-  static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 2) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0,
-                "shared-memory tables must stay 16-byte (bins, window rows) / 8-byte (twiddles) aligned");
+  const int steps_words = SPEC == SK_CPLX ? 0 : 4 * std::max(a.bank.n_steps, 1);
+  const size_t smem = sizeof(float) * size_t((P::DOUBLE_BUF ? 2 : 1) * (SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
+                                             P::N + P::TW_WORDS + steps_words);
+  static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 2) == 0,
+                "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
+  static_assert(((P::N + P::TW_WORDS) % 4) == 0, "mel step program must stay 16-byte aligned");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
-  const long long nblocks = (long long)prm.tiles_per_clip * a.batch;
-  if (nblocks <= 0 || nblocks > 0x7fffffffLL) {
-    if (err) *err = "grid too large";
+  prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;
+  if (prm.total_tiles <= 0) {
+    if (err) *err = "empty launch";
     return B2A_E_BAD_ARG;
   }
+  int dev = 0, n_sm = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC>, P::NTHREADS, smem)) != cudaSuccess)
+    return cuda_fail(e, "occupancy query", err);
+  if (per_sm < 1) {
+    if (err) *err = "frontend kernel does not fit on this device";
+    return B2A_E_CUDA;
+  }
+  const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
   if (a.whisper_norm) {
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
