@@ -210,7 +210,11 @@ def _cpu_clip_job(args):
     name, n, sr, seed, reps = args
     from oracle import reference_dsp as R
     from tests import synth
-    import numpy as _np
+    try:  # one BLAS / FFT thread per worker process: the processes already cover every core
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
     t0 = time.perf_counter()
     if name.startswith("istft"):
         nfft, hop = (16, 4) if name == "istft_hift" else (20, 5)

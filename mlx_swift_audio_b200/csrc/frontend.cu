@@ -104,7 +104,7 @@ struct FrontendParams {
   int chunk_s[P::NCHUNK + 1];  // steps   [chunk_s[c], chunk_s[c+1]) of the program belong to chunk c
   float* out;
   int* clip_max;
-  float* tile_min;
+  int* tile_min;   // per tile: ordered-int encoding of the minimum normalised value
   float window[P::WIN];
 };
 
@@ -267,8 +267,6 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   float4* s_bins = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);  // mel step program
-  __shared__ int s_tile_min;
-
   constexpr int SUB = P::SUB, NIT = NW * SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
@@ -286,23 +284,23 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       for (int i = tid; i < prm.n_steps; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_steps + i);
   }
 
-  long long t_idx = blockIdx.x;
-  if (t_idx < prm.total_tiles) stage_pcm<P>(prm, smem, t_idx / prm.tiles_per_clip, (t_idx % prm.tiles_per_clip) * FT, tid, lane, warp);
+  const unsigned total_tiles = unsigned(prm.total_tiles), tpc = unsigned(prm.tiles_per_clip);  // < 2^31, checked on the host
+  unsigned t_idx = blockIdx.x;
+  if (t_idx < total_tiles) stage_pcm<P>(prm, smem, t_idx / tpc, (long long)(t_idx % tpc) * FT, tid, lane, warp);
 
-  for (int iter = 0; t_idx < prm.total_tiles; ++iter, t_idx += gridDim.x) {
-    const int tile = int(t_idx % prm.tiles_per_clip);
-    const long long clip = t_idx / prm.tiles_per_clip;
+  for (int iter = 0; t_idx < total_tiles; ++iter, t_idx += gridDim.x) {
+    const unsigned uclip = t_idx / tpc;
+    const int tile = int(t_idx - uclip * tpc);
+    const long long clip = uclip;
     const long long f0 = (long long)tile * FT;
     float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile, later the spectrum tile
-    if (tid == 0) s_tile_min = 0x7fffffff;
 
     // ---- 1. this tile's PCM has landed; prefetch the next tile into the other buffer ------------------
     cp_async_commit_wait_all();
     __syncthreads();
     if (DB) {
-      const long long nxt = t_idx + gridDim.x;
-      if (nxt < prm.total_tiles)
-        stage_pcm<P>(prm, smem + ((iter & 1) ? 0 : R0W), nxt / prm.tiles_per_clip, (nxt % prm.tiles_per_clip) * FT, tid, lane, warp);
+      const unsigned nxt = t_idx + gridDim.x;
+      if (nxt < total_tiles) stage_pcm<P>(prm, smem + ((iter & 1) ? 0 : R0W), nxt / tpc, (long long)(nxt % tpc) * FT, tid, lane, warp);
     }
 
     // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
@@ -455,9 +453,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         dst += f0 * M;
         auto store_tm = [&](auto post) {
           for (int r = warp; r < rows; r += NW) {
-            float* d = dst + r * M;
-            const float* sr = s_o + r;
-            for (int c = lane; c < M; c += 32) d[c] = post(sr[c * OP]);
+            float* d = dst + r * M + lane;
+            const float* sr = s_o + r + lane * OP;
+            int c = lane;
+            for (; c + 96 < M; c += 128, d += 128, sr += 128 * OP) {  // four coalesced 128-byte segments per iteration
+              const float v0 = sr[0], v1 = sr[32 * OP], v2 = sr[64 * OP], v3 = sr[96 * OP];
+              d[0] = post(v0); d[32] = post(v1); d[64] = post(v2); d[96] = post(v3);
+            }
+            for (; c < M; c += 32, d += 32, sr += 32 * OP) d[0] = post(sr[0]);
           }
         };
         if (wnorm) store_tm([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
@@ -516,16 +519,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
       if (lane == 0) {
         atomicMax(prm.clip_max + clip, enc_ordered(lmax));
-        atomicMin(&s_tile_min, enc_ordered(vmin));
+        atomicMin(prm.tile_min + clip * prm.tiles_per_clip + tile, enc_ordered(vmin));  // ordered-int encoding, memset to 0x7f.. by the host
       }
-      __syncthreads();
-      if (tid == 0) prm.tile_min[clip * prm.tiles_per_clip + tile] = dec_ordered(s_tile_min);
     }
     if (!DB) {
       // single buffer: the next tile's PCM can only be staged once every warp is done with the spectrum tile
       __syncthreads();
-      const long long nxt = t_idx + gridDim.x;
-      if (nxt < prm.total_tiles) stage_pcm<P>(prm, smem, nxt / prm.tiles_per_clip, (nxt % prm.tiles_per_clip) * FT, tid, lane, warp);
+      const unsigned nxt = t_idx + gridDim.x;
+      if (nxt < total_tiles) stage_pcm<P>(prm, smem, nxt / tpc, (long long)(nxt % tpc) * FT, tid, lane, warp);
     }
   }
 }
@@ -533,14 +534,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 // Rewrites only the tiles whose minimum lies below the clip's clamp threshold:
 //   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, ((Lmax - 8) + 4) / 4)   (x -> (x+4)/4 is monotone in fp32)
 // WhisperAudio.swift:130-134, S3TokenizerUtils.swift:203-205.
-__global__ void whisper_clamp_kernel(float* out, const int* clip_max, const float* tile_min, int tiles_per_clip,
+__global__ void whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                      long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
   const long long clip = blockIdx.x;
   const float lm = dec_ordered(clip_max[clip]);
   const float thr = ((lm - 8.0f) + 4.0f) / 4.0f;
   float* o = out + clip * out_clip_stride;
   for (int t = 0; t < tiles_per_clip; ++t) {
-    if (!(tile_min[clip * tiles_per_clip + t] < thr)) continue;
+    if (!(dec_ordered(tile_min[clip * tiles_per_clip + t]) < thr)) continue;
     const long long f0 = (long long)t * ft;
     const int rows = int(n_frames - f0 < ft ? n_frames - f0 : ft);
     if (out_mode == OUT_TM) {
@@ -723,7 +724,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   prm.out = a.out;
   prm.clip_max = a.clip_max;
-  prm.tile_min = a.tile_min;
+  prm.tile_min = reinterpret_cast<int*>(a.tile_min);
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
   switch (a.out_mode) {
     case OUT_TM: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
@@ -748,7 +749,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;
-  if (prm.total_tiles <= 0) {
+  if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL) {
     if (err) *err = "empty launch";
     return B2A_E_BAD_ARG;
   }
@@ -764,12 +765,13 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
   if (a.whisper_norm) {
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+    if ((e = cudaMemsetAsync(a.tile_min, 0x7f, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
   frontend_kernel<P, PRE, SPEC><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
-    whisper_clamp_kernel<<<unsigned(a.batch), 256, 0, st>>>(a.out, a.clip_max, a.tile_min, prm.tiles_per_clip, a.n_frames,
+    whisper_clamp_kernel<<<unsigned(a.batch), 256, 0, st>>>(a.out, a.clip_max, prm.tile_min, prm.tiles_per_clip, a.n_frames,
                                                              a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);  // tiles of FT frames
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
     *launches += 1;
