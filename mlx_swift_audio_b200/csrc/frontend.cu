@@ -41,16 +41,16 @@ namespace b2a {
 // ------------------------------------------------------------------------------------------------
 #define B2A_DEV __device__ __forceinline__
 B2A_DEV void rdft(const float (&x)[16], float (&yr)[9], float (&yi)[9]) { b2a_rdft16(x, yr, yi); }
-B2A_DEV void rdft(const float (&x)[25], float (&yr)[13], float (&yi)[13]) { b2a_rdft25(x, yr, yi); }
+B2A_DEV void rdft(const float (&x)[20], float (&yr)[11], float (&yi)[11]) { b2a_rdft20(x, yr, yi); }
 B2A_DEV void rdft(const float (&x)[32], float (&yr)[17], float (&yi)[17]) { b2a_rdft32(x, yr, yi); }
 B2A_DEV void rdft(const float (&x)[60], float (&yr)[31], float (&yi)[31]) { b2a_rdft60(x, yr, yi); }
-B2A_DEV void rdftodd(const float (&x)[25], float (&yr)[13], float (&yi)[13]) { b2a_rdftodd25(x, yr, yi); }
+B2A_DEV void rdftodd(const float (&x)[20], float (&yr)[10], float (&yi)[10]) { b2a_rdftodd20(x, yr, yi); }
 B2A_DEV void rdftodd(const float (&x)[32], float (&yr)[16], float (&yi)[16]) { b2a_rdftodd32(x, yr, yi); }
-B2A_DEV void cdft(const float (&xr)[25], const float (&xi)[25], float (&yr)[25], float (&yi)[25]) { b2a_cdft25(xr, xi, yr, yi); }
+B2A_DEV void cdft(const float (&xr)[20], const float (&xi)[20], float (&yr)[20], float (&yi)[20]) { b2a_cdft20(xr, xi, yr, yi); }
 B2A_DEV void cdft(const float (&xr)[32], const float (&xi)[32], float (&yr)[32], float (&yi)[32]) { b2a_cdft32(xr, xi, yr, yi); }
 
 // inter-stage twiddles W_N^{n2*k1}, k1 = 1..N1/2-1, as (cos, -sin); filled once per device
-__constant__ float2 c_tw400[25 * 7];
+__constant__ float2 c_tw400[20 * 9];
 __constant__ float2 c_tw512[32 * 7];
 __constant__ float2 c_tw1920[32 * 29];
 
@@ -78,7 +78,8 @@ struct Plan {
   static_assert(N1 * N2 == N, "N = N1*N2");
   static_assert(FT == 32 || FT == 16, "lane == (item, frame)");
 };
-using Plan400 = Plan<400, 400, 16, 25, 160, 32, 9, 2>;
+// 400 = 20 x 20: 20 stage-A items and 9 complex + (real + odd-real) stage-B items split evenly over 10 warps
+using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 2>;
 using Plan512 = Plan<512, 400, 16, 32, 160, 32, 9, 2>;
 // n_fft 1920 (S3Gen 24 kHz mel): the exchange buffer only fits 16 frames, so half-warps take different items
 using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1>;
@@ -649,7 +650,7 @@ static void fill_tw(std::vector<float2>& v, int N, int N1, int N2) {
 int init_frontend_tables(std::string* err) {
   std::vector<float2> t;
   cudaError_t e;
-  fill_tw(t, 400, 16, 25);
+  fill_tw(t, 400, 20, 20);
   if ((e = cudaMemcpyToSymbol(c_tw400, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
   fill_tw(t, 512, 16, 32);
   if ((e = cudaMemcpyToSymbol(c_tw512, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
@@ -667,6 +668,9 @@ void frontend_plan_shape(int n_fft, int* frame_tile, int* n_chunks) {
   if (n_fft == 1920) {
     *frame_tile = Plan1920::FT;
     *n_chunks = Plan1920::NCHUNK;
+  } else if (n_fft == 512) {
+    *frame_tile = Plan512::FT;
+    *n_chunks = Plan512::NCHUNK;
   } else {
     *frame_tile = Plan400::FT;
     *n_chunks = Plan400::NCHUNK;

@@ -230,7 +230,9 @@ def dft(g, xs, sign=-1):
         m = n // r
         subs = [dft(g, xs[q::r], sign) for q in range(r)]
         ys = [None] * n
-        kmax = m  # need k2 in 0..m-1
+        # Real input: the sub-DFTs are Hermitian, so column m-k is the conjugate of column k rotated by one
+        # radix step -- butterfly(m-k)[j] = conj(butterfly(k)[r-1-j]) -- and only columns 0..m/2 are computed.
+        kmax = m // 2 + 1 if real else m
         for k in range(kmax):
             col = []
             for q in range(r):
@@ -239,6 +241,9 @@ def dft(g, xs, sign=-1):
             b = _butterfly(g, col, sign)
             for j in range(r):
                 ys[k + m * j] = b[j]
+        for k in range(kmax, m):
+            for j in range(r):
+                ys[k + m * j] = ys[(m - k) + m * (r - 1 - j)].conj()
     if real:
         # enforce exact Hermitian structure so upstream CSE sees conj pairs as the same nodes
         for k in range(n // 2 + 1, n):
@@ -367,23 +372,43 @@ def gen_rdft_odd(n):
     """Odd-frequency DFT of a real sequence: U[k] = sum_j y[j] e^{-2 pi i j (k + 1/2)/n}, k = 0..(n-1)//2.
     This is the stage-B item k1 = N1/2 of the two-stage real FFT (inputs are real after stage A;
     the inter-stage twiddle e^{-pi i j/n} is folded in here as compile-time constants).  The other
-    bins are conjugate mirrors: U[n-1-k] = conj(U[k])."""
-    g = G()
-    xs = []
-    for j in range(n):
-        ang = -math.pi * j / n
-        xs.append(C(g, g.inp("x[%d]" % j), g.ZERO).mul_const(math.cos(ang), math.sin(ang)))
-    ys = dft(g, xs, -1)
+    bins are conjugate mirrors: U[n-1-k] = conj(U[k]).
+    Two formulations are generated and the cheaper one is kept: (a) twiddle then complex DFT of size n,
+    (b) the odd bins of the real DFT of size 2n of the zero-extended sequence (real-input savings at every level)."""
     h = (n - 1) // 2 + 1
-    outs = []
-    for k in range(h):
-        outs.append(("yr[%d]" % k, ys[k].re))
-        outs.append(("yi[%d]" % k, ys[k].im))
-    return emit(g, "b2a_rdftodd%d" % n, "const float (&x)[%d], float (&yr)[%d], float (&yi)[%d]" % (n, h, h), outs)
+    name = "b2a_rdftodd%d" % n
+    args = "const float (&x)[%d], float (&yr)[%d], float (&yi)[%d]" % (n, h, h)
+
+    def form_a():
+        g = G()
+        xs = []
+        for j in range(n):
+            ang = -math.pi * j / n
+            xs.append(C(g, g.inp("x[%d]" % j), g.ZERO).mul_const(math.cos(ang), math.sin(ang)))
+        ys = dft(g, xs, -1)
+        return g, [ys[k] for k in range(h)]
+
+    def form_b():
+        g = G()
+        xs = [C(g, g.inp("x[%d]" % j), g.ZERO) for j in range(n)] + [C(g, g.ZERO, g.ZERO) for _ in range(n)]
+        ys = dft(g, xs, -1)
+        return g, [ys[2 * k + 1] for k in range(h)]
+
+    best = None
+    for form in (form_a, form_b):
+        g, ys = form()
+        outs = []
+        for k in range(h):
+            outs.append(("yr[%d]" % k, ys[k].re))
+            outs.append(("yi[%d]" % k, ys[k].im))
+        code, st = emit(g, name, args, outs)
+        if best is None or sum(st) < sum(best[1]):
+            best = (code, st)
+    return best
 
 
 RDFT = [16, 20, 25, 32, 40, 60, 64]
-RDFT_ODD = [25, 32]
+RDFT_ODD = [20, 25, 32]
 CDFT = [16, 20, 25, 30, 32]
 C2R = [16, 20]
 
