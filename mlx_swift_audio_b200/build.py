@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libb200audio.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 
 SOURCES = ["host_tables.cpp", "frontend.cu", "vocoder.cu", "capi.cu"]
-HEADERS = ["codelets.h", "internal.h", os.path.join("..", "..", "include", "b200audio.h")]
+HEADERS = ["codelets.h", "mel_baked.h", "internal.h", os.path.join("..", "..", "include", "b200audio.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
@@ -56,8 +56,27 @@ def regenerate_codelets() -> None:
             fh.write(out)
 
 
+def regenerate_mel_baked() -> None:
+    """csrc/mel_baked.h: straight-line mel projections for the standard banks, generated from the library's own
+    host-side filterbank code (host_tables.cpp compiled stand-alone with g++; see tools/gen_mel_baked.py)."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    gxx = shutil.which("g++") or shutil.which("c++")
+    if gxx is None:
+        raise RuntimeError("g++ not found: cannot generate csrc/mel_baked.h")
+    host_lib = os.path.join(OBJ_DIR, "libhosttables.so")
+    subprocess.run([gxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", host_lib, os.path.join(CSRC, "host_tables.cpp")], check=True)
+    gen = os.path.join(ROOT, "tools", "gen_mel_baked.py")
+    out = subprocess.run([sys.executable, gen, host_lib], check=True, capture_output=True, text=True).stdout
+    path = os.path.join(CSRC, "mel_baked.h")
+    if not os.path.exists(path) or open(path).read() != out:
+        with open(path, "w") as fh:
+            fh.write(out)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
+    if not os.path.exists(os.path.join(CSRC, "mel_baked.h")):
+        regenerate_mel_baked()
     stamp = os.path.join(OBJ_DIR, "stamp")
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
@@ -89,5 +108,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    regenerate_codelets()
+    regenerate_mel_baked()
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

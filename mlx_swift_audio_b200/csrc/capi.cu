@@ -29,6 +29,7 @@ struct BankStorage {
   int* desc = nullptr;
   float* weights = nullptr;
   float* steps = nullptr;
+  int baked_id = 0;
 };
 
 constexpr int kSlots = 3;  // chunk ring depth of the host pipeline
@@ -124,6 +125,9 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
       if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
     }
+    if (!bs.host.steps.empty())
+      bs.baked_id = frontend_match_baked(bs.host.steps.data(), int(bs.host.steps.size() / 4), bs.host.chunk_m.data(), bs.host.chunk_s.data(),
+                                         n_chunks, frame_tile, n_mels);
     it = c->banks.emplace(key, std::move(bs)).first;
   }
   const BankStorage& bs = it->second;
@@ -137,6 +141,7 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
   out->host_chunk_s = bs.host.chunk_s.data();
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
+  out->baked_id = bs.baked_id;
   return B2A_OK;
 }
 

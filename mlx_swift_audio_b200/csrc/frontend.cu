@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <mutex>
 #include <utility>
 #include <string>
@@ -33,6 +34,7 @@
 #include "../../include/b200audio.h"
 #include "codelets.h"
 #include "internal.h"
+#include "mel_baked.h"
 
 namespace b2a {
 
@@ -62,7 +64,8 @@ struct Plan {
   static constexpr int NTHREADS = NWARPS * 32;
   static constexpr int TS = (FT - 1) * HOP + WIN;  // samples per tile
   static constexpr int PITCH = HOP + 1;            // skewed row pitch
-  static constexpr int PCM_WORDS = ((TS - 1) + (TS - 1) / HOP + 1 + 3) & ~3;
+  static constexpr int NROWS = (TS + HOP - 1) / HOP;  // rows of HOP samples staged per tile (the last one may be partial)
+  static constexpr int PCM_WORDS = (NROWS * PITCH + 3) & ~3;
   static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT
   static constexpr int P_PITCH = FT + 1;
   static constexpr bool CPLX_DIRECT = (N / 2 + 1) * (FT + 1) * 2 * 4 > 64 * 1024;  // complex tile would not fit: stft() stores directly
@@ -90,12 +93,28 @@ template <> struct TwTable<Plan512> { static B2A_DEV const float2* get() { retur
 template <> struct TwTable<Plan1920> { static B2A_DEV const float2* get() { return c_tw1920; } };
 
 enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
+// Post-processing of a finished mel value.  POST_RUNTIME: log mode / Whisper normalisation are kernel parameters and the
+// filterbank is the interpreted step program (any bank); the other kinds belong to the baked banks of mel_baked.h.
+enum PostKind { POST_RUNTIME = 0, POST_WNORM = 1, POST_LN = 2 };
+
+template <int MEL> struct MelTraits { static constexpr int M = 0; };
+template <> struct MelTraits<1> { static constexpr int M = 128; };
+template <> struct MelTraits<2> { static constexpr int M = 80; };
+template <> struct MelTraits<3> { static constexpr int M = 80; };
+template <> struct MelTraits<4> { static constexpr int M = 80; };
+template <int MEL, class Emit>
+__device__ __forceinline__ void mel_baked(int chunk, const float* __restrict__ p, Emit&& emit) {
+  if constexpr (MEL == 1) mel_baked_1(chunk, p, emit);
+  else if constexpr (MEL == 2) mel_baked_2(chunk, p, emit);
+  else if constexpr (MEL == 3) mel_baked_3(chunk, p, emit);
+  else if constexpr (MEL == 4) mel_baked_4(chunk, p, emit);
+}
 
 template <class P>
 struct FrontendParams {
   const float* x;
   long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, lfr_rows, total_tiles;
-  int pad_mode, log_mode, whisper_norm, post_affine, out_mode, tiles_per_clip, lfr_m, lfr_n;
+  int pad_mode, log_mode, whisper_norm, post_affine, out_mode, tiles_per_clip, lfr_m, lfr_n, n_clips;
   float log_floor, post_sub, post_div;
   const int4* fb_desc;    // per filter: (first bin, number of bins, offset into fb_w, 0)
   const float* fb_w;
@@ -214,8 +233,8 @@ B2A_DEV float mel_post(float v, float log_floor, float& lmax, float& vmin) {
   constexpr float kLog = LOGM == LOG_LOG10 ? 0.30102999566398120f : (LOGM == LOG_LN ? 0.69314718055994531f : 6.0205999132796239f);
   if (LOGM != LOG_NONE) v = lg2_ftz(fmaxf(v, log_floor)) * kLog;
   if (WNORM) {
-    lmax = fmaxf(lmax, v);
     v = (v + 4.0f) * 0.25f;
+    lmax = fmaxf(lmax, v);
     vmin = fminf(vmin, v);
   }
   return v;
@@ -229,21 +248,24 @@ B2A_DEV void cp_async_commit_wait_all() {
 }
 
 // Stages the PCM of tile (clip, f0) into `buf` (skewed rows, pitch HOP+1).  Interior tiles use cp.async so that
-// the copy overlaps with the previous tile's FFT stages; edge tiles (reflect / zero padding) go through the index map.
+// the copy overlaps with the previous tile's FFT stages: whole rows of HOP samples, warp w takes rows w, w+NW, ...,
+// every copy an immediate offset from two per-warp base pointers.  Edge tiles (reflect / zero padding, clip end) go
+// through the index map.
 template <class P>
-B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, long long clip, long long f0, int tid, int lane, int warp) {
-  constexpr int HOP = P::HOP, NW = P::NWARPS;
-  constexpr int NROWS = (P::TS + HOP - 1) / HOP, CPR = (HOP + 31) / 32;
-  const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
-  const long long p0 = f0 * HOP;
+B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, int clip, int f0, int tid, int lane, int warp) {
+  constexpr int HOP = P::HOP, NW = P::NWARPS, NROWS = P::NROWS;
+  static_assert(HOP % 32 == 0, "rows are copied as whole 32-lane chunks");
+  const float* __restrict__ xc = prm.x + (long long)clip * prm.clip_stride;
+  const long long p0 = (long long)f0 * HOP;
   const long long j0 = p0 - prm.pad_left;
-  if (j0 >= 0 && j0 + P::TS <= prm.n_samples) {
-    const float* __restrict__ src = xc + j0;
-    for (int r = warp; r < NROWS; r += NW) {
+  if (j0 >= 0 && j0 + NROWS * HOP <= prm.n_samples) {
+    const float* __restrict__ src = xc + j0 + warp * HOP + lane;
+    float* dst = buf + warp * P::PITCH + lane;
 #pragma unroll
-      for (int j = 0; j < CPR; ++j) {
-        const int col = j * 32 + lane;
-        if (col < HOP && r * HOP + col < P::TS) cp_async4(buf + r * P::PITCH + col, src + r * HOP + col);
+    for (int rr = 0; rr < (NROWS + NW - 1) / NW; ++rr) {
+      if (rr * NW + warp < NROWS) {
+#pragma unroll
+        for (int j = 0; j < HOP / 32; ++j) cp_async4(dst + rr * NW * P::PITCH + j * 32, src + rr * NW * HOP + j * 32);
       }
     }
   } else {
@@ -255,19 +277,25 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, lo
 // Persistent kernel: grid = MINB CTAs per SM; every CTA loads its tables once and walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...; with DOUBLE_BUF the next tile's PCM is prefetched (cp.async)
 // into the other spectrum/PCM buffer while the current tile is in its FFT / mel / store stages.
-template <class P, int PRE, int SPEC>
+// MEL == 0: mel step program + run-time log / output modes (any bank).  MEL > 0: baked bank MEL of mel_baked.h with
+// the compile-time post-processing POST; finished values are post-processed in the mel stage (lane == frame) and the
+// store stage is a plain transposing copy.
+template <class P, int PRE, int SPEC, int MEL, int POST>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
   constexpr bool DB = P::DOUBLE_BUF;
+  constexpr bool BAKED = MEL > 0;
   constexpr int OP = FT + 1;  // output staging pitch ([m][frame], conflict-free both ways)
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
+  static_assert(!BAKED || (SPEC == SK_POWER && FT == 32), "baked banks are power-spectrum banks of the 32-frame plans");
   extern __shared__ __align__(16) float smem[];
   float2* s_y = reinterpret_cast<float2*>(smem + (DB ? 2 : 1) * R0W);
   float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   float4* s_bins = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);  // mel step program
+  __shared__ int s_red[2];                                  // per-tile max / min of the normalised values (ordered-int)
   constexpr int SUB = P::SUB, NIT = NW * SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
@@ -281,28 +309,33 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   {
     const float2* __restrict__ tw = TwTable<P>::get();
     for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) s_tw[i] = tw[i];
-    if (!cplx && prm.fb_steps != nullptr)
+    if (!cplx && !BAKED && prm.fb_steps != nullptr)
       for (int i = tid; i < prm.n_steps; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_steps + i);
   }
+  if (tid == 0) {
+    s_red[0] = int(0x80000000u);
+    s_red[1] = 0x7fffffff;
+  }
 
-  const unsigned total_tiles = unsigned(prm.total_tiles), tpc = unsigned(prm.tiles_per_clip);  // < 2^31, checked on the host
-  unsigned t_idx = blockIdx.x;
-  if (t_idx < total_tiles) stage_pcm<P>(prm, smem, t_idx / tpc, (long long)(t_idx % tpc) * FT, tid, lane, warp);
+  // tile walk: (clip, tile) advances by gridDim.x tiles per iteration without divisions in the loop
+  const int tpc = prm.tiles_per_clip, n_clips = prm.n_clips;
+  const int step_clip = int(gridDim.x) / tpc, step_tile = int(gridDim.x) - step_clip * tpc;
+  int clip = int(blockIdx.x) / tpc, tile = int(blockIdx.x) - clip * tpc;
+  if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, tid, lane, warp);
 
-  for (int iter = 0; t_idx < total_tiles; ++iter, t_idx += gridDim.x) {
-    const unsigned uclip = t_idx / tpc;
-    const int tile = int(t_idx - uclip * tpc);
-    const long long clip = uclip;
-    const long long f0 = (long long)tile * FT;
+  for (int iter = 0; clip < n_clips; ++iter) {
+    const int f0 = tile * FT;
     float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile, later the spectrum tile
+    int nclip = clip + step_clip, ntile = tile + step_tile;
+    if (ntile >= tpc) {
+      ntile -= tpc;
+      ++nclip;
+    }
 
     // ---- 1. this tile's PCM has landed; prefetch the next tile into the other buffer ------------------
     cp_async_commit_wait_all();
     __syncthreads();
-    if (DB) {
-      const unsigned nxt = t_idx + gridDim.x;
-      if (nxt < total_tiles) stage_pcm<P>(prm, smem + ((iter & 1) ? 0 : R0W), nxt / tpc, (long long)(nxt % tpc) * FT, tid, lane, warp);
-    }
+    if (DB && nclip < n_clips) stage_pcm<P>(prm, smem + ((iter & 1) ? 0 : R0W), nclip, ntile * FT, tid, lane, warp);
 
     // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
     float mu = 0.0f;
@@ -357,7 +390,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         if (cplx) {
           if (P::CPLX_DIRECT) {
             // tile too large for a staged complex spectrum: store straight to (T', F) global memory
-            if (fl < rows) reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride)[(f0 + fl) * P::NBINS + k] = make_float2(re, im);
+            if (fl < rows)
+              reinterpret_cast<float2*>(prm.out + (long long)clip * prm.out_clip_stride)[(long long)(f0 + fl) * P::NBINS + k] = make_float2(re, im);
           } else {
             reinterpret_cast<float2*>(s_r0)[k * P::P_PITCH + fl] = make_float2(re, im);
           }
@@ -410,19 +444,32 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     if (cplx) {
       if (!P::CPLX_DIRECT) {
         const int nb = P::NBINS;
-        float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + clip * prm.out_clip_stride) + f0 * nb;
+        float2* __restrict__ dst = reinterpret_cast<float2*>(prm.out + (long long)clip * prm.out_clip_stride) + (long long)f0 * nb;
         const float2* sp = reinterpret_cast<const float2*>(s_r0);
         for (int e = tid; e < rows * nb; e += P::NTHREADS) {
           const int r = e / nb, k = e - r * nb;
           dst[e] = sp[k * P::P_PITCH + r];
         }
       }
-      continue;  // the loop-top barrier orders this tile's reads before the next tile's writes
-    }
+    } else {   // (the loop-top barrier orders a complex tile's reads before the next tile's writes)
 
     // ---- 4b. sparse mel projection into the [m][frame] staging tile ------------------------------------
-    const int M = prm.n_mels;
-    {
+    const int M = BAKED ? MelTraits<MEL>::M : prm.n_mels;
+    float lmax = -3.0e38f, vmin = 3.0e38f;   // of the normalised values (Whisper clamp bookkeeping)
+    if (BAKED) {
+      const float log_floor = prm.log_floor;
+      mel_baked<MEL>(wsub, s_r0 + fl, [&](int m, float v) {
+        if (POST == POST_WNORM) {
+          // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
+          v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
+          lmax = fmaxf(lmax, v);
+          vmin = fminf(vmin, v);
+        } else if (POST == POST_LN) {
+          v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
+        }
+        s_o[m * OP + fl] = v;
+      });
+    } else {
       const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
       if (prm.fb_steps != nullptr) {
         mel_steps(s_r0 + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
@@ -440,18 +487,69 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
+    if (BAKED && POST == POST_WNORM) {
+      // warp-level max / min with one REDUX each on the ordered-int encoding, then one shared-memory atomic per warp
+      const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
+      const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
+      if (lane == 0) {
+        atomicMax(&s_red[0], wmax);
+        atomicMin(&s_red[1], wmin);
+      }
+    }
     __syncthreads();
 
-    // ---- 5. log / floor / scale fused into the coalesced store of the staged tile -----------------------
-    float lmax = -3.0e38f, vmin = 3.0e38f;
-    {
+    // ---- 5. store of the staged tile (baked: plain transposing copy; otherwise log / floor / scale fused in) ----
+    float* __restrict__ dst = prm.out + (long long)clip * prm.out_clip_stride;
+    if (BAKED) {
+      if (POST == POST_WNORM && tid == 0) {
+        atomicMax(prm.clip_max + clip, s_red[0]);
+        prm.tile_min[clip * tpc + tile] = s_red[1];
+        s_red[0] = int(0x80000000u);   // the next tile's shared atomics come after at least one more barrier
+        s_red[1] = 0x7fffffff;
+      }
+      constexpr int MB = MelTraits<MEL>::M;
+      if (prm.out_mode == OUT_TM) {
+        // (T', M) rows: lanes run over m, every row a run of coalesced 128-byte segments
+        float* d = dst + (long long)f0 * MB + lane;
+        const float* sr = s_o + lane * OP;
+        for (int r = warp; r < rows; r += NW) {
+#pragma unroll
+          for (int c = 0; c < MB / 32; ++c) d[r * MB + c * 32] = sr[r + c * 32 * OP];
+          if (MB % 32 != 0 && lane < MB % 32) d[r * MB + (MB / 32) * 32] = sr[r + (MB / 32) * 32 * OP];
+        }
+      } else if (prm.out_mode == OUT_MT) {
+        // (M, T') rows: lanes run over frames
+        const long long nfr = prm.n_frames;
+        float* d = dst + f0 + fl;
+        if (frame_ok)
+          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = s_o[m * OP + fl];
+      } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
+        const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
+        const int T = int(prm.n_frames), last_row = int(prm.lfr_rows) - 1;
+        int i_lo = f0 + left - (lm - 1) < 0 ? 0 : (f0 + left - (lm - 1)) / ln;
+        int i_hi = (f0 + rows - 1 + left) / ln;
+        if (f0 + rows >= T || i_hi > last_row) i_hi = last_row;
+        const int nseg = (i_hi - i_lo + 1) * lm;
+        for (int sg = warp; sg < nseg; sg += NW) {
+          const int i = i_lo + sg / lm;
+          const int j = sg - (sg / lm) * lm;
+          int t = i * ln + j - left;
+          t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+          if (t < f0 || t >= f0 + rows) continue;
+          const float* sr = s_o + (t - f0) + lane * OP;
+          float* d = dst + ((long long)i * lm + j) * MB + lane;
+#pragma unroll
+          for (int c = 0; c < MB / 32; ++c) d[c * 32] = sr[c * 32 * OP];
+          if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = sr[(MB / 32) * 32 * OP];
+        }
+      }
+    } else {
       const int log_mode = prm.log_mode;
       const float log_floor = prm.log_floor;
       const bool wnorm = prm.whisper_norm != 0;
-      float* __restrict__ dst = prm.out + clip * prm.out_clip_stride;
       if (prm.out_mode == OUT_TM) {
         // (T', M) rows: lanes run over m
-        dst += f0 * M;
+        dst += (long long)f0 * M;
         auto store_tm = [&](auto post) {
           for (int r = warp; r < rows; r += NW) {
             float* d = dst + r * M + lane;
@@ -512,34 +610,32 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (prm.whisper_norm) {
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
-      }
+    if (!BAKED && prm.whisper_norm) {
+      const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
+      const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
       if (lane == 0) {
-        atomicMax(prm.clip_max + clip, enc_ordered(lmax));
-        atomicMin(prm.tile_min + clip * prm.tiles_per_clip + tile, enc_ordered(vmin));  // ordered-int encoding, memset to 0x7f.. by the host
+        atomicMax(prm.clip_max + clip, wmax);
+        atomicMin(prm.tile_min + clip * tpc + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
       }
     }
+    }  // !cplx
     if (!DB) {
       // single buffer: the next tile's PCM can only be staged once every warp is done with the spectrum tile
       __syncthreads();
-      const unsigned nxt = t_idx + gridDim.x;
-      if (nxt < total_tiles) stage_pcm<P>(prm, smem, nxt / tpc, (long long)(nxt % tpc) * FT, tid, lane, warp);
+      if (nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, tid, lane, warp);
     }
+    clip = nclip;
+    tile = ntile;
   }
 }
 
 // Rewrites only the tiles whose minimum lies below the clip's clamp threshold:
-//   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, ((Lmax - 8) + 4) / 4)   (x -> (x+4)/4 is monotone in fp32)
+//   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, (Lmax + 4) / 4 - 2)   (x -> (x+4)/4 is monotone)
 // WhisperAudio.swift:130-134, S3TokenizerUtils.swift:203-205.
 __global__ void whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                      long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
   const long long clip = blockIdx.x;
-  const float lm = dec_ordered(clip_max[clip]);
-  const float thr = ((lm - 8.0f) + 4.0f) / 4.0f;
+  const float thr = dec_ordered(clip_max[clip]) - 2.0f;   // clip_max holds the maximum of the normalised values: ((Lmax - 8) + 4) / 4 = (Lmax + 4) / 4 - 2
   float* o = out + clip * out_clip_stride;
   for (int t = 0; t < tiles_per_clip; ++t) {
     if (!(dec_ordered(tile_min[clip * tiles_per_clip + t]) < thr)) continue;
@@ -683,7 +779,7 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
   static FrontendParams<P> prm;  // large (window table); filled and launched under the lock
   static std::mutex mu;
@@ -730,6 +826,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.clip_max = a.clip_max;
   prm.tile_min = reinterpret_cast<int*>(a.tile_min);
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
+  prm.n_clips = int(a.batch);
   switch (a.out_mode) {
     case OUT_TM: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
     case OUT_MT: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
@@ -744,23 +841,23 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       return B2A_E_BAD_ARG;
     }
   }
-  const int steps_words = SPEC == SK_CPLX ? 0 : 4 * std::max(a.bank.n_steps, 1);
+  const int steps_words = (SPEC == SK_CPLX || MEL > 0) ? 0 : 4 * std::max(a.bank.n_steps, 1);
   const size_t smem = sizeof(float) * size_t((P::DOUBLE_BUF ? 2 : 1) * (SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
                                              P::N + P::TW_WORDS + steps_words);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 2) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
   static_assert(((P::N + P::TW_WORDS) % 4) == 0, "mel step program must stay 16-byte aligned");
-  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;
-  if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL) {
+  if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL || a.batch > 0x7fffffffLL || a.n_frames > 0x7fffffffLL) {
     if (err) *err = "empty launch";
     return B2A_E_BAD_ARG;
   }
   int dev = 0, n_sm = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC>, P::NTHREADS, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST>, P::NTHREADS, smem)) != cudaSuccess)
     return cuda_fail(e, "occupancy query", err);
   if (per_sm < 1) {
     if (err) *err = "frontend kernel does not fit on this device";
@@ -771,7 +868,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     if ((e = cudaMemsetAsync(a.tile_min, 0x7f, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
-  frontend_kernel<P, PRE, SPEC><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
@@ -783,15 +880,40 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   return B2A_OK;
 }
 
+// Id of the baked bank (mel_baked.h) whose step program equals this one word for word, or 0.
+int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, const int* chunk_s, int n_chunks, int frame_tile, int n_mels) {
+  for (int i = 0; i < kMelBakedCount; ++i) {
+    const MelBakedInfo& b = mel_baked_infos[i];
+    if (b.n_steps != n_steps || b.n_chunks != n_chunks || b.frame_tile != frame_tile || b.n_mels != n_mels) continue;
+    if (memcmp(b.steps, steps, sizeof(float) * 4 * size_t(n_steps)) != 0) continue;
+    if (memcmp(b.chunk_m, chunk_m, sizeof(int) * size_t(n_chunks + 1)) != 0) continue;
+    if (memcmp(b.chunk_s, chunk_s, sizeof(int) * size_t(n_chunks + 1)) != 0) continue;
+    return b.id;
+  }
+  return 0;
+}
+
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int spec = a.out_mode == OUT_COMPLEX ? SK_CPLX : (a.spec_mode == SPEC_POWER ? SK_POWER : SK_MAG);
+  // baked banks (mel_baked.h): the bank's step program matched one of them word for word and the post-processing is the
+  // one the baked kernel was compiled for
+  int post = -1;
+  if (a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
+    if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
+    else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
+  }
   if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE) {
+    if (post == POST_WNORM && a.bank.baked_id == 1) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM>(a, st, launches, err);
+    if (post == POST_WNORM && a.bank.baked_id == 2) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM>(a, st, launches, err);
+    if (post == POST_LN && a.bank.baked_id == 3) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN>(a, st, launches, err);
     if (spec == SK_POWER) return launch_plan<Plan400, PRE_NONE, SK_POWER>(a, st, launches, err);
     if (spec == SK_MAG) return launch_plan<Plan400, PRE_NONE, SK_MAG>(a, st, launches, err);
     return launch_plan<Plan400, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) {
+    if (a.pre_mode == PRE_KALDI && post == POST_LN && a.bank.baked_id == 4 && a.out_mode == OUT_TM)
+      return launch_plan<Plan512, PRE_KALDI, SK_POWER, 4, POST_LN>(a, st, launches, err);
     if (a.pre_mode == PRE_KALDI && spec == SK_POWER) return launch_plan<Plan512, PRE_KALDI, SK_POWER>(a, st, launches, err);
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }

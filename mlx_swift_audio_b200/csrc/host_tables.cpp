@@ -418,4 +418,25 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
   return int(sb.steps.size() / 4);
 }
 
+// Build hook (host only): the mel step program of `bank` for a CTA shape, as raw 32-bit words (4 per step) plus the
+// per-chunk filter / step boundaries.  tools/gen_mel_baked.py turns the programs of the reference's standard banks into
+// straight-line device code at build time; at run time the program built for the caller's bank is compared with the baked
+// one word for word before the baked kernel is chosen.  Returns the number of steps, -1 if the bank has no step program,
+// -2 if `cap_steps` is too small.
+int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int frame_tile, int out_pitch, int n_chunks,
+                               unsigned* steps_out, int cap_steps, int* chunk_m, int* chunk_s) {
+  b2a::SparseBank sb;
+  b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, frame_tile, out_pitch, n_chunks, sb);
+  if (sb.steps.empty()) return -1;
+  const int n = int(sb.steps.size() / 4);
+  if (n > cap_steps) return -2;
+  memcpy(steps_out, sb.steps.data(), sizeof(float) * sb.steps.size());
+  for (int c = 0; c <= n_chunks; ++c) {
+    chunk_m[c] = sb.chunk_m[c];
+    chunk_s[c] = sb.chunk_s[c];
+  }
+  return n;
+}
+
 }  // extern "C"

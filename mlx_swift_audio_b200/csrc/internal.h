@@ -49,6 +49,7 @@ struct DeviceBank {  // sparse filterbank in device memory
   const int* host_chunk_s = nullptr;
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
+  int baked_id = 0;     // > 0: the step program equals baked bank `baked_id` of mel_baked.h (straight-line kernel available)
 };
 
 struct FrontendArgs {
@@ -85,6 +86,7 @@ struct FrontendArgs {
 // Returns 0 or a b2a_status; sets *launches to the number of kernels enqueued.
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err);
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames);
+int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, const int* chunk_s, int n_chunks, int frame_tile, int n_mels);
 bool frontend_plan_exists(int n_fft, int hop, int win_len);
 int init_frontend_tables(std::string* err);  // once per device: twiddle tables into __constant__ memory
 
