@@ -94,8 +94,9 @@ const std::vector<float>& cached_window(b2a_ctx* c, const std::string& key, cons
 
 int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int n_bins, bool bin_major,
                 const std::function<int(float*)>& make_dense, DeviceBank* out) {
-  int frame_tile = 32, n_chunks = 9;
-  frontend_plan_shape(n_fft, &frame_tile, &n_chunks);
+  const PlanShape* ps = plan_shape(n_fft);
+  if (!ps) return fail(c, B2A_E_UNSUPPORTED, "no FFT plan for this n_fft");
+  const int frame_tile = ps->frame_tile, n_chunks = ps->n_chunks;
   const std::string key = key0 + "_ft" + std::to_string(frame_tile) + "_c" + std::to_string(n_chunks);
   auto it = c->banks.find(key);
   if (it == c->banks.end()) {
@@ -119,7 +120,10 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
     if (!bs.host.weights.empty())
       if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
         return cu(c, e, "bank upload");
-    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, frame_tile + 1, n_chunks, bs.host);
+    std::vector<int> slots;
+    spectrum_slots(*ps, slots);
+    if (n_bins > int(slots.size())) return fail(c, B2A_E_BAD_ARG, "filterbank has more bins than the spectrum");
+    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, frame_tile + 1, n_chunks, slots.data(), bs.host);
     if (!bs.host.steps.empty()) {
       if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
       if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess)

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -56,7 +57,7 @@ __constant__ float2 c_tw400[20 * 9];
 __constant__ float2 c_tw512[32 * 7];
 __constant__ float2 c_tw1920[32 * 29];
 
-template <int N_, int WIN_, int N1_, int N2_, int HOP_, int FT_, int NWARPS_, int MINB_>
+template <int N_, int WIN_, int N1_, int N2_, int HOP_, int FT_, int NWARPS_, int MINB_, bool DB_>
 struct Plan {
   static constexpr int N = N_, WIN = WIN_, N1 = N1_, N2 = N2_, HOP = HOP_, FT = FT_, NWARPS = NWARPS_, MINB = MINB_;
   static constexpr int H1 = N1 / 2;
@@ -66,26 +67,33 @@ struct Plan {
   static constexpr int PITCH = HOP + 1;            // skewed row pitch
   static constexpr int NROWS = (TS + HOP - 1) / HOP;  // rows of HOP samples staged per tile (the last one may be partial)
   static constexpr int PCM_WORDS = (NROWS * PITCH + 3) & ~3;
-  static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT
+  static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT; stage B leaves the real spectrum tile here too
   static constexpr int P_PITCH = FT + 1;
   static constexpr bool CPLX_DIRECT = (N / 2 + 1) * (FT + 1) * 2 * 4 > 64 * 1024;  // complex tile would not fit: stft() stores directly
   static constexpr int MAX_STEPS = NBINS + 32 * NWARPS * (32 / FT);    // mel step program: one step per bin (+ chunk-boundary repeats, empty filters)
-  static constexpr int P_WORDS_REAL = NBINS * FT;
   static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
-  static constexpr int R0_WORDS_REAL = PCM_WORDS > P_WORDS_REAL ? PCM_WORDS : P_WORDS_REAL;
+  // region 0: the PCM tile, later the [m][frame] output staging tile (plain stft(): the complex spectrum tile)
+  static constexpr int R0_WORDS_REAL = PCM_WORDS;
   static constexpr int R0_WORDS_CPLX = CPLX_DIRECT ? ((PCM_WORDS + 3) & ~3) : (((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3);
   static constexpr int TW_WORDS = (2 * N2 * (N1 / 2 - 1) + 3) & ~3;  // padded so that the mel program behind it stays 16-byte aligned
-  static constexpr bool DOUBLE_BUF = MINB_ > 1;       // second PCM/spectrum buffer: prefetch the next tile with cp.async
+  static constexpr bool DOUBLE_BUF = DB_;           // second region 0: prefetch the next tile's PCM with cp.async during this tile
   static constexpr int SUB = 32 / FT;               // a warp covers FT frames x SUB items (lane = sub * FT + frame)
   static constexpr int NCHUNK = NWARPS * SUB;       // mel-program chunks
   static_assert(N1 * N2 == N, "N = N1*N2");
   static_assert(FT == 32 || FT == 16, "lane == (item, frame)");
 };
-// 400 = 20 x 20: 20 stage-A items and 9 complex + (real + odd-real) stage-B items split evenly over 10 warps
-using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 2>;
-using Plan512 = Plan<512, 400, 16, 32, 160, 32, 9, 2>;
+// 400 = 20 x 20: 20 stage-A items and 9 complex + 1 (real + odd-real) stage-B items split evenly over 10 warps; 74.4 KB of
+// shared memory per CTA -> three CTAs (30 warps) per SM, which hides the barrier / shared-memory latencies better than
+// prefetching the next tile into a second buffer with two CTAs per SM
+using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 3, false>;
+using Plan512 = Plan<512, 400, 16, 32, 160, 32, 8, 2, false>;
 // n_fft 1920 (S3Gen 24 kHz mel): the exchange buffer only fits 16 frames, so half-warps take different items
-using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1>;
+using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1, false>;
+template <class P> constexpr bool plan_matches(const PlanShape& s) {
+  return s.n_fft == P::N && s.n1 == P::N1 && s.n2 == P::N2 && s.frame_tile == P::FT && s.n_warps == P::NWARPS && s.n_chunks == P::NCHUNK;
+}
+static_assert(plan_matches<Plan400>(kPlanShapes[0]) && plan_matches<Plan512>(kPlanShapes[1]) && plan_matches<Plan1920>(kPlanShapes[2]),
+              "internal.h kPlanShapes (host tables, baked mel generator) must describe these plans");
 
 template <class P> struct TwTable;
 template <> struct TwTable<Plan400> { static B2A_DEV const float2* get() { return c_tw400; } };
@@ -247,6 +255,17 @@ B2A_DEV void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// Row of the exchange buffer that holds bin k after stage B (same map as spectrum_slots() in host_tables.cpp)
+template <class P>
+B2A_DEV int spectrum_slot(int k) {
+  constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, N = P::N;
+  const int r = k % N1;
+  if (r == 0) return k / N1;
+  if (r == H1) return N2 / 2 + 1 + (k - H1) / N1;
+  if (r < H1) return r * 2 * N2 + k / N1;
+  return (N1 - r) * 2 * N2 + (N - (N1 - r) - k) / N1;
+}
+
 // Stages the PCM of tile (clip, f0) into `buf` (skewed rows, pitch HOP+1).  Interior tiles use cp.async so that
 // the copy overlaps with the previous tile's FFT stages: whole rows of HOP samples, warp w takes rows w, w+NW, ...,
 // every copy an immediate offset from two per-warp base pointers.  Edge tiles (reflect / zero padding, clip end) go
@@ -291,7 +310,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   static_assert(!BAKED || (SPEC == SK_POWER && FT == 32), "baked banks are power-spectrum banks of the 32-frame plans");
   extern __shared__ __align__(16) float smem[];
   float2* s_y = reinterpret_cast<float2*>(smem + (DB ? 2 : 1) * R0W);
-  float* s_o = reinterpret_cast<float*>(s_y);               // output staging aliases the exchange buffer
+  float* s_p = reinterpret_cast<float*>(s_y);               // stage B leaves the spectrum tile in the exchange buffer (spectrum_slots)
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   float4* s_bins = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);  // mel step program
@@ -325,7 +344,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
   for (int iter = 0; clip < n_clips; ++iter) {
     const int f0 = tile * FT;
-    float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile, later the spectrum tile
+    float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile, later the output staging tile
+    float* s_o = s_r0;
     int nclip = clip + step_clip, ntile = tile + step_tile;
     if (ntile >= tpc) {
       ntile -= tpc;
@@ -344,11 +364,11 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       static_assert(PRE != PRE_KALDI || SUB == 1, "Kaldi pre-processing is built for 32-frame tiles");
       const int fk = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
       for (int o = warp; o < WIN; o += NW) part += s_r0[fk * P::PITCH + o + o / HOP];
-      s_o[warp * FT + fl] = part;
+      s_p[warp * FT + fl] = part;   // scratch: the exchange buffer is idle until stage A
       __syncthreads();
       float tot = 0.0f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) tot += s_o[w * FT + fl];
+      for (int w = 0; w < NW; ++w) tot += s_p[w * FT + fl];
       mu = tot / float(WIN);
       __syncthreads();
     }
@@ -385,8 +405,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     __syncthreads();
 
     // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
+    // The power / magnitude of every bin goes back into the item's own rows of the exchange buffer (row = slot of
+    // spectrum_slots(), FT floats per row): no separate spectrum tile.  An item's rows are touched by its (half-)warp only,
+    // and every lane has its inputs in registers before any lane stores (__syncwarp).
     {
-      auto put = [&](int k, float re, float im) {
+      const unsigned item_mask = FT == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
+      auto put = [&](int it, int slot, int k, float re, float im) {
         if (cplx) {
           if (P::CPLX_DIRECT) {
             // tile too large for a staged complex spectrum: store straight to (T', F) global memory
@@ -397,26 +421,32 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
           }
         } else {
           const float pw = re * re + im * im;
-          s_r0[k * FT + fl] = SPEC == SK_POWER ? pw : sqrtf(pw);
+          s_p[(it * 2 * N2 + slot) * FT + fl] = SPEC == SK_POWER ? pw : sqrtf(pw);
         }
       };
-      for (int it = wsub; it <= H1; it += NIT) {
+      for (int it = wsub; it < H1; it += NIT) {
         if (it == 0) {
-          float in[N2];
+          // k1 = 0 (real DFT of the DC row) and k1 = N1/2 (odd-frequency real DFT of the Nyquist row) share the row block
+          float xa[N2], xb[N2];
 #pragma unroll
-          for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].x;
-          float ur[N2 / 2 + 1], ui[N2 / 2 + 1];
-          rdft(in, ur, ui);
+          for (int n2 = 0; n2 < N2; ++n2) {
+            const float2 v = s_y[n2 * FT + fl];
+            xa[n2] = v.x;
+            xb[n2] = v.y;
+          }
+          __syncwarp(item_mask);
+          {
+            float ur[N2 / 2 + 1], ui[N2 / 2 + 1];
+            rdft(xa, ur, ui);
 #pragma unroll
-          for (int k2 = 0; k2 <= N2 / 2; ++k2) put(N1 * k2, ur[k2], ui[k2]);
-        } else if (it == H1) {
-          float in[N2];
+            for (int k2 = 0; k2 <= N2 / 2; ++k2) put(0, k2, N1 * k2, ur[k2], ui[k2]);
+          }
+          {
+            float ur[(N2 - 1) / 2 + 1], ui[(N2 - 1) / 2 + 1];
+            rdftodd(xb, ur, ui);
 #pragma unroll
-          for (int n2 = 0; n2 < N2; ++n2) in[n2] = s_y[n2 * FT + fl].y;
-          float ur[(N2 - 1) / 2 + 1], ui[(N2 - 1) / 2 + 1];
-          rdftodd(in, ur, ui);
-#pragma unroll
-          for (int k2 = 0; k2 <= (N2 - 1) / 2; ++k2) put(H1 + N1 * k2, ur[k2], ui[k2]);
+            for (int k2 = 0; k2 <= (N2 - 1) / 2; ++k2) put(0, N2 / 2 + 1 + k2, H1 + N1 * k2, ur[k2], ui[k2]);
+          }
         } else {
           float xr[N2], xi[N2], ur[N2], ui[N2];
           const float2* yb = s_y + it * N2 * FT + fl;
@@ -426,12 +456,13 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
             xr[n2] = v.x;
             xi[n2] = v.y;
           }
+          __syncwarp(item_mask);
           cdft(xr, xi, ur, ui);
 #pragma unroll
           for (int k2 = 0; k2 < N2; ++k2) {
             const int kc = N1 * k2;  // k = it + kc
-            if (kc + H1 <= N / 2) put(it + kc, ur[k2], ui[k2]);       // it < H1  =>  it + kc <= N/2
-            else put(N - kc - it, ur[k2], -ui[k2]);                    // conjugate mirror
+            if (kc + H1 <= N / 2) put(it, k2, it + kc, ur[k2], ui[k2]);       // it < H1  =>  it + kc <= N/2
+            else put(it, k2, N - kc - it, ur[k2], -ui[k2]);                    // conjugate mirror
           }
         }
       }
@@ -458,7 +489,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     float lmax = -3.0e38f, vmin = 3.0e38f;   // of the normalised values (Whisper clamp bookkeeping)
     if (BAKED) {
       const float log_floor = prm.log_floor;
-      mel_baked<MEL>(wsub, s_r0 + fl, [&](int m, float v) {
+      mel_baked<MEL>(wsub, s_p + fl, [&](int m, float v) {
         if (POST == POST_WNORM) {
           // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
           v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
@@ -472,7 +503,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     } else {
       const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
       if (prm.fb_steps != nullptr) {
-        mel_steps(s_r0 + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
+        mel_steps(s_p + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
       } else {
         // generic path: arbitrary filterbank, one short loop per filter
         const int4* __restrict__ fdesc = prm.fb_desc;
@@ -480,9 +511,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         for (int m = ma; m < mb; ++m) {
           const int4 d = __ldg(fdesc + m);
           const float* __restrict__ w = fw + d.z;
-          const float* pp = s_r0 + d.x * FT + fl;
           float v = 0.0f;
-          for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), pp[i * FT], v);
+          for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), s_p[spectrum_slot<P>(d.x + i) * FT + fl], v);
           s_o[m * OP + fl] = v;
         }
       }
@@ -760,22 +790,9 @@ bool frontend_plan_exists(int n_fft, int hop, int win_len) {
          (n_fft == 1920 && hop == 480 && win_len == 1920);
 }
 
-void frontend_plan_shape(int n_fft, int* frame_tile, int* n_chunks) {
-  if (n_fft == 1920) {
-    *frame_tile = Plan1920::FT;
-    *n_chunks = Plan1920::NCHUNK;
-  } else if (n_fft == 512) {
-    *frame_tile = Plan512::FT;
-    *n_chunks = Plan512::NCHUNK;
-  } else {
-    *frame_tile = Plan400::FT;
-    *n_chunks = Plan400::NCHUNK;
-  }
-}
-
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
-  int ft, nc;
-  frontend_plan_shape(n_fft, &ft, &nc);
+  const PlanShape* ps = plan_shape(n_fft);
+  const int ft = ps ? ps->frame_tile : 32;
   return int((n_frames + ft - 1) / ft);
 }
 
@@ -835,8 +852,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   for (int o = 0; o < P::WIN; ++o) prm.window[o] = a.window[o];
   if (SPEC != SK_CPLX) {
-    // the (M x frames) staging tile aliases the exchange buffer
-    if (a.bank.n_mels <= 0 || a.bank.n_mels * (P::FT + 1) > P::Y_WORDS || a.bank.n_steps > P::MAX_STEPS) {
+    // the (M x frames) staging tile takes the place of the PCM tile
+    if (a.bank.n_mels <= 0 || a.bank.n_mels * (P::FT + 1) > P::R0_WORDS_REAL || a.bank.n_steps > P::MAX_STEPS) {
       if (err) *err = "n_mels out of range for this plan";
       return B2A_E_BAD_ARG;
     }
@@ -863,6 +880,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     if (err) *err = "frontend kernel does not fit on this device";
     return B2A_E_CUDA;
   }
+  if (const char* cap = getenv("B2A_DEBUG_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));  // occupancy experiments
   const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
   if (a.whisper_norm) {
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
@@ -899,7 +917,8 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   // baked banks (mel_baked.h): the bank's step program matched one of them word for word and the post-processing is the
   // one the baked kernel was compiled for
   int post = -1;
-  if (a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
+  static const bool no_baked = getenv("B2A_DEBUG_NO_BAKED") != nullptr;  // A/B experiments: force the step-program kernel
+  if (!no_baked && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }

@@ -229,8 +229,22 @@ void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major
 // W[m][k]*P[k] to the open accumulator and W[m+1][k]*P[k] to the next one, and its last step emits.  A chunk
 // (the filters of one warp) starts with zero-emit steps for the bins its first filter shares with the
 // previous chunk's last filter.  Chunks are cut at filter boundaries, balanced by step count.
+void spectrum_slots(const PlanShape& ps, std::vector<int>& slot_of_bin) {
+  const int N = ps.n_fft, N1 = ps.n1, N2 = ps.n2, H1 = N1 / 2;
+  slot_of_bin.assign(N / 2 + 1, -1);
+  for (int k = 0; k <= N / 2; ++k) {
+    const int r = k % N1;
+    int slot;
+    if (r == 0) slot = k / N1;                                   // item 0, real part: bins N1*k2, k2 = 0..N2/2
+    else if (r == H1) slot = N2 / 2 + 1 + (k - H1) / N1;         // item 0, odd part: bins H1 + N1*k2
+    else if (r < H1) slot = r * 2 * N2 + k / N1;                 // item r, direct output k2 = k / N1
+    else slot = (N1 - r) * 2 * N2 + (N - (N1 - r) - k) / N1;      // item N1-r, mirrored output k2: k = N - N1*k2 - (N1-r)
+    slot_of_bin[k] = slot;
+  }
+}
+
 void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
-                       SparseBank& sb) {
+                       const int* bin_slot, SparseBank& sb) {
   sb.steps.clear();
   sb.chunk_m.assign(n_chunks + 1, 0);
   sb.chunk_s.assign(n_chunks + 1, 0);
@@ -249,14 +263,15 @@ void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major
     const int m = sb.bin_mlo[k];
     if (m >= 0 && m < n_mels && (at(m, k) != 0.0f || at(m + 1, k) != 0.0f)) own[m].push_back(k);
   }
-  // balance: cost of a filter = number of its steps (at least one: the emit)
+  // balance: cost of a filter = 3 instructions per step (spectrum load, two multiply-adds) + 6 per emit (floor, log, scale, store)
+  auto cost = [&](int m) { return (long long)(3 * own[m].size() + 6); };
   long long total = 0;
-  for (int m = 0; m < n_mels; ++m) total += std::max<size_t>(own[m].size(), 1);
+  for (int m = 0; m < n_mels; ++m) total += cost(m);
   {
     long long run = 0;
     int w = 1;
     for (int m = 0; m < n_mels && w < n_chunks; ++m) {
-      run += std::max<size_t>(own[m].size(), 1);
+      run += cost(m);
       while (w < n_chunks && run * n_chunks >= total * w) sb.chunk_m[w++] = m + 1;
     }
     for (; w <= n_chunks; ++w) sb.chunk_m[w] = n_mels;
@@ -265,7 +280,7 @@ void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major
   auto push = [&](float wlo, float whi, int k, bool emit) {
     sb.steps.push_back(wlo);
     sb.steps.push_back(whi);
-    sb.steps.push_back(bits(k * frame_tile * int(sizeof(float))));
+    sb.steps.push_back(bits((bin_slot ? bin_slot[k] : k) * frame_tile * int(sizeof(float))));
     sb.steps.push_back(bits(emit ? out_pitch * int(sizeof(float)) : 0));
   };
   for (int c = 0; c < n_chunks; ++c) {
@@ -393,7 +408,7 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
   b2a::SparseBank sb;
   b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
   const int kChunks = 9;
-  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, 1, kChunks, sb);
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, 1, kChunks, nullptr, sb);
   if (sb.steps.empty()) return -1;
   for (int c = 0; c < kChunks; ++c) {
     float acc0 = 0.0f, acc1 = 0.0f;
@@ -418,16 +433,24 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
   return int(sb.steps.size() / 4);
 }
 
-// Build hook (host only): the mel step program of `bank` for a CTA shape, as raw 32-bit words (4 per step) plus the
+// Build hook (host only): the mel step program of `bank` for the FFT plan of `n_fft`, as raw 32-bit words (4 per step) plus the
 // per-chunk filter / step boundaries.  tools/gen_mel_baked.py turns the programs of the reference's standard banks into
 // straight-line device code at build time; at run time the program built for the caller's bank is compared with the baked
 // one word for word before the baked kernel is chosen.  Returns the number of steps, -1 if the bank has no step program,
 // -2 if `cap_steps` is too small.
-int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int frame_tile, int out_pitch, int n_chunks,
-                               unsigned* steps_out, int cap_steps, int* chunk_m, int* chunk_s) {
+int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int n_fft, int out_pitch,
+                               unsigned* steps_out, int cap_steps, int* chunk_m, int* chunk_s, int* n_chunks_out, int* frame_tile_out) {
+  const b2a::PlanShape* ps = b2a::plan_shape(n_fft);
+  if (!ps) return -3;
+  const int frame_tile = ps->frame_tile, n_chunks = ps->n_chunks;
+  *n_chunks_out = n_chunks;
+  *frame_tile_out = frame_tile;
+  std::vector<int> slots;
+  b2a::spectrum_slots(*ps, slots);
+  if (n_bins > int(slots.size())) return -3;
   b2a::SparseBank sb;
   b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
-  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, frame_tile, out_pitch, n_chunks, sb);
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, frame_tile, out_pitch, n_chunks, slots.data(), sb);
   if (sb.steps.empty()) return -1;
   const int n = int(sb.steps.size() / 4);
   if (n > cap_steps) return -2;

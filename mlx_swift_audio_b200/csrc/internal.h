@@ -23,9 +23,21 @@ int mel_filters_funasr(int sample_rate, int n_fft, int n_mels, float* out);
 int mel_filters_htk_int(int sample_rate, int n_fft, int n_mels, float f_min, float f_max, float* out);
 int64_t reflect_pad_index(int64_t i, int64_t n, int64_t pad);
 void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major, SparseBank& sb);
+// Shape of the frontend kernel's FFT plans (frontend.cu static_asserts that its Plan types agree): n_fft = n1 * n2, CTA tile
+// of `frame_tile` frames, `n_chunks` mel chunks (one per warp, or per half-warp for 16-frame tiles).
+struct PlanShape { int n_fft, n1, n2, frame_tile, n_warps, n_chunks; };
+constexpr PlanShape kPlanShapes[3] = {{400, 20, 20, 32, 10, 10}, {512, 16, 32, 32, 8, 8}, {1920, 60, 32, 16, 8, 16}};
+inline const PlanShape* plan_shape(int n_fft) {
+  for (const PlanShape& p : kPlanShapes)
+    if (p.n_fft == n_fft) return &p;
+  return nullptr;
+}
+// Stage B leaves the spectrum tile in the exchange buffer, item by item: slot_of_bin[k] is the row (of frame_tile floats)
+// that holds bin k.  Item k1 = k mod n1 (or n1 - k mod n1 for the conjugate-mirrored bins) owns rows [k1*2*n2, (k1+1)*2*n2).
+void spectrum_slots(const PlanShape& ps, std::vector<int>& slot_of_bin);
+// bin_slot: nullptr = identity (bin k in row k)
 void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
-                       SparseBank& sb);
-void frontend_plan_shape(int n_fft, int* frame_tile, int* n_chunks);  // CTA shape the mel program must be compiled for
+                       const int* bin_slot, SparseBank& sb);
 
 // ---- fused STFT -> (power | magnitude) -> mel -> log front-end (frontend.cu) -----------------
 enum PadMode { PAD_NONE = 0, PAD_REFLECT = 1, PAD_ZERO = 2 };

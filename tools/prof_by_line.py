@@ -65,6 +65,8 @@ if len(sys.argv) > 5:
         cur, _ = seq[i]
         if cur[0] == 'codelets.h':
             return 'codelets(' + str(cur[3]) + ')'
+        if cur[0] == 'mel_baked.h':
+            return 'mel_baked'
         key = (cur[0], cur[1])
         if key[0] == 'frontend.cu':
             for lo, hi in ranges:
