@@ -213,7 +213,7 @@ B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const 
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */
 B2A_API int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out);
 /* Build hook (host only): raw mel step program for a CTA shape (see tools/gen_mel_baked.py). */
-B2A_API int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int n_fft, int out_pitch,
+B2A_API int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int n_fft,
                                        unsigned* steps_out, int cap_steps, int* chunk_m, int* chunk_s, int* n_chunks_out,
                                        int* frame_tile_out);
 

@@ -123,7 +123,9 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
     std::vector<int> slots;
     spectrum_slots(*ps, slots);
     if (n_bins > int(slots.size())) return fail(c, B2A_E_BAD_ARG, "filterbank has more bins than the spectrum");
-    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, frame_tile + 1, n_chunks, slots.data(), bs.host);
+    std::vector<int> words;
+    if (!output_words(*ps, n_mels, words)) return fail(c, B2A_E_BAD_ARG, "n_mels out of range for this FFT plan");
+    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, words.data(), n_chunks, slots.data(), bs.host);
     if (!bs.host.steps.empty()) {
       if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
       if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess)

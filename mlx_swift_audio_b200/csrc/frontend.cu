@@ -196,42 +196,43 @@ B2A_DEV float lg2_ftz(float x) {
   return y;
 }
 
-// Branch-free sparse mel projection for one warp's chunk of filters.  The filterbank is compiled on the host
-// into a "step program": step = (w_lo, w_hi, byte offset of the spectrum bin, emit stride).  Each step adds
-// w_lo*P to the open filter and w_hi*P to the next one; a non-zero emit stride stores the open filter's sum
-// to the [m][frame] staging tile, advances the output pointer and shifts the accumulators.  A bin touches at
-// most two adjacent triangular filters; filters without bins get a zero-weight step.  LANE == FRAME.
-B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, float*& so) {
-  const int adv = __float_as_int(t.w);
+// Sparse mel projection for one warp's chunk of filters.  The filterbank is compiled on the host into a "step
+// program": step = (w_lo, w_hi, byte offset of the spectrum bin's row, emit word).  Each step adds w_lo*P to the open filter
+// and w_hi*P to the next one; a non-zero emit word (byte offset of the filter's staging position, see output_words() in
+// host_tables.cpp) stores the open filter's sum and shifts the accumulators.  A bin touches at most two adjacent triangular
+// filters; filters without bins get a zero-weight step.  LANE == FRAME.  The program is read straight from global memory:
+// every lane reads the same 16 bytes (one L1 sector per step), which keeps shared memory for a third CTA per SM.
+B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, char* so_lane) {
+  const int w = __float_as_int(t.w);
   acc0 = fmaf(t.x, pk, acc0);
   acc1 = fmaf(t.y, pk, acc1);
-  const bool e = adv != 0;
-  if (e) *so = acc0;
-  so = reinterpret_cast<float*>(reinterpret_cast<char*>(so) + adv);
-  acc0 = e ? acc1 : acc0;
-  acc1 = e ? 0.0f : acc1;
+  if (w != 0) {   // warp-uniform
+    *reinterpret_cast<float*>(so_lane + w) = acc0;
+    acc0 = acc1;
+    acc1 = 0.0f;
+  }
 }
 
-B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_in) {
-  float* so = so_in;
+B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_lane_f) {
+  char* so_lane = reinterpret_cast<char*>(so_lane_f);
   float acc0 = 0.0f, acc1 = 0.0f;
   const char* pb = reinterpret_cast<const char*>(p_lane);
   int s = s0;
-  // four steps per iteration, all shared-memory loads issued before the (serial) accumulator updates
+  // four steps per iteration, all loads issued before the (serial) accumulator updates
   for (; s + 4 <= s1; s += 4) {
-    const float4 t0 = steps[s], t1 = steps[s + 1], t2 = steps[s + 2], t3 = steps[s + 3];
+    const float4 t0 = __ldg(steps + s), t1 = __ldg(steps + s + 1), t2 = __ldg(steps + s + 2), t3 = __ldg(steps + s + 3);
     const float p0 = *reinterpret_cast<const float*>(pb + __float_as_int(t0.z));
     const float p1 = *reinterpret_cast<const float*>(pb + __float_as_int(t1.z));
     const float p2 = *reinterpret_cast<const float*>(pb + __float_as_int(t2.z));
     const float p3 = *reinterpret_cast<const float*>(pb + __float_as_int(t3.z));
-    mel_step_apply(t0, p0, acc0, acc1, so);
-    mel_step_apply(t1, p1, acc0, acc1, so);
-    mel_step_apply(t2, p2, acc0, acc1, so);
-    mel_step_apply(t3, p3, acc0, acc1, so);
+    mel_step_apply(t0, p0, acc0, acc1, so_lane);
+    mel_step_apply(t1, p1, acc0, acc1, so_lane);
+    mel_step_apply(t2, p2, acc0, acc1, so_lane);
+    mel_step_apply(t3, p3, acc0, acc1, so_lane);
   }
   for (; s < s1; ++s) {
-    const float4 t = steps[s];
-    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so);
+    const float4 t = __ldg(steps + s);
+    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so_lane);
   }
 }
 
@@ -264,6 +265,14 @@ B2A_DEV int spectrum_slot(int k) {
   if (r == H1) return N2 / 2 + 1 + (k - H1) / N1;
   if (r < H1) return r * 2 * N2 + k / N1;
   return (N1 - r) * 2 * N2 + (N - (N1 - r) - k) / N1;
+}
+
+// Staging position of mel value (filter m, frame f) = out_base_words(m) + f: word offset into the exchange buffer
+// (same map as output_words() in host_tables.cpp; bank = (m + f) mod 32)
+template <class P>
+B2A_DEV constexpr int out_base_words(int m) {
+  constexpr int CAP = ((P::N2 - 1) * P::FT - (P::FT - 1)) / (P::FT + 1);
+  return ((m / CAP) * 2 * P::N2 + P::N2 + 1) * P::FT + (CAP * (m / CAP)) % P::FT + (m % CAP) * (P::FT + 1);
 }
 
 // Stages the PCM of tile (clip, f0) into `buf` (skewed rows, pitch HOP+1).  Interior tiles use cp.async so that
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   constexpr bool cplx = SPEC == SK_CPLX;
   constexpr bool DB = P::DOUBLE_BUF;
   constexpr bool BAKED = MEL > 0;
-  constexpr int OP = FT + 1;  // output staging pitch ([m][frame], conflict-free both ways)
+  constexpr bool EARLY_PREFETCH = !cplx && !DB;   // the PCM region is dead after stage A: refill it during stage B / mel / store
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
   static_assert(!BAKED || (SPEC == SK_POWER && FT == 32), "baked banks are power-spectrum banks of the 32-frame plans");
   extern __shared__ __align__(16) float smem[];
@@ -313,7 +322,6 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float* s_p = reinterpret_cast<float*>(s_y);               // stage B leaves the spectrum tile in the exchange buffer (spectrum_slots)
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
-  float4* s_bins = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);  // mel step program
   __shared__ int s_red[2];                                  // per-tile max / min of the normalised values (ordered-int)
   constexpr int SUB = P::SUB, NIT = NW * SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -328,8 +336,6 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   {
     const float2* __restrict__ tw = TwTable<P>::get();
     for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) s_tw[i] = tw[i];
-    if (!cplx && !BAKED && prm.fb_steps != nullptr)
-      for (int i = tid; i < prm.n_steps; i += P::NTHREADS) s_bins[i] = __ldg(prm.fb_steps + i);
   }
   if (tid == 0) {
     s_red[0] = int(0x80000000u);
@@ -344,8 +350,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
   for (int iter = 0; clip < n_clips; ++iter) {
     const int f0 = tile * FT;
-    float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile, later the output staging tile
-    float* s_o = s_r0;
+    float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile (plain stft(): later the complex spectrum tile)
     int nclip = clip + step_clip, ntile = tile + step_tile;
     if (ntile >= tpc) {
       ntile -= tpc;
@@ -403,6 +408,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
     __syncthreads();
+    if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, tid, lane, warp);
 
     // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
     // The power / magnitude of every bin goes back into the item's own rows of the exchange buffer (row = slot of
@@ -484,7 +490,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     } else {   // (the loop-top barrier orders a complex tile's reads before the next tile's writes)
 
-    // ---- 4b. sparse mel projection into the [m][frame] staging tile ------------------------------------
+    // ---- 4b. sparse mel projection; finished values wait in the free rows of the exchange buffer (output_words()) ----
     const int M = BAKED ? MelTraits<MEL>::M : prm.n_mels;
     float lmax = -3.0e38f, vmin = 3.0e38f;   // of the normalised values (Whisper clamp bookkeeping)
     if (BAKED) {
@@ -498,12 +504,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         } else if (POST == POST_LN) {
           v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
         }
-        s_o[m * OP + fl] = v;
+        s_p[out_base_words<P>(m) + fl] = v;
       });
     } else {
       const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
       if (prm.fb_steps != nullptr) {
-        mel_steps(s_p + fl, s_bins, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_o + ma * OP + fl);
+        mel_steps(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl);
       } else {
         // generic path: arbitrary filterbank, one short loop per filter
         const int4* __restrict__ fdesc = prm.fb_desc;
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
           const float* __restrict__ w = fw + d.z;
           float v = 0.0f;
           for (int i = 0; i < d.y; ++i) v = fmaf(__ldg(w + i), s_p[spectrum_slot<P>(d.x + i) * FT + fl], v);
-          s_o[m * OP + fl] = v;
+          s_p[out_base_words<P>(m) + fl] = v;
         }
       }
     }
@@ -538,39 +544,49 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         s_red[1] = 0x7fffffff;
       }
       constexpr int MB = MelTraits<MEL>::M;
-      if (prm.out_mode == OUT_TM) {
-        // (T', M) rows: lanes run over m, every row a run of coalesced 128-byte segments
-        float* d = dst + (long long)f0 * MB + lane;
-        const float* sr = s_o + lane * OP;
-        for (int r = warp; r < rows; r += NW) {
-#pragma unroll
-          for (int c = 0; c < MB / 32; ++c) d[r * MB + c * 32] = sr[r + c * 32 * OP];
-          if (MB % 32 != 0 && lane < MB % 32) d[r * MB + (MB / 32) * 32] = sr[r + (MB / 32) * 32 * OP];
-        }
-      } else if (prm.out_mode == OUT_MT) {
+      constexpr int NC = MB > 0 ? (MB + 31) / 32 : 1;   // (MEL == 0 instantiates this dead branch with MB == 0)
+      if (prm.out_mode == OUT_MT) {
         // (M, T') rows: lanes run over frames
         const long long nfr = prm.n_frames;
         float* d = dst + f0 + fl;
         if (frame_ok)
-          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = s_o[m * OP + fl];
-      } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
-        const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
-        const int T = int(prm.n_frames), last_row = int(prm.lfr_rows) - 1;
-        int i_lo = f0 + left - (lm - 1) < 0 ? 0 : (f0 + left - (lm - 1)) / ln;
-        int i_hi = (f0 + rows - 1 + left) / ln;
-        if (f0 + rows >= T || i_hi > last_row) i_hi = last_row;
-        const int nseg = (i_hi - i_lo + 1) * lm;
-        for (int sg = warp; sg < nseg; sg += NW) {
-          const int i = i_lo + sg / lm;
-          const int j = sg - (sg / lm) * lm;
-          int t = i * ln + j - left;
-          t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-          if (t < f0 || t >= f0 + rows) continue;
-          const float* sr = s_o + (t - f0) + lane * OP;
-          float* d = dst + ((long long)i * lm + j) * MB + lane;
+          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = s_p[out_base_words<P>(m) + fl];
+      } else {
+        // lanes run over m: one staging pointer per 32-filter chunk (bank = (m + frame) mod 32: conflict free)
+        const float* srow[NC];
 #pragma unroll
-          for (int c = 0; c < MB / 32; ++c) d[c * 32] = sr[c * 32 * OP];
-          if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = sr[(MB / 32) * 32 * OP];
+        for (int c = 0; c < NC; ++c) srow[c] = s_p + out_base_words<P>(c * 32 + lane < MB ? c * 32 + lane : MB - 1);
+        if (prm.out_mode == OUT_TM) {
+          // (T', M) rows, every row a run of coalesced 128-byte segments; rows warp, warp + NW, ... as immediates
+          float* d = dst + ((long long)f0 + warp) * MB + lane;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (c < MB / 32 || lane < MB % 32) {
+              const float* sr = srow[c] + warp;
+#pragma unroll
+              for (int i = 0; i < (FT + NW - 1) / NW; ++i)
+                if (warp + i * NW < rows) d[i * NW * MB + c * 32] = sr[i * NW];
+            }
+          }
+        } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
+          const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
+          const int T = int(prm.n_frames), last_row = int(prm.lfr_rows) - 1;
+          int i_lo = f0 + left - (lm - 1) < 0 ? 0 : (f0 + left - (lm - 1)) / ln;
+          int i_hi = (f0 + rows - 1 + left) / ln;
+          if (f0 + rows >= T || i_hi > last_row) i_hi = last_row;
+          const int nseg = (i_hi - i_lo + 1) * lm;
+          for (int sg = warp; sg < nseg; sg += NW) {
+            const int i = i_lo + sg / lm;
+            const int j = sg - (sg / lm) * lm;
+            int t = i * ln + j - left;
+            t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
+            if (t < f0 || t >= f0 + rows) continue;
+            const int x = t - f0;
+            float* d = dst + ((long long)i * lm + j) * MB + lane;
+#pragma unroll
+            for (int c = 0; c < MB / 32; ++c) d[c * 32] = srow[c][x];
+            if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = srow[NC - 1][x];
+          }
         }
       }
     } else {
@@ -581,15 +597,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         // (T', M) rows: lanes run over m
         dst += (long long)f0 * M;
         auto store_tm = [&](auto post) {
-          for (int r = warp; r < rows; r += NW) {
-            float* d = dst + r * M + lane;
-            const float* sr = s_o + r + lane * OP;
-            int c = lane;
-            for (; c + 96 < M; c += 128, d += 128, sr += 128 * OP) {  // four coalesced 128-byte segments per iteration
-              const float v0 = sr[0], v1 = sr[32 * OP], v2 = sr[64 * OP], v3 = sr[96 * OP];
-              d[0] = post(v0); d[32] = post(v1); d[64] = post(v2); d[96] = post(v3);
-            }
-            for (; c < M; c += 32, d += 32, sr += 32 * OP) d[0] = post(sr[0]);
+          for (int c = lane; c < M; c += 32) {
+            const float* sr = s_p + out_base_words<P>(c);
+            for (int r = warp; r < rows; r += NW) dst[r * M + c] = post(sr[r]);
           }
         };
         if (wnorm) store_tm([&](float v) { return mel_post<LOG_LOG10, true>(v, log_floor, lmax, vmin); });
@@ -604,7 +614,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         const bool post = prm.post_affine != 0;
         auto store_mt = [&](auto fn) {
           for (int m = wsub; m < M; m += NIT) {
-            float v = fn(s_o[m * OP + fl]);
+            float v = fn(s_p[out_base_words<P>(m) + fl]);
             if (post) v = (v - prm.post_sub) / prm.post_div;
             if (frame_ok) dst[m * nfr] = v;
           }
@@ -629,10 +639,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
           long long t = i * ln + j - left;
           t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
           if (t < f0 || t >= f0 + rows) continue;
-          const float* sr = s_o + int(t - f0);
+          const int x = int(t - f0);
           float* d = dst + (i * lm + j) * (long long)M;
           for (int c = lane; c < M; c += 32) {
-            float v = sr[c * OP];
+            float v = s_p[out_base_words<P>(c) + x];
             if (log_mode == LOG_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
             else if (log_mode == LOG_LOG10) v = lg2_ftz(fmaxf(v, log_floor)) * 0.30102999566398120f;
             d[c] = v;
@@ -649,8 +659,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
     }  // !cplx
-    if (!DB) {
-      // single buffer: the next tile's PCM can only be staged once every warp is done with the spectrum tile
+    if (!DB && !EARLY_PREFETCH) {
+      // plain stft(), single buffer: the next tile's PCM can only be staged once every warp is done with the complex tile
       __syncthreads();
       if (nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, tid, lane, warp);
     }
@@ -852,15 +862,14 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   for (int o = 0; o < P::WIN; ++o) prm.window[o] = a.window[o];
   if (SPEC != SK_CPLX) {
-    // the (M x frames) staging tile takes the place of the PCM tile
-    if (a.bank.n_mels <= 0 || a.bank.n_mels * (P::FT + 1) > P::R0_WORDS_REAL || a.bank.n_steps > P::MAX_STEPS) {
+    // the finished mel values are staged in the rows of the exchange buffer that the spectrum tile leaves free
+    if (a.bank.n_mels <= 0 || a.bank.n_mels > (((P::N2 - 1) * P::FT - (P::FT - 1)) / (P::FT + 1)) * P::H1) {
       if (err) *err = "n_mels out of range for this plan";
       return B2A_E_BAD_ARG;
     }
   }
-  const int steps_words = (SPEC == SK_CPLX || MEL > 0) ? 0 : 4 * std::max(a.bank.n_steps, 1);
   const size_t smem = sizeof(float) * size_t((P::DOUBLE_BUF ? 2 : 1) * (SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
-                                             P::N + P::TW_WORDS + steps_words);
+                                             P::N + P::TW_WORDS);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 2) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
   static_assert(((P::N + P::TW_WORDS) % 4) == 0, "mel step program must stay 16-byte aligned");

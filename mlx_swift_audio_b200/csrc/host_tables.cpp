@@ -243,7 +243,28 @@ void spectrum_slots(const PlanShape& ps, std::vector<int>& slot_of_bin) {
   }
 }
 
-void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
+// Staging word of filter m: the finished mel values wait for the store phase in the rows of the exchange buffer that stage B
+// leaves unused (rows N2+1 .. 2*N2-1 of every item's block).  Inside a block the filters sit at pitch frame_tile+1 and block q
+// is skewed by (C*q mod frame_tile) words, C = filters per block, so that word(m, f) = base(m) + f has bank (m + f) mod 32:
+// the frame-major writes of the mel stage and the filter-major reads of the store stage are both conflict free.
+// emit_word[m] = byte offset of base(m) in the exchange buffer (never 0).
+int output_block_capacity(const PlanShape& ps) {
+  const int free_words = (ps.n2 - 1) * ps.frame_tile;
+  return (free_words - (ps.frame_tile - 1)) / (ps.frame_tile + 1);
+}
+bool output_words(const PlanShape& ps, int n_mels, std::vector<int>& emit_word) {
+  const int cap = output_block_capacity(ps);
+  emit_word.assign(n_mels, 0);
+  for (int m = 0; m < n_mels; ++m) {
+    const int q = m / cap, j = m % cap;
+    if (q >= ps.n1 / 2) return false;
+    const int word = (q * 2 * ps.n2 + ps.n2 + 1) * ps.frame_tile + (cap * q) % ps.frame_tile + j * (ps.frame_tile + 1);
+    emit_word[m] = word * int(sizeof(float));
+  }
+  return true;
+}
+
+void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, const int* emit_word, int n_chunks,
                        const int* bin_slot, SparseBank& sb) {
   sb.steps.clear();
   sb.chunk_m.assign(n_chunks + 1, 0);
@@ -277,26 +298,26 @@ void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major
     for (; w <= n_chunks; ++w) sb.chunk_m[w] = n_mels;
     sb.chunk_m[n_chunks] = n_mels;
   }
-  auto push = [&](float wlo, float whi, int k, bool emit) {
+  auto push = [&](float wlo, float whi, int k, int emit_m) {   // emit_m: filter finished by this step, or -1
     sb.steps.push_back(wlo);
     sb.steps.push_back(whi);
     sb.steps.push_back(bits((bin_slot ? bin_slot[k] : k) * frame_tile * int(sizeof(float))));
-    sb.steps.push_back(bits(emit ? out_pitch * int(sizeof(float)) : 0));
+    sb.steps.push_back(bits(emit_m >= 0 ? emit_word[emit_m] : 0));
   };
   for (int c = 0; c < n_chunks; ++c) {
     sb.chunk_s[c] = int(sb.steps.size() / 4);
     const int ma = sb.chunk_m[c], mb = sb.chunk_m[c + 1];
     if (ma < mb && ma > 0)
       for (int k : own[ma - 1])
-        if (at(ma, k) != 0.0f) push(at(ma, k), 0.0f, k, false);
+        if (at(ma, k) != 0.0f) push(at(ma, k), 0.0f, k, -1);
     for (int m = ma; m < mb; ++m) {
       if (own[m].empty()) {
-        push(0.0f, 0.0f, 0, true);
+        push(0.0f, 0.0f, 0, m);
         continue;
       }
       for (size_t i = 0; i < own[m].size(); ++i) {
         const int k = own[m][i];
-        push(at(m, k), at(m + 1, k), k, i + 1 == own[m].size());
+        push(at(m, k), at(m + 1, k), k, i + 1 == own[m].size() ? m : -1);
       }
     }
   }
@@ -408,28 +429,33 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
   b2a::SparseBank sb;
   b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
   const int kChunks = 9;
-  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, 1, kChunks, nullptr, sb);
+  std::vector<int> words(n_mels);
+  for (int m = 0; m < n_mels; ++m) words[m] = (m + 1) * 128;   // emit word = "row" m+1, no swizzle
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, 1, words.data(), kChunks, nullptr, sb);
   if (sb.steps.empty()) return -1;
+  std::vector<int> seen(n_mels, 0);
   for (int c = 0; c < kChunks; ++c) {
     float acc0 = 0.0f, acc1 = 0.0f;
-    float* so = out + sb.chunk_m[c];
     for (int s = sb.chunk_s[c]; s < sb.chunk_s[c + 1]; ++s) {
       const float* t = &sb.steps[size_t(s) * 4];
-      int off, adv;
+      int off, w;
       memcpy(&off, t + 2, 4);
-      memcpy(&adv, t + 3, 4);
+      memcpy(&w, t + 3, 4);
       const float pk = p[off / 4];
       acc0 = fmaf(t[0], pk, acc0);
       acc1 = fmaf(t[1], pk, acc1);
-      if (adv != 0) {
-        *so = acc0;
-        so += adv / 4;
+      if (w != 0) {
+        const int m = w / 128 - 1;
+        if (m < sb.chunk_m[c] || m >= sb.chunk_m[c + 1]) return -2;  // a chunk emits its own filters only
+        out[m] = acc0;
+        seen[m] += 1;
         acc0 = acc1;
         acc1 = 0.0f;
       }
     }
-    if (so != out + sb.chunk_m[c + 1]) return -2;  // every filter of the chunk must have been emitted exactly once
   }
+  for (int m = 0; m < n_mels; ++m)
+    if (seen[m] != 1) return -2;  // every filter must have been emitted exactly once
   return int(sb.steps.size() / 4);
 }
 
@@ -438,7 +464,7 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
 // straight-line device code at build time; at run time the program built for the caller's bank is compared with the baked
 // one word for word before the baked kernel is chosen.  Returns the number of steps, -1 if the bank has no step program,
 // -2 if `cap_steps` is too small.
-int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int n_fft, int out_pitch,
+int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int n_fft,
                                unsigned* steps_out, int cap_steps, int* chunk_m, int* chunk_s, int* n_chunks_out, int* frame_tile_out) {
   const b2a::PlanShape* ps = b2a::plan_shape(n_fft);
   if (!ps) return -3;
@@ -450,7 +476,9 @@ int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bi
   if (n_bins > int(slots.size())) return -3;
   b2a::SparseBank sb;
   b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
-  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, frame_tile, out_pitch, n_chunks, slots.data(), sb);
+  std::vector<int> words;
+  if (!b2a::output_words(*ps, n_mels, words)) return -3;
+  b2a::build_mel_program(bank, n_mels, n_bins, bin_major != 0, frame_tile, words.data(), n_chunks, slots.data(), sb);
   if (sb.steps.empty()) return -1;
   const int n = int(sb.steps.size() / 4);
   if (n > cap_steps) return -2;

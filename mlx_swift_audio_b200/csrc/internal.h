@@ -36,7 +36,10 @@ inline const PlanShape* plan_shape(int n_fft) {
 // that holds bin k.  Item k1 = k mod n1 (or n1 - k mod n1 for the conjugate-mirrored bins) owns rows [k1*2*n2, (k1+1)*2*n2).
 void spectrum_slots(const PlanShape& ps, std::vector<int>& slot_of_bin);
 // bin_slot: nullptr = identity (bin k in row k)
-void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, int out_pitch, int n_chunks,
+// emit_word[m]: what the step that finishes filter m carries (see output_words); false if n_mels does not fit the free rows
+bool output_words(const PlanShape& ps, int n_mels, std::vector<int>& emit_word);
+int output_block_capacity(const PlanShape& ps);
+void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, const int* emit_word, int n_chunks,
                        const int* bin_slot, SparseBank& sb);
 
 // ---- fused STFT -> (power | magnitude) -> mel -> log front-end (frontend.cu) -----------------
