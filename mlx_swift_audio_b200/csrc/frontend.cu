@@ -202,18 +202,20 @@ B2A_DEV float lg2_ftz(float x) {
 // host_tables.cpp) stores the open filter's sum and shifts the accumulators.  A bin touches at most two adjacent triangular
 // filters; filters without bins get a zero-weight step.  LANE == FRAME.  The program is read straight from global memory:
 // every lane reads the same 16 bytes (one L1 sector per step), which keeps shared memory for a third CTA per SM.
-B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, char* so_lane) {
+template <class Post>
+B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, char* so_lane, Post& post) {
   const int w = __float_as_int(t.w);
   acc0 = fmaf(t.x, pk, acc0);
   acc1 = fmaf(t.y, pk, acc1);
   if (w != 0) {   // warp-uniform
-    *reinterpret_cast<float*>(so_lane + w) = acc0;
+    *reinterpret_cast<float*>(so_lane + w) = post(acc0);
     acc0 = acc1;
     acc1 = 0.0f;
   }
 }
 
-B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_lane_f) {
+template <class Post>
+B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_lane_f, Post&& post) {
   char* so_lane = reinterpret_cast<char*>(so_lane_f);
   float acc0 = 0.0f, acc1 = 0.0f;
   const char* pb = reinterpret_cast<const char*>(p_lane);
@@ -225,14 +227,14 @@ B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restric
     const float p1 = *reinterpret_cast<const float*>(pb + __float_as_int(t1.z));
     const float p2 = *reinterpret_cast<const float*>(pb + __float_as_int(t2.z));
     const float p3 = *reinterpret_cast<const float*>(pb + __float_as_int(t3.z));
-    mel_step_apply(t0, p0, acc0, acc1, so_lane);
-    mel_step_apply(t1, p1, acc0, acc1, so_lane);
-    mel_step_apply(t2, p2, acc0, acc1, so_lane);
-    mel_step_apply(t3, p3, acc0, acc1, so_lane);
+    mel_step_apply(t0, p0, acc0, acc1, so_lane, post);
+    mel_step_apply(t1, p1, acc0, acc1, so_lane, post);
+    mel_step_apply(t2, p2, acc0, acc1, so_lane, post);
+    mel_step_apply(t3, p3, acc0, acc1, so_lane, post);
   }
   for (; s < s1; ++s) {
     const float4 t = __ldg(steps + s);
-    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so_lane);
+    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so_lane, post);
   }
 }
 
@@ -275,6 +277,14 @@ B2A_DEV constexpr int out_base_words(int m) {
   return ((m / CAP) * 2 * P::N2 + P::N2 + 1) * P::FT + (CAP * (m / CAP)) % P::FT + (m % CAP) * (P::FT + 1);
 }
 
+// Edge tiles (2 of 94 for a 30 s clip): kept out of line so that the 64-bit index arithmetic of the padding map does not sit
+// in the instruction stream of the interior tiles (the hot loop has to stay inside the 32 KB the instruction cache serves at
+// full rate: tools/microbench/icache.cu).
+__device__ __noinline__ void stage_pcm_edge(const float* __restrict__ xc, float* __restrict__ buf, long long p0, long long pad_left,
+                                            long long n_samples, long long n_eff, int pad_mode, int tid, int ts, int hop, int nthreads) {
+  for (int s = tid; s < ts; s += nthreads) buf[s + s / hop] = fetch_padded(xc, p0 + s, pad_left, n_samples, n_eff, pad_mode);
+}
+
 // Stages the PCM of tile (clip, f0) into `buf` (skewed rows, pitch HOP+1).  Interior tiles use cp.async so that
 // the copy overlaps with the previous tile's FFT stages: whole rows of HOP samples, warp w takes rows w, w+NW, ...,
 // every copy an immediate offset from two per-warp base pointers.  Edge tiles (reflect / zero padding, clip end) go
@@ -297,8 +307,7 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
       }
     }
   } else {
-    for (int s = tid; s < P::TS; s += P::NTHREADS)
-      buf[s + s / HOP] = fetch_padded(xc, p0 + s, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode);
+    stage_pcm_edge(xc, buf, p0, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode, tid, P::TS, HOP, P::NTHREADS);
   }
 }
 
@@ -308,15 +317,19 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // MEL == 0: mel step program + run-time log / output modes (any bank).  MEL > 0: baked bank MEL of mel_baked.h with
 // the compile-time post-processing POST; finished values are post-processed in the mel stage (lane == frame) and the
 // store stage is a plain transposing copy.
-template <class P, int PRE, int SPEC, int MEL, int POST>
+// CODE: 0 = mel step program interpreted in a loop (small code), 1 = straight-line baked code of bank MEL.
+// OUT: compile-time output mode (OUT_TM / OUT_MT / OUT_LFR), or -1 = prm.out_mode.
+template <class P, int PRE, int SPEC, int MEL, int POST, int CODE, int OUT>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
   constexpr bool DB = P::DOUBLE_BUF;
-  constexpr bool BAKED = MEL > 0;
+  constexpr bool BAKED = MEL > 0 && CODE == 1;    // straight-line mel code
+  constexpr bool FUSED = POST != POST_RUNTIME;    // post-processing at emit (mel stage), copy-only store; needs a known bank
+  static_assert(!FUSED || MEL > 0, "fused post-processing is built for the known banks");
   constexpr bool EARLY_PREFETCH = !cplx && !DB;   // the PCM region is dead after stage A: refill it during stage B / mel / store
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
-  static_assert(!BAKED || (SPEC == SK_POWER && FT == 32), "baked banks are power-spectrum banks of the 32-frame plans");
+  static_assert(MEL == 0 || (SPEC == SK_POWER && FT == 32), "known banks are power-spectrum banks of the 32-frame plans");
   extern __shared__ __align__(16) float smem[];
   float2* s_y = reinterpret_cast<float2*>(smem + (DB ? 2 : 1) * R0W);
   float* s_p = reinterpret_cast<float*>(s_y);               // stage B leaves the spectrum tile in the exchange buffer (spectrum_slots)
@@ -491,11 +504,13 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     } else {   // (the loop-top barrier orders a complex tile's reads before the next tile's writes)
 
     // ---- 4b. sparse mel projection; finished values wait in the free rows of the exchange buffer (output_words()) ----
-    const int M = BAKED ? MelTraits<MEL>::M : prm.n_mels;
+    const int M = MEL > 0 ? MelTraits<MEL>::M : prm.n_mels;
+    const int out_mode = OUT >= 0 ? OUT : prm.out_mode;
     float lmax = -3.0e38f, vmin = 3.0e38f;   // of the normalised values (Whisper clamp bookkeeping)
-    if (BAKED) {
-      const float log_floor = prm.log_floor;
-      mel_baked<MEL>(wsub, s_p + fl, [&](int m, float v) {
+    const float log_floor = prm.log_floor;
+    // Interpreted mel program: post-processing at emit (lane == frame).  Straight-line (baked) mel code: in the store loop,
+    // which keeps the unrolled code a third shorter (the tile loop has to fit the instruction cache).
+    auto post = [&](float v) {
         if (POST == POST_WNORM) {
           // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
           v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
@@ -504,14 +519,16 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         } else if (POST == POST_LN) {
           v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
         }
-        s_p[out_base_words<P>(m) + fl] = v;
-      });
-    } else {
-      const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
-      if (prm.fb_steps != nullptr) {
-        mel_steps(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl);
+      return v;
+    };
+    {
+      if (BAKED) {
+        mel_baked<MEL>(wsub, s_p + fl, [&](int m, float v) { s_p[out_base_words<P>(m) + fl] = v; });
+      } else if (MEL > 0 || prm.fb_steps != nullptr) {
+        mel_steps(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl, post);
       } else {
         // generic path: arbitrary filterbank, one short loop per filter
+        const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
         const int4* __restrict__ fdesc = prm.fb_desc;
         const float* __restrict__ fw = prm.fb_w;
         for (int m = ma; m < mb; ++m) {
@@ -523,7 +540,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (BAKED && POST == POST_WNORM) {
+    if (FUSED && !BAKED && POST == POST_WNORM) {
       // warp-level max / min with one REDUX each on the ordered-int encoding, then one shared-memory atomic per warp
       const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
       const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
@@ -536,8 +553,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
     // ---- 5. store of the staged tile (baked: plain transposing copy; otherwise log / floor / scale fused in) ----
     float* __restrict__ dst = prm.out + (long long)clip * prm.out_clip_stride;
-    if (BAKED) {
-      if (POST == POST_WNORM && tid == 0) {
+    if (FUSED) {
+      auto pst = [&](float v) { return BAKED ? post(v) : v; };
+      if (!BAKED && POST == POST_WNORM && tid == 0) {
         atomicMax(prm.clip_max + clip, s_red[0]);
         prm.tile_min[clip * tpc + tile] = s_red[1];
         s_red[0] = int(0x80000000u);   // the next tile's shared atomics come after at least one more barrier
@@ -545,27 +563,37 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
       constexpr int MB = MelTraits<MEL>::M;
       constexpr int NC = MB > 0 ? (MB + 31) / 32 : 1;   // (MEL == 0 instantiates this dead branch with MB == 0)
-      if (prm.out_mode == OUT_MT) {
+      if (out_mode == OUT_MT) {
         // (M, T') rows: lanes run over frames
         const long long nfr = prm.n_frames;
         float* d = dst + f0 + fl;
         if (frame_ok)
-          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = s_p[out_base_words<P>(m) + fl];
+          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = pst(s_p[out_base_words<P>(m) + fl]);
       } else {
         // lanes run over m: one staging pointer per 32-filter chunk (bank = (m + frame) mod 32: conflict free)
         const float* srow[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) srow[c] = s_p + out_base_words<P>(c * 32 + lane < MB ? c * 32 + lane : MB - 1);
-        if (prm.out_mode == OUT_TM) {
+        if (out_mode == OUT_TM) {
           // (T', M) rows, every row a run of coalesced 128-byte segments; rows warp, warp + NW, ... as immediates
           float* d = dst + ((long long)f0 + warp) * MB + lane;
+          constexpr int NI = (FT + NW - 1) / NW;
+          // one predicate per row slot (the last slot exists for the first warps only; partial tiles end early): the
+          // loads are unconditional (staging rows past `rows` hold the recomputed last frame), only the stores are guarded
+          bool ok[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) ok[i] = warp + i * NW < rows;
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
-            if (c < MB / 32 || lane < MB % 32) {
-              const float* sr = srow[c] + warp;
+            const bool col_ok = c < MB / 32 || lane < MB % 32;
+            const float* sr = srow[c] + warp;
+            float v[NI];
 #pragma unroll
-              for (int i = 0; i < (FT + NW - 1) / NW; ++i)
-                if (warp + i * NW < rows) d[i * NW * MB + c * 32] = sr[i * NW];
+            for (int i = 0; i < NI; ++i) v[i] = sr[(warp + i * NW < FT ? i : 0) * NW];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const float o = pst(v[i]);
+              if (ok[i] && col_ok) d[i * NW * MB + c * 32] = o;
             }
           }
         } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
@@ -584,16 +612,24 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
             const int x = t - f0;
             float* d = dst + ((long long)i * lm + j) * MB + lane;
 #pragma unroll
-            for (int c = 0; c < MB / 32; ++c) d[c * 32] = srow[c][x];
-            if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = srow[NC - 1][x];
+            for (int c = 0; c < MB / 32; ++c) d[c * 32] = pst(srow[c][x]);
+            if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = pst(srow[NC - 1][x]);
           }
+        }
+      }
+      if (BAKED && POST == POST_WNORM) {
+        const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
+        const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
+        if (lane == 0) {
+          atomicMax(prm.clip_max + clip, wmax);
+          atomicMin(prm.tile_min + clip * tpc + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
         }
       }
     } else {
       const int log_mode = prm.log_mode;
       const float log_floor = prm.log_floor;
       const bool wnorm = prm.whisper_norm != 0;
-      if (prm.out_mode == OUT_TM) {
+      if (out_mode == OUT_TM) {
         // (T', M) rows: lanes run over m
         dst += (long long)f0 * M;
         auto store_tm = [&](auto post) {
@@ -607,7 +643,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         else if (log_mode == LOG_LOG10) store_tm([&](float v) { return mel_post<LOG_LOG10, false>(v, log_floor, lmax, vmin); });
         else if (log_mode == LOG_DB20) store_tm([&](float v) { return mel_post<LOG_DB20, false>(v, log_floor, lmax, vmin); });
         else store_tm([&](float v) { return v; });
-      } else if (prm.out_mode == OUT_MT) {
+      } else if (out_mode == OUT_MT) {
         // (M, T') rows: lanes run over frames
         dst += f0 + fl;
         const long long nfr = prm.n_frames;
@@ -650,7 +686,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (!BAKED && prm.whisper_norm) {
+    if (!FUSED && prm.whisper_norm) {
       const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
       const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
       if (lane == 0) {
@@ -806,7 +842,7 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int CODE = 0, int OUT = -1>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
   static FrontendParams<P> prm;  // large (window table); filled and launched under the lock
   static std::mutex mu;
@@ -873,7 +909,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 2) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
   static_assert(((P::N + P::TW_WORDS) % 4) == 0, "mel step program must stay 16-byte aligned");
-  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;
   if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL || a.batch > 0x7fffffffLL || a.n_frames > 0x7fffffffLL) {
@@ -883,19 +919,20 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   int dev = 0, n_sm = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST>, P::NTHREADS, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT>, P::NTHREADS, smem)) != cudaSuccess)
     return cuda_fail(e, "occupancy query", err);
   if (per_sm < 1) {
     if (err) *err = "frontend kernel does not fit on this device";
     return B2A_E_CUDA;
   }
+  per_sm = std::min(per_sm, P::MINB);
   if (const char* cap = getenv("B2A_DEBUG_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));  // occupancy experiments
   const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
   if (a.whisper_norm) {
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     if ((e = cudaMemsetAsync(a.tile_min, 0x7f, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
-  frontend_kernel<P, PRE, SPEC, MEL, POST><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
@@ -923,25 +960,29 @@ int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, co
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int spec = a.out_mode == OUT_COMPLEX ? SK_CPLX : (a.spec_mode == SPEC_POWER ? SK_POWER : SK_MAG);
-  // baked banks (mel_baked.h): the bank's step program matched one of them word for word and the post-processing is the
-  // one the baked kernel was compiled for
+  // Known banks (mel_baked.h): the bank's step program matched one of them word for word.  Their kernels are specialised
+  // at compile time on the post-processing and the output layout (small code: the whole tile loop stays inside the
+  // instruction cache); everything else runs the run-time-configured kernel.
   int post = -1;
-  static const bool no_baked = getenv("B2A_DEBUG_NO_BAKED") != nullptr;  // A/B experiments: force the step-program kernel
-  if (!no_baked && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
+  static const bool no_fused = getenv("B2A_DEBUG_NO_FUSED") != nullptr;   // A/B experiments
+  if (!no_fused && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }
+  const int id = a.bank.baked_id, om = a.out_mode;
   if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE) {
-    if (post == POST_WNORM && a.bank.baked_id == 1) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM>(a, st, launches, err);
-    if (post == POST_WNORM && a.bank.baked_id == 2) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM>(a, st, launches, err);
-    if (post == POST_LN && a.bank.baked_id == 3) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN>(a, st, launches, err);
+    if (post == POST_WNORM && id == 1 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, 1, OUT_TM>(a, st, launches, err);
+    if (post == POST_WNORM && id == 1 && om == OUT_MT) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, 1, OUT_MT>(a, st, launches, err);
+    if (post == POST_WNORM && id == 2 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM, 1, OUT_TM>(a, st, launches, err);
+    if (post == POST_LN && id == 3 && om == OUT_LFR) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, 1, OUT_LFR>(a, st, launches, err);
+    if (post == POST_LN && id == 3 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, 1, OUT_TM>(a, st, launches, err);
     if (spec == SK_POWER) return launch_plan<Plan400, PRE_NONE, SK_POWER>(a, st, launches, err);
     if (spec == SK_MAG) return launch_plan<Plan400, PRE_NONE, SK_MAG>(a, st, launches, err);
     return launch_plan<Plan400, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) {
-    if (a.pre_mode == PRE_KALDI && post == POST_LN && a.bank.baked_id == 4 && a.out_mode == OUT_TM)
-      return launch_plan<Plan512, PRE_KALDI, SK_POWER, 4, POST_LN>(a, st, launches, err);
+    if (a.pre_mode == PRE_KALDI && post == POST_LN && id == 4 && om == OUT_TM)
+      return launch_plan<Plan512, PRE_KALDI, SK_POWER, 4, POST_LN, 1, OUT_TM>(a, st, launches, err);
     if (a.pre_mode == PRE_KALDI && spec == SK_POWER) return launch_plan<Plan512, PRE_KALDI, SK_POWER>(a, st, launches, err);
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }

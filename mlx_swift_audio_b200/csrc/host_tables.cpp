@@ -284,8 +284,8 @@ void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major
     const int m = sb.bin_mlo[k];
     if (m >= 0 && m < n_mels && (at(m, k) != 0.0f || at(m + 1, k) != 0.0f)) own[m].push_back(k);
   }
-  // balance: cost of a filter = 3 instructions per step (spectrum load, two multiply-adds) + 6 per emit (floor, log, scale, store)
-  auto cost = [&](int m) { return (long long)(3 * own[m].size() + 6); };
+  // balance: cost of a filter = 3 instructions per step (spectrum load, two multiply-adds) + 1 for the store of the sum
+  auto cost = [&](int m) { return (long long)(3 * own[m].size() + 1); };
   long long total = 0;
   for (int m = 0; m < n_mels; ++m) total += cost(m);
   {
