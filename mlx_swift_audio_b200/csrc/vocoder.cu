@@ -60,6 +60,22 @@ B2A_DEV void sincos_fast(float x, float* s, float* c) {
   }
 }
 
+// sin and cos for |x| < pi/2 (what the vocoders feed: phase = sin(.) in [-1, 1]): no range reduction, no quadrant logic.
+// Minimax polynomials in x^2 fitted on [0, (1.0005 pi/2)^2]: |err| < 7e-9 (sin, degree 9), 5e-8 (cos, degree 8) before fp32
+// rounding; 1.7e-7 / 1.9e-7 evaluated in fp32.
+B2A_DEV float cos_small(float u) {  // u = x*x
+  float p = fmaf(u, 2.315233542e-05f, -1.385363517e-03f);
+  p = fmaf(p, u, 4.166357592e-02f);
+  p = fmaf(p, u, -4.999990463e-01f);
+  return fmaf(p, u, 9.999999404e-01f);
+}
+B2A_DEV float sin_small(float x, float u) {
+  float p = fmaf(u, 2.605078407e-06f, -1.980901143e-04f);
+  p = fmaf(p, u, 8.333050646e-03f);
+  p = fmaf(p, u, -1.666665822e-01f);
+  return fmaf(p * u, x, x);
+}
+
 template <int NFFT, int HOP>
 struct IstftParams {
   const float* mag;
@@ -112,9 +128,14 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       xr[k] = m;
       amax = fmaxf(amax, fabsf(ph[k]));
     }
-    if (prm.unwrap_flag != nullptr) {
-      // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.
-      // (warp-uniform branch; every lane takes part in the shuffles)
+    // every phase of the warp's 32 frames inside (-pi/2, pi/2)?  (false for NaN)  Then (a) sin / cos need no range
+    // reduction and (b) no phase step inside the warp can reach pi.
+    const bool small = __all_sync(0xffffffffu, amax < 1.5707963f);
+    if (prm.unwrap_flag != nullptr && !small) {
+      // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.  A pair (t-1, t) is
+      // examined by the warp of frame t (left neighbour: shuffle, lane 0 from global memory) and, when t-1 is a warp's last
+      // lane, also by that warp (right neighbour from global memory) -- so warps whose phases are all small can skip the test
+      // even when their neighbour warp's are not.  (warp-uniform branch; every lane takes part in the shuffles)
       bool bad = false;
 #pragma unroll
       for (int k = 0; k < F; ++k) {
@@ -123,11 +144,20 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
           if (lane == 0) prev = __ldg(pp + k * nF - 1);
           bad |= !(fabsf(ph[k] - prev) < 3.14159274f);
         }
+        if (lane == 31 && has_frame && f + 1 < nF) bad |= !(fabsf(__ldg(pp + k * nF + 1) - ph[k]) < 3.14159274f);
       }
       if (bad) *prm.unwrap_flag = 1;
     }
-    if (amax < 48000.0f) {  // false for NaN too
-      // imaginary parts of DC / Nyquist are ignored by the codelet, as by irfft: no sine needed there
+    if (small) {
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        const float u = ph[k] * ph[k];
+        const float m = xr[k];
+        xr[k] = m * cos_small(u);
+        // imaginary parts of DC / Nyquist are ignored by the codelet, as by irfft: no sine needed there
+        xi[k] = (k == 0 || k == F - 1) ? 0.0f : m * sin_small(ph[k], u);
+      }
+    } else if (amax < 48000.0f) {  // false for NaN too
       float sn, cs;
       sincos_fast<false>(ph[0], &sn, &cs);
       xr[0] *= cs; xi[0] = 0.0f;

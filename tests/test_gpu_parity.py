@@ -202,6 +202,24 @@ def test_kokoro_inverse_unwrap_path(api, ctx):
     assert np.abs(got - want64).max() <= max(4 * ref_err, 1e-4)
 
 
+@pytest.mark.parametrize("t_jump", [28, 29, 60, 61, 252, 253, 300])
+def test_kokoro_inverse_single_phase_jump(api, ctx, t_jump):
+    # All phases small (the kernel's fast path: no unwrap test, no range reduction) except ONE frame with a large phase:
+    # the step of >= pi into and out of it must still be found, also when the neighbouring frame sits in another warp or
+    # block of the kernel (frame f is lane (f + 3) % 32 of its warp, 253 segments per block).
+    mag, ph = synth.mag_phase(2, 11, 400, seed=21)
+    mag = np.minimum(mag, 1.0)
+    ph = (0.3 * ph).astype(np.float32)
+    ph[:, :, t_jump] = 3.0
+    ph[1, 4, t_jump] = -3.1
+    st = api.MLXSTFT(20, 5, 20, ctx=ctx)
+    got = st.inverse(mag, ph)
+    want = R.kokoro_inverse(mag, ph)
+    # the reference's unwrap changes the phases after the jump by multiples of 2 pi (visible in fp32 as ~1e-6 rad)
+    assert np.abs(R.unwrap(ph[0]) - ph[0]).max() > 3.0
+    assert np.abs(got - want).max() <= 2e-5
+
+
 def test_forward_vocoder_stfts(api, ctx):
     x = synth.pcm(2, 4000, sample_rate=24000, seed=11, zero_tail_frac=0.0)
     w = R.hann_window_periodic(16)
