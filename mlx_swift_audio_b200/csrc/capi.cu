@@ -176,7 +176,13 @@ int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t i
                 size_t in1_per_clip, float* out0, size_t out0_per_clip, float* out1, size_t out1_per_clip, const Body& body) {
   if (space == B2A_DEVICE) {
     if (c->timing) cudaEventRecord(c->ev_t0, c->stream);
-    int rc = body(in0, in1, out0, out1, batch, 0);
+    int rc = B2A_OK;
+    const int64_t kMaxClipsPerLaunch = 32768;   // several kernels index clips with gridDim.y (limit 65535)
+    for (int64_t c0 = 0; c0 < batch && rc == B2A_OK; c0 += kMaxClipsPerLaunch) {
+      const int64_t n = std::min(kMaxClipsPerLaunch, batch - c0);
+      rc = body(in0 + c0 * in0_per_clip, in1 ? in1 + c0 * in1_per_clip : nullptr, out0 + c0 * out0_per_clip,
+                out1 ? out1 + c0 * out1_per_clip : nullptr, n, 0);
+    }
     if (c->timing) {
       cudaEventRecord(c->ev_t1, c->stream);
       c->timed = true;

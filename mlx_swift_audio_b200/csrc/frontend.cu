@@ -708,12 +708,15 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 // Rewrites only the tiles whose minimum lies below the clip's clamp threshold:
 //   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, (Lmax + 4) / 4 - 2)   (x -> (x+4)/4 is monotone)
 // WhisperAudio.swift:130-134, S3TokenizerUtils.swift:203-205.
+constexpr int kClampTilesPerCta = 4;
 __global__ void whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                      long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
-  const long long clip = blockIdx.x;
+  // grid = (groups of kClampTilesPerCta tiles, clips): enough CTAs in flight to run at memory speed on the tiles it touches
+  const long long clip = blockIdx.y;
   const float thr = dec_ordered(clip_max[clip]) - 2.0f;   // clip_max holds the maximum of the normalised values: ((Lmax - 8) + 4) / 4 = (Lmax + 4) / 4 - 2
   float* o = out + clip * out_clip_stride;
-  for (int t = 0; t < tiles_per_clip; ++t) {
+  const int t_end = min(tiles_per_clip, int(blockIdx.x + 1) * kClampTilesPerCta);
+  for (int t = blockIdx.x * kClampTilesPerCta; t < t_end; ++t) {
     if (!(dec_ordered(tile_min[clip * tiles_per_clip + t]) < thr)) continue;
     const long long f0 = (long long)t * ft;
     const int rows = int(n_frames - f0 < ft ? n_frames - f0 : ft);
@@ -936,8 +939,12 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
-    whisper_clamp_kernel<<<unsigned(a.batch), 256, 0, st>>>(a.out, a.clip_max, prm.tile_min, prm.tiles_per_clip, a.n_frames,
-                                                             a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);  // tiles of FT frames
+    for (long long c0 = 0; c0 < a.batch; c0 += 65535) {   // gridDim.y limit
+      const long long nb = std::min<long long>(65535, a.batch - c0);
+      whisper_clamp_kernel<<<dim3(unsigned((prm.tiles_per_clip + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, st>>>(
+          a.out + c0 * prm.out_clip_stride, a.clip_max + c0, prm.tile_min + c0 * prm.tiles_per_clip, prm.tiles_per_clip, a.n_frames,
+          a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);  // tiles of FT frames
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
     *launches += 1;
   }
