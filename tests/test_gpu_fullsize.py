@@ -1,0 +1,101 @@
+"""GPU tests at BASELINE.json's full clip lengths (30 s clips, large batches), through size-independent properties --
+the oracle only sees a handful of clips:
+
+* batch invariance: clip b of a big batch == the same clip run alone, bit for bit (per-clip statistics stay per clip);
+* spot checks of a few clips against the CPU oracle at the stated tolerance;
+* the Whisper clamp invariant (min >= max - 2 in the normalised domain);
+* forward STFT -> inverse STFT round trip (HiFT 16/4 is COLA with the envelope normalisation; Kokoro's pair is not), with phases from atan2, i.e.
+  outside (-pi/2, pi/2): exercises the range-reduced sincos path of the iSTFT kernel;
+* linearity of the iSTFT in the magnitudes.
+"""
+import numpy as np
+import pytest
+
+from oracle import reference_dsp as R
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_whisper_128_full_length_batch(ctx):
+    import torch
+    from mlx_swift_audio_b200 import api
+    B, n = 96, 480000                       # 96 x 30 s: 9024 tiles, every persistent CTA walks several clips
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = 0.1 * torch.randn((B, n), generator=g, device="cuda")
+    t = torch.arange(n, device="cuda", dtype=torch.float32) / 16000.0
+    x += 0.3 * torch.sin(2 * np.pi * 440.0 * t)[None, :] * torch.rand((B, 1), generator=g, device="cuda")
+    x[:, n - n // 10:] = 0.0                # silent tail: the max-8 clamp is active
+    x[5] *= 1e-3                            # a quiet clip: its own maximum, not the batch's
+    got = api.whisperLogMelSpectrogram(x, nMels=128)
+    torch.cuda.synchronize()
+    assert got.shape == (B, 3000, 128)
+    # clamp invariant per clip
+    mx = got.amax(dim=(1, 2))
+    mn = got.amin(dim=(1, 2))
+    assert bool(torch.all(mn >= mx - 2.0 - 1e-6))
+    assert bool(torch.all(torch.isfinite(got)))
+    # batch invariance, bit for bit
+    for b in (0, 5, 95):
+        alone = api.whisperLogMelSpectrogram(x[b:b + 1].contiguous(), nMels=128)
+        torch.cuda.synchronize()
+        assert torch.equal(alone[0], got[b]), f"clip {b} differs between batch and single run"
+    # oracle on a few clips
+    for b in (3, 5):
+        want = R.whisper_log_mel_spectrogram(x[b].cpu().numpy(), 128)
+        err = np.abs(got[b].cpu().numpy().astype(np.float64) - want) / np.maximum(1.0, np.abs(want))
+        assert err.max() <= 1e-4, (b, err.max())
+
+
+def test_hift_round_trip_and_linearity_full_length(ctx):
+    import torch
+    from mlx_swift_audio_b200 import api
+    B, n = 24, 720000                       # 24 x 30 s at 24 kHz: 180001 frames per clip
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = 0.2 * torch.randn((B, n), generator=g, device="cuda")
+    w = R.hann_window_periodic(16)
+    re, im = api.stftHiFiGAN(x, 16, 4, w)
+    assert re.shape == (B, 9, n // 4 + 1)
+    mag = torch.sqrt(re * re + im * im)
+    ph = torch.atan2(im, re)                # in (-pi, pi]: the iSTFT kernel's range-reduced sincos path
+    y = api.istftHiFiGAN(mag, ph, 16, 4, w)
+    torch.cuda.synchronize()
+    assert y.shape == (B, n)
+    # COLA + envelope normalisation: exact reconstruction up to fp32 rounding (the reflect-padded edges included)
+    assert float((y - x).abs().max()) <= 2e-6 * 16
+    # oracle on one clip, at the iSTFT tolerance
+    want = R.istft_hifigan(mag[1:2].cpu().numpy(), ph[1:2].cpu().numpy(), 16, 4, w)
+    assert np.abs(y[1:2].cpu().numpy() - want).max() <= 1e-5
+    # linearity in the magnitudes (no clipping active: mag << 100)
+    y3 = api.istftHiFiGAN(3.0 * mag, ph, 16, 4, w)
+    torch.cuda.synchronize()
+    assert float((y3 - 3.0 * y).abs().max()) <= 1e-5
+
+
+def test_kokoro_full_length(ctx):
+    import torch
+    from mlx_swift_audio_b200 import api
+    B, n = 8, 720000
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = 0.2 * torch.randn((B, n), generator=g, device="cuda")
+    st = api.MLXSTFT(20, 5, 20, ctx=None)
+    mag, ph = st.transform(x)
+    assert mag.shape == (B, 11, n // 5 + 1)
+    y = st.inverse(mag, ph)                 # phases from atan2: unwrap is active, the flag path runs
+    torch.cuda.synchronize()
+    assert y.shape == (B, 1, n)
+    assert bool(torch.all(torch.isfinite(y)))
+    # (the reference's pair is not a perfect-reconstruction pair: the inverse divides by sum w, not sum w^2)
+    # unwrap is causal along time, so the head of a clip only depends on the head of its spectrum: oracle on 3000 frames
+    # (the unwrapped phase random-walks to hundreds of radians, where the fp32 cumsum order matters: compare with fp64 truth at
+    # the resolution the fp32 reference itself has there, as tests/test_gpu_parity.py::test_kokoro_inverse_unwrap_path does)
+    m_np, p_np = mag[2:3, :, :3000].cpu().numpy(), ph[2:3, :, :3000].cpu().numpy()
+    want = R.kokoro_inverse(m_np, p_np)
+    want64 = R.kokoro_inverse(m_np, p_np, dt=np.float64)
+    k = (3000 - 4) * 5
+    ref_err = np.abs(want[:, :, :k] - want64[:, :, :k]).max()
+    assert np.abs(y[2:3, :, :k].cpu().numpy() - want64[:, :, :k]).max() <= max(4 * ref_err, 1e-4)
+    # batch invariance, bit for bit
+    alone = st.inverse(mag[5:6].contiguous(), ph[5:6].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(alone[0], y[5])
