@@ -75,7 +75,8 @@ struct Plan {
   // region 0: the PCM tile, later the [m][frame] output staging tile (plain stft(): the complex spectrum tile)
   static constexpr int R0_WORDS_REAL = PCM_WORDS;
   static constexpr int R0_WORDS_CPLX = CPLX_DIRECT ? ((PCM_WORDS + 3) & ~3) : (((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3);
-  static constexpr int TW_WORDS = (2 * N2 * (N1 / 2 - 1) + 3) & ~3;  // padded so that the mel program behind it stays 16-byte aligned
+  static constexpr int TW_ROW = (2 * (N1 / 2 - 1) + 3) & ~3;         // twiddles of one stage-A item, padded to whole float4s
+  static constexpr int TW_WORDS = N2 * TW_ROW;
   static constexpr bool DOUBLE_BUF = DB_;           // second region 0: prefetch the next tile's PCM with cp.async during this tile
   static constexpr int SUB = 32 / FT;               // a warp covers FT frames x SUB items (lane = sub * FT + frame)
   static constexpr int NCHUNK = NWARPS * SUB;       // mel-program chunks
@@ -348,7 +349,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   }
   {
     const float2* __restrict__ tw = TwTable<P>::get();
-    for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) s_tw[i] = tw[i];
+    for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) {
+      const int n2 = i / (H1 - 1), k = i - n2 * (H1 - 1);
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(s_tw) + n2 * P::TW_ROW + 2 * k) = tw[i];
+    }
   }
   if (tid == 0) {
     s_red[0] = int(0x80000000u);
@@ -412,11 +416,17 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         rdft(in, yr, yi);
         float2* yb = s_y + n2 * FT + fl;
         yb[0] = make_float2(yr[0], yr[H1]);
-        const float2* twr = s_tw + n2 * (H1 - 1);
+        // the item's twiddles as whole float4 loads, all in flight before the first complex multiply
+        float twv[P::TW_ROW];
+#pragma unroll
+        for (int q = 0; q < P::TW_ROW / 4; ++q) {
+          const float4 t4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(s_tw) + n2 * P::TW_ROW)[q];
+          twv[4 * q] = t4.x; twv[4 * q + 1] = t4.y; twv[4 * q + 2] = t4.z; twv[4 * q + 3] = t4.w;
+        }
 #pragma unroll
         for (int k1 = 1; k1 < H1; ++k1) {
-          const float2 t = twr[k1 - 1];
-          yb[k1 * N2 * FT] = make_float2(yr[k1] * t.x - yi[k1] * t.y, yr[k1] * t.y + yi[k1] * t.x);
+          const float tx = twv[2 * (k1 - 1)], ty = twv[2 * (k1 - 1) + 1];
+          yb[k1 * N2 * FT] = make_float2(yr[k1] * tx - yi[k1] * ty, yr[k1] * ty + yi[k1] * tx);
         }
       }
     }
@@ -510,15 +520,21 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     const float log_floor = prm.log_floor;
     // Interpreted mel program: post-processing at emit (lane == frame).  Straight-line (baked) mel code: in the store loop,
     // which keeps the unrolled code a third shorter (the tile loop has to fit the instruction cache).
+    auto post_pure = [&](float v) {
+      // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
+      if (POST == POST_WNORM) v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
+      else if (POST == POST_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
+      return v;
+    };
+    auto track2 = [&](float a, float b) {   // two values per three-input min / max (FMNMX3)
+      if (POST == POST_WNORM) {
+        lmax = fmaxf(lmax, fmaxf(a, b));
+        vmin = fminf(vmin, fminf(a, b));
+      }
+    };
     auto post = [&](float v) {
-        if (POST == POST_WNORM) {
-          // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
-          v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
-          lmax = fmaxf(lmax, v);
-          vmin = fminf(vmin, v);
-        } else if (POST == POST_LN) {
-          v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
-        }
+      v = post_pure(v);
+      track2(v, v);
       return v;
     };
     {
@@ -591,10 +607,15 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 #pragma unroll
             for (int i = 0; i < NI; ++i) v[i] = sr[(warp + i * NW < FT ? i : 0) * NW];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) {
-              const float o = pst(v[i]);
-              if (ok[i] && col_ok) d[i * NW * MB + c * 32] = o;
+            for (int i = 0; i < NI; ++i) v[i] = BAKED ? post_pure(v[i]) : v[i];
+            if (BAKED) {
+#pragma unroll
+              for (int i = 0; i + 1 < NI; i += 2) track2(v[i], v[i + 1]);
+              if (NI % 2) track2(v[NI - 1], v[NI - 1]);
             }
+#pragma unroll
+            for (int i = 0; i < NI; ++i)
+              if (ok[i] && col_ok) d[i * NW * MB + c * 32] = v[i];
           }
         } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
           const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
@@ -909,9 +930,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   const size_t smem = sizeof(float) * size_t((P::DOUBLE_BUF ? 2 : 1) * (SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
                                              P::N + P::TW_WORDS);
-  static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 2) == 0,
+  static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
-  static_assert(((P::N + P::TW_WORDS) % 4) == 0, "mel step program must stay 16-byte aligned");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;

@@ -18,6 +18,7 @@
 
 #include <cmath>
 #include <string>
+#include <type_traits>
 
 #include "../../include/b200audio.h"
 #include "codelets.h"
@@ -81,7 +82,8 @@ struct IstftParams {
   const float* mag;
   const float* phase;
   float* out;
-  long long n_frames, out_len;
+  int n_frames;           // < 2^31 / (NFFT/2+1) (checked on the host): per-clip offsets fit 32 bits, one IMAD.WIDE per load address
+  long long out_len;
   float clip_lo, clip_hi;
   int use_clip_lo, norm;
   int* unwrap_flag;       // set to 1 if any |dphi| >= pi was seen (Kokoro optimistic path); may be null
@@ -106,23 +108,28 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
 
   const int tid = threadIdx.x, lane = tid & 31;
   const long long clip = blockIdx.y;
-  const long long nF = prm.n_frames;
-  const long long nSeg = nF + HALO;                      // segments of the untrimmed OLA buffer
-  const long long seg0 = (long long)blockIdx.x * SEG_PER_BLOCK;  // first segment this block emits
-  const long long f = seg0 - HALO + tid;                 // frame (== segment) of this thread
+  const int nF = prm.n_frames;
+  // Row stride of the (F, frames) inputs as a load-address operand.  32 bits (one IMAD.WIDE per address) for the 20-point
+  // transform; 64 bits for the 16-point one, whose loads then issue interleaved with the longer address arithmetic --
+  // measured 10 % faster there (the kernel runs at ~90 % of the HBM roofline and is sensitive to how its 18 loads are paced).
+  using stride_t = typename std::conditional<NFFT == 16, long long, unsigned>::type;
+  const stride_t nFu = stride_t(nF);
+  const int nSeg = nF + HALO;                            // segments of the untrimmed OLA buffer
+  const int seg0 = int(blockIdx.x) * SEG_PER_BLOCK;      // first segment this block emits
+  const int f = seg0 - HALO + tid;                       // frame (== segment) of this thread
   const bool has_frame = f >= 0 && f < nF;
 
   // ---- per-frame inverse real FFT, windowed ------------------------------------------------------
   {
     float y[NFFT];
-    const float* __restrict__ mp = prm.mag + clip * F * nF + f;
-    const float* __restrict__ pp = prm.phase + clip * F * nF + f;
+    const float* __restrict__ mp = prm.mag + (clip * F * nF + f);
+    const float* __restrict__ pp = prm.phase + (clip * F * nF + f);
     float xr[F], xi[F], ph[F];
     float amax = 0.0f;
 #pragma unroll
     for (int k = 0; k < F; ++k) {
-      float m = has_frame ? __ldg(mp + k * nF) : 0.0f;
-      ph[k] = has_frame ? __ldg(pp + k * nF) : 0.0f;
+      float m = has_frame ? __ldg(mp + k * nFu) : 0.0f;
+      ph[k] = has_frame ? __ldg(pp + k * nFu) : 0.0f;
       m = fminf(m, prm.clip_hi);
       if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
       xr[k] = m;
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
     // every phase of the warp's 32 frames inside (-pi/2, pi/2)?  (false for NaN)  Then (a) sin / cos need no range
     // reduction and (b) no phase step inside the warp can reach pi.
     const bool small = __all_sync(0xffffffffu, amax < 1.5707963f);
-    if (prm.unwrap_flag != nullptr && !small) {
+    if (NFFT == 20 && prm.unwrap_flag != nullptr && !small) {   // (only Kokoro's 20 / 5 transform unwraps)
       // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.  A pair (t-1, t) is
       // examined by the warp of frame t (left neighbour: shuffle, lane 0 from global memory) and, when t-1 is a warp's last
       // lane, also by that warp (right neighbour from global memory) -- so warps whose phases are all small can skip the test
@@ -141,10 +148,10 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       for (int k = 0; k < F; ++k) {
         float prev = __shfl_up_sync(0xffffffffu, ph[k], 1);
         if (has_frame && f > 0) {
-          if (lane == 0) prev = __ldg(pp + k * nF - 1);
+          if (lane == 0) prev = __ldg(pp + k * nFu - 1);
           bad |= !(fabsf(ph[k] - prev) < 3.14159274f);
         }
-        if (lane == 31 && has_frame && f + 1 < nF) bad |= !(fabsf(__ldg(pp + k * nF + 1) - ph[k]) < 3.14159274f);
+        if (lane == 31 && has_frame && f + 1 < nF) bad |= !(fabsf(__ldg(pp + k * nFu + 1) - ph[k]) < 3.14159274f);
       }
       if (bad) *prm.unwrap_flag = 1;
     }
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
 
   // ---- overlap-add as a gather: segment s = y_s[0:h] + y_{s-1}[h:2h] + y_{s-2}[2h:3h] + y_{s-3}[3h:4h] -------------
   // (added in that order: the frame order of the reference's scatter-add)
-  const long long s = f;
+  const int s = f;
   const bool emit = tid >= HALO && s >= R / 2 && s < nSeg - R / 2;
   float o[HOP];
   if (emit) {
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
   float* __restrict__ dst = prm.out + clip * prm.out_len;
   if (HOP == 4) {
     if (emit) {
-      float* d = dst + (s - R / 2) * HOP;
+      float* d = dst + (long long)(s - R / 2) * HOP;
       if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
         *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
@@ -255,13 +262,13 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
     }
     __syncthreads();
     // block emits segments [max(seg0, R/2), min(seg0 + SEG_PER_BLOCK, nSeg - R/2))
-    const long long a = seg0 > R / 2 ? seg0 : R / 2;
-    long long b = seg0 + SEG_PER_BLOCK;
+    const int a = seg0 > R / 2 ? seg0 : R / 2;
+    int b = seg0 + SEG_PER_BLOCK;
     if (b > nSeg - R / 2) b = nSeg - R / 2;
-    const long long n = (b - a) * HOP;
+    const int n = (b - a) * HOP;
     const float* src = s_stage + (a - seg0) * HOP;
-    float* d = dst + (a - R / 2) * HOP;
-    for (long long i = tid; i < n; i += kIstftThreads) d[i] = src[i];
+    float* d = dst + (long long)(a - R / 2) * HOP;
+    for (int i = tid; i < n; i += kIstftThreads) d[i] = src[i];
   }
 }
 
@@ -374,7 +381,11 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   prm.mag = a.mag;
   prm.phase = phase;
   prm.out = a.out;
-  prm.n_frames = a.n_frames;
+  if (a.n_frames >= (1LL << 31) / (4 * (NFFT / 2 + 1)) - 1024) {
+    if (err) *err = "iSTFT: too many frames per clip";
+    return B2A_E_BAD_ARG;
+  }
+  prm.n_frames = int(a.n_frames);
   prm.out_len = (a.n_frames - 1) * HOP;
   prm.clip_lo = a.clip_lo;
   prm.clip_hi = a.clip_hi;
