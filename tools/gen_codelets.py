@@ -173,6 +173,9 @@ class C:
         return C(g, re, im)
 
 
+USE_PFA = True
+
+
 def _is_real_seq(g, xs):
     return all(x.im == g.ZERO for x in xs)
 
@@ -219,13 +222,47 @@ def _butterfly(g, xs, sign):
     return out
 
 
+def _coprime_split(n):
+    """(r, m) with n = r*m, gcd(r, m) = 1 and r in {4, 5, 3} (a radix the butterflies handle directly), or None."""
+    for r in (4, 5, 3):
+        if n % r == 0 and n > r and math.gcd(r, n // r) == 1:
+            return r, n // r
+    return None
+
+
+def _dft_pfa(g, xs, sign, r, m):
+    """Good-Thomas prime-factor step: n = r*m with gcd(r, m) = 1 becomes an r x m two-dimensional DFT with NO twiddle
+    factors.  Input map n = (m*n1 + r*n2) mod N, output map k = (m*(m^-1 mod r)*k1 + r*(r^-1 mod m)*k2) mod N."""
+    n = r * m
+    real = _is_real_seq(g, xs)
+    rows = [dft(g, [xs[(m * n1 + r * n2) % n] for n2 in range(m)], sign) for n1 in range(r)]   # DFTs of size m over n2
+    u = pow(m, -1, r)
+    v = pow(r, -1, m)
+    ys = [None] * n
+    # real input: rows are Hermitian in k2, so the columns k2 > m/2 are conjugates: X[-k] = conj(X[k])
+    k2max = m // 2 + 1 if real else m
+    for k2 in range(k2max):
+        b = _butterfly(g, [rows[n1][k2] for n1 in range(r)], sign)
+        for k1 in range(r):
+            ys[(m * u * k1 + r * v * k2) % n] = b[k1]
+    if real:
+        for k in range(n):
+            if ys[k] is None:
+                ys[k] = ys[(n - k) % n].conj()
+    assert all(y is not None for y in ys)
+    return ys
+
+
 def dft(g, xs, sign=-1):
     """Symbolic DFT.  sign=-1 forward (e^{-2 pi i nk/N})."""
     n = len(xs)
     real = _is_real_seq(g, xs)
     r = _factor(n)
+    cp = _coprime_split(n) if USE_PFA else None
     if r is None:
         ys = _butterfly(g, xs, sign)
+    elif cp is not None:
+        ys = _dft_pfa(g, xs, sign, cp[0], cp[1])
     else:
         m = n // r
         subs = [dft(g, xs[q::r], sign) for q in range(r)]
