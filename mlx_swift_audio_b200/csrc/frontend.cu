@@ -25,7 +25,6 @@
 
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -57,7 +56,7 @@ __constant__ float2 c_tw400[20 * 9];
 __constant__ float2 c_tw512[32 * 7];
 __constant__ float2 c_tw1920[32 * 29];
 
-template <int N_, int WIN_, int N1_, int N2_, int HOP_, int FT_, int NWARPS_, int MINB_, bool DB_>
+template <int N_, int WIN_, int N1_, int N2_, int HOP_, int FT_, int NWARPS_, int MINB_>
 struct Plan {
   static constexpr int N = N_, WIN = WIN_, N1 = N1_, N2 = N2_, HOP = HOP_, FT = FT_, NWARPS = NWARPS_, MINB = MINB_;
   static constexpr int H1 = N1 / 2;
@@ -77,7 +76,6 @@ struct Plan {
   static constexpr int R0_WORDS_CPLX = CPLX_DIRECT ? ((PCM_WORDS + 3) & ~3) : (((PCM_WORDS > P_WORDS_CPLX ? PCM_WORDS : P_WORDS_CPLX) + 3) & ~3);
   static constexpr int TW_ROW = (2 * (N1 / 2 - 1) + 3) & ~3;         // twiddles of one stage-A item, padded to whole float4s
   static constexpr int TW_WORDS = N2 * TW_ROW;
-  static constexpr bool DOUBLE_BUF = DB_;           // second region 0: prefetch the next tile's PCM with cp.async during this tile
   static constexpr int SUB = 32 / FT;               // a warp covers FT frames x SUB items (lane = sub * FT + frame)
   static constexpr int NCHUNK = NWARPS * SUB;       // mel-program chunks
   static_assert(N1 * N2 == N, "N = N1*N2");
@@ -86,10 +84,10 @@ struct Plan {
 // 400 = 20 x 20: 20 stage-A items and 9 complex + 1 (real + odd-real) stage-B items split evenly over 10 warps; 74.4 KB of
 // shared memory per CTA -> three CTAs (30 warps) per SM, which hides the barrier / shared-memory latencies better than
 // prefetching the next tile into a second buffer with two CTAs per SM
-using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 3, false>;
-using Plan512 = Plan<512, 400, 16, 32, 160, 32, 8, 2, false>;
+using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 3>;
+using Plan512 = Plan<512, 400, 16, 32, 160, 32, 8, 2>;
 // n_fft 1920 (S3Gen 24 kHz mel): the exchange buffer only fits 16 frames, so half-warps take different items
-using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1, false>;
+using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1>;
 template <class P> constexpr bool plan_matches(const PlanShape& s) {
   return s.n_fft == P::N && s.n1 == P::N1 && s.n2 == P::N2 && s.frame_tile == P::FT && s.n_warps == P::NWARPS && s.n_chunks == P::NCHUNK;
 }
@@ -203,20 +201,18 @@ B2A_DEV float lg2_ftz(float x) {
 // host_tables.cpp) stores the open filter's sum and shifts the accumulators.  A bin touches at most two adjacent triangular
 // filters; filters without bins get a zero-weight step.  LANE == FRAME.  The program is read straight from global memory:
 // every lane reads the same 16 bytes (one L1 sector per step), which keeps shared memory for a third CTA per SM.
-template <class Post>
-B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, char* so_lane, Post& post) {
+B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1, char* so_lane) {
   const int w = __float_as_int(t.w);
   acc0 = fmaf(t.x, pk, acc0);
   acc1 = fmaf(t.y, pk, acc1);
   if (w != 0) {   // warp-uniform
-    *reinterpret_cast<float*>(so_lane + w) = post(acc0);
+    *reinterpret_cast<float*>(so_lane + w) = acc0;
     acc0 = acc1;
     acc1 = 0.0f;
   }
 }
 
-template <class Post>
-B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_lane_f, Post&& post) {
+B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_lane_f) {
   char* so_lane = reinterpret_cast<char*>(so_lane_f);
   float acc0 = 0.0f, acc1 = 0.0f;
   const char* pb = reinterpret_cast<const char*>(p_lane);
@@ -228,14 +224,14 @@ B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restric
     const float p1 = *reinterpret_cast<const float*>(pb + __float_as_int(t1.z));
     const float p2 = *reinterpret_cast<const float*>(pb + __float_as_int(t2.z));
     const float p3 = *reinterpret_cast<const float*>(pb + __float_as_int(t3.z));
-    mel_step_apply(t0, p0, acc0, acc1, so_lane, post);
-    mel_step_apply(t1, p1, acc0, acc1, so_lane, post);
-    mel_step_apply(t2, p2, acc0, acc1, so_lane, post);
-    mel_step_apply(t3, p3, acc0, acc1, so_lane, post);
+    mel_step_apply(t0, p0, acc0, acc1, so_lane);
+    mel_step_apply(t1, p1, acc0, acc1, so_lane);
+    mel_step_apply(t2, p2, acc0, acc1, so_lane);
+    mel_step_apply(t3, p3, acc0, acc1, so_lane);
   }
   for (; s < s1; ++s) {
     const float4 t = __ldg(steps + s);
-    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so_lane, post);
+    mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so_lane);
   }
 }
 
@@ -313,30 +309,25 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 }
 
 // Persistent kernel: grid = MINB CTAs per SM; every CTA loads its tables once and walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ...; with DOUBLE_BUF the next tile's PCM is prefetched (cp.async)
-// into the other spectrum/PCM buffer while the current tile is in its FFT / mel / store stages.
-// MEL == 0: mel step program + run-time log / output modes (any bank).  MEL > 0: baked bank MEL of mel_baked.h with
-// the compile-time post-processing POST; finished values are post-processed in the mel stage (lane == frame) and the
-// store stage is a plain transposing copy.
-// CODE: 0 = mel step program interpreted in a loop (small code), 1 = straight-line baked code of bank MEL.
-// OUT: compile-time output mode (OUT_TM / OUT_MT / OUT_LFR), or -1 = prm.out_mode.
-template <class P, int PRE, int SPEC, int MEL, int POST, int CODE, int OUT>
+// blockIdx.x, blockIdx.x + gridDim.x, ...  The next tile's PCM is prefetched (cp.async) into the PCM region as soon as
+// stage A has consumed the current one.
+// MEL == 0: any bank -- mel step program interpreted in a loop, run-time log / output modes (POST_RUNTIME, OUT = -1).
+// MEL > 0: bank MEL of mel_baked.h as straight-line code, with compile-time post-processing POST (applied in the store
+// loop) and output layout OUT (OUT_TM / OUT_MT / OUT_LFR).
+template <class P, int PRE, int SPEC, int MEL, int POST, int OUT>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
-  constexpr bool DB = P::DOUBLE_BUF;
-  constexpr bool BAKED = MEL > 0 && CODE == 1;    // straight-line mel code
-  constexpr bool FUSED = POST != POST_RUNTIME;    // post-processing at emit (mel stage), copy-only store; needs a known bank
-  static_assert(!FUSED || MEL > 0, "fused post-processing is built for the known banks");
-  constexpr bool EARLY_PREFETCH = !cplx && !DB;   // the PCM region is dead after stage A: refill it during stage B / mel / store
+  constexpr bool BAKED = MEL > 0;    // straight-line mel code, compile-time post-processing and output layout
+  static_assert(BAKED == (POST != POST_RUNTIME) && BAKED == (OUT >= 0), "known banks come with compile-time POST and OUT");
+  constexpr bool EARLY_PREFETCH = !cplx;   // the PCM region is dead after stage A: refill it during stage B / mel / store
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
   static_assert(MEL == 0 || (SPEC == SK_POWER && FT == 32), "known banks are power-spectrum banks of the 32-frame plans");
   extern __shared__ __align__(16) float smem[];
-  float2* s_y = reinterpret_cast<float2*>(smem + (DB ? 2 : 1) * R0W);
+  float2* s_y = reinterpret_cast<float2*>(smem + R0W);
   float* s_p = reinterpret_cast<float*>(s_y);               // stage B leaves the spectrum tile in the exchange buffer (spectrum_slots)
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
-  __shared__ int s_red[2];                                  // per-tile max / min of the normalised values (ordered-int)
   constexpr int SUB = P::SUB, NIT = NW * SUB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
@@ -354,10 +345,6 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       *reinterpret_cast<float2*>(reinterpret_cast<float*>(s_tw) + n2 * P::TW_ROW + 2 * k) = tw[i];
     }
   }
-  if (tid == 0) {
-    s_red[0] = int(0x80000000u);
-    s_red[1] = 0x7fffffff;
-  }
 
   // tile walk: (clip, tile) advances by gridDim.x tiles per iteration without divisions in the loop
   const int tpc = prm.tiles_per_clip, n_clips = prm.n_clips;
@@ -365,9 +352,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   int clip = int(blockIdx.x) / tpc, tile = int(blockIdx.x) - clip * tpc;
   if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, tid, lane, warp);
 
-  for (int iter = 0; clip < n_clips; ++iter) {
+  while (clip < n_clips) {
     const int f0 = tile * FT;
-    float* s_r0 = smem + ((DB && (iter & 1)) ? R0W : 0);    // PCM tile (plain stft(): later the complex spectrum tile)
+    float* s_r0 = smem;    // PCM tile (plain stft(): later the complex spectrum tile)
     int nclip = clip + step_clip, ntile = tile + step_tile;
     if (ntile >= tpc) {
       ntile -= tpc;
@@ -377,7 +364,6 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     // ---- 1. this tile's PCM has landed; prefetch the next tile into the other buffer ------------------
     cp_async_commit_wait_all();
     __syncthreads();
-    if (DB && nclip < n_clips) stage_pcm<P>(prm, smem + ((iter & 1) ? 0 : R0W), nclip, ntile * FT, tid, lane, warp);
 
     // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
     float mu = 0.0f;
@@ -518,8 +504,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     const int out_mode = OUT >= 0 ? OUT : prm.out_mode;
     float lmax = -3.0e38f, vmin = 3.0e38f;   // of the normalised values (Whisper clamp bookkeeping)
     const float log_floor = prm.log_floor;
-    // Interpreted mel program: post-processing at emit (lane == frame).  Straight-line (baked) mel code: in the store loop,
-    // which keeps the unrolled code a third shorter (the tile loop has to fit the instruction cache).
+    // Known banks: post-processing sits in the store loop, which keeps the unrolled mel code a third shorter (the tile loop
+    // has to fit the instruction cache).
     auto post_pure = [&](float v) {
       // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
       if (POST == POST_WNORM) v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
@@ -540,8 +526,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     {
       if (BAKED) {
         mel_baked<MEL>(wsub, s_p + fl, [&](int m, float v) { s_p[out_base_words<P>(m) + fl] = v; });
-      } else if (MEL > 0 || prm.fb_steps != nullptr) {
-        mel_steps(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl, post);
+      } else if (prm.fb_steps != nullptr) {
+        mel_steps(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl);
       } else {
         // generic path: arbitrary filterbank, one short loop per filter
         const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
@@ -556,27 +542,11 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (FUSED && !BAKED && POST == POST_WNORM) {
-      // warp-level max / min with one REDUX each on the ordered-int encoding, then one shared-memory atomic per warp
-      const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
-      const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
-      if (lane == 0) {
-        atomicMax(&s_red[0], wmax);
-        atomicMin(&s_red[1], wmin);
-      }
-    }
     __syncthreads();
 
     // ---- 5. store of the staged tile (baked: plain transposing copy; otherwise log / floor / scale fused in) ----
     float* __restrict__ dst = prm.out + (long long)clip * prm.out_clip_stride;
-    if (FUSED) {
-      auto pst = [&](float v) { return BAKED ? post(v) : v; };
-      if (!BAKED && POST == POST_WNORM && tid == 0) {
-        atomicMax(prm.clip_max + clip, s_red[0]);
-        prm.tile_min[clip * tpc + tile] = s_red[1];
-        s_red[0] = int(0x80000000u);   // the next tile's shared atomics come after at least one more barrier
-        s_red[1] = 0x7fffffff;
-      }
+    if (BAKED) {
       constexpr int MB = MelTraits<MEL>::M;
       constexpr int NC = MB > 0 ? (MB + 31) / 32 : 1;   // (MEL == 0 instantiates this dead branch with MB == 0)
       if (out_mode == OUT_MT) {
@@ -584,7 +554,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         const long long nfr = prm.n_frames;
         float* d = dst + f0 + fl;
         if (frame_ok)
-          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = pst(s_p[out_base_words<P>(m) + fl]);
+          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = post(s_p[out_base_words<P>(m) + fl]);
       } else {
         // lanes run over m: one staging pointer per 32-filter chunk (bank = (m + frame) mod 32: conflict free)
         const float* srow[NC];
@@ -607,12 +577,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 #pragma unroll
             for (int i = 0; i < NI; ++i) v[i] = sr[(warp + i * NW < FT ? i : 0) * NW];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) v[i] = BAKED ? post_pure(v[i]) : v[i];
-            if (BAKED) {
+            for (int i = 0; i < NI; ++i) v[i] = post_pure(v[i]);
 #pragma unroll
-              for (int i = 0; i + 1 < NI; i += 2) track2(v[i], v[i + 1]);
-              if (NI % 2) track2(v[NI - 1], v[NI - 1]);
-            }
+            for (int i = 0; i + 1 < NI; i += 2) track2(v[i], v[i + 1]);
+            if (NI % 2) track2(v[NI - 1], v[NI - 1]);
 #pragma unroll
             for (int i = 0; i < NI; ++i)
               if (ok[i] && col_ok) d[i * NW * MB + c * 32] = v[i];
@@ -633,12 +601,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
             const int x = t - f0;
             float* d = dst + ((long long)i * lm + j) * MB + lane;
 #pragma unroll
-            for (int c = 0; c < MB / 32; ++c) d[c * 32] = pst(srow[c][x]);
-            if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = pst(srow[NC - 1][x]);
+            for (int c = 0; c < MB / 32; ++c) d[c * 32] = post(srow[c][x]);
+            if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = post(srow[NC - 1][x]);
           }
         }
       }
-      if (BAKED && POST == POST_WNORM) {
+      if (POST == POST_WNORM) {
         const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
         const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
         if (lane == 0) {
@@ -707,7 +675,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (!FUSED && prm.whisper_norm) {
+    if (!BAKED && prm.whisper_norm) {
       const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
       const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
       if (lane == 0) {
@@ -716,7 +684,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
     }  // !cplx
-    if (!DB && !EARLY_PREFETCH) {
+    if (!EARLY_PREFETCH) {
       // plain stft(), single buffer: the next tile's PCM can only be staged once every warp is done with the complex tile
       __syncthreads();
       if (nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, tid, lane, warp);
@@ -866,7 +834,7 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int CODE = 0, int OUT = -1>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
   static FrontendParams<P> prm;  // large (window table); filled and launched under the lock
   static std::mutex mu;
@@ -928,11 +896,11 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       return B2A_E_BAD_ARG;
     }
   }
-  const size_t smem = sizeof(float) * size_t((P::DOUBLE_BUF ? 2 : 1) * (SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
+  const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
                                              P::N + P::TW_WORDS);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
-  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;
   if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL || a.batch > 0x7fffffffLL || a.n_frames > 0x7fffffffLL) {
@@ -942,20 +910,19 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   int dev = 0, n_sm = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT>, P::NTHREADS, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT>, P::NTHREADS, smem)) != cudaSuccess)
     return cuda_fail(e, "occupancy query", err);
   if (per_sm < 1) {
     if (err) *err = "frontend kernel does not fit on this device";
     return B2A_E_CUDA;
   }
   per_sm = std::min(per_sm, P::MINB);
-  if (const char* cap = getenv("B2A_DEBUG_MAX_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(cap)));  // occupancy experiments
   const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
   if (a.whisper_norm) {
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     if ((e = cudaMemsetAsync(a.tile_min, 0x7f, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
-  frontend_kernel<P, PRE, SPEC, MEL, POST, CODE, OUT><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
@@ -991,25 +958,24 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   // at compile time on the post-processing and the output layout (small code: the whole tile loop stays inside the
   // instruction cache); everything else runs the run-time-configured kernel.
   int post = -1;
-  static const bool no_fused = getenv("B2A_DEBUG_NO_FUSED") != nullptr;   // A/B experiments
-  if (!no_fused && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
+  if (a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }
   const int id = a.bank.baked_id, om = a.out_mode;
   if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE) {
-    if (post == POST_WNORM && id == 1 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, 1, OUT_TM>(a, st, launches, err);
-    if (post == POST_WNORM && id == 1 && om == OUT_MT) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, 1, OUT_MT>(a, st, launches, err);
-    if (post == POST_WNORM && id == 2 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM, 1, OUT_TM>(a, st, launches, err);
-    if (post == POST_LN && id == 3 && om == OUT_LFR) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, 1, OUT_LFR>(a, st, launches, err);
-    if (post == POST_LN && id == 3 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, 1, OUT_TM>(a, st, launches, err);
+    if (post == POST_WNORM && id == 1 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM>(a, st, launches, err);
+    if (post == POST_WNORM && id == 1 && om == OUT_MT) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_MT>(a, st, launches, err);
+    if (post == POST_WNORM && id == 2 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM, OUT_TM>(a, st, launches, err);
+    if (post == POST_LN && id == 3 && om == OUT_LFR) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, OUT_LFR>(a, st, launches, err);
+    if (post == POST_LN && id == 3 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, OUT_TM>(a, st, launches, err);
     if (spec == SK_POWER) return launch_plan<Plan400, PRE_NONE, SK_POWER>(a, st, launches, err);
     if (spec == SK_MAG) return launch_plan<Plan400, PRE_NONE, SK_MAG>(a, st, launches, err);
     return launch_plan<Plan400, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400) {
     if (a.pre_mode == PRE_KALDI && post == POST_LN && id == 4 && om == OUT_TM)
-      return launch_plan<Plan512, PRE_KALDI, SK_POWER, 4, POST_LN, 1, OUT_TM>(a, st, launches, err);
+      return launch_plan<Plan512, PRE_KALDI, SK_POWER, 4, POST_LN, OUT_TM>(a, st, launches, err);
     if (a.pre_mode == PRE_KALDI && spec == SK_POWER) return launch_plan<Plan512, PRE_KALDI, SK_POWER>(a, st, launches, err);
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
