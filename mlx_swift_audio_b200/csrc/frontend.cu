@@ -87,7 +87,7 @@ struct Plan {
 using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 3>;
 using Plan512 = Plan<512, 400, 16, 32, 160, 32, 8, 2>;
 // n_fft 1920 (S3Gen 24 kHz mel): the exchange buffer only fits 16 frames, so half-warps take different items
-using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 8, 1>;
+using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 16, 1>;
 template <class P> constexpr bool plan_matches(const PlanShape& s) {
   return s.n_fft == P::N && s.n1 == P::N1 && s.n2 == P::N2 && s.frame_tile == P::FT && s.n_warps == P::NWARPS && s.n_chunks == P::NCHUNK;
 }
@@ -187,6 +187,12 @@ B2A_DEV float load_sample(const float* lane_pcm, int n2, float mu) {
 template <class P, int PRE, int... I>
 B2A_DEV void load_item(const float* lane_pcm, int n2, float mu, const float* wrow, float (&in)[P::N1], std::integer_sequence<int, I...>) {
   ((in[I] = load_sample<P, PRE, I>(lane_pcm, n2, mu) * wrow[I]), ...);
+}
+
+B2A_DEV float sqrt_approx(float x) {   // MUFU-based square root (~2 ulp): |X| for the magnitude front ends, 1e-4 tolerance downstream
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 B2A_DEV float lg2_ftz(float x) {
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
           }
         } else {
           const float pw = re * re + im * im;
-          s_p[(it * 2 * N2 + slot) * FT + fl] = SPEC == SK_POWER ? pw : sqrtf(pw);
+          s_p[(it * 2 * N2 + slot) * FT + fl] = SPEC == SK_POWER ? pw : sqrt_approx(pw);
         }
       };
       for (int it = wsub; it < H1; it += NIT) {
