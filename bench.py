@@ -44,6 +44,7 @@ WORKLOADS = {
     "kaldi": dict(batch=512, clip_s=20.0, sr=16000, desc="Kaldi-style 80-dim fbank (CAM++) + mean-norm, 512 x 20 s (configs[2], 3b)"),
     "s3gen": dict(batch=256, clip_s=10.0, sr=24000, desc="CosyVoice2/Chatterbox 24 kHz 80-mel (n_fft 1920, hop 480), 256 x 10 s (configs[3])"),
     "istft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="CosyVoice HiFT iSTFT (n_fft 16, hop 4), 512 x 30 s of mag/phase (configs[4], 5a)"),
+    "hift_head": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
     "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
 }
 
@@ -133,7 +134,18 @@ class GpuWorkload:
         g.manual_seed(1000 + (int(os.environ.get("RANK", "0"))))
         B, n = self.batch, self.n
         DEV = _lib.B2A_DEVICE
-        if name.startswith("istft"):
+        if name == "hift_head":
+            frames = n // 4 + 1
+            h = torch.randn((B, 18, frames), generator=g, device=dev)
+            h[:, :9] -= 2.0
+            h[:, 9:] *= 2.0
+            self.inputs = [h]
+            self.out = torch.empty((B, (frames - 1) * 4), device=dev)
+            win = np.ascontiguousarray(api.hannWindowPeriodic(16), np.float32)
+            self._keep = win
+            wp = win.ctypes.data_as(C.POINTER(C.c_float))
+            self.call = lambda c, i, o, sp: lib.b2a_hift_head_istft(c.h, i[0], B, frames, 16, 4, wp, C.c_float(0.99), o, sp)
+        elif name.startswith("istft"):
             nfft, hop = (16, 4) if name == "istft_hift" else (20, 5)
             F = nfft // 2 + 1
             frames = n // hop + 1
@@ -216,7 +228,17 @@ def _cpu_clip_job(args):
     except Exception:
         pass
     t0 = time.perf_counter()
-    if name.startswith("istft"):
+    if name == "hift_head":
+        frames = n // 4 + 1
+        rng = np.random.default_rng(seed)
+        h = rng.standard_normal((1, 18, frames)).astype(np.float32)
+        h[:, :9] -= 2.0
+        h[:, 9:] *= 2.0
+        gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            R.hift_head_istft(h, 16, 4, R.hann_window_periodic(16))
+    elif name.startswith("istft"):
         nfft, hop = (16, 4) if name == "istft_hift" else (20, 5)
         frames = n // hop + 1
         mag, ph = synth.mag_phase(1, nfft // 2 + 1, frames, seed=seed)

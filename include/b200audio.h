@@ -208,6 +208,16 @@ B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const 
                                     int64_t n_frames, int filter_length, int hop_length, int win_length,
                                     float* out, int space);
 
+/* ---- adjacent rows: vocoder glue fused around the iSTFT ----------------------------------------
+ * HiFT head: h = convPost output (batch, n_fft + 2, frames).  magnitude = exp(h[:, :F]), phase = sin(h[:, F:]),
+ * istftHiFiGAN, clip(output, -audio_limit, audio_limit).  Codec/S3Gen/HiFiGAN.swift:577-589 (audio_limit 0.99). */
+B2A_API int b2a_hift_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t batch, int64_t n_frames, int n_fft, int hop,
+                                const float* window, float audio_limit, float* out, int space);
+/* Kokoro head: x = conv_post output (batch, filter_length + 2, frames).  spec = exp(x[:, :F]), phase = sin(x[:, F:]),
+ * MLXSTFT.inverse.  TTS/Kokoro/Decoder/Generator.swift:182-190.  out (batch, 1, (frames-1)*hop). */
+B2A_API int b2a_kokoro_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t batch, int64_t n_frames, int filter_length,
+                                  int hop_length, int win_length, float* out, int space);
+
 /* Test hook (host only, no GPU): compiles a dense filterbank ((n_mels, n_bins), or (n_bins, n_mels) when
  * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */

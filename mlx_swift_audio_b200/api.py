@@ -488,6 +488,38 @@ def cosyVoice3Istft(magnitude, phase, nFft: int, hopLength: int, window, ctx: Co
     return _istft("b2a_cosyvoice3_istft", magnitude, phase, nFft, hopLength, window, ctx)
 
 
+def _head_istft(conv_out, n_fft, hop, ctx, call, out_shape):
+    h = _Arr(conv_out)
+    if len(h.shape) != 3 or h.shape[1] != n_fft + 2:
+        raise B2AError(L.B2A_E_BAD_ARG, f"expected the convolution output (B, {n_fft + 2}, frames)")
+    b, _, frames = h.shape
+    c = _ctx_for(h, ctx)
+    if frames < 2:
+        _raise(L.B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames")
+    out = h.empty(out_shape(b, (frames - 1) * hop))
+    c.check(call(c, h, b, frames, out))
+    return out
+
+
+def hiftHeadIstft(convOut, nFft: int, hopLength: int, window, audioLimit: float = 0.99, ctx: Context | None = None):
+    """Tail of HiFTGenerator.decode (Codec/S3Gen/HiFiGAN.swift:577-589) as one kernel: exp / sin split of the convPost
+    output (B, nFft+2, frames), istftHiFiGAN, clip to +-audioLimit.  -> (B, (frames-1)*hop)"""
+    w = np.ascontiguousarray(window, np.float32)
+    return _head_istft(convOut, nFft, hopLength, ctx,
+                       lambda c, h, b, frames, out: c.lib.b2a_hift_head_istft(c.h, h.ptr, b, frames, nFft, hopLength, _fptr(w),
+                                                                              float(audioLimit), _ptr(out), h.space),
+                       lambda b, n: (b, n))
+
+
+def kokoroHeadIstft(convOut, filterLength: int = 20, hopLength: int = 5, winLength: int = 20, ctx: Context | None = None):
+    """Tail of the Kokoro generator (TTS/Kokoro/Decoder/Generator.swift:182-190) as one kernel: exp / sin split of the
+    conv_post output (B, filterLength+2, frames) and MLXSTFT.inverse.  -> (B, 1, (frames-1)*hop)"""
+    return _head_istft(convOut, filterLength, hopLength, ctx,
+                       lambda c, h, b, frames, out: c.lib.b2a_kokoro_head_istft(c.h, h.ptr, b, frames, filterLength, hopLength,
+                                                                                winLength, _ptr(out), h.space),
+                       lambda b, n: (b, 1, n))
+
+
 class MLXSTFT:
     """TTS/Kokoro/Decoder/MLXSTFT.swift:165-235 (``transform`` / ``inverse`` / call)."""
 

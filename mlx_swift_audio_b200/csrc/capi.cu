@@ -757,21 +757,24 @@ int b2a_kokoro_stft_transform(b2a_ctx* c, const float* x, int64_t batch, int64_t
                            phase_out, space);
 }
 
+// head != 0: `mag` is the vocoder's convolution output (batch, 2F, frames), `phase` is unused (exp / sin are formed in the kernel)
 static int istft_common(b2a_ctx* c, const float* mag, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,
-                        const float* window, int use_clip_lo, float clip_hi, int norm, int unwrap, float* out, int space) {
+                        const float* window, int use_clip_lo, float clip_hi, int norm, int unwrap, float* out, int space,
+                        int head = 0, float out_limit = 0.0f) {
   int rc = check_common(c, mag, out, batch, n_frames);
   if (rc != B2A_OK) return rc;
-  if (!phase || !window) return fail(c, B2A_E_BAD_ARG, "null buffer");
+  if ((!head && !phase) || !window) return fail(c, B2A_E_BAD_ARG, "null buffer");
   if (n_frames < 2) return fail(c, B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames");
   Guard g(c);
   if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
-  const size_t per_in = size_t(n_fft / 2 + 1) * n_frames;
+  const size_t per_in = size_t(n_fft / 2 + 1) * n_frames * (head ? 2 : 1);
   const size_t per_out = size_t(n_frames - 1) * hop;
   Body body = [&](const float* d_mag, const float* d_phase, float* d_out, float*, int64_t n, int slot) -> int {
     IstftArgs a;
     a.n_fft = n_fft; a.hop = hop; a.mag = d_mag; a.phase = d_phase; a.batch = n; a.n_frames = n_frames; a.window = window;
     a.use_clip_lo = use_clip_lo; a.clip_lo = 0.0f; a.clip_hi = clip_hi; a.norm = norm; a.out = d_out;
-    if (unwrap) {
+    a.head = head; a.out_limit = out_limit;
+    if (unwrap && !head) {   // (head: phase = sin(.) in [-1, 1], unwrap is the identity)
       int r;
       if ((r = ensure(c, c->scratch[slot][0], sizeof(int))) != B2A_OK) return r;
       if ((r = ensure(c, c->scratch[slot][2], sizeof(float) * per_in * size_t(n))) != B2A_OK) return r;
@@ -787,7 +790,24 @@ static int istft_common(b2a_ctx* c, const float* mag, const float* phase, int64_
     if (r != B2A_OK) c->err = err;
     return r;
   };
-  return run_batched(c, space, batch, mag, per_in, phase, per_in, out, per_out, nullptr, 0, body);
+  return run_batched(c, space, batch, mag, per_in, head ? nullptr : phase, head ? 0 : per_in, out, per_out, nullptr, 0, body);
+}
+
+int b2a_hift_head_istft(b2a_ctx* c, const float* conv_out, int64_t batch, int64_t n_frames, int n_fft, int hop, const float* window,
+                        float audio_limit, float* out, int space) {
+  // magnitude = exp(h[:, :F]), phase = sin(h[:, F:]), istftHiFiGAN, clip to +-audioLimit (HiFiGAN.swift:577-589)
+  return istft_common(c, conv_out, nullptr, batch, n_frames, n_fft, hop, window, 0, 100.0f, NORM_WSQ_FLOOR, 0, out, space, 1, audio_limit);
+}
+
+int b2a_kokoro_head_istft(b2a_ctx* c, const float* conv_out, int64_t batch, int64_t n_frames, int filter_length, int hop_length,
+                          int win_length, float* out, int space) {
+  // spec = exp(x[:, :F]), phase = sin(x[:, F:]), MLXSTFT.inverse (Generator.swift:182-190); no limiter
+  if (!c) return B2A_E_BAD_ARG;
+  if (win_length != filter_length) return fail(c, B2A_E_UNSUPPORTED, "Kokoro inverse is built for win_length == filter_length");
+  std::vector<float> w;
+  hann_periodic_via_hanning(win_length, w);
+  return istft_common(c, conv_out, nullptr, batch, n_frames, filter_length, hop_length, w.data(), 0, 3.402823466e+38f, NORM_WSUM_NONZERO,
+                      1, out, space, 1, 0.0f);
 }
 
 int b2a_istft_hifigan(b2a_ctx* c, const float* magnitude, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,

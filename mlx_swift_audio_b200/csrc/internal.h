@@ -131,6 +131,8 @@ struct IstftArgs {
   int* h_flag = nullptr;
   float* out = nullptr;           // device (batch, (frames-1)*hop)
   float* scratch_phase = nullptr; // device, same size as phase, when unwrap != 0
+  int head = 0;                   // 1: `mag` is the vocoder's conv output (batch, 2F, frames); exp / sin formed in the kernel, `phase` unused
+  float out_limit = 0.0f;         // head: clip the waveform to +-out_limit (0 = none)
 };
 int launch_istft(const IstftArgs& a, void* stream, int* launches, std::string* err);
 

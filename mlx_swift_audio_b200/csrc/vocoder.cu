@@ -77,6 +77,32 @@ B2A_DEV float sin_small(float x, float u) {
   return fmaf(p * u, x, x);
 }
 
+// sin(x) for the fused vocoder head (phase = sin(conv output), any argument): the Cody-Waite path below 4.8e4, libdevice above
+__device__ __noinline__ float sin_huge(float x) { return sinf(x); }   // out of line: keeps the Payne-Hanek code off the hot path
+// sin(x), |x| < 4.8e4: x = k*pi + r with r in [-pi/2, pi/2] (magic-number rounding, 3-term Cody-Waite), sin(x) = (-1)^k sin(r)
+// with the degree-9 polynomial of sin_small; the parity of k goes straight into the sign bit.
+B2A_DEV float sin_any(float x) {
+  if (!(fabsf(x) < 48000.0f)) return sin_huge(x);
+  float q = fmaf(x, 0.318309886f, 12582912.0f);   // 1.5 * 2^23: round(x / pi) lands in the mantissa
+  const int k = __float_as_int(q);
+  q -= 12582912.0f;
+  float r = fmaf(q, -3.14159203e+00f, x);
+  r = fmaf(q, -6.27832947e-07f, r);
+  r = fmaf(q, -1.07806051e-14f, r);
+  const float s = sin_small(r, r * r);
+  return __int_as_float(__float_as_int(s) ^ (k << 31));
+}
+// exp(x) = 2^(x log2 e) on the MUFU, with the rounding error of the product x*log2(e) fed back (first-order): ~1.5 ulp for
+// |x| < 88, 0 below (flush to zero), +inf above -- the magnitudes are clipped at 100 right after.
+B2A_DEV float exp_fast(float x) {
+  const float t = x * 1.44269504f;
+  float e = fmaf(x, 1.44269504f, -t);          // exact residual of the product
+  e = fmaf(x, 1.92596299e-8f, e);              // + x * (log2 e - fl(log2 e))
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+  return fmaf(y, e * 0.693147182f, y);
+}
+
 template <int NFFT, int HOP>
 struct IstftParams {
   const float* mag;
@@ -87,6 +113,7 @@ struct IstftParams {
   float clip_lo, clip_hi;
   int use_clip_lo, norm;
   int* unwrap_flag;       // set to 1 if any |dphi| >= pi was seen (Kokoro optimistic path); may be null
+  float out_limit;        // HEAD: clip(output, -out_limit, out_limit) (HiFiGAN.swift:587); <= 0 = none
   float wn[NFFT];         // window[n] / NFFT
   float wenv[NFFT];       // window^2 (HiFT/CosyVoice3) or window (Kokoro): envelope contributions
   float inv_env[HOP];     // interior 1 / envelope
@@ -94,7 +121,10 @@ struct IstftParams {
 
 constexpr int kIstftThreads = 256;
 
-template <int NFFT, int HOP>
+// HEAD: the input is the vocoder's last convolution output h (batch, 2F, frames); magnitude = exp(h[:, :F]),
+// phase = sin(h[:, F:]) are formed in registers (HiFiGAN.swift:577-580, Generator.swift:182-183) and the waveform is clipped to
+// +-out_limit (HiFiGAN.swift:587) -- the exp / sin pass, the iSTFT and the limiter are one pass over 88 bytes per frame.
+template <int NFFT, int HOP, bool HEAD>
 __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_constant__ IstftParams<NFFT, HOP> prm) {
   constexpr int F = NFFT / 2 + 1;
   constexpr int R = NFFT / HOP;          // overlapping frames per output segment
@@ -122,22 +152,40 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
   // ---- per-frame inverse real FFT, windowed ------------------------------------------------------
   {
     float y[NFFT];
-    const float* __restrict__ mp = prm.mag + (clip * F * nF + f);
-    const float* __restrict__ pp = prm.phase + (clip * F * nF + f);
+    const long long clip_rows = HEAD ? 2 * F : F;   // rows of `frames` floats per clip in the source tensor(s)
+    const float* __restrict__ mp = prm.mag + (clip * clip_rows * nF + f);
+    const float* __restrict__ pp = prm.phase + (clip * clip_rows * nF + f);
     float xr[F], xi[F], ph[F];
     float amax = 0.0f;
+    if (HEAD) {
+      // all 2F loads first (memory-level parallelism), then the exp / sin arithmetic
 #pragma unroll
-    for (int k = 0; k < F; ++k) {
-      float m = has_frame ? __ldg(mp + k * nFu) : 0.0f;
-      ph[k] = has_frame ? __ldg(pp + k * nFu) : 0.0f;
-      m = fminf(m, prm.clip_hi);
-      if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
-      xr[k] = m;
-      amax = fmaxf(amax, fabsf(ph[k]));
+      for (int k = 0; k < F; ++k) {
+        xr[k] = has_frame ? __ldg(mp + k * nFu) : -200.0f;   // exp(-200) flushes to 0: frames outside the clip contribute nothing
+        ph[k] = has_frame ? __ldg(pp + k * nFu) : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        float m = fminf(exp_fast(xr[k]), prm.clip_hi);
+        if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
+        xr[k] = m;
+        ph[k] = sin_any(ph[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        float m = has_frame ? __ldg(mp + k * nFu) : 0.0f;
+        ph[k] = has_frame ? __ldg(pp + k * nFu) : 0.0f;
+        m = fminf(m, prm.clip_hi);
+        if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
+        xr[k] = m;
+        amax = fmaxf(amax, fabsf(ph[k]));
+      }
     }
     // every phase of the warp's 32 frames inside (-pi/2, pi/2)?  (false for NaN)  Then (a) sin / cos need no range
     // reduction and (b) no phase step inside the warp can reach pi.
-    const bool small = __all_sync(0xffffffffu, amax < 1.5707963f);
+    // (HEAD: |phase| <= 1 by construction, or NaN, which the polynomials propagate like the reference's cos / sin)
+    const bool small = HEAD || __all_sync(0xffffffffu, amax < 1.5707963f);
     if (NFFT == 20 && prm.unwrap_flag != nullptr && !small) {   // (only Kokoro's 20 / 5 transform unwraps)
       // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.  A pair (t-1, t) is
       // examined by the warp of frame t (left neighbour: shuffle, lane 0 from global memory) and, when t-1 is a warp's last
@@ -240,6 +288,10 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
         else o[i] = e != 0.0f ? o[i] / e : o[i];
       }
     }
+  }
+  if (HEAD && prm.out_limit > 0.0f) {
+#pragma unroll
+    for (int i = 0; i < HOP; ++i) o[i] = fminf(fmaxf(o[i], -prm.out_limit), prm.out_limit);
   }
   float* __restrict__ dst = prm.out + clip * prm.out_len;
   if (HOP == 4) {
@@ -376,6 +428,7 @@ static int cuda_fail2(cudaError_t e, const char* what, std::string* err) {
 template <int NFFT, int HOP>
 static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, std::string* err, const float* phase,
                           int* unwrap_flag) {
+  constexpr int F = NFFT / 2 + 1;
   constexpr int R = NFFT / HOP;
   IstftParams<NFFT, HOP> prm;
   prm.mag = a.mag;
@@ -392,6 +445,10 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   prm.use_clip_lo = a.use_clip_lo;
   prm.norm = a.norm;
   prm.unwrap_flag = unwrap_flag;
+  prm.out_limit = a.out_limit;
+  if (a.head) {   // one tensor (batch, 2F, frames): the phase rows follow the magnitude rows of the same clip
+    prm.phase = a.mag + (long long)F * a.n_frames;
+  }
   for (int n = 0; n < NFFT; ++n) {
     prm.wn[n] = a.window[n] / float(NFFT);
     prm.wenv[n] = a.norm == NORM_WSQ_FLOOR ? a.window[n] * a.window[n] : a.window[n];
@@ -405,7 +462,8 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   const long long n_seg = a.n_frames + R - 1;
   const int per_block = kIstftThreads - (R - 1);
   dim3 grid(unsigned((n_seg + per_block - 1) / per_block), unsigned(a.batch));
-  istft_kernel<NFFT, HOP><<<grid, kIstftThreads, 0, st>>>(prm);
+  if (a.head) istft_kernel<NFFT, HOP, true><<<grid, kIstftThreads, 0, st>>>(prm);
+  else istft_kernel<NFFT, HOP, false><<<grid, kIstftThreads, 0, st>>>(prm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail2(e, "istft_kernel launch", err);
   *launches += 1;

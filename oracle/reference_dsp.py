@@ -642,3 +642,26 @@ def kokoro_inverse(magnitude, phase, n_fft=20, hop=5, win_length=20, dt=F32) -> 
 
 def batch(fn, clips, *a, **k):
     return np.stack([fn(c, *a, **k) for c in clips])
+
+
+# --------------------------------------------------------------------------------------
+# adjacent rows: vocoder glue around the iSTFT
+# --------------------------------------------------------------------------------------
+
+def hift_head_istft(conv_out, n_fft: int, hop: int, window, audio_limit: float = 0.99, dt=F32) -> np.ndarray:
+    """Tail of HiFTGenerator.decode, Codec/S3Gen/HiFiGAN.swift:577-589: h (B, n_fft+2, frames) -> magnitude = exp(h[:, :F]),
+    phase = sin(h[:, F:]), istftHiFiGAN, clip(output, -audio_limit, audio_limit)."""
+    h = np.asarray(conv_out, dt)
+    f = n_fft // 2 + 1
+    mag = np.exp(h[:, :f, :]).astype(dt)
+    ph = np.sin(h[:, f:, :]).astype(dt)
+    y = istft_hifigan(mag, ph, n_fft, hop, window, dt)
+    return np.clip(y, dt(-audio_limit), dt(audio_limit)).astype(dt)
+
+
+def kokoro_head_istft(conv_out, n_fft: int = 20, hop: int = 5, win_length: int = 20, dt=F32) -> np.ndarray:
+    """Tail of the Kokoro generator, TTS/Kokoro/Decoder/Generator.swift:182-190: x (B, n_fft+2, frames) ->
+    spec = exp(x[:, :F]), phase = sin(x[:, F:]), MLXSTFT.inverse.  -> (B, 1, L)."""
+    x = np.asarray(conv_out, dt)
+    f = n_fft // 2 + 1
+    return kokoro_inverse(np.exp(x[:, :f, :]).astype(dt), np.sin(x[:, f:, :]).astype(dt), n_fft, hop, win_length, dt)

@@ -220,6 +220,31 @@ def test_kokoro_inverse_single_phase_jump(api, ctx, t_jump):
     assert np.abs(got - want).max() <= 2e-5
 
 
+@pytest.mark.parametrize("frames", [2, 254, 3001])
+def test_hift_head_istft(api, ctx, frames):
+    # convPost output: log-magnitudes N(-2, 1) (a few large ones: exp > 100 exercises the clip at 100), phase arguments N(0, 2^2)
+    rng = np.random.default_rng(300 + frames)
+    h = np.concatenate([rng.normal(-2.0, 1.0, (2, 9, frames)), rng.normal(0.0, 2.0, (2, 9, frames))], axis=1).astype(np.float32)
+    h[0, 3, frames // 2] = 5.5          # exp -> 244 -> clipped to 100 -> output beyond the +-0.99 limiter
+    h[1, 12, 0] = 4.0e4                 # large sine argument: range reduction path
+    w = R.hann_window_periodic(16)
+    got = api.hiftHeadIstft(h, 16, 4, w, 0.99, ctx=ctx)
+    want = R.hift_head_istft(h, 16, 4, w, 0.99)
+    assert got.shape == want.shape == (2, (frames - 1) * 4)
+    assert np.abs(got - want).max() <= 2e-5   # fp32 sin(4e4) itself is only good to ~4e-3 * 2^-23 * 4e4 ... see DESIGN.md
+    assert np.abs(got).max() <= 0.99
+
+
+@pytest.mark.parametrize("frames", [2, 253, 1201])
+def test_kokoro_head_istft(api, ctx, frames):
+    rng = np.random.default_rng(400 + frames)
+    x = np.concatenate([rng.normal(-2.0, 1.0, (2, 11, frames)), rng.normal(0.0, 2.0, (2, 11, frames))], axis=1).astype(np.float32)
+    got = api.kokoroHeadIstft(x, 20, 5, 20, ctx=ctx)
+    want = R.kokoro_head_istft(x)
+    assert got.shape == want.shape == (2, 1, (frames - 1) * 5)
+    assert np.abs(got - want).max() <= ISTFT_ATOL
+
+
 def test_forward_vocoder_stfts(api, ctx):
     x = synth.pcm(2, 4000, sample_rate=24000, seed=11, zero_tail_frac=0.0)
     w = R.hann_window_periodic(16)

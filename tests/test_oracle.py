@@ -128,3 +128,14 @@ def test_htk_bank_has_the_all_zero_filter():
     for nm in (80, 128, 40):
         f = R.mel_filters(16000, 400, nm, 0.0, 8000.0)
         assert ((f != 0).sum(axis=0) <= 2).all()
+
+
+def test_vocoder_heads_compose_the_pieces():
+    rng = np.random.default_rng(5)
+    h = rng.normal(0.0, 1.5, (2, 18, 40)).astype(np.float32)
+    w = R.hann_window_periodic(16)
+    y = R.hift_head_istft(h, 16, 4, w, 0.5)
+    ref = np.clip(R.istft_hifigan(np.exp(h[:, :9]), np.sin(h[:, 9:]), 16, 4, w), -0.5, 0.5)
+    assert np.array_equal(y, ref.astype(np.float32)) and np.abs(y).max() <= 0.5
+    x = rng.normal(0.0, 1.5, (1, 22, 30)).astype(np.float32)
+    assert np.array_equal(R.kokoro_head_istft(x), R.kokoro_inverse(np.exp(x[:, :11]), np.sin(x[:, 11:])))
