@@ -44,6 +44,7 @@ WORKLOADS = {
     "kaldi": dict(batch=512, clip_s=20.0, sr=16000, desc="Kaldi-style 80-dim fbank (CAM++) + mean-norm, 512 x 20 s (configs[2], 3b)"),
     "s3gen": dict(batch=256, clip_s=10.0, sr=24000, desc="CosyVoice2/Chatterbox 24 kHz 80-mel (n_fft 1920, hop 480), 256 x 10 s (configs[3])"),
     "istft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="CosyVoice HiFT iSTFT (n_fft 16, hop 4), 512 x 30 s of mag/phase (configs[4], 5a)"),
+    "whisper_segment": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper seek window: slice + zero-pad + fp16 cast of the 128-mel log-mel, 1024 clips (SURVEY 8f rank 1)"),
     "hift_head": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
     "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
 }
@@ -134,7 +135,19 @@ class GpuWorkload:
         g.manual_seed(1000 + (int(os.environ.get("RANK", "0"))))
         B, n = self.batch, self.n
         DEV = _lib.B2A_DEVICE
-        if name == "hift_head":
+        if name == "whisper_segment":
+            frames = 6000                      # mel of 30 s of audio + the 30 s of padding transcribe() appends
+            mel = torch.randn((B, frames, 128), generator=g, device=dev)
+            self.inputs = [mel]
+            self.out = torch.empty((B, 3000, 128), dtype=torch.float16, device=dev)
+            rs = np.random.default_rng(3)
+            seek = np.ascontiguousarray(rs.integers(0, 3000, B), np.int64)     # arbitrary frame offsets, as the decoder produces
+            content = np.full(B, 3000, np.int64)                               # 30 s of content: windows near the end are zero-padded
+            self._keep = (seek, content)
+            I64 = C.POINTER(C.c_int64)
+            self.call = lambda c, i, o, sp: lib.b2a_whisper_mel_segment_f16(c.h, i[0], B, frames, 128, seek.ctypes.data_as(I64),
+                                                                            content.ctypes.data_as(I64), 3000, o, sp)
+        elif name == "hift_head":
             frames = n // 4 + 1
             h = torch.randn((B, 18, frames), generator=g, device=dev)
             h[:, :9] -= 2.0
@@ -189,9 +202,11 @@ class GpuWorkload:
                 self.call = lambda c, i, o, sp: lib.b2a_s3gen_mel_spectrogram(c.h, i[0], B, n, 1920, 80, 24000, 480, 1920, 0, 8000, o, sp)
             else:
                 raise SystemExit(f"unknown workload {name}")
-        self.in_bytes = sum(t.numel() * 4 for t in self.inputs)
-        self.out_bytes = self.out.numel() * 4
+        self.in_bytes = sum(t.numel() * t.element_size() for t in self.inputs)
+        self.out_bytes = self.out.numel() * self.out.element_size()
         self.algo_bytes = self.in_bytes + self.out_bytes
+        if name == "whisper_segment":   # only the windows' rows are read (here: the rows up to frame 3000 from each seek)
+            self.algo_bytes = int(sum(3000 - int(s0) for s0 in self._keep[0])) * 128 * 4 + self.out_bytes
         self.DEV, self.HOST = _lib.B2A_DEVICE, _lib.B2A_HOST
         self.h_in = self.h_out = None
 
@@ -205,7 +220,7 @@ class GpuWorkload:
         self.h_in = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True) for t in self.inputs]
         for h, d in zip(self.h_in, self.inputs):
             h.copy_(d)
-        self.h_out = torch.empty(self.out.shape, dtype=torch.float32, pin_memory=True)
+        self.h_out = torch.empty(self.out.shape, dtype=self.out.dtype, pin_memory=True)
         torch.cuda.synchronize()
 
     def step_host(self):
@@ -228,7 +243,14 @@ def _cpu_clip_job(args):
     except Exception:
         pass
     t0 = time.perf_counter()
-    if name == "hift_head":
+    if name == "whisper_segment":
+        rng = np.random.default_rng(seed)
+        mel = rng.standard_normal((6000, 128)).astype(np.float32)
+        gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            R.whisper_mel_segment(mel, int(seed) % 3000, 3000)
+    elif name == "hift_head":
         frames = n // 4 + 1
         rng = np.random.default_rng(seed)
         h = rng.standard_normal((1, 18, frames)).astype(np.float32)

@@ -218,6 +218,13 @@ B2A_API int b2a_hift_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t bat
 B2A_API int b2a_kokoro_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t batch, int64_t n_frames, int filter_length,
                                   int hop_length, int win_length, float* out, int space);
 
+/* Whisper seek window: per clip, rows [seek, seek + min(length, content_frames - seek)) of the
+ * (batch, n_frames, n_mels) fp32 log-mel, zero-padded to `length` rows and cast to fp16 -- melSegment / padOrTrimMel / asType(.float16),
+ * STT/Whisper/WhisperSTT.swift:171-182,624-635 (and :156-157 with seek = 0).  seek / content_frames: HOST int64[batch].
+ * out_f16: (batch, length, n_mels) IEEE half, in `space`. */
+B2A_API int b2a_whisper_mel_segment_f16(b2a_ctx* ctx, const float* mel, int64_t batch, int64_t n_frames, int n_mels,
+                                        const int64_t* seek, const int64_t* content_frames, int64_t length, void* out_f16, int space);
+
 /* Test hook (host only, no GPU): compiles a dense filterbank ((n_mels, n_bins), or (n_bins, n_mels) when
  * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */

@@ -488,6 +488,28 @@ def cosyVoice3Istft(magnitude, phase, nFft: int, hopLength: int, window, ctx: Co
     return _istft("b2a_cosyvoice3_istft", magnitude, phase, nFft, hopLength, window, ctx)
 
 
+def whisperMelSegment(mel, seek, contentFrames, length: int = 3000, ctx: Context | None = None):
+    """Seek window of the Whisper decode loop (STT/Whisper/WhisperSTT.swift:171-182,624-635): rows
+    [seek, seek + min(length, contentFrames - seek)) of the fp32 log-mel (T', M) or (B, T', M), zero-padded to ``length`` rows,
+    as float16.  ``seek`` / ``contentFrames``: ints, or one per clip."""
+    a = _Arr(mel)
+    had_batch = len(a.shape) == 3
+    shape = a.shape if had_batch else (1,) + tuple(a.shape)
+    b, t, m = shape
+    sk = np.ascontiguousarray(np.broadcast_to(np.asarray(seek, np.int64), (b,)))
+    cf = np.ascontiguousarray(np.broadcast_to(np.asarray(contentFrames, np.int64), (b,)))
+    c = _ctx_for(a, ctx)
+    if a.space == L.B2A_DEVICE:
+        import torch
+        out = torch.empty((b, length, m), dtype=torch.float16, device=a.t.device)
+    else:
+        out = np.empty((b, length, m), np.float16)
+    I64 = C.POINTER(C.c_int64)
+    c.check(c.lib.b2a_whisper_mel_segment_f16(c.h, a.ptr, b, t, m, sk.ctypes.data_as(I64), cf.ctypes.data_as(I64), length, _ptr(out),
+                                              a.space))
+    return out if had_batch else out[0]
+
+
 def _head_istft(conv_out, n_fft, hop, ctx, call, out_shape):
     h = _Arr(conv_out)
     if len(h.shape) != 3 or h.shape[1] != n_fft + 2:

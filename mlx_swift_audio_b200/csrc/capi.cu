@@ -464,6 +464,42 @@ int b2a_pad_or_trim(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples
   return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(length), nullptr, 0, body);
 }
 
+int b2a_whisper_mel_segment_f16(b2a_ctx* c, const float* mel, int64_t batch, int64_t n_frames, int n_mels, const int64_t* seek,
+                                const int64_t* content_frames, int64_t length, void* out_f16, int space) {
+  int rc = check_common(c, mel, out_f16, batch, n_frames);
+  if (rc != B2A_OK) return rc;
+  if (!seek || !content_frames) return fail(c, B2A_E_BAD_ARG, "null seek / content_frames");
+  if (n_mels <= 0 || length <= 0 || length > 0x7fffffff || ((length * n_mels) & 1)) return fail(c, B2A_E_BAD_ARG, "bad n_mels / length");
+  for (int64_t b = 0; b < batch; ++b)
+    if (seek[b] < 0 || seek[b] > n_frames) return fail(c, B2A_E_BAD_ARG, "seek outside the mel");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  int64_t done = 0;   // clips already handed to the kernel (run_batched walks the batch in order)
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int slot) -> int {
+    int r;
+    if ((r = ensure(c, c->scratch[slot][0], sizeof(long long) * 2 * size_t(n))) != B2A_OK) return r;
+    std::vector<long long> sc(2 * size_t(n));
+    for (int64_t i = 0; i < n; ++i) {
+      sc[2 * i] = seek[done + i];
+      sc[2 * i + 1] = content_frames[done + i];
+    }
+    done += n;
+    // pageable-source copy: the host vector may be released as soon as the call returns
+    cudaError_t e = cudaMemcpyAsync(c->scratch[slot][0].p, sc.data(), sizeof(long long) * sc.size(), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return cu(c, e, "seek upload");
+    int launches = 0;
+    std::string err;
+    r = launch_mel_segment_f16(d_in, d_out, n, n_frames, n_mels, static_cast<const long long*>(c->scratch[slot][0].p), int(length),
+                               c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  // the fp16 output travels through the float-typed pipeline as (length * n_mels / 2) 32-bit words per clip
+  return run_batched(c, space, batch, mel, size_t(n_frames) * n_mels, nullptr, 0, static_cast<float*>(out_f16),
+                     size_t(length) * n_mels / 2, nullptr, 0, body);
+}
+
 static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding, float* out,
                         int space, bool chatterbox) {
   int rc = check_common(c, audio, out, batch, n_samples);

@@ -21,6 +21,7 @@
 //   * the per-clip max-8 clamp of Whisper / S3Tokenizer needs a clip-global maximum: the main
 //     kernel writes normalised values, tracks per-clip max and per-tile min, and a second tiny
 //     kernel rewrites only tiles whose minimum is below the clamp threshold.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -797,6 +798,50 @@ __global__ void pad_or_trim_kernel(const float* __restrict__ in, float* __restri
   const long long clip = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < length) out[clip * length + i] = i < n ? in[clip * n + i] : 0.0f;
+}
+
+// Whisper seek window (STT/Whisper/WhisperSTT.swift:171-182,624-635): rows
+// [seek, seek + min(length, content_frames - seek)) of a clip's (T', M) log-mel, zero-padded to `length` rows, cast to fp16
+// (round to nearest even, like MLX asType(.float16)).  One thread = 8 consecutive values: two 16-byte loads, one 16-byte store.
+// seek_content: per clip (seek, content_frames) as int64 pairs.
+__global__ void __launch_bounds__(256) mel_segment_f16_kernel(const float* __restrict__ mel, __half* __restrict__ out, long long n_frames,
+                                                              int n_mels, const long long* __restrict__ seek_content, int length) {
+  const long long clip = blockIdx.y;
+  const long long seek = seek_content[2 * clip], content = seek_content[2 * clip + 1];
+  long long seg = content - seek;
+  seg = seg < 0 ? 0 : (seg > length ? length : seg);
+  if (seek + seg > n_frames) seg = n_frames - seek > 0 ? n_frames - seek : 0;   // never read past the mel
+  const long long total = (long long)length * n_mels;
+  const float* __restrict__ src = mel + (clip * n_frames + seek) * n_mels;
+  __half* __restrict__ dst = out + clip * total;
+  const long long valid = seg * n_mels;   // the segment's rows are contiguous in both tensors
+  const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (e0 >= total) return;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && e0 + 8 <= total;
+  if (vec && e0 + 8 <= valid) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + e0)), b = __ldg(reinterpret_cast<const float4*>(src + e0 + 4));
+    __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(dst + e0) = *reinterpret_cast<const uint4*>(h);
+  } else if (vec && e0 >= valid) {
+    *reinterpret_cast<uint4*>(dst + e0) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (long long e = e0; e < e0 + 8 && e < total; ++e) dst[e] = e < valid ? __float2half_rn(__ldg(src + e)) : __float2half_rn(0.0f);
+  }
+}
+
+int launch_mel_segment_f16(const float* mel, void* out_f16, int64_t batch, int64_t n_frames, int n_mels, const long long* d_seek_content,
+                           int length, void* stream, int* launches, std::string* err) {
+  const long long total = (long long)length * n_mels;
+  dim3 grid(unsigned((total + 2047) / 2048), unsigned(batch));
+  mel_segment_f16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mel, static_cast<__half*>(out_f16), n_frames, n_mels,
+                                                                              d_seek_content, length);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("mel_segment_f16_kernel launch: ") + cudaGetErrorString(e);
+    return B2A_E_CUDA;
+  }
+  *launches += 1;
+  return B2A_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -111,6 +111,8 @@ int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int di
 int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err);
 int launch_lfr(const float* in, float* out, int64_t batch, int64_t n_frames, int n_mels, int lfr_m, int lfr_n,
                void* stream, int* launches, std::string* err);
+int launch_mel_segment_f16(const float* mel, void* out_f16, int64_t batch, int64_t n_frames, int n_mels, const long long* d_seek_content,
+                           int length, void* stream, int* launches, std::string* err);
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
                        int* launches, std::string* err);
 

@@ -665,3 +665,16 @@ def kokoro_head_istft(conv_out, n_fft: int = 20, hop: int = 5, win_length: int =
     x = np.asarray(conv_out, dt)
     f = n_fft // 2 + 1
     return kokoro_inverse(np.exp(x[:, :f, :]).astype(dt), np.sin(x[:, f:, :]).astype(dt), n_fft, hop, win_length, dt)
+
+
+
+def whisper_mel_segment(mel, seek: int, content_frames: int, length: int = 3000) -> np.ndarray:
+    """melSegment of the seek loop, STT/Whisper/WhisperSTT.swift:171-182 with padOrTrimMel (:624-635):
+    segmentSize = min(nFrames, contentFrames - seek); fullMel[seek ..< seek + segmentSize] zero-padded to nFrames rows,
+    cast to float16.  mel (T', M) fp32 -> (length, M) float16."""
+    mel = np.asarray(mel, F32)
+    seg = max(0, min(length, content_frames - seek))
+    rows = mel[seek:seek + seg]
+    out = np.zeros((length, mel.shape[1]), F32)
+    out[:rows.shape[0]] = rows
+    return out.astype(np.float16)

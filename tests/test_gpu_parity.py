@@ -220,6 +220,27 @@ def test_kokoro_inverse_single_phase_jump(api, ctx, t_jump):
     assert np.abs(got - want).max() <= 2e-5
 
 
+def test_whisper_mel_segment_f16(api, ctx):
+    # transcribe(): mel of the audio + 30 s of padding, content frames = len(audio) // 160, windows at arbitrary seeks
+    x = synth.pcm(2, 16000 * 7 + 123, seed=31)
+    mel = api.whisperLogMelSpectrogram(x, nMels=80, padding=480000, ctx=ctx)          # (2, 3700, 80)
+    content = x.shape[1] // 160
+    for seek in (0, 137, content - 5, content):
+        got = api.whisperMelSegment(mel, seek, content, ctx=ctx)
+        want = np.stack([R.whisper_mel_segment(m, seek, content) for m in mel])
+        assert got.dtype == np.float16 and got.shape == (2, 3000, 80)
+        assert np.array_equal(got.view(np.uint16), want.view(np.uint16)), seek     # a cast and a copy: bit exact
+    # per-clip seeks, 128 mels, a window that runs into the end of the mel, device tensors
+    import torch
+    mel128 = api.whisperLogMelSpectrogram(torch.from_numpy(x).cuda(), nMels=128)
+    seeks = np.array([10, mel128.shape[1] - 100])
+    got = api.whisperMelSegment(mel128, seeks, mel128.shape[1], length=3000)
+    torch.cuda.synchronize()
+    for b in range(2):
+        want = R.whisper_mel_segment(mel128[b].cpu().numpy(), int(seeks[b]), mel128.shape[1])
+        assert np.array_equal(got[b].cpu().numpy().view(np.uint16), want.view(np.uint16))
+
+
 @pytest.mark.parametrize("frames", [2, 254, 3001])
 def test_hift_head_istft(api, ctx, frames):
     # convPost output: log-magnitudes N(-2, 1) (a few large ones: exp > 100 exercises the clip at 100), phase arguments N(0, 2^2)

@@ -139,3 +139,13 @@ def test_vocoder_heads_compose_the_pieces():
     assert np.array_equal(y, ref.astype(np.float32)) and np.abs(y).max() <= 0.5
     x = rng.normal(0.0, 1.5, (1, 22, 30)).astype(np.float32)
     assert np.array_equal(R.kokoro_head_istft(x), R.kokoro_inverse(np.exp(x[:, :11]), np.sin(x[:, 11:])))
+
+
+
+def test_whisper_mel_segment_shapes_and_padding():
+    mel = np.arange(50 * 4, dtype=np.float32).reshape(50, 4) / 7
+    seg = R.whisper_mel_segment(mel, 45, 48, length=10)
+    assert seg.dtype == np.float16 and seg.shape == (10, 4)
+    assert np.array_equal(seg[:3], mel[45:48].astype(np.float16)) and not seg[3:].any()
+    assert not R.whisper_mel_segment(mel, 48, 48, length=10).any()
+    assert np.array_equal(R.whisper_mel_segment(mel, 0, 48, length=10), mel[:10].astype(np.float16))
