@@ -120,6 +120,29 @@ class Context {
     return out;
   }
 
+  // ---- adjacent rows ----
+  // Tail of HiFTGenerator.decode, Codec/S3Gen/HiFiGAN.swift:577-589: convPost output (B, nFft+2, frames) -> waveform, one kernel
+  Array hiftHeadIstft(const Array& convOut, int nFft, int hopLength, const std::vector<float>& window, float audioLimit = 0.99f) const {
+    const int64_t b = convOut.shape[0], frames = convOut.shape[2];
+    Array out({b, (frames - 1) * hopLength});
+    check(b2a_hift_head_istft(c_, convOut.data.data(), b, frames, nFft, hopLength, window.data(), audioLimit, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Tail of the Kokoro generator, TTS/Kokoro/Decoder/Generator.swift:182-190
+  Array kokoroHeadIstft(const Array& convOut, int filterLength = 20, int hopLength = 5, int winLength = 20) const {
+    const int64_t b = convOut.shape[0], frames = convOut.shape[2];
+    Array out({b, 1, (frames - 1) * hopLength});
+    check(b2a_kokoro_head_istft(c_, convOut.data.data(), b, frames, filterLength, hopLength, winLength, out.data.data(), B2A_HOST));
+    return out;
+  }
+  // Seek window of the Whisper decode loop, STT/Whisper/WhisperSTT.swift:171-182,624-635: (T', M) fp32 -> (length, M) IEEE half bits
+  std::vector<uint16_t> whisperMelSegment(const Array& mel, int64_t seek, int64_t contentFrames, int64_t length = 3000) const {
+    const int64_t t = mel.shape[0], m = mel.shape[1];
+    std::vector<uint16_t> out(size_t(length * m));
+    check(b2a_whisper_mel_segment_f16(c_, mel.data.data(), 1, t, int(m), &seek, &contentFrames, length, out.data(), B2A_HOST));
+    return out;
+  }
+
  private:
   b2a_ctx* c_ = nullptr;
 };

@@ -133,6 +133,30 @@ public final class B200Audio {
       } } } }
     return (re, im)
   }
+  /// Tail of HiFTGenerator.decode (Codec/S3Gen/HiFiGAN.swift:577-589) as one kernel: exp / sin split of the convPost output
+  /// (B, nFft+2, frames), istftHiFiGAN, clip to +-audioLimit.
+  public func hiftHeadIstft(convOut: Tensor, nFft: Int, hopLength: Int, window: Tensor, audioLimit: Float = 0.99) -> Tensor {
+    let b = convOut.shape[0], frames = convOut.shape[2]
+    var out = Tensor(zeros: [b, (frames - 1) * hopLength])
+    convOut.data.withUnsafeBufferPointer { h in window.data.withUnsafeBufferPointer { w in
+      out.data.withUnsafeMutableBufferPointer { o in
+        check(b2a_hift_head_istft(ctx, h.baseAddress, Int64(b), Int64(frames), Int32(nFft), Int32(hopLength), w.baseAddress, audioLimit,
+                                  o.baseAddress, Int32(B2A_HOST.rawValue)))
+      } } }
+    return out
+  }
+
+  /// Seek window of the Whisper decode loop (STT/Whisper/WhisperSTT.swift:171-182,624-635): (T', M) fp32 -> (length, M) Float16
+  public func whisperMelSegment(mel: Tensor, seek: Int, contentFrames: Int, length: Int = 3000) -> [Float16] {
+    var out = [Float16](repeating: 0, count: length * mel.shape[1])
+    var s = Int64(seek), c = Int64(contentFrames)
+    mel.data.withUnsafeBufferPointer { m in out.withUnsafeMutableBytes { o in
+      check(b2a_whisper_mel_segment_f16(ctx, m.baseAddress, 1, Int64(mel.shape[0]), Int32(mel.shape[1]), &s, &c, Int64(length),
+                                        o.baseAddress, Int32(B2A_HOST.rawValue)))
+    } }
+    return out
+  }
+  // kokoroHeadIstft binds b2a_kokoro_head_istft like hiftHeadIstft.
   // cosyVoice3Stft / cosyVoice3Istft, MLXSTFT.transform / .inverse, funASRLogMelSpectrogram, applyLFR, applyCMVN,
   // voiceEncoderMelspectrogram and stft bind b2a_cosyvoice3_*, b2a_kokoro_stft_*, b2a_funasr_log_mel_spectrogram,
   // b2a_apply_lfr, b2a_apply_cmvn, b2a_voice_encoder_melspectrogram and b2a_stft in exactly the same way.
