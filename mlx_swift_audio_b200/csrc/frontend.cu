@@ -704,21 +704,41 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 // Rewrites only the tiles whose minimum lies below the clip's clamp threshold:
 //   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, (Lmax + 4) / 4 - 2)   (x -> (x+4)/4 is monotone)
 // WhisperAudio.swift:130-134, S3TokenizerUtils.swift:203-205.
-constexpr int kClampTilesPerCta = 4;
-__global__ void whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
-                                     long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
-  // grid = (groups of kClampTilesPerCta tiles, clips): enough CTAs in flight to run at memory speed on the tiles it touches
+// One CTA per (clip, group of kClampTilesPerCta tiles): the group's tile minima are tested in parallel (one round trip to
+// memory), the tiles that need it are rewritten with 16-byte accesses.
+constexpr int kClampTilesPerCta = 32;
+__global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
+                                                            long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
+  __shared__ int s_list[kClampTilesPerCta];
+  __shared__ int s_count;
   const long long clip = blockIdx.y;
   const float thr = dec_ordered(clip_max[clip]) - 2.0f;   // clip_max holds the maximum of the normalised values: ((Lmax - 8) + 4) / 4 = (Lmax + 4) / 4 - 2
+  const int t0 = blockIdx.x * kClampTilesPerCta;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  if (threadIdx.x < kClampTilesPerCta && t0 + int(threadIdx.x) < tiles_per_clip &&
+      dec_ordered(tile_min[clip * tiles_per_clip + t0 + threadIdx.x]) < thr)
+    s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
+  __syncthreads();
+  const int count = s_count;
   float* o = out + clip * out_clip_stride;
-  const int t_end = min(tiles_per_clip, int(blockIdx.x + 1) * kClampTilesPerCta);
-  for (int t = blockIdx.x * kClampTilesPerCta; t < t_end; ++t) {
-    if (!(dec_ordered(tile_min[clip * tiles_per_clip + t]) < thr)) continue;
+  for (int i = 0; i < count; ++i) {
+    const int t = s_list[i];
     const long long f0 = (long long)t * ft;
     const int rows = int(n_frames - f0 < ft ? n_frames - f0 : ft);
     if (out_mode == OUT_TM) {
       float* d = o + f0 * n_mels;
-      for (int e = threadIdx.x; e < rows * n_mels; e += blockDim.x) d[e] = fmaxf(d[e], thr);
+      const int n = rows * n_mels;
+      if ((reinterpret_cast<uintptr_t>(d) & 15) == 0 && (n & 3) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(d);
+        for (int e = threadIdx.x; e < n / 4; e += blockDim.x) {
+          float4 v = d4[e];
+          v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+          d4[e] = v;
+        }
+      } else {
+        for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = fmaxf(d[e], thr);
+      }
     } else {  // OUT_MT
       for (int e = threadIdx.x; e < rows * n_mels; e += blockDim.x) {
         const int m = e / rows, r = e - m * rows;
