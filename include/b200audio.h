@@ -225,6 +225,13 @@ B2A_API int b2a_kokoro_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t b
 B2A_API int b2a_whisper_mel_segment_f16(b2a_ctx* ctx, const float* mel, int64_t batch, int64_t n_frames, int n_mels,
                                         const int64_t* seek, const int64_t* content_frames, int64_t length, void* out_f16, int space);
 
+/* resampleAudio / linearInterpolate1d: align_corners=False linear interpolation in fp32, bit-exact with
+ * TTS/CosyVoice2/CosyVoice2TTS.swift:733-744 + TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58.  out (batch, new length).
+ * (AVAudioConverter, Audio/AudioResampler.swift, is Apple's proprietary converter and has no reproducible definition.) */
+B2A_API int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int to_rate);
+B2A_API int b2a_resample_linear(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out,
+                                int space);
+
 /* Test hook (host only, no GPU): compiles a dense filterbank ((n_mels, n_bins), or (n_bins, n_mels) when
  * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */

@@ -488,6 +488,18 @@ def cosyVoice3Istft(magnitude, phase, nFft: int, hopLength: int, window, ctx: Co
     return _istft("b2a_cosyvoice3_istft", magnitude, phase, nFft, hopLength, window, ctx)
 
 
+def resampleAudio(audio, fromRate: int, toRate: int, ctx: Context | None = None):
+    """resampleAudio (TTS/CosyVoice2/CosyVoice2TTS.swift:733-744) = linearInterpolate1d
+    (TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58) on (T,) or (B, T); bit-exact fp32."""
+    a = _Arr(audio)
+    b, n, had_batch = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    new_t = int(c.lib.b2a_resample_linear_length(n, fromRate, toRate))
+    out = a.empty((b, new_t))
+    c.check(c.lib.b2a_resample_linear(c.h, a.ptr, b, n, fromRate, toRate, _ptr(out), a.space))
+    return out if had_batch else out[0]
+
+
 def whisperMelSegment(mel, seek, contentFrames, length: int = 3000, ctx: Context | None = None):
     """Seek window of the Whisper decode loop (STT/Whisper/WhisperSTT.swift:171-182,624-635): rows
     [seek, seek + min(length, contentFrames - seek)) of the fp32 log-mel (T', M) or (B, T', M), zero-padded to ``length`` rows,

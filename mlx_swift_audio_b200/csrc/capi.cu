@@ -464,6 +464,32 @@ int b2a_pad_or_trim(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples
   return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(length), nullptr, 0, body);
 }
 
+int b2a_resample_linear(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out, int space) {
+  int rc = check_common(c, x, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (from_rate <= 0 || to_rate <= 0) return fail(c, B2A_E_BAD_ARG, "sample rates must be positive");
+  if (n_samples >= (1LL << 31)) return fail(c, B2A_E_BAD_ARG, "clip too long");   // the reference indexes with int32
+  const int64_t new_t = b2a_resample_linear_length(n_samples, from_rate, to_rate);
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  const float step = float(n_samples) / float(new_t);
+  const float hi_clip = float(n_samples) - 1.001f;
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r;
+    if (from_rate == to_rate) {   // identity (CosyVoice2TTS.swift:734-736)
+      r = cu(c, cudaMemcpyAsync(d_out, d_in, sizeof(float) * size_t(n) * n_samples, cudaMemcpyDeviceToDevice, c->stream), "copy");
+    } else {
+      r = launch_resample_linear(d_in, d_out, n, n_samples, new_t, step, hi_clip, c->stream, &launches, &err);
+      if (r != B2A_OK) c->err = err;
+    }
+    c->launches += launches;
+    return r;
+  };
+  return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(new_t), nullptr, 0, body);
+}
+
 int b2a_whisper_mel_segment_f16(b2a_ctx* c, const float* mel, int64_t batch, int64_t n_frames, int n_mels, const int64_t* seek,
                                 const int64_t* content_frames, int64_t length, void* out_f16, int space) {
   int rc = check_common(c, mel, out_f16, batch, n_frames);

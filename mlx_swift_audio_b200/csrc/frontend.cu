@@ -864,6 +864,39 @@ int launch_mel_segment_f16(const float* mel, void* out_f16, int64_t batch, int64
   return B2A_OK;
 }
 
+// resampleAudio / linearInterpolate1d (TTS/CosyVoice2/CosyVoice2TTS.swift:733-744,
+// TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58): PyTorch-style align_corners=False linear interpolation, every
+// step in fp32 in the reference's op order (the source index is computed in fp32, so the order matters for bit-exactness;
+// __fmul_rn / __fadd_rn keep the compiler from contracting them into FMAs).
+__global__ void __launch_bounds__(256) resample_linear_kernel(const float* __restrict__ x, float* __restrict__ out, long long T, long long new_t,
+                                                              float step /* Float(T) / Float(newT) */, float hi_clip /* Float(T) - 1.001 */) {
+  const long long clip = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= new_t) return;
+  float idx = __fadd_rn(__fmul_rn(__fadd_rn(float(int(i)), 0.5f), step), -0.5f);   // (arange(int32).asType(float32) + 0.5) * step - 0.5
+  idx = fminf(fmaxf(idx, 0.0f), hi_clip);
+  const float fl = floorf(idx);
+  const int lo = int(fl);
+  const int hi = lo + 1 < int(T - 1) ? lo + 1 : int(T - 1);
+  const float wh = __fadd_rn(idx, -fl);
+  const float wl = __fadd_rn(1.0f, -wh);
+  const float* __restrict__ xc = x + clip * T;
+  out[clip * new_t + i] = __fadd_rn(__fmul_rn(__ldg(xc + lo), wl), __fmul_rn(__ldg(xc + hi), wh));
+}
+
+int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T, int64_t new_t, float step, float hi_clip, void* stream,
+                           int* launches, std::string* err) {
+  dim3 grid(unsigned((new_t + 255) / 256), unsigned(batch));
+  resample_linear_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, T, new_t, step, hi_clip);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("resample_linear_kernel launch: ") + cudaGetErrorString(e);
+    return B2A_E_CUDA;
+  }
+  *launches += 1;
+  return B2A_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------

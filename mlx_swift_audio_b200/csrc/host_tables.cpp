@@ -420,6 +420,14 @@ void b2a_voice_enc_config_default(b2a_voice_enc_config* c) {  // Config/Chatterb
   c->stft_magnitude_min = 1e-4f;
 }
 
+int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int to_rate) {  // CosyVoice2TTS.swift:733-739, CosyHiFTGenerator.swift:26-31
+  if (n_samples <= 0 || from_rate <= 0 || to_rate <= 0) return 0;
+  if (from_rate == to_rate) return n_samples;
+  const float ratio = float(to_rate) / float(from_rate);
+  int64_t n = int64_t(float(n_samples) * ratio);   // Int(Float(T) * scaleFactor): truncation, fp32 product
+  return n == 0 ? 1 : n;
+}
+
 const char* b2a_version(void) { return "b200audio 0.1 (sm_100a)"; }
 
 // Test hook (host only): compiles `bank` into the frontend kernel's mel step program and interprets it on the

@@ -678,3 +678,29 @@ def whisper_mel_segment(mel, seek: int, content_frames: int, length: int = 3000)
     out = np.zeros((length, mel.shape[1]), F32)
     out[:rows.shape[0]] = rows
     return out.astype(np.float16)
+
+
+
+def linear_interpolate_1d(x, scale_factor) -> np.ndarray:
+    """linearInterpolate1d, TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58, on (T,) or (B, T): PyTorch
+    align_corners=False linear interpolation, every step in fp32 in the reference's op order."""
+    x = np.asarray(x, F32)
+    t = x.shape[-1]
+    new_t = int(F32(t) * F32(scale_factor))
+    if new_t == 0:
+        new_t = 1
+    step = F32(t) / F32(new_t)
+    idx = ((np.arange(new_t, dtype=np.int32).astype(F32) + F32(0.5)) * step - F32(0.5)).astype(F32)
+    idx = np.clip(idx, F32(0), F32(t) - F32(1.001)).astype(F32)
+    lo = np.floor(idx).astype(np.int32)
+    hi = np.minimum(lo + 1, np.int32(t - 1))
+    wh = (idx - lo.astype(F32)).astype(F32)
+    wl = (F32(1.0) - wh).astype(F32)
+    return ((x[..., lo] * wl).astype(F32) + (x[..., hi] * wh).astype(F32)).astype(F32)
+
+
+def resample_audio(audio, from_rate: int, to_rate: int) -> np.ndarray:
+    """resampleAudio, TTS/CosyVoice2/CosyVoice2TTS.swift:733-744."""
+    if from_rate == to_rate:
+        return np.asarray(audio, F32)
+    return linear_interpolate_1d(audio, F32(to_rate) / F32(from_rate))

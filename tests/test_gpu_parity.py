@@ -220,6 +220,17 @@ def test_kokoro_inverse_single_phase_jump(api, ctx, t_jump):
     assert np.abs(got - want).max() <= 2e-5
 
 
+@pytest.mark.parametrize("rates", [(24000, 16000), (16000, 24000), (44100, 16000), (16000, 16000), (48000, 7)])
+def test_resample_audio_bit_exact(api, ctx, rates):
+    x = synth.pcm(2, 24000 * 3 + 17, sample_rate=rates[0], seed=41, zero_tail_frac=0.0)
+    got = api.resampleAudio(x, rates[0], rates[1], ctx=ctx)
+    want = R.resample_audio(x, rates[0], rates[1])
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    one = api.resampleAudio(x[0, :5], rates[0], rates[1], ctx=ctx)
+    assert np.array_equal(one, R.resample_audio(x[0, :5], rates[0], rates[1]))
+
+
 def test_whisper_mel_segment_f16(api, ctx):
     # transcribe(): mel of the audio + 30 s of padding, content frames = len(audio) // 160, windows at arbitrary seeks
     x = synth.pcm(2, 16000 * 7 + 123, seed=31)

@@ -149,3 +149,18 @@ def test_whisper_mel_segment_shapes_and_padding():
     assert np.array_equal(seg[:3], mel[45:48].astype(np.float16)) and not seg[3:].any()
     assert not R.whisper_mel_segment(mel, 48, 48, length=10).any()
     assert np.array_equal(R.whisper_mel_segment(mel, 0, 48, length=10), mel[:10].astype(np.float16))
+
+
+
+def test_resample_audio_matches_torch_interpolate():
+    import torch
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(4801).astype(np.float32)
+    for fr, to in ((24000, 16000), (16000, 24000), (22050, 16000)):
+        got = R.resample_audio(x, fr, to)
+        ref = torch.nn.functional.interpolate(torch.from_numpy(x)[None, None], size=got.shape[-1], mode="linear", align_corners=False)[0, 0].numpy()
+        assert got.shape == (int(np.float32(4801) * (np.float32(to) / np.float32(fr))),)
+        # same rule as torch (the reference's comment cites it) except at the very end, where the reference clips the source
+        # index to T - 1.001 instead of T - 1; elsewhere only the fp32 rounding of the source index differs
+        assert np.abs(got[:-2] - ref[:-2]).max() <= 1e-4
+    assert R.resample_audio(x, 16000, 16000) is not None and np.array_equal(R.resample_audio(x, 16000, 16000), x)
