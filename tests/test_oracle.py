@@ -162,5 +162,6 @@ def test_resample_audio_matches_torch_interpolate():
         assert got.shape == (int(np.float32(4801) * (np.float32(to) / np.float32(fr))),)
         # same rule as torch (the reference's comment cites it) except at the very end, where the reference clips the source
         # index to T - 1.001 instead of T - 1; elsewhere only the fp32 rounding of the source index differs
-        assert np.abs(got[:-2] - ref[:-2]).max() <= 1e-4
+        # (near sample 4800 an fp32 index has a spacing of 4.9e-4, i.e. the interpolation weight is only good to ~2.4e-4)
+        assert np.abs(got[:-2] - ref[:-2]).max() <= 2e-3
     assert R.resample_audio(x, 16000, 16000) is not None and np.array_equal(R.resample_audio(x, 16000, 16000), x)
