@@ -47,14 +47,16 @@ B2A_DEV void rdft(const float (&x)[16], float (&yr)[9], float (&yi)[9]) { b2a_rd
 B2A_DEV void rdft(const float (&x)[20], float (&yr)[11], float (&yi)[11]) { b2a_rdft20(x, yr, yi); }
 B2A_DEV void rdft(const float (&x)[32], float (&yr)[17], float (&yi)[17]) { b2a_rdft32(x, yr, yi); }
 B2A_DEV void rdft(const float (&x)[60], float (&yr)[31], float (&yi)[31]) { b2a_rdft60(x, yr, yi); }
+B2A_DEV void rdftodd(const float (&x)[16], float (&yr)[8], float (&yi)[8]) { b2a_rdftodd16(x, yr, yi); }
 B2A_DEV void rdftodd(const float (&x)[20], float (&yr)[10], float (&yi)[10]) { b2a_rdftodd20(x, yr, yi); }
 B2A_DEV void rdftodd(const float (&x)[32], float (&yr)[16], float (&yi)[16]) { b2a_rdftodd32(x, yr, yi); }
+B2A_DEV void cdft(const float (&xr)[16], const float (&xi)[16], float (&yr)[16], float (&yi)[16]) { b2a_cdft16(xr, xi, yr, yi); }
 B2A_DEV void cdft(const float (&xr)[20], const float (&xi)[20], float (&yr)[20], float (&yi)[20]) { b2a_cdft20(xr, xi, yr, yi); }
 B2A_DEV void cdft(const float (&xr)[32], const float (&xi)[32], float (&yr)[32], float (&yi)[32]) { b2a_cdft32(xr, xi, yr, yi); }
 
 // inter-stage twiddles W_N^{n2*k1}, k1 = 1..N1/2-1, as (cos, -sin); filled once per device
 __constant__ float2 c_tw400[20 * 9];
-__constant__ float2 c_tw512[32 * 7];
+__constant__ float2 c_tw512[16 * 15];
 __constant__ float2 c_tw1920[32 * 29];
 
 template <int N_, int WIN_, int N1_, int N2_, int HOP_, int FT_, int NWARPS_, int MINB_>
@@ -86,7 +88,8 @@ struct Plan {
 // shared memory per CTA -> three CTAs (30 warps) per SM, which hides the barrier / shared-memory latencies better than
 // prefetching the next tile into a second buffer with two CTAs per SM
 using Plan400 = Plan<400, 400, 20, 20, 160, 32, 10, 3>;
-using Plan512 = Plan<512, 400, 16, 32, 160, 32, 8, 2>;
+// 512 = 32 x 16: 16 stage-A items (real DFTs of size 32) and 15 complex + 1 (real + odd-real) stage-B items of size 16, one per warp
+using Plan512 = Plan<512, 400, 32, 16, 160, 32, 16, 2>;
 // n_fft 1920 (S3Gen 24 kHz mel): the exchange buffer only fits 16 frames, so half-warps take different items
 using Plan1920 = Plan<1920, 1920, 60, 32, 480, 16, 16, 1>;
 template <class P> constexpr bool plan_matches(const PlanShape& s) {
@@ -920,7 +923,7 @@ int init_frontend_tables(std::string* err) {
   cudaError_t e;
   fill_tw(t, 400, 20, 20);
   if ((e = cudaMemcpyToSymbol(c_tw400, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
-  fill_tw(t, 512, 16, 32);
+  fill_tw(t, 512, 32, 16);
   if ((e = cudaMemcpyToSymbol(c_tw512, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
   fill_tw(t, 1920, 60, 32);
   if ((e = cudaMemcpyToSymbol(c_tw1920, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);

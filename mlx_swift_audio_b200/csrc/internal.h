@@ -26,7 +26,7 @@ void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major
 // Shape of the frontend kernel's FFT plans (frontend.cu static_asserts that its Plan types agree): n_fft = n1 * n2, CTA tile
 // of `frame_tile` frames, `n_chunks` mel chunks (one per warp, or per half-warp for 16-frame tiles).
 struct PlanShape { int n_fft, n1, n2, frame_tile, n_warps, n_chunks; };
-constexpr PlanShape kPlanShapes[3] = {{400, 20, 20, 32, 10, 10}, {512, 16, 32, 32, 8, 8}, {1920, 60, 32, 16, 16, 32}};
+constexpr PlanShape kPlanShapes[3] = {{400, 20, 20, 32, 10, 10}, {512, 32, 16, 32, 16, 16}, {1920, 60, 32, 16, 16, 32}};
 inline const PlanShape* plan_shape(int n_fft) {
   for (const PlanShape& p : kPlanShapes)
     if (p.n_fft == n_fft) return &p;

@@ -445,7 +445,7 @@ def gen_rdft_odd(n):
 
 
 RDFT = [16, 20, 25, 32, 40, 60, 64]
-RDFT_ODD = [20, 25, 32]
+RDFT_ODD = [16, 20, 25, 32]
 CDFT = [16, 20, 25, 30, 32]
 C2R = [16, 20]
 
