@@ -188,6 +188,37 @@ B2A_DEV float load_sample(const float* lane_pcm, int n2, float mu) {
   return v;
 }
 
+// Kaldi pre-processing in two steps around the per-frame mean: the raw samples of the item (zero beyond the window) ...
+template <class P, int n1>
+B2A_DEV float raw_sample(const float* lane_pcm, int n2) {
+  constexpr int base = P::N2 * n1;
+  if (base >= P::WIN) return 0.0f;
+  const float v = lane_pcm[pcm_off<P, n1>(n2)];
+  return (base + P::N2 - 1 >= P::WIN && base + n2 >= P::WIN) ? 0.0f : v;
+}
+// ... and (x[o]-mu) - 0.97*(x[o-1]-mu), first sample only DC-removed (CAMPPlus.swift:66-72), times the window
+template <class P, int n1>
+B2A_DEV float kaldi_sample(float raw, const float* lane_pcm, int n2, float mu, float w) {
+  constexpr int base = P::N2 * n1;
+  if (base >= P::WIN) return 0.0f;
+  const int o = base + n2;
+  float v = raw - mu;
+  if (o > 0) {
+    const int poff = pcm_off<P, n1>(n2) - 1 - ((o % P::HOP) == 0 ? 1 : 0);  // previous sample may sit before the row's pad word
+    v = v - 0.97f * (lane_pcm[poff] - mu);
+  }
+  if (base + P::N2 - 1 >= P::WIN && o >= P::WIN) v = 0.0f;
+  return v * w;
+}
+template <class P, int... I>
+B2A_DEV void load_raw_item(const float* lane_pcm, int n2, float (&raw)[P::N1], std::integer_sequence<int, I...>) {
+  ((raw[I] = raw_sample<P, I>(lane_pcm, n2)), ...);
+}
+template <class P, int... I>
+B2A_DEV void kaldi_item(const float* lane_pcm, int n2, float mu, const float* wrow, float (&v)[P::N1], std::integer_sequence<int, I...>) {
+  ((v[I] = kaldi_sample<P, I>(v[I], lane_pcm, n2, mu, wrow[I])), ...);
+}
+
 template <class P, int PRE, int... I>
 B2A_DEV void load_item(const float* lane_pcm, int n2, float mu, const float* wrow, float (&in)[P::N1], std::integer_sequence<int, I...>) {
   ((in[I] = load_sample<P, PRE, I>(lane_pcm, n2, mu) * wrow[I]), ...);
@@ -339,6 +370,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   constexpr int SUB = P::SUB, NIT = NW * SUB;
+  __shared__ float s_part[PRE == PRE_KALDI ? NW * FT : 1];   // Kaldi: per-warp partial sums of the frame mean
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
 
@@ -375,22 +407,6 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     cp_async_commit_wait_all();
     __syncthreads();
 
-    // ---- 1b. Kaldi per-frame mean (CAMPPlus.swift:66): partial sums per warp, fixed-order combine ----
-    float mu = 0.0f;
-    if (PRE == PRE_KALDI) {
-      float part = 0.0f;
-      static_assert(PRE != PRE_KALDI || SUB == 1, "Kaldi pre-processing is built for 32-frame tiles");
-      const int fk = lane < (prm.n_frames - f0) ? lane : int(prm.n_frames - f0) - 1;
-      for (int o = warp; o < WIN; o += NW) part += s_r0[fk * P::PITCH + o + o / HOP];
-      s_p[warp * FT + fl] = part;   // scratch: the exchange buffer is idle until stage A
-      __syncthreads();
-      float tot = 0.0f;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) tot += s_p[w * FT + fl];
-      mu = tot / float(WIN);
-      __syncthreads();
-    }
-
     // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
     // not a conflict), so that per-tile max / min need no lane masking.
     const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
@@ -407,7 +423,24 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
           wrow[4 * q] = w4.x; wrow[4 * q + 1] = w4.y; wrow[4 * q + 2] = w4.z; wrow[4 * q + 3] = w4.w;
         }
         float in[N1];
-        load_item<P, PRE>(lane_pcm, n2, mu, wrow, in, std::make_integer_sequence<int, N1>{});
+        if (PRE == PRE_KALDI) {
+          // Per-frame mean (CAMPPlus.swift:66) without a pass of its own: every warp owns exactly one item, sums the raw
+          // samples it has just loaded, and the warps' partial sums are combined in fixed order.
+          static_assert(PRE != PRE_KALDI || (SUB == 1 && N2 == NIT), "Kaldi pre-processing: 32-frame tiles, one stage-A item per warp");
+          load_raw_item<P>(lane_pcm, n2, in, std::make_integer_sequence<int, N1>{});
+          float part = 0.0f;
+#pragma unroll
+          for (int i = 0; i < N1; ++i) part += in[i];
+          s_part[warp * FT + fl] = part;
+          __syncthreads();
+          float tot = 0.0f;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) tot += s_part[w * FT + fl];
+          const float mu = tot / float(WIN);
+          kaldi_item<P>(lane_pcm, n2, mu, wrow, in, std::make_integer_sequence<int, N1>{});
+        } else {
+          load_item<P, PRE>(lane_pcm, n2, 0.0f, wrow, in, std::make_integer_sequence<int, N1>{});
+        }
         float yr[H1 + 1], yi[H1 + 1];
         rdft(in, yr, yi);
         float2* yb = s_y + n2 * FT + fl;
