@@ -81,6 +81,24 @@ def main():
     size = os.path.getsize(os.path.join(OUT, "oracle_fp32_v1.npz"))
     print("wrote", len(g), "arrays,", size // 1024, "KiB")
 
+    # adjacent rows: separate file, the v1 vectors stay byte-identical
+    a = {}
+    rng = np.random.default_rng(2010)
+    h16 = np.concatenate([rng.normal(-2.0, 1.0, (2, 9, 301)), rng.normal(0.0, 2.0, (2, 9, 301))], axis=1).astype(np.float32)
+    h16[0, 2, 100] = 5.2                                  # exp -> 181 -> magnitude clip at 100 -> output limiter
+    h20 = np.concatenate([rng.normal(-2.0, 1.0, (2, 11, 241)), rng.normal(0.0, 2.0, (2, 11, 241))], axis=1).astype(np.float32)
+    a["in_h16"], a["in_h20"] = h16, h20
+    a["hift_head_istft"] = R.hift_head_istft(h16, 16, 4, w16, 0.99)
+    a["kokoro_head_istft"] = R.kokoro_head_istft(h20)
+    mel = R.whisper_log_mel_spectrogram(np.concatenate([x16[0], np.zeros(4000, np.float32)]), 80)   # 75 frames, 50 of content
+    a["in_mel"] = mel
+    a["mel_segment_seek0"] = R.whisper_mel_segment(mel, 0, 50, length=64)
+    a["mel_segment_seek37"] = R.whisper_mel_segment(mel, 37, 50, length=64)
+    a["resample_24k_16k"] = R.resample_audio(x24, 24000, 16000)
+    a["resample_16k_24k"] = R.resample_audio(x16, 16000, 24000)
+    np.savez_compressed(os.path.join(OUT, "oracle_fp32_v2_adjacent.npz"), **{k: np.asarray(v) for k, v in a.items()})
+    print("wrote", len(a), "arrays,", os.path.getsize(os.path.join(OUT, "oracle_fp32_v2_adjacent.npz")) // 1024, "KiB")
+
 
 if __name__ == "__main__":
     main()

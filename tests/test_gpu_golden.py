@@ -49,3 +49,17 @@ def test_cuda_path_matches_golden_vectors(ctx):
     assert max(np.abs(re - g["cv3_stft_re"]).max(), np.abs(im - g["cv3_stft_im"]).max()) <= 1e-5
     mag, ph = st.transform(x24[:, :2000])
     assert np.abs(mag - g["kokoro_mag"]).max() <= 1e-5
+
+
+def test_cuda_adjacent_rows_match_golden_vectors(ctx):
+    from mlx_swift_audio_b200 import api as A
+    a = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_fp32_v2_adjacent.npz"))
+    g = np.load(GOLD)
+    w16 = A.hannWindowPeriodic(16)
+    assert np.abs(A.hiftHeadIstft(a["in_h16"], 16, 4, w16, 0.99, ctx=ctx) - a["hift_head_istft"]).max() <= 2e-5
+    assert np.abs(A.kokoroHeadIstft(a["in_h20"], ctx=ctx) - a["kokoro_head_istft"]).max() <= 1e-5
+    for seek, key in ((0, "mel_segment_seek0"), (37, "mel_segment_seek37")):
+        got = A.whisperMelSegment(a["in_mel"], seek, 50, length=64, ctx=ctx)
+        assert np.array_equal(got.view(np.uint16), a[key].view(np.uint16))
+    assert np.array_equal(A.resampleAudio(g["in_x24"], 24000, 16000, ctx=ctx), a["resample_24k_16k"])
+    assert np.array_equal(A.resampleAudio(g["in_x16"], 16000, 24000, ctx=ctx), a["resample_16k_24k"])

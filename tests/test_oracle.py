@@ -165,3 +165,15 @@ def test_resample_audio_matches_torch_interpolate():
         # (near sample 4800 an fp32 index has a spacing of 4.9e-4, i.e. the interpolation weight is only good to ~2.4e-4)
         assert np.abs(got[:-2] - ref[:-2]).max() <= 2e-3
     assert R.resample_audio(x, 16000, 16000) is not None and np.array_equal(R.resample_audio(x, 16000, 16000), x)
+
+
+def test_golden_adjacent_rows():
+    a = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_fp32_v2_adjacent.npz"))
+    g = np.load(GOLD)
+    w16 = R.hann_window_periodic(16)
+    assert np.abs(R.hift_head_istft(a["in_h16"], 16, 4, w16, 0.99) - a["hift_head_istft"]).max() <= 1e-6
+    assert np.abs(R.kokoro_head_istft(a["in_h20"]) - a["kokoro_head_istft"]).max() <= 1e-6
+    assert np.array_equal(R.whisper_mel_segment(a["in_mel"], 0, 50, length=64).view(np.uint16), a["mel_segment_seek0"].view(np.uint16))
+    assert np.array_equal(R.whisper_mel_segment(a["in_mel"], 37, 50, length=64).view(np.uint16), a["mel_segment_seek37"].view(np.uint16))
+    assert np.array_equal(R.resample_audio(g["in_x24"], 24000, 16000), a["resample_24k_16k"])
+    assert np.array_equal(R.resample_audio(g["in_x16"], 16000, 24000), a["resample_16k_24k"])
