@@ -5,22 +5,26 @@
 // Codec/S3Tokenizer/S3TokenizerUtils.swift:224-263, STT/Whisper/WhisperAudio.swift:78-137 and the
 // other front ends listed in include/b200audio.h).  Nothing here is derived from MLX source.
 //
-// Design (see DESIGN.md "frontend kernel"):
-//   * a CTA owns a tile of FT = 32 consecutive frames of one clip; LANE == FRAME in every stage, so
+// Design:
+//   * persistent CTAs; a tile is FT = 32 (or 16) consecutive frames of one clip; LANE == FRAME in every stage, so
 //     twiddles / window values / filter weights are warp-uniform operands and every shared-memory
 //     access is stride-1 across lanes (conflict-free by construction);
-//   * PCM for the tile is loaded once from HBM with coalesced float4 loads into shared memory
-//     (row pitch HOP+1 so that the stride-HOP frame starts fall in distinct banks) -- the 2.5x
-//     (or 4x) frame overlap is served from shared memory, never from HBM;
+//   * PCM for the tile is copied once from HBM with cp.async into shared memory (row pitch HOP+1 so that the
+//     stride-HOP frame starts fall in distinct banks) -- the 2.5x (or 4x) frame overlap is served from shared
+//     memory, never from HBM; the next tile's copy is issued as soon as stage A has consumed the current one;
 //   * real FFT of size N = N1*N2 as two register-resident stages of generated straight-line
 //     codelets (tools/gen_codelets.py): stage A = N2 real DFTs of size N1 (+ inter-stage twiddle),
-//     one shared-memory exchange, stage B = N1/2+1 DFTs of size N2 (complex / real / odd-real);
+//     one shared-memory exchange, stage B = N1/2 items of size N2 (complex; k1 = 0 and N1/2 share one item);
 //     warps split the items of each stage;
-//   * mel projection is sparse (each triangular filter is a short contiguous run of bins), fused
-//     with log/floor/scale; output tile is staged and written with coalesced stores;
+//   * shared memory is used three times per tile: stage B writes |X|^2 back into its own rows of the exchange
+//     buffer, the mel stage leaves its sums in the rows the spectrum does not use;
+//   * mel projection is sparse (a bin feeds at most two adjacent triangular filters): a step program interpreted
+//     in a loop for arbitrary banks, build-time generated straight-line code (mel_baked.h) for the standard ones;
+//     log / floor / scale fused into the coalesced store loop;
 //   * the per-clip max-8 clamp of Whisper / S3Tokenizer needs a clip-global maximum: the main
-//     kernel writes normalised values, tracks per-clip max and per-tile min, and a second tiny
-//     kernel rewrites only tiles whose minimum is below the clamp threshold.
+//     kernel writes normalised values, tracks per-clip max and per-tile min, and a second small
+//     kernel rewrites only tiles whose minimum is below the clamp threshold;
+//   * the tile loop's instruction footprint is kept near 32 KB (what the SM's instruction cache serves at full rate).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -72,7 +76,6 @@ struct Plan {
   static constexpr int Y_WORDS = N * FT;           // H1 float2 slots x N2 x FT; stage B leaves the real spectrum tile here too
   static constexpr int P_PITCH = FT + 1;
   static constexpr bool CPLX_DIRECT = (N / 2 + 1) * (FT + 1) * 2 * 4 > 64 * 1024;  // complex tile would not fit: stft() stores directly
-  static constexpr int MAX_STEPS = NBINS + 32 * NWARPS * (32 / FT);    // mel step program: one step per bin (+ chunk-boundary repeats, empty filters)
   static constexpr int P_WORDS_CPLX = NBINS * P_PITCH * 2;
   // region 0: the PCM tile, later the [m][frame] output staging tile (plain stft(): the complex spectrum tile)
   static constexpr int R0_WORDS_REAL = PCM_WORDS;
