@@ -609,27 +609,32 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         if (out_mode == OUT_TM) {
           // (T', M) rows, every row a run of coalesced 128-byte segments; rows warp, warp + NW, ... as immediates
           float* d = dst + ((long long)f0 + warp) * MB + lane;
-          constexpr int NI = (FT + NW - 1) / NW;
-          // one predicate per row slot (the last slot exists for the first warps only; partial tiles end early): the
-          // loads are unconditional (staging rows past `rows` hold the recomputed last frame), only the stores are guarded
-          bool ok[NI];
+          // Row slots warp, warp + NW, ...: NF of them exist for every warp (branch-free: loads unconditional -- staging
+          // rows past `rows` hold the recomputed last frame -- only the stores are guarded); the remaining FT - NF*NW rows
+          // go to the first warps under a warp-uniform branch.
+          constexpr int NF = FT / NW;
+          bool ok[NF + 1];
 #pragma unroll
-          for (int i = 0; i < NI; ++i) ok[i] = warp + i * NW < rows;
+          for (int i = 0; i <= NF; ++i) ok[i] = warp + i * NW < rows;
+          const bool extra = FT % NW != 0 && warp + NF * NW < FT;   // warp-uniform
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             const bool col_ok = c < MB / 32 || lane < MB % 32;
             const float* sr = srow[c] + warp;
-            float v[NI];
+            float v[NF + 1];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) v[i] = sr[(warp + i * NW < FT ? i : 0) * NW];
+            for (int i = 0; i < NF; ++i) v[i] = post_pure(sr[i * NW]);
 #pragma unroll
-            for (int i = 0; i < NI; ++i) v[i] = post_pure(v[i]);
+            for (int i = 0; i + 1 < NF; i += 2) track2(v[i], v[i + 1]);
+            if (NF % 2) track2(v[NF - 1], v[NF - 1]);
 #pragma unroll
-            for (int i = 0; i + 1 < NI; i += 2) track2(v[i], v[i + 1]);
-            if (NI % 2) track2(v[NI - 1], v[NI - 1]);
-#pragma unroll
-            for (int i = 0; i < NI; ++i)
+            for (int i = 0; i < NF; ++i)
               if (ok[i] && col_ok) d[i * NW * MB + c * 32] = v[i];
+            if (extra) {
+              v[NF] = post_pure(sr[NF * NW]);
+              track2(v[NF], v[NF]);
+              if (ok[NF] && col_ok) d[NF * NW * MB + c * 32] = v[NF];
+            }
           }
         } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
           const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
