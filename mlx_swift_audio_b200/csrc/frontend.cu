@@ -362,8 +362,10 @@ template <class P, int PRE, int SPEC, int MEL, int POST, int OUT>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
-  constexpr bool BAKED = MEL > 0;    // straight-line mel code, compile-time post-processing and output layout
-  static_assert(BAKED == (POST != POST_RUNTIME) && BAKED == (OUT >= 0), "known banks come with compile-time POST and OUT");
+  constexpr bool BAKED = MEL > 0;                 // straight-line mel code
+  constexpr bool FIXED = POST != POST_RUNTIME;    // compile-time post-processing and output layout: short store code
+  static_assert((!BAKED || FIXED) && FIXED == (OUT >= 0), "known banks come with compile-time POST and OUT");
+  static_assert(BAKED || !FIXED || OUT == OUT_MT, "interpreted bank with compile-time POST: built for the (M, T') layout");
   constexpr bool EARLY_PREFETCH = !cplx;   // the PCM region is dead after stage A: refill it during stage B / mel / store
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
   static_assert(MEL == 0 || (SPEC == SK_POWER && FT == 32), "known banks are power-spectrum banks of the 32-frame plans");
@@ -592,15 +594,15 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
     // ---- 5. store of the staged tile (baked: plain transposing copy; otherwise log / floor / scale fused in) ----
     float* __restrict__ dst = prm.out + (long long)clip * prm.out_clip_stride;
-    if (BAKED) {
+    if (FIXED) {
       constexpr int MB = MelTraits<MEL>::M;
-      constexpr int NC = MB > 0 ? (MB + 31) / 32 : 1;   // (MEL == 0 instantiates this dead branch with MB == 0)
+      constexpr int NC = MB > 0 ? (MB + 31) / 32 : 1;   // (MEL == 0: the row-major branches below are dead, MB == 0)
       if (out_mode == OUT_MT) {
         // (M, T') rows: lanes run over frames
         const long long nfr = prm.n_frames;
         float* d = dst + f0 + fl;
         if (frame_ok)
-          for (int m = wsub; m < MB; m += NIT) d[m * nfr] = post(s_p[out_base_words<P>(m) + fl]);
+          for (int m = wsub; m < M; m += NIT) d[m * nfr] = post(s_p[out_base_words<P>(m) + fl]);
       } else {
         // lanes run over m: one staging pointer per 32-filter chunk (bank = (m + frame) mod 32: conflict free)
         const float* srow[NC];
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (!BAKED && prm.whisper_norm) {
+    if (!FIXED && prm.whisper_norm) {
       const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
       const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
       if (lane == 0) {
@@ -1128,6 +1130,9 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (a.n_fft == 1920 && a.hop == 480 && a.win_len == 1920 && a.pre_mode == PRE_NONE) {
+    // S3Gen 24 kHz mel (S3GenMel.swift:43-102): magnitude spectrum, ln, (M, T') -- compile-time post-processing keeps the store code short
+    if (spec == SK_MAG && a.bank.steps != nullptr && a.log_mode == LOG_LN && !a.whisper_norm && !a.post_affine && a.out_mode == OUT_MT)
+      return launch_plan<Plan1920, PRE_NONE, SK_MAG, 0, POST_LN, OUT_MT>(a, st, launches, err);
     if (spec == SK_POWER) return launch_plan<Plan1920, PRE_NONE, SK_POWER>(a, st, launches, err);
     if (spec == SK_MAG) return launch_plan<Plan1920, PRE_NONE, SK_MAG>(a, st, launches, err);
     return launch_plan<Plan1920, PRE_NONE, SK_CPLX>(a, st, launches, err);
