@@ -232,6 +232,16 @@ B2A_API int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int
 B2A_API int b2a_resample_linear(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out,
                                 int space);
 
+/* S3Tokenizer long-audio windows: the segment plan of quantize / quantizeMixedBatch
+ * (Codec/S3Tokenizer/S3Tokenizer.swift:474-571; window 3000 frames, stride 2600) -- host only; pass null outputs to count -- and the
+ * gather of the unified batch: out[s] = mel[batch_idx[s]][:, start[s] ..< start[s] + length[s]] zero-padded to `window` frames.
+ * mel (batch, n_mels, t_max) fp32, out (n_segments, n_mels, window) fp32; batch_idx / start / length: HOST int32[n_segments]. */
+B2A_API int64_t b2a_s3tokenizer_plan_segments(const int64_t* mel_len, int64_t batch, int64_t window, int64_t stride, int32_t* batch_idx,
+                                              int32_t* start, int32_t* length, int64_t cap);
+B2A_API int b2a_s3tokenizer_gather_segments(b2a_ctx* ctx, const float* mel, int64_t batch, int n_mels, int64_t t_max, int64_t n_segments,
+                                            const int32_t* batch_idx, const int32_t* start, const int32_t* length, int64_t window,
+                                            float* out, int space);
+
 /* Test hook (host only, no GPU): compiles a dense filterbank ((n_mels, n_bins), or (n_bins, n_mels) when
  * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */

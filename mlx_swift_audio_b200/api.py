@@ -488,6 +488,35 @@ def cosyVoice3Istft(magnitude, phase, nFft: int, hopLength: int, window, ctx: Co
     return _istft("b2a_cosyvoice3_istft", magnitude, phase, nFft, hopLength, window, ctx)
 
 
+def s3TokenizerSegments(mel, melLen, window: int = 3000, stride: int = 2600, ctx: Context | None = None):
+    """Unified segment batch of S3Tokenizer.quantize / quantizeMixedBatch (Codec/S3Tokenizer/S3Tokenizer.swift:474-571):
+    mel (B, M, Tmax), melLen (B,) -> (segments (S, M, window), lengths (S,) int32, [(batch index, segment index), ...])."""
+    a = _Arr(mel)
+    if len(a.shape) != 3:
+        raise B2AError(L.B2A_E_BAD_ARG, "mel must be (B, M, Tmax)")
+    b, m, t = a.shape
+    ml = np.ascontiguousarray(melLen, np.int64)
+    if ml.shape != (b,) or (ml > t).any():
+        raise B2AError(L.B2A_E_BAD_ARG, "melLen must hold one length <= Tmax per clip")
+    c = _ctx_for(a, ctx)
+    I64, I32 = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    n = int(c.lib.b2a_s3tokenizer_plan_segments(ml.ctypes.data_as(I64), b, window, stride, None, None, None, 0))
+    if n < 0:
+        raise B2AError(L.B2A_E_BAD_ARG, "bad segment plan arguments")
+    bi, st, ln = (np.empty(n, np.int32) for _ in range(3))
+    c.lib.b2a_s3tokenizer_plan_segments(ml.ctypes.data_as(I64), b, window, stride, bi.ctypes.data_as(I32), st.ctypes.data_as(I32),
+                                        ln.ctypes.data_as(I32), n)
+    out = a.empty((n, m, window))
+    c.check(c.lib.b2a_s3tokenizer_gather_segments(c.h, a.ptr, b, m, t, n, bi.ctypes.data_as(I32), st.ctypes.data_as(I32),
+                                                  ln.ctypes.data_as(I32), window, _ptr(out), a.space))
+    info, k, prev = [], 0, -1
+    for i in range(n):
+        k = k + 1 if bi[i] == prev else 0
+        prev = bi[i]
+        info.append((int(bi[i]), k))
+    return out, ln, info
+
+
 def resampleAudio(audio, fromRate: int, toRate: int, ctx: Context | None = None):
     """resampleAudio (TTS/CosyVoice2/CosyVoice2TTS.swift:733-744) = linearInterpolate1d
     (TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58) on (T,) or (B, T); bit-exact fp32."""

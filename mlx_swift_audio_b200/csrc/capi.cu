@@ -468,6 +468,54 @@ int b2a_pad_or_trim(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples
   return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(length), nullptr, 0, body);
 }
 
+int b2a_s3tokenizer_gather_segments(b2a_ctx* c, const float* mel, int64_t batch, int n_mels, int64_t t_max, int64_t n_segments,
+                                    const int32_t* batch_idx, const int32_t* start, const int32_t* length, int64_t window, float* out,
+                                    int space) {
+  int rc = check_common(c, mel, out, batch, t_max);
+  if (rc != B2A_OK) return rc;
+  if (!batch_idx || !start || !length || n_mels <= 0 || n_mels > 65535 || window <= 0 || window > 0x7fffffff || n_segments <= 0 ||
+      n_segments > 0x7fffffff)
+    return fail(c, B2A_E_BAD_ARG, "bad segment arguments");
+  std::vector<int> seg(3 * size_t(n_segments));
+  for (int64_t s = 0; s < n_segments; ++s) {
+    if (batch_idx[s] < 0 || batch_idx[s] >= batch || start[s] < 0 || length[s] < 0 || length[s] > window ||
+        int64_t(start[s]) + length[s] > t_max)
+      return fail(c, B2A_E_BAD_ARG, "segment outside the mel");
+    seg[3 * s] = batch_idx[s]; seg[3 * s + 1] = start[s]; seg[3 * s + 2] = length[s];
+  }
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  // segments index clips freely, so the batch is not streamed clip by clip: host buffers are copied whole
+  const size_t in_bytes = sizeof(float) * size_t(batch) * n_mels * size_t(t_max);
+  const size_t out_bytes = sizeof(float) * size_t(n_segments) * n_mels * size_t(window);
+  const float* d_in = mel;
+  float* d_out = out;
+  cudaError_t e;
+  if (space == B2A_HOST) {
+    if ((rc = ensure(c, c->in[0][0], in_bytes)) != B2A_OK) return rc;
+    if ((rc = ensure(c, c->out[0][0], out_bytes)) != B2A_OK) return rc;
+    if ((e = cudaMemcpyAsync(c->in[0][0].p, mel, in_bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) return cu(c, e, "H2D copy");
+    d_in = static_cast<const float*>(c->in[0][0].p);
+    d_out = static_cast<float*>(c->out[0][0].p);
+  } else if (space != B2A_DEVICE) {
+    return fail(c, B2A_E_BAD_ARG, "space must be B2A_HOST or B2A_DEVICE");
+  }
+  if ((rc = ensure(c, c->scratch[0][0], sizeof(int) * seg.size())) != B2A_OK) return rc;
+  if ((e = cudaMemcpyAsync(c->scratch[0][0].p, seg.data(), sizeof(int) * seg.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+    return cu(c, e, "segment upload");
+  int launches = 0;
+  std::string err;
+  rc = launch_mel_windows(d_in, d_out, n_mels, t_max, static_cast<const int*>(c->scratch[0][0].p), int(n_segments), int(window), c->stream,
+                          &launches, &err);
+  c->launches += launches;
+  if (rc != B2A_OK) return fail(c, rc, err);
+  if (space == B2A_HOST) {
+    if ((e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return cu(c, e, "D2H copy");
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return cu(c, e, "sync");
+  }
+  return B2A_OK;
+}
+
 int b2a_resample_linear(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out, int space) {
   int rc = check_common(c, x, out, batch, n_samples);
   if (rc != B2A_OK) return rc;

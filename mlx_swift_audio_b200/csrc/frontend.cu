@@ -910,6 +910,36 @@ int launch_mel_segment_f16(const float* mel, void* out_f16, int64_t batch, int64
   return B2A_OK;
 }
 
+// S3Tokenizer long-audio windows (Codec/S3Tokenizer/S3Tokenizer.swift:499-571): segment s of the
+// unified batch = mel[batch_idx[s]][:, start[s] ..< start[s] + len[s]] zero-padded to `window` frames.  (M, T) rows are
+// contiguous along time: one warp-coalesced copy per row.  seg: per segment (batch index, start, length) as int32 triples.
+__global__ void __launch_bounds__(256) mel_windows_kernel(const float* __restrict__ mel, float* __restrict__ out, int n_mels, long long t_max,
+                                                          const int* __restrict__ seg, int window) {
+  const int s = blockIdx.z, m = blockIdx.y;
+  const int b = seg[3 * s], start = seg[3 * s + 1], len = seg[3 * s + 2];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= window) return;
+  const float* __restrict__ src = mel + ((long long)b * n_mels + m) * t_max + start;
+  out[((long long)s * n_mels + m) * window + t] = t < len ? __ldg(src + t) : 0.0f;
+}
+
+int launch_mel_windows(const float* mel, float* out, int n_mels, int64_t t_max, const int* d_seg, int n_segments, int window, void* stream,
+                       int* launches, std::string* err) {
+  for (int s0 = 0; s0 < n_segments; s0 += 65535) {   // gridDim.z limit
+    const int ns = std::min(65535, n_segments - s0);
+    dim3 grid(unsigned((window + 255) / 256), unsigned(n_mels), unsigned(ns));
+    mel_windows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mel, out + (long long)s0 * n_mels * window, n_mels, t_max,
+                                                                            d_seg + 3 * s0, window);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("mel_windows_kernel launch: ") + cudaGetErrorString(e);
+      return B2A_E_CUDA;
+    }
+    *launches += 1;
+  }
+  return B2A_OK;
+}
+
 // resampleAudio / linearInterpolate1d (TTS/CosyVoice2/CosyVoice2TTS.swift:733-744,
 // TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58): PyTorch-style align_corners=False linear interpolation, every
 // step in fp32 in the reference's op order (the source index is computed in fp32, so the order matters for bit-exactness;

@@ -420,6 +420,36 @@ void b2a_voice_enc_config_default(b2a_voice_enc_config* c) {  // Config/Chatterb
   c->stft_magnitude_min = 1e-4f;
 }
 
+// S3Tokenizer.quantize / quantizeMixedBatch segment plan (Codec/S3Tokenizer/S3Tokenizer.swift:474-571): a clip of at most `window`
+// frames is one segment of its own length; a longer clip is cut into windows of `window` frames at stride `stride` (start = 0,
+// stride, ... while start < length; the last ones are shorter).  Writes (batch index, start, length) per segment when the output
+// pointers are non-null (capacity `cap` segments) and returns the number of segments (or -1 on bad arguments / overflow).
+int64_t b2a_s3tokenizer_plan_segments(const int64_t* mel_len, int64_t batch, int64_t window, int64_t stride, int32_t* batch_idx,
+                                      int32_t* start, int32_t* length, int64_t cap) {
+  if (!mel_len || batch < 0 || window <= 0 || stride <= 0) return -1;
+  int64_t n = 0;
+  for (int64_t b = 0; b < batch; ++b) {
+    const int64_t len = mel_len[b];
+    if (len < 0 || len >= (int64_t(1) << 31)) return -1;
+    if (len <= window) {   // "short audio": one segment (also for length 0: an all-zero window)
+      if (batch_idx) {
+        if (n >= cap) return -1;
+        batch_idx[n] = int32_t(b); start[n] = 0; length[n] = int32_t(len);
+      }
+      ++n;
+      continue;
+    }
+    for (int64_t st = 0; st < len; st += stride) {
+      if (batch_idx) {
+        if (n >= cap) return -1;
+        batch_idx[n] = int32_t(b); start[n] = int32_t(st); length[n] = int32_t(std::min(window, len - st));
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
 int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int to_rate) {  // CosyVoice2TTS.swift:733-739, CosyHiFTGenerator.swift:26-31
   if (n_samples <= 0 || from_rate <= 0 || to_rate <= 0) return 0;
   if (from_rate == to_rate) return n_samples;

@@ -113,6 +113,8 @@ int launch_lfr(const float* in, float* out, int64_t batch, int64_t n_frames, int
                void* stream, int* launches, std::string* err);
 int launch_mel_segment_f16(const float* mel, void* out_f16, int64_t batch, int64_t n_frames, int n_mels, const long long* d_seek_content,
                            int length, void* stream, int* launches, std::string* err);
+int launch_mel_windows(const float* mel, float* out, int n_mels, int64_t t_max, const int* d_seg, int n_segments, int window, void* stream,
+                       int* launches, std::string* err);
 int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T, int64_t new_t, float step, float hi_clip, void* stream,
                            int* launches, std::string* err);
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,

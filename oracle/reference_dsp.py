@@ -704,3 +704,30 @@ def resample_audio(audio, from_rate: int, to_rate: int) -> np.ndarray:
     if from_rate == to_rate:
         return np.asarray(audio, F32)
     return linear_interpolate_1d(audio, F32(to_rate) / F32(from_rate))
+
+
+
+def s3tokenizer_segments(mel, mel_len, window: int = 3000, stride: int = 2600):
+    """Segment plan + unified batch of S3Tokenizer.quantize / quantizeMixedBatch, Codec/S3Tokenizer/S3Tokenizer.swift:474-571.
+    mel (B, M, Tmax), mel_len (B,) -> (segments (S, M, window) fp32, lengths (S,), info [(batch_idx, segment_idx), ...]).
+    (The all-short path stacks mel as it is; this is the mixed-batch path, whose short clips are padded to the window.)"""
+    mel = np.asarray(mel, F32)
+    segs, lens, info = [], [], []
+    for b in range(mel.shape[0]):
+        n = int(mel_len[b])
+        if n <= window:
+            seg = mel[b][:, :n]
+            segs.append(np.pad(seg, ((0, 0), (0, window - n))))
+            lens.append(n)
+            info.append((b, 0))
+        else:
+            start, k = 0, 0
+            while start < n:
+                end = min(start + window, n)
+                seg = mel[b][:, start:end]
+                segs.append(np.pad(seg, ((0, 0), (0, window - seg.shape[1]))))
+                lens.append(seg.shape[1])
+                info.append((b, k))
+                k += 1
+                start += stride
+    return np.stack(segs).astype(F32), np.asarray(lens, np.int32), info

@@ -231,6 +231,20 @@ def test_resample_audio_bit_exact(api, ctx, rates):
     assert np.array_equal(one, R.resample_audio(x[0, :5], rates[0], rates[1]))
 
 
+def test_s3tokenizer_segments(api, ctx):
+    rng = np.random.default_rng(51)
+    mel = rng.standard_normal((4, 8, 700)).astype(np.float32)
+    lens = np.array([700, 120, 300, 301])               # window 300, stride 260: 3 windows, 1 short, exactly one window, 2 windows
+    got, got_len, got_info = api.s3TokenizerSegments(mel, lens, window=300, stride=260, ctx=ctx)
+    want, want_len, want_info = R.s3tokenizer_segments(mel, lens, window=300, stride=260)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(got_len, want_len) and got_info == want_info
+    import torch
+    got_d, _, _ = api.s3TokenizerSegments(torch.from_numpy(mel).cuda(), lens, window=300, stride=260)
+    torch.cuda.synchronize()
+    assert np.array_equal(got_d.cpu().numpy(), want)
+
+
 def test_whisper_mel_segment_f16(api, ctx):
     # transcribe(): mel of the audio + 30 s of padding, content frames = len(audio) // 160, windows at arbitrary seeks
     x = synth.pcm(2, 16000 * 7 + 123, seed=31)

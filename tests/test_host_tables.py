@@ -121,3 +121,21 @@ def test_bad_arguments_are_rejected_without_a_gpu(built_lib):
     assert L.b2a_window(0, 0, out.ctypes.data_as(P)) != 0
     assert L.b2a_reflect_pad_index(100, 5, 8) == -1
     assert L.b2a_whisper_log_mel_spectrogram(None, None, 1, 16000, 80, 0, None, 0) != 0  # null context
+
+
+
+def test_s3tokenizer_segment_plan_matches_the_oracle(built_lib):
+    import ctypes as C
+    from oracle import reference_dsp as R
+    lens = np.array([7000, 3000, 3001, 1, 0, 5200, 5201], np.int64)
+    I64, I32 = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    n = built_lib.b2a_s3tokenizer_plan_segments(lens.ctypes.data_as(I64), len(lens), 3000, 2600, None, None, None, 0)
+    bi, st, ln = (np.empty(n, np.int32) for _ in range(3))
+    assert built_lib.b2a_s3tokenizer_plan_segments(lens.ctypes.data_as(I64), len(lens), 3000, 2600, bi.ctypes.data_as(I32),
+                                                   st.ctypes.data_as(I32), ln.ctypes.data_as(I32), n) == n
+    mel = np.zeros((len(lens), 1, 7000), np.float32)
+    _, want_len, info = R.s3tokenizer_segments(mel, lens)
+    assert n == len(info) and np.array_equal(ln, want_len) and [b for b, _ in info] == bi.tolist()
+    assert st.tolist() == [0, 2600, 5200, 0, 0, 2600, 0, 0, 0, 2600, 0, 2600, 5200]
+    assert built_lib.b2a_s3tokenizer_plan_segments(lens.ctypes.data_as(I64), len(lens), 3000, 2600, bi.ctypes.data_as(I32),
+                                                   st.ctypes.data_as(I32), ln.ctypes.data_as(I32), n - 1) == -1
