@@ -246,6 +246,8 @@ B2A_API int b2a_s3tokenizer_gather_segments(b2a_ctx* ctx, const float* mel, int6
  * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */
 B2A_API int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out);
+/* Test hook (host only): shared-memory layout of the FFT plan of n_fft (spectrum rows and mel staging words in the exchange buffer). */
+B2A_API int b2a_debug_plan_layout(int n_fft, int n_mels, int* slots_out, int* words_out);
 /* Build hook (host only): raw mel step program for a CTA shape (see tools/gen_mel_baked.py). */
 B2A_API int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins, int bin_major, int n_fft,
                                        unsigned* steps_out, int cap_steps, int* chunk_m, int* chunk_s, int* n_chunks_out,

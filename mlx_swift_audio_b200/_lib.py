@@ -81,6 +81,7 @@ SIGNATURES = {
     "b2a_hift_head_istft": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, _f, C.c_float, C.c_void_p, C.c_int]),
     "b2a_kokoro_head_istft": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_debug_mel_program_apply": (C.c_int, [_f, C.c_int, C.c_int, C.c_int, _f, _f]),
+    "b2a_debug_plan_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2a_debug_mel_program_dump": (C.c_int, [_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), C.c_int,
                                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2a_ctx_enable_timing": (C.c_int, [_ctx, C.c_int]),

@@ -817,7 +817,18 @@ __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ 
     return;
   }
   float s = 0.0f;
-  if (ok) for (long long r = ry; r < rows; r += 8) s += src[r * dim + col];
+  // (eight independent loads per thread in flight before the serial adds: the kernel is bound by memory latency)
+  if (ok) {
+    long long r = ry;
+    for (; r + 56 < rows; r += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(r + 8 * u) * dim + col];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; r < rows; r += 8) s += src[r * dim + col];
+  }
   s_red[ry][cx] = s;
   __syncthreads();
   float mean = 0.0f;
@@ -828,7 +839,17 @@ __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ 
   float denom = 1.0f;
   if (do_var) {
     float q = 0.0f;
-    if (ok) for (long long r = ry; r < rows; r += 8) { const float d = src[r * dim + col] - mean; q = fmaf(d, d, q); }
+    if (ok) {
+      long long r = ry;
+      for (; r + 56 < rows; r += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[(r + 8 * u) * dim + col];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const float d = v[u] - mean; q = fmaf(d, d, q); }
+      }
+      for (; r < rows; r += 8) { const float d = src[r * dim + col] - mean; q = fmaf(d, d, q); }
+    }
     s_red[ry][cx] = q;
     __syncthreads();
     float var = 0.0f;
@@ -838,8 +859,15 @@ __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ 
     denom = sqrtf(var) + 1e-6f;
   }
   if (ok) {
-    if (do_var) for (long long r = ry; r < rows; r += 8) dst[r * dim + col] = (src[r * dim + col] - mean) / denom;
-    else for (long long r = ry; r < rows; r += 8) dst[r * dim + col] = src[r * dim + col] - mean;
+    long long r = ry;
+    for (; r + 56 < rows; r += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(r + 8 * u) * dim + col];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[(r + 8 * u) * dim + col] = do_var ? (v[u] - mean) / denom : v[u] - mean;
+    }
+    for (; r < rows; r += 8) dst[r * dim + col] = do_var ? (src[r * dim + col] - mean) / denom : src[r * dim + col] - mean;
   }
 }
 

@@ -497,6 +497,21 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
   return int(sb.steps.size() / 4);
 }
 
+// Test hook (host only): the shared-memory layout of the FFT plan of `n_fft` -- row of the exchange buffer that holds each spectrum
+// bin after stage B (slots_out, n_fft/2+1 entries, in rows of frame_tile floats) and the word offset at which each of `n_mels`
+// mel sums is staged (words_out).  Returns frame_tile * 65536 + n1 * 256 + n2 / 1 packed as (frame_tile << 16) | (n1 << 8) | n2,
+// or -1 if there is no plan / n_mels does not fit.
+int b2a_debug_plan_layout(int n_fft, int n_mels, int* slots_out, int* words_out) {
+  const b2a::PlanShape* ps = b2a::plan_shape(n_fft);
+  if (!ps) return -1;
+  std::vector<int> slots, words;
+  b2a::spectrum_slots(*ps, slots);
+  if (!b2a::output_words(*ps, n_mels, words)) return -1;
+  for (size_t k = 0; k < slots.size(); ++k) slots_out[k] = slots[k];
+  for (int m = 0; m < n_mels; ++m) words_out[m] = words[m] / int(sizeof(float));
+  return (ps->frame_tile << 16) | (ps->n1 << 8) | ps->n2;
+}
+
 // Build hook (host only): the mel step program of `bank` for the FFT plan of `n_fft`, as raw 32-bit words (4 per step) plus the
 // per-chunk filter / step boundaries.  tools/gen_mel_baked.py turns the programs of the reference's standard banks into
 // straight-line device code at build time; at run time the program built for the caller's bank is compared with the baked

@@ -40,6 +40,19 @@ def test_whisper_log_mel(api, ctx, n_mels, n):
     assert_feat_close(got, want, what="whisper")
 
 
+def test_random_lengths_frontends(api, ctx):
+    # seeded random clip lengths around the tile (32 frames = 5120 samples) and row (160 samples) boundaries of the kernel
+    rng = np.random.default_rng(77)
+    lengths = sorted(set(int(v) for v in rng.integers(401, 40000, 10)) | {5120, 5119, 5121, 10240 + 200, 160 * 33})
+    for n in lengths:
+        x = synth.pcm(2, n, seed=n)
+        assert_feat_close(api.whisperLogMelSpectrogram(x, nMels=80, ctx=ctx), np.stack([R.whisper_log_mel_spectrogram(c, 80) for c in x]),
+                          what=f"whisper n={n}")
+        assert_feat_close(api.kaldiFbankCAMPPlus(x, ctx=ctx), np.stack([R.kaldi_fbank_camp_plus(c) for c in x]), what=f"kaldi n={n}")
+        assert_feat_close(api.funASRLogMelSpectrogram(x, ctx=ctx), np.stack([R.funasr_log_mel_spectrogram(c) for c in x]),
+                          what=f"funasr n={n}")
+
+
 def test_whisper_padding_and_single_clip(api, ctx):
     x = synth.pcm(1, 20000, seed=7)[0]
     got = api.whisperLogMelSpectrogram(x, nMels=80, padding=4000, ctx=ctx)

@@ -139,3 +139,37 @@ def test_s3tokenizer_segment_plan_matches_the_oracle(built_lib):
     assert st.tolist() == [0, 2600, 5200, 0, 0, 2600, 0, 0, 0, 2600, 0, 2600, 5200]
     assert built_lib.b2a_s3tokenizer_plan_segments(lens.ctypes.data_as(I64), len(lens), 3000, 2600, bi.ctypes.data_as(I32),
                                                    st.ctypes.data_as(I32), ln.ctypes.data_as(I32), n - 1) == -1
+
+
+@pytest.mark.parametrize("n_fft,n_mels", [(400, 128), (400, 80), (400, 40), (512, 80), (1920, 80)])
+def test_exchange_buffer_layout_is_consistent(built_lib, n_fft, n_mels):
+    """The frontend kernel uses the exchange buffer three times per tile.  Invariants of the layout: every spectrum bin has its
+    own row inside the block of the stage-B item that produces it; the mel sums are staged in words that belong to no spectrum
+    row and to no other filter, inside the buffer; writes by frame and reads by filter are bank-conflict free."""
+    import ctypes as C
+    nb = n_fft // 2 + 1
+    slots = (C.c_int * nb)()
+    words = (C.c_int * n_mels)()
+    packed = built_lib.b2a_debug_plan_layout(n_fft, n_mels, slots, words)
+    assert packed > 0
+    ft, n1, n2 = packed >> 16, (packed >> 8) & 0xff, packed & 0xff
+    assert n1 * n2 == n_fft
+    slots, words = np.array(slots[:]), np.array(words[:])
+    assert len(set(slots.tolist())) == nb and slots.min() >= 0 and slots.max() < n_fft
+    for k in range(nb):
+        item = k % n1 if k % n1 < n1 // 2 else n1 - k % n1          # the item that holds residue k mod n1 (mirrored above n1/2)
+        if k % n1 in (0, n1 // 2):
+            item = 0                                                    # k1 = 0 and k1 = n1/2 share item 0
+        assert slots[k] // (2 * n2) == item
+    spectrum_words = set()
+    for r in slots:
+        spectrum_words.update(range(r * ft, (r + 1) * ft))
+    staged = set()
+    for m in range(n_mels):
+        w = set(range(words[m], words[m] + ft))
+        assert not (w & spectrum_words) and not (w & staged) and words[m] >= 0 and words[m] + ft <= n_fft * ft
+        staged |= w
+    if ft == 32:
+        for f in (0, 5, 31):   # 32 consecutive filters read at one frame index fall in 32 different banks
+            for m0 in range(0, n_mels - 31, 32):
+                assert len({(words[m] + f) % 32 for m in range(m0, m0 + 32)}) == 32
