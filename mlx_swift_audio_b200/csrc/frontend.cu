@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
 
-  // ---- 0. per-CTA tables (once): window in item-major order, twiddles, mel step program -------------
+  // ---- 0. per-CTA tables (once): window in item-major order, twiddles (the loop-top barrier publishes them) ----
   for (int i = tid; i < N; i += P::NTHREADS) {
     const int n2 = i / N1, n1 = i - n2 * N1;
     const int o = N2 * n1 + n2;
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       ++nclip;
     }
 
-    // ---- 1. this tile's PCM has landed; prefetch the next tile into the other buffer ------------------
+    // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
     cp_async_commit_wait_all();
     __syncthreads();
 
