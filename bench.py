@@ -387,6 +387,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override clips per GPU (debug)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="none", choices=["none", "fused", "nccl"],
+                    help="N > 1 only: also time the step WITH the features delivered to rank 0 -- 'fused' = the kernels store "
+                         "straight into rank 0's HBM through peer-mapped memory (shard.FusedGather), 'nccl' = kernel then dist.gather")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -459,6 +462,43 @@ def main():
         except Exception:
             pass
 
+    # ---- optional: the same step with the features delivered to a consumer rank ("with and without the gather") ----
+    gather = None
+    if world > 1 and args.gather != "none":
+        from mlx_swift_audio_b200.shard import FusedGather, gather_features
+        per_clip = tuple(wl.out.shape[1:])
+        if args.gather == "fused":
+            if wl.out.dtype != torch.float32:
+                raise SystemExit("--gather fused: float32 outputs only")
+            fg = FusedGather(wl.ctx, wl.batch * world, per_clip, dst=0)
+            peer_out = C.c_void_p(fg.local_out().data_ptr())
+
+            def gstep():
+                rc = wl.call(wl.ctx, [C.c_void_p(t.data_ptr()) for t in wl.inputs], peer_out, wl.DEV)
+                if rc != 0:
+                    raise RuntimeError("b200audio call failed: " + wl.lib.b2a_last_error(wl.ctx.h).decode())
+        else:
+            def gstep():
+                wl.step_device()
+                gather_features(wl.out, wl.batch * world, dst=0)
+        for _ in range(2):
+            gstep()
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            gstep()
+        g1.record()
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1) / args.steps)
+        gather = {"mode": args.gather, "value": wl.audio_s * world / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms,
+                  "bytes_to_consumer_per_step": wl.out_bytes * (world - 1),
+                  "consumer_ingress_GBps": wl.out_bytes * (world - 1) / (gms * 1e-3) / 1e9,
+                  "note": "all ranks' features land in rank 0's HBM; bounded by rank 0's NVLink ingress, not by the kernels"}
+        if args.gather == "fused":
+            fg.close()
+
     # ---- end-to-end through the C ABI with pinned host buffers ---------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -486,6 +526,8 @@ def main():
                            if wl.algo_bytes > 4 * 126e6 else "working set fits L2: numbers are L2-warm",
                            "parallelism": f"dp{world} (clips sharded by rank, no collective)"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if gather is not None:
+            line["gather"] = gather
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

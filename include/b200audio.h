@@ -80,6 +80,28 @@ B2A_API int b2a_host_alloc(void** ptr, uint64_t bytes);
 B2A_API int b2a_host_free(void* ptr);
 
 /* ---------------------------------------------------------------------------------------
+ * multi-GPU: fused gather over peer memory
+ *
+ * One process per GPU.  The consumer rank allocates the full (all clips) feature buffer with
+ * b2a_device_alloc and exports it; every producer rank opens the handle and passes
+ * `peer_base + first_clip * clip_bytes` as the `out` pointer (space = B2A_DEVICE) of any compute
+ * entry point: the kernels' own epilogue stores then travel over NVLink / NVSwitch into the
+ * consumer's HBM while the producer is still computing -- no separate copy, no NCCL call on the
+ * data path.  (The reference is single-device: MLX unified memory has no counterpart.)
+ * The caller orders "all producers done" (b2a_ctx_sync on each rank + a host barrier) before the
+ * consumer reads.  Handles are CUDA IPC handles (64 bytes) and are valid between processes of one
+ * box.
+ * ------------------------------------------------------------------------------------- */
+#define B2A_IPC_HANDLE_BYTES 64
+B2A_API int b2a_device_alloc(b2a_ctx* ctx, void** ptr, uint64_t bytes);   /* cudaMalloc on the context's device (IPC-exportable) */
+B2A_API int b2a_device_free(b2a_ctx* ctx, void* ptr);
+B2A_API int b2a_ipc_export(b2a_ctx* ctx, void* device_ptr, unsigned char handle[B2A_IPC_HANDLE_BYTES]);
+B2A_API int b2a_ipc_open(b2a_ctx* ctx, const unsigned char handle[B2A_IPC_HANDLE_BYTES], void** peer_ptr);
+B2A_API int b2a_ipc_close(b2a_ctx* ctx, void* peer_ptr);
+/* Plain copies on the context's stream (device buffers obtained above have no torch / MLX owner to copy them). */
+B2A_API int b2a_memcpy_d2h(b2a_ctx* ctx, void* host_dst, const void* device_src, uint64_t bytes);   /* synchronous */
+
+/* ---------------------------------------------------------------------------------------
  * host-side pure functions (no GPU needed): windows, filterbanks, index and shape rules
  * ------------------------------------------------------------------------------------- */
 B2A_API int b2a_window(int kind, int length, float* out);                       /* see enum b2a_window_kind */

@@ -14,6 +14,7 @@ B2A_OK, B2A_E_BAD_ARG, B2A_E_TOO_SHORT, B2A_E_CUDA, B2A_E_UNSUPPORTED, B2A_E_NOM
 B2A_HOST, B2A_DEVICE = 0, 1
 WIN_WHISPER_HANN, WIN_HANNING, WIN_HAMMING, WIN_POVEY, WIN_HANN_PERIODIC = range(5)
 
+IPC_HANDLE_BYTES = 64   # B2A_IPC_HANDLE_BYTES
 STATUS_NAMES = {0: "OK", 1: "BAD_ARG", 2: "TOO_SHORT", 3: "CUDA", 4: "UNSUPPORTED", 5: "NOMEM"}
 
 _f = C.POINTER(C.c_float)
@@ -38,6 +39,12 @@ SIGNATURES = {
     "b2a_ctx_launch_count": (_i64, [_ctx]),
     "b2a_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "b2a_host_free": (C.c_int, [C.c_void_p]),
+    "b2a_device_alloc": (C.c_int, [_ctx, C.POINTER(C.c_void_p), C.c_uint64]),
+    "b2a_device_free": (C.c_int, [_ctx, C.c_void_p]),
+    "b2a_ipc_export": (C.c_int, [_ctx, C.c_void_p, C.c_char_p]),
+    "b2a_ipc_open": (C.c_int, [_ctx, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b2a_ipc_close": (C.c_int, [_ctx, C.c_void_p]),
+    "b2a_memcpy_d2h": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_uint64]),
     "b2a_window": (C.c_int, [C.c_int, C.c_int, _f]),
     "b2a_mel_filters": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _f]),
     "b2a_funasr_mel_filters": (C.c_int, [C.c_int, C.c_int, C.c_int, _f]),

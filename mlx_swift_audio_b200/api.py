@@ -129,10 +129,39 @@ class _Arr:
         return np.empty(shape, np.float32)
 
 
+class DevicePtr:
+    """A raw device address used as ``out=`` of a front end: e.g. this rank's slice of a peer-mapped gather buffer
+    (shard.FusedGather), so that the kernel's own stores deliver the features to the consumer GPU."""
+
+    def __init__(self, address: int, shape=None):
+        self.address = int(address)
+        self.shape = None if shape is None else tuple(shape)
+
+    def data_ptr(self) -> int:
+        return self.address
+
+
 def _ptr(a):
-    if _is_torch(a):
+    if _is_torch(a) or isinstance(a, DevicePtr):
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(a.ctypes.data)
+
+
+def _out_for(a: "_Arr", shape, out):
+    """Result buffer: a fresh array of the input's kind, or the caller's ``out`` (device inputs only: a contiguous float32
+    torch CUDA tensor or a DevicePtr of the batched result shape)."""
+    if out is None:
+        return a.empty(shape)
+    if a.space != L.B2A_DEVICE:
+        raise B2AError(L.B2A_E_BAD_ARG, "out= needs device-resident input (torch CUDA tensor)")
+    if isinstance(out, DevicePtr):
+        if out.shape is not None and tuple(out.shape) != tuple(shape):
+            raise B2AError(L.B2A_E_BAD_ARG, f"out has shape {out.shape}, the result has shape {tuple(shape)}")
+        return out
+    import torch
+    if not (_is_torch(out) and out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == tuple(shape)):
+        raise B2AError(L.B2A_E_BAD_ARG, f"out must be a contiguous float32 CUDA tensor of shape {tuple(shape)}")
+    return out
 
 
 def _ctx_for(a: _Arr, ctx: Context | None) -> Context:
@@ -252,7 +281,7 @@ def padOrTrim(array, length: int = 480000, ctx: Context | None = None):
     return out if had else out[0]
 
 
-def whisperLogMelSpectrogram(audio, nMels: int, padding: int = 0, ctx: Context | None = None):
+def whisperLogMelSpectrogram(audio, nMels: int, padding: int = 0, ctx: Context | None = None, out=None):
     """STT/Whisper/WhisperAudio.swift:78-137 -> (T', nMels)"""
     a = _Arr(audio)
     b, n, had = _batched(a, 1)
@@ -260,12 +289,12 @@ def whisperLogMelSpectrogram(audio, nMels: int, padding: int = 0, ctx: Context |
     frames = int(c.lib.b2a_whisper_num_frames(n, padding))
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
-    out = a.empty((b, frames, nMels))
+    out = _out_for(a, (b, frames, nMels), out)
     c.check(c.lib.b2a_whisper_log_mel_spectrogram(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space))
-    return out if had else out[0]
+    return out if had or isinstance(out, DevicePtr) else out[0]
 
 
-def logMelSpectrogramChatterbox(audio, nMels: int = 128, padding: int = 0, ctx: Context | None = None):
+def logMelSpectrogramChatterbox(audio, nMels: int = 128, padding: int = 0, ctx: Context | None = None, out=None):
     """Codec/S3Tokenizer/S3TokenizerUtils.swift:160-208 -> (nMels, T')"""
     a = _Arr(audio)
     b, n, had = _batched(a, 1)
@@ -273,9 +302,9 @@ def logMelSpectrogramChatterbox(audio, nMels: int = 128, padding: int = 0, ctx: 
     frames = int(c.lib.b2a_whisper_num_frames(n, padding))
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
-    out = a.empty((b, nMels, frames))
+    out = _out_for(a, (b, nMels, frames), out)
     c.check(c.lib.b2a_log_mel_spectrogram_chatterbox(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space))
-    return out if had else out[0]
+    return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def logMelSpectrogramCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 128, ctx: Context | None = None):
@@ -283,7 +312,7 @@ def logMelSpectrogramCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 
     return logMelSpectrogramChatterbox(audio, nMels=numMelBins, padding=0, ctx=ctx)
 
 
-def funASRLogMelSpectrogram(audio, nMels: int = 80, nFft: int = 400, hopLength: int = 160, ctx: Context | None = None):
+def funASRLogMelSpectrogram(audio, nMels: int = 80, nFft: int = 400, hopLength: int = 160, ctx: Context | None = None, out=None):
     """STT/FunASR/FunASRAudio.swift:57-94 -> (T', nMels)"""
     if (nFft, hopLength) != (400, 160):
         _raise(L.B2A_E_UNSUPPORTED, "Fun-ASR log-mel is built for nFft 400 / hopLength 160")
@@ -293,9 +322,9 @@ def funASRLogMelSpectrogram(audio, nMels: int = 80, nFft: int = 400, hopLength: 
     frames = int(c.lib.b2a_funasr_num_frames(n))
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
-    out = a.empty((b, frames, nMels))
+    out = _out_for(a, (b, frames, nMels), out)
     c.check(c.lib.b2a_funasr_log_mel_spectrogram(c.h, a.ptr, b, n, nMels, _ptr(out), a.space))
-    return out if had else out[0]
+    return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def applyLFR(features, lfrM: int = 7, lfrN: int = 6, ctx: Context | None = None):
@@ -347,7 +376,7 @@ def applyCMVN(features, cmvnMean=None, cmvnIstd=None, ctx: Context | None = None
 
 
 def preprocessAudio(audio, nMels: int = 80, lfrM: int = 7, lfrN: int = 6, applyNormalization: bool = True,
-                    ctx: Context | None = None):
+                    ctx: Context | None = None, out=None):
     """STT/FunASR/FunASRAudio.swift:197-216 -> (ceil(T'/lfrN), nMels*lfrM)"""
     a = _Arr(audio)
     b, n, had = _batched(a, 1)
@@ -356,13 +385,13 @@ def preprocessAudio(audio, nMels: int = 80, lfrM: int = 7, lfrN: int = 6, applyN
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
     rows = int(c.lib.b2a_lfr_num_rows(frames, lfrN))
-    out = a.empty((b, rows, nMels * lfrM))
+    out = _out_for(a, (b, rows, nMels * lfrM), out)
     c.check(c.lib.b2a_funasr_preprocess_audio(c.h, a.ptr, b, n, nMels, lfrM, lfrN, int(applyNormalization), _ptr(out), a.space))
-    return out if had else out[0]
+    return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def kaldiFbankCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 80, frameLength: float = 25.0,
-                       frameShift: float = 10.0, meanNorm: bool = False, ctx: Context | None = None):
+                       frameShift: float = 10.0, meanNorm: bool = False, ctx: Context | None = None, out=None):
     """Codec/S3Gen/CAMPPlus.swift:32-106 -> (T', numMelBins).  ``meanNorm`` adds the caller-side
     ``fbank - mean(fbank, axis: 0)`` of CAMPPlus.inference (:797-802)."""
     a = _Arr(audio)
@@ -373,15 +402,15 @@ def kaldiFbankCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 80, fra
     frames = int(c.lib.b2a_kaldi_num_frames(n, win, hop))
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "signal shorter than one analysis window")
-    out = a.empty((b, frames, numMelBins))
+    out = _out_for(a, (b, frames, numMelBins), out)
     c.check(c.lib.b2a_kaldi_fbank_campplus(c.h, a.ptr, b, n, sampleRate, numMelBins, frameLength, frameShift, int(meanNorm),
                                            _ptr(out), a.space))
-    return out if had else out[0]
+    return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def s3genMelSpectrogram(y, nFft: int = 1920, numMels: int = 80, samplingRate: int = 24000, hopSize: int = 480,
                         winSize: int = 1920, fmin: int = 0, fmax: int = 8000, center: bool = False,
-                        ctx: Context | None = None):
+                        ctx: Context | None = None, out=None):
     """Codec/S3Gen/Mel/S3GenMel.swift:43-102 : (B, T) or (T,) -> (B, numMels, T') or (numMels, T')"""
     a = _Arr(y)
     b, n, had = _batched(a, 1)
@@ -389,10 +418,10 @@ def s3genMelSpectrogram(y, nFft: int = 1920, numMels: int = 80, samplingRate: in
     frames = int(c.lib.b2a_s3gen_num_frames(n, nFft, hopSize))
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
-    out = a.empty((b, numMels, frames))
+    out = _out_for(a, (b, numMels, frames), out)
     c.check(c.lib.b2a_s3gen_mel_spectrogram(c.h, a.ptr, b, n, nFft, numMels, samplingRate, hopSize, winSize, fmin, fmax,
                                             _ptr(out), a.space))
-    return out if had else out[0]
+    return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def voiceEncoderMelspectrogram(wav, config: L.VoiceEncConfig | None = None, pad: bool = True, ctx: Context | None = None):

@@ -435,6 +435,67 @@ int b2a_host_alloc(void** ptr, uint64_t bytes) {
 }
 int b2a_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? B2A_OK : B2A_E_CUDA; }
 
+// ---- multi-GPU: peer-mapped output buffers (the kernels' epilogue stores are the gather) ----------
+namespace {
+struct DeviceGuard {   // the calling thread's current device is restored on scope exit
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+}  // namespace
+
+int b2a_device_alloc(b2a_ctx* c, void** ptr, uint64_t bytes) {
+  if (!c || !ptr || bytes == 0) return fail(c, B2A_E_BAD_ARG, "b2a_device_alloc: bad argument");
+  DeviceGuard g(c->device);
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    return fail(c, e == cudaErrorMemoryAllocation ? B2A_E_NOMEM : B2A_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  return B2A_OK;
+}
+
+int b2a_device_free(b2a_ctx* c, void* ptr) {
+  if (!c) return B2A_E_BAD_ARG;
+  DeviceGuard g(c->device);
+  return cu(c, cudaFree(ptr), "cudaFree");
+}
+
+int b2a_ipc_export(b2a_ctx* c, void* device_ptr, unsigned char handle[B2A_IPC_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == B2A_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  if (!c || !device_ptr || !handle) return fail(c, B2A_E_BAD_ARG, "b2a_ipc_export: bad argument");
+  DeviceGuard g(c->device);
+  cudaIpcMemHandle_t h;
+  int rc = cu(c, cudaIpcGetMemHandle(&h, device_ptr), "cudaIpcGetMemHandle");
+  if (rc == B2A_OK) std::memcpy(handle, &h, sizeof(h));
+  return rc;
+}
+
+int b2a_ipc_open(b2a_ctx* c, const unsigned char handle[B2A_IPC_HANDLE_BYTES], void** peer_ptr) {
+  if (!c || !handle || !peer_ptr) return fail(c, B2A_E_BAD_ARG, "b2a_ipc_open: bad argument");
+  DeviceGuard g(c->device);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  // (peer access between the two devices is enabled by the runtime as part of the open)
+  return cu(c, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int b2a_ipc_close(b2a_ctx* c, void* peer_ptr) {
+  if (!c || !peer_ptr) return fail(c, B2A_E_BAD_ARG, "b2a_ipc_close: bad argument");
+  DeviceGuard g(c->device);
+  return cu(c, cudaIpcCloseMemHandle(peer_ptr), "cudaIpcCloseMemHandle");
+}
+
+int b2a_memcpy_d2h(b2a_ctx* c, void* host_dst, const void* device_src, uint64_t bytes) {
+  if (!c || !host_dst || !device_src) return fail(c, B2A_E_BAD_ARG, "b2a_memcpy_d2h: bad argument");
+  DeviceGuard g(c->device);
+  int rc = cu(c, cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, c->stream), "cudaMemcpyAsync");
+  return rc != B2A_OK ? rc : cu(c, cudaStreamSynchronize(c->stream), "sync");
+}
+
 int b2a_ctx_enable_timing(b2a_ctx* c, int on) {
   if (!c) return B2A_E_BAD_ARG;
   c->timing = on != 0;

@@ -37,3 +37,81 @@ def gather_features(local, n_clips: int, dst: int = 0, group=None):
     if rank != dst:
         return None
     return torch.cat([bufs[r][: sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+
+
+class FusedGather:
+    """Gather fused into the producing kernels: rank ``dst`` owns ONE (n_clips, *per_clip_shape)
+    float32 buffer, every rank maps it (CUDA IPC over NVLink 5 / NVSwitch peer memory) and passes its own slice as ``out=`` of
+    the front end, so the kernel's epilogue stores ARE the transfer -- they overlap the FFT work tile by tile, there is no
+    staging copy and no NCCL call on the data path.  torch.distributed only carries the 64-byte handle and the final barrier.
+
+        fg = FusedGather(ctx, n_clips, (3000, 128))
+        api.whisperLogMelSpectrogram(x_local, 128, ctx=ctx, out=fg.local_out())     # x_local: this rank's shard_range() clips
+        full = fg.finish()          # rank dst: torch view of all clips' features; None elsewhere
+
+    The buffer is reused by later calls; ``close()`` unmaps / frees it (collective: every rank calls it)."""
+
+    def __init__(self, ctx, n_clips: int, per_clip_shape, dst: int = 0, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib as L
+        self.ctx, self.group, self.dst = ctx, group, dst
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_clips = int(n_clips)
+        self.per_clip_shape = tuple(int(d) for d in per_clip_shape)
+        self.clip_elems = 1
+        for d in self.per_clip_shape:
+            self.clip_elems *= d
+        self.start, self.stop = shard_range(self.n_clips, self.rank, self.world)
+        nbytes = max(1, self.n_clips * self.clip_elems * 4)
+        lib = ctx.lib
+        base = C.c_void_p()
+        handle = [None]
+        self._owner = self.rank == dst
+        if self._owner:
+            ctx.check(lib.b2a_device_alloc(ctx.h, C.byref(base), nbytes))
+            buf = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+            ctx.check(lib.b2a_ipc_export(ctx.h, base, buf))
+            handle[0] = buf.raw
+        dist.broadcast_object_list(handle, src=dst, group=group)
+        if not self._owner:
+            ctx.check(lib.b2a_ipc_open(ctx.h, handle[0], C.byref(base)))
+        self.base = int(base.value)
+        self.nbytes = nbytes
+
+    def local_out(self):
+        """This rank's slice of the consumer's buffer, usable as ``out=`` of the api front ends."""
+        from .api import DevicePtr
+        return DevicePtr(self.base + self.start * self.clip_elems * 4, (self.stop - self.start,) + self.per_clip_shape)
+
+    def finish(self):
+        """Orders every producer's stores before the consumer's reads: stream sync on each rank, then a barrier.
+        -> on ``dst`` a zero-copy torch view (n_clips, *per_clip_shape) of the gathered features, None elsewhere."""
+        import torch
+        import torch.distributed as dist
+        self.ctx.sync()
+        dist.barrier(group=self.group)
+        if not self._owner:
+            return None
+
+        class _View:   # __cuda_array_interface__ v2: torch wraps the allocation without copying
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.n_clips,) + self.per_clip_shape, "typestr": "<f4", "data": (self.base, False),
+                                      "version": 2, "strides": None}
+        self._keep = v
+        return torch.as_tensor(v, device=torch.device("cuda", self.ctx.device))
+
+    def close(self):
+        import ctypes as C
+        import torch.distributed as dist
+        if self.base:
+            self.ctx.sync()
+            dist.barrier(group=self.group)   # nobody still writes / reads through a mapping that is about to go away
+            if not self._owner:
+                self.ctx.check(self.ctx.lib.b2a_ipc_close(self.ctx.h, C.c_void_p(self.base)))
+            dist.barrier(group=self.group)
+            if self._owner:
+                self.ctx.check(self.ctx.lib.b2a_device_free(self.ctx.h, C.c_void_p(self.base)))
+            self.base = 0
