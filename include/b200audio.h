@@ -195,6 +195,29 @@ B2A_API void b2a_voice_enc_config_default(b2a_voice_enc_config* cfg);
 B2A_API int b2a_voice_encoder_melspectrogram(b2a_ctx* ctx, const float* wav, int64_t batch, int64_t n_samples,
                                              const b2a_voice_enc_config* cfg, float* out, int space);
 
+/* ---------------------------------------------------------------------------------------
+ * ragged batches: per-clip lengths ("optional per-clip lengths[B]")
+ *
+ * The reference helpers take one clip, so clips of different lengths are simply separate calls there.  These variants run
+ * a whole batch of unequal clips in ONE launch: clip b holds lengths[b] (host array, 1 <= lengths[b] <= n_samples) valid
+ * samples at the start of row b of the (batch, n_samples) input, and every clip is processed exactly as the single-clip
+ * reference call on audio[b, :lengths[b]] would process it (padding, frame count, per-clip max / CMVN / mean over ITS frames).
+ * Output strides are those of an n_samples-long clip -- (batch, frames(n_samples), n_mels) etc. -- rows past a clip's own
+ * count are zero; out_frames / out_rows (host, may be NULL) receive each clip's count.
+ * ------------------------------------------------------------------------------------- */
+B2A_API int b2a_whisper_log_mel_spectrogram_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                                   int n_mels, int64_t padding, float* out, int64_t* out_frames, int space);
+B2A_API int b2a_log_mel_spectrogram_chatterbox_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                                      int n_mels, int64_t padding, float* out, int64_t* out_frames, int space);
+B2A_API int b2a_funasr_preprocess_audio_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                               int n_mels, int lfr_m, int lfr_n, int apply_normalization, float* out, int64_t* out_rows, int space);
+B2A_API int b2a_kaldi_fbank_campplus_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                            int sample_rate, int num_mel_bins, float frame_length_ms, float frame_shift_ms, int mean_norm,
+                                            float* out, int64_t* out_frames, int space);
+B2A_API int b2a_s3gen_mel_spectrogram_ragged(b2a_ctx* ctx, const float* y, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_fft,
+                                             int num_mels, int sampling_rate, int hop_size, int win_size, int fmin, int fmax, float* out,
+                                             int64_t* out_frames, int space);
+
 /* stft                     Codec/S3Tokenizer/S3TokenizerUtils.swift:224-263 (== funASRSTFT FunASRAudio.swift:240-277).
  * window (win_len,) host pointer, zero-extended to n_fft; out (batch, T', n_fft/2+1) complex64 interleaved (re, im).
  * Built for n_fft in {400, 512, 1920} with hop {160, 160, 480}. */

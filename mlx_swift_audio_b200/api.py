@@ -424,6 +424,88 @@ def s3genMelSpectrogram(y, nFft: int = 1920, numMels: int = 80, samplingRate: in
     return out if had or isinstance(out, DevicePtr) else out[0]
 
 
+# ---- ragged batches: one launch for clips of different lengths (include/b200audio.h, "ragged batches") ------------
+
+def _ragged(audio, lengths, ctx):
+    a = _Arr(audio)
+    if len(a.shape) != 2:
+        raise B2AError(L.B2A_E_BAD_ARG, f"ragged batches take a (B, T_max) array, got shape {a.shape}")
+    ln = np.ascontiguousarray(lengths, dtype=np.int64)
+    if ln.shape != (a.shape[0],):
+        raise B2AError(L.B2A_E_BAD_ARG, "lengths must hold one entry per clip")
+    rows = np.zeros(a.shape[0], np.int64)
+    I64 = C.POINTER(C.c_int64)
+    return a, _ctx_for(a, ctx), ln, rows, ln.ctypes.data_as(I64), rows.ctypes.data_as(I64)
+
+
+def whisperLogMelSpectrogramRagged(audio, lengths, nMels: int, padding: int = 0, ctx: Context | None = None):
+    """whisperLogMelSpectrogram (WhisperAudio.swift:78-137) of every audio[b, :lengths[b]] in one launch
+    -> ((B, T'max, nMels) with rows past a clip's frame count zero, frames per clip)"""
+    a, c, ln, rows, lp, rp = _ragged(audio, lengths, ctx)
+    b, n = a.shape
+    frames = int(c.lib.b2a_whisper_num_frames(n, padding))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, frames, nMels))
+    c.check(c.lib.b2a_whisper_log_mel_spectrogram_ragged(c.h, a.ptr, b, n, lp, nMels, padding, _ptr(out), rp, a.space))
+    return out, rows
+
+
+def logMelSpectrogramChatterboxRagged(audio, lengths, nMels: int = 128, padding: int = 0, ctx: Context | None = None):
+    """logMelSpectrogramChatterbox (S3TokenizerUtils.swift:160-208) per clip -> ((B, nMels, T'max), frames per clip)"""
+    a, c, ln, rows, lp, rp = _ragged(audio, lengths, ctx)
+    b, n = a.shape
+    frames = int(c.lib.b2a_whisper_num_frames(n, padding))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, nMels, frames))
+    c.check(c.lib.b2a_log_mel_spectrogram_chatterbox_ragged(c.h, a.ptr, b, n, lp, nMels, padding, _ptr(out), rp, a.space))
+    return out, rows
+
+
+def preprocessAudioRagged(audio, lengths, nMels: int = 80, lfrM: int = 7, lfrN: int = 6, applyNormalization: bool = True,
+                          ctx: Context | None = None):
+    """preprocessAudio (FunASRAudio.swift:197-216) per clip -> ((B, rows_max, nMels*lfrM), LFR rows per clip)"""
+    a, c, ln, rows, lp, rp = _ragged(audio, lengths, ctx)
+    b, n = a.shape
+    frames = int(c.lib.b2a_funasr_num_frames(n))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, int(c.lib.b2a_lfr_num_rows(frames, lfrN)), nMels * lfrM))
+    c.check(c.lib.b2a_funasr_preprocess_audio_ragged(c.h, a.ptr, b, n, lp, nMels, lfrM, lfrN, int(applyNormalization), _ptr(out), rp, a.space))
+    return out, rows
+
+
+def kaldiFbankCAMPPlusRagged(audio, lengths, sampleRate: int = 16000, numMelBins: int = 80, frameLength: float = 25.0,
+                             frameShift: float = 10.0, meanNorm: bool = False, ctx: Context | None = None):
+    """kaldiFbankCAMPPlus (CAMPPlus.swift:32-106) per clip -> ((B, T'max, numMelBins), frames per clip)"""
+    a, c, ln, rows, lp, rp = _ragged(audio, lengths, ctx)
+    b, n = a.shape
+    win = int(np.float32(sampleRate) * np.float32(frameLength) / np.float32(1000))
+    hop = int(np.float32(sampleRate) * np.float32(frameShift) / np.float32(1000))
+    frames = int(c.lib.b2a_kaldi_num_frames(n, win, hop))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "signal shorter than one analysis window")
+    out = a.empty((b, frames, numMelBins))
+    c.check(c.lib.b2a_kaldi_fbank_campplus_ragged(c.h, a.ptr, b, n, lp, sampleRate, numMelBins, frameLength, frameShift, int(meanNorm),
+                                                  _ptr(out), rp, a.space))
+    return out, rows
+
+
+def s3genMelSpectrogramRagged(y, lengths, nFft: int = 1920, numMels: int = 80, samplingRate: int = 24000, hopSize: int = 480,
+                              winSize: int = 1920, fmin: int = 0, fmax: int = 8000, ctx: Context | None = None):
+    """s3genMelSpectrogram (S3GenMel.swift:43-102) per clip -> ((B, numMels, T'max), frames per clip)"""
+    a, c, ln, rows, lp, rp = _ragged(y, lengths, ctx)
+    b, n = a.shape
+    frames = int(c.lib.b2a_s3gen_num_frames(n, nFft, hopSize))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, numMels, frames))
+    c.check(c.lib.b2a_s3gen_mel_spectrogram_ragged(c.h, a.ptr, b, n, lp, nFft, numMels, samplingRate, hopSize, winSize, fmin, fmax,
+                                                   _ptr(out), rp, a.space))
+    return out, rows
+
+
 def voiceEncoderMelspectrogram(wav, config: L.VoiceEncConfig | None = None, pad: bool = True, ctx: Context | None = None):
     """TTS/Chatterbox/VoiceEncoder/VoiceEncoderMelspec.swift:17-68 -> (numMels, T')"""
     cfg = config

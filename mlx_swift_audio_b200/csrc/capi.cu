@@ -51,7 +51,8 @@ struct b2a_ctx {
   std::map<std::string, BankStorage> banks;      // like the reference's MelFilterCache (CAMPPlus.swift:111-131), per context
   std::map<std::string, std::vector<float>> windows;
   DevBuf in[kSlots][2], out[kSlots][2];          // host-pipeline staging
-  DevBuf scratch[kSlots][3];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase
+  DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3 / 4: ragged clip / tile tables
+  int64_t chunk_clip0 = 0;                       // first clip of the chunk run_batched is handing to the body
   int* h_flag = nullptr;                         // pinned
 };
 
@@ -181,6 +182,7 @@ int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t i
     const int64_t kMaxClipsPerLaunch = 32768;   // several kernels index clips with gridDim.y (limit 65535)
     for (int64_t c0 = 0; c0 < batch && rc == B2A_OK; c0 += kMaxClipsPerLaunch) {
       const int64_t n = std::min(kMaxClipsPerLaunch, batch - c0);
+      c->chunk_clip0 = c0;
       rc = body(in0 + c0 * in0_per_clip, in1 ? in1 + c0 * in1_per_clip : nullptr, out0 + c0 * out0_per_clip,
                 out1 ? out1 + c0 * out1_per_clip : nullptr, n, 0);
     }
@@ -223,6 +225,7 @@ int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t i
       return cu(c, e, "H2D copy");
     if ((e = cudaEventRecord(c->ev_h2d[s], c->s_h2d)) != cudaSuccess) return cu(c, e, "event record");
     if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
+    c->chunk_clip0 = c0;
     int rc = body(static_cast<const float*>(c->in[s][0].p), static_cast<const float*>(c->in[s][1].p),
                   static_cast<float*>(c->out[s][0].p), static_cast<float*>(c->out[s][1].p), n, s);
     if (rc != B2A_OK) {
@@ -274,7 +277,30 @@ struct Preset {
   int post_mean_norm = 0;  // CAM++ time-mean removal
 };
 
-int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, int64_t n_samples, float* out, int space) {
+// Per-clip lengths of a ragged batch (the *_ragged entry points): clip b holds lengths[b] <= n_samples valid samples at the
+// start of its row; `frames_of` is the front end's own frame-count rule.  Outputs keep the strides of an n_samples-long clip;
+// rows past a clip's own count are zero.
+struct Ragged {
+  const int64_t* lengths = nullptr;             // host
+  std::function<int64_t(int64_t)> frames_of;
+  int64_t* out_rows = nullptr;                  // host, optional: rows (frames / LFR rows) written per clip
+};
+
+int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, int64_t n_samples, float* out, int space,
+               const Ragged* rg = nullptr) {
+  std::vector<int64_t> clip_frames;
+  if (rg) {
+    if (p.out_mode == OUT_COMPLEX) return fail(c, B2A_E_UNSUPPORTED, "ragged batches are built for the mel front ends only");
+    clip_frames.resize(size_t(batch));
+    for (int64_t b = 0; b < batch; ++b) {
+      const int64_t len = rg->lengths[b];
+      if (len <= 0 || len > n_samples) return fail(c, B2A_E_BAD_ARG, "lengths[b] must lie in [1, n_samples]");
+      const int64_t fr = rg->frames_of(len);
+      if (fr <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
+      clip_frames[size_t(b)] = fr;
+      if (rg->out_rows) rg->out_rows[b] = p.out_mode == OUT_LFR ? b2a_lfr_num_rows(fr, p.lfr_n) : fr;
+    }
+  }
   size_t out_per_clip;
   switch (p.out_mode) {
     case OUT_LFR: out_per_clip = size_t(p.lfr_rows) * p.lfr_m * p.bank.n_mels; break;
@@ -291,6 +317,41 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
     a.spec_mode = p.spec_mode; a.bank = p.bank; a.log_mode = p.log_mode; a.log_floor = p.log_floor;
     a.whisper_norm = p.whisper_norm; a.post_affine = p.post_affine; a.post_sub = p.post_sub; a.post_div = p.post_div;
     a.out_mode = p.out_mode; a.n_frames = p.n_frames; a.out = d_out; a.lfr_m = p.lfr_m; a.lfr_n = p.lfr_n; a.lfr_rows = p.lfr_rows;
+    std::vector<int> clip_tab, tile_tab;   // (pageable-memory uploads below are staged before cudaMemcpyAsync returns)
+    if (rg) {
+      const PlanShape* ps = plan_shape(p.n_fft);
+      const int ft = ps ? ps->frame_tile : 32;
+      const int64_t c0 = c->chunk_clip0;
+      clip_tab.resize(size_t(n) * 4);
+      int64_t total = 0;
+      for (int64_t b = 0; b < n; ++b) {
+        const int64_t fr = clip_frames[size_t(c0 + b)];
+        clip_tab[4 * b + 0] = int(rg->lengths[c0 + b]);
+        clip_tab[4 * b + 1] = int(fr);
+        clip_tab[4 * b + 2] = int(p.out_mode == OUT_LFR ? b2a_lfr_num_rows(fr, p.lfr_n) : 0);
+        clip_tab[4 * b + 3] = int(total);
+        total += (fr + ft - 1) / ft;
+      }
+      if (total > 0x7fffffffLL) return fail(c, B2A_E_BAD_ARG, "too many tiles in one launch");
+      tile_tab.resize(size_t(total) * 2);
+      for (int64_t b = 0, g = 0; b < n; ++b)
+        for (int64_t t = 0, nt = (clip_frames[size_t(c0 + b)] + ft - 1) / ft; t < nt; ++t, ++g) {
+          tile_tab[2 * g] = int(b);
+          tile_tab[2 * g + 1] = int(t);
+        }
+      int rc;
+      if ((rc = ensure(c, c->scratch[slot][3], sizeof(int) * clip_tab.size())) != B2A_OK) return rc;
+      if ((rc = ensure(c, c->scratch[slot][4], sizeof(int) * tile_tab.size())) != B2A_OK) return rc;
+      cudaError_t e;
+      if ((e = cudaMemcpyAsync(c->scratch[slot][3].p, clip_tab.data(), sizeof(int) * clip_tab.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+        return cu(c, e, "table upload");
+      if ((e = cudaMemcpyAsync(c->scratch[slot][4].p, tile_tab.data(), sizeof(int) * tile_tab.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+        return cu(c, e, "table upload");
+      if ((e = cudaMemsetAsync(d_out, 0, sizeof(float) * out_per_clip * size_t(n), c->stream)) != cudaSuccess) return cu(c, e, "memset");
+      a.clip_tab = c->scratch[slot][3].p;
+      a.tile_tab = c->scratch[slot][4].p;
+      a.total_tiles = total;
+    }
     if (p.whisper_norm) {
       int rc;
       if ((rc = ensure(c, c->scratch[slot][0], sizeof(int) * size_t(n))) != B2A_OK) return rc;
@@ -302,8 +363,8 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
     std::string err;
     int rc = launch_frontend(a, c->stream, &launches, &err);
     if (rc == B2A_OK && p.post_cmvn)
-      rc = launch_cmvn(d_out, d_out, n, p.lfr_rows, p.lfr_m * p.bank.n_mels, nullptr, nullptr, c->stream, &launches, &err);
-    if (rc == B2A_OK && p.post_mean_norm) rc = launch_mean_norm(d_out, n, p.n_frames, p.bank.n_mels, c->stream, &launches, &err);
+      rc = launch_cmvn(d_out, d_out, n, p.lfr_rows, p.lfr_m * p.bank.n_mels, nullptr, nullptr, c->stream, &launches, &err, a.clip_tab);
+    if (rc == B2A_OK && p.post_mean_norm) rc = launch_mean_norm(d_out, n, p.n_frames, p.bank.n_mels, c->stream, &launches, &err, a.clip_tab);
     c->launches += launches;
     if (rc != B2A_OK) c->err = err;
     return rc;
@@ -399,7 +460,7 @@ int b2a_ctx_destroy(b2a_ctx* c) {
       if (c->in[s][j].p) cudaFree(c->in[s][j].p);
       if (c->out[s][j].p) cudaFree(c->out[s][j].p);
     }
-    for (int j = 0; j < 3; ++j)
+    for (int j = 0; j < 5; ++j)
       if (c->scratch[s][j].p) cudaFree(c->scratch[s][j].p);
     if (c->ev_h2d[s]) cudaEventDestroy(c->ev_h2d[s]);
     if (c->ev_comp[s]) cudaEventDestroy(c->ev_comp[s]);
@@ -640,7 +701,7 @@ int b2a_whisper_mel_segment_f16(b2a_ctx* c, const float* mel, int64_t batch, int
 }
 
 static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding, float* out,
-                        int space, bool chatterbox) {
+                        int space, bool chatterbox, const int64_t* lengths = nullptr, int64_t* out_rows = nullptr) {
   int rc = check_common(c, audio, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (padding < 0) return fail(c, B2A_E_BAD_ARG, "padding must be >= 0");
@@ -659,7 +720,8 @@ static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n
   p.whisper_norm = 1;
   p.out_mode = chatterbox ? OUT_MT : OUT_TM;
   p.n_frames = frames;  // the last STFT frame is dropped (WhisperAudio.swift:105, S3TokenizerUtils.swift:184)
-  return run_preset(c, p, audio, batch, n_samples, out, space);
+  Ragged rg{lengths, [&](int64_t len) { return b2a_whisper_num_frames(len, padding); }, out_rows};
+  return run_preset(c, p, audio, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
 
 int b2a_whisper_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
@@ -672,8 +734,20 @@ int b2a_log_mel_spectrogram_chatterbox(b2a_ctx* c, const float* audio, int64_t b
   return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, true);
 }
 
+int b2a_whisper_log_mel_spectrogram_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                           int n_mels, int64_t padding, float* out, int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, false, lengths, out_frames);
+}
+
+int b2a_log_mel_spectrogram_chatterbox_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                              int n_mels, int64_t padding, float* out, int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, true, lengths, out_frames);
+}
+
 static int funasr_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
-                         int lfr, int norm, float* out, int space) {
+                         int lfr, int norm, float* out, int space, const int64_t* lengths = nullptr, int64_t* out_rows = nullptr) {
   int rc = check_common(c, audio, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (n_mels <= 0) return fail(c, B2A_E_BAD_ARG, "n_mels must be positive");
@@ -697,7 +771,8 @@ static int funasr_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t 
     p.lfr_rows = b2a_lfr_num_rows(frames, lfr_n);
     p.post_cmvn = norm;
   }
-  return run_preset(c, p, audio, batch, n_samples, out, space);
+  Ragged rg{lengths, [](int64_t len) { return b2a_funasr_num_frames(len); }, out_rows};
+  return run_preset(c, p, audio, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
 
 int b2a_funasr_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, float* out, int space) {
@@ -707,6 +782,12 @@ int b2a_funasr_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch
 int b2a_funasr_preprocess_audio(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
                                 int apply_normalization, float* out, int space) {
   return funasr_common(c, audio, batch, n_samples, n_mels, lfr_m, lfr_n, 1, apply_normalization != 0, out, space);
+}
+
+int b2a_funasr_preprocess_audio_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_mels,
+                                       int lfr_m, int lfr_n, int apply_normalization, float* out, int64_t* out_rows, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return funasr_common(c, audio, batch, n_samples, n_mels, lfr_m, lfr_n, 1, apply_normalization != 0, out, space, lengths, out_rows);
 }
 
 int b2a_apply_lfr(b2a_ctx* c, const float* features, int64_t batch, int64_t n_frames, int n_mels, int lfr_m, int lfr_n, float* out,
@@ -764,8 +845,9 @@ int b2a_apply_cmvn(b2a_ctx* c, const float* features, int64_t batch, int64_t n_r
   return run_batched(c, space, batch, features, size_t(n_rows) * dim, nullptr, 0, out, size_t(n_rows) * dim, nullptr, 0, body);
 }
 
-int b2a_kaldi_fbank_campplus(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
-                             float frame_length_ms, float frame_shift_ms, int mean_norm, float* out, int space) {
+static int kaldi_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
+                        float frame_length_ms, float frame_shift_ms, int mean_norm, float* out, int space, const int64_t* lengths,
+                        int64_t* out_rows) {
   int rc = check_common(c, audio, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (sample_rate <= 0 || num_mel_bins <= 0) return fail(c, B2A_E_BAD_ARG, "sample_rate and num_mel_bins must be positive");
@@ -792,11 +874,24 @@ int b2a_kaldi_fbank_campplus(b2a_ctx* c, const float* audio, int64_t batch, int6
   p.log_floor = 1.1920929e-07f;
   p.n_frames = frames;
   p.post_mean_norm = mean_norm != 0;
-  return run_preset(c, p, audio, batch, n_samples, out, space);
+  Ragged rg{lengths, [&](int64_t len) { return b2a_kaldi_num_frames(len, win_length, hop); }, out_rows};
+  return run_preset(c, p, audio, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
 
-int b2a_s3gen_mel_spectrogram(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
-                              int hop_size, int win_size, int fmin, int fmax, float* out, int space) {
+int b2a_kaldi_fbank_campplus(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
+                             float frame_length_ms, float frame_shift_ms, int mean_norm, float* out, int space) {
+  return kaldi_common(c, audio, batch, n_samples, sample_rate, num_mel_bins, frame_length_ms, frame_shift_ms, mean_norm, out, space, nullptr, nullptr);
+}
+
+int b2a_kaldi_fbank_campplus_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths, int sample_rate,
+                                    int num_mel_bins, float frame_length_ms, float frame_shift_ms, int mean_norm, float* out,
+                                    int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return kaldi_common(c, audio, batch, n_samples, sample_rate, num_mel_bins, frame_length_ms, frame_shift_ms, mean_norm, out, space, lengths, out_frames);
+}
+
+static int s3gen_common(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
+                        int hop_size, int win_size, int fmin, int fmax, float* out, int space, const int64_t* lengths, int64_t* out_rows) {
   int rc = check_common(c, y, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (win_size > n_fft || win_size <= 0) return fail(c, B2A_E_BAD_ARG, "win_size must be in (0, n_fft]");
@@ -817,7 +912,23 @@ int b2a_s3gen_mel_spectrogram(b2a_ctx* c, const float* y, int64_t batch, int64_t
   p.log_floor = 1e-5f;
   p.out_mode = OUT_MT;
   p.n_frames = frames;
-  return run_preset(c, p, y, batch, n_samples, out, space);
+  if (lengths)   // reflectPad2D truncates the pad for clips of <= pad samples: one pad_left per launch, so those stay out of ragged batches
+    for (int64_t b = 0; b < batch; ++b)
+      if (lengths[b] <= pad) return fail(c, B2A_E_UNSUPPORTED, "ragged s3gen mel needs every clip longer than (n_fft - hop) / 2 samples");
+  Ragged rg{lengths, [&](int64_t len) { return b2a_s3gen_num_frames(len, n_fft, hop_size); }, out_rows};
+  return run_preset(c, p, y, batch, n_samples, out, space, lengths ? &rg : nullptr);
+}
+
+int b2a_s3gen_mel_spectrogram(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
+                              int hop_size, int win_size, int fmin, int fmax, float* out, int space) {
+  return s3gen_common(c, y, batch, n_samples, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, out, space, nullptr, nullptr);
+}
+
+int b2a_s3gen_mel_spectrogram_ragged(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_fft,
+                                     int num_mels, int sampling_rate, int hop_size, int win_size, int fmin, int fmax, float* out,
+                                     int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return s3gen_common(c, y, batch, n_samples, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, out, space, lengths, out_frames);
 }
 
 int b2a_voice_encoder_melspectrogram(b2a_ctx* c, const float* wav, int64_t batch, int64_t n_samples, const b2a_voice_enc_config* cfg_in,

@@ -139,6 +139,10 @@ struct FrontendParams {
   float* out;
   int* clip_max;
   int* tile_min;   // per tile: ordered-int encoding of the minimum normalised value
+  // Ragged batches (per-clip lengths; RAGGED kernels only): clip b = (n_samples, n_frames, lfr_rows, index of its first tile);
+  // tile g of the launch = (clip, tile within the clip).  Strides (clip_stride, out_clip_stride) stay those of the longest clip.
+  const int4* clip_tab;
+  const int2* tile_tab;
   float window[P::WIN];
 };
 
@@ -331,13 +335,14 @@ __device__ __noinline__ void stage_pcm_edge(const float* __restrict__ xc, float*
 // every copy an immediate offset from two per-warp base pointers.  Edge tiles (reflect / zero padding, clip end) go
 // through the index map.
 template <class P>
-B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, int clip, int f0, int tid, int lane, int warp) {
+B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, int clip, int f0, long long n_samples, long long n_eff,
+                       int tid, int lane, int warp) {
   constexpr int HOP = P::HOP, NW = P::NWARPS, NROWS = P::NROWS;
   static_assert(HOP % 32 == 0, "rows are copied as whole 32-lane chunks");
   const float* __restrict__ xc = prm.x + (long long)clip * prm.clip_stride;
   const long long p0 = (long long)f0 * HOP;
   const long long j0 = p0 - prm.pad_left;
-  if (j0 >= 0 && j0 + NROWS * HOP <= prm.n_samples) {
+  if (j0 >= 0 && j0 + NROWS * HOP <= n_samples) {
     const float* __restrict__ src = xc + j0 + warp * HOP + lane;
     float* dst = buf + warp * P::PITCH + lane;
 #pragma unroll
@@ -348,7 +353,7 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
       }
     }
   } else {
-    stage_pcm_edge(xc, buf, p0, prm.pad_left, prm.n_samples, prm.n_eff, prm.pad_mode, tid, P::TS, HOP, P::NTHREADS);
+    stage_pcm_edge(xc, buf, p0, prm.pad_left, n_samples, n_eff, prm.pad_mode, tid, P::TS, HOP, P::NTHREADS);
   }
 }
 
@@ -358,7 +363,9 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // MEL == 0: any bank -- mel step program interpreted in a loop, run-time log / output modes (POST_RUNTIME, OUT = -1).
 // MEL > 0: bank MEL of mel_baked.h as straight-line code, with compile-time post-processing POST (applied in the store
 // loop) and output layout OUT (OUT_TM / OUT_MT / OUT_LFR).
-template <class P, int PRE, int SPEC, int MEL, int POST, int OUT>
+// RAGGED: per-clip lengths -- the tile walk and the clip geometry come from prm.tile_tab / prm.clip_tab (one uniform load each
+// per tile) instead of the launch-wide constants; built for the run-time-configured kernels only.
+template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
@@ -397,7 +404,28 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   const int tpc = prm.tiles_per_clip, n_clips = prm.n_clips;
   const int step_clip = int(gridDim.x) / tpc, step_tile = int(gridDim.x) - step_clip * tpc;
   int clip = int(blockIdx.x) / tpc, tile = int(blockIdx.x) - clip * tpc;
-  if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, tid, lane, warp);
+  // geometry of the current clip: launch-wide constants, or (RAGGED) the clip's own row of clip_tab
+  long long n_samples = prm.n_samples, n_frames = prm.n_frames, lfr_rows = prm.lfr_rows;
+  const long long zero_tail = prm.n_eff - prm.n_samples;
+  long long g = blockIdx.x;    // RAGGED: index of the tile within the launch
+  int first_tile = 0;
+  auto load_clip = [&](int cl) {
+    const int4 ci = __ldg(prm.clip_tab + cl);
+    n_samples = ci.x;
+    n_frames = ci.y;
+    lfr_rows = ci.z;
+    first_tile = ci.w;
+  };
+  if (RAGGED) {
+    clip = n_clips;
+    if (g < prm.total_tiles) {
+      const int2 t = __ldg(prm.tile_tab + g);
+      clip = t.x;
+      tile = t.y;
+      load_clip(clip);
+    }
+  }
+  if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
 
   while (clip < n_clips) {
     const int f0 = tile * FT;
@@ -407,6 +435,16 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       ntile -= tpc;
       ++nclip;
     }
+    long long nn_samples = n_samples;   // next tile's clip length
+    if (RAGGED) {
+      nclip = n_clips;
+      if (g + gridDim.x < prm.total_tiles) {
+        const int2 t = __ldg(prm.tile_tab + g + gridDim.x);
+        nclip = t.x;
+        ntile = t.y;
+        nn_samples = __ldg(prm.clip_tab + nclip).x;
+      }
+    }
 
     // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
     cp_async_commit_wait_all();
@@ -414,7 +452,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
     // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
     // not a conflict), so that per-tile max / min need no lane masking.
-    const int rows = int(prm.n_frames - f0 < FT ? prm.n_frames - f0 : FT);
+    const int rows = int(n_frames - f0 < FT ? n_frames - f0 : FT);
     const int flane = fl < rows ? fl : rows - 1;
 
     // ---- 2. stage A: N2 real DFTs of size N1 over samples o = N2*n1 + n2, twiddle, exchange --------
@@ -465,7 +503,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
     __syncthreads();
-    if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, tid, lane, warp);
+    if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
 
     // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
     // The power / magnitude of every bin goes back into the item's own rows of the exchange buffer (row = slot of
@@ -640,7 +678,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
           }
         } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
           const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
-          const int T = int(prm.n_frames), last_row = int(prm.lfr_rows) - 1;
+          const int T = int(n_frames), last_row = int(lfr_rows) - 1;
           int i_lo = f0 + left - (lm - 1) < 0 ? 0 : (f0 + left - (lm - 1)) / ln;
           int i_hi = (f0 + rows - 1 + left) / ln;
           if (f0 + rows >= T || i_hi > last_row) i_hi = last_row;
@@ -664,7 +702,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
         if (lane == 0) {
           atomicMax(prm.clip_max + clip, wmax);
-          atomicMin(prm.tile_min + clip * tpc + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
+          atomicMin(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
         }
       }
     } else {
@@ -704,12 +742,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         else store_mt([&](float v) { return v; });
       } else {  // OUT_LFR: out[i][j*M + m] = ln(feat)[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
         const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
-        const long long T = prm.n_frames;
+        const long long T = n_frames;
         long long i_lo = (f0 + left - (lm - 1)) / ln;
         if (f0 + left - (lm - 1) < 0) i_lo = 0;
         long long i_hi = (f0 + rows - 1 + left) / ln;
-        if (f0 + rows >= T) i_hi = prm.lfr_rows - 1;
-        if (i_hi > prm.lfr_rows - 1) i_hi = prm.lfr_rows - 1;
+        if (f0 + rows >= T) i_hi = lfr_rows - 1;
+        if (i_hi > lfr_rows - 1) i_hi = lfr_rows - 1;
         const int nseg = int(i_hi - i_lo + 1) * lm;
         for (int sg = warp; sg < nseg; sg += NW) {
           const long long i = i_lo + sg / lm;
@@ -733,17 +771,21 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
       if (lane == 0) {
         atomicMax(prm.clip_max + clip, wmax);
-        atomicMin(prm.tile_min + clip * tpc + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
+        atomicMin(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
       }
     }
     }  // !cplx
     if (!EARLY_PREFETCH) {
       // plain stft(), single buffer: the next tile's PCM can only be staged once every warp is done with the complex tile
       __syncthreads();
-      if (nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, tid, lane, warp);
+      if (nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
     }
     clip = nclip;
     tile = ntile;
+    if (RAGGED) {
+      g += gridDim.x;
+      if (clip < n_clips) load_clip(clip);
+    }
   }
 }
 
@@ -753,17 +795,27 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 // One CTA per (clip, group of kClampTilesPerCta tiles): the group's tile minima are tested in parallel (one round trip to
 // memory), the tiles that need it are rewritten with 16-byte accesses.
 constexpr int kClampTilesPerCta = 32;
+// clip_tab != null (ragged batch): the clip's own frame count and first tile; `n_frames` stays the (M, T') row stride.
 __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
-                                                            long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft) {
+                                                            long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft,
+                                                            const int4* __restrict__ clip_tab) {
   __shared__ int s_list[kClampTilesPerCta];
   __shared__ int s_count;
   const long long clip = blockIdx.y;
+  const long long mt_stride = n_frames;
+  long long tile_base = clip * tiles_per_clip;
+  if (clip_tab != nullptr) {
+    const int4 ci = clip_tab[clip];
+    n_frames = ci.y;
+    tiles_per_clip = int((n_frames + ft - 1) / ft);
+    tile_base = ci.w;
+  }
   const float thr = dec_ordered(clip_max[clip]) - 2.0f;   // clip_max holds the maximum of the normalised values: ((Lmax - 8) + 4) / 4 = (Lmax + 4) / 4 - 2
   const int t0 = blockIdx.x * kClampTilesPerCta;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   if (threadIdx.x < kClampTilesPerCta && t0 + int(threadIdx.x) < tiles_per_clip &&
-      dec_ordered(tile_min[clip * tiles_per_clip + t0 + threadIdx.x]) < thr)
+      dec_ordered(tile_min[tile_base + t0 + threadIdx.x]) < thr)
     s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
   __syncthreads();
   const int count = s_count;
@@ -788,7 +840,7 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
     } else {  // OUT_MT
       for (int e = threadIdx.x; e < rows * n_mels; e += blockDim.x) {
         const int m = e / rows, r = e - m * rows;
-        float* d = o + (long long)m * n_frames + f0 + r;
+        float* d = o + (long long)m * mt_stride + f0 + r;
         *d = fmaxf(*d, thr);
       }
     }
@@ -799,15 +851,21 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
 // per-clip column statistics: CMVN (FunASRAudio.swift:165-180) and time-mean removal (CAMPPlus.swift:800)
 // block = 32 columns x 8 row groups; grid = (column chunks, batch)
 // ------------------------------------------------------------------------------------------------
+// clip_tab != null (ragged batch): the statistics run over the clip's own rows (component `tab_rows` of its clip_tab entry:
+// 1 = frames, 2 = LFR rows); the clip stride stays `rows` (the longest clip's) x dim.
 __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows,
                                                       int dim, const float* __restrict__ gmean, const float* __restrict__ gistd,
-                                                      int do_var) {
+                                                      int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
   __shared__ float s_red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + cx;
   const long long clip = blockIdx.y;
   const float* src = in + clip * rows * dim;
   float* dst = out + clip * rows * dim;
+  if (clip_tab != nullptr) {
+    const int4 ci = clip_tab[clip];
+    rows = tab_rows == 2 ? ci.z : ci.y;
+  }
   const bool ok = col < dim;
   if (gmean != nullptr) {  // (x + mean) * istd with precomputed statistics
     if (ok) {
@@ -1042,8 +1100,14 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
+  if (!RAGGED && a.clip_tab != nullptr) {
+    // per-clip lengths: the run-time-configured kernel of the same plan, reading the clip / tile tables
+    if constexpr (MEL == 0 && POST == POST_RUNTIME && OUT == -1 && SPEC != SK_CPLX) return launch_plan<P, PRE, SPEC, 0, POST_RUNTIME, -1, true>(a, st, launches, err);
+    if (err) *err = "ragged batches are built for the mel front ends only";
+    return B2A_E_UNSUPPORTED;
+  }
   static FrontendParams<P> prm;  // large (window table); filled and launched under the lock
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
@@ -1090,6 +1154,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.tile_min = reinterpret_cast<int*>(a.tile_min);
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
   prm.n_clips = int(a.batch);
+  prm.clip_tab = static_cast<const int4*>(a.clip_tab);
+  prm.tile_tab = static_cast<const int2*>(a.tile_tab);
   switch (a.out_mode) {
     case OUT_TM: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
     case OUT_MT: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
@@ -1108,9 +1174,9 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
                                              P::N + P::TW_WORDS);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
-  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
-  prm.total_tiles = (long long)prm.tiles_per_clip * a.batch;
+  prm.total_tiles = RAGGED ? (long long)a.total_tiles : (long long)prm.tiles_per_clip * a.batch;
   if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL || a.batch > 0x7fffffffLL || a.n_frames > 0x7fffffffLL) {
     if (err) *err = "empty launch";
     return B2A_E_BAD_ARG;
@@ -1118,7 +1184,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   int dev = 0, n_sm = 148, per_sm = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT>, P::NTHREADS, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED>, P::NTHREADS, smem)) != cudaSuccess)
     return cuda_fail(e, "occupancy query", err);
   if (per_sm < 1) {
     if (err) *err = "frontend kernel does not fit on this device";
@@ -1130,15 +1196,16 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     if ((e = cudaMemsetAsync(a.tile_min, 0x7f, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
   }
-  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
     for (long long c0 = 0; c0 < a.batch; c0 += 65535) {   // gridDim.y limit
       const long long nb = std::min<long long>(65535, a.batch - c0);
       whisper_clamp_kernel<<<dim3(unsigned((prm.tiles_per_clip + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, st>>>(
-          a.out + c0 * prm.out_clip_stride, a.clip_max + c0, prm.tile_min + c0 * prm.tiles_per_clip, prm.tiles_per_clip, a.n_frames,
-          a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT);  // tiles of FT frames
+          a.out + c0 * prm.out_clip_stride, a.clip_max + c0, RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip, prm.tiles_per_clip, a.n_frames,
+          a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT,   // tiles of FT frames
+          RAGGED ? prm.clip_tab + c0 : nullptr);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
     *launches += 1;
@@ -1166,7 +1233,8 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   // at compile time on the post-processing and the output layout (small code: the whole tile loop stays inside the
   // instruction cache); everything else runs the run-time-configured kernel.
   int post = -1;
-  if (a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
+  const bool ragged = a.clip_tab != nullptr;   // per-clip lengths: run-time-configured kernels only
+  if (!ragged && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }
@@ -1189,7 +1257,7 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   }
   if (a.n_fft == 1920 && a.hop == 480 && a.win_len == 1920 && a.pre_mode == PRE_NONE) {
     // S3Gen 24 kHz mel (S3GenMel.swift:43-102): magnitude spectrum, ln, (M, T') -- compile-time post-processing keeps the store code short
-    if (spec == SK_MAG && a.bank.steps != nullptr && a.log_mode == LOG_LN && !a.whisper_norm && !a.post_affine && a.out_mode == OUT_MT)
+    if (!ragged && spec == SK_MAG && a.bank.steps != nullptr && a.log_mode == LOG_LN && !a.whisper_norm && !a.post_affine && a.out_mode == OUT_MT)
       return launch_plan<Plan1920, PRE_NONE, SK_MAG, 0, POST_LN, OUT_MT>(a, st, launches, err);
     if (spec == SK_POWER) return launch_plan<Plan1920, PRE_NONE, SK_POWER>(a, st, launches, err);
     if (spec == SK_MAG) return launch_plan<Plan1920, PRE_NONE, SK_MAG>(a, st, launches, err);
@@ -1200,18 +1268,18 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
 }
 
 int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
-                void* stream, int* launches, std::string* err) {
+                void* stream, int* launches, std::string* err, const void* clip_tab) {
   dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));
-  colstat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, dim, mean, istd, 1);
+  colstat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, dim, mean, istd, 1, static_cast<const int4*>(clip_tab), 2);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "colstat_kernel launch", err);
   *launches += 1;
   return B2A_OK;
 }
 
-int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err) {
+int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err, const void* clip_tab) {
   dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));
-  colstat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(inout, inout, rows, dim, nullptr, nullptr, 0);
+  colstat_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(inout, inout, rows, dim, nullptr, nullptr, 0, static_cast<const int4*>(clip_tab), 1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "colstat_kernel launch", err);
   *launches += 1;

@@ -96,6 +96,12 @@ struct FrontendArgs {
   // scratch for the Whisper clamp (device): clip_max (batch) ordered-int encoded, tile_min (batch * tiles)
   int* clip_max = nullptr;
   float* tile_min = nullptr;
+  // ragged batch (per-clip lengths): device tables built by the C ABI -- clip_tab[b] = int4(n_samples, n_frames, lfr_rows,
+  // first tile of the clip), tile_tab[g] = int2(clip, tile); n_samples / n_frames / lfr_rows above are then those of the
+  // longest clip (they give the strides).  Null = every clip has n_samples samples.
+  const void* clip_tab = nullptr;
+  const void* tile_tab = nullptr;
+  int64_t total_tiles = 0;
 };
 
 // Returns 0 or a b2a_status; sets *launches to the number of kernels enqueued.
@@ -107,8 +113,9 @@ int init_frontend_tables(std::string* err);  // once per device: twiddle tables 
 
 // per-clip column statistics kernels (frontend.cu)
 int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
-                void* stream, int* launches, std::string* err);
-int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err);
+                void* stream, int* launches, std::string* err, const void* clip_tab = nullptr);
+int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err,
+                     const void* clip_tab = nullptr);
 int launch_lfr(const float* in, float* out, int64_t batch, int64_t n_frames, int n_mels, int lfr_m, int lfr_n,
                void* stream, int* launches, std::string* err);
 int launch_mel_segment_f16(const float* mel, void* out_f16, int64_t batch, int64_t n_frames, int n_mels, const long long* d_seek_content,
