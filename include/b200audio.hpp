@@ -143,6 +143,49 @@ class Context {
     return out;
   }
 
+  // ---- ragged batches: clips of different lengths in one launch (b200audio.h, "ragged batches") ----
+  // audio (B, T_max) with lengths[b] valid samples per row -> (B, T'max, nMels) (rows past a clip's frame count are zero) and the
+  // frame count of every clip; each clip is processed exactly like whisperLogMelSpectrogram(audio[b, :lengths[b]])
+  std::pair<Array, std::vector<int64_t>> whisperLogMelSpectrogramRagged(const Array& audio, const std::vector<int64_t>& lengths, int nMels,
+                                                                       int64_t padding = 0) const {
+    const int64_t b = audio.shape.at(0), n = audio.shape.at(1), frames = b2a_whisper_num_frames(n, padding);
+    if (frames <= 0 || int64_t(lengths.size()) != b) throw Error(B2A_E_BAD_ARG, "bad ragged batch");
+    Array out({b, frames, nMels});
+    std::vector<int64_t> rows(size_t(b), 0);
+    check(b2a_whisper_log_mel_spectrogram_ragged(c_, audio.data.data(), b, n, lengths.data(), nMels, padding, out.data.data(), rows.data(), B2A_HOST));
+    return {std::move(out), std::move(rows)};
+  }
+  // preprocessAudio per clip -> (B, rows_max, nMels * lfrM) and the LFR row count of every clip
+  std::pair<Array, std::vector<int64_t>> preprocessAudioRagged(const Array& audio, const std::vector<int64_t>& lengths, int nMels = 80, int lfrM = 7,
+                                                              int lfrN = 6, bool applyNormalization = true) const {
+    const int64_t b = audio.shape.at(0), n = audio.shape.at(1), frames = b2a_funasr_num_frames(n);
+    if (frames <= 0 || int64_t(lengths.size()) != b) throw Error(B2A_E_BAD_ARG, "bad ragged batch");
+    Array out({b, b2a_lfr_num_rows(frames, lfrN), int64_t(nMels) * lfrM});
+    std::vector<int64_t> rows(size_t(b), 0);
+    check(b2a_funasr_preprocess_audio_ragged(c_, audio.data.data(), b, n, lengths.data(), nMels, lfrM, lfrN, applyNormalization, out.data.data(),
+                                             rows.data(), B2A_HOST));
+    return {std::move(out), std::move(rows)};
+  }
+
+  // ---- multi-GPU: the consumer rank's feature buffer, mapped into every producer process (b200audio.h, "fused gather") ----
+  void* deviceAlloc(uint64_t bytes) const {
+    void* p = nullptr;
+    check(b2a_device_alloc(c_, &p, bytes));
+    return p;
+  }
+  void deviceFree(void* p) const { check(b2a_device_free(c_, p)); }
+  std::vector<unsigned char> ipcExport(void* devicePtr) const {
+    std::vector<unsigned char> h(B2A_IPC_HANDLE_BYTES);
+    check(b2a_ipc_export(c_, devicePtr, h.data()));
+    return h;
+  }
+  void* ipcOpen(const std::vector<unsigned char>& handle) const {
+    void* p = nullptr;
+    check(b2a_ipc_open(c_, handle.data(), &p));
+    return p;
+  }
+  void ipcClose(void* peerPtr) const { check(b2a_ipc_close(c_, peerPtr)); }
+
  private:
   b2a_ctx* c_ = nullptr;
 };

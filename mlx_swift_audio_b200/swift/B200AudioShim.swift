@@ -156,6 +156,29 @@ public final class B200Audio {
     } }
     return out
   }
+  /// Ragged batch: clips of different lengths in one launch (include/b200audio.h, "ragged batches").  `audio` is (B, T_max),
+  /// `lengths[b]` the valid samples of row b; every clip comes out as whisperLogMelSpectrogram(audio[b, ..<lengths[b]]) would,
+  /// rows past a clip's frame count are zero.  Replaces the per-clip Swift loops of the callers (e.g. S3Tokenizer.swift:474-571).
+  public func whisperLogMelSpectrogramRagged(audio: Tensor, lengths: [Int], nMels: Int, padding: Int = 0) -> (Tensor, [Int]) {
+    let b = audio.shape[0], n = audio.shape[1]
+    let frames = Int(b2a_whisper_num_frames(Int64(n), Int64(padding)))
+    if frames <= 0 || lengths.count != b { fatalError("Input is too short for STFT") }
+    var out = Tensor(zeros: [b, frames, nMels])
+    var rows = [Int64](repeating: 0, count: b)
+    let len64 = lengths.map { Int64($0) }
+    audio.data.withUnsafeBufferPointer { x in out.data.withUnsafeMutableBufferPointer { o in
+      check(b2a_whisper_log_mel_spectrogram_ragged(ctx, x.baseAddress, Int64(b), Int64(n), len64, Int32(nMels), Int64(padding), o.baseAddress,
+                                                   &rows, Int32(B2A_HOST.rawValue)))
+    } }
+    return (out, rows.map { Int($0) })
+  }
+  // logMelSpectrogramChatterboxRagged, preprocessAudioRagged, kaldiFbankCAMPPlusRagged and s3genMelSpectrogramRagged bind the other
+  // b2a_*_ragged entry points in the same way.
+  //
+  // Multi-GPU (one process per GPU): the consumer rank calls b2a_device_alloc + b2a_ipc_export and ships the 64-byte handle to the
+  // producer processes (any host channel); each producer calls b2a_ipc_open and passes `peer + firstClip * clipBytes` as the `out`
+  // pointer of a B2A_DEVICE call -- the kernel's stores then land in the consumer's HBM over NVLink (INTEGRATION.md section 6).
+
   // kokoroHeadIstft binds b2a_kokoro_head_istft like hiftHeadIstft.
   // cosyVoice3Stft / cosyVoice3Istft, MLXSTFT.transform / .inverse, funASRLogMelSpectrogram, applyLFR, applyCMVN,
   // voiceEncoderMelspectrogram and stft bind b2a_cosyvoice3_*, b2a_kokoro_stft_*, b2a_funasr_log_mel_spectrogram,

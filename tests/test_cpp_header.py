@@ -14,6 +14,11 @@ int main() {
   auto w = b2a::hannWindowPeriodic(16);
   auto f = b2a::melFilters(16000, 400, 80, 0.0f, 8000.0f);
   std::printf("%s %.3f %zu\n", b2a_version(), w[4], f.size());
+  // (taking the addresses instantiates the ragged-batch and peer-memory wrappers without needing a GPU)
+  auto pr = &b2a::Context::whisperLogMelSpectrogramRagged;
+  auto pf = &b2a::Context::preprocessAudioRagged;
+  auto pi = &b2a::Context::ipcOpen;
+  if (!pr || !pf || !pi) return 2;
   try { b2a::Context c(0); } catch (const b2a::Error& e) { std::printf("no gpu: %s\n", e.what()); }
   return (w[4] > 0.49f && w[4] < 0.51f && f.size() == 80u * 201u) ? 0 : 1;
 }
