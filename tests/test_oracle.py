@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import reference_dsp as R
+from tests import synth
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_fp32_v1.npz")
 
@@ -177,3 +178,67 @@ def test_golden_adjacent_rows():
     assert np.array_equal(R.whisper_mel_segment(a["in_mel"], 37, 50, length=64).view(np.uint16), a["mel_segment_seek37"].view(np.uint16))
     assert np.array_equal(R.resample_audio(g["in_x24"], 24000, 16000), a["resample_24k_16k"])
     assert np.array_equal(R.resample_audio(g["in_x16"], 16000, 24000), a["resample_16k_24k"])
+
+
+# ---- independent pins: public implementations of the published algorithms the reference restates -------------------
+# The reference ships no golden vectors, so the oracle is additionally pinned against two libraries that implement
+# the same published definitions independently of it: torchaudio (melscale_fbanks, Kaldi-compatible framing) and Hugging Face
+# transformers (the OpenAI Whisper log-mel pipeline).
+
+def test_filterbanks_match_torchaudio_and_transformers():
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    # funASRMelFilters (FunASRAudio.swift:322-396) is torchaudio's melscale_fbanks evaluated on nFft/2 = 200 grid points
+    fb = ta.functional.melscale_fbanks(200, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="htk").numpy().T
+    assert np.abs(R.funasr_mel_filters(16000, 400, 80) - fb).max() <= 5e-7
+    # melFilters (S3TokenizerUtils.swift:301-375) is the Slaney bank of librosa / OpenAI Whisper
+    for n_mels in (80, 128):
+        fb = ta.functional.melscale_fbanks(201, 0.0, 8000.0, n_mels, 16000, norm="slaney", mel_scale="slaney").numpy().T
+        assert np.abs(R.mel_filters(16000, 400, n_mels, 0.0, 8000.0) - fb).max() <= 1e-6
+    au = pytest.importorskip("transformers.audio_utils")
+    fb = au.mel_filter_bank(num_frequency_bins=961, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0, sampling_rate=24000,
+                            norm="slaney", mel_scale="slaney").T
+    assert np.abs(R.mel_filters(24000, 1920, 80, 0.0, 8000.0) - fb).max() <= 1e-6
+
+
+@pytest.mark.parametrize("which", ["chatterbox", "whisper"])
+def test_log_mel_matches_the_openai_whisper_pipeline(which):
+    au = pytest.importorskip("transformers.audio_utils")
+    x = synth.pcm(1, 16000 * 6 + 123, seed=31)[0]
+    bank = au.mel_filter_bank(num_frequency_bins=201, num_mel_filters=128, min_frequency=0.0, max_frequency=8000.0, sampling_rate=16000,
+                              norm="slaney", mel_scale="slaney")
+    # S3Tokenizer / Chatterbox use the periodic Hann window of OpenAI Whisper; the reference's own Whisper front end deviates
+    # from OpenAI only in the window (symmetric Hann, WhisperAudio.swift:32-44), so the same pipeline with that window pins it too
+    n = np.arange(400)
+    w = au.window_function(400, "hann") if which == "chatterbox" else 0.5 * (1.0 - np.cos(2.0 * np.pi * n / 399.0))
+    ls = au.spectrogram(x.astype(np.float64), w, frame_length=400, hop_length=160, power=2.0, mel_filters=bank, log_mel="log10")[:, :-1]
+    ls = (np.maximum(ls, ls.max() - 8.0) + 4.0) / 4.0
+    if which == "chatterbox":
+        o32, o64 = R.log_mel_spectrogram_chatterbox(x, 128), R.log_mel_spectrogram_chatterbox(x, 128, dt=np.float64)
+    else:
+        o32, o64 = R.whisper_log_mel_spectrogram(x, 128).T, R.whisper_log_mel_spectrogram(x, 128, dt=np.float64).T
+    assert o64.shape == ls.shape
+    assert np.abs(o64 - ls).max() <= 1e-6      # same algorithm in fp64: only the fp32 filterbank tables differ
+    assert np.abs(o32 - ls).max() <= 2e-4      # the fp32 restatement (what the GPU path is compared with)
+
+
+def test_kaldi_framing_matches_torchaudio():
+    torch = pytest.importorskip("torch")
+    kaldi = pytest.importorskip("torchaudio.compliance.kaldi")
+    x = synth.pcm(1, 16000 + 77, seed=33)[0]
+    # snip-edges framing, per-frame DC removal, 0.97 pre-emphasis and the Povey window of kaldiFbankCAMPPlus
+    # (CAMPPlus.swift:32-106) are Kaldi's; torchaudio's Kaldi-compatible front end gives the same windowed frames
+    # (the two treat the first sample of a frame differently, but the Povey window is zero there)
+    frames, _ = kaldi._get_window(torch.from_numpy(x), 512, 400, 160, "povey", 0.42, True, True, 0.0, 0.0, True, 0.97)
+    n_frames = (len(x) - 400) // 160 + 1
+    assert frames.shape == (n_frames, 512)
+    fr = np.stack([x[f * 160:f * 160 + 400] for f in range(n_frames)]).astype(np.float32)
+    fr = fr - fr.mean(axis=1, keepdims=True)
+    pre = fr.copy()
+    pre[:, 1:] = fr[:, 1:] - np.float32(0.97) * fr[:, :-1]
+    mine = np.pad(pre * R.povey_window(400), ((0, 0), (0, 112)))
+    assert np.abs(frames.numpy() - mine).max() <= 1e-6
+    # ... and the oracle's fbank is the log of (|rfft|^2 of exactly these frames) through the reference's integer-bin HTK bank
+    power = np.abs(np.fft.rfft(mine.astype(np.float64), axis=1)) ** 2
+    want = np.log(np.maximum(power @ R.mel_filters_htk(16000, 512, 80, 20.0, 8000.0).astype(np.float64), 1.1920929e-07))
+    assert np.abs(R.kaldi_fbank_camp_plus(x) - want).max() <= 2e-3   # fp32 restatement vs fp64 on un-clamped logs
