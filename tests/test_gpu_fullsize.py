@@ -99,3 +99,30 @@ def test_kokoro_full_length(ctx):
     alone = st.inverse(mag[5:6].contiguous(), ph[5:6].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(alone[0], y[5])
+
+
+def test_one_very_long_clip(ctx):
+    """Maximum sizes along the time axis: ONE 30-minute clip (28.8 M samples, 180 000 frames, 5625 tiles) through the Whisper,
+    Fun-ASR and Kaldi front ends -- the clip-global maximum, the tile walk and the 64-bit output offsets of a clip that is 60x
+    longer than the benchmark's -- and a 12.5-minute HiFT iSTFT (4.5 M frames).  Checked against the oracle on the whole clip."""
+    from mlx_swift_audio_b200 import api
+    n = 16000 * 60 * 30 + 77
+    x = synth.pcm(1, n, seed=404)[0]
+    got = api.whisperLogMelSpectrogram(x, nMels=80, ctx=ctx)
+    want = R.whisper_log_mel_spectrogram(x, 80)
+    assert got.shape == want.shape == (n // 160, 80)
+    assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) <= 1e-4
+    got = api.kaldiFbankCAMPPlus(x, ctx=ctx)
+    want = R.kaldi_fbank_camp_plus(x)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) <= 1e-4
+    got = api.preprocessAudio(x, applyNormalization=False, ctx=ctx)
+    want = R.preprocess_audio(x, apply_normalization=False)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want))) <= 1e-4
+    frames = 4_500_001
+    mag, ph = synth.mag_phase(1, 9, frames, seed=405)
+    w = R.hann_window_periodic(16)
+    y = api.istftHiFiGAN(mag, ph, 16, 4, w, ctx=ctx)
+    assert y.shape == (1, (frames - 1) * 4)
+    assert np.abs(y - R.istft_hifigan(mag, ph, 16, 4, w)).max() <= 1e-5
