@@ -374,6 +374,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   static_assert((!BAKED || FIXED) && FIXED == (OUT >= 0), "known banks come with compile-time POST and OUT");
   static_assert(BAKED || !FIXED || OUT == OUT_MT, "interpreted bank with compile-time POST: built for the (M, T') layout");
   constexpr bool EARLY_PREFETCH = !cplx;   // the PCM region is dead after stage A: refill it during stage B / mel / store
+  // LATE_TOP: the barrier that separates a tile from the previous one (every warp done reading the staged mel values out of the
+  // exchange buffer) sits in front of the tile's first exchange-buffer WRITE instead of at the loop top, so a warp that leaves
+  // the store phase early already loads and transforms its first stage-A item while the others finish.  The prefetched PCM is
+  // published by the post-mel barrier of the previous tile (cp.async wait in front of it).  Kaldi keeps the barrier at the top
+  // (its stage A has a barrier of its own for the frame means).
+  constexpr bool LATE_TOP = EARLY_PREFETCH && PRE != PRE_KALDI;
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
   static_assert(MEL == 0 || (SPEC == SK_POWER && FT == 32), "known banks are power-spectrum banks of the 32-frame plans");
   extern __shared__ __align__(16) float smem[];
@@ -426,6 +432,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     }
   }
   if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
+  if (LATE_TOP) {   // first tile's PCM and the tables
+    cp_async_commit_wait_all();
+    __syncthreads();
+  }
 
   while (clip < n_clips) {
     const int f0 = tile * FT;
@@ -447,8 +457,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     }
 
     // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
-    cp_async_commit_wait_all();
-    __syncthreads();
+    if (!LATE_TOP) {
+      cp_async_commit_wait_all();
+      __syncthreads();
+    }
 
     // Lanes past the clip's last frame recompute the last valid frame (same shared-memory words: a broadcast,
     // not a conflict), so that per-tile max / min need no lane masking.
@@ -486,6 +498,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
         float yr[H1 + 1], yi[H1 + 1];
         rdft(in, yr, yi);
+        if (LATE_TOP && n2 == wsub) __syncthreads();   // (every warp owns at least one stage-A item: all threads get here once per tile)
         float2* yb = s_y + n2 * FT + fl;
         yb[0] = make_float2(yr[0], yr[H1]);
         // the item's twiddles as whole float4 loads, all in flight before the first complex multiply
@@ -628,6 +641,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
+    if (LATE_TOP) cp_async_commit_wait_all();   // the next tile's PCM (issued after stage A) becomes visible with this barrier
     __syncthreads();
 
     // ---- 5. store of the staged tile (baked: plain transposing copy; otherwise log / floor / scale fused in) ----
