@@ -49,7 +49,8 @@ class FusedGather:
         api.whisperLogMelSpectrogram(x_local, 128, ctx=ctx, out=fg.local_out())     # x_local: this rank's shard_range() clips
         full = fg.finish()          # rank dst: torch view of all clips' features; None elsewhere
 
-    The buffer is reused by later calls; ``close()`` unmaps / frees it (collective: every rank calls it)."""
+    The buffer can be produced into again after ``reuse()`` (collective: the consumer calls it when it has finished reading);
+    ``close()`` unmaps / frees it (collective: every rank calls it)."""
 
     def __init__(self, ctx, n_clips: int, per_clip_shape, dst: int = 0, group=None):
         import ctypes as C
@@ -87,21 +88,31 @@ class FusedGather:
     def finish(self):
         """Orders every producer's stores before the consumer's reads: stream sync on each rank, then a barrier.
         -> on ``dst`` a zero-copy torch view (n_clips, *per_clip_shape) of the gathered features, None elsewhere."""
-        import torch
         import torch.distributed as dist
         self.ctx.sync()
         dist.barrier(group=self.group)
         if not self._owner:
             return None
+        return self._view(self.base, (self.n_clips,) + self.per_clip_shape)
+
+    def _view(self, base: int, shape):
+        """Zero-copy torch view of the consumer's buffer (overridden by the CPU test, whose "peer memory" is POSIX shared memory)."""
+        import torch
 
         class _View:   # __cuda_array_interface__ v2: torch wraps the allocation without copying
             pass
 
         v = _View()
-        v.__cuda_array_interface__ = {"shape": (self.n_clips,) + self.per_clip_shape, "typestr": "<f4", "data": (self.base, False),
-                                      "version": 2, "strides": None}
+        v.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (base, False), "version": 2, "strides": None}
         self._keep = v
         return torch.as_tensor(v, device=torch.device("cuda", self.ctx.device))
+
+    def reuse(self):
+        """Collective, before the buffer is produced into again: the consumer calls it once it is done reading the previous
+        result (its reads are ordered on the context's stream), the producers before their next front-end call."""
+        import torch.distributed as dist
+        self.ctx.sync()
+        dist.barrier(group=self.group)
 
     def close(self):
         import ctypes as C

@@ -80,16 +80,18 @@ def _fused_worker(rank, world, port, n_clips, q):
         fg2 = FusedGather(ctx, n_clips, ((n // 160 + 1 + 5) // 6, 560), dst=0)
         for rep in range(2):   # the buffers are reused
             if b > a:
-                api.whisperLogMelSpectrogram(xl, nMels=128, ctx=ctx, out=fg.local_out())
-                api.preprocessAudio(xl, ctx=ctx, out=fg2.local_out())
+                api.whisperLogMelSpectrogram(xl * (rep + 1), nMels=128, ctx=ctx, out=fg.local_out())
+                api.preprocessAudio(xl * (rep + 1), ctx=ctx, out=fg2.local_out())
             full, full2 = fg.finish(), fg2.finish()
             if rank == 0:
-                xa = torch.from_numpy(x).cuda()
+                xa = torch.from_numpy(x).cuda() * (rep + 1)
                 ok = ok and bool(torch.equal(full, api.whisperLogMelSpectrogram(xa, nMels=128, ctx=ctx)))
                 ok = ok and bool(torch.equal(full2, api.preprocessAudio(xa, ctx=ctx)))
                 torch.cuda.synchronize()
             else:
                 assert full is None and full2 is None
+            fg.reuse()    # the consumer is done reading: the producers may overwrite the buffers
+            fg2.reuse()
         fg.close()
         fg2.close()
         ctx.close()

@@ -121,6 +121,15 @@ def test_bad_arguments_are_rejected_without_a_gpu(built_lib):
     assert L.b2a_window(0, 0, out.ctypes.data_as(P)) != 0
     assert L.b2a_reflect_pad_index(100, 5, 8) == -1
     assert L.b2a_whisper_log_mel_spectrogram(None, None, 1, 16000, 80, 0, None, 0) != 0  # null context
+    # the ragged-batch and peer-memory entry points reject a null context / null buffers before any CUDA call
+    assert L.b2a_whisper_log_mel_spectrogram_ragged(None, None, 1, 16000, None, 80, 0, None, None, 0) != 0
+    assert L.b2a_funasr_preprocess_audio_ragged(None, None, 1, 16000, None, 80, 7, 6, 1, None, None, 0) != 0
+    assert L.b2a_kaldi_fbank_campplus_ragged(None, None, 1, 16000, None, 16000, 80, 25.0, 10.0, 0, None, None, 0) != 0
+    assert L.b2a_s3gen_mel_spectrogram_ragged(None, None, 1, 24000, None, 1920, 80, 24000, 480, 1920, 0, 8000, None, None, 0) != 0
+    p = C.c_void_p()
+    assert L.b2a_device_alloc(None, C.byref(p), 1024) != 0 and not p.value
+    assert L.b2a_ipc_open(None, b"\0" * 64, C.byref(p)) != 0
+    assert L.b2a_ipc_export(None, None, C.create_string_buffer(64)) != 0
 
 
 
