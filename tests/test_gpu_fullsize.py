@@ -131,3 +131,62 @@ def test_one_very_long_clip(ctx):
     y = api.istftHiFiGAN(mag, ph, 16, 4, w, ctx=ctx)
     assert y.shape == (1, (frames - 1) * 4)
     assert np.abs(y - R.istft_hifigan(mag, ph, 16, 4, w)).max() <= 1e-5
+
+
+def _pcm_batch(B, n, sr, seed):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = 0.1 * torch.randn((B, n), generator=g, device="cuda")
+    t = torch.arange(n, device="cuda", dtype=torch.float32) / float(sr)
+    for f in (220.0, 1000.0, 3300.0):
+        x += 0.2 * torch.sin(2 * np.pi * f * t[None, :] + 2 * np.pi * torch.rand((B, 1), generator=g, device="cuda"))
+    x.clamp_(-1.0, 1.0)
+    x[:, n - n // 10:] = 0.0
+    x[3] *= 1e-3   # a quiet clip: per-clip statistics must stay per clip
+    return x
+
+
+def test_funasr_kaldi_s3gen_full_length_batches(ctx):
+    """BASELINE configs 3a / 3b / 4 at their full clip lengths (20 s @16 kHz, 10 s @24 kHz) in batches large enough that every
+    persistent CTA walks several clips: batch invariance bit for bit (CMVN / mean-norm statistics are per clip), finiteness, the
+    defining property of each normalisation (zero column mean; unit column variance for CMVN), spot checks against the oracle."""
+    import torch
+    from mlx_swift_audio_b200 import api
+    B, n = 64, 320000
+    x = _pcm_batch(B, n, 16000, 11)
+    # 3a: Fun-ASR preprocessAudio (log-mel + LFR 7/6 + per-utterance CMVN)
+    got = api.preprocessAudio(x)
+    torch.cuda.synchronize()
+    assert got.shape == (B, 334, 560) and bool(torch.all(torch.isfinite(got)))
+    assert float(got.mean(dim=1).abs().max()) <= 2e-4
+    assert float((got.var(dim=1, unbiased=False).sqrt() - 1.0).abs().max()) <= 2e-3
+    for b in (0, 3, B - 1):
+        alone = api.preprocessAudio(x[b:b + 1].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(alone[0], got[b]), f"funasr clip {b} differs between batch and single run"
+    want = R.preprocess_audio(x[5].cpu().numpy())
+    assert np.max(np.abs(got[5].cpu().numpy() - want) / np.maximum(1.0, np.abs(want))) <= 2e-4
+    # 3b: Kaldi fbank + CAM++ mean normalisation
+    got = api.kaldiFbankCAMPPlus(x, meanNorm=True)
+    torch.cuda.synchronize()
+    assert got.shape == (B, 1998, 80) and bool(torch.all(torch.isfinite(got)))
+    assert float(got.mean(dim=1).abs().max()) <= 2e-4
+    for b in (0, 3, B - 1):
+        alone = api.kaldiFbankCAMPPlus(x[b:b + 1].contiguous(), meanNorm=True)
+        torch.cuda.synchronize()
+        assert torch.equal(alone[0], got[b]), f"kaldi clip {b} differs between batch and single run"
+    want = R.kaldi_fbank_mean_norm(R.kaldi_fbank_camp_plus(x[5].cpu().numpy()))
+    assert np.max(np.abs(got[5].cpu().numpy() - want) / np.maximum(1.0, np.abs(want))) <= 2e-4
+    # 4: S3Gen 24 kHz mel
+    B, n = 64, 240000
+    y = _pcm_batch(B, n, 24000, 12)
+    got = api.s3genMelSpectrogram(y)
+    torch.cuda.synchronize()
+    assert got.shape == (B, 80, 500) and bool(torch.all(torch.isfinite(got)))
+    assert float(got.min()) >= np.log(1e-5) - 1e-5          # ln(max(., 1e-5)) floor
+    for b in (0, 3, B - 1):
+        alone = api.s3genMelSpectrogram(y[b:b + 1].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(alone[0], got[b]), f"s3gen clip {b} differs between batch and single run"
+    want = R.s3gen_mel_spectrogram(y[4:6].cpu().numpy())
+    assert np.max(np.abs(got[4:6].cpu().numpy() - want) / np.maximum(1.0, np.abs(want))) <= 1e-4
