@@ -175,8 +175,14 @@ def test_funasr_kaldi_s3gen_full_length_batches(ctx):
         alone = api.kaldiFbankCAMPPlus(x[b:b + 1].contiguous(), meanNorm=True)
         torch.cuda.synchronize()
         assert torch.equal(alone[0], got[b]), f"kaldi clip {b} differs between batch and single run"
-    want = R.kaldi_fbank_mean_norm(R.kaldi_fbank_camp_plus(x[5].cpu().numpy()))
-    assert np.max(np.abs(got[5].cpu().numpy() - want) / np.maximum(1.0, np.abs(want))) <= 2e-4
+    # (un-clamped logs: fp64 truth and the fp32 oracle's own error are the yardstick)
+    x5 = x[5].cpu().numpy()
+    want = R.kaldi_fbank_mean_norm(R.kaldi_fbank_camp_plus(x5))
+    truth = R.kaldi_fbank_mean_norm(R.kaldi_fbank_camp_plus(x5, dt=np.float64))
+    scale = np.maximum(1.0, np.abs(truth))
+    e_oracle = float(np.max(np.abs(want - truth) / scale))
+    e_gpu = float(np.max(np.abs(got[5].cpu().numpy() - truth) / scale))
+    assert e_gpu <= max(2e-4, 4.0 * e_oracle), (e_gpu, e_oracle)
     # 4: S3Gen 24 kHz mel
     B, n = 64, 240000
     y = _pcm_batch(B, n, 24000, 12)
