@@ -198,8 +198,8 @@ B2A_API int b2a_voice_encoder_melspectrogram(b2a_ctx* ctx, const float* wav, int
 /* ---------------------------------------------------------------------------------------
  * ragged batches: per-clip lengths ("optional per-clip lengths[B]")
  *
- * The reference helpers take one clip, so clips of different lengths are simply separate calls there.  These variants run
- * a whole batch of unequal clips in ONE launch: clip b holds lengths[b] (host array, 1 <= lengths[b] <= n_samples) valid
+ * The reference helpers take one clip, so clips of different lengths are simply separate calls there.  These variants (every mel front end)
+ * run a whole batch of unequal clips in ONE launch: clip b holds lengths[b] (host array, 1 <= lengths[b] <= n_samples) valid
  * samples at the start of row b of the (batch, n_samples) input, and every clip is processed exactly as the single-clip
  * reference call on audio[b, :lengths[b]] would process it (padding, frame count, per-clip max / CMVN / mean over ITS frames).
  * Output strides are those of an n_samples-long clip -- (batch, frames(n_samples), n_mels) etc. -- rows past a clip's own
@@ -209,6 +209,11 @@ B2A_API int b2a_whisper_log_mel_spectrogram_ragged(b2a_ctx* ctx, const float* au
                                                    int n_mels, int64_t padding, float* out, int64_t* out_frames, int space);
 B2A_API int b2a_log_mel_spectrogram_chatterbox_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
                                                       int n_mels, int64_t padding, float* out, int64_t* out_frames, int space);
+B2A_API int b2a_funasr_log_mel_spectrogram_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                                  int n_mels, float* out, int64_t* out_frames, int space);
+B2A_API int b2a_voice_encoder_melspectrogram_ragged(b2a_ctx* ctx, const float* wav, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                                    const b2a_voice_enc_config* cfg /* NULL = defaults */, float* out, int64_t* out_frames,
+                                                    int space);
 B2A_API int b2a_funasr_preprocess_audio_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
                                                int n_mels, int lfr_m, int lfr_n, int apply_normalization, float* out, int64_t* out_rows, int space);
 B2A_API int b2a_kaldi_fbank_campplus_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,

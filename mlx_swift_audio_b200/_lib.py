@@ -65,6 +65,8 @@ SIGNATURES = {
     "b2a_log_mel_spectrogram_chatterbox": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_void_p, C.c_int]),
     "b2a_whisper_log_mel_spectrogram_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, _i64, C.c_void_p, C.POINTER(_i64), C.c_int]),
     "b2a_log_mel_spectrogram_chatterbox_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, _i64, C.c_void_p, C.POINTER(_i64), C.c_int]),
+    "b2a_funasr_log_mel_spectrogram_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, C.c_void_p, C.POINTER(_i64), C.c_int]),
+    "b2a_voice_encoder_melspectrogram_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.POINTER(VoiceEncConfig), C.c_void_p, C.POINTER(_i64), C.c_int]),
     "b2a_funasr_preprocess_audio_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_i64), C.c_int]),
     "b2a_kaldi_fbank_campplus_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(_i64), C.c_int]),
     "b2a_s3gen_mel_spectrogram_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(_i64), C.c_int]),

@@ -492,6 +492,34 @@ def kaldiFbankCAMPPlusRagged(audio, lengths, sampleRate: int = 16000, numMelBins
     return out, rows
 
 
+def funASRLogMelSpectrogramRagged(audio, lengths, nMels: int = 80, ctx: Context | None = None):
+    """funASRLogMelSpectrogram (FunASRAudio.swift:57-94) per clip -> ((B, T'max, nMels), frames per clip)"""
+    a, c, ln, rows, lp, rp = _ragged(audio, lengths, ctx)
+    b, n = a.shape
+    frames = int(c.lib.b2a_funasr_num_frames(n))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, frames, nMels))
+    c.check(c.lib.b2a_funasr_log_mel_spectrogram_ragged(c.h, a.ptr, b, n, lp, nMels, _ptr(out), rp, a.space))
+    return out, rows
+
+
+def voiceEncoderMelspectrogramRagged(wav, lengths, config: L.VoiceEncConfig | None = None, ctx: Context | None = None):
+    """voiceEncoderMelspectrogram (VoiceEncoderMelspec.swift:17-68) per clip -> ((B, numMels, T'max), frames per clip)"""
+    cfg = config
+    if cfg is None:
+        cfg = L.VoiceEncConfig()
+        L.load().b2a_voice_enc_config_default(C.byref(cfg))
+    a, c, ln, rows, lp, rp = _ragged(wav, lengths, ctx)
+    b, n = a.shape
+    frames = int(c.lib.b2a_stft_num_frames(n, cfg.n_fft, cfg.hop_size, 1))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    out = a.empty((b, cfg.num_mels, frames))
+    c.check(c.lib.b2a_voice_encoder_melspectrogram_ragged(c.h, a.ptr, b, n, lp, C.byref(cfg), _ptr(out), rp, a.space))
+    return out, rows
+
+
 def s3genMelSpectrogramRagged(y, lengths, nFft: int = 1920, numMels: int = 80, samplingRate: int = 24000, hopSize: int = 480,
                               winSize: int = 1920, fmin: int = 0, fmax: int = 8000, ctx: Context | None = None):
     """s3genMelSpectrogram (S3GenMel.swift:43-102) per clip -> ((B, numMels, T'max), frames per clip)"""

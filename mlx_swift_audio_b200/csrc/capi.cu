@@ -784,6 +784,12 @@ int b2a_funasr_preprocess_audio(b2a_ctx* c, const float* audio, int64_t batch, i
   return funasr_common(c, audio, batch, n_samples, n_mels, lfr_m, lfr_n, 1, apply_normalization != 0, out, space);
 }
 
+int b2a_funasr_log_mel_spectrogram_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_mels,
+                                          float* out, int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return funasr_common(c, audio, batch, n_samples, n_mels, 0, 0, 0, 0, out, space, lengths, out_frames);
+}
+
 int b2a_funasr_preprocess_audio_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_mels,
                                        int lfr_m, int lfr_n, int apply_normalization, float* out, int64_t* out_rows, int space) {
   if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
@@ -931,8 +937,8 @@ int b2a_s3gen_mel_spectrogram_ragged(b2a_ctx* c, const float* y, int64_t batch, 
   return s3gen_common(c, y, batch, n_samples, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, out, space, lengths, out_frames);
 }
 
-int b2a_voice_encoder_melspectrogram(b2a_ctx* c, const float* wav, int64_t batch, int64_t n_samples, const b2a_voice_enc_config* cfg_in,
-                                     float* out, int space) {
+static int voice_encoder_common(b2a_ctx* c, const float* wav, int64_t batch, int64_t n_samples, const b2a_voice_enc_config* cfg_in,
+                                float* out, int space, const int64_t* lengths, int64_t* out_rows) {
   int rc = check_common(c, wav, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   b2a_voice_enc_config cfg;
@@ -963,7 +969,19 @@ int b2a_voice_encoder_melspectrogram(b2a_ctx* c, const float* wav, int64_t batch
   }
   p.out_mode = OUT_MT;
   p.n_frames = frames;
-  return run_preset(c, p, wav, batch, n_samples, out, space);
+  Ragged rg{lengths, [&](int64_t len) { return b2a_stft_num_frames(len, cfg.n_fft, cfg.hop_size, 1); }, out_rows};
+  return run_preset(c, p, wav, batch, n_samples, out, space, lengths ? &rg : nullptr);
+}
+
+int b2a_voice_encoder_melspectrogram(b2a_ctx* c, const float* wav, int64_t batch, int64_t n_samples, const b2a_voice_enc_config* cfg_in,
+                                     float* out, int space) {
+  return voice_encoder_common(c, wav, batch, n_samples, cfg_in, out, space, nullptr, nullptr);
+}
+
+int b2a_voice_encoder_melspectrogram_ragged(b2a_ctx* c, const float* wav, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                            const b2a_voice_enc_config* cfg_in, float* out, int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return voice_encoder_common(c, wav, batch, n_samples, cfg_in, out, space, lengths, out_frames);
 }
 
 int b2a_stft(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, const float* window, int win_len, int n_fft, int hop,

@@ -32,3 +32,35 @@ int main() {
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "b200audio" in r.stdout
+
+
+def test_c_header_is_plain_c99(built_lib):
+    """include/b200audio.h is the drop-in boundary: it has to compile as C (no C++-isms), and a C program has to link
+    against the shared library and call the host-side functions."""
+    src = r'''
+#include "b200audio.h"
+#include <stdio.h>
+int main(void) {
+  float w[16];
+  unsigned char handle[B2A_IPC_HANDLE_BYTES];
+  b2a_ctx* ctx = 0;
+  int64_t lengths[2] = {4000, 3000}, rows[2];
+  if (b2a_window(B2A_WIN_HANN_PERIODIC, 16, w) != B2A_OK) return 1;
+  if (b2a_whisper_num_frames(480000, 0) != 3000) return 2;
+  if (b2a_reflect_pad_index(0, 10, 3) != 3) return 3;
+  /* no context: every compute / peer-memory entry point must refuse, not crash */
+  if (b2a_whisper_log_mel_spectrogram_ragged(ctx, w, 2, 4000, lengths, 80, 0, w, rows, B2A_HOST) == B2A_OK) return 4;
+  if (b2a_ipc_export(ctx, w, handle) == B2A_OK) return 5;
+  printf("%s %.3f\n", b2a_version(), w[4]);
+  return 0;
+}
+'''
+    d = tempfile.mkdtemp()
+    c, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
+    open(c, "w").write(src)
+    libdir = os.path.join(ROOT, "mlx_swift_audio_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+                    "-L", libdir, "-l:libb200audio.so", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout + r.stderr)
+    assert "b200audio" in r.stdout

@@ -82,6 +82,20 @@ def test_funasr_ragged(api, ctx):
     _check(got2, rows2, [R.preprocess_audio(x[b, :n], apply_normalization=False) for b, n in enumerate(LENGTHS)], "funasr LFR ragged", 0)
 
 
+def test_funasr_log_mel_and_voice_encoder_ragged(api, ctx):
+    x = _batch(LENGTHS, seed=29)
+    got, rows = api.funASRLogMelSpectrogramRagged(x, LENGTHS, ctx=ctx)
+    _check(got, rows, [R.funasr_log_mel_spectrogram(x[b, :n]) for b, n in enumerate(LENGTHS)], "funasr log-mel ragged", 0)
+    got, rows = api.voiceEncoderMelspectrogramRagged(x, LENGTHS, ctx=ctx)
+    want = [R.voice_encoder_melspectrogram(x[b, :n]) for b, n in enumerate(LENGTHS)]
+    g = np.asarray(got)
+    for b, w in enumerate(want):   # linear-power mel (no log): relative to the clip's peak like the non-ragged test
+        t = w.shape[1]
+        assert rows[b] == t
+        assert np.abs(g[b, :, :t] - w).max() <= 1e-4 * max(np.abs(w).max(), 1e-30), f"voice encoder ragged clip {b}"
+        assert not np.any(g[b, :, t:])
+
+
 def test_kaldi_ragged(api, ctx):
     lengths = [n for n in LENGTHS if n >= 400]
     x = _batch(lengths, seed=13)
