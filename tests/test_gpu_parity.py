@@ -351,3 +351,42 @@ def test_device_tensors_roundtrip(api, ctx):
     y = api.istftHiFiGAN(torch.from_numpy(mag).cuda(), torch.from_numpy(ph).cuda(), 16, 4, w)
     torch.cuda.synchronize()
     assert np.abs(y.cpu().numpy() - R.istft_hifigan(mag, ph, 16, 4, w)).max() <= ISTFT_ATOL
+
+
+def test_contexts_on_concurrent_host_threads(api):
+    """The reference's helpers are re-entrant free functions called from several Swift actors ("Threading"): one
+    context per host thread, no shared mutable state.  Four threads with their own contexts hammer different front ends at
+    once; every result must equal the single-threaded one bit for bit."""
+    import threading
+    x = synth.pcm(4, 16000 * 4 + 321, seed=61)
+    mag, ph = synth.mag_phase(2, 9, 3001, seed=62)
+    w16 = R.hann_window_periodic(16)
+    jobs = [
+        lambda c: api.whisperLogMelSpectrogram(x, nMels=128, ctx=c),
+        lambda c: api.preprocessAudio(x, ctx=c),
+        lambda c: api.kaldiFbankCAMPPlus(x, meanNorm=True, ctx=c),
+        lambda c: api.istftHiFiGAN(mag, ph, 16, 4, w16, ctx=c),
+    ]
+    ref_ctx = api.Context(0)
+    want = [np.array(j(ref_ctx)) for j in jobs]
+    ref_ctx.close()
+    errors = []
+
+    def worker(i):
+        try:
+            c = api.Context(0)
+            for rep in range(15):
+                k = (i + rep) % len(jobs)
+                got = np.array(jobs[k](c))
+                if not np.array_equal(got, want[k]):
+                    errors.append((i, rep, k))
+            c.close()
+        except Exception as e:   # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
