@@ -196,3 +196,30 @@ def test_funasr_kaldi_s3gen_full_length_batches(ctx):
         assert torch.equal(alone[0], got[b]), f"s3gen clip {b} differs between batch and single run"
     want = R.s3gen_mel_spectrogram(y[4:6].cpu().numpy())
     assert np.max(np.abs(got[4:6].cpu().numpy() - want) / np.maximum(1.0, np.abs(want))) <= 1e-4
+
+
+def test_repeated_runs_are_bit_identical(ctx):
+    """Determinism under load: the front-end kernels reuse shared memory several times per tile (PCM tile, exchange buffer, spectrum,
+    staged mel values) behind four CTA barriers, the iSTFT overlaps frames through a shared tile; a missing barrier shows up as
+    run-to-run differences long before it shows up as a tolerance failure.  20 back-to-back runs of the large batches must agree
+    bit for bit (compute-sanitizer is not available on the GPU pool)."""
+    import torch
+    from mlx_swift_audio_b200 import api
+    x = _pcm_batch(48, 480000, 16000, 21)
+    first = api.whisperLogMelSpectrogram(x, nMels=128)
+    firstk = api.kaldiFbankCAMPPlus(x[:, :320000].contiguous(), meanNorm=True)
+    firstf = api.preprocessAudio(x[:, :320000].contiguous())
+    y = _pcm_batch(16, 240000, 24000, 22)
+    firsts = api.s3genMelSpectrogram(y)
+    g = torch.Generator(device="cuda").manual_seed(23)
+    mag = torch.exp(torch.randn((8, 9, 180001), generator=g, device="cuda") - 2.0)
+    ph = torch.sin(2.0 * torch.randn((8, 9, 180001), generator=g, device="cuda"))
+    w16 = R.hann_window_periodic(16)
+    firsti = api.istftHiFiGAN(mag, ph, 16, 4, w16)
+    torch.cuda.synchronize()
+    for rep in range(20):
+        assert torch.equal(api.whisperLogMelSpectrogram(x, nMels=128), first), f"whisper run {rep}"
+        assert torch.equal(api.kaldiFbankCAMPPlus(x[:, :320000].contiguous(), meanNorm=True), firstk), f"kaldi run {rep}"
+        assert torch.equal(api.preprocessAudio(x[:, :320000].contiguous()), firstf), f"funasr run {rep}"
+        assert torch.equal(api.s3genMelSpectrogram(y), firsts), f"s3gen run {rep}"
+        assert torch.equal(api.istftHiFiGAN(mag, ph, 16, 4, w16), firsti), f"istft run {rep}"
