@@ -291,6 +291,7 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
   std::vector<int64_t> clip_frames;
   if (rg) {
     if (p.out_mode == OUT_COMPLEX) return fail(c, B2A_E_UNSUPPORTED, "ragged batches are built for the mel front ends only");
+    if (n_samples > 0x7fffffffLL) return fail(c, B2A_E_BAD_ARG, "ragged batches hold clips of fewer than 2^31 samples");   // (32-bit clip table)
     clip_frames.resize(size_t(batch));
     for (int64_t b = 0; b < batch; ++b) {
       const int64_t len = rg->lengths[b];
