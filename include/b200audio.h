@@ -263,6 +263,13 @@ B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const 
  * istftHiFiGAN, clip(output, -audio_limit, audio_limit).  Codec/S3Gen/HiFiGAN.swift:577-589 (audio_limit 0.99). */
 B2A_API int b2a_hift_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t batch, int64_t n_frames, int n_fft, int hop,
                                 const float* window, float audio_limit, float* out, int space);
+/* The same followed by the 20 ms fade-in of S3Gen.callAsFunction (Codec/S3Gen/S3Gen.swift:259-262, 284-289), still one kernel:
+ * the first fade_len samples of every clip are multiplied by fade[] (host, fade_len floats) when the clip has at least fade_len
+ * samples.  b2a_s3gen_trim_fade writes the reference's window, zeros(sr/50) ++ (cos(linspace(pi, 0, sr/50)) + 1) / 2, into
+ * out[2 * (sr / 50)] (pure host function). */
+B2A_API int b2a_hift_head_istft_fade(b2a_ctx* ctx, const float* conv_out, int64_t batch, int64_t n_frames, int n_fft, int hop,
+                                     const float* window, float audio_limit, const float* fade, int64_t fade_len, float* out, int space);
+B2A_API int b2a_s3gen_trim_fade(int sampling_rate, float* out);
 /* Kokoro head: x = conv_post output (batch, filter_length + 2, frames).  spec = exp(x[:, :F]), phase = sin(x[:, F:]),
  * MLXSTFT.inverse.  TTS/Kokoro/Decoder/Generator.swift:182-190.  out (batch, 1, (frames-1)*hop). */
 B2A_API int b2a_kokoro_head_istft(b2a_ctx* ctx, const float* conv_out, int64_t batch, int64_t n_frames, int filter_length,

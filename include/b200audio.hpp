@@ -128,6 +128,15 @@ class Context {
     check(b2a_hift_head_istft(c_, convOut.data.data(), b, frames, nFft, hopLength, window.data(), audioLimit, out.data.data(), B2A_HOST));
     return out;
   }
+  // ... followed by the fade-in of S3Token2Wav.callAsFunction (Codec/S3Gen/S3Gen.swift:284-289); trimFade from s3genTrimFade()
+  Array hiftHeadIstftFade(const Array& convOut, int nFft, int hopLength, const std::vector<float>& window, const std::vector<float>& trimFade,
+                          float audioLimit = 0.99f) const {
+    const int64_t b = convOut.shape[0], frames = convOut.shape[2];
+    Array out({b, (frames - 1) * hopLength});
+    check(b2a_hift_head_istft_fade(c_, convOut.data.data(), b, frames, nFft, hopLength, window.data(), audioLimit, trimFade.data(),
+                                   int64_t(trimFade.size()), out.data.data(), B2A_HOST));
+    return out;
+  }
   // Tail of the Kokoro generator, TTS/Kokoro/Decoder/Generator.swift:182-190
   Array kokoroHeadIstft(const Array& convOut, int filterLength = 20, int hopLength = 5, int winLength = 20) const {
     const int64_t b = convOut.shape[0], frames = convOut.shape[2];
@@ -191,6 +200,11 @@ class Context {
 };
 
 // host-only helpers
+inline std::vector<float> s3genTrimFade(int samplingRate = 24000) {  // Codec/S3Gen/S3Gen.swift:259-262
+  std::vector<float> f(size_t(2 * (samplingRate / 50)));
+  if (b2a_s3gen_trim_fade(samplingRate, f.data()) != B2A_OK) throw Error(B2A_E_BAD_ARG, "bad sampling rate");
+  return f;
+}
 inline std::vector<float> hannWindowPeriodic(int size) {  // Codec/S3Gen/HiFiGAN.swift:15-20
   std::vector<float> w(size);
   b2a_window(B2A_WIN_HANN_PERIODIC, size, w.data());

@@ -713,6 +713,25 @@ def hiftHeadIstft(convOut, nFft: int, hopLength: int, window, audioLimit: float 
                        lambda b, n: (b, n))
 
 
+def s3genTrimFade(samplingRate: int = 24000) -> np.ndarray:
+    """Fade-in window of S3Token2Wav (Codec/S3Gen/S3Gen.swift:259-262): zeros(sr/50) ++ (cos(linspace(pi, 0, sr/50)) + 1) / 2"""
+    out = np.empty(2 * (samplingRate // 50), np.float32)
+    rc = L.load().b2a_s3gen_trim_fade(samplingRate, _fptr(out))
+    if rc != L.B2A_OK:
+        _raise(rc, "bad sampling rate")
+    return out
+
+
+def hiftHeadIstftFade(convOut, nFft: int, hopLength: int, window, trimFade, audioLimit: float = 0.99, ctx: Context | None = None):
+    """hiftHeadIstft followed by ``result[..., :fadeLen] *= trimFade`` of S3Token2Wav.callAsFunction (S3Gen.swift:284-289), one kernel."""
+    w = np.ascontiguousarray(window, np.float32)
+    fd = np.ascontiguousarray(trimFade, np.float32)
+    return _head_istft(convOut, nFft, hopLength, ctx,
+                       lambda c, h, b, frames, out: c.lib.b2a_hift_head_istft_fade(c.h, h.ptr, b, frames, nFft, hopLength, _fptr(w),
+                                                                                   float(audioLimit), _fptr(fd), len(fd), _ptr(out), h.space),
+                       lambda b, n: (b, n))
+
+
 def kokoroHeadIstft(convOut, filterLength: int = 20, hopLength: int = 5, winLength: int = 20, ctx: Context | None = None):
     """Tail of the Kokoro generator (TTS/Kokoro/Decoder/Generator.swift:182-190) as one kernel: exp / sin split of the
     conv_post output (B, filterLength+2, frames) and MLXSTFT.inverse.  -> (B, 1, (frames-1)*hop)"""

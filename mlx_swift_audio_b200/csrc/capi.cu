@@ -51,6 +51,8 @@ struct b2a_ctx {
   std::map<std::string, BankStorage> banks;      // like the reference's MelFilterCache (CAMPPlus.swift:111-131), per context
   std::map<std::string, std::vector<float>> windows;
   DevBuf in[kSlots][2], out[kSlots][2];          // host-pipeline staging
+  DevBuf fade;                                   // fade-in window of the fused vocoder head (device copy of fade_host)
+  std::vector<float> fade_host;
   DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3 / 4: ragged clip / tile tables
   int64_t chunk_clip0 = 0;                       // first clip of the chunk run_batched is handing to the body
   int* h_flag = nullptr;                         // pinned
@@ -474,6 +476,7 @@ int b2a_ctx_destroy(b2a_ctx* c) {
   }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->fade.p) cudaFree(c->fade.p);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1065,13 +1068,25 @@ int b2a_kokoro_stft_transform(b2a_ctx* c, const float* x, int64_t batch, int64_t
 // head != 0: `mag` is the vocoder's convolution output (batch, 2F, frames), `phase` is unused (exp / sin are formed in the kernel)
 static int istft_common(b2a_ctx* c, const float* mag, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,
                         const float* window, int use_clip_lo, float clip_hi, int norm, int unwrap, float* out, int space,
-                        int head = 0, float out_limit = 0.0f) {
+                        int head = 0, float out_limit = 0.0f, const float* fade = nullptr, int64_t fade_len = 0) {
   int rc = check_common(c, mag, out, batch, n_frames);
   if (rc != B2A_OK) return rc;
   if ((!head && !phase) || !window) return fail(c, B2A_E_BAD_ARG, "null buffer");
   if (n_frames < 2) return fail(c, B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames");
+  if (fade_len < 0 || fade_len > 0x7fffffffLL || (fade_len > 0 && !fade)) return fail(c, B2A_E_BAD_ARG, "bad fade window");
   Guard g(c);
   if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  // S3Gen applies its fade only to waveforms at least as long as the window (S3Gen.swift:286)
+  const bool use_fade = head && fade_len > 0 && (n_frames - 1) * int64_t(hop) >= fade_len;
+  if (use_fade && (c->fade_host.size() != size_t(fade_len) || std::memcmp(c->fade_host.data(), fade, sizeof(float) * size_t(fade_len)) != 0)) {
+    // a new window (once per model in practice): synchronous upload -- earlier kernels may still read the old table
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return cu(c, e, "sync");
+    c->fade_host.clear();
+    if ((rc = ensure(c, c->fade, sizeof(float) * size_t(fade_len))) != B2A_OK) return rc;
+    if ((e = cudaMemcpy(c->fade.p, fade, sizeof(float) * size_t(fade_len), cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "fade upload");
+    c->fade_host.assign(fade, fade + fade_len);
+  }
   const size_t per_in = size_t(n_fft / 2 + 1) * n_frames * (head ? 2 : 1);
   const size_t per_out = size_t(n_frames - 1) * hop;
   Body body = [&](const float* d_mag, const float* d_phase, float* d_out, float*, int64_t n, int slot) -> int {
@@ -1079,6 +1094,10 @@ static int istft_common(b2a_ctx* c, const float* mag, const float* phase, int64_
     a.n_fft = n_fft; a.hop = hop; a.mag = d_mag; a.phase = d_phase; a.batch = n; a.n_frames = n_frames; a.window = window;
     a.use_clip_lo = use_clip_lo; a.clip_lo = 0.0f; a.clip_hi = clip_hi; a.norm = norm; a.out = d_out;
     a.head = head; a.out_limit = out_limit;
+    if (use_fade) {
+      a.fade = static_cast<const float*>(c->fade.p);
+      a.fade_len = int(fade_len);
+    }
     if (unwrap && !head) {   // (head: phase = sin(.) in [-1, 1], unwrap is the identity)
       int r;
       if ((r = ensure(c, c->scratch[slot][0], sizeof(int))) != B2A_OK) return r;
@@ -1102,6 +1121,26 @@ int b2a_hift_head_istft(b2a_ctx* c, const float* conv_out, int64_t batch, int64_
                         float audio_limit, float* out, int space) {
   // magnitude = exp(h[:, :F]), phase = sin(h[:, F:]), istftHiFiGAN, clip to +-audioLimit (HiFiGAN.swift:577-589)
   return istft_common(c, conv_out, nullptr, batch, n_frames, n_fft, hop, window, 0, 100.0f, NORM_WSQ_FLOOR, 0, out, space, 1, audio_limit);
+}
+
+int b2a_hift_head_istft_fade(b2a_ctx* c, const float* conv_out, int64_t batch, int64_t n_frames, int n_fft, int hop, const float* window,
+                             float audio_limit, const float* fade, int64_t fade_len, float* out, int space) {
+  // ... followed by result[..., 0 ..< fadeLen] *= trimFade of S3Gen.callAsFunction (S3Gen.swift:284-289), in the same kernel
+  return istft_common(c, conv_out, nullptr, batch, n_frames, n_fft, hop, window, 0, 100.0f, NORM_WSQ_FLOOR, 0, out, space, 1, audio_limit,
+                      fade, fade_len);
+}
+
+int b2a_s3gen_trim_fade(int sampling_rate, float* out) {
+  // zeros(nTrim) ++ (cos(linspace(pi, 0, nTrim)) + 1) / 2, nTrim = sr / 50 (S3Gen.swift:259-262)
+  const int n = sampling_rate / 50;
+  if (n < 2 || !out) return B2A_E_BAD_ARG;
+  for (int i = 0; i < n; ++i) out[i] = 0.0f;
+  const float pi = 3.14159265358979323846f;
+  for (int i = 0; i < n; ++i) {
+    const float t = pi + float(i) * ((0.0f - pi) / float(n - 1));   // fp32 linspace
+    out[n + i] = (cosf(t) + 1.0f) / 2.0f;
+  }
+  return B2A_OK;
 }
 
 int b2a_kokoro_head_istft(b2a_ctx* c, const float* conv_out, int64_t batch, int64_t n_frames, int filter_length, int hop_length,

@@ -146,6 +146,8 @@ struct IstftArgs {
   float* scratch_phase = nullptr; // device, same size as phase, when unwrap != 0
   int head = 0;                   // 1: `mag` is the vocoder's conv output (batch, 2F, frames); exp / sin formed in the kernel, `phase` unused
   float out_limit = 0.0f;         // head: clip the waveform to +-out_limit (0 = none)
+  const float* fade = nullptr;    // head: device, fade_len floats multiplying the start of every clip's waveform (null = none)
+  int fade_len = 0;
 };
 int launch_istft(const IstftArgs& a, void* stream, int* launches, std::string* err);
 

@@ -114,6 +114,8 @@ struct IstftParams {
   int use_clip_lo, norm;
   int* unwrap_flag;       // set to 1 if any |dphi| >= pi was seen (Kokoro optimistic path); may be null
   float out_limit;        // HEAD: clip(output, -out_limit, out_limit) (HiFiGAN.swift:587); <= 0 = none
+  const float* fade;      // HEAD: fade-in window multiplying the first fade_len output samples of every clip (S3Gen.swift:284-289)
+  int fade_len;           //       0 = none
   float wn[NFFT];         // window[n] / NFFT
   float wenv[NFFT];       // window^2 (HiFT/CosyVoice3) or window (Kokoro): envelope contributions
   float inv_env[HOP];     // interior 1 / envelope
@@ -293,6 +295,12 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
 #pragma unroll
     for (int i = 0; i < HOP; ++i) o[i] = fminf(fmaxf(o[i], -prm.out_limit), prm.out_limit);
   }
+  if (HEAD && emit && (s - R / 2) * HOP < prm.fade_len) {   // only the first blocks of a clip get here
+    const int t0 = (s - R / 2) * HOP;
+#pragma unroll
+    for (int i = 0; i < HOP; ++i)
+      if (t0 + i < prm.fade_len) o[i] *= __ldg(prm.fade + t0 + i);
+  }
   float* __restrict__ dst = prm.out + clip * prm.out_len;
   if (HOP == 4) {
     if (emit) {
@@ -446,6 +454,8 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   prm.norm = a.norm;
   prm.unwrap_flag = unwrap_flag;
   prm.out_limit = a.out_limit;
+  prm.fade = a.fade;
+  prm.fade_len = a.head && a.fade != nullptr ? a.fade_len : 0;
   if (a.head) {   // one tensor (batch, 2F, frames): the phase rows follow the magnitude rows of the same clip
     prm.phase = a.mag + (long long)F * a.n_frames;
   }

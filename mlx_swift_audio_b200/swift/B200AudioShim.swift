@@ -179,6 +179,8 @@ public final class B200Audio {
   // producer processes (any host channel); each producer calls b2a_ipc_open and passes `peer + firstClip * clipBytes` as the `out`
   // pointer of a B2A_DEVICE call -- the kernel's stores then land in the consumer's HBM over NVLink (INTEGRATION.md section 6).
 
+  // hiftHeadIstftFade(convOut:..., trimFade:) binds b2a_hift_head_istft_fade (the head plus `result[0..., 0 ..< fadeLen] *= trimFade`
+  // of S3Token2Wav.callAsFunction, S3Gen.swift:284-289); b2a_s3gen_trim_fade builds `_trimFade` (S3Gen.swift:259-262).
   // kokoroHeadIstft binds b2a_kokoro_head_istft like hiftHeadIstft.
   // cosyVoice3Stft / cosyVoice3Istft, MLXSTFT.transform / .inverse, funASRLogMelSpectrogram, applyLFR, applyCMVN,
   // voiceEncoderMelspectrogram and stft bind b2a_cosyvoice3_*, b2a_kokoro_stft_*, b2a_funasr_log_mel_spectrogram,

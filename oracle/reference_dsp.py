@@ -659,6 +659,22 @@ def hift_head_istft(conv_out, n_fft: int, hop: int, window, audio_limit: float =
     return np.clip(y, dt(-audio_limit), dt(audio_limit)).astype(dt)
 
 
+def s3gen_trim_fade(sampling_rate: int = 24000, dt=F32) -> np.ndarray:
+    """Codec/S3Gen/S3Gen.swift:259-262: nTrim = sr / 50; zeros(nTrim) ++ (cos(linspace(pi, 0, nTrim)) + 1) / 2"""
+    n = sampling_rate // 50
+    ramp = (np.cos(np.linspace(np.pi, 0.0, n).astype(dt)).astype(dt) + dt(1.0)) / dt(2.0)
+    return np.concatenate([np.zeros(n, dt), ramp.astype(dt)])
+
+
+def apply_trim_fade(wav, fade) -> np.ndarray:
+    """Codec/S3Gen/S3Gen.swift:284-289: result[..., 0 ..< fadeLen] *= trimFade when the waveform has at least fadeLen samples"""
+    out = np.array(wav, copy=True)
+    n = len(fade)
+    if out.shape[1] >= n:
+        out[:, :n] = out[:, :n] * np.asarray(fade, out.dtype)
+    return out
+
+
 def kokoro_head_istft(conv_out, n_fft: int = 20, hop: int = 5, win_length: int = 20, dt=F32) -> np.ndarray:
     """Tail of the Kokoro generator, TTS/Kokoro/Decoder/Generator.swift:182-190: x (B, n_fft+2, frames) ->
     spec = exp(x[:, :F]), phase = sin(x[:, F:]), MLXSTFT.inverse.  -> (B, 1, L)."""

@@ -294,6 +294,30 @@ def test_hift_head_istft(api, ctx, frames):
     assert np.abs(got).max() <= 0.99
 
 
+
+@pytest.mark.parametrize("frames", [2001, 300, 200])
+def test_hift_head_istft_with_s3gen_fade(api, ctx, frames):
+    # S3Token2Wav: vocoder head, then result[..., :960] *= trimFade when the waveform has >= 960 samples (S3Gen.swift:259-262, 284-289)
+    rng = np.random.default_rng(frames)
+    h = rng.standard_normal((2, 18, frames)).astype(np.float32)
+    h[:, :9] -= 2.0
+    h[:, 9:] *= 2.0
+    w = R.hann_window_periodic(16)
+    fade = api.s3genTrimFade(24000)
+    assert np.abs(fade - R.s3gen_trim_fade(24000)).max() <= 2e-7
+    got = api.hiftHeadIstftFade(h, 16, 4, w, fade, ctx=ctx)
+    want = R.apply_trim_fade(R.hift_head_istft(h, 16, 4, w), fade)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= ISTFT_ATOL
+    if want.shape[1] >= len(fade):
+        assert not np.any(got[:, :480])                      # the first 20 ms are silenced
+    else:
+        assert np.abs(got - R.hift_head_istft(h, 16, 4, w)).max() <= ISTFT_ATOL   # too short: no fade at all
+    # a different window on the same context replaces the cached table
+    fade2 = np.linspace(0.0, 1.0, 100).astype(np.float32)
+    got2 = api.hiftHeadIstftFade(h, 16, 4, w, fade2, ctx=ctx)
+    assert np.abs(got2 - R.apply_trim_fade(R.hift_head_istft(h, 16, 4, w), fade2)).max() <= ISTFT_ATOL
+
 @pytest.mark.parametrize("frames", [2, 253, 1201])
 def test_kokoro_head_istft(api, ctx, frames):
     rng = np.random.default_rng(400 + frames)

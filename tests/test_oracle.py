@@ -242,3 +242,14 @@ def test_kaldi_framing_matches_torchaudio():
     power = np.abs(np.fft.rfft(mine.astype(np.float64), axis=1)) ** 2
     want = np.log(np.maximum(power @ R.mel_filters_htk(16000, 512, 80, 20.0, 8000.0).astype(np.float64), 1.1920929e-07))
     assert np.abs(R.kaldi_fbank_camp_plus(x) - want).max() <= 2e-3   # fp32 restatement vs fp64 on un-clamped logs
+
+
+def test_s3gen_trim_fade_window():
+    # S3Gen.swift:259-262: 20 ms of zeros, then a raised-cosine ramp from 0 to 1 over 20 ms
+    f = R.s3gen_trim_fade(24000)
+    assert f.shape == (960,) and not np.any(f[:480])
+    assert f[480] == 0.0 and f[-1] == 1.0 and np.all(np.diff(f[480:]) >= 0)
+    assert abs(float(f[480 + 240]) - 0.5) < 5e-3
+    y = np.ones((2, 1000), np.float32)
+    assert np.array_equal(R.apply_trim_fade(y, f)[:, :960], np.broadcast_to(f, (2, 960)))
+    assert np.array_equal(R.apply_trim_fade(y[:, :900], f), y[:, :900])      # shorter than the window: untouched
