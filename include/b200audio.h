@@ -257,6 +257,9 @@ B2A_API int b2a_kokoro_stft_transform(b2a_ctx* ctx, const float* x, int64_t batc
 B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const float* phase, int64_t batch,
                                     int64_t n_frames, int filter_length, int hop_length, int win_length,
                                     float* out, int space);
+/* unwrap                   TTS/Kokoro/Decoder/MLXSTFT.swift:23-46: numpy-style phase unwrap along the last axis of (n_rows, n_frames)
+ * (what b2a_kokoro_stft_inverse applies to the phase; the identity unless some |phase[t] - phase[t-1]| >= pi). */
+B2A_API int b2a_unwrap(b2a_ctx* ctx, const float* phase, int64_t n_rows, int64_t n_frames, float* out, int space);
 
 /* ---- adjacent rows: vocoder glue fused around the iSTFT ----------------------------------------
  * HiFT head: h = convPost output (batch, n_fft + 2, frames).  magnitude = exp(h[:, :F]), phase = sin(h[:, F:]),

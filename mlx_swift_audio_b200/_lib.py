@@ -92,6 +92,7 @@ SIGNATURES = {
     "b2a_resample_linear": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_whisper_mel_segment_f16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.POINTER(_i64), C.POINTER(_i64), _i64, C.c_void_p,
                                               C.c_int]),
+    "b2a_unwrap": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_void_p, C.c_int]),
     "b2a_hift_head_istft": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, _f, C.c_float, C.c_void_p, C.c_int]),
     "b2a_hift_head_istft_fade": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, _f, C.c_float, _f, _i64, C.c_void_p, C.c_int]),
     "b2a_s3gen_trim_fade": (C.c_int, [C.c_int, _f]),

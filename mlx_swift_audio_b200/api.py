@@ -713,6 +713,34 @@ def hiftHeadIstft(convOut, nFft: int, hopLength: int, window, audioLimit: float 
                        lambda b, n: (b, n))
 
 
+def unwrap(p, ctx: Context | None = None):
+    """TTS/Kokoro/Decoder/MLXSTFT.swift:23-46: numpy-style phase unwrap along the last axis"""
+    a = _Arr(p)
+    if len(a.shape) < 1 or a.shape[-1] < 1:
+        raise B2AError(L.B2A_E_BAD_ARG, "unwrap needs at least one sample along the last axis")
+    n = a.shape[-1]
+    rows = int(np.prod(a.shape[:-1])) if len(a.shape) > 1 else 1
+    c = _ctx_for(a, ctx)
+    out = a.empty(a.shape)
+    c.check(c.lib.b2a_unwrap(c.h, a.ptr, rows, n, _ptr(out), a.space))
+    return out
+
+
+def mlxStft(x, nFft: int = 20, hopLength: int = 5, ctx: Context | None = None):
+    """TTS/Kokoro/Decoder/MLXSTFT.swift:69-113 for the configuration the package uses (periodic Hann of nFft taps, centre reflect
+    padding): (T,) or (B, T) -> complex64 (F, frames) or (B, F, frames), i.e. the reference's transposed rfft of the frames."""
+    w = np.ascontiguousarray(hanningWindow(nFft + 1)[:nFft], np.float32)
+    a = _Arr(x)
+    single = len(a.shape) == 1
+    re, im = stftHiFiGAN(a.t[None] if single else a.t, nFft, hopLength, w, ctx=ctx)
+    if _is_torch(re):
+        import torch
+        z = torch.complex(re, im)
+    else:
+        z = (re + 1j * im).astype(np.complex64)
+    return z[0] if single else z
+
+
 def s3genTrimFade(samplingRate: int = 24000) -> np.ndarray:
     """Fade-in window of S3Token2Wav (Codec/S3Gen/S3Gen.swift:259-262): zeros(sr/50) ++ (cos(linspace(pi, 0, sr/50)) + 1) / 2"""
     out = np.empty(2 * (samplingRate // 50), np.float32)

@@ -1154,6 +1154,23 @@ int b2a_kokoro_head_istft(b2a_ctx* c, const float* conv_out, int64_t batch, int6
                       1, out, space, 1, 0.0f);
 }
 
+int b2a_unwrap(b2a_ctx* c, const float* phase, int64_t n_rows, int64_t n_frames, float* out, int space) {
+  // numpy-style unwrap along the last axis of (n_rows, n_frames) (MLXSTFT.swift:23-46)
+  int rc = check_common(c, phase, out, n_rows, n_frames);
+  if (rc != B2A_OK) return rc;
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r = launch_unwrap(d_in, d_out, n, n_frames, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, n_rows, phase, size_t(n_frames), nullptr, 0, out, size_t(n_frames), nullptr, 0, body);
+}
+
 int b2a_istft_hifigan(b2a_ctx* c, const float* magnitude, const float* phase, int64_t batch, int64_t n_frames, int n_fft, int hop,
                       const float* window, float* out, int space) {
   // clip(magnitude, max: 1e2) only (HiFiGAN.swift:300)

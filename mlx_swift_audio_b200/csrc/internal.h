@@ -163,5 +163,6 @@ struct SmallStftArgs {
   float* out1 = nullptr;          //                            imag or phase
 };
 int launch_small_stft(const SmallStftArgs& a, void* stream, int* launches, std::string* err);
+int launch_unwrap(const float* phase, float* out, int64_t n_rows, int64_t n_frames, void* stream, int* launches, std::string* err);
 
 }  // namespace b2a

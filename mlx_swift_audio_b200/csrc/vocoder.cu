@@ -542,6 +542,14 @@ static int launch_small_stft_t(const SmallStftArgs& a, cudaStream_t st, int* lau
   return B2A_OK;
 }
 
+int launch_unwrap(const float* phase, float* out, int64_t n_rows, int64_t n_frames, void* stream, int* launches, std::string* err) {
+  unwrap_kernel<<<unsigned((n_rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(phase, out, n_frames, n_rows);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail2(e, "unwrap_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
 int launch_small_stft(const SmallStftArgs& a, void* stream, int* launches, std::string* err) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a.n_fft == 16 && a.hop == 4) return launch_small_stft_t<16, 4>(a, st, launches, err);

@@ -414,3 +414,26 @@ def test_contexts_on_concurrent_host_threads(api):
     for t in threads:
         t.join(120)
     assert not errors, errors
+
+
+def test_unwrap_and_mlx_stft(api, ctx):
+    # unwrap (MLXSTFT.swift:23-46) as a stand-alone call: rows with phase jumps >= pi, rows without, 3-D input
+    rng = np.random.default_rng(5)
+    p = np.cumsum(rng.uniform(-2.5, 2.5, (3, 11, 700)), axis=-1)
+    p = ((p + np.pi) % (2 * np.pi) - np.pi).astype(np.float32)          # wrapped random walk: many 2 pi jumps
+    p[1] = np.sin(rng.standard_normal((11, 700))).astype(np.float32)    # the vocoders' case: no jump at all -> identity
+    got = api.unwrap(p, ctx=ctx)
+    want = np.stack([R.unwrap(q) for q in p])
+    assert got.shape == want.shape
+    assert np.array_equal(got[1], p[1])
+    # fp32 cumulative sums over 700 steps: a few ulp of the running phase (hundreds of radians)
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+    assert np.abs(got - np.unwrap(p.astype(np.float64), axis=-1)).max() <= 1e-3
+    # mlxStft (MLXSTFT.swift:69-113) in the package's configuration: complex (F, frames)
+    x = synth.pcm(2, 24000 // 4 + 3, sample_rate=24000, seed=6)
+    z = api.mlxStft(x, 20, 5, ctx=ctx)
+    ref = np.stack([R.mlx_stft(c, 20, 5, 20) for c in x])
+    assert z.shape == ref.shape and z.dtype == np.complex64
+    assert np.abs(z - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    z1 = api.mlxStft(x[0], 20, 5, ctx=ctx)
+    assert np.array_equal(z1, z[0])
