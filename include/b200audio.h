@@ -136,6 +136,10 @@ B2A_API int64_t b2a_istft_out_length(int64_t n_frames, int hop);                
 /* padOrTrim                STT/Whisper/WhisperAudio.swift:54-67.  out (batch, length). */
 B2A_API int b2a_pad_or_trim(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int64_t length,
                             float* out, int space);
+/* reflectPad / reflectPad1D   Codec/S3Tokenizer/S3TokenizerUtils.swift:266-298, STT/FunASR/FunASRAudio.swift:280-310.
+ * x (batch, n_samples) -> out (batch, n_samples + 2 * padding), incl. the reference's loops for n_samples - 1 < padding and
+ * the n_samples == 1 replicate case.  (The front ends never call this: they apply the same index map while staging frames.) */
+B2A_API int b2a_reflect_pad(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int64_t padding, float* out, int space);
 
 /* whisperLogMelSpectrogram STT/Whisper/WhisperAudio.swift:78-137.
  * audio (batch, n_samples) -> out (batch, T', n_mels), T' = b2a_whisper_num_frames(n_samples, padding).

@@ -60,6 +60,7 @@ SIGNATURES = {
     "b2a_s3gen_num_frames": (_i64, [_i64, C.c_int, C.c_int]),
     "b2a_vocoder_stft_num_frames": (_i64, [_i64, C.c_int, C.c_int]),
     "b2a_istft_out_length": (_i64, [_i64, C.c_int]),
+    "b2a_reflect_pad": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, _i64, C.c_void_p, C.c_int]),
     "b2a_pad_or_trim": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, _i64, C.c_void_p, C.c_int]),
     "b2a_whisper_log_mel_spectrogram": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_void_p, C.c_int]),
     "b2a_log_mel_spectrogram_chatterbox": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_void_p, C.c_int]),

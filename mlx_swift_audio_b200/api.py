@@ -281,6 +281,19 @@ def padOrTrim(array, length: int = 480000, ctx: Context | None = None):
     return out if had else out[0]
 
 
+def reflectPad(x, padding: int, ctx: Context | None = None):
+    """Codec/S3Tokenizer/S3TokenizerUtils.swift:266-298 (== reflectPad1D, STT/FunASR/FunASRAudio.swift:280-310): (T,) -> (T + 2*padding,)"""
+    a = _Arr(x)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    out = a.empty((b, n + 2 * padding))
+    c.check(c.lib.b2a_reflect_pad(c.h, a.ptr, b, n, padding, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+reflectPad1D = reflectPad
+
+
 def whisperLogMelSpectrogram(audio, nMels: int, padding: int = 0, ctx: Context | None = None, out=None):
     """STT/Whisper/WhisperAudio.swift:78-137 -> (T', nMels)"""
     a = _Arr(audio)

@@ -594,6 +594,23 @@ int b2a_pad_or_trim(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples
   return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(length), nullptr, 0, body);
 }
 
+int b2a_reflect_pad(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int64_t padding, float* out, int space) {
+  int rc = check_common(c, x, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (padding < 0) return fail(c, B2A_E_BAD_ARG, "padding must be >= 0");
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r = launch_reflect_pad(d_in, d_out, n, n_samples, padding, c->stream, &launches, &err);
+    c->launches += launches;
+    if (r != B2A_OK) c->err = err;
+    return r;
+  };
+  return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(n_samples + 2 * padding), nullptr, 0, body);
+}
+
 int b2a_s3tokenizer_gather_segments(b2a_ctx* c, const float* mel, int64_t batch, int n_mels, int64_t t_max, int64_t n_segments,
                                     const int32_t* batch_idx, const int32_t* start, const int32_t* length, int64_t window, float* out,
                                     int space) {

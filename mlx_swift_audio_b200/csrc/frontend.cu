@@ -1050,6 +1050,14 @@ __global__ void pad_or_trim_kernel(const float* __restrict__ in, float* __restri
   if (i < length) out[clip * length + i] = i < n ? in[clip * n + i] : 0.0f;
 }
 
+// reflectPad / reflectPad1D (S3TokenizerUtils.swift:266-298, FunASRAudio.swift:280-310) as a stand-alone call: the index map the
+// fused front ends apply on the fly (fetch_padded), including the reference's short-input loops
+__global__ void reflect_pad_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, long long pad) {
+  const long long clip = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n + 2 * pad) out[clip * (n + 2 * pad) + i] = fetch_padded(in + clip * n, i, pad, n, n, PAD_REFLECT);
+}
+
 // Whisper seek window (STT/Whisper/WhisperSTT.swift:171-182,624-635): rows
 // [seek, seek + min(length, content_frames - seek)) of a clip's (T', M) log-mel, zero-padded to `length` rows, cast to fp16
 // (round to nearest even, like MLX asType(.float16)).  One thread = 8 consecutive values: two 16-byte loads, one 16-byte store.
@@ -1434,6 +1442,15 @@ int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, in
   pad_or_trim_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, length);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pad_or_trim_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+int launch_reflect_pad(const float* in, float* out, int64_t batch, int64_t n, int64_t pad, void* stream, int* launches, std::string* err) {
+  dim3 grid(unsigned((n + 2 * pad + 255) / 256), unsigned(batch));
+  reflect_pad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, pad);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "reflect_pad_kernel launch", err);
   *launches += 1;
   return B2A_OK;
 }

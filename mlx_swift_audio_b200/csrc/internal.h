@@ -126,6 +126,7 @@ int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T,
                            int* launches, std::string* err);
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
                        int* launches, std::string* err);
+int launch_reflect_pad(const float* in, float* out, int64_t batch, int64_t n, int64_t pad, void* stream, int* launches, std::string* err);
 
 // ---- vocoder STFT / iSTFT (vocoder.cu) -------------------------------------------------------
 enum IstftNorm { NORM_WSQ_FLOOR = 0 /* HiFT, CosyVoice3: / max(sum w^2, 1e-8) */, NORM_WSUM_NONZERO = 1 /* Kokoro */ };

@@ -437,3 +437,15 @@ def test_unwrap_and_mlx_stft(api, ctx):
     assert np.abs(z - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
     z1 = api.mlxStft(x[0], 20, 5, ctx=ctx)
     assert np.array_equal(z1, z[0])
+
+
+def test_reflect_pad_stand_alone(api, ctx):
+    # reflectPad (S3TokenizerUtils.swift:266-298): ordinary inputs, the short-input loops (n - 1 < padding), n == 1, padding 0
+    rng = np.random.default_rng(9)
+    for n, pad in ((1000, 200), (201, 200), (150, 200), (37, 200), (2, 5), (1, 4), (64, 0), (1920, 720)):
+        x = rng.standard_normal((3, n)).astype(np.float32)
+        got = api.reflectPad(x, pad, ctx=ctx)
+        want = np.stack([R.reflect_pad(c, pad) for c in x])
+        assert got.shape == want.shape == (3, n + 2 * pad)
+        assert np.array_equal(got, want), (n, pad)
+    assert np.array_equal(api.reflectPad1D(x[0], 720, ctx=ctx), R.reflect_pad(x[0], 720))
