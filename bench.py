@@ -46,6 +46,7 @@ WORKLOADS = {
     "istft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="CosyVoice HiFT iSTFT (n_fft 16, hop 4), 512 x 30 s of mag/phase (configs[4], 5a)"),
     "whisper_segment": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper seek window: slice + zero-pad + fp16 cast of the 128-mel log-mel, 1024 clips (SURVEY 8f rank 1)"),
     "hift_head": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
+    "whisper128_ragged": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper 128-mel log-mel of a RAGGED batch: 1024 clips of 5..30 s (uniform) in one launch (b2a_whisper_log_mel_spectrogram_ragged)"),
     "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
 }
 
@@ -182,7 +183,19 @@ class GpuWorkload:
             x.clamp_(-1.0, 1.0)
             x[:, n - n // 10:] = 0.0
             self.inputs = [x]
-            if name in ("whisper128", "whisper80_1clip"):
+            if name == "whisper128_ragged":
+                rs = np.random.default_rng(4)
+                lens = np.ascontiguousarray(rs.integers(5 * self.sr, n + 1, B), np.int64)
+                lens[0] = n
+                rows = np.zeros(B, np.int64)
+                self._keep = (lens, rows)
+                I64 = C.POINTER(C.c_int64)
+                frames = int(lib.b2a_whisper_num_frames(n, 0))
+                self.out = torch.empty((B, frames, 128), device=dev)
+                self.audio_s = float(lens.sum()) / self.sr
+                self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram_ragged(c.h, i[0], B, n, lens.ctypes.data_as(I64), 128, 0, o,
+                                                                                           rows.ctypes.data_as(I64), sp)
+            elif name in ("whisper128", "whisper80_1clip"):
                 nm = 128 if name == "whisper128" else 80
                 frames = int(lib.b2a_whisper_num_frames(n, 0))
                 self.out = torch.empty((B, frames, nm), device=dev)
@@ -205,6 +218,8 @@ class GpuWorkload:
         self.in_bytes = sum(t.numel() * t.element_size() for t in self.inputs)
         self.out_bytes = self.out.numel() * self.out.element_size()
         self.algo_bytes = self.in_bytes + self.out_bytes
+        if name == "whisper128_ragged":   # valid samples in, the whole (zero-filled) output out
+            self.algo_bytes = int(self._keep[0].sum()) * 4 + self.out_bytes
         if name == "whisper_segment":   # only the windows' rows are read (here: the rows up to frame 3000 from each seek)
             self.algo_bytes = int(sum(3000 - int(s0) for s0 in self._keep[0])) * 128 * 4 + self.out_bytes
         self.DEV, self.HOST = _lib.B2A_DEVICE, _lib.B2A_HOST
@@ -329,6 +344,8 @@ def cpu_arm(name: str, core_seconds: float = 2.0, reps: int = 1):
     The sample is sized so that every core is busy for about `core_seconds` (10-30 s of CPU work in total).
     Where the compiled twin covers the workload, the faster of the two CPU restatements is the reported value and the
     other one is quoted in the sample text."""
+    if name == "whisper128_ragged":   # the CPU restatements process one clip at a time anyway: audio-s/s of the equal-length workload
+        name = "whisper128"
     twin = cpu_arm_twin(name, core_seconds)
     if twin is not None:
         nv, ncores, nsample = cpu_arm_numpy(name, core_seconds / 2, reps)

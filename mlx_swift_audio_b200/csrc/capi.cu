@@ -53,7 +53,7 @@ struct b2a_ctx {
   DevBuf in[kSlots][2], out[kSlots][2];          // host-pipeline staging
   DevBuf fade;                                   // fade-in window of the fused vocoder head (device copy of fade_host)
   std::vector<float> fade_host;
-  DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3 / 4: ragged clip / tile tables
+  DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3: ragged clip table
   int64_t chunk_clip0 = 0;                       // first clip of the chunk run_batched is handing to the body
   int* h_flag = nullptr;                         // pinned
 };
@@ -320,7 +320,9 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
     a.spec_mode = p.spec_mode; a.bank = p.bank; a.log_mode = p.log_mode; a.log_floor = p.log_floor;
     a.whisper_norm = p.whisper_norm; a.post_affine = p.post_affine; a.post_sub = p.post_sub; a.post_div = p.post_div;
     a.out_mode = p.out_mode; a.n_frames = p.n_frames; a.out = d_out; a.lfr_m = p.lfr_m; a.lfr_n = p.lfr_n; a.lfr_rows = p.lfr_rows;
-    std::vector<int> clip_tab, tile_tab;   // (pageable-memory uploads below are staged before cudaMemcpyAsync returns)
+    std::vector<int> clip_tab;   // (the pageable-memory upload below is staged before cudaMemcpyAsync returns)
+    int launches = 0;
+    std::string err;
     if (rg) {
       const PlanShape* ps = plan_shape(p.n_fft);
       const int ft = ps ? ps->frame_tile : 32;
@@ -336,24 +338,21 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
         total += (fr + ft - 1) / ft;
       }
       if (total > 0x7fffffffLL) return fail(c, B2A_E_BAD_ARG, "too many tiles in one launch");
-      tile_tab.resize(size_t(total) * 2);
-      for (int64_t b = 0, g = 0; b < n; ++b)
-        for (int64_t t = 0, nt = (clip_frames[size_t(c0 + b)] + ft - 1) / ft; t < nt; ++t, ++g) {
-          tile_tab[2 * g] = int(b);
-          tile_tab[2 * g + 1] = int(t);
-        }
       int rc;
       if ((rc = ensure(c, c->scratch[slot][3], sizeof(int) * clip_tab.size())) != B2A_OK) return rc;
-      if ((rc = ensure(c, c->scratch[slot][4], sizeof(int) * tile_tab.size())) != B2A_OK) return rc;
       cudaError_t e;
       if ((e = cudaMemcpyAsync(c->scratch[slot][3].p, clip_tab.data(), sizeof(int) * clip_tab.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
         return cu(c, e, "table upload");
-      if ((e = cudaMemcpyAsync(c->scratch[slot][4].p, tile_tab.data(), sizeof(int) * tile_tab.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
-        return cu(c, e, "table upload");
-      if ((e = cudaMemsetAsync(d_out, 0, sizeof(float) * out_per_clip * size_t(n), c->stream)) != cudaSuccess) return cu(c, e, "memset");
       a.clip_tab = c->scratch[slot][3].p;
-      a.tile_tab = c->scratch[slot][4].p;
       a.total_tiles = total;
+      // rows past a clip's own count are zero (only those: the kernels write the rest)
+      if (p.out_mode == OUT_MT) rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.bank.n_mels, p.n_frames, 1, c->stream, &launches, &err);
+      else if (p.out_mode == OUT_LFR) rc = launch_zero_tails(d_out, a.clip_tab, 2, n, p.lfr_rows, int64_t(p.lfr_m) * p.bank.n_mels, 0, c->stream, &launches, &err);
+      else rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.n_frames, p.bank.n_mels, 0, c->stream, &launches, &err);
+      if (rc != B2A_OK) {
+        c->err = err;
+        return rc;
+      }
     }
     if (p.whisper_norm) {
       int rc;
@@ -362,8 +361,6 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
       a.clip_max = static_cast<int*>(c->scratch[slot][0].p);
       a.tile_min = static_cast<float*>(c->scratch[slot][1].p);
     }
-    int launches = 0;
-    std::string err;
     int rc = launch_frontend(a, c->stream, &launches, &err);
     if (rc == B2A_OK && p.post_cmvn)
       rc = launch_cmvn(d_out, d_out, n, p.lfr_rows, p.lfr_m * p.bank.n_mels, nullptr, nullptr, c->stream, &launches, &err, a.clip_tab);

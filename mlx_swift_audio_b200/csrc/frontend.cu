@@ -140,9 +140,9 @@ struct FrontendParams {
   int* clip_max;
   int* tile_min;   // per tile: ordered-int encoding of the minimum normalised value
   // Ragged batches (per-clip lengths; RAGGED kernels only): clip b = (n_samples, n_frames, lfr_rows, index of its first tile);
-  // tile g of the launch = (clip, tile within the clip).  Strides (clip_stride, out_clip_stride) stay those of the longest clip.
+  // the clip of tile g of the launch is found by bisection over the first-tile column.  Strides (clip_stride, out_clip_stride)
+  // stay those of the longest clip.
   const int4* clip_tab;
-  const int2* tile_tab;
   float window[P::WIN];
 };
 
@@ -363,8 +363,8 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // MEL == 0: any bank -- mel step program interpreted in a loop, run-time log / output modes (POST_RUNTIME, OUT = -1).
 // MEL > 0: bank MEL of mel_baked.h as straight-line code, with compile-time post-processing POST (applied in the store
 // loop) and output layout OUT (OUT_TM / OUT_MT / OUT_LFR).
-// RAGGED: per-clip lengths -- the tile walk and the clip geometry come from prm.tile_tab / prm.clip_tab (one uniform load each
-// per tile) instead of the launch-wide constants; built for the run-time-configured kernels only.
+// RAGGED: per-clip lengths -- the tile walk and the clip geometry come from prm.clip_tab (a bisection of ~log2(clips) uniform
+// loads per tile) instead of the launch-wide constants.
 template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
@@ -422,13 +422,22 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     lfr_rows = ci.z;
     first_tile = ci.w;
   };
+  // clip that owns tile gt of the launch: the last one whose first tile is <= gt (every clip has at least one tile)
+  auto find_clip = [&](long long gt) {
+    int lo = 0, hi = n_clips - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&prm.clip_tab[mid].w) <= gt) lo = mid;
+      else hi = mid - 1;
+    }
+    return lo;
+  };
   if (RAGGED) {
     clip = n_clips;
     if (g < prm.total_tiles) {
-      const int2 t = __ldg(prm.tile_tab + g);
-      clip = t.x;
-      tile = t.y;
+      clip = find_clip(g);
       load_clip(clip);
+      tile = int(g) - first_tile;
     }
   }
   if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
@@ -449,10 +458,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     if (RAGGED) {
       nclip = n_clips;
       if (g + gridDim.x < prm.total_tiles) {
-        const int2 t = __ldg(prm.tile_tab + g + gridDim.x);
-        nclip = t.x;
-        ntile = t.y;
-        nn_samples = __ldg(prm.clip_tab + nclip).x;
+        nclip = find_clip(g + gridDim.x);
+        const int4 ci = __ldg(prm.clip_tab + nclip);
+        ntile = int(g + gridDim.x) - ci.w;
+        nn_samples = ci.x;
       }
     }
 
@@ -1209,7 +1218,8 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
 template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
   if (!RAGGED && a.clip_tab != nullptr) {
-    // per-clip lengths: the run-time-configured kernel of the same plan, reading the clip / tile tables
+    // per-clip lengths: the RAGGED instantiation of the run-time-configured kernel of the same plan (and of the Whisper
+    // 128-mel kernel, dispatched in launch_frontend), reading the clip table
     if constexpr (MEL == 0 && POST == POST_RUNTIME && OUT == -1 && SPEC != SK_CPLX) return launch_plan<P, PRE, SPEC, 0, POST_RUNTIME, -1, true>(a, st, launches, err);
     if (err) *err = "ragged batches are built for the mel front ends only";
     return B2A_E_UNSUPPORTED;
@@ -1261,7 +1271,6 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
   prm.n_clips = int(a.batch);
   prm.clip_tab = static_cast<const int4*>(a.clip_tab);
-  prm.tile_tab = static_cast<const int2*>(a.tile_tab);
   switch (a.out_mode) {
     case OUT_TM: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
     case OUT_MT: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
@@ -1339,7 +1348,10 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   // at compile time on the post-processing and the output layout (small code: the whole tile loop stays inside the
   // instruction cache); everything else runs the run-time-configured kernel.
   int post = -1;
-  const bool ragged = a.clip_tab != nullptr;   // per-clip lengths: run-time-configured kernels only
+  const bool ragged = a.clip_tab != nullptr;   // per-clip lengths: run-time-configured kernels, except Whisper 128-mel (below)
+  if (ragged && a.bank.baked_id == 1 && spec == SK_POWER && !a.post_affine && a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode == OUT_TM &&
+      a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE)
+    return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM, true>(a, st, launches, err);
   if (!ragged && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
@@ -1442,6 +1454,34 @@ int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, in
   pad_or_trim_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, length);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pad_or_trim_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
+// Ragged batches: rows past a clip's own count are zero.  out is (batch, rows_max, row_len) ("time-major": whole rows) or
+// (batch, n_rows, t_max) with the valid part the first `count` entries of every row ("mel-major").
+__global__ void __launch_bounds__(256) zero_tail_kernel(float* __restrict__ out, const int4* __restrict__ clip_tab, int which, long long rows_max,
+                                                        long long row_len, int mel_major) {
+  const long long clip = blockIdx.y;
+  const int4 ci = clip_tab[clip];
+  const long long count = which == 2 ? ci.z : ci.y;
+  float* o = out + clip * rows_max * row_len;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (!mel_major) {
+    for (long long i = count * row_len + i0; i < rows_max * row_len; i += stride) o[i] = 0.0f;
+  } else {   // rows_max = number of mel rows, row_len = t_max
+    const long long tail = row_len - count;
+    for (long long i = i0; i < rows_max * tail; i += stride) o[(i / tail) * row_len + count + i % tail] = 0.0f;
+  }
+}
+
+int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, void* stream,
+                      int* launches, std::string* err) {
+  const long long per_clip = rows_max * row_len;
+  dim3 grid(unsigned(std::max<long long>(1, std::min<long long>(64, (per_clip + 4095) / 4096))), unsigned(batch));
+  zero_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, static_cast<const int4*>(clip_tab), which, rows_max, row_len, mel_major);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "zero_tail_kernel launch", err);
   *launches += 1;
   return B2A_OK;
 }
