@@ -253,3 +253,61 @@ def test_s3gen_trim_fade_window():
     y = np.ones((2, 1000), np.float32)
     assert np.array_equal(R.apply_trim_fade(y, f)[:, :960], np.broadcast_to(f, (2, 960)))
     assert np.array_equal(R.apply_trim_fade(y[:, :900], f), y[:, :900])      # shorter than the window: untouched
+
+
+def test_s3gen_and_voice_encoder_mels_match_torchaudio():
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    # s3genMelSpectrogram (S3GenMel.swift:43-102) is the Matcha / HiFi-GAN mel: reflect pad (n_fft - hop) / 2, periodic Hann,
+    # magnitude spectrum, Slaney bank 0..8000 Hz, ln(max(., 1e-5)) -- torchaudio's MelSpectrogram with power 1 on the padded signal
+    y = synth.pcm(2, 24000 + 480 * 3, sample_rate=24000, seed=41)
+    t = torch.from_numpy(y)
+    padded = torch.nn.functional.pad(t[:, None, :], (720, 720), mode="reflect")[:, 0]
+    ms = ta.transforms.MelSpectrogram(sample_rate=24000, n_fft=1920, win_length=1920, hop_length=480, f_min=0.0, f_max=8000.0, n_mels=80,
+                                      power=1.0, center=False, norm="slaney", mel_scale="slaney")
+    want = torch.log(torch.clamp(ms(padded.double().float()), min=1e-5)).numpy()
+    got = R.s3gen_mel_spectrogram(y)
+    assert got.shape == want.shape == (2, 80, 53)
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max())
+    # voiceEncoderMelspectrogram (VoiceEncoderMelspec.swift:17-68): centred reflect-padded power mel, 40 Slaney filters, no log
+    x = synth.pcm(1, 16000 + 55, seed=42)[0]
+    ve = ta.transforms.MelSpectrogram(sample_rate=16000, n_fft=400, win_length=400, hop_length=160, f_min=0.0, f_max=8000.0, n_mels=40,
+                                      power=2.0, center=True, pad_mode="reflect", norm="slaney", mel_scale="slaney")
+    want = ve(torch.from_numpy(x)).numpy()
+    got = R.voice_encoder_melspectrogram(x)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_funasr_log_mel_and_vocoder_stfts_match_torch():
+    torch = pytest.importorskip("torch")
+    ta = pytest.importorskip("torchaudio")
+    # funASRLogMelSpectrogram (FunASRAudio.swift:57-94): centred STFT with a symmetric Hamming window, |X|^2 of bins 0..199, the
+    # 200-point torchaudio-style HTK bank, natural log floored at 1e-10 -- composed here from torch.stft and torchaudio's bank
+    x = synth.pcm(1, 16000 * 2 + 9, seed=51)[0]
+    st = torch.stft(torch.from_numpy(x).double(), 400, 160, window=torch.hamming_window(400, periodic=False, dtype=torch.float64),
+                    center=True, pad_mode="reflect", return_complex=True)
+    bank = ta.functional.melscale_fbanks(200, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="htk").double()
+    want = torch.log(torch.clamp((st.abs() ** 2)[:200].T @ bank, min=1e-10)).numpy()
+    got64 = R.funasr_log_mel_spectrogram(x, dt=np.float64)
+    assert got64.shape == want.shape == (1 + len(x) // 160, 80)
+    assert np.abs(got64 - want).max() <= 2e-4            # (fp32 filterbank tables on the torchaudio side)
+    # fp32 restatement: its fp32 bank differs from torchaudio's by ~1e-7 absolute, which a strong tone sitting on a filter's edge
+    # (weight ~1e-6, power ~1e3) turns into ~1e-3 of an un-clamped log: table rounding, not the transform
+    assert np.abs(R.funasr_log_mel_spectrogram(x) - want).max() <= 2e-3
+    # stftHiFiGAN (reflect), cosyVoice3Stft (zero pad) and MLXSTFT.transform: torch.stft with n_fft 16 / 20 and periodic Hann
+    sig = synth.pcm(2, 2403, sample_rate=24000, seed=52)
+    ts = torch.from_numpy(sig).double()
+    w16 = torch.hann_window(16, periodic=True, dtype=torch.float64)
+    for fn, mode in ((R.stft_hifigan, "reflect"), (R.cosyvoice3_stft, "constant")):
+        re, im = fn(sig, 16, 4, R.hann_window_periodic(16))
+        ref = torch.stft(ts, 16, 4, window=w16, center=True, pad_mode=mode, return_complex=True).numpy()
+        assert re.shape == ref.shape
+        assert np.abs((re + 1j * im) - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    mag, ph = R.kokoro_transform(sig)
+    ref = torch.stft(ts, 20, 5, window=torch.hann_window(20, periodic=True, dtype=torch.float64), center=True, pad_mode="reflect",
+                     return_complex=True).numpy()
+    assert np.abs(mag - np.abs(ref)).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    strong = np.abs(ref) > 1e-2          # the phase of a near-zero bin is ill-conditioned
+    d = np.angle(np.exp(1j * (ph - np.angle(ref))))
+    assert np.abs(d[strong]).max() <= 1e-4
