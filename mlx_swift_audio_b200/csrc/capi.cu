@@ -53,7 +53,7 @@ struct b2a_ctx {
   DevBuf in[kSlots][2], out[kSlots][2];          // host-pipeline staging
   DevBuf fade;                                   // fade-in window of the fused vocoder head (device copy of fade_host)
   std::vector<float> fade_host;
-  DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3: ragged clip table
+  DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3 / 4: ragged clip / tile tables
   int64_t chunk_clip0 = 0;                       // first clip of the chunk run_batched is handing to the body
   int* h_flag = nullptr;                         // pinned
 };
@@ -343,8 +343,14 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
       cudaError_t e;
       if ((e = cudaMemcpyAsync(c->scratch[slot][3].p, clip_tab.data(), sizeof(int) * clip_tab.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
         return cu(c, e, "table upload");
+      if ((rc = ensure(c, c->scratch[slot][4], sizeof(int) * 2 * size_t(total))) != B2A_OK) return rc;
       a.clip_tab = c->scratch[slot][3].p;
+      a.tile_tab = c->scratch[slot][4].p;
       a.total_tiles = total;
+      if ((rc = launch_tile_table(a.clip_tab, n, total, c->scratch[slot][4].p, c->stream, &launches, &err)) != B2A_OK) {
+        c->err = err;
+        return rc;
+      }
       // rows past a clip's own count are zero (only those: the kernels write the rest)
       if (p.out_mode == OUT_MT) rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.bank.n_mels, p.n_frames, 1, c->stream, &launches, &err);
       else if (p.out_mode == OUT_LFR) rc = launch_zero_tails(d_out, a.clip_tab, 2, n, p.lfr_rows, int64_t(p.lfr_m) * p.bank.n_mels, 0, c->stream, &launches, &err);

@@ -140,9 +140,10 @@ struct FrontendParams {
   int* clip_max;
   int* tile_min;   // per tile: ordered-int encoding of the minimum normalised value
   // Ragged batches (per-clip lengths; RAGGED kernels only): clip b = (n_samples, n_frames, lfr_rows, index of its first tile);
-  // the clip of tile g of the launch is found by bisection over the first-tile column.  Strides (clip_stride, out_clip_stride)
-  // stay those of the longest clip.
+  // tile g of the launch = tile_tab[g] = (clip, tile within the clip), built on the device from clip_tab (tile_table_kernel).
+  // Strides (clip_stride, out_clip_stride) stay those of the longest clip.
   const int4* clip_tab;
+  const int2* tile_tab;
   float window[P::WIN];
 };
 
@@ -363,8 +364,8 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // MEL == 0: any bank -- mel step program interpreted in a loop, run-time log / output modes (POST_RUNTIME, OUT = -1).
 // MEL > 0: bank MEL of mel_baked.h as straight-line code, with compile-time post-processing POST (applied in the store
 // loop) and output layout OUT (OUT_TM / OUT_MT / OUT_LFR).
-// RAGGED: per-clip lengths -- the tile walk and the clip geometry come from prm.clip_tab (a bisection of ~log2(clips) uniform
-// loads per tile) instead of the launch-wide constants.
+// RAGGED: per-clip lengths -- the tile walk and the clip geometry come from prm.tile_tab / prm.clip_tab (one uniform load each
+// per tile, issued one tile ahead) instead of the launch-wide constants.
 template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
@@ -422,22 +423,13 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     lfr_rows = ci.z;
     first_tile = ci.w;
   };
-  // clip that owns tile gt of the launch: the last one whose first tile is <= gt (every clip has at least one tile)
-  auto find_clip = [&](long long gt) {
-    int lo = 0, hi = n_clips - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&prm.clip_tab[mid].w) <= gt) lo = mid;
-      else hi = mid - 1;
-    }
-    return lo;
-  };
   if (RAGGED) {
     clip = n_clips;
     if (g < prm.total_tiles) {
-      clip = find_clip(g);
+      const int2 t = __ldg(prm.tile_tab + g);
+      clip = t.x;
+      tile = t.y;
       load_clip(clip);
-      tile = int(g) - first_tile;
     }
   }
   if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
@@ -458,10 +450,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     if (RAGGED) {
       nclip = n_clips;
       if (g + gridDim.x < prm.total_tiles) {
-        nclip = find_clip(g + gridDim.x);
-        const int4 ci = __ldg(prm.clip_tab + nclip);
-        ntile = int(g + gridDim.x) - ci.w;
-        nn_samples = ci.x;
+        const int2 t = __ldg(prm.tile_tab + g + gridDim.x);
+        nclip = t.x;
+        ntile = t.y;
+        nn_samples = __ldg(prm.clip_tab + nclip).x;
       }
     }
 
@@ -1271,6 +1263,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
   prm.n_clips = int(a.batch);
   prm.clip_tab = static_cast<const int4*>(a.clip_tab);
+  prm.tile_tab = static_cast<const int2*>(a.tile_tab);
   switch (a.out_mode) {
     case OUT_TM: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
     case OUT_MT: prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels; break;
@@ -1473,6 +1466,30 @@ __global__ void __launch_bounds__(256) zero_tail_kernel(float* __restrict__ out,
     const long long tail = row_len - count;
     for (long long i = i0; i < rows_max * tail; i += stride) o[(i / tail) * row_len + count + i % tail] = 0.0f;
   }
+}
+
+// tile_tab[g] = (clip, tile) for a ragged launch: the clip of tile g is the last one whose first tile is <= g (bisection over the
+// first-tile column of clip_tab; every clip has at least one tile).  Built once per call on the device -- the main kernel would
+// otherwise pay the ~10 dependent loads per tile itself, mostly as L2 hits (its cp.async traffic sweeps the L1).
+__global__ void tile_table_kernel(const int4* __restrict__ clip_tab, int n_clips, int total_tiles, int2* __restrict__ tile_tab) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total_tiles) return;
+  int lo = 0, hi = n_clips - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (clip_tab[mid].w <= g) lo = mid;
+    else hi = mid - 1;
+  }
+  tile_tab[g] = make_int2(lo, g - clip_tab[lo].w);
+}
+
+int launch_tile_table(const void* clip_tab, int64_t n_clips, int64_t total_tiles, void* tile_tab, void* stream, int* launches, std::string* err) {
+  tile_table_kernel<<<unsigned((total_tiles + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const int4*>(clip_tab), int(n_clips), int(total_tiles), static_cast<int2*>(tile_tab));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "tile_table_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
 }
 
 int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, void* stream,

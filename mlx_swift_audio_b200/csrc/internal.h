@@ -96,10 +96,12 @@ struct FrontendArgs {
   // scratch for the Whisper clamp (device): clip_max (batch) ordered-int encoded, tile_min (batch * tiles)
   int* clip_max = nullptr;
   float* tile_min = nullptr;
-  // ragged batch (per-clip lengths): device table built by the C ABI -- clip_tab[b] = int4(n_samples, n_frames, lfr_rows,
-  // first tile of the clip); n_samples / n_frames / lfr_rows above are then those of the longest clip (they give the
-  // strides).  Null = every clip has n_samples samples.
+  // ragged batch (per-clip lengths): device tables -- clip_tab[b] = int4(n_samples, n_frames, lfr_rows, first tile of the
+  // clip), uploaded by the C ABI, and tile_tab[g] = int2(clip, tile), built from it on the device (launch_tile_table);
+  // n_samples / n_frames / lfr_rows above are then those of the longest clip (they give the strides).
+  // Null = every clip has n_samples samples.
   const void* clip_tab = nullptr;
+  const void* tile_tab = nullptr;
   int64_t total_tiles = 0;
 };
 
@@ -125,6 +127,7 @@ int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T,
                            int* launches, std::string* err);
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
                        int* launches, std::string* err);
+int launch_tile_table(const void* clip_tab, int64_t n_clips, int64_t total_tiles, void* tile_tab, void* stream, int* launches, std::string* err);
 int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, void* stream,
                       int* launches, std::string* err);
 int launch_reflect_pad(const float* in, float* out, int64_t batch, int64_t n, int64_t pad, void* stream, int* launches, std::string* err);
