@@ -107,6 +107,7 @@ template <> struct TwTable<Plan512> { static B2A_DEV const float2* get() { retur
 template <> struct TwTable<Plan1920> { static B2A_DEV const float2* get() { return c_tw1920; } };
 
 enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
+constexpr int kStepsSmemMax = 2048;   // mel-program steps a one-CTA-per-SM kernel keeps in shared memory (32 KB)
 // Post-processing of a finished mel value.  POST_RUNTIME: log mode / Whisper normalisation are kernel parameters and the
 // filterbank is the interpreted step program (any bank); the other kinds belong to the baked banks of mel_baked.h.
 enum PostKind { POST_RUNTIME = 0, POST_WNORM = 1, POST_LN = 2 };
@@ -261,14 +262,23 @@ B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1,
   }
 }
 
-B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restrict__ steps, int s0, int s1, float* so_lane_f) {
+// SMEM: the program was copied into shared memory (plans with one CTA per SM have the room; global-memory reads of the program are
+// mostly L2 hits there, because the cp.async traffic of the PCM staging sweeps the L1)
+template <bool SMEM>
+B2A_DEV float4 load_step(const float4* steps, int s) {
+  return SMEM ? steps[s] : __ldg(steps + s);
+}
+
+template <bool SMEM>
+B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* steps, int s0, int s1, float* so_lane_f) {
   char* so_lane = reinterpret_cast<char*>(so_lane_f);
   float acc0 = 0.0f, acc1 = 0.0f;
   const char* pb = reinterpret_cast<const char*>(p_lane);
   int s = s0;
   // four steps per iteration, all loads issued before the (serial) accumulator updates
   for (; s + 4 <= s1; s += 4) {
-    const float4 t0 = __ldg(steps + s), t1 = __ldg(steps + s + 1), t2 = __ldg(steps + s + 2), t3 = __ldg(steps + s + 3);
+    const float4 t0 = load_step<SMEM>(steps, s), t1 = load_step<SMEM>(steps, s + 1), t2 = load_step<SMEM>(steps, s + 2),
+                 t3 = load_step<SMEM>(steps, s + 3);
     const float p0 = *reinterpret_cast<const float*>(pb + __float_as_int(t0.z));
     const float p1 = *reinterpret_cast<const float*>(pb + __float_as_int(t1.z));
     const float p2 = *reinterpret_cast<const float*>(pb + __float_as_int(t2.z));
@@ -279,7 +289,7 @@ B2A_DEV void mel_steps(const float* __restrict__ p_lane, const float4* __restric
     mel_step_apply(t3, p3, acc0, acc1, so_lane);
   }
   for (; s < s1; ++s) {
-    const float4 t = __ldg(steps + s);
+    const float4 t = load_step<SMEM>(steps, s);
     mel_step_apply(t, *reinterpret_cast<const float*>(pb + __float_as_int(t.z)), acc0, acc1, so_lane);
   }
 }
@@ -389,6 +399,12 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   constexpr int SUB = P::SUB, NIT = NW * SUB;
+  // one-CTA-per-SM plans: the interpreted mel program lives in shared memory behind the tables (kStepsSmemMax steps of room)
+  constexpr bool STEPS_SMEM = P::MINB == 1 && MEL == 0 && !cplx;
+  float4* s_steps = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);
+  const bool steps_in_smem = STEPS_SMEM && prm.fb_steps != nullptr && prm.n_steps <= kStepsSmemMax;
+  if (steps_in_smem)
+    for (int i = threadIdx.x; i < prm.n_steps; i += P::NTHREADS) s_steps[i] = __ldg(prm.fb_steps + i);
   __shared__ float s_part[PRE == PRE_KALDI ? NW * FT : 1];   // Kaldi: per-warp partial sums of the frame mean
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
@@ -626,8 +642,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     {
       if (BAKED) {
         mel_baked<MEL>(wsub, s_p + fl, [&](int m, float v) { s_p[out_base_words<P>(m) + fl] = v; });
+      } else if (STEPS_SMEM && steps_in_smem) {
+        mel_steps<true>(s_p + fl, s_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl);
       } else if (prm.fb_steps != nullptr) {
-        mel_steps(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl);
+        mel_steps<false>(s_p + fl, prm.fb_steps, prm.chunk_s[wsub], prm.chunk_s[wsub + 1], s_p + fl);
       } else {
         // generic path: arbitrary filterbank, one short loop per filter
         const int ma = prm.chunk_m[wsub], mb = prm.chunk_m[wsub + 1];
@@ -1279,7 +1297,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     }
   }
   const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
-                                             P::N + P::TW_WORDS);
+                                             P::N + P::TW_WORDS) +
+                      ((P::MINB == 1 && MEL == 0 && SPEC != SK_CPLX) ? sizeof(float4) * size_t(kStepsSmemMax) : 0);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
