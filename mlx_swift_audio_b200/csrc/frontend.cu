@@ -107,7 +107,8 @@ template <> struct TwTable<Plan512> { static B2A_DEV const float2* get() { retur
 template <> struct TwTable<Plan1920> { static B2A_DEV const float2* get() { return c_tw1920; } };
 
 enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
-constexpr int kStepsSmemMax = 2048;   // mel-program steps a one-CTA-per-SM kernel keeps in shared memory (32 KB)
+// mel-program steps a kernel keeps in shared memory when its plan leaves the room: 32 KB with one CTA per SM (1920), 16 KB with two (512)
+template <class P> constexpr int steps_smem_max() { return P::MINB == 1 ? 2048 : (P::MINB == 2 ? 1024 : 0); }
 // Post-processing of a finished mel value.  POST_RUNTIME: log mode / Whisper normalisation are kernel parameters and the
 // filterbank is the interpreted step program (any bank); the other kinds belong to the baked banks of mel_baked.h.
 enum PostKind { POST_RUNTIME = 0, POST_WNORM = 1, POST_LN = 2 };
@@ -266,7 +267,7 @@ B2A_DEV void mel_step_apply(const float4& t, float pk, float& acc0, float& acc1,
 // mostly L2 hits there, because the cp.async traffic of the PCM staging sweeps the L1)
 template <bool SMEM>
 B2A_DEV float4 load_step(const float4* steps, int s) {
-  return SMEM ? steps[s] : __ldg(steps + s);
+  return SMEM ? steps[s] : __ldg(steps + s);   // (an L1::evict_last hint on the global loads changed nothing: measured)
 }
 
 template <bool SMEM>
@@ -399,8 +400,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
   float2* s_tw = reinterpret_cast<float2*>(s_wt + N);       // inter-stage twiddles [n2][k1-1]
   constexpr int SUB = P::SUB, NIT = NW * SUB;
-  // one-CTA-per-SM plans: the interpreted mel program lives in shared memory behind the tables (kStepsSmemMax steps of room)
-  constexpr bool STEPS_SMEM = P::MINB == 1 && MEL == 0 && !cplx;
+  // plans with one or two CTAs per SM: the interpreted mel program lives in shared memory behind the tables
+  constexpr int kStepsSmemMax = steps_smem_max<P>();
+  constexpr bool STEPS_SMEM = kStepsSmemMax > 0 && MEL == 0 && !cplx;
   float4* s_steps = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);
   const bool steps_in_smem = STEPS_SMEM && prm.fb_steps != nullptr && prm.n_steps <= kStepsSmemMax;
   if (steps_in_smem)
@@ -1298,7 +1300,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
                                              P::N + P::TW_WORDS) +
-                      ((P::MINB == 1 && MEL == 0 && SPEC != SK_CPLX) ? sizeof(float4) * size_t(kStepsSmemMax) : 0);
+                      ((MEL == 0 && SPEC != SK_CPLX) ? sizeof(float4) * size_t(steps_smem_max<P>()) : 0);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
   cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
@@ -1360,15 +1362,24 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   // at compile time on the post-processing and the output layout (small code: the whole tile loop stays inside the
   // instruction cache); everything else runs the run-time-configured kernel.
   int post = -1;
-  const bool ragged = a.clip_tab != nullptr;   // per-clip lengths: run-time-configured kernels, except Whisper 128-mel (below)
-  if (ragged && a.bank.baked_id == 1 && spec == SK_POWER && !a.post_affine && a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode == OUT_TM &&
-      a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE)
-    return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM, true>(a, st, launches, err);
-  if (!ragged && a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
+  const bool ragged = a.clip_tab != nullptr;   // per-clip lengths: RAGGED instantiations
+  if (a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }
   const int id = a.bank.baked_id, om = a.out_mode;
+  if (ragged) {
+    // the headline front ends keep their tuned kernels (Whisper 128 (T', M) and (M, T'), Fun-ASR LFR, CAM++ fbank); every other
+    // ragged call runs the run-time-configured kernel of its plan (launch_plan forwards to the RAGGED instantiation)
+    if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE) {
+      if (post == POST_WNORM && id == 1 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM, true>(a, st, launches, err);
+      if (post == POST_WNORM && id == 1 && om == OUT_MT) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_MT, true>(a, st, launches, err);
+      if (post == POST_LN && id == 3 && om == OUT_LFR) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, OUT_LFR, true>(a, st, launches, err);
+    }
+    if (a.n_fft == 512 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_KALDI && post == POST_LN && id == 4 && om == OUT_TM)
+      return launch_plan<Plan512, PRE_KALDI, SK_POWER, 4, POST_LN, OUT_TM, true>(a, st, launches, err);
+    post = -1;
+  }
   if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE) {
     if (post == POST_WNORM && id == 1 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM>(a, st, launches, err);
     if (post == POST_WNORM && id == 1 && om == OUT_MT) return launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_MT>(a, st, launches, err);
