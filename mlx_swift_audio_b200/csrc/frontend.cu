@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     for (int i = threadIdx.x; i < prm.n_steps; i += P::NTHREADS) s_steps[i] = __ldg(prm.fb_steps + i);
   __shared__ float s_part[PRE == PRE_KALDI ? NW * FT : 1];   // Kaldi: per-warp partial sums of the frame mean
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fl = lane % FT, wsub = warp * SUB + lane / FT;  // frame lane; item / chunk slot of this half-warp
+  // frame lane; item / chunk slot of this (half-)warp.  The two half-warps of a 16-frame plan take slots NW apart (not adjacent):
+  // their stage-A items then start 16 samples apart, so the 32 lanes' PCM loads (row pitch HOP + 1) fall into 32 different banks
+  const int fl = lane % FT, wsub = warp + NW * (lane / FT);
 
   // ---- 0. per-CTA tables (once): window in item-major order, twiddles (the loop-top barrier publishes them) ----
   for (int i = tid; i < N; i += P::NTHREADS) {
