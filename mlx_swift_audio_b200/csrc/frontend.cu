@@ -41,6 +41,11 @@
 #include "internal.h"
 #include "mel_baked.h"
 
+// 1 = interior tiles of the standard 7/6 LFR stacking take the division-free store (0 keeps the generic segment loop: A/B switch)
+#ifndef B2A_LFR_FAST
+#define B2A_LFR_FAST 1
+#endif
+
 namespace b2a {
 
 // ------------------------------------------------------------------------------------------------
@@ -716,6 +721,30 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
           const int lm = prm.lfr_m, ln = prm.lfr_n, left = (lm - 1) / 2;
           const int T = int(n_frames), last_row = int(lfr_rows) - 1;
+          if (B2A_LFR_FAST && lm == 7 && ln == 6 && f0 > 0 && f0 + FT < T) {
+            // Interior tile of the standard 7/6 stacking (no replicated edge frame, all FT rows valid).  The output of a clip is a
+            // stream of M-float slots, slot(i, j) = 7 i + j; frame t (u = t + 3) is element j = u - 6 i of row i = u / 6, i.e. slot
+            // u + u / 6, and when u is a multiple of 6 also element 6 of row i - 1: the slot just before.  Rows warp, warp + NW, ...
+            // of the tile as in the (T', M) store; no per-segment division, no skipped segments.
+            constexpr int NF = FT / NW;
+            const bool extra = FT % NW != 0 && warp + NF * NW < FT;   // warp-uniform
+            auto put_row = [&](int x) {
+              const int u = f0 + x + 3, i1 = u / 6;
+              const bool own = i1 <= last_row, dup = u == 6 * i1;     // (i1 - 1 <= last_row always: u <= T + 1)
+              float* d = dst + (long long)(u + i1) * MB + lane;
+#pragma unroll
+              for (int c = 0; c < NC; ++c) {
+                if (c < MB / 32 || lane < MB % 32) {
+                  const float v = post(srow[c][x]);
+                  if (own) d[c * 32] = v;
+                  if (dup) d[c * 32 - MB] = v;
+                }
+              }
+            };
+#pragma unroll
+            for (int i = 0; i < NF; ++i) put_row(warp + i * NW);
+            if (extra) put_row(warp + NF * NW);
+          } else {
           int i_lo = f0 + left - (lm - 1) < 0 ? 0 : (f0 + left - (lm - 1)) / ln;
           int i_hi = (f0 + rows - 1 + left) / ln;
           if (f0 + rows >= T || i_hi > last_row) i_hi = last_row;
@@ -731,6 +760,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 #pragma unroll
             for (int c = 0; c < MB / 32; ++c) d[c * 32] = post(srow[c][x]);
             if (MB % 32 != 0 && lane < MB % 32) d[(MB / 32) * 32] = post(srow[NC - 1][x]);
+          }
           }
         }
       }
@@ -963,6 +993,80 @@ __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ 
       for (int u = 0; u < 8; ++u) dst[(r + 8 * u) * dim + col] = do_var ? (v[u] - mean) / denom : v[u] - mean;
     }
     for (; r < rows; r += 8) dst[r * dim + col] = do_var ? (src[r * dim + col] - mean) / denom : src[r * dim + col] - mean;
+  }
+}
+
+// The same statistics for clips of at most 8 * RPT rows (Fun-ASR CMVN: ceil(2001 / 6) = 334 rows of 560): a thread keeps its
+// <= RPT rows of the column in REGISTERS, so the slab is read once (all loads in flight together) and the variance and the
+// normalisation run out of registers -- no second and third pass over L2, a third of the instructions of colstat_kernel (which
+// is bound by instruction issue, not by memory: ~39 instructions per element, ten of them the IEEE division).  Same layout
+// (32 columns x 8 row groups), same summation order per column.  The quotient (x - mean) / denom is one reciprocal per column
+// and a Newton correction per element (the fast path of the IEEE division without its range check; the denominators are
+// >= 1e-6 and the quotients far from the fp32 range limits).
+template <int RPT>
+__global__ void __launch_bounds__(256) colstat_reg_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int dim,
+                                                          int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
+  __shared__ float s_red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  const long long clip = blockIdx.y;
+  int nrows = int(rows);
+  if (clip_tab != nullptr) {
+    const int4 ci = clip_tab[clip];
+    nrows = tab_rows == 2 ? ci.z : ci.y;
+  }
+  const bool ok = col < dim;
+  const int nr = ok && nrows > ry ? (nrows - ry + 7) >> 3 : 0;   // rows ry, ry + 8, ... of this thread
+  // rows of the thread: one 64-bit pointer walked by a 32-bit byte step
+  const long long off0 = clip * rows * dim + (long long)ry * dim + col;
+  const char* __restrict__ src = reinterpret_cast<const char*>(in + off0);
+  char* __restrict__ dst = reinterpret_cast<char*>(out + off0);
+  const unsigned step = 32u * unsigned(dim);   // bytes between rows r and r + 8
+  float v[RPT];
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    v[u] = u < nr ? *reinterpret_cast<const float*>(src) : 0.0f;
+    src += step;
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) s += v[u];
+  s_red[ry][cx] = s;
+  __syncthreads();
+  float mean = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += s_red[i][cx];
+  mean = mean / float(nrows);
+  if (!do_var) {
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const float r = v[u] - mean;
+      if (u < nr) *reinterpret_cast<float*>(dst) = r;
+      dst += step;
+    }
+    return;
+  }
+  __syncthreads();
+  float q = 0.0f;
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    v[u] -= mean;
+    q = fmaf(u < nr ? v[u] : 0.0f, v[u], q);
+  }
+  s_red[ry][cx] = q;
+  __syncthreads();
+  float var = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) var += s_red[i][cx];
+  var = var / float(nrows);
+  const float denom = sqrtf(var) + 1e-6f;
+  const float inv = 1.0f / denom;
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const float q0 = v[u] * inv;
+    const float r = fmaf(fmaf(-q0, denom, v[u]), inv, q0);
+    if (u < nr) *reinterpret_cast<float*>(dst) = r;
+    dst += step;
   }
 }
 
@@ -1438,8 +1542,38 @@ static int launch_colstat4(const float* in, float* out, int64_t batch, int64_t r
   return B2A_OK;
 }
 
+// Register-resident statistics kernel for clips of at most 512 rows (-> true when launched)
+#ifndef B2A_COLSTAT_REG
+#define B2A_COLSTAT_REG 1
+#endif
+template <int RPT>
+static void launch_colstat_reg_t(const float* in, float* out, int64_t batch, int64_t rows, int dim, int do_var, const void* clip_tab,
+                                 int tab_rows, cudaStream_t st) {
+  dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));
+  colstat_reg_kernel<RPT><<<grid, 256, 0, st>>>(in, out, rows, dim, do_var, static_cast<const int4*>(clip_tab), tab_rows);
+}
+static bool launch_colstat_reg(const float* in, float* out, int64_t batch, int64_t rows, int dim, int do_var, const void* clip_tab, int tab_rows,
+                               cudaStream_t st, int* launches, std::string* err, int* rc) {
+  if (!B2A_COLSTAT_REG || rows > 512 || dim > (1 << 20)) return false;
+  if (rows <= 128) launch_colstat_reg_t<16>(in, out, batch, rows, dim, do_var, clip_tab, tab_rows, st);
+  else if (rows <= 256) launch_colstat_reg_t<32>(in, out, batch, rows, dim, do_var, clip_tab, tab_rows, st);
+  else if (rows <= 384) launch_colstat_reg_t<48>(in, out, batch, rows, dim, do_var, clip_tab, tab_rows, st);
+  else launch_colstat_reg_t<64>(in, out, batch, rows, dim, do_var, clip_tab, tab_rows, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *rc = cuda_fail(e, "colstat_reg_kernel launch", err);
+    return true;
+  }
+  *launches += 1;
+  *rc = B2A_OK;
+  return true;
+}
+
 int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
                 void* stream, int* launches, std::string* err, const void* clip_tab) {
+  int rc = B2A_OK;
+  if (mean == nullptr && launch_colstat_reg(in, out, batch, rows, dim, 1, clip_tab, 2, static_cast<cudaStream_t>(stream), launches, err, &rc))
+    return rc;
   if (mean == nullptr && colstat_use_vec(in, out, rows, dim))
     return launch_colstat4(in, out, batch, rows, dim, 1, clip_tab, 2, static_cast<cudaStream_t>(stream), launches, err);
   dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));
@@ -1451,6 +1585,8 @@ int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int di
 }
 
 int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err, const void* clip_tab) {
+  int rc = B2A_OK;
+  if (launch_colstat_reg(inout, inout, batch, rows, dim, 0, clip_tab, 1, static_cast<cudaStream_t>(stream), launches, err, &rc)) return rc;
   if (colstat_use_vec(inout, inout, rows, dim))
     return launch_colstat4(inout, inout, batch, rows, dim, 0, clip_tab, 1, static_cast<cudaStream_t>(stream), launches, err);
   dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));

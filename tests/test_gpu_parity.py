@@ -107,6 +107,18 @@ def test_cmvn_with_stats(api, ctx):
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("dim", [560, 80, 33])
+def test_cmvn_row_counts(api, ctx, dim):
+    # every bracket of the register-resident statistics kernel (<= 128 / 256 / 384 / 512 rows), its edges, and the streaming
+    # kernels beyond it; rows = 1 has zero variance (x - mean = 0 over 1e-6)
+    rng = np.random.default_rng(dim)
+    for rows in (1, 2, 7, 8, 9, 100, 128, 129, 256, 257, 334, 384, 385, 511, 512, 513, 700):
+        f = (rng.standard_normal((3, rows, dim)) * rng.uniform(0.1, 5.0, (1, 1, dim)) + rng.uniform(-8, 2, (1, 1, dim))).astype(np.float32)
+        got = api.applyCMVN(f, ctx=ctx)
+        want = np.stack([R.apply_cmvn(a) for a in f])
+        assert_feat_close(got, want, tol=2e-4, what=f"cmvn rows={rows} dim={dim}")
+
+
 @pytest.mark.parametrize("n", [32000, 400, 16000 + 123])
 def test_kaldi_fbank(api, ctx, n):
     x = synth.pcm(2, n, seed=1004)
