@@ -1070,6 +1070,81 @@ __global__ void __launch_bounds__(256) colstat_reg_kernel(const float* __restric
   }
 }
 
+// The same statistics for clips whose CW-column slab (rows x CW floats) fits shared memory (CAM++ mean-norm: 1998 rows of 80):
+// the slab is copied in ONCE with 16-byte cp.async (all copies of the block in flight together), reduced and normalised out of
+// shared memory, and written back -- one DRAM read and one write instead of the two reads of the streaming kernels, whose
+// slabs (512 resident clips x 639 KB) do not survive in the L2.  Three blocks per SM overlap each other's load / store phases.
+// Column sums run over rows g, g + G, ... (G = 256 / CW row groups) and are combined in fixed order: deterministic.
+template <int CW>
+__global__ void __launch_bounds__(256) colstat_smem_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int dim,
+                                                           int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
+  extern __shared__ __align__(16) float s_slab[];   // [row][CW]
+  __shared__ float s_red[256];
+  __shared__ float s_stat[2 * CW];
+  constexpr int Q = CW / 4, G = 256 / CW;
+  const int tid = threadIdx.x;
+  const long long clip = blockIdx.y;
+  const int c0 = int(blockIdx.x) * CW;
+  int nrows = int(rows);
+  if (clip_tab != nullptr) {
+    const int4 ci = clip_tab[clip];
+    nrows = tab_rows == 2 ? ci.z : ci.y;
+  }
+  const float* __restrict__ src = in + clip * rows * dim + c0;
+  float* __restrict__ dst = out + clip * rows * dim + c0;
+  const int cwq = (dim - c0) / 4 < Q ? (dim - c0) / 4 : Q;   // float4 columns of this chunk (the last chunk may be narrower)
+  const int q = tid % Q, r0 = tid / Q;
+  if (q < cwq) {
+    const unsigned sbase = static_cast<unsigned>(__cvta_generic_to_shared(s_slab + 4 * q));
+    for (int r = r0; r < nrows; r += 256 / Q)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + unsigned(r) * (CW * 4)), "l"(src + (long long)r * dim + 4 * q));
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+  const int c = tid % CW, g = tid / CW;   // (columns past a narrow last chunk hold stale shared memory: computed, never stored)
+  {
+    float a = 0.0f;
+    for (int r = g; r < nrows; r += G) a += s_slab[r * CW + c];
+    s_red[tid] = a;
+  }
+  __syncthreads();
+  if (tid < CW) {
+    float m = 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < G; ++i) m += s_red[i * CW + tid];
+    s_stat[tid] = m / float(nrows);
+    s_stat[CW + tid] = 1.0f;
+  }
+  __syncthreads();
+  if (do_var) {
+    const float mean = s_stat[c];
+    float a = 0.0f;
+    for (int r = g; r < nrows; r += G) {
+      const float d = s_slab[r * CW + c] - mean;
+      a = fmaf(d, d, a);
+    }
+    s_red[tid] = a;
+    __syncthreads();
+    if (tid < CW) {
+      float v = 0.0f;
+#pragma unroll 8
+      for (int i = 0; i < G; ++i) v += s_red[i * CW + tid];
+      s_stat[CW + tid] = sqrtf(v / float(nrows)) + 1e-6f;
+    }
+    __syncthreads();
+  }
+  if (q < cwq) {
+    const float4 mean = *reinterpret_cast<const float4*>(s_stat + 4 * q);
+    const float4 den = *reinterpret_cast<const float4*>(s_stat + CW + 4 * q);
+    for (int r = r0; r < nrows; r += 256 / Q) {
+      float4 v = *reinterpret_cast<const float4*>(s_slab + r * CW + 4 * q);
+      v.x -= mean.x; v.y -= mean.y; v.z -= mean.z; v.w -= mean.w;
+      if (do_var) { v.x = v.x / den.x; v.y = v.y / den.y; v.z = v.z / den.z; v.w = v.w / den.w; }
+      *reinterpret_cast<float4*>(dst + (long long)r * dim + 4 * q) = v;
+    }
+  }
+}
+
 // The same statistics with a thread owning FOUR adjacent columns (16-byte loads and stores: four times the bytes in flight per
 // thread; the kernel is bound by memory latency): used when dim % 4 == 0 and the buffers are 16-byte aligned.  Same two-pass
 // arithmetic per column as colstat_kernel (RG = 8 also sums in the same order).
@@ -1569,10 +1644,38 @@ static bool launch_colstat_reg(const float* in, float* out, int64_t batch, int64
   return true;
 }
 
+// Shared-memory-resident statistics kernel: 8-column slabs of at most 96 KB (-> true when launched)
+#ifndef B2A_COLSTAT_SMEM
+#define B2A_COLSTAT_SMEM 1
+#endif
+static bool launch_colstat_smem(const float* in, float* out, int64_t batch, int64_t rows, int dim, int do_var, const void* clip_tab, int tab_rows,
+                                cudaStream_t st, int* launches, std::string* err, int* rc) {
+  constexpr int CW = 8;
+  const size_t bytes = size_t(rows) * CW * sizeof(float);
+  if (!B2A_COLSTAT_SMEM || bytes > 96 * 1024 || !colstat_vec_ok(in, out, dim)) return false;
+  cudaError_t e = cudaFuncSetAttribute(colstat_smem_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);   // (per device: every launch)
+  if (e != cudaSuccess) {
+    *rc = cuda_fail(e, "cudaFuncSetAttribute", err);
+    return true;
+  }
+  dim3 grid(unsigned((dim + CW - 1) / CW), unsigned(batch));
+  colstat_smem_kernel<CW><<<grid, 256, bytes, st>>>(in, out, rows, dim, do_var, static_cast<const int4*>(clip_tab), tab_rows);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *rc = cuda_fail(e, "colstat_smem_kernel launch", err);
+    return true;
+  }
+  *launches += 1;
+  *rc = B2A_OK;
+  return true;
+}
+
 int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
                 void* stream, int* launches, std::string* err, const void* clip_tab) {
   int rc = B2A_OK;
   if (mean == nullptr && launch_colstat_reg(in, out, batch, rows, dim, 1, clip_tab, 2, static_cast<cudaStream_t>(stream), launches, err, &rc))
+    return rc;
+  if (mean == nullptr && launch_colstat_smem(in, out, batch, rows, dim, 1, clip_tab, 2, static_cast<cudaStream_t>(stream), launches, err, &rc))
     return rc;
   if (mean == nullptr && colstat_use_vec(in, out, rows, dim))
     return launch_colstat4(in, out, batch, rows, dim, 1, clip_tab, 2, static_cast<cudaStream_t>(stream), launches, err);
@@ -1587,6 +1690,7 @@ int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int di
 int launch_mean_norm(float* inout, int64_t batch, int64_t rows, int dim, void* stream, int* launches, std::string* err, const void* clip_tab) {
   int rc = B2A_OK;
   if (launch_colstat_reg(inout, inout, batch, rows, dim, 0, clip_tab, 1, static_cast<cudaStream_t>(stream), launches, err, &rc)) return rc;
+  if (launch_colstat_smem(inout, inout, batch, rows, dim, 0, clip_tab, 1, static_cast<cudaStream_t>(stream), launches, err, &rc)) return rc;
   if (colstat_use_vec(inout, inout, rows, dim))
     return launch_colstat4(inout, inout, batch, rows, dim, 0, clip_tab, 1, static_cast<cudaStream_t>(stream), launches, err);
   dim3 grid(unsigned((dim + 31) / 32), unsigned(batch));

@@ -107,7 +107,7 @@ def test_cmvn_with_stats(api, ctx):
     np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("dim", [560, 80, 33])
+@pytest.mark.parametrize("dim", [560, 80, 100, 33])
 def test_cmvn_row_counts(api, ctx, dim):
     # every bracket of the register-resident statistics kernel (<= 128 / 256 / 384 / 512 rows), its edges, and the streaming
     # kernels beyond it; rows = 1 has zero variance (x - mean = 0 over 1e-6)
