@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
   constexpr bool VEC = HOP == 4;
   constexpr int YP = VEC ? (((NFFT / 4) % 2 == 1) ? NFFT : NFFT + 4) : NFFT + 1;
   static_assert(NFFT % HOP == 0 && R == 4 && NFFT % 4 == 0, "built for 4x overlap");
-  __shared__ __align__(16) float s_y[kIstftThreads * YP];  // windowed frames of the block, later the staged output
+  __shared__ __align__(16) float s_y[kIstftThreads * YP];  // windowed frames of the block
+  __shared__ float s_stage[HOP == 4 ? 1 : kIstftThreads * HOP];   // hop 5: per-warp output staging
 
   const int tid = threadIdx.x, lane = tid & 31;
   const long long clip = blockIdx.y;
@@ -313,22 +314,21 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       }
     }
   } else {
-    // hop 5: stage the block's segments and write them out contiguously
-    __syncthreads();
-    float* s_stage = s_y;
+    // hop 5: a segment is 20 bytes, so the warp stages its 32 segments (160 floats, lane stride 5: conflict-free) in its own
+    // rows of a separate staging buffer and writes them out as contiguous 128-byte runs -- no block barrier (the frame tile
+    // s_y is still being read by other warps), only __syncwarp.  The emitting lanes of a warp are a contiguous lane range.
     if (emit) {
 #pragma unroll
-      for (int i = 0; i < HOP; ++i) s_stage[(tid - HALO) * HOP + i] = o[i];
+      for (int i = 0; i < HOP; ++i) s_stage[tid * HOP + i] = o[i];
     }
-    __syncthreads();
-    // block emits segments [max(seg0, R/2), min(seg0 + SEG_PER_BLOCK, nSeg - R/2))
-    const int a = seg0 > R / 2 ? seg0 : R / 2;
-    int b = seg0 + SEG_PER_BLOCK;
-    if (b > nSeg - R / 2) b = nSeg - R / 2;
-    const int n = (b - a) * HOP;
-    const float* src = s_stage + (a - seg0) * HOP;
-    float* d = dst + (long long)(a - R / 2) * HOP;
-    for (int i = tid; i < n; i += kIstftThreads) d[i] = src[i];
+    __syncwarp();
+    const unsigned em = __ballot_sync(0xffffffffu, emit);
+    if (em != 0u) {
+      const int la = __ffs(em) - 1, n = __popc(em) * HOP;
+      const float* src = s_stage + ((tid - lane) + la) * HOP;
+      float* d = dst + (long long)(s - lane + la - R / 2) * HOP;   // first emitted segment of the warp
+      for (int i = lane; i < n; i += 32) d[i] = src[i];
+    }
   }
 }
 
