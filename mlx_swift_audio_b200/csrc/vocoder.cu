@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
   constexpr int SEG_PER_BLOCK = kIstftThreads - HALO;
   // row pitch of the frame tile: hop 4 uses 128-bit accesses (pitch odd in 16-byte units), hop 5 scalar ones (odd pitch)
   constexpr bool VEC = HOP == 4;
-  constexpr int YP = VEC ? (((NFFT / 4) % 2 == 1) ? NFFT : NFFT + 4) : NFFT + 1;
+  // hop 5 (20-point frames): rows of five 16-byte units (odd pitch: conflict-free) written as float4; the gather reads the two
+  // aligned float4 that cover the five floats it needs from each row (8 LDS.128 instead of 20 LDS)
+  constexpr bool VEC5 = HOP == 5 && NFFT == 20;
+  constexpr int YP = (VEC || VEC5) ? (((NFFT / 4) % 2 == 1) ? NFFT : NFFT + 4) : NFFT + 1;
   static_assert(NFFT % HOP == 0 && R == 4 && NFFT % 4 == 0, "built for 4x overlap");
   __shared__ __align__(16) float s_y[kIstftThreads * YP];  // windowed frames of the block
   __shared__ float s_stage[HOP == 4 ? 1 : kIstftThreads * HOP];   // hop 5: per-warp output staging
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
     }
     c2r(xr, xi, y);
     // frames outside [0, nF) have magnitude 0 -> exact zeros
-    if (VEC) {
+    if (VEC || VEC5) {
       float4* row = reinterpret_cast<float4*>(s_y + tid * YP);
 #pragma unroll
       for (int q = 0; q < NFFT / 4; ++q)
@@ -266,6 +269,15 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       for (int r = 1; r <= HALO; ++r) {
         const float4 a = *reinterpret_cast<const float4*>(s_y + (tid - r) * YP + r * HOP);
         o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+      }
+    } else if (VEC5) {
+#pragma unroll
+      for (int r = 0; r <= HALO; ++r) {
+        const float4* row = reinterpret_cast<const float4*>(s_y + (tid - r) * YP) + (r * HOP) / 4;
+        const float4 a = row[0], b = row[1];
+        const float t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < HOP; ++i) o[i] = r == 0 ? t[i] : o[i] + t[(r * HOP) % 4 + i];
       }
     } else {
 #pragma unroll
