@@ -81,8 +81,10 @@ B2A_DEV float sin_small(float x, float u) {
 __device__ __noinline__ float sin_huge(float x) { return sinf(x); }   // out of line: keeps the Payne-Hanek code off the hot path
 // sin(x), |x| < 4.8e4: x = k*pi + r with r in [-pi/2, pi/2] (magic-number rounding, 3-term Cody-Waite), sin(x) = (-1)^k sin(r)
 // with the degree-9 polynomial of sin_small; the parity of k goes straight into the sign bit.
+// CHECK = false: the caller has established |x| < 4.8e4 (one test per frame instead of one per bin)
+template <bool CHECK = true>
 B2A_DEV float sin_any(float x) {
-  if (!(fabsf(x) < 48000.0f)) return sin_huge(x);
+  if (CHECK && !(fabsf(x) < 48000.0f)) return sin_huge(x);
   float q = fmaf(x, 0.318309886f, 12582912.0f);   // 1.5 * 2^23: round(x / pi) lands in the mantissa
   const int k = __float_as_int(q);
   q -= 12582912.0f;
@@ -170,12 +172,23 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
         xr[k] = has_frame ? __ldg(mp + k * nFu) : -200.0f;   // exp(-200) flushes to 0: frames outside the clip contribute nothing
         ph[k] = has_frame ? __ldg(pp + k * nFu) : 0.0f;
       }
+      float hmax = 0.0f;
+#pragma unroll
+      for (int k = 0; k < F; ++k) hmax = fmaxf(hmax, fabsf(ph[k]));
+      // (fmaxf drops NaN operands: a NaN bin rides the fast path, which propagates it like sinf does; +-inf takes the slow one)
+      const bool in_range = hmax < 48000.0f;
 #pragma unroll
       for (int k = 0; k < F; ++k) {
         float m = fminf(exp_fast(xr[k]), prm.clip_hi);
         if (prm.use_clip_lo) m = fmaxf(m, prm.clip_lo);
         xr[k] = m;
-        ph[k] = sin_any(ph[k]);
+      }
+      if (in_range) {
+#pragma unroll
+        for (int k = 0; k < F; ++k) ph[k] = sin_any<false>(ph[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < F; ++k) ph[k] = sin_any<true>(ph[k]);
       }
     } else {
 #pragma unroll

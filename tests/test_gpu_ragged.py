@@ -113,6 +113,21 @@ def test_kaldi_ragged(api, ctx):
         assert_feat_close(g[b, :rows[b]], want, tol=2e-4, what=f"kaldi mean-norm ragged clip {b}")
 
 
+@pytest.mark.parametrize("longest", [100000, 500000])
+def test_kaldi_mean_norm_ragged_long_clips(api, ctx, longest):
+    # the statistics kernel is chosen by the LONGEST clip's row count: 623 rows -> the shared-memory-resident kernel, 3123 rows -> the
+    # streaming kernels; both take the per-clip row counts from the clip table
+    lengths = [5120, longest, 48011, 401, 16000]
+    x = _batch(lengths, seed=17)
+    got, rows = api.kaldiFbankCAMPPlusRagged(x, lengths, meanNorm=True, ctx=ctx)
+    g = np.asarray(got)
+    for b, n in enumerate(lengths):
+        want = R.kaldi_fbank_mean_norm(R.kaldi_fbank_camp_plus(x[b, :n]))
+        assert rows[b] == want.shape[0]
+        assert_feat_close(g[b, :rows[b]], want, tol=2e-4, what=f"kaldi mean-norm ragged clip {b} (longest {longest})")
+        assert not np.any(g[b, rows[b]:])
+
+
 def test_s3gen_ragged(api, ctx):
     lengths = [24000, 480 * 17, 24000 * 2 + 5, 1921, 9600]
     x = _batch(lengths, sr=24000, seed=17)
