@@ -48,6 +48,7 @@ WORKLOADS = {
     "hift_head": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
     "whisper128_ragged": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper 128-mel log-mel of a RAGGED batch: 1024 clips of 5..30 s (uniform) in one launch (b2a_whisper_log_mel_spectrogram_ragged)"),
     "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
+    "stft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT forward STFT of the source signal (stftHiFiGAN, n_fft 16, hop 4, reflect pad), 512 x 30 s -> real / imag (SURVEY 8a row a22)"),
 }
 
 
@@ -159,6 +160,15 @@ class GpuWorkload:
             self._keep = win
             wp = win.ctypes.data_as(C.POINTER(C.c_float))
             self.call = lambda c, i, o, sp: lib.b2a_hift_head_istft(c.h, i[0], B, frames, 16, 4, wp, C.c_float(0.99), o, sp)
+        elif name == "stft_hift":
+            frames = int(lib.b2a_vocoder_stft_num_frames(n, 16, 4))
+            self.inputs = [0.1 * torch.randn((B, n), generator=g, device=dev)]
+            self.out = torch.empty((2, B, 9, frames), device=dev)   # real and imaginary parts, one buffer
+            win = np.ascontiguousarray(api.hannWindowPeriodic(16), np.float32)
+            self._keep = win
+            wp = win.ctypes.data_as(C.POINTER(C.c_float))
+            half = B * 9 * frames * 4
+            self.call = lambda c, i, o, sp: lib.b2a_stft_hifigan(c.h, i[0], B, n, 16, 4, wp, o, C.c_void_p(o.value + half), sp)
         elif name.startswith("istft"):
             nfft, hop = (16, 4) if name == "istft_hift" else (20, 5)
             F = nfft // 2 + 1
@@ -275,6 +285,12 @@ def _cpu_clip_job(args):
         t0 = time.perf_counter()
         for _ in range(reps):
             R.hift_head_istft(h, 16, 4, R.hann_window_periodic(16))
+    elif name == "stft_hift":
+        x = synth.pcm(1, n, sample_rate=sr, seed=seed)
+        gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            R.stft_hifigan(x, 16, 4, R.hann_window_periodic(16))
     elif name.startswith("istft"):
         nfft, hop = (16, 4) if name == "istft_hift" else (20, 5)
         frames = n // hop + 1

@@ -419,8 +419,21 @@ __global__ void __launch_bounds__(256) small_stft_kernel(const __grid_constant__
   float in[NFFT];
   const long long j0 = f * HOP - PAD;
   if (j0 >= 0 && j0 + NFFT <= T) {
+    if (HOP % 4 == 0 && NFFT % 4 == 0 && (reinterpret_cast<uintptr_t>(xc + j0) & 15) == 0) {
+      // hop 4: a frame starts on a 16-byte boundary whenever the clip does -- NFFT/4 coalesced 16-byte loads per thread
+      const float4* __restrict__ x4 = reinterpret_cast<const float4*>(xc + j0);
 #pragma unroll
-    for (int n = 0; n < NFFT; ++n) in[n] = __ldg(xc + j0 + n) * prm.w[n];
+      for (int q = 0; q < NFFT / 4; ++q) {
+        const float4 v = __ldg(x4 + q);
+        in[4 * q] = v.x * prm.w[4 * q];
+        in[4 * q + 1] = v.y * prm.w[4 * q + 1];
+        in[4 * q + 2] = v.z * prm.w[4 * q + 2];
+        in[4 * q + 3] = v.w * prm.w[4 * q + 3];
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NFFT; ++n) in[n] = __ldg(xc + j0 + n) * prm.w[n];
+    }
   } else {
 #pragma unroll
     for (int n = 0; n < NFFT; ++n) {
