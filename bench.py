@@ -48,6 +48,9 @@ WORKLOADS = {
     "hift_head": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
     "whisper128_ragged": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper 128-mel log-mel of a RAGGED batch: 1024 clips of 5..30 s (uniform) in one launch (b2a_whisper_log_mel_spectrogram_ragged)"),
     "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
+    "chatterbox128": dict(batch=1024, clip_s=10.0, sr=16000, desc="S3Tokenizer / Chatterbox 128-mel log-mel (periodic Hann, (M, T') layout), 1024 x 10 s @16 kHz (SURVEY 8a row a14)"),
+    "voice_encoder": dict(batch=1024, clip_s=10.0, sr=16000, desc="Chatterbox voice-encoder 40-mel power mel ((M, T') layout, interpreted bank), 1024 x 10 s @16 kHz (SURVEY 8a row a21)"),
+    "stft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro MLXSTFT.transform (n_fft 20, hop 5): magnitude and atan2 phase, 512 x 30 s (SURVEY 8a row a26)"),
     "stft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT forward STFT of the source signal (stftHiFiGAN, n_fft 16, hop 4, reflect pad), 512 x 30 s -> real / imag (SURVEY 8a row a22)"),
 }
 
@@ -160,6 +163,12 @@ class GpuWorkload:
             self._keep = win
             wp = win.ctypes.data_as(C.POINTER(C.c_float))
             self.call = lambda c, i, o, sp: lib.b2a_hift_head_istft(c.h, i[0], B, frames, 16, 4, wp, C.c_float(0.99), o, sp)
+        elif name == "stft_kokoro":
+            frames = int(lib.b2a_vocoder_stft_num_frames(n, 20, 5))
+            self.inputs = [0.1 * torch.randn((B, n), generator=g, device=dev)]
+            self.out = torch.empty((2, B, 11, frames), device=dev)   # magnitude and phase, one buffer
+            half = B * 11 * frames * 4
+            self.call = lambda c, i, o, sp: lib.b2a_kokoro_stft_transform(c.h, i[0], B, n, 20, 5, 20, o, C.c_void_p(o.value + half), sp)
         elif name == "stft_hift":
             frames = int(lib.b2a_vocoder_stft_num_frames(n, 16, 4))
             self.inputs = [0.1 * torch.randn((B, n), generator=g, device=dev)]
@@ -210,6 +219,17 @@ class GpuWorkload:
                 frames = int(lib.b2a_whisper_num_frames(n, 0))
                 self.out = torch.empty((B, frames, nm), device=dev)
                 self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram(c.h, i[0], B, n, nm, 0, o, sp)
+            elif name == "chatterbox128":
+                frames = int(lib.b2a_whisper_num_frames(n, 0))   # the last STFT frame is dropped, as in the Whisper front end
+                self.out = torch.empty((B, 128, frames), device=dev)
+                self.call = lambda c, i, o, sp: lib.b2a_log_mel_spectrogram_chatterbox(c.h, i[0], B, n, 128, 0, o, sp)
+            elif name == "voice_encoder":
+                cfg = _lib.VoiceEncConfig()
+                lib.b2a_voice_enc_config_default(C.byref(cfg))
+                frames = int(lib.b2a_stft_num_frames(n, cfg.n_fft, cfg.hop_size, 1))
+                self.out = torch.empty((B, cfg.num_mels, frames), device=dev)
+                self._keep = cfg
+                self.call = lambda c, i, o, sp: lib.b2a_voice_encoder_melspectrogram(c.h, i[0], B, n, C.byref(cfg), o, sp)
             elif name == "funasr":
                 frames = int(lib.b2a_funasr_num_frames(n))
                 rows = int(lib.b2a_lfr_num_rows(frames, 6))
@@ -285,6 +305,12 @@ def _cpu_clip_job(args):
         t0 = time.perf_counter()
         for _ in range(reps):
             R.hift_head_istft(h, 16, 4, R.hann_window_periodic(16))
+    elif name == "stft_kokoro":
+        x = synth.pcm(1, n, sample_rate=sr, seed=seed)
+        gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            R.kokoro_transform(x)
     elif name == "stft_hift":
         x = synth.pcm(1, n, sample_rate=sr, seed=seed)
         gen = time.perf_counter() - t0
@@ -317,6 +343,10 @@ def _cpu_clip_job(args):
                 R.kaldi_fbank_mean_norm(R.kaldi_fbank_camp_plus(x))
             elif name == "s3gen":
                 R.s3gen_mel_spectrogram(x)
+            elif name == "chatterbox128":
+                R.log_mel_spectrogram_chatterbox(x, 128)
+            elif name == "voice_encoder":
+                R.voice_encoder_melspectrogram(x)
     return time.perf_counter() - t0, gen
 
 

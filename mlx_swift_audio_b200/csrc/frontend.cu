@@ -339,12 +339,36 @@ B2A_DEV constexpr int out_base_words(int m) {
   return ((m / CAP) * 2 * P::N2 + P::N2 + 1) * P::FT + (CAP * (m / CAP)) % P::FT + (m % CAP) * (P::FT + 1);
 }
 
-// Edge tiles (2 of 94 for a 30 s clip): kept out of line so that the 64-bit index arithmetic of the padding map does not sit
-// in the instruction stream of the interior tiles (the hot loop has to stay inside the 32 KB the instruction cache serves at
-// full rate: tools/microbench/icache.cu).
+// Edge tiles (2 of 94 for a 30 s clip, 2 of 32 for a 10 s one): kept out of line so that the 64-bit index arithmetic of the padding
+// map does not sit in the instruction stream of the interior tiles (the hot loop has to stay inside the 32 KB the instruction
+// cache serves at full rate: tools/microbench/icache.cu).  Like the interior tiles they are ASYNCHRONOUS: every sample is a
+// 4-byte cp.async from its mapped source index (same map as fetch_padded; zero padding is a plain shared-memory store), so an
+// edge tile prefetched behind stage A lands during stage B / mel / store instead of stalling the CTA on ~17 rounds of global
+// loads; the modulo of the reference's repeated reflection only runs for clips shorter than the pad.
+template <class P>
 __device__ __noinline__ void stage_pcm_edge(const float* __restrict__ xc, float* __restrict__ buf, long long p0, long long pad_left,
-                                            long long n_samples, long long n_eff, int pad_mode, int tid, int ts, int hop, int nthreads) {
-  for (int s = tid; s < ts; s += nthreads) buf[s + s / hop] = fetch_padded(xc, p0 + s, pad_left, n_samples, n_eff, pad_mode);
+                                            long long n_samples, long long n_eff, int pad_mode, int tid) {
+  for (int s = tid; s < P::TS; s += P::NTHREADS) {
+    long long j = p0 + s - pad_left;
+    if (j < 0 || j >= n_eff) {
+      if (pad_mode != PAD_REFLECT) {
+        j = -1;
+      } else if (n_eff == 1) {
+        j = 0;
+      } else if (j < 0) {
+        long long t = -j - 1;
+        if (t >= n_eff - 1) t %= n_eff - 1;
+        j = t + 1;
+      } else {
+        long long t = j - n_eff;
+        if (t >= n_eff - 1) t %= n_eff - 1;
+        j = n_eff - 2 - t;
+      }
+    }
+    float* d = buf + s + s / P::HOP;
+    if (j >= 0 && j < n_samples) cp_async4(d, xc + j);
+    else *d = 0.0f;
+  }
 }
 
 // Stages the PCM of tile (clip, f0) into `buf` (skewed rows, pitch HOP+1).  Interior tiles use cp.async so that
@@ -370,7 +394,7 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
       }
     }
   } else {
-    stage_pcm_edge(xc, buf, p0, prm.pad_left, n_samples, n_eff, prm.pad_mode, tid, P::TS, HOP, P::NTHREADS);
+    stage_pcm_edge<P>(xc, buf, p0, prm.pad_left, n_samples, n_eff, prm.pad_mode, tid);
   }
 }
 
