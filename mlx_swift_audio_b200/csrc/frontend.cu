@@ -344,30 +344,41 @@ B2A_DEV constexpr int out_base_words(int m) {
 // cache serves at full rate: tools/microbench/icache.cu).  Like the interior tiles they are ASYNCHRONOUS: every sample is a
 // 4-byte cp.async from its mapped source index (same map as fetch_padded; zero padding is a plain shared-memory store), so an
 // edge tile prefetched behind stage A lands during stage B / mel / store instead of stalling the CTA on ~17 rounds of global
-// loads; the modulo of the reference's repeated reflection only runs for clips shorter than the pad.
+// loads; rows that lie inside the clip take the interior tiles' row copy, only the rows that touch the padding go through the
+// map, and the modulo of the reference's repeated reflection only runs for clips shorter than the pad.
 template <class P>
 __device__ __noinline__ void stage_pcm_edge(const float* __restrict__ xc, float* __restrict__ buf, long long p0, long long pad_left,
                                             long long n_samples, long long n_eff, int pad_mode, int tid) {
-  for (int s = tid; s < P::TS; s += P::NTHREADS) {
-    long long j = p0 + s - pad_left;
-    if (j < 0 || j >= n_eff) {
-      if (pad_mode != PAD_REFLECT) {
-        j = -1;
-      } else if (n_eff == 1) {
-        j = 0;
-      } else if (j < 0) {
-        long long t = -j - 1;
-        if (t >= n_eff - 1) t %= n_eff - 1;
-        j = t + 1;
-      } else {
-        long long t = j - n_eff;
-        if (t >= n_eff - 1) t %= n_eff - 1;
-        j = n_eff - 2 - t;
-      }
+  const int lane = tid & 31, warp = tid >> 5;
+  const long long j0 = p0 - pad_left;
+  for (int row = warp; row < P::NROWS; row += P::NWARPS) {
+    const long long jr = j0 + (long long)row * P::HOP;
+    float* d = buf + row * P::PITCH + lane;
+    if (jr >= 0 && jr + P::HOP <= n_samples) {   // (warp-uniform) the row lies inside the clip: the interior tiles' row copy
+#pragma unroll
+      for (int q = 0; q < P::HOP / 32; ++q) cp_async4(d + q * 32, xc + jr + lane + q * 32);
+      continue;
     }
-    float* d = buf + s + s / P::HOP;
-    if (j >= 0 && j < n_samples) cp_async4(d, xc + j);
-    else *d = 0.0f;
+    for (int q = 0; q < P::HOP / 32; ++q) {      // rows that touch the padding: sample by sample through the index map
+      long long j = jr + lane + q * 32;
+      if (j < 0 || j >= n_eff) {
+        if (pad_mode != PAD_REFLECT) {
+          j = -1;
+        } else if (n_eff == 1) {
+          j = 0;
+        } else if (j < 0) {
+          long long t = -j - 1;
+          if (t >= n_eff - 1) t %= n_eff - 1;
+          j = t + 1;
+        } else {
+          long long t = j - n_eff;
+          if (t >= n_eff - 1) t %= n_eff - 1;
+          j = n_eff - 2 - t;
+        }
+      }
+      if (j >= 0 && j < n_samples) cp_async4(d + q * 32, xc + j);
+      else d[q * 32] = 0.0f;
+    }
   }
 }
 
