@@ -160,17 +160,26 @@ B2A_DEV int enc_ordered(float f) {
 }
 B2A_DEV float dec_ordered(int e) { return __int_as_float(e >= 0 ? e : e ^ 0x7fffffff); }
 
-// value of padded coordinate p of one clip (generic / edge path)
-B2A_DEV float fetch_padded(const float* __restrict__ xc, long long p, long long pad_left, long long n_samples,
-                           long long n_eff, int pad_mode) {
+// Source index of padded coordinate p of one clip, or -1 where the padding is zero (the one statement of the padding rules:
+// reflectPad with the reference's repeated same-direction reflection for clips shorter than the pad, S3TokenizerUtils.swift:266-298,
+// and MLX.padded's zeros).  The modulo only runs when the overshoot exceeds one reflection.
+B2A_DEV long long padded_index(long long p, long long pad_left, long long n_eff, int pad_mode) {
   long long j = p - pad_left;
   if (j < 0 || j >= n_eff) {
-    if (pad_mode != PAD_REFLECT) return 0.0f;
-    if (n_eff == 1) j = 0;
-    else if (j < 0) j = ((-j - 1) % (n_eff - 1)) + 1;
-    else j = n_eff - 2 - ((j - n_eff) % (n_eff - 1));
+    if (pad_mode != PAD_REFLECT) return -1;
+    if (n_eff == 1) return 0;
+    long long t = j < 0 ? -j - 1 : j - n_eff;
+    if (t >= n_eff - 1) t %= n_eff - 1;
+    j = j < 0 ? t + 1 : n_eff - 2 - t;
   }
-  return j < n_samples ? __ldg(xc + j) : 0.0f;
+  return j;
+}
+
+// value of padded coordinate p of one clip (samples in [n_samples, n_eff) are the caller's zero tail)
+B2A_DEV float fetch_padded(const float* __restrict__ xc, long long p, long long pad_left, long long n_samples,
+                           long long n_eff, int pad_mode) {
+  const long long j = padded_index(p, pad_left, n_eff, pad_mode);
+  return j >= 0 && j < n_samples ? __ldg(xc + j) : 0.0f;
 }
 
 // Shared-memory word offset (relative to the lane's frame start) of sample o = N2*n1 + n2 in the skewed
@@ -342,7 +351,7 @@ B2A_DEV constexpr int out_base_words(int m) {
 // Edge tiles (2 of 94 for a 30 s clip, 2 of 32 for a 10 s one): kept out of line so that the 64-bit index arithmetic of the padding
 // map does not sit in the instruction stream of the interior tiles (the hot loop has to stay inside the 32 KB the instruction
 // cache serves at full rate: tools/microbench/icache.cu).  Like the interior tiles they are ASYNCHRONOUS: every sample is a
-// 4-byte cp.async from its mapped source index (same map as fetch_padded; zero padding is a plain shared-memory store), so an
+// 4-byte cp.async from its mapped source index (`padded_index`; zero padding is a plain shared-memory store), so an
 // edge tile prefetched behind stage A lands during stage B / mel / store instead of stalling the CTA on ~17 rounds of global
 // loads; rows that lie inside the clip take the interior tiles' row copy, only the rows that touch the padding go through the
 // map, and the modulo of the reference's repeated reflection only runs for clips shorter than the pad.
@@ -360,22 +369,7 @@ __device__ __noinline__ void stage_pcm_edge(const float* __restrict__ xc, float*
       continue;
     }
     for (int q = 0; q < P::HOP / 32; ++q) {      // rows that touch the padding: sample by sample through the index map
-      long long j = jr + lane + q * 32;
-      if (j < 0 || j >= n_eff) {
-        if (pad_mode != PAD_REFLECT) {
-          j = -1;
-        } else if (n_eff == 1) {
-          j = 0;
-        } else if (j < 0) {
-          long long t = -j - 1;
-          if (t >= n_eff - 1) t %= n_eff - 1;
-          j = t + 1;
-        } else {
-          long long t = j - n_eff;
-          if (t >= n_eff - 1) t %= n_eff - 1;
-          j = n_eff - 2 - t;
-        }
-      }
+      const long long j = padded_index(p0 + (long long)row * P::HOP + lane + q * 32, pad_left, n_eff, pad_mode);
       if (j >= 0 && j < n_samples) cp_async4(d + q * 32, xc + j);
       else d[q * 32] = 0.0f;
     }
