@@ -182,3 +182,31 @@ def test_exchange_buffer_layout_is_consistent(built_lib, n_fft, n_mels):
         for f in (0, 5, 31):   # 32 consecutive filters read at one frame index fall in 32 different banks
             for m0 in range(0, n_mels - 31, 32):
                 assert len({(words[m] + f) % 32 for m in range(m0, m0 + 32)}) == 32
+
+
+def test_lfr_slot_rule_of_the_interior_tile_store():
+    """The main kernel's division-free LFR store (frontend.cu, OUT_LFR of the baked Fun-ASR bank) relies on this rule for the
+    standard 7 / 6 stacking (FunASRAudio.swift:108-154): the output of a clip is a stream of slots, slot(i, j) = 7 i + j; an
+    interior frame t (tile without frame 0 and frame T-1) fills slot u + u // 6 with u = t + 3, and also the slot before it
+    when u is a multiple of 6; every other slot belongs to an edge tile.  Checked against the oracle's applyLFR."""
+    for T in list(range(34, 300)) + [1998, 2001, 3000]:
+        feat = np.arange(T, dtype=np.float32)[:, None] * np.ones((1, 2), np.float32)   # feature value = frame index
+        src = R.apply_lfr(feat).reshape(-1, 7, 2)[:, :, 0].astype(np.int64).reshape(-1)   # slot -> source frame
+        rows = (T + 5) // 6
+        assert src.size == rows * 7
+        got = np.full(rows * 7, -1, np.int64)
+        for f0 in range(32, T, 32):
+            if f0 + 32 >= T:
+                continue   # the tile holding frame T-1 takes the generic path
+            for t in range(f0, f0 + 32):
+                u = t + 3
+                i1 = u // 6
+                if i1 <= rows - 1:
+                    assert got[u + i1] == -1
+                    got[u + i1] = t
+                if u == 6 * i1:
+                    assert got[u + i1 - 1] == -1
+                    got[u + i1 - 1] = t
+        interior = (src >= 32) & (src // 32 * 32 + 32 < T)
+        assert np.array_equal(got[interior], src[interior]), f"T={T}: interior slots"
+        assert np.all(got[~interior] == -1), f"T={T}: a slot of an edge tile was written by the interior rule"
