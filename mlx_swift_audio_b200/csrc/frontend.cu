@@ -45,6 +45,10 @@
 #ifndef B2A_LFR_FAST
 #define B2A_LFR_FAST 1
 #endif
+// 1 = the (M, T') store of the baked banks walks out_base_words() incrementally (0 keeps the per-row evaluation: A/B switch)
+#ifndef B2A_MT_WALK
+#define B2A_MT_WALK 1
+#endif
 
 namespace b2a {
 
@@ -347,6 +351,26 @@ B2A_DEV constexpr int out_base_words(int m) {
   constexpr int CAP = ((P::N2 - 1) * P::FT - (P::FT - 1)) / (P::FT + 1);
   return ((m / CAP) * 2 * P::N2 + P::N2 + 1) * P::FT + (CAP * (m / CAP)) % P::FT + (m % CAP) * (P::FT + 1);
 }
+
+// out_base_words<P>(m) for m = m0, m0 + STEP, ... without a division per row: the (M, T') store loops walk the filters with a
+// run-time m, and the compiler's code for the two constant divisions and the modulo was ~35 instructions per stored row (45 % of
+// the Chatterbox kernel).  q = m / CAP and r = m % CAP advance incrementally.
+template <class P, int STEP>
+struct OutBaseWalk {
+  static constexpr int CAP = ((P::N2 - 1) * P::FT - (P::FT - 1)) / (P::FT + 1);
+  static_assert((P::FT & (P::FT - 1)) == 0, "frame tile is a power of two");
+  int q, r;
+  B2A_DEV explicit OutBaseWalk(int m0) : q(m0 / CAP), r(m0 - (m0 / CAP) * CAP) {}
+  B2A_DEV int words() const { return (q * 2 * P::N2 + P::N2 + 1) * P::FT + ((CAP * q) & (P::FT - 1)) + r * (P::FT + 1); }
+  B2A_DEV void next() {
+    r += STEP % CAP;
+    q += STEP / CAP;
+    if (r >= CAP) {
+      r -= CAP;
+      ++q;
+    }
+  }
+};
 
 // Edge tiles (2 of 94 for a 30 s clip, 2 of 32 for a 10 s one): kept out of line so that the 64-bit index arithmetic of the padding
 // map does not sit in the instruction stream of the interior tiles (the hot loop has to stay inside the 32 KB the instruction
@@ -711,7 +735,13 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         const long long nfr = prm.n_frames;
         float* d = dst + f0 + fl;
         if (frame_ok)
-          for (int m = wsub; m < M; m += NIT) d[m * nfr] = post(s_p[out_base_words<P>(m) + fl]);
+          if (B2A_MT_WALK) {
+            OutBaseWalk<P, NIT> ob(wsub);
+            float* dm = d + wsub * nfr;
+            for (int m = wsub; m < M; m += NIT, ob.next(), dm += NIT * nfr) *dm = post(s_p[ob.words() + fl]);
+          } else {
+            for (int m = wsub; m < M; m += NIT) d[m * nfr] = post(s_p[out_base_words<P>(m) + fl]);
+          }
       } else {
         // lanes run over m: one staging pointer per 32-filter chunk (bank = (m + frame) mod 32: conflict free)
         const float* srow[NC];
@@ -825,8 +855,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         const long long nfr = prm.n_frames;
         const bool post = prm.post_affine != 0;
         auto store_mt = [&](auto fn) {
-          for (int m = wsub; m < M; m += NIT) {
-            float v = fn(s_p[out_base_words<P>(m) + fl]);
+          OutBaseWalk<P, NIT> ob(wsub);
+          for (int m = wsub; m < M; m += NIT, ob.next()) {
+            float v = fn(s_p[(B2A_MT_WALK ? ob.words() : out_base_words<P>(m)) + fl]);
             if (post) v = (v - prm.post_sub) / prm.post_div;
             if (frame_ok) dst[m * nfr] = v;
           }
