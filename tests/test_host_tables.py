@@ -210,3 +210,25 @@ def test_lfr_slot_rule_of_the_interior_tile_store():
         interior = (src >= 32) & (src // 32 * 32 + 32 < T)
         assert np.array_equal(got[interior], src[interior]), f"T={T}: interior slots"
         assert np.all(got[~interior] == -1), f"T={T}: a slot of an edge tile was written by the interior rule"
+
+
+@pytest.mark.parametrize("n_fft,n_mels,step", [(400, 128, 10), (400, 40, 10), (512, 80, 16), (1920, 80, 32)])
+def test_incremental_walk_of_the_staging_offsets(built_lib, n_fft, n_mels, step):
+    """The (M, T') store loops of the frontend kernel (OutBaseWalk in frontend.cu) advance quotient and remainder of m / CAP
+    incrementally instead of dividing per row; the walk must reproduce the library's own staging map (output_words(), through
+    b2a_debug_plan_layout) for every start slot and every filter.  step = items per pass of the plan (warps x sub-items)."""
+    import ctypes as C
+    slots = (C.c_int * (n_fft // 2 + 1))()
+    words = (C.c_int * n_mels)()
+    packed = built_lib.b2a_debug_plan_layout(n_fft, n_mels, slots, words)
+    ft, n2 = packed >> 16, packed & 0xff
+    cap = ((n2 - 1) * ft - (ft - 1)) // (ft + 1)
+    for m0 in range(min(step, n_mels)):
+        q, r = divmod(m0, cap)
+        for m in range(m0, n_mels, step):
+            assert (q * 2 * n2 + n2 + 1) * ft + ((cap * q) & (ft - 1)) + r * (ft + 1) == words[m], (m0, m)
+            r += step % cap
+            q += step // cap
+            if r >= cap:
+                r -= cap
+                q += 1
