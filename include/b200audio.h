@@ -72,6 +72,9 @@ B2A_API int b2a_ctx_create(b2a_ctx** ctx, int device);
 B2A_API int b2a_ctx_create_on_stream(b2a_ctx** ctx, int device, void* cuda_stream);
 B2A_API int b2a_ctx_destroy(b2a_ctx* ctx);
 B2A_API int b2a_ctx_sync(b2a_ctx* ctx);
+/* The cudaStream_t (as void*) the context enqueues on: callers that produce device inputs or consume device outputs on another
+ * stream order the two with events (the Python mirror does this for torch tensors). */
+B2A_API void* b2a_ctx_stream(const b2a_ctx* ctx);
 B2A_API const char* b2a_last_error(const b2a_ctx* ctx);
 /* Number of kernel launches issued through this context so far (bench.py's gpu_launches). */
 B2A_API int64_t b2a_ctx_launch_count(const b2a_ctx* ctx);
@@ -146,6 +149,18 @@ B2A_API int b2a_reflect_pad(b2a_ctx* ctx, const float* x, int64_t batch, int64_t
  * The max-8 clamp uses each clip's own global maximum, as the single-clip reference does. */
 B2A_API int b2a_whisper_log_mel_spectrogram(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
                                             int n_mels, int64_t padding, float* out, int space);
+/* The same features as IEEE fp16: whisperLogMelSpectrogram(...).asType(.float16), the only form the Whisper encoder ever consumes
+ * (STT/Whisper/WhisperSTT.swift:156-157,181-182,649-655).  The cast is the last statement of the kernel's store loop (round to
+ * nearest even of the fp32 value, so the result is bit-identical to casting b2a_whisper_log_mel_spectrogram's output): no fp32
+ * feature tensor is written or re-read, and a B2A_HOST caller receives half the bytes.  n_mels = 80 or 128 (Whisper's banks).
+ * out_f16 (batch, T', n_mels) of uint16 / __half. */
+B2A_API int b2a_whisper_log_mel_spectrogram_f16(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
+                                                int n_mels, int64_t padding, void* out_f16, int space);
+/* 16-bit PCM in: sample = int16 / 32768 (exact in fp32), which is what AVAudioFile's float processing format hands the reference
+ * for a 16-bit file (STT/Whisper/WhisperEngine.swift:327-369); then exactly the entry points above.  Halves the host->device
+ * bytes of a B2A_HOST call.  out: float (out_is_f16 = 0) or fp16 (out_is_f16 = 1), (batch, T', n_mels). */
+B2A_API int b2a_whisper_log_mel_spectrogram_pcm16(b2a_ctx* ctx, const int16_t* audio, int64_t batch, int64_t n_samples,
+                                                  int n_mels, int64_t padding, int out_is_f16, void* out, int space);
 
 /* logMelSpectrogramChatterbox Codec/S3Tokenizer/S3TokenizerUtils.swift:160-208 (and the wrapper
  * logMelSpectrogramCAMPPlus TTS/CosyVoice2/CosyVoice2TTS.swift:787-795).  out (batch, n_mels, T'). */
@@ -211,6 +226,8 @@ B2A_API int b2a_voice_encoder_melspectrogram(b2a_ctx* ctx, const float* wav, int
  * ------------------------------------------------------------------------------------- */
 B2A_API int b2a_whisper_log_mel_spectrogram_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
                                                    int n_mels, int64_t padding, float* out, int64_t* out_frames, int space);
+B2A_API int b2a_whisper_log_mel_spectrogram_f16_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                                       int n_mels /* 128 */, int64_t padding, void* out_f16, int64_t* out_frames, int space);
 B2A_API int b2a_log_mel_spectrogram_chatterbox_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
                                                       int n_mels, int64_t padding, float* out, int64_t* out_frames, int space);
 B2A_API int b2a_funasr_log_mel_spectrogram_ragged(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
@@ -261,6 +278,11 @@ B2A_API int b2a_kokoro_stft_transform(b2a_ctx* ctx, const float* x, int64_t batc
 B2A_API int b2a_kokoro_stft_inverse(b2a_ctx* ctx, const float* magnitude, const float* phase, int64_t batch,
                                     int64_t n_frames, int filter_length, int hop_length, int win_length,
                                     float* out, int space);
+/* mlxIstft TTS/Kokoro/Decoder/MLXSTFT.swift:115-163 (stand-alone: no unwrap, no polar conversion).  spec_complex: complex64
+ * (batch, F, frames) as interleaved (re, im) floats, F = win_length / 2 + 1; "hann" window; out (batch, (frames-1)*hop).
+ * Built for (win_length, hop_length) = (20, 5) and (16, 4). */
+B2A_API int b2a_mlx_istft(b2a_ctx* ctx, const float* spec_complex, int64_t batch, int64_t n_frames, int win_length, int hop_length,
+                          float* out, int space);
 /* unwrap                   TTS/Kokoro/Decoder/MLXSTFT.swift:23-46: numpy-style phase unwrap along the last axis of (n_rows, n_frames)
  * (what b2a_kokoro_stft_inverse applies to the phase; the identity unless some |phase[t] - phase[t-1]| >= pi). */
 B2A_API int b2a_unwrap(b2a_ctx* ctx, const float* phase, int64_t n_rows, int64_t n_frames, float* out, int space);
@@ -302,6 +324,11 @@ B2A_API int b2a_resample_linear(b2a_ctx* ctx, const float* x, int64_t batch, int
  * mel (batch, n_mels, t_max) fp32, out (n_segments, n_mels, window) fp32; batch_idx / start / length: HOST int32[n_segments]. */
 B2A_API int64_t b2a_s3tokenizer_plan_segments(const int64_t* mel_len, int64_t batch, int64_t window, int64_t stride, int32_t* batch_idx,
                                               int32_t* start, int32_t* length, int64_t cap);
+/* mergeTokenizedSegments Codec/S3Tokenizer/S3TokenizerUtils.swift:71-88 (pure host function): joins the token sequences of a long
+ * clip's windows, dropping (overlap / 2) * token_rate tokens at every inner edge.  tokens = the segments back to back,
+ * seg_len[n_segments]; returns the merged length (out may be NULL to query it), -1 on bad arguments or when `cap` is too small. */
+B2A_API int64_t b2a_merge_tokenized_segments(const int32_t* tokens, const int64_t* seg_len, int64_t n_segments, int overlap, int token_rate,
+                                             int32_t* out, int64_t cap);
 B2A_API int b2a_s3tokenizer_gather_segments(b2a_ctx* ctx, const float* mel, int64_t batch, int n_mels, int64_t t_max, int64_t n_segments,
                                             const int32_t* batch_idx, const int32_t* start, const int32_t* length, int64_t window,
                                             float* out, int space);

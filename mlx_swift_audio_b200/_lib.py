@@ -35,6 +35,7 @@ SIGNATURES = {
     "b2a_ctx_create_on_stream": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_void_p]),
     "b2a_ctx_destroy": (C.c_int, [_ctx]),
     "b2a_ctx_sync": (C.c_int, [_ctx]),
+    "b2a_ctx_stream": (C.c_void_p, [_ctx]),
     "b2a_last_error": (C.c_char_p, [_ctx]),
     "b2a_ctx_launch_count": (_i64, [_ctx]),
     "b2a_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
@@ -63,6 +64,9 @@ SIGNATURES = {
     "b2a_reflect_pad": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, _i64, C.c_void_p, C.c_int]),
     "b2a_pad_or_trim": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, _i64, C.c_void_p, C.c_int]),
     "b2a_whisper_log_mel_spectrogram": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_void_p, C.c_int]),
+    "b2a_whisper_log_mel_spectrogram_f16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_void_p, C.c_int]),
+    "b2a_whisper_log_mel_spectrogram_pcm16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_int, C.c_void_p, C.c_int]),
+    "b2a_whisper_log_mel_spectrogram_f16_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, _i64, C.c_void_p, C.POINTER(_i64), C.c_int]),
     "b2a_log_mel_spectrogram_chatterbox": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, _i64, C.c_void_p, C.c_int]),
     "b2a_whisper_log_mel_spectrogram_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, _i64, C.c_void_p, C.POINTER(_i64), C.c_int]),
     "b2a_log_mel_spectrogram_chatterbox_ragged": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.POINTER(_i64), C.c_int, _i64, C.c_void_p, C.POINTER(_i64), C.c_int]),
@@ -93,6 +97,8 @@ SIGNATURES = {
     "b2a_resample_linear": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_whisper_mel_segment_f16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.POINTER(_i64), C.POINTER(_i64), _i64, C.c_void_p,
                                               C.c_int]),
+    "b2a_mlx_istft": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "b2a_merge_tokenized_segments": (_i64, [C.POINTER(C.c_int32), C.POINTER(_i64), _i64, C.c_int, C.c_int, C.POINTER(C.c_int32), _i64]),
     "b2a_unwrap": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_void_p, C.c_int]),
     "b2a_hift_head_istft": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, _f, C.c_float, C.c_void_p, C.c_int]),
     "b2a_hift_head_istft_fade": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, _f, C.c_float, _f, _i64, C.c_void_p, C.c_int]),

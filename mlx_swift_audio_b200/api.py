@@ -51,6 +51,8 @@ class Context:
             _raise(rc, "cannot create a context (no sm_100 CUDA device?)")
         self.h = h
         self.device = device
+        self.stream = int(self.lib.b2a_ctx_stream(h) or 0)   # the cudaStream_t the context enqueues on
+        self._torch_order = None                            # torch stream that must wait for the call just issued (see _ctx_for)
 
     def close(self):
         if getattr(self, "h", None):
@@ -67,8 +69,15 @@ class Context:
         self.check(self.lib.b2a_ctx_sync(self.h))
 
     def check(self, rc: int):
+        pending, self._torch_order = self._torch_order, None
         if rc != L.B2A_OK:
             _raise(rc, self.lib.b2a_last_error(self.h).decode())
+        if pending is not None:
+            # the context enqueued on its OWN stream while the caller's tensors live on torch's stream: the result must not be
+            # consumed (nor the inputs reused) on torch's stream before the kernels are done
+            import torch
+            ext = torch.cuda.ExternalStream(self.stream, device=pending.device)
+            pending.wait_event(ext.record_event())
 
     @property
     def launch_count(self) -> int:
@@ -165,7 +174,16 @@ def _out_for(a: "_Arr", shape, out):
 
 
 def _ctx_for(a: _Arr, ctx: Context | None) -> Context:
+    """The context of a call.  An explicit context that enqueues on a stream other than torch's current one (``Context(dev)``
+    owns a non-blocking stream) is ordered against it for device-resident tensors: the context's stream waits for the work that
+    produced the inputs before the launch, torch's stream waits for the kernels after it (``Context.check``)."""
     if ctx is not None:
+        if a.space == L.B2A_DEVICE:
+            import torch
+            cur = torch.cuda.current_stream(a.device)
+            if int(cur.cuda_stream) != ctx.stream:
+                torch.cuda.ExternalStream(ctx.stream, device=cur.device).wait_event(cur.record_event())
+                ctx._torch_order = cur
         return ctx
     if a.space == L.B2A_DEVICE:
         import torch
@@ -304,6 +322,66 @@ def whisperLogMelSpectrogram(audio, nMels: int, padding: int = 0, ctx: Context |
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
     out = _out_for(a, (b, frames, nMels), out)
     c.check(c.lib.b2a_whisper_log_mel_spectrogram(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space))
+    return out if had or isinstance(out, DevicePtr) else out[0]
+
+
+def whisperLogMelSpectrogramF16(audio, nMels: int, padding: int = 0, ctx: Context | None = None, out=None):
+    """``whisperLogMelSpectrogram(...).asType(.float16)`` in one kernel (STT/Whisper/WhisperAudio.swift:78-137 followed by the cast
+    of STT/Whisper/WhisperSTT.swift:156-157,181-182) -> (T', nMels) float16.  ``audio`` may also be 16-bit PCM (NumPy int16 array
+    or torch int16 CUDA tensor): sample = int16 / 32768, as AVAudioFile decodes a 16-bit file (WhisperEngine.swift:327-369)."""
+    return _whisper_typed(audio, nMels, padding, ctx, out, True)
+
+
+def whisperLogMelSpectrogramPCM16(audio_i16, nMels: int, padding: int = 0, ctx: Context | None = None, out=None):
+    """whisperLogMelSpectrogram of 16-bit PCM (sample = int16 / 32768) -> (T', nMels) float32."""
+    return _whisper_typed(audio_i16, nMels, padding, ctx, out, False)
+
+
+def _whisper_typed(audio, nMels, padding, ctx, out, f16: bool):
+    is_t = _is_torch(audio)
+    if is_t:
+        import torch
+        i16 = audio.dtype == torch.int16
+    else:
+        audio = np.asarray(audio)
+        i16 = audio.dtype == np.int16
+    if i16:
+        a = _Arr.__new__(_Arr)   # 16-bit PCM: same plumbing, no float conversion on the host
+        if is_t:
+            if not audio.is_cuda:
+                raise B2AError(L.B2A_E_BAD_ARG, "torch tensors must live on a CUDA device (use NumPy arrays for host data)")
+            a.t, a.space, a.device = audio.contiguous(), L.B2A_DEVICE, audio.device.index or 0
+            a.ptr = C.c_void_p(a.t.data_ptr())
+        else:
+            a.t, a.space, a.device = np.ascontiguousarray(audio), L.B2A_HOST, None
+            a.ptr = C.c_void_p(a.t.ctypes.data)
+        a.shape = tuple(a.t.shape)
+    else:
+        a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    frames = int(c.lib.b2a_whisper_num_frames(n, padding))
+    if frames <= 0:
+        _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
+    shape = (b, frames, nMels)
+    if out is None:
+        if a.space == L.B2A_DEVICE:
+            import torch
+            out = torch.empty(shape, dtype=torch.float16 if f16 else torch.float32, device=a.t.device)
+        else:
+            out = np.empty(shape, np.float16 if f16 else np.float32)
+    elif not isinstance(out, DevicePtr):
+        import torch
+        want = torch.float16 if f16 else torch.float32
+        if not (_is_torch(out) and out.is_cuda and out.dtype == want and out.is_contiguous() and tuple(out.shape) == shape and a.space == L.B2A_DEVICE):
+            raise B2AError(L.B2A_E_BAD_ARG, f"out must be a contiguous {want} CUDA tensor of shape {shape} (device-resident input)")
+    if i16:
+        rc = c.lib.b2a_whisper_log_mel_spectrogram_pcm16(c.h, a.ptr, b, n, nMels, padding, int(f16), _ptr(out), a.space)
+    elif f16:
+        rc = c.lib.b2a_whisper_log_mel_spectrogram_f16(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space)
+    else:
+        rc = c.lib.b2a_whisper_log_mel_spectrogram(c.h, a.ptr, b, n, nMels, padding, _ptr(out), a.space)
+    c.check(rc)
     return out if had or isinstance(out, DevicePtr) else out[0]
 
 
@@ -780,6 +858,58 @@ def kokoroHeadIstft(convOut, filterLength: int = 20, hopLength: int = 5, winLeng
                        lambda c, h, b, frames, out: c.lib.b2a_kokoro_head_istft(c.h, h.ptr, b, frames, filterLength, hopLength,
                                                                                 winLength, _ptr(out), h.space),
                        lambda b, n: (b, 1, n))
+
+
+def mlxIstft(real, imag=None, hopLength: int | None = None, winLength: int | None = None, window: str = "hann", center: bool = True,
+             ctx: Context | None = None):
+    """TTS/Kokoro/Decoder/MLXSTFT.swift:115-163: complex spectrum (F, frames) [or (B, F, frames)] -> (L,).  The spectrum is
+    given as a complex64 array, or as separate real / imaginary float32 arrays."""
+    if window.lower() != "hann":
+        raise B2AError(L.B2A_E_BAD_ARG, f"Only hanning is supported for window, not {window}")
+    if not center:
+        raise B2AError(L.B2A_E_UNSUPPORTED, "mlxIstft is built for center = true (the only form the reference calls)")
+    if imag is None:
+        z = np.asarray(real)
+        if not np.iscomplexobj(z):
+            raise B2AError(L.B2A_E_BAD_ARG, "mlxIstft needs a complex spectrum")
+        inter = np.ascontiguousarray(np.stack([z.real, z.imag], axis=-1), np.float32)
+    elif _is_torch(real):
+        import torch
+        inter = torch.stack([real, imag], dim=-1).contiguous()
+    else:
+        inter = np.ascontiguousarray(np.stack([np.asarray(real, np.float32), np.asarray(imag, np.float32)], axis=-1))
+    a = _Arr(inter)
+    had = len(a.shape) == 4
+    if len(a.shape) not in (3, 4):
+        raise B2AError(L.B2A_E_BAD_ARG, "spectrum must be (F, frames) or (B, F, frames)")
+    b = a.shape[0] if had else 1
+    f, frames = a.shape[-3], a.shape[-2]
+    win = winLength if winLength is not None else (f - 1) * 2
+    hop = hopLength if hopLength is not None else win // 4
+    if f != win // 2 + 1:
+        raise B2AError(L.B2A_E_BAD_ARG, "spectrum rows must equal winLength / 2 + 1")
+    if frames < 2:
+        _raise(L.B2A_E_TOO_SHORT, "iSTFT needs at least 2 frames")
+    c = _ctx_for(a, ctx)
+    out = a.empty((b, (frames - 1) * hop))
+    c.check(c.lib.b2a_mlx_istft(c.h, a.ptr, b, frames, win, hop, _ptr(out), a.space))
+    return out if had else out[0]
+
+
+def mergeTokenizedSegments(tokenizedSegments, overlap: int, tokenRate: int):
+    """Codec/S3Tokenizer/S3TokenizerUtils.swift:71-88 (host-side integer rule) -> list[int]"""
+    segs = [np.asarray(t, np.int32).reshape(-1) for t in tokenizedSegments]
+    lens = np.asarray([len(t) for t in segs], np.int64)
+    flat = np.ascontiguousarray(np.concatenate(segs) if segs else np.zeros(0, np.int32), np.int32)
+    if flat.size == 0:
+        flat = np.zeros(1, np.int32)
+    out = np.empty(max(1, int(lens.sum())), np.int32)
+    I32, I64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    n = int(L.load().b2a_merge_tokenized_segments(flat.ctypes.data_as(I32), lens.ctypes.data_as(I64), len(segs), overlap, tokenRate,
+                                                  out.ctypes.data_as(I32), out.shape[0]))
+    if n < 0:
+        _raise(L.B2A_E_BAD_ARG, "mergeTokenizedSegments: bad segment lengths")
+    return [int(v) for v in out[:n]]
 
 
 class MLXSTFT:

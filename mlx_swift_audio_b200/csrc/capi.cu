@@ -107,33 +107,43 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
     std::vector<float> dense(size_t(n_mels) * n_bins);
     int rc = make_dense(dense.data());
     if (rc != B2A_OK) return fail(c, rc, "bad filterbank parameters");
+    // validation and the (host-only) mel program first: nothing is allocated on the device for a bank that cannot run
+    std::vector<int> slots;
+    spectrum_slots(*ps, slots);
+    if (n_bins > int(slots.size())) return fail(c, B2A_E_BAD_ARG, "filterbank has more bins than the spectrum");
+    std::vector<int> words;
+    if (!output_words(*ps, n_mels, words)) return fail(c, B2A_E_BAD_ARG, "n_mels out of range for this FFT plan");
     BankStorage bs;
     build_sparse_bank(dense.data(), n_mels, n_bins, bin_major, bs.host);
+    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, words.data(), n_chunks, slots.data(), bs.host);
     const size_t nw = std::max<size_t>(bs.host.weights.size(), 1);
-    cudaError_t e;
     std::vector<int> desc(size_t(n_mels) * 4, 0);
     for (int m = 0; m < n_mels; ++m) {
       desc[4 * m + 0] = bs.host.start[m];
       desc[4 * m + 1] = bs.host.count[m];
       desc[4 * m + 2] = bs.host.offset[m];
     }
-    if ((e = cudaMalloc(&bs.desc, sizeof(int) * desc.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
-    if ((e = cudaMalloc(&bs.weights, sizeof(float) * nw)) != cudaSuccess) return cu(c, e, "cudaMalloc");
-    // synchronous uploads (once per configuration), ordered before any later launch
-    if ((e = cudaMemcpy(bs.desc, desc.data(), sizeof(int) * desc.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return cu(c, e, "bank upload");
-    if (!bs.host.weights.empty())
-      if ((e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
-        return cu(c, e, "bank upload");
-    std::vector<int> slots;
-    spectrum_slots(*ps, slots);
-    if (n_bins > int(slots.size())) return fail(c, B2A_E_BAD_ARG, "filterbank has more bins than the spectrum");
-    std::vector<int> words;
-    if (!output_words(*ps, n_mels, words)) return fail(c, B2A_E_BAD_ARG, "n_mels out of range for this FFT plan");
-    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, words.data(), n_chunks, slots.data(), bs.host);
-    if (!bs.host.steps.empty()) {
-      if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return cu(c, e, "cudaMalloc");
-      if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
-        return cu(c, e, "bank upload");
+    // synchronous uploads (once per configuration), ordered before any later launch; a failure frees what was allocated
+    auto upload = [&]() -> cudaError_t {
+      cudaError_t e;
+      if ((e = cudaMalloc(&bs.desc, sizeof(int) * desc.size())) != cudaSuccess) return e;
+      if ((e = cudaMalloc(&bs.weights, sizeof(float) * nw)) != cudaSuccess) return e;
+      if ((e = cudaMemcpy(bs.desc, desc.data(), sizeof(int) * desc.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+      if (!bs.host.weights.empty() &&
+          (e = cudaMemcpy(bs.weights, bs.host.weights.data(), sizeof(float) * bs.host.weights.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return e;
+      if (!bs.host.steps.empty()) {
+        if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+      }
+      return cudaSuccess;
+    };
+    const cudaError_t ue = upload();
+    if (ue != cudaSuccess) {
+      if (bs.desc) cudaFree(bs.desc);
+      if (bs.weights) cudaFree(bs.weights);
+      if (bs.steps) cudaFree(bs.steps);
+      return cu(c, ue, "filterbank upload");
     }
     if (!bs.host.steps.empty())
       bs.baked_id = frontend_match_baked(bs.host.steps.data(), int(bs.host.steps.size() / 4), bs.host.chunk_m.data(), bs.host.chunk_s.data(),
@@ -175,18 +185,25 @@ struct Guard {
 //  B2A_HOST  : clips are streamed through device staging buffers in chunks; H2D of chunk i+1, the
 //              kernels of chunk i and D2H of chunk i-1 overlap on three streams.
 using Body = std::function<int(const float*, const float*, float*, float*, int64_t, int)>;
+constexpr int64_t kMaxClipsPerLaunch = 32768;   // several kernels index clips with gridDim.y (limit 65535): both memory spaces split here
 
-int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t in0_per_clip, const float* in1,
-                size_t in1_per_clip, float* out0, size_t out0_per_clip, float* out1, size_t out1_per_clip, const Body& body) {
+// Sizes per clip in BYTES (the buffers may hold fp32, fp16 or 16-bit PCM); the body sees them through float-typed pointers.
+int run_batched_bytes(b2a_ctx* c, int space, int64_t batch, const void* in0_v, size_t in0_per_clip, const void* in1_v,
+                      size_t in1_per_clip, void* out0_v, size_t out0_per_clip, void* out1_v, size_t out1_per_clip, const Body& body) {
+  const char* in0 = static_cast<const char*>(in0_v);
+  const char* in1 = static_cast<const char*>(in1_v);
+  char* out0 = static_cast<char*>(out0_v);
+  char* out1 = static_cast<char*>(out1_v);
+  auto F = [](const char* p) { return reinterpret_cast<const float*>(p); };
+  auto FM = [](char* p) { return reinterpret_cast<float*>(p); };
   if (space == B2A_DEVICE) {
     if (c->timing) cudaEventRecord(c->ev_t0, c->stream);
     int rc = B2A_OK;
-    const int64_t kMaxClipsPerLaunch = 32768;   // several kernels index clips with gridDim.y (limit 65535)
     for (int64_t c0 = 0; c0 < batch && rc == B2A_OK; c0 += kMaxClipsPerLaunch) {
       const int64_t n = std::min(kMaxClipsPerLaunch, batch - c0);
       c->chunk_clip0 = c0;
-      rc = body(in0 + c0 * in0_per_clip, in1 ? in1 + c0 * in1_per_clip : nullptr, out0 + c0 * out0_per_clip,
-                out1 ? out1 + c0 * out1_per_clip : nullptr, n, 0);
+      rc = body(F(in0 + c0 * in0_per_clip), in1 ? F(in1 + c0 * in1_per_clip) : nullptr, FM(out0 + c0 * out0_per_clip),
+                out1 ? FM(out1 + c0 * out1_per_clip) : nullptr, n, 0);
     }
     if (c->timing) {
       cudaEventRecord(c->ev_t1, c->stream);
@@ -195,22 +212,22 @@ int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t i
     return rc;
   }
   if (space != B2A_HOST) return fail(c, B2A_E_BAD_ARG, "space must be B2A_HOST or B2A_DEVICE");
-  const size_t per_clip = sizeof(float) * (in0_per_clip + in1_per_clip + out0_per_clip + out1_per_clip);
+  const size_t per_clip = in0_per_clip + in1_per_clip + out0_per_clip + out1_per_clip;
   // bytes per chunk (inputs + outputs).  Measured on the B200 box (tools/gpu/e2e_sweep.sh): the host path is bound by the H2D copies
   // (~54 GB/s) for any chunk of 32..192 MB; 128 MB keeps fill / drain at a few % of a multi-GB call (ramping the first and last
   // chunks down to 1/8 of the size changed nothing: the step is bound by the duplex PCIe traffic itself).  B2A_HOST_CHUNK_MB overrides.
   size_t target = size_t(128) << 20;
   if (const char* mb = getenv("B2A_HOST_CHUNK_MB")) target = size_t(std::max(1, atoi(mb))) << 20;
   int64_t chunk = std::max<int64_t>(1, int64_t(target / std::max<size_t>(per_clip, 1)));
-  chunk = std::min(chunk, batch);
+  chunk = std::min(std::min(chunk, batch), kMaxClipsPerLaunch);   // (tiny clips: the byte target alone would exceed gridDim.y)
   const int64_t n_chunks = (batch + chunk - 1) / chunk;
   const int slots = int(std::min<int64_t>(kSlots, n_chunks));
   for (int s = 0; s < slots; ++s) {
     int rc;
-    if ((rc = ensure(c, c->in[s][0], sizeof(float) * in0_per_clip * chunk)) != B2A_OK) return rc;
-    if (in1 && (rc = ensure(c, c->in[s][1], sizeof(float) * in1_per_clip * chunk)) != B2A_OK) return rc;
-    if ((rc = ensure(c, c->out[s][0], sizeof(float) * out0_per_clip * chunk)) != B2A_OK) return rc;
-    if (out1 && (rc = ensure(c, c->out[s][1], sizeof(float) * out1_per_clip * chunk)) != B2A_OK) return rc;
+    if ((rc = ensure(c, c->in[s][0], in0_per_clip * chunk)) != B2A_OK) return rc;
+    if (in1 && (rc = ensure(c, c->in[s][1], in1_per_clip * chunk)) != B2A_OK) return rc;
+    if ((rc = ensure(c, c->out[s][0], out0_per_clip * chunk)) != B2A_OK) return rc;
+    if (out1 && (rc = ensure(c, c->out[s][1], out1_per_clip * chunk)) != B2A_OK) return rc;
   }
   cudaError_t e;
   // order the copy streams after whatever is already queued on the compute stream
@@ -222,9 +239,9 @@ int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t i
     if (i >= kSlots) {  // slot reuse: its previous D2H must have drained
       if ((e = cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
     }
-    if ((e = cudaMemcpyAsync(c->in[s][0].p, in0 + c0 * in0_per_clip, sizeof(float) * in0_per_clip * n, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(c->in[s][0].p, in0 + c0 * in0_per_clip, in0_per_clip * n, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
       return cu(c, e, "H2D copy");
-    if (in1 && (e = cudaMemcpyAsync(c->in[s][1].p, in1 + c0 * in1_per_clip, sizeof(float) * in1_per_clip * n, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
+    if (in1 && (e = cudaMemcpyAsync(c->in[s][1].p, in1 + c0 * in1_per_clip, in1_per_clip * n, cudaMemcpyHostToDevice, c->s_h2d)) != cudaSuccess)
       return cu(c, e, "H2D copy");
     if ((e = cudaEventRecord(c->ev_h2d[s], c->s_h2d)) != cudaSuccess) return cu(c, e, "event record");
     if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
@@ -239,15 +256,22 @@ int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t i
     }
     if ((e = cudaEventRecord(c->ev_comp[s], c->stream)) != cudaSuccess) return cu(c, e, "event record");
     if ((e = cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0)) != cudaSuccess) return cu(c, e, "stream wait");
-    if ((e = cudaMemcpyAsync(out0 + c0 * out0_per_clip, c->out[s][0].p, sizeof(float) * out0_per_clip * n, cudaMemcpyDeviceToHost, c->s_d2h)) != cudaSuccess)
+    if ((e = cudaMemcpyAsync(out0 + c0 * out0_per_clip, c->out[s][0].p, out0_per_clip * n, cudaMemcpyDeviceToHost, c->s_d2h)) != cudaSuccess)
       return cu(c, e, "D2H copy");
-    if (out1 && (e = cudaMemcpyAsync(out1 + c0 * out1_per_clip, c->out[s][1].p, sizeof(float) * out1_per_clip * n, cudaMemcpyDeviceToHost, c->s_d2h)) != cudaSuccess)
+    if (out1 && (e = cudaMemcpyAsync(out1 + c0 * out1_per_clip, c->out[s][1].p, out1_per_clip * n, cudaMemcpyDeviceToHost, c->s_d2h)) != cudaSuccess)
       return cu(c, e, "D2H copy");
     if ((e = cudaEventRecord(c->ev_d2h[s], c->s_d2h)) != cudaSuccess) return cu(c, e, "event record");
   }
   if ((e = cudaStreamSynchronize(c->s_d2h)) != cudaSuccess) return cu(c, e, "sync");
   if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return cu(c, e, "sync");
   return B2A_OK;
+}
+
+// fp32 buffers: sizes per clip in floats
+int run_batched(b2a_ctx* c, int space, int64_t batch, const float* in0, size_t in0_per_clip, const float* in1,
+                size_t in1_per_clip, float* out0, size_t out0_per_clip, float* out1, size_t out1_per_clip, const Body& body) {
+  return run_batched_bytes(c, space, batch, in0, sizeof(float) * in0_per_clip, in1, sizeof(float) * in1_per_clip, out0,
+                           sizeof(float) * out0_per_clip, out1, sizeof(float) * out1_per_clip, body);
 }
 
 int check_common(b2a_ctx* c, const void* in, const void* out, int64_t batch, int64_t n) {
@@ -276,6 +300,8 @@ struct Preset {
   int64_t n_frames = 0;
   int lfr_m = 7, lfr_n = 6;
   int64_t lfr_rows = 0;
+  int in_i16 = 0;          // the clips are 16-bit PCM (converted to fp32 in [-1, 1) on the device, x / 32768)
+  int out_f16 = 0;         // the features are written as fp16 by the store loop (Whisper (T', M) front end)
   int post_cmvn = 0;       // Fun-ASR per-utterance CMVN on the LFR features
   int post_mean_norm = 0;  // CAM++ time-mean removal
 };
@@ -289,8 +315,9 @@ struct Ragged {
   int64_t* out_rows = nullptr;                  // host, optional: rows (frames / LFR rows) written per clip
 };
 
-int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, int64_t n_samples, float* out, int space,
+int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, int64_t n_samples, void* out, int space,
                const Ragged* rg = nullptr) {
+  if (p.out_f16 && (p.bank.n_mels & 1)) return fail(c, B2A_E_BAD_ARG, "fp16 output needs an even n_mels");
   std::vector<int64_t> clip_frames;
   if (rg) {
     if (p.out_mode == OUT_COMPLEX) return fail(c, B2A_E_UNSUPPORTED, "ragged batches are built for the mel front ends only");
@@ -315,7 +342,7 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
   Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int slot) -> int {
     FrontendArgs a;
     a.n_fft = p.n_fft; a.hop = p.hop; a.win_len = p.win_len;
-    a.x = d_in; a.batch = n; a.n_samples = n_samples; a.zero_tail = p.zero_tail;
+    a.x = d_in; a.batch = n; a.n_samples = n_samples; a.zero_tail = p.zero_tail; a.out_f16 = p.out_f16;
     a.pad_mode = p.pad_mode; a.pad_left = p.pad_left; a.pre_mode = p.pre_mode;
     a.window = p.window->data();
     a.spec_mode = p.spec_mode; a.bank = p.bank; a.log_mode = p.log_mode; a.log_floor = p.log_floor;
@@ -324,6 +351,15 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
     std::vector<int> clip_tab;   // (the pageable-memory upload below is staged before cudaMemcpyAsync returns)
     int launches = 0;
     std::string err;
+    if (p.in_i16) {   // 16-bit PCM -> fp32 scratch (x / 32768, exact), then the fp32 front end
+      int rc;
+      if ((rc = ensure(c, c->scratch[slot][2], sizeof(float) * size_t(n) * size_t(n_samples))) != B2A_OK) return rc;
+      if ((rc = launch_pcm16_to_f32(d_in, static_cast<float*>(c->scratch[slot][2].p), n * n_samples, c->stream, &launches, &err)) != B2A_OK) {
+        c->err = err;
+        return rc;
+      }
+      a.x = static_cast<const float*>(c->scratch[slot][2].p);
+    }
     if (rg) {
       const PlanShape* ps = plan_shape(p.n_fft);
       const int ft = ps ? ps->frame_tile : 32;
@@ -355,7 +391,7 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
       // rows past a clip's own count are zero (only those: the kernels write the rest)
       if (p.out_mode == OUT_MT) rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.bank.n_mels, p.n_frames, 1, c->stream, &launches, &err);
       else if (p.out_mode == OUT_LFR) rc = launch_zero_tails(d_out, a.clip_tab, 2, n, p.lfr_rows, int64_t(p.lfr_m) * p.bank.n_mels, 0, c->stream, &launches, &err);
-      else rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.n_frames, p.bank.n_mels, 0, c->stream, &launches, &err);
+      else rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.n_frames, p.out_f16 ? p.bank.n_mels / 2 : p.bank.n_mels, 0, c->stream, &launches, &err);   // (fp16 rows: n_mels / 2 words of zero bits)
       if (rc != B2A_OK) {
         c->err = err;
         return rc;
@@ -363,10 +399,11 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
     }
     if (p.whisper_norm) {
       int rc;
-      if ((rc = ensure(c, c->scratch[slot][0], sizeof(int) * size_t(n))) != B2A_OK) return rc;
-      if ((rc = ensure(c, c->scratch[slot][1], sizeof(float) * size_t(n) * tiles)) != B2A_OK) return rc;
+      // clip maxima and tile minima back to back: one memset initialises both (launch_plan)
+      const size_t n_tiles = rg ? size_t(a.total_tiles) : size_t(n) * tiles;
+      if ((rc = ensure(c, c->scratch[slot][0], sizeof(int) * (size_t(n) + n_tiles))) != B2A_OK) return rc;
       a.clip_max = static_cast<int*>(c->scratch[slot][0].p);
-      a.tile_min = static_cast<float*>(c->scratch[slot][1].p);
+      a.tile_min = reinterpret_cast<float*>(a.clip_max + n);
     }
     int rc = launch_frontend(a, c->stream, &launches, &err);
     if (rc == B2A_OK && p.post_cmvn)
@@ -376,7 +413,8 @@ int run_preset(b2a_ctx* c, const Preset& p, const float* audio, int64_t batch, i
     if (rc != B2A_OK) c->err = err;
     return rc;
   };
-  return run_batched(c, space, batch, audio, size_t(n_samples), nullptr, 0, out, out_per_clip, nullptr, 0, body);
+  return run_batched_bytes(c, space, batch, audio, size_t(n_samples) * (p.in_i16 ? sizeof(int16_t) : sizeof(float)), nullptr, 0, out,
+                           out_per_clip * (p.out_f16 ? sizeof(uint16_t) : sizeof(float)), nullptr, 0, body);
 }
 
 std::string key_of(const char* tag, std::initializer_list<double> v) {
@@ -494,6 +532,8 @@ int b2a_ctx_sync(b2a_ctx* c) {
   if (!c) return B2A_E_BAD_ARG;
   return cu(c, cudaStreamSynchronize(c->stream), "sync");
 }
+
+void* b2a_ctx_stream(const b2a_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 
 const char* b2a_last_error(const b2a_ctx* c) { return c ? c->err.c_str() : "null context"; }
 int64_t b2a_ctx_launch_count(const b2a_ctx* c) { return c ? c->launches : 0; }
@@ -725,8 +765,9 @@ int b2a_whisper_mel_segment_f16(b2a_ctx* c, const float* mel, int64_t batch, int
                      size_t(length) * n_mels / 2, nullptr, 0, body);
 }
 
-static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding, float* out,
-                        int space, bool chatterbox, const int64_t* lengths = nullptr, int64_t* out_rows = nullptr) {
+static int whisper_like(b2a_ctx* c, const void* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding, void* out,
+                        int space, bool chatterbox, const int64_t* lengths = nullptr, int64_t* out_rows = nullptr, bool in_i16 = false,
+                        bool out_f16 = false) {
   int rc = check_common(c, audio, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (padding < 0) return fail(c, B2A_E_BAD_ARG, "padding must be >= 0");
@@ -745,6 +786,8 @@ static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n
   p.whisper_norm = 1;
   p.out_mode = chatterbox ? OUT_MT : OUT_TM;
   p.n_frames = frames;  // the last STFT frame is dropped (WhisperAudio.swift:105, S3TokenizerUtils.swift:184)
+  p.in_i16 = in_i16;
+  p.out_f16 = out_f16;
   Ragged rg{lengths, [&](int64_t len) { return b2a_whisper_num_frames(len, padding); }, out_rows};
   return run_preset(c, p, audio, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
@@ -752,6 +795,22 @@ static int whisper_like(b2a_ctx* c, const float* audio, int64_t batch, int64_t n
 int b2a_whisper_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
                                     float* out, int space) {
   return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, false);
+}
+
+int b2a_whisper_log_mel_spectrogram_f16(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
+                                        void* out_f16, int space) {
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out_f16, space, false, nullptr, nullptr, false, true);
+}
+
+int b2a_whisper_log_mel_spectrogram_pcm16(b2a_ctx* c, const int16_t* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
+                                          int out_is_f16, void* out, int space) {
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, false, nullptr, nullptr, true, out_is_f16 != 0);
+}
+
+int b2a_whisper_log_mel_spectrogram_f16_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths,
+                                               int n_mels, int64_t padding, void* out_f16, int64_t* out_frames, int space) {
+  if (!lengths) return fail(c, B2A_E_BAD_ARG, "lengths must not be NULL");
+  return whisper_like(c, audio, batch, n_samples, n_mels, padding, out_f16, space, false, lengths, out_frames, false, true);
 }
 
 int b2a_log_mel_spectrogram_chatterbox(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int64_t padding,
@@ -1173,6 +1232,18 @@ int b2a_kokoro_head_istft(b2a_ctx* c, const float* conv_out, int64_t batch, int6
   hann_periodic_via_hanning(win_length, w);
   return istft_common(c, conv_out, nullptr, batch, n_frames, filter_length, hop_length, w.data(), 0, 3.402823466e+38f, NORM_WSUM_NONZERO,
                       1, out, space, 1, 0.0f);
+}
+
+int b2a_mlx_istft(b2a_ctx* c, const float* spec_complex, int64_t batch, int64_t n_frames, int win_length, int hop_length, float* out,
+                  int space) {
+  // mlxIstft (MLXSTFT.swift:115-163): x complex64 (F, frames), irfft of every frame, "hann" window, overlap-add, division by the
+  // window sum where it is non-zero, trim of win_length / 2 at both ends (center = true).  No unwrap, no magnitude clip.
+  if (!c) return B2A_E_BAD_ARG;
+  if (win_length <= 0 || hop_length <= 0) return fail(c, B2A_E_BAD_ARG, "win_length and hop_length must be positive");
+  std::vector<float> w;
+  hann_periodic_via_hanning(win_length, w);   // getWindow "hann" (MLXSTFT.swift:48-67)
+  return istft_common(c, spec_complex, nullptr, batch, n_frames, win_length, hop_length, w.data(), 0, 3.402823466e+38f, NORM_WSUM_NONZERO,
+                      0, out, space, 2, 0.0f);
 }
 
 int b2a_unwrap(b2a_ctx* c, const float* phase, int64_t n_rows, int64_t n_frames, float* out, int space) {

@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -149,7 +150,7 @@ struct FrontendParams {
   int chunk_s[P::NCHUNK + 1];  // steps   [chunk_s[c], chunk_s[c+1]) of the program belong to chunk c
   float* out;
   int* clip_max;
-  int* tile_min;   // per tile: ordered-int encoding of the minimum normalised value
+  int* tile_min;   // per tile: ordered-int encoding of MINUS the minimum normalised value (atomicMax, same 0x80.. initial pattern as clip_max)
   // Ragged batches (per-clip lengths; RAGGED kernels only): clip b = (n_samples, n_frames, lfr_rows, index of its first tile);
   // tile g of the launch = tile_tab[g] = (clip, tile within the clip), built on the device from clip_tab (tile_table_kernel).
   // Strides (clip_stride, out_clip_stride) stay those of the longest clip.
@@ -435,7 +436,9 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // loop) and output layout OUT (OUT_TM / OUT_MT / OUT_LFR).
 // RAGGED: per-clip lengths -- the tile walk and the clip geometry come from prm.tile_tab / prm.clip_tab (one uniform load each
 // per tile, issued one tile ahead) instead of the launch-wide constants.
-template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false>
+// F16: the (T', M) store of a baked bank writes __half (round to nearest even of the fp32 value: bit-identical to the reference's
+// asType(.float16) of the fp32 feature, WhisperSTT.swift:156-157,181-182); clamp bookkeeping stays in fp32.
+template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false, bool F16 = false>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
@@ -452,6 +455,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   constexpr bool LATE_TOP = EARLY_PREFETCH && PRE != PRE_KALDI;
   constexpr int R0W = cplx ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL;
   static_assert(MEL == 0 || (SPEC == SK_POWER && FT == 32), "known banks are power-spectrum banks of the 32-frame plans");
+  static_assert(!F16 || (BAKED && OUT == OUT_TM), "fp16 output is built for the (T', M) store of the baked banks");
   extern __shared__ __align__(16) float smem[];
   float2* s_y = reinterpret_cast<float2*>(smem + R0W);
   float* s_p = reinterpret_cast<float*>(s_y);               // stage B leaves the spectrum tile in the exchange buffer (spectrum_slots)
@@ -750,6 +754,11 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         if (out_mode == OUT_TM) {
           // (T', M) rows, every row a run of coalesced 128-byte segments; rows warp, warp + NW, ... as immediates
           float* d = dst + ((long long)f0 + warp) * MB + lane;
+          __half* dh = reinterpret_cast<__half*>(prm.out) + (long long)clip * prm.out_clip_stride + ((long long)f0 + warp) * MB + lane;
+          auto put = [&](int off, float v) {
+            if (F16) dh[off] = __float2half_rn(v);
+            else d[off] = v;
+          };
           // Row slots warp, warp + NW, ...: NF of them exist for every warp (branch-free: loads unconditional -- staging
           // rows past `rows` hold the recomputed last frame -- only the stores are guarded); the remaining FT - NF*NW rows
           // go to the first warps under a warp-uniform branch.
@@ -770,11 +779,11 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
             if (NF % 2) track2(v[NF - 1], v[NF - 1]);
 #pragma unroll
             for (int i = 0; i < NF; ++i)
-              if (ok[i] && col_ok) d[i * NW * MB + c * 32] = v[i];
+              if (ok[i] && col_ok) put(i * NW * MB + c * 32, v[i]);
             if (extra) {
               v[NF] = post_pure(sr[NF * NW]);
               track2(v[NF], v[NF]);
-              if (ok[NF] && col_ok) d[NF * NW * MB + c * 32] = v[NF];
+              if (ok[NF] && col_ok) put(NF * NW * MB + c * 32, v[NF]);
             }
           }
         } else {  // OUT_LFR: out[i][j*M + m] = feat[clamp(i*n + j - left, 0, T'-1)][m]   (FunASRAudio.swift:108-154)
@@ -828,7 +837,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
         if (lane == 0) {
           atomicMax(prm.clip_max + clip, wmax);
-          atomicMin(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
+          atomicMax(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, enc_ordered(-dec_ordered(wmin)));  // the NEGATED minimum, ordered-int encoded: one 0x80 memset initialises clip_max and tile_min alike
         }
       }
     } else {
@@ -898,7 +907,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
       if (lane == 0) {
         atomicMax(prm.clip_max + clip, wmax);
-        atomicMin(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, wmin);  // ordered-int encoding, memset to 0x7f.. by the host
+        atomicMax(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, enc_ordered(-dec_ordered(wmin)));  // the NEGATED minimum, ordered-int encoded: one 0x80 memset initialises clip_max and tile_min alike
       }
     }
     }  // !cplx
@@ -925,7 +934,7 @@ constexpr int kClampTilesPerCta = 32;
 // clip_tab != null (ragged batch): the clip's own frame count and first tile; `n_frames` stays the (M, T') row stride.
 __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                                             long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft,
-                                                            const int4* __restrict__ clip_tab) {
+                                                            const int4* __restrict__ clip_tab, int f16) {
   __shared__ int s_list[kClampTilesPerCta];
   __shared__ int s_count;
   const long long clip = blockIdx.y;
@@ -942,7 +951,7 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   if (threadIdx.x < kClampTilesPerCta && t0 + int(threadIdx.x) < tiles_per_clip &&
-      dec_ordered(tile_min[tile_base + t0 + threadIdx.x]) < thr)
+      -dec_ordered(tile_min[tile_base + t0 + threadIdx.x]) < thr)   // tile_min holds the negated minimum
     s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
   __syncthreads();
   const int count = s_count;
@@ -951,7 +960,24 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
     const int t = s_list[i];
     const long long f0 = (long long)t * ft;
     const int rows = int(n_frames - f0 < ft ? n_frames - f0 : ft);
-    if (out_mode == OUT_TM) {
+    if (out_mode == OUT_TM && f16) {
+      // fp16 features: rounding is monotone, so max(half(v), half(thr)) == half(max(v, thr))
+      __half* d = reinterpret_cast<__half*>(out) + clip * out_clip_stride + f0 * n_mels;
+      const int n = rows * n_mels;
+      const __half th = __float2half_rn(thr);
+      if ((reinterpret_cast<uintptr_t>(d) & 15) == 0 && (n & 7) == 0) {
+        const __half2 th2 = __half2half2(th);
+        uint4* d4 = reinterpret_cast<uint4*>(d);
+        for (int e = threadIdx.x; e < n / 8; e += blockDim.x) {
+          uint4 v = d4[e];
+          __half2* h = reinterpret_cast<__half2*>(&v);
+          h[0] = __hmax2(h[0], th2); h[1] = __hmax2(h[1], th2); h[2] = __hmax2(h[2], th2); h[3] = __hmax2(h[3], th2);
+          d4[e] = v;
+        }
+      } else {
+        for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = __hmax(d[e], th);
+      }
+    } else if (out_mode == OUT_TM) {
       float* d = o + f0 * n_mels;
       const int n = rows * n_mels;
       if ((reinterpret_cast<uintptr_t>(d) & 15) == 0 && (n & 3) == 0) {
@@ -978,9 +1004,11 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
 // per-clip column statistics: CMVN (FunASRAudio.swift:165-180) and time-mean removal (CAMPPlus.swift:800)
 // block = 32 columns x 8 row groups; grid = (column chunks, batch)
 // ------------------------------------------------------------------------------------------------
+// `in` and `out` may be the same buffer (CMVN / mean-norm run in place on the front end's output): no __restrict__, no
+// non-coherent loads on them; every thread re-reads only elements it has not yet written.
 // clip_tab != null (ragged batch): the statistics run over the clip's own rows (component `tab_rows` of its clip_tab entry:
 // 1 = frames, 2 = LFR rows); the clip stride stays `rows` (the longest clip's) x dim.
-__global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows,
+__global__ void __launch_bounds__(256) colstat_kernel(const float* in, float* out, long long rows,
                                                       int dim, const float* __restrict__ gmean, const float* __restrict__ gistd,
                                                       int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
   __shared__ float s_red[8][33];
@@ -1064,7 +1092,7 @@ __global__ void __launch_bounds__(256) colstat_kernel(const float* __restrict__ 
 // and a Newton correction per element (the fast path of the IEEE division without its range check; the denominators are
 // >= 1e-6 and the quotients far from the fp32 range limits).
 template <int RPT>
-__global__ void __launch_bounds__(256) colstat_reg_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int dim,
+__global__ void __launch_bounds__(256) colstat_reg_kernel(const float* in, float* out, long long rows, int dim,
                                                           int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
   __shared__ float s_red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -1136,7 +1164,7 @@ __global__ void __launch_bounds__(256) colstat_reg_kernel(const float* __restric
 // slabs (512 resident clips x 639 KB) do not survive in the L2.  Three blocks per SM overlap each other's load / store phases.
 // Column sums run over rows g, g + G, ... (G = 256 / CW row groups) and are combined in fixed order: deterministic.
 template <int CW>
-__global__ void __launch_bounds__(256) colstat_smem_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int dim,
+__global__ void __launch_bounds__(256) colstat_smem_kernel(const float* in, float* out, long long rows, int dim,
                                                            int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
   extern __shared__ __align__(16) float s_slab[];   // [row][CW]
   __shared__ float s_red[256];
@@ -1209,7 +1237,7 @@ __global__ void __launch_bounds__(256) colstat_smem_kernel(const float* __restri
 // thread; the kernel is bound by memory latency): used when dim % 4 == 0 and the buffers are 16-byte aligned.  Same two-pass
 // arithmetic per column as colstat_kernel (RG = 8 also sums in the same order).
 template <int RG>
-__global__ void __launch_bounds__(32 * RG) colstat4_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long rows, int dim4,
+__global__ void __launch_bounds__(32 * RG) colstat4_kernel(const float4* in, float4* out, long long rows, int dim4,
                                                           int do_var, const int4* __restrict__ clip_tab, int tab_rows) {
   __shared__ float4 s_red[RG][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -1303,6 +1331,38 @@ __global__ void lfr_kernel(const float* __restrict__ in, float* __restrict__ out
   const float* s = in + (clip * n_frames + t) * n_mels;
   float* d = out + (clip * lfr_rows * lfr_m + seg) * n_mels;
   for (int c = threadIdx.x & 31; c < n_mels; c += 32) d[c] = s[c];
+}
+
+// 16-bit PCM -> fp32 in [-1, 1): x / 32768, exact in fp32 (what AVAudioFile's float processing format hands the reference for a
+// 16-bit file, STT/Whisper/WhisperEngine.swift:327-369).  One thread = 8 samples: one 16-byte load, two 16-byte stores.
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (e0 >= n) return;
+  constexpr float k = 1.0f / 32768.0f;
+  if (e0 + 8 <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + e0));
+    const short* h = reinterpret_cast<const short*>(&v);
+    reinterpret_cast<float4*>(out + e0)[0] = make_float4(float(h[0]) * k, float(h[1]) * k, float(h[2]) * k, float(h[3]) * k);
+    reinterpret_cast<float4*>(out + e0)[1] = make_float4(float(h[4]) * k, float(h[5]) * k, float(h[6]) * k, float(h[7]) * k);
+  } else {
+    for (long long e = e0; e < e0 + 8 && e < n; ++e) out[e] = float(in[e]) * k;
+  }
+}
+
+int launch_pcm16_to_f32(const void* in_i16, float* out, int64_t n, void* stream, int* launches, std::string* err) {
+  const long long blocks = (n + 2047) / 2048;
+  if (blocks <= 0 || blocks > 0x7fffffffLL) {
+    if (err) *err = "pcm16_to_f32: bad size";
+    return B2A_E_BAD_ARG;
+  }
+  pcm16_to_f32_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const short*>(in_i16), out, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("pcm16_to_f32_kernel launch: ") + cudaGetErrorString(e);
+    return B2A_E_CUDA;
+  }
+  *launches += 1;
+  return B2A_OK;
 }
 
 // padOrTrim (WhisperAudio.swift:54-67)
@@ -1406,8 +1466,9 @@ __global__ void __launch_bounds__(256) resample_linear_kernel(const float* __res
   float idx = __fadd_rn(__fmul_rn(__fadd_rn(float(int(i)), 0.5f), step), -0.5f);   // (arange(int32).asType(float32) + 0.5) * step - 0.5
   idx = fminf(fmaxf(idx, 0.0f), hi_clip);
   const float fl = floorf(idx);
-  const int lo = int(fl);
-  const int hi = lo + 1 < int(T - 1) ? lo + 1 : int(T - 1);
+  // (T == 1: hi_clip = -0.001 < 0 leaves idx = -0.001 and floor -1; the reference's negative index wraps to x[T - 1] = x[0])
+  const int lo = int(fl) < 0 ? int(fl) + int(T) : int(fl);
+  const int hi = int(fl) + 1 < int(T - 1) ? int(fl) + 1 : int(T - 1);
   const float wh = __fadd_rn(idx, -fl);
   const float wl = __fadd_rn(1.0f, -wh);
   const float* __restrict__ xc = x + clip * T;
@@ -1468,7 +1529,7 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false, bool F16 = false>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
   if (!RAGGED && a.clip_tab != nullptr) {
     // per-clip lengths: the RAGGED instantiation of the run-time-configured kernel of the same plan (and of the Whisper
@@ -1477,9 +1538,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     if (err) *err = "ragged batches are built for the mel front ends only";
     return B2A_E_UNSUPPORTED;
   }
-  static FrontendParams<P> prm;  // large (window table); filled and launched under the lock
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lk(mu);
+  // (by value on the stack: launches from different contexts / threads share nothing)
+  FrontendParams<P> prm;
   prm.x = a.x;
   prm.clip_stride = a.n_samples;
   prm.n_samples = a.n_samples;
@@ -1544,38 +1604,64 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
                       ((MEL == 0 && SPEC != SK_CPLX) ? sizeof(float4) * size_t(steps_smem_max<P>()) : 0);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
-  cudaError_t e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute", err);
   prm.total_tiles = RAGGED ? (long long)a.total_tiles : (long long)prm.tiles_per_clip * a.batch;
   if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL || a.batch > 0x7fffffffLL || a.n_frames > 0x7fffffffLL) {
     if (err) *err = "empty launch";
     return B2A_E_BAD_ARG;
   }
-  int dev = 0, n_sm = 148, per_sm = 1;
+  // shared-memory opt-in and residency of this instantiation: queried once per device, then cached (a single 30 s clip is a
+  // ~12 us kernel; two runtime queries per launch under a process-wide lock used to cost more than that on the host)
+  struct DevInfo { std::atomic<int> ready{0}; int n_sm = 0, per_sm = 0; };
+  static DevInfo infos[64];
+  static std::mutex info_mu;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED>, P::NTHREADS, smem)) != cudaSuccess)
-    return cuda_fail(e, "occupancy query", err);
-  if (per_sm < 1) {
-    if (err) *err = "frontend kernel does not fit on this device";
+  if (dev < 0 || dev >= 64) {
+    if (err) *err = "device index out of range";
     return B2A_E_CUDA;
   }
-  per_sm = std::min(per_sm, P::MINB);
+  DevInfo& di = infos[dev];
+  cudaError_t e;
+  if (!di.ready.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(info_mu);
+    if (!di.ready.load(std::memory_order_relaxed)) {
+      int n_sm = 148, per_sm = 1;
+      if ((e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
+        return cuda_fail(e, "cudaFuncSetAttribute", err);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16>, P::NTHREADS, smem)) != cudaSuccess)
+        return cuda_fail(e, "occupancy query", err);
+      if (per_sm < 1) {
+        if (err) *err = "frontend kernel does not fit on this device";
+        return B2A_E_CUDA;
+      }
+      di.n_sm = n_sm;
+      di.per_sm = std::min(per_sm, P::MINB);
+      di.ready.store(1, std::memory_order_release);
+    }
+  }
+  const int n_sm = di.n_sm, per_sm = di.per_sm;
   const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
   if (a.whisper_norm) {
-    if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
-    if ((e = cudaMemsetAsync(a.tile_min, 0x7f, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+    // clip_max and the (negated) tile minima start from the same "very negative" pattern: one memset when the C ABI placed them
+    // back to back
+    if (reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch) {
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+    } else {
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+      if ((e = cudaMemsetAsync(a.tile_min, 0x80, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+    }
   }
-  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
     for (long long c0 = 0; c0 < a.batch; c0 += 65535) {   // gridDim.y limit
       const long long nb = std::min<long long>(65535, a.batch - c0);
       whisper_clamp_kernel<<<dim3(unsigned((prm.tiles_per_clip + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, st>>>(
-          a.out + c0 * prm.out_clip_stride, a.clip_max + c0, RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip, prm.tiles_per_clip, a.n_frames,
+          F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.out) + c0 * prm.out_clip_stride) : a.out + c0 * prm.out_clip_stride, a.clip_max + c0, RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip, prm.tiles_per_clip, a.n_frames,
           a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT,   // tiles of FT frames
-          RAGGED ? prm.clip_tab + c0 : nullptr);
+          RAGGED ? prm.clip_tab + c0 : nullptr, F16 ? 1 : 0);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
     *launches += 1;
@@ -1609,6 +1695,16 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }
   const int id = a.bank.baked_id, om = a.out_mode;
+  if (a.out_f16) {
+    // fp16 features straight from the store loop: the Whisper front end's two standard banks, (T', M) layout
+    if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE && post == POST_WNORM && om == OUT_TM) {
+      if (id == 1) return ragged ? launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM, true, true>(a, st, launches, err)
+                                 : launch_plan<Plan400, PRE_NONE, SK_POWER, 1, POST_WNORM, OUT_TM, false, true>(a, st, launches, err);
+      if (id == 2 && !ragged) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM, OUT_TM, false, true>(a, st, launches, err);
+    }
+    if (err) *err = "fp16 output is built for the Whisper log-mel front end with its standard 80 / 128-mel banks";
+    return B2A_E_UNSUPPORTED;
+  }
   if (ragged) {
     // the headline front ends keep their tuned kernels (Whisper 128 (T', M) and (M, T'), Fun-ASR LFR, CAM++ fbank); every other
     // ragged call runs the run-time-configured kernel of its plan (launch_plan forwards to the RAGGED instantiation)

@@ -450,6 +450,34 @@ int64_t b2a_s3tokenizer_plan_segments(const int64_t* mel_len, int64_t batch, int
   return n;
 }
 
+// mergeTokenizedSegments (Codec/S3Tokenizer/S3TokenizerUtils.swift:71-88; call sites S3Tokenizer.swift:622,837 with overlap = 4 s,
+// tokenRate = 25): the token sequences of consecutive long-audio windows are joined by dropping (overlap / 2) * tokenRate tokens at
+// every inner edge -- the left edge of every segment but the first, the right edge of every segment but the last; a segment whose
+// kept range is empty contributes nothing.  tokens: the segments back to back; seg_len[n_segments].  Writes at most `cap` tokens
+// to `out` (may be NULL to query) and returns the merged length, or -1 on bad arguments / overflow of `cap`.
+int64_t b2a_merge_tokenized_segments(const int32_t* tokens, const int64_t* seg_len, int64_t n_segments, int overlap, int token_rate,
+                                     int32_t* out, int64_t cap) {
+  if (!seg_len || n_segments < 0 || (n_segments > 0 && !tokens)) return -1;
+  const int64_t overlap_tokens = int64_t(overlap / 2) * token_rate;   // integer division first, as in the reference
+  int64_t n = 0, base = 0;
+  for (int64_t i = 0; i < n_segments; ++i) {
+    const int64_t len = seg_len[i];
+    if (len < 0) return -1;
+    const int64_t left = i == 0 ? 0 : overlap_tokens;
+    const int64_t right = i != n_segments - 1 ? len - overlap_tokens : len;
+    if (left < right) {
+      if (left < 0 || right > len) return -1;   // (the reference would trap on the out-of-range slice)
+      if (out) {
+        if (n + (right - left) > cap) return -1;
+        for (int64_t t = left; t < right; ++t) out[n + (t - left)] = tokens[base + t];
+      }
+      n += right - left;
+    }
+    base += len;
+  }
+  return n;
+}
+
 int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int to_rate) {  // CosyVoice2TTS.swift:733-739, CosyHiFTGenerator.swift:26-31
   if (n_samples <= 0 || from_rate <= 0 || to_rate <= 0) return 0;
   if (from_rate == to_rate) return n_samples;

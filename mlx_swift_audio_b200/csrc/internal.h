@@ -91,6 +91,7 @@ struct FrontendArgs {
   int out_mode = OUT_TM;
   int64_t n_frames = 0;           // frames to emit per clip
   float* out = nullptr;           // device
+  int out_f16 = 0;                // `out` holds __half (Whisper (T', M) front end only): the store loop rounds, no second pass
   int lfr_m = 7, lfr_n = 6;       // OUT_LFR only
   int64_t lfr_rows = 0;
   // scratch for the Whisper clamp (device): clip_max (batch) ordered-int encoded, tile_min (batch * tiles)
@@ -125,6 +126,7 @@ int launch_mel_windows(const float* mel, float* out, int n_mels, int64_t t_max, 
                        int* launches, std::string* err);
 int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T, int64_t new_t, float step, float hi_clip, void* stream,
                            int* launches, std::string* err);
+int launch_pcm16_to_f32(const void* in_i16, float* out, int64_t n, void* stream, int* launches, std::string* err);
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
                        int* launches, std::string* err);
 int launch_tile_table(const void* clip_tab, int64_t n_clips, int64_t total_tiles, void* tile_tab, void* stream, int* launches, std::string* err);
@@ -150,6 +152,7 @@ struct IstftArgs {
   float* out = nullptr;           // device (batch, (frames-1)*hop)
   float* scratch_phase = nullptr; // device, same size as phase, when unwrap != 0
   int head = 0;                   // 1: `mag` is the vocoder's conv output (batch, 2F, frames); exp / sin formed in the kernel, `phase` unused
+                                  // 2: `mag` is the complex64 spectrum (batch, F, frames) itself (mlxIstft); `phase` unused
   float out_limit = 0.0f;         // head: clip the waveform to +-out_limit (0 = none)
   const float* fade = nullptr;    // head: device, fade_len floats multiplying the start of every clip's waveform (null = none)
   int fade_len = 0;

@@ -128,8 +128,12 @@ constexpr int kIstftThreads = 256;
 // HEAD: the input is the vocoder's last convolution output h (batch, 2F, frames); magnitude = exp(h[:, :F]),
 // phase = sin(h[:, F:]) are formed in registers (HiFiGAN.swift:577-580, Generator.swift:182-183) and the waveform is clipped to
 // +-out_limit (HiFiGAN.swift:587) -- the exp / sin pass, the iSTFT and the limiter are one pass over 88 bytes per frame.
-template <int NFFT, int HOP, bool HEAD>
+// MODE 2 (RECT): the input is the complex spectrum itself, complex64 (batch, F, frames) -- stand-alone mlxIstft
+// (MLXSTFT.swift:115-163): no clip, no polar conversion, no unwrap.
+enum IstftMode { IM_POLAR = 0, IM_HEAD = 1, IM_RECT = 2 };
+template <int NFFT, int HOP, int MODE>
 __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_constant__ IstftParams<NFFT, HOP> prm) {
+  constexpr bool HEAD = MODE == IM_HEAD, RECT = MODE == IM_RECT;
   constexpr int F = NFFT / 2 + 1;
   constexpr int R = NFFT / HOP;          // overlapping frames per output segment
   constexpr int HALO = R - 1;
@@ -165,7 +169,15 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
     const float* __restrict__ pp = prm.phase + (clip * clip_rows * nF + f);
     float xr[F], xi[F], ph[F];
     float amax = 0.0f;
-    if (HEAD) {
+    if (RECT) {
+      const float2* __restrict__ cp = reinterpret_cast<const float2*>(prm.mag) + (clip * F * nF + f);
+#pragma unroll
+      for (int k = 0; k < F; ++k) {
+        const float2 v = has_frame ? __ldg(cp + k * nFu) : make_float2(0.0f, 0.0f);
+        xr[k] = v.x;
+        xi[k] = v.y;   // (DC / Nyquist imaginary parts are ignored by the codelet, as by irfft)
+      }
+    } else if (HEAD) {
       // all 2F loads first (memory-level parallelism), then the exp / sin arithmetic
 #pragma unroll
       for (int k = 0; k < F; ++k) {
@@ -204,7 +216,10 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
     // every phase of the warp's 32 frames inside (-pi/2, pi/2)?  (false for NaN)  Then (a) sin / cos need no range
     // reduction and (b) no phase step inside the warp can reach pi.
     // (HEAD: |phase| <= 1 by construction, or NaN, which the polynomials propagate like the reference's cos / sin)
-    const bool small = HEAD || __all_sync(0xffffffffu, amax < 1.5707963f);
+    const bool small = RECT || HEAD || __all_sync(0xffffffffu, amax < 1.5707963f);
+    if (RECT) {
+      // rectangular input: nothing to convert
+    } else
     if (NFFT == 20 && prm.unwrap_flag != nullptr && !small) {   // (only Kokoro's 20 / 5 transform unwraps)
       // Kokoro's unwrap (MLXSTFT.swift:23-46) is the identity unless some |phase[t] - phase[t-1]| >= pi.  A pair (t-1, t) is
       // examined by the warp of frame t (left neighbour: shuffle, lane 0 from global memory) and, when t-1 is a warp's last
@@ -222,7 +237,8 @@ __global__ void __launch_bounds__(kIstftThreads) istft_kernel(const __grid_const
       }
       if (bad) *prm.unwrap_flag = 1;
     }
-    if (small) {
+    if (RECT) {
+    } else if (small) {
 #pragma unroll
       for (int k = 0; k < F; ++k) {
         const float u = ph[k] * ph[k];
@@ -493,8 +509,8 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   prm.unwrap_flag = unwrap_flag;
   prm.out_limit = a.out_limit;
   prm.fade = a.fade;
-  prm.fade_len = a.head && a.fade != nullptr ? a.fade_len : 0;
-  if (a.head) {   // one tensor (batch, 2F, frames): the phase rows follow the magnitude rows of the same clip
+  prm.fade_len = a.head == 1 && a.fade != nullptr ? a.fade_len : 0;
+  if (a.head == 1) {   // one tensor (batch, 2F, frames): the phase rows follow the magnitude rows of the same clip
     prm.phase = a.mag + (long long)F * a.n_frames;
   }
   for (int n = 0; n < NFFT; ++n) {
@@ -510,8 +526,9 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   const long long n_seg = a.n_frames + R - 1;
   const int per_block = kIstftThreads - (R - 1);
   dim3 grid(unsigned((n_seg + per_block - 1) / per_block), unsigned(a.batch));
-  if (a.head) istft_kernel<NFFT, HOP, true><<<grid, kIstftThreads, 0, st>>>(prm);
-  else istft_kernel<NFFT, HOP, false><<<grid, kIstftThreads, 0, st>>>(prm);
+  if (a.head == 2) istft_kernel<NFFT, HOP, IM_RECT><<<grid, kIstftThreads, 0, st>>>(prm);
+  else if (a.head) istft_kernel<NFFT, HOP, IM_HEAD><<<grid, kIstftThreads, 0, st>>>(prm);
+  else istft_kernel<NFFT, HOP, IM_POLAR><<<grid, kIstftThreads, 0, st>>>(prm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail2(e, "istft_kernel launch", err);
   *launches += 1;

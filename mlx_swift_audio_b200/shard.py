@@ -45,7 +45,8 @@ class FusedGather:
     the front end, so the kernel's epilogue stores ARE the transfer -- they overlap the FFT work tile by tile, there is no
     staging copy and no NCCL call on the data path.  torch.distributed only carries the 64-byte handle and the final barrier.
 
-        fg = FusedGather(ctx, n_clips, (3000, 128))
+        ctx = api.Context(dev, torch.cuda.current_stream(dev).cuda_stream)      # (an own-stream Context also works: api orders it
+        fg = FusedGather(ctx, n_clips, (3000, 128))                             #  against torch's current stream around every call)
         api.whisperLogMelSpectrogram(x_local, 128, ctx=ctx, out=fg.local_out())     # x_local: this rank's shard_range() clips
         full = fg.finish()          # rank dst: torch view of all clips' features; None elsewhere
 

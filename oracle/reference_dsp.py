@@ -723,6 +723,20 @@ def resample_audio(audio, from_rate: int, to_rate: int) -> np.ndarray:
 
 
 
+def merge_tokenized_segments(tokenized_segments, overlap: int, token_rate: int):
+    """mergeTokenizedSegments, Codec/S3Tokenizer/S3TokenizerUtils.swift:71-88."""
+    merged = []
+    overlap_tokens = (overlap // 2) * token_rate
+    n = len(tokenized_segments)
+    for i, tokens in enumerate(tokenized_segments):
+        tokens = list(tokens)
+        left = 0 if i == 0 else overlap_tokens
+        right = len(tokens) - overlap_tokens if i != n - 1 else len(tokens)
+        if left < right:
+            merged.extend(tokens[left:right])
+    return merged
+
+
 def s3tokenizer_segments(mel, mel_len, window: int = 3000, stride: int = 2600):
     """Segment plan + unified batch of S3Tokenizer.quantize / quantizeMixedBatch, Codec/S3Tokenizer/S3Tokenizer.swift:474-571.
     mel (B, M, Tmax), mel_len (B,) -> (segments (S, M, window) fp32, lengths (S,), info [(batch_idx, segment_idx), ...]).

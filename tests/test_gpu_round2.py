@@ -1,0 +1,165 @@
+"""GPU parity tests of the round-2 entry points and of the branches round 1 left untested (VERDICT r01 "What's weak" 4,
+"Next round" 3 and 6): fp16 / 16-bit-PCM Whisper entries (bit-exact), voice-encoder dB / normalised branches, b2a_stft n_fft 512,
+stand-alone mlxIstft, resample of a one-sample clip, own-stream contexts with torch tensors, tiny clips through the host pipeline."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import reference_dsp as R
+from tests import synth
+from tests.test_gpu_parity import assert_feat_close, ISTFT_ATOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(ctx):
+    from mlx_swift_audio_b200 import api as A
+    return A
+
+
+def _bits(a):
+    return np.asarray(a).view(np.uint16)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+@pytest.mark.parametrize("n", [16000 * 3 + 37, 5000, 480000 // 4])
+def test_whisper_f16_is_the_cast_of_the_fp32_entry(api, ctx, n_mels, n):
+    # asType(.float16) of the fp32 feature (WhisperSTT.swift:156-157): round-to-nearest-even is what NumPy's astype does too
+    x = synth.pcm(3, n, seed=2001)
+    f32 = api.whisperLogMelSpectrogram(x, nMels=n_mels, ctx=ctx)
+    f16 = api.whisperLogMelSpectrogramF16(x, nMels=n_mels, ctx=ctx)
+    assert f16.dtype == np.float16 and f16.shape == f32.shape
+    assert np.array_equal(_bits(f16), _bits(f32.astype(np.float16)))
+    # and against the oracle: fp16 spacing at |v| <= 2 is <= 9.8e-4, on top of the 1e-4 fp32 tolerance
+    want = np.stack([R.whisper_log_mel_spectrogram(c, n_mels) for c in x]).astype(np.float16)
+    assert np.abs(f16.astype(np.float32) - want.astype(np.float32)).max() <= 2e-3
+
+
+def test_whisper_f16_device_space_and_padding(api, ctx):
+    import torch
+    x = synth.pcm(2, 20000, seed=2002)
+    f32 = api.whisperLogMelSpectrogram(x, nMels=128, padding=4000, ctx=ctx)
+    xd = torch.from_numpy(x).cuda()
+    f16 = api.whisperLogMelSpectrogramF16(xd, nMels=128, padding=4000)
+    assert f16.dtype == torch.float16
+    assert np.array_equal(_bits(f16.cpu().numpy()), _bits(f32.astype(np.float16)))
+
+
+@pytest.mark.parametrize("f16", [False, True])
+@pytest.mark.parametrize("n", [16001, 48000])     # (odd length: the 16-bit rows are not 4-byte multiples)
+def test_whisper_pcm16_equals_float_entry_on_scaled_samples(api, ctx, f16, n):
+    rng = np.random.default_rng(2003)
+    xi = rng.integers(-32768, 32768, (3, n)).astype(np.int16)
+    xi[:, n - n // 10:] = 0
+    xi[0, :5] = [-32768, 32767, 0, 1, -1]
+    xf = xi.astype(np.float32) / np.float32(32768.0)       # exact
+    if f16:
+        got = api.whisperLogMelSpectrogramF16(xi, nMels=128, ctx=ctx)
+        want = api.whisperLogMelSpectrogramF16(xf, nMels=128, ctx=ctx)
+        assert np.array_equal(_bits(got), _bits(want))
+    else:
+        got = api.whisperLogMelSpectrogramPCM16(xi, nMels=128, ctx=ctx)
+        want = api.whisperLogMelSpectrogram(xf, nMels=128, ctx=ctx)
+        assert np.array_equal(got, want)
+        assert_feat_close(got, np.stack([R.whisper_log_mel_spectrogram(c, 128) for c in xf]), what="pcm16 vs oracle")
+
+
+def test_whisper_pcm16_device_space(api, ctx):
+    import torch
+    rng = np.random.default_rng(2004)
+    xi = rng.integers(-20000, 20000, (2, 32000)).astype(np.int16)
+    want = api.whisperLogMelSpectrogramF16(xi, nMels=80, ctx=ctx)
+    got = api.whisperLogMelSpectrogramF16(torch.from_numpy(xi).cuda(), nMels=80)
+    assert np.array_equal(_bits(got.cpu().numpy()), _bits(want))
+
+
+def test_whisper_f16_ragged(api, ctx):
+    from mlx_swift_audio_b200 import _lib as L
+    n = 30000
+    x = synth.pcm(4, n, seed=2005)
+    lens = np.array([n, 5120, 12345, 401], np.int64)
+    frames = int(ctx.lib.b2a_whisper_num_frames(n, 0))
+    out = np.full((4, frames, 128), 7.0, np.float16)
+    rows = np.zeros(4, np.int64)
+    I64 = C.POINTER(C.c_int64)
+    ctx.check(ctx.lib.b2a_whisper_log_mel_spectrogram_f16_ragged(ctx.h, C.c_void_p(x.ctypes.data), 4, n, lens.ctypes.data_as(I64), 128, 0,
+                                                               C.c_void_p(out.ctypes.data), rows.ctypes.data_as(I64), L.B2A_HOST))
+    for b in range(4):
+        want = api.whisperLogMelSpectrogram(x[b, :lens[b]], nMels=128, ctx=ctx).astype(np.float16)
+        assert rows[b] == want.shape[0]
+        assert np.array_equal(_bits(out[b, :rows[b]]), _bits(want))
+        assert not out[b, rows[b]:].any()
+
+
+def test_voice_encoder_db_and_normalized_branches(api, ctx):
+    # VoiceEncoderMelspec.swift:52-65: melType "db" (20 log10 max(., stft_magnitude_min)) and normalized_mels
+    from mlx_swift_audio_b200 import _lib as L
+    x = synth.pcm(2, 16000, seed=2006)
+    for kw in (dict(mel_type="db"), dict(mel_type="db", normalized_mels=True), dict(mel_power=1.0, mel_type="db"),
+               dict(normalized_mels=True)):
+        cfg = L.VoiceEncConfig()
+        ctx.lib.b2a_voice_enc_config_default(C.byref(cfg))
+        cfg.mel_type_db = int(kw.get("mel_type") == "db")
+        cfg.normalized_mels = int(kw.get("normalized_mels", False))
+        cfg.mel_power = kw.get("mel_power", 2.0)
+        got = api.voiceEncoderMelspectrogram(x, config=cfg, ctx=ctx)
+        want = np.stack([R.voice_encoder_melspectrogram(c, **kw) for c in x])
+        # dB values reach -80: the scaled tolerance 1e-4 * max(1, |want|) is the north-star's relative one
+        assert_feat_close(got, want, what=f"voice encoder {kw}")
+
+
+def test_stft_n_fft_512(api, ctx):
+    # plain stft() on the 512-point plan (400-tap window zero-extended, S3TokenizerUtils.swift:235-239)
+    x = synth.pcm(2, 8000, seed=2007)
+    w = api.hanningWindow(401)[:400]
+    for center in (True, False):
+        got = api.stft(x, window=w, nFft=512, hopLength=160, winLength=400, center=center, ctx=ctx)
+        want = np.stack([R.stft(c, w, 512, 160, center=center) for c in x])
+        scale = np.abs(want).max()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-5 * scale
+
+
+def test_mlx_istft_standalone(api, ctx):
+    # mlxIstft (MLXSTFT.swift:115-163): complex (F, T') spectrum in, no unwrap; Kokoro's window-sum normalisation
+    mag, ph = synth.mag_phase(2, 11, 501, seed=2008)
+    re, im = (mag * np.cos(ph)).astype(np.float32), (mag * np.sin(ph)).astype(np.float32)
+    got = api.mlxIstft(re, im, hopLength=5, winLength=20, ctx=ctx)
+    want = np.stack([R.mlx_istft((re[b] + 1j * im[b]).astype(np.complex64), 5, 20) for b in range(2)])
+    one = api.mlxIstft((re[0] + 1j * im[0]).astype(np.complex64), hopLength=5, winLength=20, ctx=ctx)
+    assert np.array_equal(one, got[0])
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= ISTFT_ATOL
+
+
+def test_resample_single_sample_clip(api, ctx):
+    # T == 1: the clip bound Float(T) - 1.001 is negative, floor gives -1 and the reference's gather wraps to x[0]
+    x = np.array([[0.75], [-0.3]], np.float32)
+    got = api.resampleAudio(x, 16000, 24000, ctx=ctx)
+    want = np.stack([R.resample_audio(c, 16000, 24000) for c in x])
+    assert np.array_equal(got, want)
+
+
+def test_tiny_clips_through_the_host_pipeline(api, ctx):
+    # 70 000 rows of 8 frames: the byte-sized chunk of the host pipeline alone would exceed gridDim.y
+    ph = np.random.default_rng(2009).uniform(-3, 3, (70000, 8)).astype(np.float32)
+    got = api.unwrap(ph, ctx=ctx)
+    assert np.abs(got - R.unwrap(ph)).max() <= 1e-5
+
+
+def test_own_stream_context_is_ordered_against_torch(api):
+    import torch
+    own = api.Context(0)           # private non-blocking stream
+    try:
+        x = torch.from_numpy(synth.pcm(8, 160000, seed=2010)).cuda()
+        ref = api.whisperLogMelSpectrogram(x, nMels=128)       # torch's stream
+        for _ in range(3):
+            y = torch.zeros_like(x)
+            y.copy_(x)                                         # producer on torch's stream
+            out = api.whisperLogMelSpectrogram(y, nMels=128, ctx=own)
+            z = out.clone()                                    # consumer on torch's stream
+            assert torch.equal(z, ref)
+    finally:
+        own.close()

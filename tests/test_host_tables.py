@@ -232,3 +232,23 @@ def test_incremental_walk_of_the_staging_offsets(built_lib, n_fft, n_mels, step)
             if r >= cap:
                 r -= cap
                 q += 1
+
+
+def test_merge_tokenized_segments_matches_the_reference_rule():
+    # mergeTokenizedSegments (S3TokenizerUtils.swift:71-88): bit-exact integer rule, incl. segments shorter than the dropped edges
+    from mlx_swift_audio_b200 import api
+    from oracle import reference_dsp as R
+    rng = np.random.default_rng(11)
+    cases = [
+        [list(range(750)), list(range(1000, 1750)), list(range(2000, 2300))],      # S3Tokenizer's own shape: 30 s windows at 25 Hz
+        [list(range(10))],                                                         # a single segment is kept whole
+        [list(range(60)), list(range(100, 140)), list(range(200, 260))],           # middle segment shorter than 2 * 50: dropped
+        [list(range(50)), list(range(100, 150))],                                  # exactly the dropped edge: nothing left of either
+        [],
+        [[], [1, 2, 3]],
+    ]
+    for _ in range(20):
+        cases.append([list(rng.integers(0, 6561, int(rng.integers(0, 400)))) for _ in range(int(rng.integers(1, 6)))])
+    for segs in cases:
+        for overlap, rate in ((4, 25), (5, 25), (2, 50), (0, 25)):
+            assert api.mergeTokenizedSegments(segs, overlap, rate) == [int(v) for v in R.merge_tokenized_segments(segs, overlap, rate)]
