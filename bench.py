@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Benchmark of the STFT-family DSP hot path on B200 (contract: see the task statement / DESIGN.md).
+"""Benchmark of the STFT-family DSP hot path on B200 (contract: see the task statement / DESIGN.md section 5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
@@ -8,12 +8,19 @@ BASELINE.json configs[1]: Whisper large-v3-turbo 128-mel log-mel of 1024 x 30 s 
 scaling: every rank owns its own 1024 clips, no data-path collective).  Prints ONE JSON line.
 
   value     whole-job audio-seconds per second with inputs resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+  e2e       same metric through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region); for the
+            Whisper workloads the headline e2e goes through the 16-bit-PCM-in / fp16-out entry point (the bytes a Whisper
+            pipeline actually needs to move), with the fp32-in / fp32-out call and the two copy directions alone beside it
   roofline  algorithmic bytes / device time of the call vs the measured HBM copy bandwidth
-  cpu_baseline  the CPU oracle (port of the reference's algorithm) on a bounded sample, all host cores
+  cpu_baseline  the CPU restatement of the reference's algorithm on a bounded sample, all host cores
+  workloads (default run only) the same record -- ms_per_step, roofline, e2e, clocks, cpu_baseline -- for every other BASELINE
+            config: HiFT iSTFT (5a), Kokoro iSTFT (5b), Fun-ASR (3a), Kaldi fbank (3b), S3Gen 24 kHz mel (4), one 30 s clip (1)
+  gather    (N > 1) the step WITH the features delivered to rank 0 on a reduced batch, fused peer stores and kernel + NCCL,
+            each verified bit for bit against rank 0's own single-GPU run of every rank's clips
 
---impl reference times the CPU restatement of the reference (oracle/: the NumPy port and, for the headline
-workloads, its compiled multi-threaded twin; the reference itself cannot be built outside macOS) on the host cores for the same workload; under torchrun only rank 0 works.
+--impl reference times ONE named CPU restatement of the reference (oracle/: its compiled multi-threaded twin for the workloads
+it covers, the NumPy port otherwise; the reference itself is Swift + MLX and cannot be built outside macOS) on the host cores
+for the same workload: a fixed bounded sample per step, median over the steps, spread reported; under torchrun only rank 0 works.
 """
 from __future__ import annotations
 
@@ -34,25 +41,30 @@ import numpy as np  # noqa: E402
 
 METRIC = "audio_seconds_per_second"
 UNIT = "audio-s/s"
+PARITY_NOTE = "partial: bit-exact / 1e-4 / 1e-5 against a CPU restatement of the reference (oracle/); the reference has no golden vectors and cannot run here, so parity is UNPINNED"
 
-# name -> dict(batch, seconds per clip, sample rate, algorithmic bytes per clip, description)
+# name -> dict(batch, seconds per clip, sample rate, seed (1000 + BASELINE config index), description)
 WORKLOADS = {
     # SURVEY.md 8(d) / BASELINE.md section 3
-    "whisper128": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper large-v3-turbo 128-mel log-mel, 1024 x 30 s @16 kHz (configs[1])"),
-    "whisper80_1clip": dict(batch=1, clip_s=30.0, sr=16000, desc="Whisper 80-mel log-mel, 1 x 30 s (configs[0])"),
-    "funasr": dict(batch=512, clip_s=20.0, sr=16000, desc="Fun-ASR preprocessAudio (log-mel + LFR 7/6 + CMVN), 512 x 20 s (configs[2], 3a)"),
-    "kaldi": dict(batch=512, clip_s=20.0, sr=16000, desc="Kaldi-style 80-dim fbank (CAM++) + mean-norm, 512 x 20 s (configs[2], 3b)"),
-    "s3gen": dict(batch=256, clip_s=10.0, sr=24000, desc="CosyVoice2/Chatterbox 24 kHz 80-mel (n_fft 1920, hop 480), 256 x 10 s (configs[3])"),
-    "istft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="CosyVoice HiFT iSTFT (n_fft 16, hop 4), 512 x 30 s of mag/phase (configs[4], 5a)"),
-    "whisper_segment": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper seek window: slice + zero-pad + fp16 cast of the 128-mel log-mel, 1024 clips (SURVEY 8f rank 1)"),
-    "hift_head": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
-    "whisper128_ragged": dict(batch=1024, clip_s=30.0, sr=16000, desc="Whisper 128-mel log-mel of a RAGGED batch: 1024 clips of 5..30 s (uniform) in one launch (b2a_whisper_log_mel_spectrogram_ragged)"),
-    "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
-    "chatterbox128": dict(batch=1024, clip_s=10.0, sr=16000, desc="S3Tokenizer / Chatterbox 128-mel log-mel (periodic Hann, (M, T') layout), 1024 x 10 s @16 kHz (SURVEY 8a row a14)"),
-    "voice_encoder": dict(batch=1024, clip_s=10.0, sr=16000, desc="Chatterbox voice-encoder 40-mel power mel ((M, T') layout, interpreted bank), 1024 x 10 s @16 kHz (SURVEY 8a row a21)"),
-    "stft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, desc="Kokoro MLXSTFT.transform (n_fft 20, hop 5): magnitude and atan2 phase, 512 x 30 s (SURVEY 8a row a26)"),
-    "stft_hift": dict(batch=512, clip_s=30.0, sr=24000, desc="HiFT forward STFT of the source signal (stftHiFiGAN, n_fft 16, hop 4, reflect pad), 512 x 30 s -> real / imag (SURVEY 8a row a22)"),
+    "whisper128": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper large-v3-turbo 128-mel log-mel, 1024 x 30 s @16 kHz (configs[1])"),
+    "whisper80_1clip": dict(batch=1, clip_s=30.0, sr=16000, seed=1000, desc="Whisper 80-mel log-mel, 1 x 30 s (configs[0])"),
+    "funasr": dict(batch=512, clip_s=20.0, sr=16000, seed=1002, desc="Fun-ASR preprocessAudio (log-mel + LFR 7/6 + CMVN), 512 x 20 s (configs[2], 3a)"),
+    "kaldi": dict(batch=512, clip_s=20.0, sr=16000, seed=1002, desc="Kaldi-style 80-dim fbank (CAM++) + mean-norm, 512 x 20 s (configs[2], 3b)"),
+    "s3gen": dict(batch=256, clip_s=10.0, sr=24000, seed=1003, desc="CosyVoice2/Chatterbox 24 kHz 80-mel (n_fft 1920, hop 480), 256 x 10 s (configs[3])"),
+    "istft_hift": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="CosyVoice HiFT iSTFT (n_fft 16, hop 4), 512 x 30 s of mag/phase (configs[4], 5a)"),
+    "whisper_segment": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper seek window: slice + zero-pad + fp16 cast of the 128-mel log-mel, 1024 clips (SURVEY 8f rank 1)"),
+    "whisper128_f16": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper 128-mel log-mel written as fp16 by the store loop (asType(.float16) fused), 1024 x 30 s (SURVEY 8f rank 1)"),
+    "hift_head": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
+    "whisper128_ragged": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper 128-mel log-mel of a RAGGED batch: 1024 clips of 5..30 s (uniform) in one launch (b2a_whisper_log_mel_spectrogram_ragged)"),
+    "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
+    "chatterbox128": dict(batch=1024, clip_s=10.0, sr=16000, seed=1003, desc="S3Tokenizer / Chatterbox 128-mel log-mel (periodic Hann, (M, T') layout), 1024 x 10 s @16 kHz (SURVEY 8a row a14)"),
+    "voice_encoder": dict(batch=1024, clip_s=10.0, sr=16000, seed=1003, desc="Chatterbox voice-encoder 40-mel power mel ((M, T') layout), 1024 x 10 s @16 kHz (SURVEY 8a row a21)"),
+    "stft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="Kokoro MLXSTFT.transform (n_fft 20, hop 5): magnitude and atan2 phase, 512 x 30 s (SURVEY 8a row a26)"),
+    "stft_hift": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="HiFT forward STFT of the source signal (stftHiFiGAN, n_fft 16, hop 4, reflect pad), 512 x 30 s -> real / imag (SURVEY 8a row a22)"),
 }
+# every other BASELINE config, measured inside the default run
+SECONDARY = ["istft_hift", "istft_kokoro", "funasr", "kaldi", "s3gen", "whisper80_1clip"]
+UNIQUE_CLIPS = 16   # distinct synthetic clips per rank (SURVEY 8d streams seed, b), tiled to the batch
 
 
 def _peaks():
@@ -115,14 +127,54 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def numa_bind(local_rank: int) -> dict:
+    """Pins this process to the CPUs of its GPU's NUMA node BEFORE any pinned host buffer is allocated (first-touch places the
+    pages next to the GPU's PCIe root).  -> what was done, for the JSON line (per-rank NUMA / affinity attribution of the e2e
+    numbers).  Best effort: cgroup CPU sets, missing sysfs entries or a single-node host leave the affinity untouched."""
+    info = {"gpu": local_rank, "numa_node": None, "cpus_before": len(os.sched_getaffinity(0)), "bound": False}
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        info["numa_node"] = node
+        info["pci"] = bdf
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if node >= 0 and want and want != allowed:
+            os.sched_setaffinity(0, want)
+            info["bound"] = True
+        info["cpus_after"] = len(os.sched_getaffinity(0))
+    except Exception as ex:   # noqa: BLE001
+        info["error"] = str(ex)[:120]
+    return info
+
+
 # ------------------------------------------------------------------------------------------------------
 # workloads on the GPU (direct C-ABI calls on preallocated buffers)
 # ------------------------------------------------------------------------------------------------------
 
+def _tile(torch, u, batch, dev):
+    """(U, ...) NumPy clips -> (batch, ...) device tensor: clip b = unique clip b mod U."""
+    t = torch.from_numpy(np.ascontiguousarray(u)).to(dev)
+    reps = (batch + t.shape[0] - 1) // t.shape[0]
+    return t.repeat((reps,) + (1,) * (t.dim() - 1))[:batch].contiguous()
+
+
 class GpuWorkload:
-    def __init__(self, name, batch_override=None):
+    def __init__(self, name, batch_override=None, rank=None):
         import torch
         from mlx_swift_audio_b200 import api, _lib
+        from tests import synth
         self.torch = torch
         self.name = name
         w = WORKLOADS[name]
@@ -136,16 +188,19 @@ class GpuWorkload:
         self.hctx = api.Context(dev.index)  # own stream for the host-buffer (e2e) path
         lib = self.ctx.lib
         self.lib = lib
-        g = torch.Generator(device=dev)
-        g.manual_seed(1000 + (int(os.environ.get("RANK", "0"))))
+        rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+        seed = w["seed"] + 100 * rank          # 1000 + config index; clip b uses the stream (seed, b)
+        self.seed = seed
         B, n = self.batch, self.n
-        DEV = _lib.B2A_DEVICE
+        U = min(B, UNIQUE_CLIPS)
+        self.pcm16 = None                      # Whisper workloads: unique clips as 16-bit PCM for the e2e headline
+        self.e2e16 = None
         if name == "whisper_segment":
             frames = 6000                      # mel of 30 s of audio + the 30 s of padding transcribe() appends
-            mel = torch.randn((B, frames, 128), generator=g, device=dev)
+            rs = np.random.default_rng(seed)
+            mel = _tile(torch, rs.standard_normal((U, frames, 128)).astype(np.float32), B, dev)
             self.inputs = [mel]
             self.out = torch.empty((B, 3000, 128), dtype=torch.float16, device=dev)
-            rs = np.random.default_rng(3)
             seek = np.ascontiguousarray(rs.integers(0, 3000, B), np.int64)     # arbitrary frame offsets, as the decoder produces
             content = np.full(B, 3000, np.int64)                               # 30 s of content: windows near the end are zero-padded
             self._keep = (seek, content)
@@ -154,10 +209,11 @@ class GpuWorkload:
                                                                             content.ctypes.data_as(I64), 3000, o, sp)
         elif name == "hift_head":
             frames = n // 4 + 1
-            h = torch.randn((B, 18, frames), generator=g, device=dev)
+            rs = np.random.default_rng(seed)
+            h = rs.standard_normal((U, 18, frames)).astype(np.float32)
             h[:, :9] -= 2.0
             h[:, 9:] *= 2.0
-            self.inputs = [h]
+            self.inputs = [_tile(torch, h, B, dev)]
             self.out = torch.empty((B, (frames - 1) * 4), device=dev)
             win = np.ascontiguousarray(api.hannWindowPeriodic(16), np.float32)
             self._keep = win
@@ -165,13 +221,13 @@ class GpuWorkload:
             self.call = lambda c, i, o, sp: lib.b2a_hift_head_istft(c.h, i[0], B, frames, 16, 4, wp, C.c_float(0.99), o, sp)
         elif name == "stft_kokoro":
             frames = int(lib.b2a_vocoder_stft_num_frames(n, 20, 5))
-            self.inputs = [0.1 * torch.randn((B, n), generator=g, device=dev)]
+            self.inputs = [_tile(torch, synth.pcm(U, n, sample_rate=self.sr, seed=seed), B, dev)]
             self.out = torch.empty((2, B, 11, frames), device=dev)   # magnitude and phase, one buffer
             half = B * 11 * frames * 4
             self.call = lambda c, i, o, sp: lib.b2a_kokoro_stft_transform(c.h, i[0], B, n, 20, 5, 20, o, C.c_void_p(o.value + half), sp)
         elif name == "stft_hift":
             frames = int(lib.b2a_vocoder_stft_num_frames(n, 16, 4))
-            self.inputs = [0.1 * torch.randn((B, n), generator=g, device=dev)]
+            self.inputs = [_tile(torch, synth.pcm(U, n, sample_rate=self.sr, seed=seed), B, dev)]
             self.out = torch.empty((2, B, 9, frames), device=dev)   # real and imaginary parts, one buffer
             win = np.ascontiguousarray(api.hannWindowPeriodic(16), np.float32)
             self._keep = win
@@ -182,9 +238,8 @@ class GpuWorkload:
             nfft, hop = (16, 4) if name == "istft_hift" else (20, 5)
             F = nfft // 2 + 1
             frames = n // hop + 1
-            self.inputs = [torch.exp(torch.randn((B, F, frames), generator=g, device=dev) - 2.0),
-                           torch.sin(2.0 * torch.randn((B, F, frames), generator=g, device=dev))]
-            self.inputs[0][torch.rand((B, F, frames), generator=g, device=dev) < 1e-3] = 150.0
+            mag, ph = synth.mag_phase(min(U, 8), F, frames, seed=seed)     # exp(N(-2,1)) with 0.1 % at 150, sin(N(0, 2^2))
+            self.inputs = [_tile(torch, mag, B, dev), _tile(torch, ph, B, dev)]
             self.out = torch.empty((B, (frames - 1) * hop), device=dev)
             win = np.ascontiguousarray(api.hannWindowPeriodic(16), np.float32)
             self._keep = win
@@ -194,14 +249,8 @@ class GpuWorkload:
             else:
                 self.call = lambda c, i, o, sp: lib.b2a_kokoro_stft_inverse(c.h, i[0], i[1], B, frames, 20, 5, 20, o, sp)
         else:
-            t = torch.arange(n, device=dev, dtype=torch.float32) / self.sr
-            x = 0.1 * torch.randn((B, n), generator=g, device=dev)
-            for f in (220.0, 1000.0, 3300.0):
-                ph = 2 * np.pi * torch.rand((B, 1), generator=g, device=dev)
-                x += 0.2 * torch.sin(2 * np.pi * f * t[None, :] + ph)
-            x.clamp_(-1.0, 1.0)
-            x[:, n - n // 10:] = 0.0
-            self.inputs = [x]
+            xu = synth.pcm(U, n, sample_rate=self.sr, seed=seed)            # SURVEY 8d PCM streams
+            self.inputs = [_tile(torch, xu, B, dev)]
             if name == "whisper128_ragged":
                 rs = np.random.default_rng(4)
                 lens = np.ascontiguousarray(rs.integers(5 * self.sr, n + 1, B), np.int64)
@@ -214,11 +263,18 @@ class GpuWorkload:
                 self.audio_s = float(lens.sum()) / self.sr
                 self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram_ragged(c.h, i[0], B, n, lens.ctypes.data_as(I64), 128, 0, o,
                                                                                            rows.ctypes.data_as(I64), sp)
-            elif name in ("whisper128", "whisper80_1clip"):
-                nm = 128 if name == "whisper128" else 80
+            elif name in ("whisper128", "whisper80_1clip", "whisper128_f16"):
+                nm = 80 if name == "whisper80_1clip" else 128
                 frames = int(lib.b2a_whisper_num_frames(n, 0))
-                self.out = torch.empty((B, frames, nm), device=dev)
-                self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram(c.h, i[0], B, n, nm, 0, o, sp)
+                if name == "whisper128_f16":
+                    self.out = torch.empty((B, frames, nm), dtype=torch.float16, device=dev)
+                    self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram_f16(c.h, i[0], B, n, nm, 0, o, sp)
+                else:
+                    self.out = torch.empty((B, frames, nm), device=dev)
+                    self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram(c.h, i[0], B, n, nm, 0, o, sp)
+                self.pcm16 = np.clip(np.rint(xu * 32767.0), -32768, 32767).astype(np.int16)
+                self.e2e16 = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram_pcm16(c.h, i, B, n, nm, 0, 1, o, sp)
+                self.out16_shape = (B, frames, nm)
             elif name == "chatterbox128":
                 frames = int(lib.b2a_whisper_num_frames(n, 0))   # the last STFT frame is dropped, as in the Whisper front end
                 self.out = torch.empty((B, 128, frames), device=dev)
@@ -253,29 +309,49 @@ class GpuWorkload:
         if name == "whisper_segment":   # only the windows' rows are read (here: the rows up to frame 3000 from each seek)
             self.algo_bytes = int(sum(3000 - int(s0) for s0 in self._keep[0])) * 128 * 4 + self.out_bytes
         self.DEV, self.HOST = _lib.B2A_DEVICE, _lib.B2A_HOST
-        self.h_in = self.h_out = None
+        self.h_in = self.h_out = self.h_in16 = self.h_out16 = None
 
-    def step_device(self):
-        rc = self.call(self.ctx, [C.c_void_p(t.data_ptr()) for t in self.inputs], C.c_void_p(self.out.data_ptr()), self.DEV)
+    def close(self):
+        self.inputs = self.out = self.h_in = self.h_out = self.h_in16 = self.h_out16 = None
+        self.ctx.close()
+        self.hctx.close()
+        self.torch.cuda.empty_cache()
+
+    def _check(self, ctx, rc, what):
         if rc != 0:
-            raise RuntimeError("b200audio call failed: " + self.lib.b2a_last_error(self.ctx.h).decode())
+            raise RuntimeError(f"b200audio {what} failed: " + self.lib.b2a_last_error(ctx.h).decode())
+
+    def step_device(self, out_ptr=None):
+        rc = self.call(self.ctx, [C.c_void_p(t.data_ptr()) for t in self.inputs], out_ptr or C.c_void_p(self.out.data_ptr()), self.DEV)
+        self._check(self.ctx, rc, "device call")
 
     def prepare_host(self):
         torch = self.torch
-        self.h_in = [torch.empty(t.shape, dtype=torch.float32, pin_memory=True) for t in self.inputs]
+        self.h_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in self.inputs]
         for h, d in zip(self.h_in, self.inputs):
             h.copy_(d)
         self.h_out = torch.empty(self.out.shape, dtype=self.out.dtype, pin_memory=True)
+        if self.e2e16 is not None:
+            B = self.batch
+            self.h_in16 = torch.empty((B, self.n), dtype=torch.int16, pin_memory=True)
+            u = torch.from_numpy(self.pcm16)
+            for b0 in range(0, B, u.shape[0]):
+                m = min(u.shape[0], B - b0)
+                self.h_in16[b0:b0 + m].copy_(u[:m])
+            self.h_out16 = torch.empty(self.out16_shape, dtype=torch.float16, pin_memory=True)
         torch.cuda.synchronize()
 
     def step_host(self):
         rc = self.call(self.hctx, [C.c_void_p(t.data_ptr()) for t in self.h_in], C.c_void_p(self.h_out.data_ptr()), self.HOST)
-        if rc != 0:
-            raise RuntimeError("b200audio host call failed: " + self.lib.b2a_last_error(self.hctx.h).decode())
+        self._check(self.hctx, rc, "host call")
+
+    def step_host16(self):
+        rc = self.e2e16(self.hctx, C.c_void_p(self.h_in16.data_ptr()), C.c_void_p(self.h_out16.data_ptr()), self.HOST)
+        self._check(self.hctx, rc, "host call (pcm16 -> fp16)")
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (port of the reference's algorithm) over all host cores on a bounded sample
+# CPU arm: ONE named restatement of the reference (oracle/) over all host cores on a bounded, fixed sample
 # ------------------------------------------------------------------------------------------------------
 
 def _cpu_clip_job(args):
@@ -333,8 +409,10 @@ def _cpu_clip_job(args):
         gen = time.perf_counter() - t0
         t0 = time.perf_counter()
         for _ in range(reps):
-            if name == "whisper128":
-                R.whisper_log_mel_spectrogram(x, 128)
+            if name in ("whisper128", "whisper128_f16"):
+                m = R.whisper_log_mel_spectrogram(x, 128)
+                if name == "whisper128_f16":
+                    m.astype(np.float16)
             elif name == "whisper80_1clip":
                 R.whisper_log_mel_spectrogram(x, 80)
             elif name == "funasr":
@@ -353,70 +431,89 @@ def _cpu_clip_job(args):
 TWIN_WORKLOADS = ("whisper128", "whisper80_1clip", "istft_hift")
 
 
-def cpu_arm_twin(name: str, seconds: float = 2.0):
-    """The compiled multi-threaded twin of the oracle (oracle/cpu_twin.cpp; BASELINE.md section 4, baseline B) on a bounded
-    sample.  -> (audio-s/s, threads, sample description) or None when the twin does not cover the workload / is not built."""
+def cpu_impl_for(name: str) -> str:
+    """The ONE CPU implementation that stands in for the reference on this workload, by name (no per-run choice)."""
     from oracle import cpu_twin as T
-    from tests import synth
-    if name not in TWIN_WORKLOADS or not T.available():
-        return None
-    w = WORKLOADS[name]
-    n = int(round(w["clip_s"] * w["sr"]))
-    cores = os.cpu_count() or 1
-
-    def make(clips):
-        if name == "istft_hift":
-            mag, ph = synth.mag_phase(clips, 9, n // 4 + 1, seed=5000)
-            return lambda: T.istft_hifigan(mag, ph, n_threads=cores)
-        x = synth.pcm(clips, n, sample_rate=w["sr"], seed=5000)
-        return lambda: T.whisper_log_mel_spectrogram(x, 128 if name == "whisper128" else 80, n_threads=cores)
-
-    probe = make(cores)
-    probe()
-    t0 = time.perf_counter()
-    probe()
-    t1 = time.perf_counter() - t0
-    clips = int(min(16 * cores, max(cores, cores * round(seconds / max(t1, 1e-4)))))
-    run = make(clips) if clips != cores else probe
-    t0 = time.perf_counter()
-    run()
-    dt = time.perf_counter() - t0
-    return clips * w["clip_s"] / dt, cores, (f"{clips} clips x {w['clip_s']:.0f} s, C++ twin of the oracle (oracle/cpu_twin.cpp: same op order, generated "
-                                             f"FFT codelets) on {cores} threads (all host cores); input synthesis excluded")
+    return "cpp_twin" if name in TWIN_WORKLOADS and T.available() else "numpy"
 
 
-def cpu_arm(name: str, core_seconds: float = 2.0, reps: int = 1):
-    """-> (audio-s/s, cores, sample description).  Warm-up (filterbank caches) excluded.
-    The sample is sized so that every core is busy for about `core_seconds` (10-30 s of CPU work in total).
-    Where the compiled twin covers the workload, the faster of the two CPU restatements is the reported value and the
-    other one is quoted in the sample text."""
-    if name == "whisper128_ragged":   # the CPU restatements process one clip at a time anyway: audio-s/s of the equal-length workload
-        name = "whisper128"
-    twin = cpu_arm_twin(name, core_seconds)
-    if twin is not None:
-        nv, ncores, nsample = cpu_arm_numpy(name, core_seconds / 2, reps)
-        best = twin if twin[0] >= nv else (nv, ncores, nsample)
-        other = f"NumPy/SciPy oracle on {ncores} processes: {nv:.3g} audio-s/s" if best is twin else f"C++ twin: {twin[0]:.3g} audio-s/s"
-        return best[0], best[1], best[2] + "; " + other
-    return cpu_arm_numpy(name, core_seconds, reps)
+class CpuArm:
+    """A fixed bounded sample of the workload on all host cores; run() times one pass over it -> audio-s/s.
+    cpp_twin: oracle/cpu_twin.cpp (same op order as the NumPy oracle, OpenMP-style thread pool over clips), clips_per_core clips
+    per thread.  numpy: oracle/reference_dsp.py (pocketfft), one process per core, clips_per_core clips each."""
+
+    def __init__(self, name: str, seconds: float = 1.5):
+        if name == "whisper128_ragged":   # the CPU restatements process one clip at a time anyway: audio-s/s of the equal-length workload
+            name = "whisper128"
+        self.name = name
+        self.w = WORKLOADS[name]
+        self.n = int(round(self.w["clip_s"] * self.w["sr"]))
+        self.cores = len(os.sched_getaffinity(0)) or os.cpu_count() or 1
+        self.impl = cpu_impl_for(name)
+        self.pool = None
+        from tests import synth
+        if self.impl == "cpp_twin":
+            from oracle import cpu_twin as T
+            probe_clips = self.cores
+            run = self._make_twin(T, synth, probe_clips)
+            run()
+            t0 = time.perf_counter()
+            run()
+            t1 = time.perf_counter() - t0
+            per = int(min(16, max(1, round(seconds / max(t1, 1e-4)))))
+            self.clips = per * self.cores
+            self._run = run if per == 1 else self._make_twin(T, synth, self.clips)
+            self.sample = (f"{self.clips} clips x {self.w['clip_s']:.0f} s per step on {self.cores} threads (all host cores), compiled "
+                           "multi-threaded twin of the NumPy oracle (oracle/cpu_twin.cpp); input synthesis excluded")
+        else:
+            import multiprocessing as mp
+            self.pool = mp.get_context("fork").Pool(self.cores)
+            self.pool.map(_cpu_clip_job, [(name, min(self.n, 16000), self.w["sr"], 1, 1)] * self.cores)  # warm caches in every worker
+            t1 = max(r[0] for r in self.pool.map(_cpu_clip_job, [(name, self.n, self.w["sr"], 4999, 1)] * self.cores, chunksize=1))
+            self.per = int(min(16, max(1, round(seconds / max(t1, 1e-4)))))
+            self.clips = self.per * self.cores
+            self.sample = (f"{self.clips} clips x {self.w['clip_s']:.0f} s per step on {self.cores} processes (all host cores), NumPy/SciPy"
+                           "(pocketfft) fp32 port of the reference's algorithm (oracle/reference_dsp.py); input synthesis excluded")
+
+    def _make_twin(self, T, synth, clips):
+        if self.name == "istft_hift":
+            mag, ph = synth.mag_phase(min(clips, 4), 9, self.n // 4 + 1, seed=5000)
+            reps = (clips + mag.shape[0] - 1) // mag.shape[0]
+            mag, ph = np.tile(mag, (reps, 1, 1))[:clips], np.tile(ph, (reps, 1, 1))[:clips]
+            out = np.zeros((clips, (mag.shape[2] - 1) * 4), np.float32)       # one result buffer, touched once
+            return lambda: T.istft_hifigan(mag, ph, n_threads=self.cores, out=out)
+        x = synth.pcm(min(clips, 8), self.n, sample_rate=self.w["sr"], seed=5000)
+        x = np.tile(x, ((clips + x.shape[0] - 1) // x.shape[0], 1))[:clips]
+        nm = 80 if self.name == "whisper80_1clip" else 128
+        out = np.zeros((clips, self.n // 160, nm), np.float32)               # one result buffer, touched once
+        return lambda: T.whisper_log_mel_spectrogram(x, nm, n_threads=self.cores, out=out)
+
+    def run(self) -> float:
+        if self.impl == "cpp_twin":
+            t0 = time.perf_counter()
+            self._run()
+            dt = time.perf_counter() - t0
+        else:
+            jobs = [(self.name, self.n, self.w["sr"], 5000 + i, 1) for i in range(self.clips)]
+            res = self.pool.map(_cpu_clip_job, jobs, chunksize=self.per)
+            dt = sum(r[0] for r in res) / self.cores      # all workers run concurrently; input synthesis (second field) excluded
+        return self.clips * self.w["clip_s"] / dt
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
 
 
-def cpu_arm_numpy(name: str, core_seconds: float = 2.0, reps: int = 1):
-    import multiprocessing as mp
-    w = WORKLOADS[name]
-    n = int(round(w["clip_s"] * w["sr"]))
-    cores = os.cpu_count() or 1
-    with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_clip_job, [(name, min(n, 16000), w["sr"], 1, 1)] * cores)  # warm caches in every worker
-        t1 = max(r[0] for r in pool.map(_cpu_clip_job, [(name, n, w["sr"], 4999, 1)] * cores, chunksize=1))
-        clips_per_core = int(min(64, max(1, round(core_seconds / max(t1, 1e-4)))))
-        jobs = [(name, n, w["sr"], 5000 + i, reps) for i in range(cores * clips_per_core)]
-        res = pool.map(_cpu_clip_job, jobs, chunksize=clips_per_core)
-    # all workers run concurrently; input synthesis (second field) is excluded from the timed work
-    busy = sum(r[0] for r in res) / cores
-    audio = len(jobs) * reps * w["clip_s"]
-    return audio / busy, cores, (f"{len(jobs) * reps} clips x {w['clip_s']:.0f} s on {cores} processes (all host cores), "
-                                 "NumPy/SciPy(pocketfft) fp32 port of the reference's algorithm; input synthesis excluded")
+def cpu_baseline(name: str, runs: int = 3, seconds: float = 1.5) -> dict:
+    arm = CpuArm(name, seconds)
+    try:
+        vals = [arm.run() for _ in range(runs)]
+    finally:
+        arm.close()
+    return {"value": float(np.median(vals)), "unit": UNIT, "cores": arm.cores, "kind": "port", "impl": arm.impl, "sample": arm.sample,
+            "runs": runs, "spread": [float(min(vals)), float(max(vals))]}
 
 
 def run_reference(args):
@@ -424,20 +521,198 @@ def run_reference(args):
     if rank != 0:
         return
     name = args.workload
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_arm(name, core_seconds=1.0)
-        if i >= args.warmup:
-            vals.append(v)
-    value = float(np.mean(vals))
     w = WORKLOADS[name]
+    total = max(1, args.steps + args.warmup)
+    arm = CpuArm(name, seconds=float(min(2.0, max(0.3, 45.0 / total))))   # the whole run stays under about a minute
+    try:
+        for _ in range(args.warmup):
+            arm.run()
+        vals = [arm.run() for _ in range(args.steps)]
+    finally:
+        arm.close()
+    value = float(np.median(vals))
+    batch_audio_s = w["batch"] * w["clip_s"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * (cores * w["clip_s"]) / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "note": "CPU restatement of the reference (oracle/): the reference's Swift+MLX path cannot be built on Linux"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "ms_per_step": 1e3 * batch_audio_s / value,     # time the host cores would need for one full batch of the workload
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "clips_per_gpu": w["batch"], "samples_per_clip": int(round(w["clip_s"] * w["sr"])),
+                       "note": "CPU restatement of the reference (oracle/): the reference's Swift+MLX path cannot be built on Linux; "
+                               "value = median over the timed steps of one fixed bounded sample, ms_per_step = full batch audio-s / value"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "impl": arm.impl, "sample": arm.sample,
+                             "runs": args.steps, "spread": [float(min(vals)), float(max(vals))]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "parity": PARITY_NOTE}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# one workload on the GPU: device-resident timing, roofline, e2e, clocks, cpu baseline
+# ------------------------------------------------------------------------------------------------------
+
+def measure(name, args, env, steps, warmup, e2e_steps, want_cpu, batch=None, detail=False):
+    torch, world, rank, local = env["torch"], env["world"], env["rank"], env["local"]
+    barrier, max_over_ranks = env["barrier"], env["max_over_ranks"]
+    wl = GpuWorkload(name, batch)
+    W = WORKLOADS[name]
+    peak_gbs, peak_src = _peaks()
+
+    for _ in range(warmup):
+        wl.step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = wl.ctx.launch_count
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wl.step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = wl.ctx.launch_count - launches0
+    if ms < 400.0:  # keep the sampler alive long enough to catch the clocks under this load
+        t_end = time.time() + 0.5
+        while time.time() < t_end:
+            wl.step_device()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(ms / steps)
+    value = wl.audio_s * world / (ms_step * 1e-3)
+
+    achieved = wl.algo_bytes / (ms / steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.algo_bytes,
+                "kernel": "whole C-ABI call on the device (main fused kernel + its small fix-up / statistics kernels)"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(name)
+        except Exception:
+            pass
+
+    e2e = None
+    if e2e_steps > 0:
+        wl.prepare_host()
+
+        def timed(fn, k):
+            fn()  # warm the staging buffers
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                fn()
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) / k)
+
+        dt32 = timed(wl.step_host, e2e_steps)
+        f32 = {"value": wl.audio_s * world / dt32, "unit": UNIT, "h2d_bytes_per_step": wl.in_bytes, "d2h_bytes_per_step": wl.out_bytes,
+               "ms_per_step": dt32 * 1e3, "steps": e2e_steps, "entry": "fp32 PCM in, fp32 features out"}
+        e2e = f32
+        if wl.e2e16 is not None:
+            dt16 = timed(wl.step_host16, e2e_steps)
+            h2d16, d2h16 = wl.h_in16.numel() * 2, wl.h_out16.numel() * 2
+            e2e = {"value": wl.audio_s * world / dt16, "unit": UNIT, "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h16,
+                   "ms_per_step": dt16 * 1e3, "steps": e2e_steps,
+                   "entry": "b2a_whisper_log_mel_spectrogram_pcm16: 16-bit PCM in (x / 32768, as AVAudioFile decodes it), fp16 features out "
+                            "(asType(.float16), the form the Whisper encoder consumes) -- bit-identical to casting the fp32 entry's result",
+                   "fp32_in_fp32_out": f32}
+        if detail:
+            # the copy directions alone (pinned <-> device, no kernels), for the attribution of the e2e ceiling
+            def copy_rate(dst, src):
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dst.copy_(src, non_blocking=True)
+                barrier()
+                ev0.record()
+                for _ in range(3):
+                    dst.copy_(src, non_blocking=True)
+                ev1.record()
+                barrier()
+                return src.numel() * src.element_size() * 3 / (max_over_ranks(ev0.elapsed_time(ev1)) * 1e-3) / 1e9
+            e2e["h2d_only_GBps_per_gpu"] = copy_rate(wl.inputs[0], wl.h_in[0])
+            e2e["d2h_only_GBps_per_gpu"] = copy_rate(wl.h_out, wl.out)
+            e2e["duplex_GBps_per_gpu_in_call"] = (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) / (e2e["ms_per_step"] * 1e-3) / 1e9
+
+    cpu = cpu_baseline(name) if want_cpu else None
+    rec = {"ms_per_step": ms_step, "value": value, "unit": UNIT, "roofline": roofline, "e2e": e2e, "clocks": clocks,
+           "gpu_launches": launches, "cpu_baseline": cpu, "steps": steps, "warmup": warmup,
+           "config": {"workload": W["desc"], "clips_per_gpu": wl.batch, "samples_per_clip": wl.n, "seed": wl.seed,
+                      "l2_policy": ("inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (wl.algo_bytes / 1e9))
+                      if wl.algo_bytes > 4 * 126e6 else "working set fits L2: numbers are L2-warm"}}
+    wl.close()
+    return rec
+
+
+def measure_gather(args, env, clips_per_rank=64, steps=5):
+    """N > 1: the Whisper 128-mel step WITH the features delivered to rank 0, on a reduced batch: fused into the kernels' stores
+    over peer-mapped memory (shard.FusedGather) and kernel + NCCL gather; each result compared bit for bit with rank 0's own
+    single-GPU run of every rank's clips (the inputs are seeded per rank, so rank 0 can regenerate them)."""
+    torch, world, rank = env["torch"], env["world"], env["rank"]
+    barrier, max_over_ranks = env["barrier"], env["max_over_ranks"]
+    from mlx_swift_audio_b200.shard import FusedGather, gather_features
+    out = {}
+    wl = GpuWorkload("whisper128", clips_per_rank)
+    per_clip = tuple(wl.out.shape[1:])
+    # rank 0: the single-GPU result of every rank's clips
+    want = None
+    if rank == 0:
+        want = []
+        for r in range(world):
+            w_r = wl if r == 0 else GpuWorkload("whisper128", clips_per_rank, rank=r)
+            w_r.step_device()
+            torch.cuda.synchronize()
+            want.append(w_r.out.clone())
+            if r != 0:
+                w_r.close()
+        want = torch.cat(want, 0)
+    for mode in ("fused", "nccl"):
+        fg = None
+        if mode == "fused":
+            fg = FusedGather(wl.ctx, wl.batch * world, per_clip, dst=0)
+            peer_out = C.c_void_p(fg.local_out().data_ptr())
+
+            def gstep():
+                wl.step_device(peer_out)
+                return None
+        else:
+            def gstep():
+                wl.step_device()
+                return gather_features(wl.out, wl.batch * world, dst=0)
+        got = None
+        for _ in range(2):
+            got = gstep()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            got = gstep()
+        g1.record()
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1) / steps)
+        if mode == "fused":
+            got = fg.finish()
+        verified = None
+        if rank == 0:
+            verified = bool(got is not None and tuple(got.shape) == tuple(want.shape) and torch.equal(got, want))
+        remote = wl.out_bytes * (world - 1)
+        out[mode] = {"ms": gms, "ingress_GBps": remote / (gms * 1e-3) / 1e9, "bytes_to_consumer_per_step": remote,
+                     "value": wl.audio_s * world / (gms * 1e-3), "unit": UNIT, "verified": verified, "clips_per_rank": clips_per_rank}
+        if fg is not None:
+            fg.close()
+    # the same reduced batch with the features left where they are produced
+    for _ in range(3):
+        wl.step_device()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        wl.step_device()
+    g1.record()
+    barrier()
+    out["no_gather_ms"] = max_over_ranks(g0.elapsed_time(g1) / steps)
+    out["note"] = ("all ranks' features land in rank 0's HBM; bounded by rank 0's NVLink ingress, not by the kernels; verified = bit-identical "
+                   "to rank 0's own single-GPU run of every rank's clips")
+    wl.close()
+    return out
 
 
 def main():
@@ -449,11 +724,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="override clips per GPU (debug)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="none", choices=["none", "fused", "nccl"],
-                    help="N > 1 only: also time the step WITH the features delivered to rank 0 -- 'fused' = the kernels store "
-                         "straight into rank 0's HBM through peer-mapped memory (shard.FusedGather), 'nccl' = kernel then dist.gather")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the `workloads` map of the other BASELINE configs")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the gather legs")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -461,13 +736,15 @@ def main():
         run_reference(args)
         return
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = {"bound": False, "note": "disabled"} if args.no_numa else numa_bind(local)   # before torch / CUDA allocate pinned memory
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -485,110 +762,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    wl = GpuWorkload(args.workload, args.batch)
-    W = WORKLOADS[args.workload]
-    peak_gbs, peak_src = _peaks()
+    env = dict(torch=torch, world=world, rank=rank, local=local, barrier=barrier, max_over_ranks=max_over_ranks)
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu
+    main_rec = measure(args.workload, args, env, args.steps, args.warmup, 0 if args.no_e2e else args.e2e_steps, want_cpu, args.batch, detail=True)
 
-    # ---- device-resident timing --------------------------------------------------------------------
-    for _ in range(args.warmup):
-        wl.step_device()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = wl.ctx.launch_count
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        wl.step_device()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = wl.ctx.launch_count - launches0
-    if ms < 400.0:  # keep the sampler alive long enough to catch the clocks under this load
-        t_end = time.time() + 0.5
-        while time.time() < t_end:
-            wl.step_device()
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms_step = max_over_ranks(ms / args.steps)
-    value = wl.audio_s * world / (ms_step * 1e-3)
+    workloads = None
+    if args.workload == "whisper128" and args.batch is None and not args.no_secondary:
+        workloads = {}
+        for name in SECONDARY:
+            rec = measure(name, args, env, min(args.steps, 10), 3, 0 if args.no_e2e else 2, want_cpu)
+            rec.pop("config")
+            rec["workload"] = WORKLOADS[name]["desc"]
+            workloads[name] = rec
 
-    achieved = wl.algo_bytes / (ms / args.steps * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": wl.algo_bytes,
-                "kernel": "whole C-ABI call on the device (main fused kernel + its small fix-up / statistics kernels)"}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get(args.workload)
-        except Exception:
-            pass
-
-    # ---- optional: the same step with the features delivered to a consumer rank ("with and without the gather") ----
     gather = None
-    if world > 1 and args.gather != "none":
-        from mlx_swift_audio_b200.shard import FusedGather, gather_features
-        per_clip = tuple(wl.out.shape[1:])
-        if args.gather == "fused":
-            if wl.out.dtype != torch.float32:
-                raise SystemExit("--gather fused: float32 outputs only")
-            fg = FusedGather(wl.ctx, wl.batch * world, per_clip, dst=0)
-            peer_out = C.c_void_p(fg.local_out().data_ptr())
+    if world > 1 and not args.no_gather:
+        gather = measure_gather(args, env)
 
-            def gstep():
-                rc = wl.call(wl.ctx, [C.c_void_p(t.data_ptr()) for t in wl.inputs], peer_out, wl.DEV)
-                if rc != 0:
-                    raise RuntimeError("b200audio call failed: " + wl.lib.b2a_last_error(wl.ctx.h).decode())
-        else:
-            def gstep():
-                wl.step_device()
-                gather_features(wl.out, wl.batch * world, dst=0)
-        for _ in range(2):
-            gstep()
-        barrier()
-        g0 = torch.cuda.Event(enable_timing=True)
-        g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            gstep()
-        g1.record()
-        barrier()
-        gms = max_over_ranks(g0.elapsed_time(g1) / args.steps)
-        gather = {"mode": args.gather, "value": wl.audio_s * world / (gms * 1e-3), "unit": UNIT, "ms_per_step": gms,
-                  "bytes_to_consumer_per_step": wl.out_bytes * (world - 1),
-                  "consumer_ingress_GBps": wl.out_bytes * (world - 1) / (gms * 1e-3) / 1e9,
-                  "note": "all ranks' features land in rank 0's HBM; bounded by rank 0's NVLink ingress, not by the kernels"}
-        if args.gather == "fused":
-            fg.close()
-
-    # ---- end-to-end through the C ABI with pinned host buffers ---------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        wl.prepare_host()
-        wl.step_host()  # warm the staging buffers
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            wl.step_host()
-        barrier()
-        dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
-        e2e = {"value": wl.audio_s * world / dt, "unit": UNIT, "h2d_bytes_per_step": wl.in_bytes, "d2h_bytes_per_step": wl.out_bytes,
-               "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_arm(args.workload)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if world > 1:
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
+    else:
+        numa_all = [numa]
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": W["desc"], "clips_per_gpu": wl.batch, "samples_per_clip": wl.n,
-                           "l2_policy": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (wl.algo_bytes / 1e9)
-                           if wl.algo_bytes > 4 * 126e6 else "working set fits L2: numbers are L2-warm",
-                           "parallelism": f"dp{world} (clips sharded by rank, no collective)"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        cfg = main_rec["config"]
+        cfg["parallelism"] = f"dp{world} (clips sharded by rank, no collective on the data path)"
+        cfg["synthetic_inputs"] = (f"SURVEY 8d streams (NumPy default_rng([seed + 100 * rank, b])), {UNIQUE_CLIPS} distinct clips per rank tiled to the batch")
+        cfg["numa"] = numa_all
+        line = {"metric": METRIC, "value": main_rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfg, "roofline": main_rec["roofline"], "cpu_baseline": main_rec["cpu_baseline"],
+                "e2e": main_rec["e2e"], "gpu_launches": main_rec["gpu_launches"], "clocks": main_rec["clocks"], "parity": PARITY_NOTE}
+        if workloads is not None:
+            line["workloads"] = workloads
         if gather is not None:
             line["gather"] = gather
         print(json.dumps(line), flush=True)
