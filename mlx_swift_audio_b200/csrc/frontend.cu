@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -1669,6 +1670,21 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   return B2A_OK;
 }
 
+int launch_whisper_clamp(float* out, const int* clip_max, const int* tile_min, int64_t batch, int64_t n_frames, int n_mels, void* stream,
+                         int* launches, std::string* err) {
+  const int tiles = frontend_tiles_per_clip(400, n_frames);
+  const long long stride = n_frames * (long long)n_mels;
+  for (long long c0 = 0; c0 < batch; c0 += 65535) {   // gridDim.y limit
+    const long long nb = std::min<long long>(65535, batch - c0);
+    whisper_clamp_kernel<<<dim3(unsigned((tiles + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
+  *launches += 1;
+  return B2A_OK;
+}
+
 // Id of the baked bank (mel_baked.h) whose step program equals this one word for word, or 0.
 int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, const int* chunk_s, int n_chunks, int frame_tile, int n_mels) {
   for (int i = 0; i < kMelBakedCount; ++i) {
@@ -1695,6 +1711,9 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
   }
   const int id = a.bank.baked_id, om = a.out_mode;
+  // B2A_WHISPER_TC=1: the tensor-core front end (tc_frontend.cu) instead of the FFT kernel, where it applies (A/B switch)
+  static const bool use_tc = [] { const char* v = getenv("B2A_WHISPER_TC"); return v != nullptr && v[0] == '1'; }();
+  if (use_tc && tc_whisper_applicable(a)) return launch_tc_whisper(a, stream, launches, err);
   if (a.out_f16) {
     // fp16 features straight from the store loop: the Whisper front end's two standard banks, (T', M) layout
     if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE && post == POST_WNORM && om == OUT_TM) {

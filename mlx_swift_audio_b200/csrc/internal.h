@@ -113,6 +113,16 @@ int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, co
 bool frontend_plan_exists(int n_fft, int hop, int win_len);
 int init_frontend_tables(std::string* err);  // once per device: twiddle tables into __constant__ memory
 
+// max - 8 clamp of the Whisper-style front ends over (batch, n_frames, n_mels) fp32 features in (T', M) layout, from the per-clip maxima and
+// the (negated) per-32-frame-tile minima the main kernel left behind (frontend.cu: whisper_clamp_kernel)
+int launch_whisper_clamp(float* out, const int* clip_max, const int* tile_min, int64_t batch, int64_t n_frames, int n_mels, void* stream,
+                         int* launches, std::string* err);
+
+// Tensor-core (tcgen05 + TMEM + TMA) Whisper front end (tc_frontend.cu): same inputs, outputs and clamp bookkeeping as the FFT kernel
+bool tc_whisper_applicable(const FrontendArgs& a);
+void tc_debug_set_power_buffer(float* device_ptr);
+int launch_tc_whisper(const FrontendArgs& a, void* stream, int* launches, std::string* err, float* dbg_power = nullptr);
+
 // per-clip column statistics kernels (frontend.cu)
 int launch_cmvn(const float* in, float* out, int64_t batch, int64_t rows, int dim, const float* mean, const float* istd,
                 void* stream, int* launches, std::string* err, const void* clip_tab = nullptr);
