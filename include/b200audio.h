@@ -350,6 +350,9 @@ B2A_API int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins
 /* When enabled, every compute entry point brackets its kernels with CUDA events on the
  * context's stream; b2a_ctx_last_kernel_ms returns the elapsed time of the last call
  * (synchronises the two events).  Off by default. */
+/* Switches the experimental tensor-core Whisper front end (tcgen05 split-precision DFT, csrc/tc_frontend.cu) on / off for the
+ * process; the environment variable B2A_WHISPER_TC=1 sets the initial state.  Off by default: DESIGN.md section 6. */
+B2A_API int b2a_debug_whisper_tc(int on);
 /* Bring-up hook of the tensor-core Whisper front end (B2A_WHISPER_TC=1): when a device buffer of (batch, T', 201) floats is set, the
  * kernel also leaves the power spectrum |X[k]|^2 of every frame there.  NULL switches it off. */
 B2A_API int b2a_debug_tc_power_buffer(void* device_ptr);

@@ -108,6 +108,7 @@ SIGNATURES = {
     "b2a_debug_plan_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2a_debug_mel_program_dump": (C.c_int, [_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), C.c_int,
                                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b2a_debug_whisper_tc": (C.c_int, [C.c_int]),
     "b2a_debug_tc_power_buffer": (C.c_int, [C.c_void_p]),
     "b2a_ctx_enable_timing": (C.c_int, [_ctx, C.c_int]),
     "b2a_ctx_last_kernel_ms": (C.c_int, [_ctx, _f]),

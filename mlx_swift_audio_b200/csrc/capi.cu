@@ -605,6 +605,11 @@ int b2a_memcpy_d2h(b2a_ctx* c, void* host_dst, const void* device_src, uint64_t 
   return rc != B2A_OK ? rc : cu(c, cudaStreamSynchronize(c->stream), "sync");
 }
 
+int b2a_debug_whisper_tc(int on) {
+  tc_whisper_enable(on);
+  return B2A_OK;
+}
+
 int b2a_debug_tc_power_buffer(void* device_ptr) {
   tc_debug_set_power_buffer(static_cast<float*>(device_ptr));
   return B2A_OK;

@@ -1712,8 +1712,7 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   }
   const int id = a.bank.baked_id, om = a.out_mode;
   // B2A_WHISPER_TC=1: the tensor-core front end (tc_frontend.cu) instead of the FFT kernel, where it applies (A/B switch)
-  static const bool use_tc = [] { const char* v = getenv("B2A_WHISPER_TC"); return v != nullptr && v[0] == '1'; }();
-  if (use_tc && tc_whisper_applicable(a)) return launch_tc_whisper(a, stream, launches, err);
+  if (tc_whisper_enabled() && tc_whisper_applicable(a)) return launch_tc_whisper(a, stream, launches, err);
   if (a.out_f16) {
     // fp16 features straight from the store loop: the Whisper front end's two standard banks, (T', M) layout
     if (a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE && post == POST_WNORM && om == OUT_TM) {

@@ -119,6 +119,8 @@ int launch_whisper_clamp(float* out, const int* clip_max, const int* tile_min, i
                          int* launches, std::string* err);
 
 // Tensor-core (tcgen05 + TMEM + TMA) Whisper front end (tc_frontend.cu): same inputs, outputs and clamp bookkeeping as the FFT kernel
+bool tc_whisper_enabled();
+void tc_whisper_enable(int on);
 bool tc_whisper_applicable(const FrontendArgs& a);
 void tc_debug_set_power_buffer(float* device_ptr);
 int launch_tc_whisper(const FrontendArgs& a, void* stream, int* launches, std::string* err, float* dbg_power = nullptr);

@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_whisper_kernel(const __grid_co
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long s_bar[5];   // 0,1: A/B slot free; 2,3: B slice landed; 4: accumulators complete
   __shared__ uint32_t s_tmem;
-  __shared__ TcTable s_tab;
+  __shared__ __align__(16) TcTable s_tab;
   float* s_pcm = reinterpret_cast<float*>(smem + kOffPcm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t = tid & (kM - 1);        // frame of the tile == TMEM lane
@@ -476,6 +477,18 @@ void build_table(const float* window, TcTable& tb) {
 // debug hook (tests / bring-up only): when set, the kernel also writes |X|^2 (frames x 201) of every clip there
 static float* g_dbg_power = nullptr;
 void tc_debug_set_power_buffer(float* device_ptr) { g_dbg_power = device_ptr; }
+
+// The tensor-core path is opt-in (B2A_WHISPER_TC=1 in the environment, or b2a_debug_whisper_tc(1)): see DESIGN.md section 6 for the
+// measured go / no-go.
+static int g_tc_enabled = -1;
+bool tc_whisper_enabled() {
+  if (g_tc_enabled < 0) {
+    const char* v = getenv("B2A_WHISPER_TC");
+    g_tc_enabled = (v != nullptr && v[0] == '1') ? 1 : 0;
+  }
+  return g_tc_enabled == 1;
+}
+void tc_whisper_enable(int on) { g_tc_enabled = on ? 1 : 0; }
 
 bool tc_whisper_applicable(const FrontendArgs& a) {
   return a.n_fft == 400 && a.hop == 160 && a.win_len == 400 && a.pre_mode == PRE_NONE && a.spec_mode == SPEC_POWER && a.whisper_norm &&
