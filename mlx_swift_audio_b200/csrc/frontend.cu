@@ -52,6 +52,7 @@
 #define B2A_MT_WALK 1
 #endif
 
+
 namespace b2a {
 
 // ------------------------------------------------------------------------------------------------
@@ -122,19 +123,21 @@ enum SpecKind { SK_POWER = 0, SK_MAG = 1, SK_CPLX = 2 };
 template <class P> constexpr int steps_smem_max() { return P::MINB == 1 ? 2048 : (P::MINB == 2 ? 1024 : 0); }
 // Post-processing of a finished mel value.  POST_RUNTIME: log mode / Whisper normalisation are kernel parameters and the
 // filterbank is the interpreted step program (any bank); the other kinds belong to the baked banks of mel_baked.h.
-enum PostKind { POST_RUNTIME = 0, POST_WNORM = 1, POST_LN = 2 };
+enum PostKind { POST_RUNTIME = 0, POST_WNORM = 1, POST_LN = 2, POST_NONE = 3 /* the mel value itself (voice-encoder "amp" mel) */ };
 
 template <int MEL> struct MelTraits { static constexpr int M = 0; };
 template <> struct MelTraits<1> { static constexpr int M = 128; };
 template <> struct MelTraits<2> { static constexpr int M = 80; };
 template <> struct MelTraits<3> { static constexpr int M = 80; };
 template <> struct MelTraits<4> { static constexpr int M = 80; };
+template <> struct MelTraits<5> { static constexpr int M = 40; };
 template <int MEL, class Emit>
 __device__ __forceinline__ void mel_baked(int chunk, const float* __restrict__ p, Emit&& emit) {
   if constexpr (MEL == 1) mel_baked_1(chunk, p, emit);
   else if constexpr (MEL == 2) mel_baked_2(chunk, p, emit);
   else if constexpr (MEL == 3) mel_baked_3(chunk, p, emit);
   else if constexpr (MEL == 4) mel_baked_4(chunk, p, emit);
+  else if constexpr (MEL == 5) mel_baked_5(chunk, p, emit);
 }
 
 template <class P>
@@ -1709,6 +1712,7 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
   if (a.bank.baked_id > 0 && spec == SK_POWER && !a.post_affine && a.out_mode != OUT_COMPLEX) {
     if (a.whisper_norm && a.log_mode == LOG_LOG10 && a.out_mode != OUT_LFR) post = POST_WNORM;
     else if (!a.whisper_norm && a.log_mode == LOG_LN) post = POST_LN;
+    else if (!a.whisper_norm && a.log_mode == LOG_NONE) post = POST_NONE;
   }
   const int id = a.bank.baked_id, om = a.out_mode;
   // B2A_WHISPER_TC=1: the tensor-core front end (tc_frontend.cu) instead of the FFT kernel, where it applies (A/B switch)
@@ -1741,6 +1745,8 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
     if (post == POST_WNORM && id == 2 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 2, POST_WNORM, OUT_TM>(a, st, launches, err);
     if (post == POST_LN && id == 3 && om == OUT_LFR) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, OUT_LFR>(a, st, launches, err);
     if (post == POST_LN && id == 3 && om == OUT_TM) return launch_plan<Plan400, PRE_NONE, SK_POWER, 3, POST_LN, OUT_TM>(a, st, launches, err);
+    // Chatterbox voice encoder (VoiceEncoderMelspec.swift:17-68, defaults): 40-mel power mel, no log, (M, T')
+    if (post == POST_NONE && id == 5 && om == OUT_MT) return launch_plan<Plan400, PRE_NONE, SK_POWER, 5, POST_NONE, OUT_MT>(a, st, launches, err);
     if (spec == SK_POWER) return launch_plan<Plan400, PRE_NONE, SK_POWER>(a, st, launches, err);
     if (spec == SK_MAG) return launch_plan<Plan400, PRE_NONE, SK_MAG>(a, st, launches, err);
     return launch_plan<Plan400, PRE_NONE, SK_CPLX>(a, st, launches, err);
