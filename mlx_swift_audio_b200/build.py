@@ -19,7 +19,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libb200audio.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 
-SOURCES = ["host_tables.cpp", "frontend.cu", "vocoder.cu", "tc_frontend.cu", "capi.cu"]
+SOURCES = ["host_tables.cpp", "frontend.cu", "vocoder.cu", "tc_frontend.cu", "generic_stft.cu", "capi.cu"]
 HEADERS = ["codelets.h", "mel_baked.h", "internal.h", os.path.join("..", "..", "include", "b200audio.h")]
 
 NVCC_FLAGS = [

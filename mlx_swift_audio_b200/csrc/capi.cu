@@ -56,6 +56,9 @@ struct b2a_ctx {
   DevBuf scratch[kSlots][5];                     // 0: clip_max / flags, 1: tile_min, 2: temp features / unwrapped phase, 3 / 4: ragged clip / tile tables
   int64_t chunk_clip0 = 0;                       // first clip of the chunk run_batched is handing to the body
   int* h_flag = nullptr;                         // pinned
+  int* h_tab[kSlots] = {};                       // pinned staging of the ragged clip tables (one per ring slot) ...
+  size_t h_tab_ints[kSlots] = {};
+  cudaEvent_t ev_tab[kSlots] = {};               // ... and the event behind each slot's last upload
 };
 
 namespace {
@@ -98,9 +101,8 @@ const std::vector<float>& cached_window(b2a_ctx* c, const std::string& key, cons
 
 int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int n_bins, bool bin_major,
                 const std::function<int(float*)>& make_dense, DeviceBank* out) {
-  const PlanShape* ps = plan_shape(n_fft);
-  if (!ps) return fail(c, B2A_E_UNSUPPORTED, "no FFT plan for this n_fft");
-  const int frame_tile = ps->frame_tile, n_chunks = ps->n_chunks;
+  const PlanShape* ps = plan_shape(n_fft);   // null: no tuned plan -- the bank is only used by the generic kernels (desc + weights)
+  const int frame_tile = ps ? ps->frame_tile : 0, n_chunks = ps ? ps->n_chunks : 0;
   const std::string key = key0 + "_ft" + std::to_string(frame_tile) + "_c" + std::to_string(n_chunks);
   auto it = c->banks.find(key);
   if (it == c->banks.end()) {
@@ -108,14 +110,15 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
     int rc = make_dense(dense.data());
     if (rc != B2A_OK) return fail(c, rc, "bad filterbank parameters");
     // validation and the (host-only) mel program first: nothing is allocated on the device for a bank that cannot run
-    std::vector<int> slots;
-    spectrum_slots(*ps, slots);
-    if (n_bins > int(slots.size())) return fail(c, B2A_E_BAD_ARG, "filterbank has more bins than the spectrum");
-    std::vector<int> words;
-    if (!output_words(*ps, n_mels, words)) return fail(c, B2A_E_BAD_ARG, "n_mels out of range for this FFT plan");
+    std::vector<int> slots, words;
+    if (ps) {
+      spectrum_slots(*ps, slots);
+      if (n_bins > int(slots.size())) return fail(c, B2A_E_BAD_ARG, "filterbank has more bins than the spectrum");
+      if (!output_words(*ps, n_mels, words)) return fail(c, B2A_E_BAD_ARG, "n_mels out of range for this FFT plan");
+    }
     BankStorage bs;
     build_sparse_bank(dense.data(), n_mels, n_bins, bin_major, bs.host);
-    build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, words.data(), n_chunks, slots.data(), bs.host);
+    if (ps) build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, words.data(), n_chunks, slots.data(), bs.host);
     const size_t nw = std::max<size_t>(bs.host.weights.size(), 1);
     std::vector<int> desc(size_t(n_mels) * 4, 0);
     for (int m = 0; m < n_mels; ++m) {
@@ -157,8 +160,8 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
   out->n_steps = int(bs.host.steps.size() / 4);
   out->n_chunks = n_chunks;
   out->frame_tile = frame_tile;
-  out->host_chunk_m = bs.host.chunk_m.data();
-  out->host_chunk_s = bs.host.chunk_s.data();
+  out->host_chunk_m = bs.host.chunk_m.empty() ? nullptr : bs.host.chunk_m.data();
+  out->host_chunk_s = bs.host.chunk_s.empty() ? nullptr : bs.host.chunk_s.data();
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
   out->baked_id = bs.baked_id;
@@ -348,7 +351,7 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
     a.spec_mode = p.spec_mode; a.bank = p.bank; a.log_mode = p.log_mode; a.log_floor = p.log_floor;
     a.whisper_norm = p.whisper_norm; a.post_affine = p.post_affine; a.post_sub = p.post_sub; a.post_div = p.post_div;
     a.out_mode = p.out_mode; a.n_frames = p.n_frames; a.out = d_out; a.lfr_m = p.lfr_m; a.lfr_n = p.lfr_n; a.lfr_rows = p.lfr_rows;
-    std::vector<int> clip_tab;   // (the pageable-memory upload below is staged before cudaMemcpyAsync returns)
+    int64_t max_tail = 0;        // ragged: rows the shortest clip of this chunk falls short of the batch stride
     int launches = 0;
     std::string err;
     if (p.in_i16) {   // 16-bit PCM -> fp32 scratch (x / 32768, exact), then the fp32 front end
@@ -364,22 +367,42 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
       const PlanShape* ps = plan_shape(p.n_fft);
       const int ft = ps ? ps->frame_tile : 32;
       const int64_t c0 = c->chunk_clip0;
-      clip_tab.resize(size_t(n) * 4);
-      int64_t total = 0;
+      // the table is written into pinned staging (a pageable source would make the "async" upload a synchronous staged copy);
+      // the slot's previous upload has long finished, the event only makes that a guarantee
+      const size_t n_ints = size_t(n) * 4;
+      cudaError_t e;
+      if (c->h_tab_ints[slot] < n_ints) {
+        if (c->h_tab[slot]) {
+          if ((e = cudaEventSynchronize(c->ev_tab[slot])) != cudaSuccess) return cu(c, e, "event sync");
+          cudaFreeHost(c->h_tab[slot]);
+          c->h_tab[slot] = nullptr;
+          c->h_tab_ints[slot] = 0;
+        }
+        if ((e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_tab[slot]), sizeof(int) * n_ints, cudaHostAllocDefault)) != cudaSuccess)
+          return fail(c, B2A_E_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        c->h_tab_ints[slot] = n_ints;
+      } else if ((e = cudaEventSynchronize(c->ev_tab[slot])) != cudaSuccess) {
+        return cu(c, e, "event sync");
+      }
+      int* clip_tab = c->h_tab[slot];
+      int64_t total = 0, min_rows = 0x7fffffffffffffffLL;
       for (int64_t b = 0; b < n; ++b) {
         const int64_t fr = clip_frames[size_t(c0 + b)];
+        const int64_t lfr = p.out_mode == OUT_LFR ? b2a_lfr_num_rows(fr, p.lfr_n) : 0;
         clip_tab[4 * b + 0] = int(rg->lengths[c0 + b]);
         clip_tab[4 * b + 1] = int(fr);
-        clip_tab[4 * b + 2] = int(p.out_mode == OUT_LFR ? b2a_lfr_num_rows(fr, p.lfr_n) : 0);
+        clip_tab[4 * b + 2] = int(lfr);
         clip_tab[4 * b + 3] = int(total);
         total += (fr + ft - 1) / ft;
+        min_rows = std::min(min_rows, p.out_mode == OUT_LFR ? lfr : fr);
       }
+      max_tail = (p.out_mode == OUT_LFR ? p.lfr_rows : p.n_frames) - min_rows;
       if (total > 0x7fffffffLL) return fail(c, B2A_E_BAD_ARG, "too many tiles in one launch");
       int rc;
-      if ((rc = ensure(c, c->scratch[slot][3], sizeof(int) * clip_tab.size())) != B2A_OK) return rc;
-      cudaError_t e;
-      if ((e = cudaMemcpyAsync(c->scratch[slot][3].p, clip_tab.data(), sizeof(int) * clip_tab.size(), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+      if ((rc = ensure(c, c->scratch[slot][3], sizeof(int) * n_ints)) != B2A_OK) return rc;
+      if ((e = cudaMemcpyAsync(c->scratch[slot][3].p, clip_tab, sizeof(int) * n_ints, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
         return cu(c, e, "table upload");
+      if ((e = cudaEventRecord(c->ev_tab[slot], c->stream)) != cudaSuccess) return cu(c, e, "event record");
       if ((rc = ensure(c, c->scratch[slot][4], sizeof(int) * 2 * size_t(total))) != B2A_OK) return rc;
       a.clip_tab = c->scratch[slot][3].p;
       a.tile_tab = c->scratch[slot][4].p;
@@ -389,9 +412,9 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
         return rc;
       }
       // rows past a clip's own count are zero (only those: the kernels write the rest)
-      if (p.out_mode == OUT_MT) rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.bank.n_mels, p.n_frames, 1, c->stream, &launches, &err);
-      else if (p.out_mode == OUT_LFR) rc = launch_zero_tails(d_out, a.clip_tab, 2, n, p.lfr_rows, int64_t(p.lfr_m) * p.bank.n_mels, 0, c->stream, &launches, &err);
-      else rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.n_frames, p.out_f16 ? p.bank.n_mels / 2 : p.bank.n_mels, 0, c->stream, &launches, &err);   // (fp16 rows: n_mels / 2 words of zero bits)
+      if (p.out_mode == OUT_MT) rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.bank.n_mels, p.n_frames, 1, max_tail, c->stream, &launches, &err);
+      else if (p.out_mode == OUT_LFR) rc = launch_zero_tails(d_out, a.clip_tab, 2, n, p.lfr_rows, int64_t(p.lfr_m) * p.bank.n_mels, 0, max_tail, c->stream, &launches, &err);
+      else rc = launch_zero_tails(d_out, a.clip_tab, 1, n, p.n_frames, p.out_f16 ? p.bank.n_mels / 2 : p.bank.n_mels, 0, max_tail, c->stream, &launches, &err);   // (fp16 rows: n_mels / 2 words of zero bits)
       if (rc != B2A_OK) {
         c->err = err;
         return rc;
@@ -405,7 +428,30 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
       a.clip_max = static_cast<int*>(c->scratch[slot][0].p);
       a.tile_min = reinterpret_cast<float*>(a.clip_max + n);
     }
-    int rc = launch_frontend(a, c->stream, &launches, &err);
+    int rc;
+    if (!frontend_plan_exists(p.n_fft, p.hop, p.win_len)) {
+      // no tuned plan for this (n_fft, hop): generic direct-DFT kernel (+ spectrum -> mel kernel for the mel front ends)
+      if (rg || p.pre_mode != PRE_NONE || p.whisper_norm || p.out_mode == OUT_LFR || p.in_i16 || p.out_f16 || p.zero_tail != 0) {
+        c->err = "this front end is built for its standard (n_fft, hop) only";
+        return B2A_E_UNSUPPORTED;
+      }
+      const int n_bins = p.n_fft / 2 + 1;
+      if ((rc = ensure(c, c->scratch[slot][4], sizeof(float) * size_t(p.n_fft))) != B2A_OK) return rc;
+      float* d_win = static_cast<float*>(c->scratch[slot][4].p);
+      cudaError_t e = cudaMemcpyAsync(d_win, p.window->data(), sizeof(float) * size_t(p.n_fft), cudaMemcpyHostToDevice, c->stream);   // (pageable: staged at once)
+      if (e != cudaSuccess) return cu(c, e, "window upload");
+      float* d_spec = d_out;
+      if (p.out_mode != OUT_COMPLEX) {
+        if ((rc = ensure(c, c->scratch[slot][2], sizeof(float) * 2 * size_t(n) * size_t(p.n_frames) * n_bins)) != B2A_OK) return rc;
+        d_spec = static_cast<float*>(c->scratch[slot][2].p);
+      }
+      rc = launch_generic_stft(a.x, n, n_samples, p.n_frames, p.n_fft, p.hop, p.pad_left, p.pad_mode, d_win, d_spec, c->stream, &launches, &err);
+      if (rc == B2A_OK && p.out_mode != OUT_COMPLEX)
+        rc = launch_generic_mel(d_spec, d_out, n, p.n_frames, n_bins, p.bank, p.spec_mode, p.log_mode, p.log_floor, p.post_affine, p.post_sub, p.post_div,
+                                p.out_mode, c->stream, &launches, &err);
+    } else {
+      rc = launch_frontend(a, c->stream, &launches, &err);
+    }
     if (rc == B2A_OK && p.post_cmvn)
       rc = launch_cmvn(d_out, d_out, n, p.lfr_rows, p.lfr_m * p.bank.n_mels, nullptr, nullptr, c->stream, &launches, &err, a.clip_tab);
     if (rc == B2A_OK && p.post_mean_norm) rc = launch_mean_norm(d_out, n, p.n_frames, p.bank.n_mels, c->stream, &launches, &err, a.clip_tab);
@@ -479,6 +525,9 @@ static int ctx_create(b2a_ctx** out, int device, void* stream, bool own) {
     if (rc != B2A_OK) break;
     if (cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess) { rc = B2A_E_CUDA; break; }
     if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_flag), sizeof(int), cudaHostAllocDefault) != cudaSuccess) { rc = B2A_E_CUDA; break; }
+    for (int s = 0; s < kSlots && rc == B2A_OK; ++s)
+      if (cudaEventCreateWithFlags(&c->ev_tab[s], cudaEventDisableTiming) != cudaSuccess) rc = B2A_E_CUDA;
+    if (rc != B2A_OK) break;
     std::string err;
     rc = init_frontend_tables(&err);
   } while (false);
@@ -520,6 +569,10 @@ int b2a_ctx_destroy(b2a_ctx* c) {
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->fade.p) cudaFree(c->fade.p);
   if (c->h_flag) cudaFreeHost(c->h_flag);
+  for (int s = 0; s < kSlots; ++s) {
+    if (c->h_tab[s]) cudaFreeHost(c->h_tab[s]);
+    if (c->ev_tab[s]) cudaEventDestroy(c->ev_tab[s]);
+  }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -995,7 +1048,8 @@ static int s3gen_common(b2a_ctx* c, const float* y, int64_t batch, int64_t n_sam
   int rc = check_common(c, y, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (win_size > n_fft || win_size <= 0) return fail(c, B2A_E_BAD_ARG, "win_size must be in (0, n_fft]");
-  if (!frontend_plan_exists(n_fft, hop_size, n_fft)) return fail(c, B2A_E_UNSUPPORTED, "s3gen mel is built for n_fft 1920 / hop 480 (and 400 / 160)");
+  if (!frontend_plan_exists(n_fft, hop_size, n_fft) && (!generic_stft_supported(n_fft, hop_size) || lengths))
+    return fail(c, B2A_E_UNSUPPORTED, "s3gen mel: n_fft must lie in [2, 8192] (ragged batches: 1920 / 480 and 400 / 160 only)");
   const int64_t frames = b2a_s3gen_num_frames(n_samples, n_fft, hop_size);
   if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
   Guard g(c);
@@ -1039,7 +1093,8 @@ static int voice_encoder_common(b2a_ctx* c, const float* wav, int64_t batch, int
   if (cfg_in) cfg = *cfg_in;
   else b2a_voice_enc_config_default(&cfg);
   if (cfg.win_size > cfg.n_fft || cfg.win_size <= 0) return fail(c, B2A_E_BAD_ARG, "win_size must be in (0, n_fft]");
-  if (!frontend_plan_exists(cfg.n_fft, cfg.hop_size, cfg.n_fft)) return fail(c, B2A_E_UNSUPPORTED, "voice-encoder mel is built for n_fft 400 / hop 160");
+  if (!frontend_plan_exists(cfg.n_fft, cfg.hop_size, cfg.n_fft) && (!generic_stft_supported(cfg.n_fft, cfg.hop_size) || lengths))
+    return fail(c, B2A_E_UNSUPPORTED, "voice-encoder mel: n_fft must lie in [2, 8192] (ragged batches: n_fft 400 / hop 160 only)");
   if (cfg.mel_power != 1.0f && cfg.mel_power != 2.0f) return fail(c, B2A_E_UNSUPPORTED, "mel_power 1.0 and 2.0 are built");
   const int64_t frames = b2a_stft_num_frames(n_samples, cfg.n_fft, cfg.hop_size, 1);
   if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");
@@ -1083,11 +1138,11 @@ int b2a_stft(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, const
   int rc = check_common(c, x, out_complex, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (!window || win_len <= 0 || win_len > n_fft) return fail(c, B2A_E_BAD_ARG, "window must have 1..n_fft taps");
+  // tuned plans: (n_fft, hop) = (400, 160), (1920, 480), (512, 160) with <= 400 taps; every other size runs the generic kernel
   int plan_win = n_fft;
   if (!frontend_plan_exists(n_fft, hop, plan_win)) {
-    plan_win = 400;
-    if (!(n_fft == 512 && win_len <= 400 && frontend_plan_exists(n_fft, hop, plan_win)))
-      return fail(c, B2A_E_UNSUPPORTED, "stft is built for (n_fft, hop) = (400, 160), (1920, 480), and (512, 160) with <= 400 taps");
+    if (n_fft == 512 && win_len <= 400 && frontend_plan_exists(n_fft, hop, 400)) plan_win = 400;
+    else if (!generic_stft_supported(n_fft, hop)) return fail(c, B2A_E_UNSUPPORTED, "stft: n_fft must lie in [2, 8192] and hop must be positive");
   }
   const int64_t frames = b2a_stft_num_frames(n_samples, n_fft, hop, center);
   if (frames <= 0) return fail(c, B2A_E_TOO_SHORT, "Input is too short for STFT");

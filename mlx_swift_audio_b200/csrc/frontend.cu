@@ -1944,9 +1944,12 @@ int launch_tile_table(const void* clip_tab, int64_t n_clips, int64_t total_tiles
   return B2A_OK;
 }
 
-int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, void* stream,
-                      int* launches, std::string* err) {
-  const long long per_clip = rows_max * row_len;
+// max_tail_rows: the largest number of rows any clip of the batch falls short of rows_max (mel-major: of t_max columns); the grid is
+// sized for that tail and the launch is skipped when no clip has one (equal lengths through a ragged entry point)
+int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, int64_t max_tail,
+                      void* stream, int* launches, std::string* err) {
+  if (max_tail <= 0) return B2A_OK;
+  const long long per_clip = mel_major ? rows_max * max_tail : max_tail * row_len;
   dim3 grid(unsigned(std::max<long long>(1, std::min<long long>(64, (per_clip + 4095) / 4096))), unsigned(batch));
   zero_tail_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, static_cast<const int4*>(clip_tab), which, rows_max, row_len, mel_major);
   cudaError_t e = cudaGetLastError();

@@ -142,9 +142,17 @@ int launch_pcm16_to_f32(const void* in_i16, float* out, int64_t n, void* stream,
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
                        int* launches, std::string* err);
 int launch_tile_table(const void* clip_tab, int64_t n_clips, int64_t total_tiles, void* tile_tab, void* stream, int* launches, std::string* err);
-int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, void* stream,
-                      int* launches, std::string* err);
+int launch_zero_tails(float* out, const void* clip_tab, int which, int64_t batch, int64_t rows_max, int64_t row_len, int mel_major, int64_t max_tail,
+                      void* stream, int* launches, std::string* err);
 int launch_reflect_pad(const float* in, float* out, int64_t batch, int64_t n, int64_t pad, void* stream, int* launches, std::string* err);
+
+// ---- generic (any n_fft / hop) STFT and spectrum -> mel kernels (generic_stft.cu): the sizes without a tuned plan -------------
+bool generic_stft_supported(int n_fft, int hop);
+int launch_generic_stft(const float* x, int64_t batch, int64_t n_samples, int64_t n_frames, int n_fft, int hop, int64_t pad_left, int pad_mode,
+                        const float* window_dev, float* out_complex, void* stream, int* launches, std::string* err);
+int launch_generic_mel(const float* spec_complex, float* out, int64_t batch, int64_t n_frames, int n_bins, const DeviceBank& bank, int spec_mode,
+                       int log_mode, float log_floor, int post_affine, float post_sub, float post_div, int out_mode, void* stream, int* launches,
+                       std::string* err);
 
 // ---- vocoder STFT / iSTFT (vocoder.cu) -------------------------------------------------------
 enum IstftNorm { NORM_WSQ_FLOOR = 0 /* HiFT, CosyVoice3: / max(sum w^2, 1e-8) */, NORM_WSUM_NONZERO = 1 /* Kokoro */ };

@@ -105,6 +105,33 @@ B2A_DEV float exp_fast(float x) {
   return fmaf(y, e * 0.693147182f, y);
 }
 
+// atan2(y, x) without libdevice's slow path: octant reduction a = min / max in [0, 1], atan(a) = a * P(a^2) with a degree-7
+// near-minimax P (1.4e-7 rad in fp32 over [0, 1]), then the octant / quadrant / sign fix-ups.  atan2(+-0, x >= +0) = +-0,
+// atan2(+-0, x <= -0) = +-pi as in IEEE; MLX's arctan2 (MLXSTFT.swift:204) is compared at 2e-5 on mag * exp(i phase).
+B2A_DEV float atan2_poly(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float a = __fdividef(mn, mx);
+  if (!(mx > 0.0f)) a = 0.0f;            // atan2(0, 0)
+  const float u = a * a;
+  float p = fmaf(u, -0.004054217599332333f, 0.021861661225557327f);
+  p = fmaf(p, u, -0.05591040849685669f);
+  p = fmaf(p, u, 0.0964205339550972f);
+  p = fmaf(p, u, -0.13908571004867554f);
+  p = fmaf(p, u, 0.1994655430316925f);
+  p = fmaf(p, u, -0.33329859375953674f);
+  p = fmaf(p, u, 0.9999993443489075f);
+  float r = p * a;
+  if (ay > ax) r = 1.57079637f - r;
+  if (__float_as_int(x) < 0) r = 3.14159274f - r;
+  return copysignf(r, y);
+}
+B2A_DEV float sqrt_fast(float v) {   // MUFU square root (~2 ulp): the magnitude is compared at 1e-5 absolute
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 template <int NFFT, int HOP>
 struct IstftParams {
   const float* mag;
@@ -473,8 +500,8 @@ __global__ void __launch_bounds__(256) small_stft_kernel(const __grid_constant__
       o0[k * prm.n_frames] = yr[k];
       o1[k * prm.n_frames] = yi[k];
     } else {
-      o0[k * prm.n_frames] = sqrtf(yr[k] * yr[k] + yi[k] * yi[k]);
-      o1[k * prm.n_frames] = atan2f(yi[k], yr[k]);
+      o0[k * prm.n_frames] = sqrt_fast(yr[k] * yr[k] + yi[k] * yi[k]);
+      o1[k * prm.n_frames] = atan2_poly(yi[k], yr[k]);
     }
   }
 }

@@ -186,3 +186,39 @@ def test_tensor_core_whisper_prototype(api, ctx):
     assert_feat_close(got, np.stack([R.whisper_log_mel_spectrogram(c, 128) for c in x]), tol=RTOL, what="tensor-core whisper 128")
     assert_feat_close(got80, np.stack([R.whisper_log_mel_spectrogram(c, 80) for c in x]), tol=RTOL, what="tensor-core whisper 80")
     assert_feat_close(got_tone, R.whisper_log_mel_spectrogram(tone, 80), tol=2e-4, what="tensor-core whisper, pure tone")
+
+
+@pytest.mark.parametrize("n_fft,hop,win", [(256, 64, 256), (1024, 256, 1024), (600, 150, 480), (50, 7, 50)])
+def test_generic_stft_any_size(api, ctx, n_fft, hop, win):
+    # stft() for sizes without a tuned plan (S3TokenizerUtils.swift:224-263 takes any nFft / hopLength): direct-DFT kernel
+    x = synth.pcm(2, 6000, seed=2012)
+    w = api.hanningWindow(win + 1)[:win]
+    for center in (True, False):
+        got = api.stft(x, window=w, nFft=n_fft, hopLength=hop, center=center, ctx=ctx)
+        want = np.stack([R.stft(c, w, n_fft, hop, center=center) for c in x])
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_generic_stft_short_clip_reflect_loops(api, ctx):
+    # a clip shorter than the centre pad: the reference's repeated reflection (S3TokenizerUtils.swift:287-295) through the generic kernel
+    x = synth.pcm(1, 300, seed=2013, zero_tail_frac=0.0)[0]
+    w = api.hanningWindow(1025)[:1024]
+    got = api.stft(x, window=w, nFft=1024, hopLength=256, ctx=ctx)
+    want = R.stft(x, w, 1024, 256)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_voice_encoder_and_s3gen_other_fft_sizes(api, ctx):
+    from mlx_swift_audio_b200 import _lib as L
+    x = synth.pcm(2, 16000, seed=2014)
+    cfg = L.VoiceEncConfig()
+    ctx.lib.b2a_voice_enc_config_default(C.byref(cfg))
+    cfg.n_fft, cfg.hop_size, cfg.win_size = 512, 128, 512
+    got = api.voiceEncoderMelspectrogram(x, config=cfg, ctx=ctx)
+    want = np.stack([R.voice_encoder_melspectrogram(c, n_fft=512, hop_size=128, win_size=512) for c in x])
+    assert_feat_close(got, want, what="voice encoder n_fft 512")
+    y = synth.pcm(2, 24000, sample_rate=24000, seed=2015)
+    got = api.s3genMelSpectrogram(y, nFft=1024, numMels=80, samplingRate=24000, hopSize=256, winSize=1024, ctx=ctx)
+    want = R.s3gen_mel_spectrogram(y, n_fft=1024, hop_size=256, win_size=1024)
+    assert_feat_close(got, want, what="s3gen n_fft 1024")
