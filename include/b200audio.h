@@ -315,6 +315,15 @@ B2A_API int b2a_whisper_mel_segment_f16(b2a_ctx* ctx, const float* mel, int64_t 
  * TTS/CosyVoice2/CosyVoice2TTS.swift:733-744 + TTS/CosyVoice2/HiFiGAN/CosyHiFTGenerator.swift:17-58.  out (batch, new length).
  * (AVAudioConverter, Audio/AudioResampler.swift, is Apple's proprietary converter and has no reproducible definition.) */
 B2A_API int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int to_rate);
+/* NON-PARITY EXTENSION -- anti-aliased polyphase resampler standing in for AudioResampler.resample (Audio/AudioResampler.swift:15-88,
+ * call sites TTS/Chatterbox/ChatterboxModel.swift:445-462, STT/Whisper/WhisperEngine.swift:308-322), which is Apple's AVAudioConverter
+ * and has no reproducible definition.  Defined as scipy.signal.resample_poly(x, up, down) with its default design (its documented
+ * oracle, tests at 1e-5 absolute): rates reduced by their gcd, firwin(20 max(up, down) + 1, 1 / max(up, down), kaiser beta 5) * up,
+ * zero phase, zeros outside the clip, out (batch, ceil(n up / down)).  b2a_resample_poly_filter (host) returns the padded filter. */
+B2A_API int64_t b2a_resample_poly_length(int64_t n_samples, int from_rate, int to_rate);
+B2A_API int64_t b2a_resample_poly_filter(int64_t n_samples, int from_rate, int to_rate, float* h_out, int64_t cap, int* up_out, int* down_out,
+                                         int64_t* pre_remove_out);
+B2A_API int b2a_resample_poly(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out, int space);
 B2A_API int b2a_resample_linear(b2a_ctx* ctx, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out,
                                 int space);
 

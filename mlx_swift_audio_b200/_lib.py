@@ -94,6 +94,9 @@ SIGNATURES = {
     "b2a_s3tokenizer_gather_segments": (C.c_int, [_ctx, C.c_void_p, _i64, C.c_int, _i64, _i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                                   C.POINTER(C.c_int32), _i64, C.c_void_p, C.c_int]),
     "b2a_resample_linear_length": (_i64, [_i64, C.c_int, C.c_int]),
+    "b2a_resample_poly_length": (_i64, [_i64, C.c_int, C.c_int]),
+    "b2a_resample_poly_filter": (_i64, [_i64, C.c_int, C.c_int, _f, _i64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
+    "b2a_resample_poly": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_resample_linear": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_whisper_mel_segment_f16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.POINTER(_i64), C.POINTER(_i64), _i64, C.c_void_p,
                                               C.c_int]),

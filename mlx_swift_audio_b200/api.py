@@ -759,6 +759,19 @@ def resampleAudio(audio, fromRate: int, toRate: int, ctx: Context | None = None)
     return out if had_batch else out[0]
 
 
+def resamplePoly(audio, fromRate: int, toRate: int, ctx: Context | None = None):
+    """NON-PARITY EXTENSION: anti-aliased polyphase resampling, defined as ``scipy.signal.resample_poly(audio, up, down)`` with its
+    default Kaiser design -- the stand-in for ``AudioResampler.resample`` (Audio/AudioResampler.swift:15-88: AVAudioConverter, no
+    reproducible definition).  (T,) or (B, T) -> (ceil(T up / down),)"""
+    a = _Arr(audio)
+    b, n, had = _batched(a, 1)
+    c = _ctx_for(a, ctx)
+    new_t = int(c.lib.b2a_resample_poly_length(n, fromRate, toRate))
+    out = a.empty((b, new_t))
+    c.check(c.lib.b2a_resample_poly(c.h, a.ptr, b, n, fromRate, toRate, _ptr(out), a.space))
+    return out if had else out[0]
+
+
 def whisperMelSegment(mel, seek, contentFrames, length: int = 3000, ctx: Context | None = None):
     """Seek window of the Whisper decode loop (STT/Whisper/WhisperSTT.swift:171-182,624-635): rows
     [seek, seek + min(length, contentFrames - seek)) of the fp32 log-mel (T', M) or (B, T', M), zero-padded to ``length`` rows,

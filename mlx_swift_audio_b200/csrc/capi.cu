@@ -792,6 +792,44 @@ int b2a_resample_linear(b2a_ctx* c, const float* x, int64_t batch, int64_t n_sam
   return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(new_t), nullptr, 0, body);
 }
 
+int b2a_resample_poly(b2a_ctx* c, const float* x, int64_t batch, int64_t n_samples, int from_rate, int to_rate, float* out, int space) {
+  int rc = check_common(c, x, out, batch, n_samples);
+  if (rc != B2A_OK) return rc;
+  if (from_rate <= 0 || to_rate <= 0) return fail(c, B2A_E_BAD_ARG, "sample rates must be positive");
+  const int64_t new_t = b2a_resample_poly_length(n_samples, from_rate, to_rate);
+  Guard g(c);
+  if (!g.ok) return fail(c, B2A_E_CUDA, "cudaSetDevice failed");
+  int up = 1, down = 1;
+  int64_t pre = 0;
+  std::vector<float> h;
+  if (from_rate != to_rate) {
+    const int64_t taps = b2a_resample_poly_filter(n_samples, from_rate, to_rate, nullptr, 0, &up, &down, &pre);
+    if (taps <= 0 || taps > 0x7fffffff) return fail(c, B2A_E_UNSUPPORTED, "resample_poly: rate ratio out of range (up, down <= 4096 after reduction)");
+    h.resize(size_t(taps));
+    b2a_resample_poly_filter(n_samples, from_rate, to_rate, h.data(), taps, &up, &down, &pre);
+    if ((rc = ensure(c, c->scratch[0][4], sizeof(float) * h.size())) != B2A_OK) return rc;
+    // (synchronous upload: the design depends on the rate pair only in practice, the table is small)
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(c->scratch[0][4].p, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cu(c, e, "filter upload");
+  }
+  Body body = [&](const float* d_in, const float*, float* d_out, float*, int64_t n, int) -> int {
+    int launches = 0;
+    std::string err;
+    int r;
+    if (from_rate == to_rate) {
+      r = cu(c, cudaMemcpyAsync(d_out, d_in, sizeof(float) * size_t(n) * n_samples, cudaMemcpyDeviceToDevice, c->stream), "copy");
+    } else {
+      r = launch_resample_poly(d_in, d_out, static_cast<const float*>(c->scratch[0][4].p), n, n_samples, new_t, up, down, pre, int(h.size()), c->stream,
+                               &launches, &err);
+      if (r != B2A_OK) c->err = err;
+    }
+    c->launches += launches;
+    return r;
+  };
+  return run_batched(c, space, batch, x, size_t(n_samples), nullptr, 0, out, size_t(new_t), nullptr, 0, body);
+}
+
 int b2a_whisper_mel_segment_f16(b2a_ctx* c, const float* mel, int64_t batch, int64_t n_frames, int n_mels, const int64_t* seek,
                                 const int64_t* content_frames, int64_t length, void* out_f16, int space) {
   int rc = check_common(c, mel, out_f16, batch, n_frames);

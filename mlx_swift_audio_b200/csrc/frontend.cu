@@ -1479,6 +1479,41 @@ __global__ void __launch_bounds__(256) resample_linear_kernel(const float* __res
   out[clip * new_t + i] = __fadd_rn(__fmul_rn(__ldg(xc + lo), wl), __fmul_rn(__ldg(xc + hi), wh));
 }
 
+// Polyphase resampler (non-parity extension, see b2a_resample_poly_filter): y[j] = sum_i x[i] h[(j + pre) * down - i * up] over the taps
+// that exist, zeros outside the clip.  One thread per output sample; the filter (a few hundred to a few thousand taps) is read
+// through the read-only path (every thread of a warp walks it at stride `up` from a phase that repeats every `up` outputs).
+__global__ void __launch_bounds__(256) resample_poly_kernel(const float* __restrict__ x, float* __restrict__ out, const float* __restrict__ h, long long T,
+                                                            long long new_t, int up, int down, long long pre, int n_taps) {
+  const long long clip = blockIdx.y;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= new_t) return;
+  const long long pos = (j + pre) * down;
+  long long i = pos / up;                 // newest input sample under the filter
+  int k = int(pos - i * up);              // its tap
+  if (i >= T) {                           // past the end of the clip: skip the taps that would meet zeros
+    const long long skip = i - (T - 1);
+    i -= skip;
+    k += int(skip) * up;
+  }
+  const float* __restrict__ xc = x + clip * T;
+  float acc = 0.0f;
+  for (; k < n_taps && i >= 0; k += up, --i) acc = fmaf(__ldg(h + k), __ldg(xc + i), acc);
+  out[clip * new_t + j] = acc;
+}
+
+int launch_resample_poly(const float* x, float* out, const float* h_dev, int64_t batch, int64_t T, int64_t new_t, int up, int down, int64_t pre, int n_taps,
+                         void* stream, int* launches, std::string* err) {
+  dim3 grid(unsigned((new_t + 255) / 256), unsigned(batch));
+  resample_poly_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, h_dev, T, new_t, up, down, pre, n_taps);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("resample_poly_kernel launch: ") + cudaGetErrorString(e);
+    return B2A_E_CUDA;
+  }
+  *launches += 1;
+  return B2A_OK;
+}
+
 int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T, int64_t new_t, float step, float hi_clip, void* stream,
                            int* launches, std::string* err) {
   dim3 grid(unsigned((new_t + 255) / 256), unsigned(batch));

@@ -478,6 +478,80 @@ int64_t b2a_merge_tokenized_segments(const int32_t* tokens, const int64_t* seg_l
   return n;
 }
 
+// ---- polyphase resampler (non-parity extension: the reference's AudioResampler.resample, Audio/AudioResampler.swift:15-88, is
+// Apple's AVAudioConverter and has no reproducible definition).  The design is scipy.signal.resample_poly's, which serves as its
+// documented oracle: up / down reduced by their gcd, linear-phase low-pass firwin(2 * 10 * max(up, down) + 1, 1 / max(up, down),
+// window = kaiser(beta 5)) scaled by `up`, zero-phase alignment, output length ceil(n * up / down), zeros outside the signal.
+namespace {
+double bessel_i0(double x) {   // power series, converges fast for the |x| <= 5 used here
+  double sum = 1.0, term = 1.0;
+  const double q = 0.25 * x * x;
+  for (int k = 1; k < 200; ++k) {
+    term *= q / (double(k) * double(k));
+    sum += term;
+    if (term < 1e-18 * sum) break;
+  }
+  return sum;
+}
+int64_t gcd64(int64_t a, int64_t b) {
+  while (b) {
+    const int64_t t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+int64_t upfirdn_len(int64_t len_h, int64_t n_in, int64_t up, int64_t down) {   // scipy.signal._upfirdn._output_len
+  const int64_t nt = len_h + (n_in - 1) * up;
+  return (nt + down - 1) / down;
+}
+}  // namespace
+
+int64_t b2a_resample_poly_length(int64_t n_samples, int from_rate, int to_rate) {
+  if (n_samples <= 0 || from_rate <= 0 || to_rate <= 0) return 0;
+  const int64_t g = gcd64(to_rate, from_rate);
+  const int64_t up = to_rate / g, down = from_rate / g;
+  return (n_samples * up + down - 1) / down;
+}
+
+// Writes the zero-padded polyphase filter h (scaled by `up`) and the alignment: y[j] = sum_i x[i] * h[(j + pre_remove) * down - i * up].
+// Returns the number of taps written (<= cap), or -1.
+int64_t b2a_resample_poly_filter(int64_t n_samples, int from_rate, int to_rate, float* h_out, int64_t cap, int* up_out, int* down_out,
+                                 int64_t* pre_remove_out) {
+  if (n_samples <= 0 || from_rate <= 0 || to_rate <= 0 || from_rate == to_rate) return -1;
+  const int64_t g = gcd64(to_rate, from_rate);
+  const int64_t up = to_rate / g, down = from_rate / g;
+  if (up > 4096 || down > 4096) return -1;
+  const int64_t max_rate = std::max(up, down), half_len = 10 * max_rate, taps = 2 * half_len + 1;
+  const double fc = 1.0 / double(max_rate), alpha = 0.5 * double(taps - 1), pi = 3.14159265358979323846;
+  std::vector<double> h(static_cast<size_t>(taps));
+  double sum = 0.0;
+  const double i0b = bessel_i0(5.0);
+  for (int64_t k = 0; k < taps; ++k) {
+    const double m = double(k) - alpha, a = pi * fc * m;
+    const double sinc = m == 0.0 ? 1.0 : sin(a) / a;
+    const double r = 2.0 * double(k) / double(taps - 1) - 1.0;
+    const double win = bessel_i0(5.0 * sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+    h[size_t(k)] = fc * sinc * win;
+    sum += h[size_t(k)];
+  }
+  const int64_t n_out = b2a_resample_poly_length(n_samples, from_rate, to_rate);
+  const int64_t n_pre_pad = down - half_len % down;
+  int64_t n_post_pad = 0;
+  const int64_t n_pre_remove = (half_len + n_pre_pad) / down;
+  while (upfirdn_len(taps + n_pre_pad + n_post_pad, n_samples, up, down) < n_out + n_pre_remove) ++n_post_pad;
+  const int64_t total = n_pre_pad + taps + n_post_pad;
+  if (up_out) *up_out = int(up);
+  if (down_out) *down_out = int(down);
+  if (pre_remove_out) *pre_remove_out = n_pre_remove;
+  if (h_out) {
+    if (total > cap) return -1;
+    for (int64_t k = 0; k < total; ++k) h_out[k] = 0.0f;
+    for (int64_t k = 0; k < taps; ++k) h_out[n_pre_pad + k] = float(h[size_t(k)] / sum * double(up));
+  }
+  return total;
+}
+
 int64_t b2a_resample_linear_length(int64_t n_samples, int from_rate, int to_rate) {  // CosyVoice2TTS.swift:733-739, CosyHiFTGenerator.swift:26-31
   if (n_samples <= 0 || from_rate <= 0 || to_rate <= 0) return 0;
   if (from_rate == to_rate) return n_samples;

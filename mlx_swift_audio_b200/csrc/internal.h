@@ -138,6 +138,8 @@ int launch_mel_windows(const float* mel, float* out, int n_mels, int64_t t_max, 
                        int* launches, std::string* err);
 int launch_resample_linear(const float* x, float* out, int64_t batch, int64_t T, int64_t new_t, float step, float hi_clip, void* stream,
                            int* launches, std::string* err);
+int launch_resample_poly(const float* x, float* out, const float* h_dev, int64_t batch, int64_t T, int64_t new_t, int up, int down, int64_t pre, int n_taps,
+                         void* stream, int* launches, std::string* err);
 int launch_pcm16_to_f32(const void* in_i16, float* out, int64_t n, void* stream, int* launches, std::string* err);
 int launch_pad_or_trim(const float* in, float* out, int64_t batch, int64_t n, int64_t length, void* stream,
                        int* launches, std::string* err);

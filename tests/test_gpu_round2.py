@@ -222,3 +222,17 @@ def test_voice_encoder_and_s3gen_other_fft_sizes(api, ctx):
     got = api.s3genMelSpectrogram(y, nFft=1024, numMels=80, samplingRate=24000, hopSize=256, winSize=1024, ctx=ctx)
     want = R.s3gen_mel_spectrogram(y, n_fft=1024, hop_size=256, win_size=1024)
     assert_feat_close(got, want, what="s3gen n_fft 1024")
+
+
+@pytest.mark.parametrize("fr,to", [(24000, 16000), (16000, 24000), (44100, 16000), (48000, 16000), (22050, 24000)])
+def test_resample_poly_matches_scipy(api, ctx, fr, to):
+    # non-parity extension (stand-in for AVAudioConverter, Audio/AudioResampler.swift:15-88): scipy.signal.resample_poly is the oracle
+    from math import gcd
+    from scipy import signal
+    x = synth.pcm(2, fr // 2 + 13, sample_rate=fr, seed=2016, zero_tail_frac=0.0)
+    got = api.resamplePoly(x, fr, to, ctx=ctx)
+    g = gcd(fr, to)
+    want = np.stack([signal.resample_poly(c.astype(np.float64), to // g, fr // g) for c in x])
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-5
+    assert np.array_equal(api.resamplePoly(x[0], fr, fr, ctx=ctx), x[0])

@@ -252,3 +252,27 @@ def test_merge_tokenized_segments_matches_the_reference_rule():
     for segs in cases:
         for overlap, rate in ((4, 25), (5, 25), (2, 50), (0, 25)):
             assert api.mergeTokenizedSegments(segs, overlap, rate) == [int(v) for v in R.merge_tokenized_segments(segs, overlap, rate)]
+
+
+def test_resample_poly_filter_is_scipys_design():
+    # non-parity extension: the polyphase resampler is DEFINED as scipy.signal.resample_poly (default Kaiser design); the host-side
+    # filter + alignment must reproduce it (the GPU kernel is checked against scipy in tests/test_gpu_round2.py)
+    from scipy import signal
+    from mlx_swift_audio_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(5)
+    for n, fr, to in [(2400, 24000, 16000), (1600, 16000, 24000), (4410, 44100, 16000), (1000, 48000, 16000), (777, 22050, 16000)]:
+        up, dn, pre = C.c_int(), C.c_int(), C.c_int64()
+        taps = lib.b2a_resample_poly_filter(n, fr, to, None, 0, C.byref(up), C.byref(dn), C.byref(pre))
+        assert taps > 0
+        h = np.zeros(taps, np.float32)
+        assert lib.b2a_resample_poly_filter(n, fr, to, h.ctypes.data_as(C.POINTER(C.c_float)), taps, C.byref(up), C.byref(dn), C.byref(pre)) == taps
+        x = rng.standard_normal(n)
+        want = signal.resample_poly(x, up.value, dn.value)
+        new_t = lib.b2a_resample_poly_length(n, fr, to)
+        assert new_t == len(want)
+        xu = np.zeros(n * up.value)
+        xu[::up.value] = x
+        full = np.convolve(xu, h.astype(np.float64))
+        got = full[pre.value * dn.value::dn.value][:new_t]
+        assert np.abs(got - want).max() <= 1e-6
