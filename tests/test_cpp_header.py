@@ -64,3 +64,14 @@ int main(void) {
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout + r.stderr)
     assert "b200audio" in r.stdout
+
+
+def test_swift_shim_matches_the_c_header():
+    """No Swift toolchain here: tools/check_swift_shim.py checks every b2a_* call of the shim against the C prototypes (name, argument
+    count), that every helper of SURVEY.md section 8b is bound under the reference's name, and that every entry point of the header
+    is either bound or listed as deliberately unbound."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_swift_shim.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -236,3 +236,53 @@ def test_resample_poly_matches_scipy(api, ctx, fr, to):
     assert got.shape == want.shape
     assert np.abs(got - want).max() <= 1e-5
     assert np.array_equal(api.resamplePoly(x[0], fr, fr, ctx=ctx), x[0])
+
+
+def test_compiled_c_program_runs_the_front_end_on_a_golden_clip(ctx, tmp_path):
+    """A plain C99 program built against include/b200audio.h (no Python in the call path): b2a_whisper_log_mel_spectrogram on the
+    golden fixture's clips with host buffers, compared with the frozen oracle output."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "oracle_fp32_v1.npz"))
+    x = np.ascontiguousarray(gold["in_x16"], np.float32)
+    want = gold["whisper80"]
+    src = tmp_path / "main.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "b200audio.h"
+int main(int argc, char** argv) {
+  long batch = atol(argv[3]), n = atol(argv[4]);
+  int n_mels = atoi(argv[5]);
+  long frames = (long)b2a_whisper_num_frames(n, 0);
+  float* x = (float*)malloc(sizeof(float) * batch * n);
+  float* y = (float*)malloc(sizeof(float) * batch * frames * n_mels);
+  FILE* f = fopen(argv[1], "rb");
+  if (!f || fread(x, sizeof(float), batch * n, f) != (size_t)(batch * n)) return 2;
+  fclose(f);
+  b2a_ctx* ctx = NULL;
+  if (b2a_ctx_create(&ctx, 0) != B2A_OK) { fprintf(stderr, "no device\n"); return 3; }
+  int rc = b2a_whisper_log_mel_spectrogram(ctx, x, batch, n, n_mels, 0, y, B2A_HOST);
+  if (rc != B2A_OK) { fprintf(stderr, "%s\n", b2a_last_error(ctx)); return 4; }
+  /* the reference's fatalError path: a clip too short for one frame */
+  if (b2a_whisper_log_mel_spectrogram(ctx, x, 1, 100, n_mels, 0, y, B2A_HOST) != B2A_E_TOO_SHORT) return 5;
+  f = fopen(argv[2], "wb");
+  fwrite(y, sizeof(float), batch * frames * n_mels, f);
+  fclose(f);
+  printf("%ld launches\n", (long)b2a_ctx_launch_count(ctx));
+  b2a_ctx_destroy(ctx);
+  return 0;
+}
+''')
+    exe = tmp_path / "main"
+    libdir = os.path.join(root, "mlx_swift_audio_b200")
+    subprocess.run(["gcc", "-std=c99", "-O1", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir, "-l:libb200audio.so",
+                    "-Wl,-rpath," + libdir], check=True)
+    fin, fout = tmp_path / "in.f32", tmp_path / "out.f32"
+    x.tofile(fin)
+    r = subprocess.run([str(exe), str(fin), str(fout), str(x.shape[0]), str(x.shape[1]), "80"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("launches") and int(r.stdout.split()[0]) >= 2
+    got = np.fromfile(fout, np.float32).reshape(want.shape)
+    assert_feat_close(got, want, what="compiled C program, golden whisper80")
