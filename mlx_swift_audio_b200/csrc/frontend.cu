@@ -461,6 +461,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   static_assert(MEL == 0 || (SPEC == SK_POWER && FT == 32), "known banks are power-spectrum banks of the 32-frame plans");
   static_assert(!F16 || (BAKED && OUT == OUT_TM), "fp16 output is built for the (T', M) store of the baked banks");
   extern __shared__ __align__(16) float smem[];
+  // the clamp / statistics kernel behind this one may be scheduled as soon as every CTA here has started (it waits for this grid
+  // to complete before it reads anything): hides its launch latency, which matters for the reference's one-clip calls
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   float2* s_y = reinterpret_cast<float2*>(smem + R0W);
   float* s_p = reinterpret_cast<float*>(s_y);               // stage B leaves the spectrum tile in the exchange buffer (spectrum_slots)
   float* s_wt = reinterpret_cast<float*>(s_y) + P::Y_WORDS;  // window, item-major [n2][n1]
@@ -941,6 +944,9 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
                                                             const int4* __restrict__ clip_tab, int f16) {
   __shared__ int s_list[kClampTilesPerCta];
   __shared__ int s_count;
+  // launched with programmatic stream serialisation behind the front-end kernel (launch_plan): the blocks may already be resident
+  // while that kernel drains; nothing it wrote is read before this point (a no-op for a plain launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long clip = blockIdx.y;
   const long long mt_stride = n_frames;
   long long tile_base = clip * tiles_per_clip;
@@ -1697,10 +1703,23 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   if (a.whisper_norm) {
     for (long long c0 = 0; c0 < a.batch; c0 += 65535) {   // gridDim.y limit
       const long long nb = std::min<long long>(65535, a.batch - c0);
-      whisper_clamp_kernel<<<dim3(unsigned((prm.tiles_per_clip + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, st>>>(
-          F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.out) + c0 * prm.out_clip_stride) : a.out + c0 * prm.out_clip_stride, a.clip_max + c0, RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip, prm.tiles_per_clip, a.n_frames,
-          a.bank.n_mels, prm.out_clip_stride, a.out_mode, P::FT,   // tiles of FT frames
-          RAGGED ? prm.clip_tab + c0 : nullptr, F16 ? 1 : 0);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(unsigned((prm.tiles_per_clip + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb));
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      float* c_out = F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.out) + c0 * prm.out_clip_stride) : a.out + c0 * prm.out_clip_stride;
+      const int* c_max = a.clip_max + c0;
+      const int* c_min = RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip;
+      const int4* c_tab = RAGGED ? prm.clip_tab + c0 : nullptr;
+      if ((e = cudaLaunchKernelEx(&cfg, whisper_clamp_kernel, c_out, c_max, c_min, prm.tiles_per_clip, (long long)a.n_frames, a.bank.n_mels,
+                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0)) != cudaSuccess)
+        return cuda_fail(e, "whisper_clamp_kernel launch", err);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
     *launches += 1;
