@@ -450,7 +450,9 @@ struct SmallStftParams {
   float w[NFFT];
 };
 
-template <int NFFT, int HOP>
+// POLAR: magnitude / phase outputs (Kokoro's transform) instead of real / imaginary parts -- a template parameter so that the two
+// forms do not share one register allocation
+template <int NFFT, int HOP, bool POLAR>
 __global__ void __launch_bounds__(256) small_stft_kernel(const __grid_constant__ SmallStftParams<NFFT, HOP> prm) {
   constexpr int F = NFFT / 2 + 1;
   constexpr int PAD = NFFT / 2;
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(256) small_stft_kernel(const __grid_constant__
   float* o1 = prm.out1 + clip * F * prm.n_frames + f;
 #pragma unroll
   for (int k = 0; k < F; ++k) {
-    if (prm.out_kind == SOUT_REAL_IMAG) {
+    if (!POLAR) {
       o0[k * prm.n_frames] = yr[k];
       o1[k * prm.n_frames] = yi[k];
     } else {
@@ -553,6 +555,8 @@ static int launch_istft_t(const IstftArgs& a, cudaStream_t st, int* launches, st
   const long long n_seg = a.n_frames + R - 1;
   const int per_block = kIstftThreads - (R - 1);
   dim3 grid(unsigned((n_seg + per_block - 1) / per_block), unsigned(a.batch));
+  // (residency: 5 blocks per SM by registers; capping it lower with unused dynamic shared memory only costs -- measured 1.371 ms at 5
+  // blocks, 1.373 at 4, 1.74 at 3 for the 16 / 4 transform)
   if (a.head == 2) istft_kernel<NFFT, HOP, IM_RECT><<<grid, kIstftThreads, 0, st>>>(prm);
   else if (a.head) istft_kernel<NFFT, HOP, IM_HEAD><<<grid, kIstftThreads, 0, st>>>(prm);
   else istft_kernel<NFFT, HOP, IM_POLAR><<<grid, kIstftThreads, 0, st>>>(prm);
@@ -617,7 +621,24 @@ static int launch_small_stft_t(const SmallStftArgs& a, cudaStream_t st, int* lau
   prm.out_kind = a.out_kind;
   for (int n = 0; n < NFFT; ++n) prm.w[n] = a.window[n];
   dim3 grid(unsigned((a.n_frames + 255) / 256), unsigned(a.batch));
-  small_stft_kernel<NFFT, HOP><<<grid, 256, 0, st>>>(prm);
+  // Residency cap of the real / imaginary hop-4 kernel (HiFT source STFT, 88 B per frame, no arithmetic to speak of): with all 8
+  // blocks per SM resident its 19 address streams per block thrash the DRAM pages -- measured on 512 x 30 s: 8 blocks 1.857 ms,
+  // 7: 1.62, 6: 1.61, 5: 1.52, 4: 1.51, 3: 1.68.  The unused dynamic shared memory only limits the residency to 4 blocks.
+  // (The magnitude / phase kernel has the arithmetic to hide behind and is best left alone: 1.71 ms at 8 blocks, 1.76 at 4.)
+  size_t pad = 0;
+  if (NFFT == 16 && HOP == 4 && a.out_kind == SOUT_REAL_IMAG) {
+    pad = 56000;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      cudaError_t ea = cudaFuncSetAttribute(small_stft_kernel<NFFT, HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pad));
+      if (ea != cudaSuccess) return cuda_fail2(ea, "cudaFuncSetAttribute", err);
+      attr_set[dev] = true;
+    }
+  }
+  if (a.out_kind == SOUT_REAL_IMAG) small_stft_kernel<NFFT, HOP, false><<<grid, 256, pad, st>>>(prm);
+  else small_stft_kernel<NFFT, HOP, true><<<grid, 256, 0, st>>>(prm);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail2(e, "small_stft_kernel launch", err);
   *launches += 1;
