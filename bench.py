@@ -506,14 +506,18 @@ class CpuArm:
             self.pool = None
 
 
-def cpu_baseline(name: str, runs: int = 3, seconds: float = 1.5) -> dict:
-    arm = CpuArm(name, seconds)
-    try:
-        vals = [arm.run() for _ in range(runs)]
-    finally:
-        arm.close()
-    return {"value": float(np.median(vals)), "unit": UNIT, "cores": arm.cores, "kind": "port", "impl": arm.impl, "sample": arm.sample,
-            "runs": runs, "spread": [float(min(vals)), float(max(vals))]}
+def cpu_baseline(name: str, runs: int = 3) -> dict:
+    """The CPU arm for the `cpu_baseline` object: the same code path as `--impl reference`, run in a FRESH process (inside the
+    process that holds the CUDA context, pinned buffers and torch's thread pools the same sample measured ~2x slower), so that the
+    two CPU numbers of a round are taken under the same conditions."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", name, "--steps", str(runs), "--warmup", "3"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    if r.returncode != 0 or not r.stdout.strip():
+        raise RuntimeError("cpu_baseline subprocess failed: " + r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
 
 
 def run_reference(args):

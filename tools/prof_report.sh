@@ -5,7 +5,7 @@ set -e
 cd /root/repo/gpurun_out
 ncu -i prof_frontend_$1.ncu-rep --page source --csv --print-source sass > src_$1.csv 2>/dev/null
 ncu -i prof_frontend_$1.ncu-rep --page raw --csv > raw_$1.csv 2>/dev/null
-mkdir -p /tmp/cub; cd /tmp/cub && rm -f *.cubin *.dis && cuobjdump -xelf all /root/repo/mlx_swift_audio_b200/libb200audio.so >/dev/null 2>&1; nvdisasm -g -c frontend.sm_100a.cubin > frontend.dis
+mkdir -p /tmp/cub; cd /tmp/cub && rm -f *.cubin *.dis && cuobjdump -xelf all /root/repo/mlx_swift_audio_b200/libb200audio.so >/dev/null 2>&1; nvdisasm -g -c frontend.sm_100a.cubin > frontend.dis 2>/dev/null
 cd /root/repo
 python - <<PY
 import csv
