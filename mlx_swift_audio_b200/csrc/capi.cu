@@ -422,7 +422,7 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
       if ((e = cudaMemcpyAsync(c->scratch[slot][3].p, clip_tab, sizeof(int) * n_ints, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
         return cu(c, e, "table upload");
       if ((e = cudaEventRecord(c->ev_tab[slot], c->stream)) != cudaSuccess) return cu(c, e, "event record");
-      if ((rc = ensure(c, c->scratch[slot][4], sizeof(int) * 2 * size_t(total))) != B2A_OK) return rc;
+      if ((rc = ensure(c, c->scratch[slot][4], sizeof(int) * 4 * size_t(total))) != B2A_OK) return rc;
       a.clip_tab = c->scratch[slot][3].p;
       a.tile_tab = c->scratch[slot][4].p;
       a.total_tiles = total;

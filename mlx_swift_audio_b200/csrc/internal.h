@@ -98,7 +98,7 @@ struct FrontendArgs {
   int* clip_max = nullptr;
   float* tile_min = nullptr;
   // ragged batch (per-clip lengths): device tables -- clip_tab[b] = int4(n_samples, n_frames, lfr_rows, first tile of the
-  // clip), uploaded by the C ABI, and tile_tab[g] = int2(clip, tile), built from it on the device (launch_tile_table);
+  // clip), uploaded by the C ABI, and tile_tab[g] = int4(clip, tile, n_samples, n_frames), built from it on the device (launch_tile_table);
   // n_samples / n_frames / lfr_rows above are then those of the longest clip (they give the strides).
   // Null = every clip has n_samples samples.
   const void* clip_tab = nullptr;
