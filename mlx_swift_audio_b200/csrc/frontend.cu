@@ -1003,12 +1003,13 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
       } else {
         for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = fmaxf(d[e], thr);
       }
-    } else {  // OUT_MT
-      for (int e = threadIdx.x; e < rows * n_mels; e += blockDim.x) {
-        const int m = e / rows, r = e - m * rows;
-        float* d = o + (long long)m * mt_stride + f0 + r;
-        *d = fmaxf(*d, thr);
-      }
+    } else {  // OUT_MT: lanes over the tile's (<= 32) frames, warps over the filters -- no per-element division
+      const int r = threadIdx.x & 31;
+      if (r < rows)
+        for (int m = threadIdx.x >> 5; m < n_mels; m += int(blockDim.x >> 5)) {
+          float* d = o + (long long)m * mt_stride + f0 + r;
+          *d = fmaxf(*d, thr);
+        }
     }
   }
 }
