@@ -223,3 +223,25 @@ def test_repeated_runs_are_bit_identical(ctx):
         assert torch.equal(api.preprocessAudio(x[:, :320000].contiguous()), firstf), f"funasr run {rep}"
         assert torch.equal(api.s3genMelSpectrogram(y), firsts), f"s3gen run {rep}"
         assert torch.equal(api.istftHiFiGAN(mag, ph, 16, 4, w16), firsti), f"istft run {rep}"
+
+
+def test_whisper_f16_and_pcm16_full_length_batch(ctx):
+    """Round-2 entries at BASELINE's clip length: the fp16 features are the cast of the fp32 ones bit for bit, for every clip of a
+    96 x 30 s batch (device-resident and through the chunked host pipeline), and 16-bit PCM gives exactly what the scaled floats give."""
+    import torch
+    from mlx_swift_audio_b200 import api
+    B, n = 96, 480000
+    g = torch.Generator(device="cuda").manual_seed(13)
+    xi = torch.randint(-20000, 20000, (B, n), generator=g, device="cuda", dtype=torch.int32).to(torch.int16)
+    xi[:, n - n // 10:] = 0
+    xf = xi.to(torch.float32) / 32768.0
+    f32 = api.whisperLogMelSpectrogram(xf, nMels=128)
+    f16 = api.whisperLogMelSpectrogramF16(xf, nMels=128)
+    p16 = api.whisperLogMelSpectrogramF16(xi, nMels=128)
+    torch.cuda.synchronize()
+    assert f16.dtype == torch.float16 and f16.shape == (B, 3000, 128)
+    assert torch.equal(f16, f32.to(torch.float16))
+    assert torch.equal(p16, f16)
+    # host pipeline (3 x 128 MB chunks at this size): same bits
+    h16 = api.whisperLogMelSpectrogramF16(xi.cpu().numpy(), nMels=128, ctx=ctx)
+    assert np.array_equal(h16.view(np.uint16), f16.cpu().numpy().view(np.uint16))
