@@ -346,6 +346,11 @@ B2A_API int b2a_s3tokenizer_gather_segments(b2a_ctx* ctx, const float* mel, int6
  * bin_major) into the kernel's sparse mel "step program" and interprets it on the host for one spectrum p.
  * Returns the number of steps, -1 if the bank is not of the <=2-adjacent-filters-per-bin form. */
 B2A_API int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out);
+/* Test hook (host only): builds the mel schedule of the warp-per-frame n_fft 1920 front end (balanced per-lane segments) for a dense
+ * filterbank and interprets it on the host for one spectrum p, exactly as the kernel does.  Returns the schedule's size in 32-bit
+ * words (+ 65536 x the number of segments left with a shared-memory bank conflict), -1 if the bank does not fit the schedule, -2 if a
+ * lane would read past the spectrum row, -3 if a start bin is not 16-byte aligned. */
+B2A_API int b2a_debug_wpf_mel_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out);
 /* Test hook (host only): shared-memory layout of the FFT plan of n_fft (spectrum rows and mel staging words in the exchange buffer). */
 B2A_API int b2a_debug_plan_layout(int n_fft, int n_mels, int* slots_out, int* words_out);
 /* Build hook (host only): raw mel step program for a CTA shape (see tools/gen_mel_baked.py). */
@@ -362,6 +367,9 @@ B2A_API int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins
 /* Switches the experimental tensor-core Whisper front end (tcgen05 split-precision DFT, csrc/tc_frontend.cu) on / off for the
  * process; the environment variable B2A_WHISPER_TC=1 sets the initial state.  Off by default: DESIGN.md section 6. */
 B2A_API int b2a_debug_whisper_tc(int on);
+/* Switches the warp-per-frame n_fft 1920 front end (csrc/wpf1920.cu; on by default, B2A_WPF1920=0 sets the initial state to off) on / off
+ * for the process: off = the tiled lane == frame kernel of csrc/frontend.cu runs the S3Gen mel (A/B switch, both are parity-tested). */
+B2A_API int b2a_debug_wpf1920(int on);
 /* Bring-up hook of the tensor-core Whisper front end (B2A_WHISPER_TC=1): when a device buffer of (batch, T', 201) floats is set, the
  * kernel also leaves the power spectrum |X[k]|^2 of every frame there.  NULL switches it off. */
 B2A_API int b2a_debug_tc_power_buffer(void* device_ptr);

@@ -108,10 +108,12 @@ SIGNATURES = {
     "b2a_s3gen_trim_fade": (C.c_int, [C.c_int, _f]),
     "b2a_kokoro_head_istft": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_debug_mel_program_apply": (C.c_int, [_f, C.c_int, C.c_int, C.c_int, _f, _f]),
+    "b2a_debug_wpf_mel_apply": (C.c_int, [_f, C.c_int, C.c_int, C.c_int, _f, _f]),
     "b2a_debug_plan_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2a_debug_mel_program_dump": (C.c_int, [_f, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint), C.c_int,
                                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2a_debug_whisper_tc": (C.c_int, [C.c_int]),
+    "b2a_debug_wpf1920": (C.c_int, [C.c_int]),
     "b2a_debug_tc_power_buffer": (C.c_int, [C.c_void_p]),
     "b2a_ctx_enable_timing": (C.c_int, [_ctx, C.c_int]),
     "b2a_ctx_last_kernel_ms": (C.c_int, [_ctx, _f]),

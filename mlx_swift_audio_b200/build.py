@@ -19,8 +19,8 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libb200audio.so")
 OBJ_DIR = os.path.join(HERE, "_build")
 
-SOURCES = ["host_tables.cpp", "frontend.cu", "vocoder.cu", "tc_frontend.cu", "generic_stft.cu", "capi.cu"]
-HEADERS = ["codelets.h", "mel_baked.h", "internal.h", os.path.join("..", "..", "include", "b200audio.h")]
+SOURCES = ["host_tables.cpp", "frontend.cu", "wpf1920.cu", "vocoder.cu", "tc_frontend.cu", "generic_stft.cu", "capi.cu"]
+HEADERS = ["codelets.h", "mel_baked.h", "internal.h", "pad_index.cuh", os.path.join("..", "..", "include", "b200audio.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",

@@ -31,6 +31,8 @@ struct BankStorage {
   float* weights = nullptr;
   float* steps = nullptr;
   int baked_id = 0;
+  uint32_t* wpf = nullptr;     // n_fft 1920: mel schedule of the warp-per-frame kernel (build_wpf_mel)
+  int wpf_words = 0;
 };
 
 constexpr int kSlots = 3;  // chunk ring depth of the host pipeline
@@ -119,6 +121,8 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
     BankStorage bs;
     build_sparse_bank(dense.data(), n_mels, n_bins, bin_major, bs.host);
     if (ps) build_mel_program(dense.data(), n_mels, n_bins, bin_major, frame_tile, words.data(), n_chunks, slots.data(), bs.host);
+    std::vector<uint32_t> wpf_blob;   // n_fft 1920: the warp-per-frame kernel's schedule (none when the bank does not fit: the tiled kernel runs)
+    if (n_fft == 1920) build_wpf_mel(bs.host, n_fft / 2 + 1, wpf_blob);
     const size_t nw = std::max<size_t>(bs.host.weights.size(), 1);
     std::vector<int> desc(size_t(n_mels) * 4, 0);
     for (int m = 0; m < n_mels; ++m) {
@@ -139,6 +143,11 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
         if ((e = cudaMalloc(&bs.steps, sizeof(float) * bs.host.steps.size())) != cudaSuccess) return e;
         if ((e = cudaMemcpy(bs.steps, bs.host.steps.data(), sizeof(float) * bs.host.steps.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
       }
+      if (!wpf_blob.empty()) {
+        if ((e = cudaMalloc(&bs.wpf, sizeof(uint32_t) * wpf_blob.size())) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(bs.wpf, wpf_blob.data(), sizeof(uint32_t) * wpf_blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        bs.wpf_words = int(wpf_blob.size());
+      }
       return cudaSuccess;
     };
     const cudaError_t ue = upload();
@@ -146,6 +155,7 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
       if (bs.desc) cudaFree(bs.desc);
       if (bs.weights) cudaFree(bs.weights);
       if (bs.steps) cudaFree(bs.steps);
+      if (bs.wpf) cudaFree(bs.wpf);
       return cu(c, ue, "filterbank upload");
     }
     if (!bs.host.steps.empty())
@@ -165,6 +175,8 @@ int cached_bank(b2a_ctx* c, const std::string& key0, int n_fft, int n_mels, int 
   out->n_mels = n_mels;
   out->n_bins_used = bs.host.max_bin + 1;
   out->baked_id = bs.baked_id;
+  out->wpf_mel = bs.wpf;
+  out->wpf_words = bs.wpf_words;
   return B2A_OK;
 }
 
@@ -583,6 +595,7 @@ int b2a_ctx_destroy(b2a_ctx* c) {
     cudaFree(kv.second.desc);
     cudaFree(kv.second.weights);
     if (kv.second.steps) cudaFree(kv.second.steps);
+    if (kv.second.wpf) cudaFree(kv.second.wpf);
   }
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -679,6 +692,11 @@ int b2a_memcpy_d2h(b2a_ctx* c, void* host_dst, const void* device_src, uint64_t 
 
 int b2a_debug_whisper_tc(int on) {
   tc_whisper_enable(on);
+  return B2A_OK;
+}
+
+int b2a_debug_wpf1920(int on) {
+  wpf1920_enable(on);
   return B2A_OK;
 }
 

@@ -42,6 +42,7 @@
 #include "codelets.h"
 #include "internal.h"
 #include "mel_baked.h"
+#include "pad_index.cuh"
 
 // 1 = interior tiles of the standard 7/6 LFR stacking take the division-free store (0 keeps the generic segment loop: A/B switch)
 #ifndef B2A_LFR_FAST
@@ -58,7 +59,6 @@ namespace b2a {
 // ------------------------------------------------------------------------------------------------
 // codelet dispatch by array size
 // ------------------------------------------------------------------------------------------------
-#define B2A_DEV __device__ __forceinline__
 B2A_DEV void rdft(const float (&x)[16], float (&yr)[9], float (&yi)[9]) { b2a_rdft16(x, yr, yi); }
 B2A_DEV void rdft(const float (&x)[20], float (&yr)[11], float (&yi)[11]) { b2a_rdft20(x, yr, yi); }
 B2A_DEV void rdft(const float (&x)[32], float (&yr)[17], float (&yi)[17]) { b2a_rdft32(x, yr, yi); }
@@ -170,28 +170,6 @@ B2A_DEV int enc_ordered(float f) {
   return b >= 0 ? b : b ^ 0x7fffffff;
 }
 B2A_DEV float dec_ordered(int e) { return __int_as_float(e >= 0 ? e : e ^ 0x7fffffff); }
-
-// Source index of padded coordinate p of one clip, or -1 where the padding is zero (the one statement of the padding rules:
-// reflectPad with the reference's repeated same-direction reflection for clips shorter than the pad, S3TokenizerUtils.swift:266-298,
-// and MLX.padded's zeros).  The modulo only runs when the overshoot exceeds one reflection.
-B2A_DEV long long padded_index(long long p, long long pad_left, long long n_eff, int pad_mode) {
-  long long j = p - pad_left;
-  if (j < 0 || j >= n_eff) {
-    if (pad_mode != PAD_REFLECT) return -1;
-    if (n_eff == 1) return 0;
-    long long t = j < 0 ? -j - 1 : j - n_eff;
-    if (t >= n_eff - 1) t %= n_eff - 1;
-    j = j < 0 ? t + 1 : n_eff - 2 - t;
-  }
-  return j;
-}
-
-// value of padded coordinate p of one clip (samples in [n_samples, n_eff) are the caller's zero tail)
-B2A_DEV float fetch_padded(const float* __restrict__ xc, long long p, long long pad_left, long long n_samples,
-                           long long n_eff, int pad_mode) {
-  const long long j = padded_index(p, pad_left, n_eff, pad_mode);
-  return j >= 0 && j < n_samples ? __ldg(xc + j) : 0.0f;
-}
 
 // Shared-memory word offset (relative to the lane's frame start) of sample o = N2*n1 + n2 in the skewed
 // PCM tile: o + o / HOP.  With n1 a compile-time constant this is (immediate) + n2 + carry, and the carry
@@ -1564,7 +1542,7 @@ int init_frontend_tables(std::string* err) {
   if ((e = cudaMemcpyToSymbol(c_tw512, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
   fill_tw(t, 1920, 60, 32);
   if ((e = cudaMemcpyToSymbol(c_tw1920, t.data(), t.size() * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
-  return B2A_OK;
+  return init_wpf1920_tables(err);
 }
 
 bool frontend_plan_exists(int n_fft, int hop, int win_len) {
@@ -1816,6 +1794,8 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (a.n_fft == 1920 && a.hop == 480 && a.win_len == 1920 && a.pre_mode == PRE_NONE) {
+    // equal-length mel batches: the warp-per-frame kernel (wpf1920.cu); B2A_WPF1920=0 / b2a_debug_wpf1920(0) keep the tiled kernel
+    if (spec != SK_CPLX && wpf1920_applicable(a)) return launch_wpf1920(a, stream, launches, err);
     // S3Gen 24 kHz mel (S3GenMel.swift:43-102): magnitude spectrum, ln, (M, T') -- compile-time post-processing keeps the store code short
     if (!ragged && spec == SK_MAG && a.bank.steps != nullptr && a.log_mode == LOG_LN && !a.whisper_norm && !a.post_affine && a.out_mode == OUT_MT)
       return launch_plan<Plan1920, PRE_NONE, SK_MAG, 0, POST_LN, OUT_MT>(a, st, launches, err);

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "../../include/b200audio.h"
@@ -164,6 +165,153 @@ int64_t reflect_pad_index(int64_t i, int64_t n, int64_t pad) {
 
 // ---- sparse filterbank: each filter = contiguous run of bins with non-zero weight ----------
 // bank is (n_mels, n_bins) row-major when !bin_major, else (n_bins, n_mels).
+// Mel schedule of the warp-per-frame front end (layout: internal.h)
+bool build_wpf_mel(const SparseBank& sb, int n_bins_spectrum, std::vector<uint32_t>& blob) {
+  blob.clear();
+  const int M = sb.n_mels;
+  if (M <= 0 || M > kWpfRounds * 32 || sb.max_bin >= n_bins_spectrum) return false;
+  const int span = (n_bins_spectrum + 3) & ~3;   // the kernel may read the spectrum row up to its next 16-byte boundary
+  struct Seg { int m, a, b; };   // filter m, bins [a, b)
+  std::vector<Seg> segs;
+  std::vector<int> per_filter(static_cast<size_t>(M), 1);
+  for (int m = 0; m < M; ++m) segs.push_back({m, sb.start[m], sb.start[m] + sb.count[m]});
+  const int rounds = (M + 31) / 32, want = rounds * 32;
+  while (int(segs.size()) < want) {   // halve the longest segment of a filter that still has fewer than four
+    int best = -1;
+    for (int i = 0; i < int(segs.size()); ++i)
+      if (per_filter[size_t(segs[i].m)] < 4 && segs[i].b - segs[i].a >= 2 && (best < 0 || segs[i].b - segs[i].a > segs[best].b - segs[best].a)) best = i;
+    if (best < 0) break;
+    const Seg s = segs[size_t(best)];
+    const int mid = s.a + (s.b - s.a + 1) / 2;
+    segs[size_t(best)] = {s.m, s.a, mid};
+    segs.push_back({s.m, mid, s.b});
+    per_filter[size_t(s.m)] += 1;
+  }
+  while (int(segs.size()) < want) segs.push_back({-1, 0, 0});   // idle lanes
+  std::stable_sort(segs.begin(), segs.end(), [](const Seg& x, const Seg& y) { return x.b - x.a > y.b - y.a; });
+  // Round r = segments [32 r, 32 r + 32).  A lane reads len4[r] groups of four bins from a 16-byte aligned start a0 <= a with
+  // a0 + 4 len4[r] >= b (weights zero outside [a, b)).  Within a quarter-warp the eight 16-byte reads of one instruction are
+  // conflict-free when (a0 / 4) mod 8 differs from lane to lane: the slack of the shorter segments is used for that, and the
+  // segments of a round may sit on any lane.
+  int len4[4] = {0, 0, 0, 0}, woff[4] = {0, 0, 0, 0};
+  std::vector<int> lane_of(size_t(want), -1), a0_of(size_t(want), 0);
+  int conflicts = 0;
+  int words = kWpfMelHeader;
+  for (int r = 0; r < rounds; ++r) {
+    int need = 0;
+    for (int i = r * 32; i < r * 32 + 32; ++i) {
+      const Seg& s = segs[size_t(i)];
+      if (s.b > s.a) need = std::max(need, (s.b - (s.a & ~3) + 3) / 4);
+    }
+    if (4 * need > span) return false;
+    // bipartite matching (augmenting paths) of the round's segments to the 32 (quarter-warp, residue) slots; one more group of slack is
+    // tried when the minimal length leaves a segment without a free residue
+    int best_unmatched = 33;
+    std::vector<int> best_slot;
+    int best_need = need;
+    for (int extra = 0; extra <= 1 && best_unmatched > 0; ++extra) {
+      const int nd = need + extra;
+      if (4 * nd > span) break;
+      bool ok[32][8];
+      for (int j = 0; j < 32; ++j) {
+        const Seg& s = segs[size_t(r * 32 + j)];
+        int lo = std::max(0, s.b - 4 * nd), hi = std::min(s.a, span - 4 * nd);
+        if (s.b <= s.a) { lo = 0; hi = span - 4 * nd; }
+        lo = (lo + 3) & ~3;
+        hi &= ~3;
+        for (int rho = 0; rho < 8; ++rho) ok[j][rho] = false;
+        for (int a0 = lo; a0 <= hi; a0 += 4) ok[j][(a0 / 4) & 7] = true;
+      }
+      std::vector<int> slot_owner(32, -1), slot_of(32, -1);   // slot = quarter * 8 + residue
+      std::function<bool(int, std::vector<char>&)> augment = [&](int j, std::vector<char>& seen) -> bool {
+        for (int sl = 0; sl < 32; ++sl) {
+          if (!ok[j][sl & 7] || seen[size_t(sl)]) continue;
+          seen[size_t(sl)] = 1;
+          if (slot_owner[size_t(sl)] < 0 || augment(slot_owner[size_t(sl)], seen)) {
+            slot_owner[size_t(sl)] = j;
+            slot_of[size_t(j)] = sl;
+            return true;
+          }
+        }
+        return false;
+      };
+      int unmatched = 0;
+      for (int j = 0; j < 32; ++j) {
+        std::vector<char> seen(32, 0);
+        if (!augment(j, seen)) unmatched += 1;
+      }
+      if (unmatched < best_unmatched) {
+        best_unmatched = unmatched;
+        best_slot = slot_of;
+        best_need = nd;
+      }
+    }
+    need = best_need;
+    len4[r] = need;
+    {
+      std::vector<char> taken(32, 0);
+      for (int j = 0; j < 32; ++j)
+        if (best_slot[size_t(j)] >= 0) taken[size_t(best_slot[size_t(j)])] = 1;
+      for (int j = 0; j < 32; ++j) {
+        const Seg& s = segs[size_t(r * 32 + j)];
+        int lo = std::max(0, s.b - 4 * need), hi = std::min(s.a, span - 4 * need);
+        if (s.b <= s.a) { lo = 0; hi = span - 4 * need; }
+        lo = (lo + 3) & ~3;
+        hi &= ~3;
+        int sl = best_slot[size_t(j)], a0 = hi;
+        if (sl < 0) {   // no free residue: any free slot, a two-way bank conflict on that quarter-warp's loads
+          for (sl = 0; taken[size_t(sl)]; ++sl) {}
+          taken[size_t(sl)] = 1;
+          if (s.b > s.a) conflicts += 1;
+        } else {
+          for (a0 = hi; a0 >= lo && ((a0 / 4) & 7) != (sl & 7); a0 -= 4) {}
+        }
+        lane_of[size_t(r * 32 + j)] = sl;   // lane = quarter * 8 + position; positions within a quarter are interchangeable
+        a0_of[size_t(r * 32 + j)] = a0;
+      }
+    }
+    woff[r] = words;
+    words += need * 32 * 4;
+  }
+  const int start_off = words;
+  words += rounds * 32;
+  words = (words + 3) & ~3;
+  const int fin_off = words;
+  words += M * 4;
+  if (words > kWpfMelMaxWords) return false;
+  blob.assign(size_t(words), 0u);
+  blob[0] = uint32_t(M);
+  blob[1] = uint32_t(rounds);
+  for (int r = 0; r < rounds; ++r) {
+    blob[size_t(2 + r)] = uint32_t(len4[r]);
+    blob[size_t(6 + r)] = uint32_t(woff[r]);
+  }
+  blob[10] = uint32_t(start_off);
+  blob[11] = uint32_t(fin_off);
+  blob[12] = uint32_t(words);
+  blob[13] = uint32_t(conflicts);
+  for (int m = 0; m < M; ++m)
+    for (int j = 0; j < 4; ++j) blob[size_t(fin_off + 4 * m + j)] = uint32_t(rounds * 32);   // the zero slot
+  std::vector<std::vector<std::pair<int, int>>> of_filter{size_t(M)};   // (first bin, slot)
+  for (int i = 0; i < want; ++i) {
+    const Seg& s = segs[size_t(i)];
+    const int r = i / 32, lane = lane_of[size_t(i)], a0 = a0_of[size_t(i)];
+    blob[size_t(start_off + r * 32 + lane)] = uint32_t(a0);
+    if (s.m < 0 || s.b <= s.a) continue;
+    for (int k = s.a; k < s.b; ++k) {
+      const float w = sb.weights[size_t(sb.offset[size_t(s.m)] + (k - sb.start[size_t(s.m)]))];
+      const int g = (k - a0) / 4, e = (k - a0) % 4;
+      memcpy(&blob[size_t(woff[r] + (g * 32 + lane) * 4 + e)], &w, 4);   // float4 [group][lane]
+    }
+    of_filter[size_t(s.m)].push_back({s.a, r * 32 + lane});
+  }
+  for (int m = 0; m < M; ++m) {
+    std::sort(of_filter[size_t(m)].begin(), of_filter[size_t(m)].end());
+    for (size_t j = 0; j < of_filter[size_t(m)].size(); ++j) blob[size_t(fin_off + 4 * m) + j] = uint32_t(of_filter[size_t(m)][j].second);
+  }
+  return true;
+}
+
 void build_sparse_bank(const float* bank, int n_mels, int n_bins, bool bin_major, SparseBank& sb) {
   sb.n_mels = n_mels;
   sb.n_bins = n_bins;
@@ -597,6 +745,39 @@ int b2a_debug_mel_program_apply(const float* bank, int n_mels, int n_bins, int b
   for (int m = 0; m < n_mels; ++m)
     if (seen[m] != 1) return -2;  // every filter must have been emitted exactly once
   return int(sb.steps.size() / 4);
+}
+
+// Test hook (host only): builds the warp-per-frame mel schedule (build_wpf_mel) of `bank` and interprets it on the host as wpf1920.cu does
+// (per-lane segment sums over len[r] bins from the lane's start bin, then the <= 4 segment sums of a filter in slot order), for one
+// spectrum `p` (n_bins).  Returns the schedule's size in words, or -1 when the bank does not fit.
+int b2a_debug_wpf_mel_apply(const float* bank, int n_mels, int n_bins, int bin_major, const float* p, float* out) {
+  b2a::SparseBank sb;
+  b2a::build_sparse_bank(bank, n_mels, n_bins, bin_major != 0, sb);
+  std::vector<uint32_t> blob;
+  if (!b2a::build_wpf_mel(sb, n_bins, blob)) return -1;
+  const int rounds = int(blob[1]), span = (n_bins + 3) & ~3;
+  std::vector<float> spec(size_t(span), 12345.0f);   // the words between the last bin and the 16-byte boundary hold stale finite data
+  for (int k = 0; k < n_bins; ++k) spec[size_t(k)] = p[k];
+  std::vector<float> part(size_t(rounds) * 32 + 1, 0.0f);
+  for (int r = 0; r < rounds; ++r)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int a0 = int(blob[blob[10] + size_t(r) * 32 + lane]);
+      if (a0 % 4 != 0) return -3;   // 16-byte loads
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int g = 0; g < int(blob[2 + size_t(r)]); ++g)
+        for (int e = 0; e < 4; ++e) {
+          float w;
+          memcpy(&w, &blob[blob[6 + size_t(r)] + (size_t(g) * 32 + lane) * 4 + e], 4);
+          if (a0 + 4 * g + e >= span) return -2;   // the kernel would read past the spectrum row
+          acc[e] = fmaf(w, spec[size_t(a0 + 4 * g + e)], acc[e]);
+        }
+      part[size_t(r) * 32 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+  for (int m = 0; m < n_mels; ++m) {
+    const uint32_t* f = &blob[blob[11] + 4 * size_t(m)];
+    out[m] = ((part[f[0]] + part[f[1]]) + part[f[2]]) + part[f[3]];
+  }
+  return int(blob.size()) + (int(blob[13]) << 16);   // schedule words, and the number of unavoidable bank-conflict pairs above bit 16
 }
 
 // Test hook (host only): the shared-memory layout of the FFT plan of `n_fft` -- row of the exchange buffer that holds each spectrum

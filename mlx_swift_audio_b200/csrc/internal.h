@@ -41,6 +41,18 @@ bool output_words(const PlanShape& ps, int n_mels, std::vector<int>& emit_word);
 int output_block_capacity(const PlanShape& ps);
 void build_mel_program(const float* bank, int n_mels, int n_bins, bool bin_major, int frame_tile, const int* emit_word, int n_chunks,
                        const int* bin_slot, SparseBank& sb);
+// Mel schedule of the warp-per-frame front end (wpf1920.cu: one warp = one frame, the spectrum of a frame lies bin-major in the warp's
+// shared memory).  The filters are cut into at most kWpfRounds * 32 segments of contiguous bins (the widest ones in halves / quarters), sorted
+// by length and dealt round by round to the 32 lanes: in round r every lane accumulates len4[r] groups of FOUR products (two 16-byte
+// loads: weights, bins) over its own segment, read from a 16-byte aligned start bin (weights zero outside the segment); the starts and
+// the lane of every segment are chosen so that the eight 16-byte spectrum reads of a quarter-warp fall into different banks.  Then
+// filter m is the sum of its <= 4 segment sums in ascending bin order.  32-bit words:
+//   [0] n_mels  [1] rounds  [2..5] len4[r]  [6..9] word offset of round r's weights (float4 [group][lane])  [10] word offset of the
+//   start table ([r][lane]: first bin read, a multiple of 4)  [11] word offset of the segment table ([m][4]: partial-sum slots
+//   r * 32 + lane, or rounds * 32 = the zero slot)  [12] total words  [13] segments left with a two-way bank conflict.
+// False when the bank does not fit (n_mels > kWpfRounds * 32, more than kWpfMelMaxWords words).
+constexpr int kWpfRounds = 3, kWpfMelMaxWords = 3584, kWpfMelHeader = 16;
+bool build_wpf_mel(const SparseBank& sb, int n_bins_spectrum, std::vector<uint32_t>& blob);
 
 // ---- fused STFT -> (power | magnitude) -> mel -> log front-end (frontend.cu) -----------------
 enum PadMode { PAD_NONE = 0, PAD_REFLECT = 1, PAD_ZERO = 2 };
@@ -65,6 +77,8 @@ struct DeviceBank {  // sparse filterbank in device memory
   int n_mels = 0;
   int n_bins_used = 0;  // bins [0, n_bins_used) are read by the mel stage
   int baked_id = 0;     // > 0: the step program equals baked bank `baked_id` of mel_baked.h (straight-line kernel available)
+  const uint32_t* wpf_mel = nullptr;   // n_fft 1920: mel schedule of the warp-per-frame kernel (build_wpf_mel), device memory; null = none
+  int wpf_words = 0;
 };
 
 struct FrontendArgs {
@@ -112,6 +126,11 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames);
 int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, const int* chunk_s, int n_chunks, int frame_tile, int n_mels);
 bool frontend_plan_exists(int n_fft, int hop, int win_len);
 int init_frontend_tables(std::string* err);  // once per device: twiddle tables into __constant__ memory
+// Warp-per-frame front end for n_fft 1920 / hop 480 (wpf1920.cu): |X| or |X|^2 -> any bank with a wpf_mel schedule -> log -> (M, T')
+bool wpf1920_applicable(const FrontendArgs& a);
+int launch_wpf1920(const FrontendArgs& a, void* stream, int* launches, std::string* err);
+int init_wpf1920_tables(std::string* err);
+void wpf1920_enable(int on);
 
 // max - 8 clamp of the Whisper-style front ends over (batch, n_frames, n_mels) fp32 features in (T', M) layout, from the per-clip maxima and
 // the (negated) per-32-frame-tile minima the main kernel left behind (frontend.cu: whisper_clamp_kernel)

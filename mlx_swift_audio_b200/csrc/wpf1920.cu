@@ -1,0 +1,343 @@
+// Warp-per-frame front end for n_fft = 1920, hop = 480 (S3Gen 24 kHz mel, S3GenMel.swift:43-102) on sm_100a.
+//
+// Why a second layout.  frontend.cu keeps LANE == FRAME: a CTA tile is 16 frames of 1920 points, its exchange buffer alone is
+// 123 KB, so one CTA of 16 warps per SM, four all-to-all CTA barriers per tile, 25 % occupancy and 49 % issue (0.465 ms for
+// 256 x 10 s, profiles/r01_frontend_s3gen_ncu.txt).  Here ONE WARP owns ONE FRAME and nothing is shared between warps:
+//   * 1920 = 60 x 32.  Stage A: lane n2 runs the real 60-point DFT of samples 32 n1 + n2 -- the 32 lanes read 32 consecutive
+//     samples, so the PCM comes straight from global memory as aligned 128-byte lines (the 4x frame overlap of a strip of
+//     consecutive frames is served by the L1 / L2), no shared-memory staging of PCM at all;
+//   * inter-stage twiddles and window values differ per LANE (not per warp), so they come from conflict-free shared-memory tables
+//     ([k1][lane] float2, [lane][60] read as float4) instead of immediates;
+//   * one exchange through the warp's own 8.4 KB of shared memory (row pitch 34 float2: 8-byte stores stride-1 across lanes, 16-byte
+//     loads at a lane pitch of 68 words, both conflict-free), __syncwarp only -- the kernel has NO CTA barrier after its prologue;
+//   * stage B: lane k1 (0..30) runs the complex 32-point DFT of row k1 -> bins k1 + 60 k2 (k2 < 16) and, mirrored, 1920 - k1 - 60 k2:
+//     every lane executes the same codelet (k1 = 0 with zero imaginary parts, k1 = 30 from the twiddled Nyquist value), lane 31 idles;
+//   * |X| (MUFU sqrt) or |X|^2 goes bin-major into the same shared memory; the mel projection runs over host-built balanced segments
+//     (build_wpf_mel: ~60 products per lane and frame for the 80-mel bank), then log / affine, and the (M, T') result of a strip of
+//     8 consecutive frames leaves as 32-byte row segments;
+//   * the frame is rotated by rot = pad_left mod 32 samples (x'[m] = x[(m + rot) mod 1920], window rotated alike) so that the 128-byte
+//     lines are aligned: a circular shift changes the phase of X[k] only, and only |X| is used.
+// Reflect / zero padded edge frames (4 of 500) are staged sample by sample through the padding index map (pad_index.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200audio.h"
+#include "codelets.h"
+#include "internal.h"
+#include "pad_index.cuh"
+
+#ifndef B2A_WPF_WARPS
+#define B2A_WPF_WARPS 16
+#endif
+// 1 = no staging of the (M, 8 frames) block: every frame's mel values go straight to their (M, T') rows as 4-byte stores (A/B switch)
+#ifndef B2A_WPF_DIRECT
+#define B2A_WPF_DIRECT 0
+#endif
+
+namespace b2a {
+namespace {
+
+constexpr int kN = 1920, kN1 = 60, kHop = 480, kBins = kN / 2 + 1, kStrip = 8;
+constexpr int kExPitch = 34;                      // float2 per exchange row (k1)
+constexpr int kExWords = 31 * kExPitch * 2;       // 2108 floats: rows k1 = 0..30; later the 961-bin spectrum
+constexpr int kPartWords = kWpfRounds * 32 + 4;   // segment sums + the zero slot
+constexpr int kStagePitch = kStrip + 1;
+constexpr int kStageWords = B2A_WPF_DIRECT ? 0 : kWpfRounds * 32 * kStagePitch;   // [m][frame of the strip]
+constexpr int kWarpWords = kExWords + kPartWords + kStageWords;
+static_assert(kWarpWords % 4 == 0 && kExWords % 4 == 0, "16-byte aligned warp regions");
+constexpr int kTableWords = kN + 2 * 30 * 32 + kWpfMelMaxWords;   // window, twiddles (k1 = 1..30), mel schedule
+
+__constant__ float2 c_wpf_tw[30 * 32];   // W_1920^{n2 k1} as (cos, sin of the negative angle), [k1 - 1][n2], k1 = 1..30
+
+struct WpfParams {
+  const float* x;
+  float* out;
+  const uint32_t* mel;
+  long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, total_strips;
+  int strips_per_clip, pad_mode, log_mode, post_affine, n_mels, rot, mel_words;
+  float log_floor, post_sub, post_div;
+  float window[kN];
+};
+
+B2A_DEV float wpf_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+B2A_DEV float wpf_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Edge frames: every sample through the padding index map into the warp's exchange buffer, in the order the interior path reads
+// global memory (buf[i] = frame sample (rot + i) mod 1920).  Out of line: the 64-bit index arithmetic stays out of the hot loop.
+__device__ __noinline__ void wpf_stage_edge(const float* __restrict__ xc, float* __restrict__ buf, long long p0, long long pad_left,
+                                            long long n_samples, long long n_eff, int pad_mode, int rot, int lane) {
+  for (int i = lane; i < kN; i += 32) {
+    int m = rot + i;
+    if (m >= kN) m -= kN;
+    buf[i] = fetch_padded(xc, p0 + m, pad_left, n_samples, n_eff, pad_mode);
+  }
+}
+
+template <int NW, bool MAG>
+__global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_constant__ WpfParams prm) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_win = smem;                                              // [lane][60]: window of the lane's samples (rot + 32 n1 + lane) mod 1920
+  float2* s_tw = reinterpret_cast<float2*>(smem + kN);              // [k1 - 1][lane]
+  uint32_t* s_mel = reinterpret_cast<uint32_t*>(smem + kN + 2 * 30 * 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* s_ex = smem + kTableWords + warp * kWarpWords;
+  float* s_part = s_ex + kExWords;
+  float* s_stage = s_part + kPartWords;
+  const int rot = prm.rot;
+
+  // ---- tables (once per persistent CTA) ----
+  // window: warp-uniform reads of the kernel parameter (a lane-dependent index into the parameter space is served one lane at a time:
+  // measured 16 us for the 1920 taps, 4 % of the 256 x 10 s launch); sample m of the frame belongs to lane (m - rot) mod 32, slot (m - rot) / 32
+  for (int m = warp; m < kN; m += NW) {
+    const float v = prm.window[m];
+    int i = m - rot;
+    if (i < 0) i += kN;
+    if (lane == 0) s_win[(i & 31) * kN1 + (i >> 5)] = v;
+  }
+  for (int i = tid; i < 30 * 32; i += NW * 32) s_tw[i] = c_wpf_tw[i];
+  for (int i = tid; i < prm.mel_words; i += NW * 32) s_mel[i] = __ldg(prm.mel + i);
+  __syncthreads();
+
+  const int M = prm.n_mels, rounds = int(s_mel[1]);
+  if (lane < 4) s_part[rounds * 32 + lane] = 0.0f;   // the zero slot of the segment table (never written by a round)
+  __syncwarp();
+  const int4* s_fin = reinterpret_cast<const int4*>(s_mel + s_mel[11]);
+  const uint32_t* s_start = s_mel + s_mel[10];
+  const int log_mode = prm.log_mode;
+  const float log_floor = prm.log_floor;
+  const bool affine = prm.post_affine != 0;
+  const long long n_frames = prm.n_frames, n_samples = prm.n_samples;
+  const int spc = prm.strips_per_clip;
+  // sample n1 = 59 of the lanes whose rotated position runs past the frame wraps to the frame's first samples
+  const int last_off = lane >= 32 - rot ? 59 * 32 - kN : 59 * 32;
+  const int k1 = lane < 31 ? lane : 30;   // (lane 31 repeats row 30 and stores nothing)
+
+  for (long long s = (long long)blockIdx.x * NW + warp; s < prm.total_strips; s += (long long)gridDim.x * NW) {
+    const long long clip = s / spc;
+    const int t0 = int(s - clip * spc) * kStrip;
+    const int nf = int(n_frames - t0 < kStrip ? n_frames - t0 : kStrip);
+    const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
+    float* __restrict__ oc = prm.out + clip * prm.out_clip_stride;
+    for (int f = 0; f < nf; ++f) {
+      // ---- stage A: lane n2 = real 60-point DFT over samples 32 n1 + n2 of the rotated frame ----
+      const long long p0 = (long long)(t0 + f) * kHop, j0 = p0 - prm.pad_left;
+      float in[kN1];
+      if (j0 >= 0 && j0 + kN <= n_samples) {
+        const float* __restrict__ p = xc + j0 + rot + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < kN1 - 1; ++n1) in[n1] = __ldg(p + 32 * n1);
+        in[kN1 - 1] = __ldg(p + last_off);
+      } else {
+        wpf_stage_edge(xc, s_ex, p0, prm.pad_left, n_samples, prm.n_eff, prm.pad_mode, rot, lane);
+        __syncwarp();
+#pragma unroll
+        for (int n1 = 0; n1 < kN1; ++n1) in[n1] = s_ex[32 * n1 + lane];
+        __syncwarp();
+      }
+      {
+        const float4* wl = reinterpret_cast<const float4*>(s_win + lane * kN1);
+#pragma unroll
+        for (int q = 0; q < kN1 / 4; ++q) {
+          const float4 w4 = wl[q];
+          in[4 * q] *= w4.x; in[4 * q + 1] *= w4.y; in[4 * q + 2] *= w4.z; in[4 * q + 3] *= w4.w;
+        }
+      }
+      float2* ex = reinterpret_cast<float2*>(s_ex);
+      {
+        float yr[kN1 / 2 + 1], yi[kN1 / 2 + 1];
+        b2a_rdft60(in, yr, yi);
+        ex[lane] = make_float2(yr[0], 0.0f);
+#pragma unroll
+        for (int k = 1; k < 30; ++k) {
+          const float2 tw = s_tw[(k - 1) * 32 + lane];
+          ex[k * kExPitch + lane] = make_float2(yr[k] * tw.x - yi[k] * tw.y, yr[k] * tw.y + yi[k] * tw.x);
+        }
+        const float2 tw = s_tw[29 * 32 + lane];
+        ex[30 * kExPitch + lane] = make_float2(yr[30] * tw.x, yr[30] * tw.y);
+      }
+      __syncwarp();
+
+      // ---- stage B: lane k1 = complex 32-point DFT of row k1; bins k1 + 60 k2 and their mirror images ----
+      {
+        float xr[32], xi[32], ur[32], ui[32];
+        const float4* zr = reinterpret_cast<const float4*>(ex + k1 * kExPitch);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 v = zr[q];
+          xr[2 * q] = v.x; xi[2 * q] = v.y; xr[2 * q + 1] = v.z; xi[2 * q + 1] = v.w;
+        }
+        __syncwarp();   // every lane holds its row: the buffer becomes the spectrum
+        b2a_cdft32(xr, xi, ur, ui);
+        float* pd = s_ex + lane;             // bin lane + 60 k2
+        float* pm = s_ex + kN - lane;        // bin 1920 - lane - 60 k2
+        const bool direct = lane < 31, mirror = lane >= 1 && lane < 30;
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) {
+          float pw = ur[k2] * ur[k2] + ui[k2] * ui[k2];
+          if (MAG) pw = wpf_sqrt(pw);
+          if (k2 < 16) {
+            if (direct) pd[60 * k2] = pw;
+          } else if (k2 == 16) {
+            if (lane == 0) s_ex[960] = pw;          // the Nyquist bin belongs to row 0
+            else if (mirror) pm[-60 * 16] = pw;
+          } else {
+            if (mirror) pm[-60 * k2] = pw;
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---- mel: per-lane segment sums (four products per step: 16-byte loads of weights and bins), then the <= 4 segments of a filter ----
+      for (int r = 0; r < rounds; ++r) {
+        const int len4 = int(s_mel[2 + r]);
+        const float4* __restrict__ w = reinterpret_cast<const float4*>(s_mel + s_mel[6 + r]) + lane;
+        const float4* __restrict__ pp = reinterpret_cast<const float4*>(s_ex + s_start[r * 32 + lane]);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 2
+        for (int g = 0; g < len4; ++g) {
+          const float4 wv = w[g * 32], pv = pp[g];
+          a0 = fmaf(wv.x, pv.x, a0);
+          a1 = fmaf(wv.y, pv.y, a1);
+          a2 = fmaf(wv.z, pv.z, a2);
+          a3 = fmaf(wv.w, pv.w, a3);
+        }
+        s_part[r * 32 + lane] = (a0 + a1) + (a2 + a3);
+      }
+      __syncwarp();
+      for (int q = 0; q < kWpfRounds; ++q) {
+        const int m = lane + 32 * q;
+        if (m < M) {
+          const int4 fi = s_fin[m];
+          float v = ((s_part[fi.x] + s_part[fi.y]) + s_part[fi.z]) + s_part[fi.w];
+          if (log_mode == LOG_LN) v = wpf_lg2(fmaxf(v, log_floor)) * 0.69314718055994531f;
+          else if (log_mode == LOG_LOG10) v = wpf_lg2(fmaxf(v, log_floor)) * 0.30102999566398120f;
+          else if (log_mode == LOG_DB20) v = wpf_lg2(fmaxf(v, log_floor)) * 6.0205999132796239f;
+          if (affine) v = (v - prm.post_sub) / prm.post_div;
+          if (B2A_WPF_DIRECT) oc[(long long)m * n_frames + t0 + f] = v;
+          else s_stage[m * kStagePitch + f] = v;
+        }
+      }
+      // (the next frame's first shared-memory write -- exchange rows or an edge frame -- follows the barrier above: every lane is
+      // done reading the spectrum; s_part is rewritten only after the next frame's own barriers)
+    }
+    // ---- the strip's (M, 8 frames) block leaves as 32-byte row segments ----
+    if (!B2A_WPF_DIRECT) {
+      __syncwarp();
+      const int fr = lane & (kStrip - 1);
+      float* o = oc + t0 + fr;
+      if (fr < nf)
+        for (int m = lane / kStrip; m < M; m += 32 / kStrip) o[(long long)m * n_frames] = s_stage[m * kStagePitch + fr];
+      __syncwarp();
+    }
+  }
+}
+
+int cuda_fail(cudaError_t e, const char* what, std::string* err) {
+  if (err) *err = std::string(what) + ": " + cudaGetErrorString(e);
+  return B2A_E_CUDA;
+}
+
+template <int NW, bool MAG>
+int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
+  constexpr size_t smem = sizeof(float) * size_t(kTableWords + NW * kWarpWords);
+  struct DevInfo { std::atomic<int> ready{0}; int n_sm = 0; };
+  static DevInfo infos[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) {
+    if (err) *err = "device index out of range";
+    return B2A_E_CUDA;
+  }
+  DevInfo& di = infos[dev];
+  cudaError_t e;
+  if (!di.ready.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!di.ready.load(std::memory_order_relaxed)) {
+      if ((e = cudaFuncSetAttribute(wpf1920_kernel<NW, MAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
+        return cuda_fail(e, "cudaFuncSetAttribute", err);
+      int n_sm = 148;
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      di.n_sm = n_sm;
+      di.ready.store(1, std::memory_order_release);
+    }
+  }
+  const long long blocks = std::min<long long>((prm.total_strips + NW - 1) / NW, di.n_sm);   // one persistent CTA per SM
+  wpf1920_kernel<NW, MAG><<<unsigned(blocks), NW * 32, smem, st>>>(prm);
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "wpf1920_kernel launch", err);
+  return B2A_OK;
+}
+
+}  // namespace
+
+int init_wpf1920_tables(std::string* err) {
+  std::vector<float2> t(30 * 32);
+  for (int k1 = 1; k1 <= 30; ++k1)
+    for (int n2 = 0; n2 < 32; ++n2) {
+      const double a = -2.0 * M_PI * double((n2 * k1) % kN) / double(kN);
+      t[size_t(k1 - 1) * 32 + n2] = make_float2(float(cos(a)), float(sin(a)));
+    }
+  const cudaError_t e = cudaMemcpyToSymbol(c_wpf_tw, t.data(), t.size() * sizeof(float2));
+  if (e != cudaSuccess) return cuda_fail(e, "twiddle upload", err);
+  return B2A_OK;
+}
+
+// On by default; B2A_WPF1920=0 in the environment or b2a_debug_wpf1920(0) keeps the tiled lane == frame kernel of frontend.cu (A/B switch)
+static int g_wpf_enabled = -1;
+void wpf1920_enable(int on) { g_wpf_enabled = on ? 1 : 0; }
+
+bool wpf1920_applicable(const FrontendArgs& a) {
+  if (g_wpf_enabled < 0) {
+    const char* v = getenv("B2A_WPF1920");
+    g_wpf_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return g_wpf_enabled == 1 && a.n_fft == kN && a.hop == kHop && a.win_len == kN && a.pre_mode == PRE_NONE && a.clip_tab == nullptr && a.bank.wpf_mel != nullptr &&
+         a.bank.n_mels <= kWpfRounds * 32 && !a.whisper_norm && !a.out_f16 && a.out_mode == OUT_MT &&
+         a.n_frames > 0 && a.n_frames <= 0x7fffffffLL && a.batch > 0;
+}
+
+int launch_wpf1920(const FrontendArgs& a, void* stream, int* launches, std::string* err) {
+  WpfParams prm;
+  prm.x = a.x;
+  prm.out = a.out;
+  prm.mel = a.bank.wpf_mel;
+  prm.mel_words = a.bank.wpf_words;
+  prm.clip_stride = a.n_samples;
+  prm.n_samples = a.n_samples;
+  prm.n_eff = a.n_samples + a.zero_tail;
+  prm.pad_left = a.pad_left;
+  prm.n_frames = a.n_frames;
+  prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels;
+  prm.strips_per_clip = int((a.n_frames + kStrip - 1) / kStrip);
+  prm.total_strips = (long long)prm.strips_per_clip * a.batch;
+  prm.pad_mode = a.pad_mode;
+  prm.log_mode = a.log_mode;
+  prm.post_affine = a.post_affine;
+  prm.n_mels = a.bank.n_mels;
+  prm.rot = int(((a.pad_left % 32) + 32) % 32);
+  prm.log_floor = a.log_floor;
+  prm.post_sub = a.post_sub;
+  prm.post_div = a.post_div;
+  for (int o = 0; o < kN; ++o) prm.window[o] = a.window[o];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rc = a.spec_mode == SPEC_MAGNITUDE ? launch_t<B2A_WPF_WARPS, true>(prm, st, err) : launch_t<B2A_WPF_WARPS, false>(prm, st, err);
+  if (rc == B2A_OK) *launches += 1;
+  return rc;
+}
+
+}  // namespace b2a

@@ -1,0 +1,100 @@
+"""GPU parity tests of the warp-per-frame n_fft 1920 front end (csrc/wpf1920.cu; S3GenMel.swift:43-102) against the oracle, next to the
+tiled lane == frame kernel it replaces for equal-length batches (b2a_debug_wpf1920 switches between the two): frame counts around the
+8-frame strips, clips shorter than the reflect pad, device buffers that are not 128-byte aligned, the power / dB / normalised branches
+through a 1920-point voice-encoder configuration (rotation 0), and the launch counter (one kernel per call)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import reference_dsp as R
+from tests import synth
+from tests.test_gpu_parity import assert_feat_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api(ctx):
+    from mlx_swift_audio_b200 import api as A
+    return A
+
+
+@pytest.fixture()
+def both_kernels(ctx):
+    """Runs fn() under the warp-per-frame kernel and under the tiled kernel; leaves the default (warp-per-frame) switched on."""
+    def run(fn):
+        try:
+            ctx.lib.b2a_debug_wpf1920(1)
+            new = fn()
+            ctx.lib.b2a_debug_wpf1920(0)
+            old = fn()
+        finally:
+            ctx.lib.b2a_debug_wpf1920(1)
+        return new, old
+    return run
+
+
+# frames = 1 + n // 480 for n >= 721 (pad 720 each side): 2, 7, 8, 9, 16, 17, 25 frames and two long clips
+@pytest.mark.parametrize("n", [721, 480 * 6 + 5, 480 * 7, 480 * 8 + 479, 480 * 15 + 1, 480 * 16, 480 * 24 + 100, 24000 * 2 + 17, 24000 * 3])
+def test_s3gen_mel_strip_boundaries(api, ctx, both_kernels, n):
+    x = synth.pcm(3, n, sample_rate=24000, seed=3001)
+    want = R.s3gen_mel_spectrogram(x)
+    new, old = both_kernels(lambda: api.s3genMelSpectrogram(x, ctx=ctx))
+    assert new.shape == want.shape == old.shape
+    assert_feat_close(new, want, what=f"s3gen mel (warp per frame), n = {n}")
+    assert_feat_close(old, want, what=f"s3gen mel (tiled), n = {n}")
+
+
+@pytest.mark.parametrize("n", [600 + 61, 700, 900, 1441, 1920])
+def test_s3gen_mel_short_clips_truncated_reflection(api, ctx, n):
+    # reflectPad2D truncates the reflection for clips of <= pad samples (S3GenMel.swift:17-25): every frame is an edge frame
+    x = synth.pcm(2, n, sample_rate=24000, seed=3002, zero_tail_frac=0.0)
+    want = R.s3gen_mel_spectrogram(x)
+    got = api.s3genMelSpectrogram(x, ctx=ctx)
+    assert_feat_close(got, want, what=f"s3gen mel short clip {n}")
+
+
+def test_one_kernel_per_call_and_batch_invariance(api, ctx):
+    x = synth.pcm(37, 24000 + 1000, sample_rate=24000, seed=3003)
+    before = ctx.launch_count
+    got = api.s3genMelSpectrogram(x, ctx=ctx)
+    assert ctx.launch_count - before == 1, "the S3Gen mel is one kernel launch"
+    for b in (0, 17, 36):
+        alone = api.s3genMelSpectrogram(x[b], ctx=ctx)
+        assert np.array_equal(alone, got[b]), "a clip's features do not depend on the batch around it"
+    assert np.array_equal(api.s3genMelSpectrogram(x, ctx=ctx), got), "run-to-run bit identical"
+
+
+def test_unaligned_device_buffers(api, ctx):
+    torch = pytest.importorskip("torch")
+    n = 24000 + 333
+    x = synth.pcm(4, n, sample_rate=24000, seed=3004)
+    want = R.s3gen_mel_spectrogram(x)
+    for shift in (0, 1, 3, 16):
+        buf = torch.zeros(4 * n + 64, dtype=torch.float32, device="cuda")
+        view = buf[shift:shift + 4 * n].view(4, n)
+        view.copy_(torch.from_numpy(x))
+        got = api.s3genMelSpectrogram(view, ctx=ctx)
+        assert_feat_close(got.cpu().numpy(), want, what=f"s3gen mel, device buffer shifted by {shift} floats")
+
+
+@pytest.mark.parametrize("branch", ["amp", "db", "db_normalized"])
+def test_voice_encoder_config_with_1920_point_frames(api, ctx, both_kernels, branch):
+    # VoiceEncoderMelspec.swift:17-68 with nFft 1920 / hop 480: centre pad 960 (rotation 0), power spectrum, 40 mels, no log / dB / normalised
+    from mlx_swift_audio_b200 import _lib as L
+    cfg = L.VoiceEncConfig()
+    ctx.lib.b2a_voice_enc_config_default(C.byref(cfg))
+    cfg.n_fft, cfg.hop_size, cfg.win_size, cfg.sample_rate = 1920, 480, 1920, 24000
+    kw = dict(n_fft=1920, hop_size=480, win_size=1920, sample_rate=24000)
+    if branch != "amp":
+        cfg.mel_type_db = 1
+        kw["mel_type"] = "db"
+    if branch == "db_normalized":
+        cfg.normalized_mels = 1
+        kw["normalized_mels"] = True
+    x = synth.pcm(3, 24000 + 77, sample_rate=24000, seed=3005)
+    want = np.stack([R.voice_encoder_melspectrogram(c, **kw) for c in x])
+    new, old = both_kernels(lambda: api.voiceEncoderMelspectrogram(x, config=cfg, ctx=ctx))
+    assert_feat_close(new, want, what=f"voice encoder 1920 ({branch}), warp per frame")
+    assert_feat_close(old, want, what=f"voice encoder 1920 ({branch}), tiled")

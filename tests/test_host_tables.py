@@ -276,3 +276,31 @@ def test_resample_poly_filter_is_scipys_design():
         full = np.convolve(xu, h.astype(np.float64))
         got = full[pre.value * dn.value::dn.value][:new_t]
         assert np.abs(got - want).max() <= 1e-6
+
+
+@pytest.mark.parametrize("args", [(24000, 1920, 80, 0.0, 8000.0), (24000, 1920, 96, 0.0, 8000.0), (24000, 1920, 40, 0.0, 8000.0),
+                                  (24000, 1920, 33, 0.0, 12000.0)])
+def test_wpf_mel_schedule_equals_the_dense_bank(built_lib, api, args):
+    """Mel schedule of the warp-per-frame n_fft 1920 kernel (csrc/wpf1920.cu, build_wpf_mel): the per-lane segment sums (four products per step from a
+    16-byte aligned start bin), interpreted on the host exactly as the kernel runs them, equal the dense filterbank product (the segments only regroup the additions)."""
+    import ctypes as C
+    bank = np.ascontiguousarray(R.mel_filters(*args), np.float32)          # (M, 961)
+    rng = np.random.default_rng(7)
+    for p in (rng.random(961).astype(np.float32) * 100, np.ones(961, np.float32), np.eye(961, dtype=np.float32)[960],
+              np.eye(961, dtype=np.float32)[0]):
+        out = np.zeros(args[2], np.float32)
+        fp = C.POINTER(C.c_float)
+        words = built_lib.b2a_debug_wpf_mel_apply(bank.ctypes.data_as(fp), args[2], 961, 0, p.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        assert 0 < (words & 0xffff) <= 3584
+        assert words >> 16 == 0, "every quarter-warp reads eight different 16-byte bank groups"
+        want = bank.astype(np.float64) @ p.astype(np.float64)
+        assert np.abs(out - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+
+
+def test_wpf_mel_schedule_rejects_what_does_not_fit(built_lib):
+    import ctypes as C
+    fp = C.POINTER(C.c_float)
+    bank = np.ascontiguousarray(R.mel_filters(24000, 1920, 128, 0.0, 8000.0), np.float32)   # more than 96 filters: the tiled kernel keeps it
+    p = np.ones(961, np.float32)
+    out = np.zeros(128, np.float32)
+    assert built_lib.b2a_debug_wpf_mel_apply(bank.ctypes.data_as(fp), 128, 961, 0, p.ctypes.data_as(fp), out.ctypes.data_as(fp)) == -1
