@@ -13,8 +13,11 @@
 //   * stage B: lane k1 (0..30) runs the complex 32-point DFT of row k1 -> bins k1 + 60 k2 (k2 < 16) and, mirrored, 1920 - k1 - 60 k2:
 //     every lane executes the same codelet (k1 = 0 with zero imaginary parts, k1 = 30 from the twiddled Nyquist value), lane 31 idles;
 //   * |X| (MUFU sqrt) or |X|^2 goes bin-major into the same shared memory; the mel projection runs over host-built balanced segments
-//     (build_wpf_mel: ~60 products per lane and frame for the 80-mel bank), then log / affine, and the (M, T') result of a strip of
-//     8 consecutive frames leaves as 32-byte row segments;
+//     (build_wpf_mel: 17 steps of four products per lane and frame for the 80-mel bank, 16-byte loads, conflict-free), then log /
+//     affine and 4-byte stores into the (M, T') rows;
+//   * work units are strips of 8 consecutive frames of one clip, dealt round-robin to the warps of the 148 persistent CTAs (one
+//     contiguous range of frames per warp balances the tail better but measured 7 % slower: 2368 streams 104 KB apart keep as many
+//     DRAM rows open; requesting the next frame's samples ahead of the mel projection spills at 128 registers and measured 7 % slower);
 //   * the frame is rotated by rot = pad_left mod 32 samples (x'[m] = x[(m + rot) mod 1920], window rotated alike) so that the 128-byte
 //     lines are aligned: a circular shift changes the phase of X[k] only, and only |X| is used.
 // Reflect / zero padded edge frames (4 of 500) are staged sample by sample through the padding index map (pad_index.cuh).
@@ -36,9 +39,10 @@
 #ifndef B2A_WPF_WARPS
 #define B2A_WPF_WARPS 16
 #endif
-// 1 = no staging of the (M, 8 frames) block: every frame's mel values go straight to their (M, T') rows as 4-byte stores (A/B switch)
-#ifndef B2A_WPF_DIRECT
-#define B2A_WPF_DIRECT 0
+// inter-stage twiddles are loaded in batches of this many, all in flight before the first complex multiply of the batch
+// (measured on 256 x 10 s: 1 -> 0.368 ms, 6 -> 0.362 ms, 10 -> 0.359 ms)
+#ifndef B2A_WPF_TW_BATCH
+#define B2A_WPF_TW_BATCH 10
 #endif
 
 namespace b2a {
@@ -48,9 +52,7 @@ constexpr int kN = 1920, kN1 = 60, kHop = 480, kBins = kN / 2 + 1, kStrip = 8;
 constexpr int kExPitch = 34;                      // float2 per exchange row (k1)
 constexpr int kExWords = 31 * kExPitch * 2;       // 2108 floats: rows k1 = 0..30; later the 961-bin spectrum
 constexpr int kPartWords = kWpfRounds * 32 + 4;   // segment sums + the zero slot
-constexpr int kStagePitch = kStrip + 1;
-constexpr int kStageWords = B2A_WPF_DIRECT ? 0 : kWpfRounds * 32 * kStagePitch;   // [m][frame of the strip]
-constexpr int kWarpWords = kExWords + kPartWords + kStageWords;
+constexpr int kWarpWords = kExWords + kPartWords;
 static_assert(kWarpWords % 4 == 0 && kExWords % 4 == 0, "16-byte aligned warp regions");
 constexpr int kTableWords = kN + 2 * 30 * 32 + kWpfMelMaxWords;   // window, twiddles (k1 = 1..30), mel schedule
 
@@ -97,7 +99,6 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* s_ex = smem + kTableWords + warp * kWarpWords;
   float* s_part = s_ex + kExWords;
-  float* s_stage = s_part + kPartWords;
   const int rot = prm.rot;
 
   // ---- tables (once per persistent CTA) ----
@@ -162,13 +163,20 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
         float yr[kN1 / 2 + 1], yi[kN1 / 2 + 1];
         b2a_rdft60(in, yr, yi);
         ex[lane] = make_float2(yr[0], 0.0f);
+        constexpr int CH = B2A_WPF_TW_BATCH;
 #pragma unroll
-        for (int k = 1; k < 30; ++k) {
-          const float2 tw = s_tw[(k - 1) * 32 + lane];
-          ex[k * kExPitch + lane] = make_float2(yr[k] * tw.x - yi[k] * tw.y, yr[k] * tw.y + yi[k] * tw.x);
+        for (int c = 0; c < 30; c += CH) {
+          float2 tw[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (c + j < 30) tw[j] = s_tw[(c + j) * 32 + lane];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int k = c + j + 1;
+            if (k < 30) ex[k * kExPitch + lane] = make_float2(yr[k] * tw[j].x - yi[k] * tw[j].y, yr[k] * tw[j].y + yi[k] * tw[j].x);
+            else if (k == 30) ex[30 * kExPitch + lane] = make_float2(yr[30] * tw[j].x, yr[30] * tw[j].y);
+          }
         }
-        const float2 tw = s_tw[29 * 32 + lane];
-        ex[30 * kExPitch + lane] = make_float2(yr[30] * tw.x, yr[30] * tw.y);
       }
       __syncwarp();
 
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
         const float4* __restrict__ w = reinterpret_cast<const float4*>(s_mel + s_mel[6 + r]) + lane;
         const float4* __restrict__ pp = reinterpret_cast<const float4*>(s_ex + s_start[r * 32 + lane]);
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        // (four steps per trip with all eight loads ahead of the products measured slower: 0.3745 vs 0.3679 ms)
 #pragma unroll 2
         for (int g = 0; g < len4; ++g) {
           const float4 wv = w[g * 32], pv = pp[g];
@@ -228,21 +237,13 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
           else if (log_mode == LOG_LOG10) v = wpf_lg2(fmaxf(v, log_floor)) * 0.30102999566398120f;
           else if (log_mode == LOG_DB20) v = wpf_lg2(fmaxf(v, log_floor)) * 6.0205999132796239f;
           if (affine) v = (v - prm.post_sub) / prm.post_div;
-          if (B2A_WPF_DIRECT) oc[(long long)m * n_frames + t0 + f] = v;
-          else s_stage[m * kStagePitch + f] = v;
+          // (M, T'): 4-byte stores; the eight frames of a strip fill whole 32-byte sectors in the L2 within microseconds (staging the
+          // strip's (M, 8) block in shared memory and writing 32-byte segments measured the same: 0.3716 vs 0.3694 ms)
+          oc[(long long)m * n_frames + t0 + f] = v;
         }
       }
       // (the next frame's first shared-memory write -- exchange rows or an edge frame -- follows the barrier above: every lane is
       // done reading the spectrum; s_part is rewritten only after the next frame's own barriers)
-    }
-    // ---- the strip's (M, 8 frames) block leaves as 32-byte row segments ----
-    if (!B2A_WPF_DIRECT) {
-      __syncwarp();
-      const int fr = lane & (kStrip - 1);
-      float* o = oc + t0 + fr;
-      if (fr < nf)
-        for (int m = lane / kStrip; m < M; m += 32 / kStrip) o[(long long)m * n_frames] = s_stage[m * kStagePitch + fr];
-      __syncwarp();
     }
   }
 }
