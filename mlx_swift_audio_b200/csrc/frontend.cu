@@ -1794,7 +1794,7 @@ int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::str
     if (a.pre_mode == PRE_NONE && spec == SK_CPLX) return launch_plan<Plan512, PRE_NONE, SK_CPLX>(a, st, launches, err);
   }
   if (a.n_fft == 1920 && a.hop == 480 && a.win_len == 1920 && a.pre_mode == PRE_NONE) {
-    // equal-length mel batches: the warp-per-frame kernel (wpf1920.cu); B2A_WPF1920=0 / b2a_debug_wpf1920(0) keep the tiled kernel
+    // mel batches (equal lengths or ragged): the warp-per-frame kernel (wpf1920.cu); B2A_WPF1920=0 / b2a_debug_wpf1920(0) keep the tiled kernel
     if (spec != SK_CPLX && wpf1920_applicable(a)) return launch_wpf1920(a, stream, launches, err);
     // S3Gen 24 kHz mel (S3GenMel.swift:43-102): magnitude spectrum, ln, (M, T') -- compile-time post-processing keeps the store code short
     if (!ragged && spec == SK_MAG && a.bank.steps != nullptr && a.log_mode == LOG_LN && !a.whisper_norm && !a.post_affine && a.out_mode == OUT_MT)

@@ -48,12 +48,13 @@
 namespace b2a {
 namespace {
 
-constexpr int kN = 1920, kN1 = 60, kHop = 480, kBins = kN / 2 + 1, kStrip = 8;
+constexpr int kN = 1920, kN1 = 60, kHop = 480, kStrip = 8, kRaggedTile = 16;
 constexpr int kExPitch = 34;                      // float2 per exchange row (k1)
 constexpr int kExWords = 31 * kExPitch * 2;       // 2108 floats: rows k1 = 0..30; later the 961-bin spectrum
 constexpr int kPartWords = kWpfRounds * 32 + 4;   // segment sums + the zero slot
 constexpr int kWarpWords = kExWords + kPartWords;
 static_assert(kWarpWords % 4 == 0 && kExWords % 4 == 0, "16-byte aligned warp regions");
+static_assert(kPlanShapes[2].n_fft == kN && kPlanShapes[2].frame_tile == kRaggedTile, "ragged work units are the tile table's 16-frame tiles of the 1920-point plan");
 constexpr int kTableWords = kN + 2 * 30 * 32 + kWpfMelMaxWords;   // window, twiddles (k1 = 1..30), mel schedule
 
 __constant__ float2 c_wpf_tw[30 * 32];   // W_1920^{n2 k1} as (cos, sin of the negative angle), [k1 - 1][n2], k1 = 1..30
@@ -62,7 +63,8 @@ struct WpfParams {
   const float* x;
   float* out;
   const uint32_t* mel;
-  long long clip_stride, n_samples, n_eff, pad_left, n_frames, out_clip_stride, total_strips;
+  const int4* tile_tab;   // ragged batches: work unit g = (clip, 16-frame tile of the clip, the clip's n_samples, n_frames); null = equal lengths
+  long long clip_stride, n_samples, zero_tail, pad_left, n_frames, out_clip_stride, total_strips;
   int strips_per_clip, pad_mode, log_mode, post_affine, n_mels, rot, mel_words;
   float log_floor, post_sub, post_div;
   float window[kN];
@@ -90,7 +92,7 @@ __device__ __noinline__ void wpf_stage_edge(const float* __restrict__ xc, float*
   }
 }
 
-template <int NW, bool MAG>
+template <int NW, bool MAG, bool RAGGED>
 __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_constant__ WpfParams prm) {
   extern __shared__ __align__(16) float smem[];
   float* s_win = smem;                                              // [lane][60]: window of the lane's samples (rot + 32 n1 + lane) mod 1920
@@ -122,16 +124,31 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
   const int log_mode = prm.log_mode;
   const float log_floor = prm.log_floor;
   const bool affine = prm.post_affine != 0;
-  const long long n_frames = prm.n_frames, n_samples = prm.n_samples;
+  const long long n_frames = prm.n_frames;   // row stride of the (M, T') output
   const int spc = prm.strips_per_clip;
   // sample n1 = 59 of the lanes whose rotated position runs past the frame wraps to the frame's first samples
   const int last_off = lane >= 32 - rot ? 59 * 32 - kN : 59 * 32;
   const int k1 = lane < 31 ? lane : 30;   // (lane 31 repeats row 30 and stores nothing)
 
+  // Work units: strips of kStrip consecutive frames of one clip (equal lengths), or the 16-frame tiles of the ragged batch's tile table
+  // (tile_table_kernel of frontend.cu: one 16-byte entry per unit carries the clip's own length and frame count); output strides stay
+  // those of the longest clip.
+  long long n_frames_c = n_frames, n_samples = prm.n_samples;
   for (long long s = (long long)blockIdx.x * NW + warp; s < prm.total_strips; s += (long long)gridDim.x * NW) {
-    const long long clip = s / spc;
-    const int t0 = int(s - clip * spc) * kStrip;
-    const int nf = int(n_frames - t0 < kStrip ? n_frames - t0 : kStrip);
+    long long clip;
+    int t0;
+    if (RAGGED) {
+      const int4 u = __ldg(prm.tile_tab + s);
+      clip = u.x;
+      t0 = u.y * kRaggedTile;
+      n_samples = u.z;
+      n_frames_c = u.w;
+    } else {
+      clip = s / spc;
+      t0 = int(s - clip * spc) * kStrip;
+    }
+    const int unit = RAGGED ? kRaggedTile : kStrip;
+    const int nf = int(n_frames_c - t0 < unit ? n_frames_c - t0 : unit);
     const float* __restrict__ xc = prm.x + clip * prm.clip_stride;
     float* __restrict__ oc = prm.out + clip * prm.out_clip_stride;
     for (int f = 0; f < nf; ++f) {
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
         for (int n1 = 0; n1 < kN1 - 1; ++n1) in[n1] = __ldg(p + 32 * n1);
         in[kN1 - 1] = __ldg(p + last_off);
       } else {
-        wpf_stage_edge(xc, s_ex, p0, prm.pad_left, n_samples, prm.n_eff, prm.pad_mode, rot, lane);
+        wpf_stage_edge(xc, s_ex, p0, prm.pad_left, n_samples, n_samples + prm.zero_tail, prm.pad_mode, rot, lane);
         __syncwarp();
 #pragma unroll
         for (int n1 = 0; n1 < kN1; ++n1) in[n1] = s_ex[32 * n1 + lane];
@@ -253,7 +270,7 @@ int cuda_fail(cudaError_t e, const char* what, std::string* err) {
   return B2A_E_CUDA;
 }
 
-template <int NW, bool MAG>
+template <int NW, bool MAG, bool RAGGED>
 int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
   constexpr size_t smem = sizeof(float) * size_t(kTableWords + NW * kWarpWords);
   struct DevInfo { std::atomic<int> ready{0}; int n_sm = 0; };
@@ -270,7 +287,7 @@ int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
   if (!di.ready.load(std::memory_order_acquire)) {
     std::lock_guard<std::mutex> lk(mu);
     if (!di.ready.load(std::memory_order_relaxed)) {
-      if ((e = cudaFuncSetAttribute(wpf1920_kernel<NW, MAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
+      if ((e = cudaFuncSetAttribute(wpf1920_kernel<NW, MAG, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
         return cuda_fail(e, "cudaFuncSetAttribute", err);
       int n_sm = 148;
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -279,7 +296,7 @@ int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
     }
   }
   const long long blocks = std::min<long long>((prm.total_strips + NW - 1) / NW, di.n_sm);   // one persistent CTA per SM
-  wpf1920_kernel<NW, MAG><<<unsigned(blocks), NW * 32, smem, st>>>(prm);
+  wpf1920_kernel<NW, MAG, RAGGED><<<unsigned(blocks), NW * 32, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "wpf1920_kernel launch", err);
   return B2A_OK;
 }
@@ -307,7 +324,7 @@ bool wpf1920_applicable(const FrontendArgs& a) {
     const char* v = getenv("B2A_WPF1920");
     g_wpf_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
   }
-  return g_wpf_enabled == 1 && a.n_fft == kN && a.hop == kHop && a.win_len == kN && a.pre_mode == PRE_NONE && a.clip_tab == nullptr && a.bank.wpf_mel != nullptr &&
+  return g_wpf_enabled == 1 && a.n_fft == kN && a.hop == kHop && a.win_len == kN && a.pre_mode == PRE_NONE && a.bank.wpf_mel != nullptr && (a.clip_tab == nullptr || (a.tile_tab != nullptr && a.total_tiles > 0)) &&
          a.bank.n_mels <= kWpfRounds * 32 && !a.whisper_norm && !a.out_f16 && a.out_mode == OUT_MT &&
          a.n_frames > 0 && a.n_frames <= 0x7fffffffLL && a.batch > 0;
 }
@@ -320,12 +337,13 @@ int launch_wpf1920(const FrontendArgs& a, void* stream, int* launches, std::stri
   prm.mel_words = a.bank.wpf_words;
   prm.clip_stride = a.n_samples;
   prm.n_samples = a.n_samples;
-  prm.n_eff = a.n_samples + a.zero_tail;
+  prm.zero_tail = a.zero_tail;
   prm.pad_left = a.pad_left;
   prm.n_frames = a.n_frames;
   prm.out_clip_stride = a.n_frames * (long long)a.bank.n_mels;
   prm.strips_per_clip = int((a.n_frames + kStrip - 1) / kStrip);
-  prm.total_strips = (long long)prm.strips_per_clip * a.batch;
+  prm.total_strips = a.clip_tab ? (long long)a.total_tiles : (long long)prm.strips_per_clip * a.batch;
+  prm.tile_tab = static_cast<const int4*>(a.tile_tab);
   prm.pad_mode = a.pad_mode;
   prm.log_mode = a.log_mode;
   prm.post_affine = a.post_affine;
@@ -336,7 +354,10 @@ int launch_wpf1920(const FrontendArgs& a, void* stream, int* launches, std::stri
   prm.post_div = a.post_div;
   for (int o = 0; o < kN; ++o) prm.window[o] = a.window[o];
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int rc = a.spec_mode == SPEC_MAGNITUDE ? launch_t<B2A_WPF_WARPS, true>(prm, st, err) : launch_t<B2A_WPF_WARPS, false>(prm, st, err);
+  const bool mag = a.spec_mode == SPEC_MAGNITUDE;
+  int rc;
+  if (a.clip_tab) rc = mag ? launch_t<B2A_WPF_WARPS, true, true>(prm, st, err) : launch_t<B2A_WPF_WARPS, false, true>(prm, st, err);
+  else rc = mag ? launch_t<B2A_WPF_WARPS, true, false>(prm, st, err) : launch_t<B2A_WPF_WARPS, false, false>(prm, st, err);
   if (rc == B2A_OK) *launches += 1;
   return rc;
 }

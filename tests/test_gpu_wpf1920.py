@@ -98,3 +98,20 @@ def test_voice_encoder_config_with_1920_point_frames(api, ctx, both_kernels, bra
     new, old = both_kernels(lambda: api.voiceEncoderMelspectrogram(x, config=cfg, ctx=ctx))
     assert_feat_close(new, want, what=f"voice encoder 1920 ({branch}), warp per frame")
     assert_feat_close(old, want, what=f"voice encoder 1920 ({branch}), tiled")
+
+
+def test_s3gen_ragged_batch_on_both_kernels(api, ctx, both_kernels):
+    # per-clip lengths: the warp-per-frame kernel walks the tile table's 16-frame tiles with each clip's own length and frame count
+    lengths = [24000, 480 * 17, 24000 * 2 + 5, 1921, 9600, 480 * 16, 480 * 15 + 479, 24000 * 2 + 5]
+    n = max(lengths)
+    x = synth.pcm(len(lengths), n, sample_rate=24000, seed=3006, zero_tail_frac=0.0)
+    for b, ln in enumerate(lengths):
+        x[b, ln:] = 7.0   # whatever lies past a clip's length must not be read
+    (new, rows_new), (old, rows_old) = both_kernels(lambda: api.s3genMelSpectrogramRagged(x, lengths, ctx=ctx))
+    assert list(rows_new) == list(rows_old)
+    for b, ln in enumerate(lengths):
+        want = R.s3gen_mel_spectrogram(x[b:b + 1, :ln])[0]
+        assert rows_new[b] == want.shape[1]
+        for got, name in ((np.asarray(new), "warp per frame"), (np.asarray(old), "tiled")):
+            assert_feat_close(got[b, :, :rows_new[b]], want, what=f"s3gen ragged clip {b} ({name})")
+            assert not np.any(got[b, :, rows_new[b]:]), "rows past a clip's own frame count are zero"
