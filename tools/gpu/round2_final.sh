@@ -11,6 +11,10 @@ for w in chatterbox128 voice_encoder stft_kokoro stft_hift hift_head whisper_seg
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches_whisper128.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-secondary > gpurun_out/r2f_ncu_launches.log 2>&1
 TAG=r2final bash tools/gpu/prof_whisper.sh
+# the n_fft 1920 front end under both kernels (warp per frame / tiled) and the ncu capture of the warp-per-frame kernel
+B2A_WPF1920=0 python bench.py --workload s3gen --steps 20 --warmup 5 --no-e2e --no-cpu > gpurun_out/r2f_bench_s3gen_tiled.json 2> gpurun_out/r2f_bench_s3gen_tiled.err
+python bench.py --workload s3gen --steps 20 --warmup 5 --no-e2e --no-cpu > gpurun_out/r2f_bench_s3gen_wpf1920.json 2> gpurun_out/r2f_bench_s3gen_wpf1920.err
+ncu --set full --clock-control none --import-source on -k regex:wpf1920 -s 3 -c 1 -o gpurun_out/prof_wpf_r2final -f python bench.py --workload s3gen --no-cpu --no-e2e --no-secondary --steps 2 --warmup 3 > gpurun_out/prof_wpf_r2final.log 2>&1
 for f in gpurun_out/r2f_bench_*.json; do python - "$f" <<'PY'
 import json,sys
 try:
