@@ -52,6 +52,15 @@
 #ifndef B2A_MT_WALK
 #define B2A_MT_WALK 1
 #endif
+// 1 = Whisper-style clamp bookkeeping on the RAW mel sums (A/B switch; 0 keeps the round-1 form: floor and min / max of the normalised
+// values inside the store loop).  The store phase is the latency-critical stretch of a tile (removing its 177 tracking instructions,
+// 1.6 % of the tile, measured -4.8 %), so: the log floor moves into the clamp kernel (max(max(L, floor), Lmax - 8) = max(L, max(floor,
+// Lmax - 8)): one FMNMX per value less, and nothing in front of the MUFU), the minimum / maximum are taken over the raw sums (log is
+// monotone: max f(v) = f(max v)) in trees of three-input FMNMX that do not wait for the logarithms, and the two per-warp atomics are
+// plain RED instructions instead of the compiler's warp-aggregated sequence.
+#ifndef B2A_RAW_TRACK
+#define B2A_RAW_TRACK 1
+#endif
 
 
 namespace b2a {
@@ -170,6 +179,9 @@ B2A_DEV int enc_ordered(float f) {
   return b >= 0 ? b : b ^ 0x7fffffff;
 }
 B2A_DEV float dec_ordered(int e) { return __int_as_float(e >= 0 ? e : e ^ 0x7fffffff); }
+// one thread's atomic max without a return value (atomicMax() under `if (lane == 0)` compiles to a warp-aggregated sequence: vote, leader
+// election and a second reduction, ~20 instructions)
+B2A_DEV void red_max_s32(int* p, int v) { asm volatile("red.relaxed.gpu.global.max.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // Shared-memory word offset (relative to the lane's frame start) of sample o = N2*n1 + n2 in the skewed
 // PCM tile: o + o / HOP.  With n1 a compile-time constant this is (immediate) + n2 + carry, and the carry
@@ -672,13 +684,15 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     // ---- 4b. sparse mel projection; finished values wait in the free rows of the exchange buffer (output_words()) ----
     const int M = MEL > 0 ? MelTraits<MEL>::M : prm.n_mels;
     const int out_mode = OUT >= 0 ? OUT : prm.out_mode;
-    float lmax = -3.0e38f, vmin = 3.0e38f;   // of the normalised values (Whisper clamp bookkeeping)
+    constexpr bool RAWT = B2A_RAW_TRACK && POST == POST_WNORM;   // bookkeeping on the raw mel sums (see B2A_RAW_TRACK)
+    float lmax = RAWT ? 0.0f : -3.0e38f, vmin = 3.0e38f;   // of the normalised values, or (RAWT) of the raw mel sums (>= 0)
     const float log_floor = prm.log_floor;
     // Known banks: post-processing sits in the store loop, which keeps the unrolled mel code a third shorter (the tile loop
     // has to fit the instruction cache).
     auto post_pure = [&](float v) {
-      // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2
-      if (POST == POST_WNORM) v = fmaf(lg2_ftz(fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
+      // (log10(max(v, floor)) + 4) / 4 as one FMA on the MUFU log2; RAWT: no floor here (a zero sum becomes -inf, its tile's minimum
+      // is below any threshold, and whisper_clamp_kernel lifts it to max(floor, Lmax - 8))
+      if (POST == POST_WNORM) v = fmaf(lg2_ftz(RAWT ? v : fmaxf(v, log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
       else if (POST == POST_LN) v = lg2_ftz(fmaxf(v, log_floor)) * 0.69314718055994531f;
       return v;
     };
@@ -689,6 +703,10 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     };
     auto post = [&](float v) {
+      if (RAWT) {
+        track2(v, v);
+        return post_pure(v);
+      }
       v = post_pure(v);
       track2(v, v);
       return v;
@@ -760,17 +778,35 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
             const bool col_ok = c < MB / 32 || lane < MB % 32;
             const float* sr = srow[c] + warp;
             float v[NF + 1];
+            if (RAWT) {
+              // raw sums: their minimum / maximum (one three-input FMNMX each per two values, independent of the logarithms below)
 #pragma unroll
-            for (int i = 0; i < NF; ++i) v[i] = post_pure(sr[i * NW]);
+              for (int i = 0; i < NF; ++i) v[i] = sr[i * NW];
+              float cmax = v[0], cmin = v[0];
 #pragma unroll
-            for (int i = 0; i + 1 < NF; i += 2) track2(v[i], v[i + 1]);
-            if (NF % 2) track2(v[NF - 1], v[NF - 1]);
+              for (int i = 1; i + 1 < NF; i += 2) {
+                cmax = fmaxf(cmax, fmaxf(v[i], v[i + 1]));
+                cmin = fminf(cmin, fminf(v[i], v[i + 1]));
+              }
+              if (NF % 2 == 0) {
+                cmax = fmaxf(cmax, v[NF - 1]);
+                cmin = fminf(cmin, v[NF - 1]);
+              }
+              track2(cmax, cmin);   // (max3(lmax, cmax, cmin) = max(lmax, cmax); min3 alike)
+#pragma unroll
+              for (int i = 0; i < NF; ++i) v[i] = post_pure(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < NF; ++i) v[i] = post_pure(sr[i * NW]);
+#pragma unroll
+              for (int i = 0; i + 1 < NF; i += 2) track2(v[i], v[i + 1]);
+              if (NF % 2) track2(v[NF - 1], v[NF - 1]);
+            }
 #pragma unroll
             for (int i = 0; i < NF; ++i)
               if (ok[i] && col_ok) put(i * NW * MB + c * 32, v[i]);
             if (extra) {
-              v[NF] = post_pure(sr[NF * NW]);
-              track2(v[NF], v[NF]);
+              v[NF] = post(sr[NF * NW]);
               if (ok[NF] && col_ok) put(NF * NW * MB + c * 32, v[NF]);
             }
           }
@@ -821,11 +857,25 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
       if (POST == POST_WNORM) {
-        const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
-        const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
-        if (lane == 0) {
-          atomicMax(prm.clip_max + clip, wmax);
-          atomicMax(prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile, enc_ordered(-dec_ordered(wmin)));  // the NEGATED minimum, ordered-int encoded: one 0x80 memset initialises clip_max and tile_min alike
+        int* tmin_p = prm.tile_min + (RAGGED ? first_tile : clip * tpc) + tile;
+        if (RAWT) {
+          // raw sums are >= +0: their bit patterns order like integers.  Lane 0 turns the two extremes into normalised values (the
+          // maximum with the floor, as every stored value will have it after the clamp kernel) and publishes them with plain REDs.
+          const int wmax = __reduce_max_sync(0xffffffffu, __float_as_int(lmax));
+          const int wmin = __reduce_min_sync(0xffffffffu, __float_as_int(vmin));
+          if (lane == 0) {
+            const float nmax = fmaf(lg2_ftz(fmaxf(__int_as_float(wmax), log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
+            const float nmin = fmaf(lg2_ftz(__int_as_float(wmin)), 0.25f * 0.30102999566398120f, 1.0f);
+            red_max_s32(prm.clip_max + clip, enc_ordered(nmax));
+            red_max_s32(tmin_p, enc_ordered(-nmin));   // the NEGATED minimum, ordered-int encoded: one 0x80 memset initialises clip_max and tile_min alike
+          }
+        } else {
+          const int wmax = __reduce_max_sync(0xffffffffu, enc_ordered(lmax));
+          const int wmin = __reduce_min_sync(0xffffffffu, enc_ordered(vmin));
+          if (lane == 0) {
+            atomicMax(prm.clip_max + clip, wmax);
+            atomicMax(tmin_p, enc_ordered(-dec_ordered(wmin)));  // the NEGATED minimum, ordered-int encoded: one 0x80 memset initialises clip_max and tile_min alike
+          }
         }
       }
     } else {
@@ -922,7 +972,7 @@ constexpr int kClampTilesPerCta = 32;
 // clip_tab != null (ragged batch): the clip's own frame count and first tile; `n_frames` stays the (M, T') row stride.
 __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                                             long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft,
-                                                            const int4* __restrict__ clip_tab, int f16) {
+                                                            const int4* __restrict__ clip_tab, int f16, float log_floor) {
   __shared__ int s_list[kClampTilesPerCta];
   __shared__ int s_count;
   // launched with programmatic stream serialisation behind the front-end kernel (launch_plan): the blocks may already be resident
@@ -937,7 +987,11 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
     tiles_per_clip = int((n_frames + ft - 1) / ft);
     tile_base = ci.w;
   }
-  const float thr = dec_ordered(clip_max[clip]) - 2.0f;   // clip_max holds the maximum of the normalised values: ((Lmax - 8) + 4) / 4 = (Lmax + 4) / 4 - 2
+  // clip_max holds the maximum of the normalised values: ((Lmax - 8) + 4) / 4 = (Lmax + 4) / 4 - 2.  log_floor > 0 (B2A_RAW_TRACK): the main
+  // kernel stored un-floored values -- max(max(L, floor), Lmax - 8) = max(L, max(floor, Lmax - 8)) -- and the normalised floor is formed here
+  // with the expression (and the MUFU) the store loop used for floored values in round 1
+  const float norm_floor = log_floor > 0.0f ? fmaf(lg2_ftz(log_floor), 0.25f * 0.30102999566398120f, 1.0f) : -3.0e38f;
+  const float thr = fmaxf(dec_ordered(clip_max[clip]) - 2.0f, norm_floor);
   const int t0 = blockIdx.x * kClampTilesPerCta;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
@@ -1696,11 +1750,12 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       float* c_out = F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.out) + c0 * prm.out_clip_stride) : a.out + c0 * prm.out_clip_stride;
+      const float clamp_floor = (B2A_RAW_TRACK && POST == POST_WNORM) ? a.log_floor : -1.0f;   // > 0: the clamp kernel applies the log floor
       const int* c_max = a.clip_max + c0;
       const int* c_min = RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip;
       const int4* c_tab = RAGGED ? prm.clip_tab + c0 : nullptr;
       if ((e = cudaLaunchKernelEx(&cfg, whisper_clamp_kernel, c_out, c_max, c_min, prm.tiles_per_clip, (long long)a.n_frames, a.bank.n_mels,
-                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0)) != cudaSuccess)
+                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0, clamp_floor)) != cudaSuccess)
         return cuda_fail(e, "whisper_clamp_kernel launch", err);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
@@ -1716,7 +1771,7 @@ int launch_whisper_clamp(float* out, const int* clip_max, const int* tile_min, i
   for (long long c0 = 0; c0 < batch; c0 += 65535) {   // gridDim.y limit
     const long long nb = std::min<long long>(65535, batch - c0);
     whisper_clamp_kernel<<<dim3(unsigned((tiles + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0);
+        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0, -1.0f);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
