@@ -61,6 +61,11 @@
 #ifndef B2A_RAW_TRACK
 #define B2A_RAW_TRACK 1
 #endif
+// 1 = the (M, T') store of the baked 32-frame banks reads its staging offsets from a per-warp shared-memory table built in the prologue
+// (0: the incremental out_base_words() walk, ~8 integer instructions per stored row in the unrolled loop; A/B switch)
+#ifndef B2A_MT_TABLE
+#define B2A_MT_TABLE 1
+#endif
 
 
 namespace b2a {
@@ -140,6 +145,9 @@ template <> struct MelTraits<2> { static constexpr int M = 80; };
 template <> struct MelTraits<3> { static constexpr int M = 80; };
 template <> struct MelTraits<4> { static constexpr int M = 80; };
 template <> struct MelTraits<5> { static constexpr int M = 40; };
+// (M, T') store of a baked bank: rows per warp, padded to whole 16-byte table reads
+template <class P, int MEL> constexpr int mt_slots() { return ((MelTraits<MEL>::M + P::NWARPS * P::SUB - 1) / (P::NWARPS * P::SUB) + 3) & ~3; }
+template <class P, int MEL, int OUT> constexpr bool mt_table() { return B2A_MT_TABLE && MEL > 0 && OUT == OUT_MT && P::FT == 32; }
 template <int MEL, class Emit>
 __device__ __forceinline__ void mel_baked(int chunk, const float* __restrict__ p, Emit&& emit) {
   if constexpr (MEL == 1) mel_baked_1(chunk, p, emit);
@@ -465,6 +473,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   constexpr int kStepsSmemMax = steps_smem_max<P>();
   constexpr bool STEPS_SMEM = kStepsSmemMax > 0 && MEL == 0 && !cplx;
   float4* s_steps = reinterpret_cast<float4*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);
+  int* s_mt = reinterpret_cast<int*>(reinterpret_cast<float*>(s_tw) + P::TW_WORDS);   // baked (M, T') kernels: staging word offset of row warp + j * NW, [warp][j]
   const bool steps_in_smem = STEPS_SMEM && prm.fb_steps != nullptr && prm.n_steps <= kStepsSmemMax;
   if (steps_in_smem)
     for (int i = threadIdx.x; i < prm.n_steps; i += P::NTHREADS) s_steps[i] = __ldg(prm.fb_steps + i);
@@ -485,6 +494,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     for (int i = tid; i < N2 * (H1 - 1); i += P::NTHREADS) {
       const int n2 = i / (H1 - 1), k = i - n2 * (H1 - 1);
       *reinterpret_cast<float2*>(reinterpret_cast<float*>(s_tw) + n2 * P::TW_ROW + 2 * k) = tw[i];
+    }
+  }
+
+  if constexpr (mt_table<P, MEL, OUT>()) {
+    constexpr int SL = mt_slots<P, MEL>();
+    for (int i = tid; i < NW * SL; i += P::NTHREADS) {
+      const int w = i / SL, m = w + (i - w * SL) * NIT;
+      s_mt[i] = out_base_words<P>(m < MelTraits<MEL>::M ? m : MelTraits<MEL>::M - 1);
     }
   }
 
@@ -744,7 +761,24 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         // (M, T') rows: lanes run over frames
         const long long nfr = prm.n_frames;
         float* d = dst + f0 + fl;
-        if (frame_ok)
+        if constexpr (mt_table<P, MEL, OUT>()) {
+          // staging offsets from the per-warp table: whole 16-byte (warp-uniform) reads, then one LDS / post / STG per row
+          constexpr int SL = mt_slots<P, MEL>(), MB = MelTraits<MEL>::M;
+          int off[SL];
+#pragma unroll
+          for (int q = 0; q < SL / 4; ++q) {
+            const int4 o4 = reinterpret_cast<const int4*>(s_mt + wsub * SL)[q];
+            off[4 * q] = o4.x; off[4 * q + 1] = o4.y; off[4 * q + 2] = o4.z; off[4 * q + 3] = o4.w;
+          }
+          if (frame_ok) {
+            float* dm = d + wsub * nfr;
+#pragma unroll
+            for (int j = 0; j < SL; ++j) {
+              if (j * NIT < MB && (j * NIT + NIT <= MB || wsub + j * NIT < MB)) *dm = post(s_p[off[j] + fl]);
+              dm += NIT * nfr;
+            }
+          }
+        } else if (frame_ok)
           if (B2A_MT_WALK) {
             OutBaseWalk<P, NIT> ob(wsub);
             float* dm = d + wsub * nfr;
@@ -1682,7 +1716,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   const size_t smem = sizeof(float) * size_t((SPEC == SK_CPLX ? P::R0_WORDS_CPLX : P::R0_WORDS_REAL) + P::Y_WORDS +
                                              P::N + P::TW_WORDS) +
-                      ((MEL == 0 && SPEC != SK_CPLX) ? sizeof(float4) * size_t(steps_smem_max<P>()) : 0);
+                      ((MEL == 0 && SPEC != SK_CPLX) ? sizeof(float4) * size_t(steps_smem_max<P>()) : 0) +
+                      (mt_table<P, MEL, OUT>() ? sizeof(int) * size_t(P::NWARPS * mt_slots<P, MEL>()) : 0);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
   prm.total_tiles = RAGGED ? (long long)a.total_tiles : (long long)prm.tiles_per_clip * a.batch;
