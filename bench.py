@@ -56,6 +56,7 @@ WORKLOADS = {
     "whisper128_f16": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper 128-mel log-mel written as fp16 by the store loop (asType(.float16) fused), 1024 x 30 s (SURVEY 8f rank 1)"),
     "hift_head": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="HiFT vocoder head: exp/sin split + iSTFT (16/4) + limiter fused, 512 x 30 s of conv output (SURVEY 8f rank 2)"),
     "whisper128_ragged": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper 128-mel log-mel of a RAGGED batch: 1024 clips of 5..30 s (uniform) in one launch (b2a_whisper_log_mel_spectrogram_ragged)"),
+    "whisper128_padded": dict(batch=1024, clip_s=30.0, sr=16000, seed=1001, desc="Whisper 128-mel log-mel as WhisperSTT calls it: every 30 s clip followed by 30 s of zeros (padding = 480000, WhisperSTT.swift:139-144) -> 6000 frames per clip, 1024 clips; the tiles of silence are filled, not transformed"),
     "istft_kokoro": dict(batch=512, clip_s=30.0, sr=24000, seed=1004, desc="Kokoro iSTFTNet iSTFT (n_fft 20, hop 5), 512 x 30 s of mag/phase (configs[4], 5b)"),
     "chatterbox128": dict(batch=1024, clip_s=10.0, sr=16000, seed=1003, desc="S3Tokenizer / Chatterbox 128-mel log-mel (periodic Hann, (M, T') layout), 1024 x 10 s @16 kHz (SURVEY 8a row a14)"),
     "voice_encoder": dict(batch=1024, clip_s=10.0, sr=16000, seed=1003, desc="Chatterbox voice-encoder 40-mel power mel ((M, T') layout), 1024 x 10 s @16 kHz (SURVEY 8a row a21)"),
@@ -263,6 +264,11 @@ class GpuWorkload:
                 self.audio_s = float(lens.sum()) / self.sr
                 self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram_ragged(c.h, i[0], B, n, lens.ctypes.data_as(I64), 128, 0, o,
                                                                                            rows.ctypes.data_as(I64), sp)
+            elif name == "whisper128_padded":
+                pad = 480000
+                frames = int(lib.b2a_whisper_num_frames(n, pad))
+                self.out = torch.empty((B, frames, 128), device=dev)
+                self.call = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram(c.h, i[0], B, n, 128, pad, o, sp)
             elif name in ("whisper128", "whisper80_1clip", "whisper128_f16"):
                 nm = 80 if name == "whisper80_1clip" else 128
                 frames = int(lib.b2a_whisper_num_frames(n, 0))
@@ -443,7 +449,7 @@ class CpuArm:
     per thread.  numpy: oracle/reference_dsp.py (pocketfft), one process per core, clips_per_core clips each."""
 
     def __init__(self, name: str, seconds: float = 1.5):
-        if name == "whisper128_ragged":   # the CPU restatements process one clip at a time anyway: audio-s/s of the equal-length workload
+        if name in ("whisper128_ragged", "whisper128_padded"):   # the CPU restatements process one clip at a time anyway: audio-s/s of the equal-length workload
             name = "whisper128"
         self.name = name
         self.w = WORKLOADS[name]

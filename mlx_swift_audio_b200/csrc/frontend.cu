@@ -61,6 +61,13 @@
 #ifndef B2A_RAW_TRACK
 #define B2A_RAW_TRACK 1
 #endif
+// 1 = tiles that lie entirely in the caller's zero tail (Whisper `padding`: WhisperSTT.swift:139-144 appends 30 s of zeros to every clip, so
+// half of the frames of a 30 s call are silence) are not transformed at all: the main kernel only marks them (kTileFill in tile_min) and the
+// clamp kernel, which would have lifted their log floor to max(floor, Lmax - 8) anyway, fills them without reading (A/B switch)
+#ifndef B2A_SKIP_ZERO_TILES
+#define B2A_SKIP_ZERO_TILES 1
+#endif
+constexpr int kTileFill = 0x7fffffff;   // tile_min entry of a skipped tile (no float's ordered-int encoding: enc_ordered(+inf) = 0x7f800000)
 // 1 = the (M, T') store of the baked 32-frame banks reads its staging offsets from a per-warp shared-memory table built in the prologue
 // (0: the incremental out_base_words() walk, ~8 integer instructions per stored row in the unrolled loop; A/B switch)
 #ifndef B2A_MT_TABLE
@@ -432,6 +439,14 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
   }
 }
 
+// Out-of-line copy for the cold call site (the tile after a skipped tile of silence): the hot loop keeps ONE inlined copy of the staging code
+// (its instruction footprint is at the edge of what the instruction cache serves at full rate)
+template <class P>
+__device__ __noinline__ void stage_pcm_cold(const FrontendParams<P>& prm, float* __restrict__ buf, int clip, int f0, long long n_samples,
+                                            long long n_eff, int tid, int lane, int warp) {
+  stage_pcm<P>(prm, buf, clip, f0, n_samples, n_eff, tid, lane, warp);
+}
+
 // Persistent kernel: grid = MINB CTAs per SM; every CTA loads its tables once and walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...  The next tile's PCM is prefetched (cp.async) into the PCM region as soon as
 // stage A has consumed the current one.
@@ -442,7 +457,9 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // per tile, issued one tile ahead) instead of the launch-wide constants.
 // F16: the (T', M) store of a baked bank writes __half (round to nearest even of the fp32 value: bit-identical to the reference's
 // asType(.float16) of the fp32 feature, WhisperSTT.swift:156-157,181-182); clamp bookkeeping stays in fp32.
-template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false, bool F16 = false>
+// ZS: the launch has a zero tail (Whisper `padding` > 0) -- the instantiation that skips tiles of silence (B2A_SKIP_ZERO_TILES); launches
+// without one keep the kernel without that code (measured: the test alone cost 0.35 - 0.5 % of the unpadded 1024 x 30 s step).
+template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false, bool F16 = false, bool ZS = false>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
@@ -530,7 +547,16 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       set_clip(t, g);
     }
   }
-  if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
+  // ZSKIP: is every sample of this tile a zero of the caller's zero tail (directly, or reflected from it at the right edge)?
+  constexpr bool ZSKIP = ZS && B2A_SKIP_ZERO_TILES && B2A_RAW_TRACK && POST == POST_WNORM && LATE_TOP;
+  auto tile_zero = [&](int tl, long long ns) {
+    if (!ZSKIP || zero_tail <= 0) return false;
+    const long long j0 = (long long)tl * (FT * HOP) - prm.pad_left;
+    if (j0 < ns) return false;
+    const long long over = j0 + (P::TS - 1) - (ns + zero_tail);   // how far the tile's last sample lies beyond the padded signal
+    return over < 0 || prm.pad_mode != PAD_REFLECT || over <= zero_tail - 2;
+  };
+  if (clip < n_clips && !tile_zero(tile, n_samples)) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
   if (LATE_TOP) {   // first tile's PCM and the tables
     cp_async_commit_wait_all();
     __syncthreads();
@@ -554,6 +580,21 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         ntile = nt.y;
         nn_samples = nt.z;
       }
+    }
+
+    // ---- 0. a tile of silence: mark it for the clamp kernel's fill, stage the next tile, publish it like the post-mel barrier would ----
+    if (ZSKIP && tile_zero(tile, n_samples)) {
+      if (tid == 0) prm.tile_min[(RAGGED ? first_tile : clip * tpc) + tile] = kTileFill;
+      if (nclip < n_clips && !tile_zero(ntile, nn_samples)) stage_pcm_cold<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
+      cp_async_commit_wait_all();
+      __syncthreads();
+      clip = nclip;
+      tile = ntile;
+      if (RAGGED) {
+        g += gridDim.x;
+        if (clip < n_clips) set_clip(nt, g);
+      }
+      continue;
     }
 
     // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
@@ -616,7 +657,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
     __syncthreads();
-    if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
+    if (EARLY_PREFETCH && nclip < n_clips && !tile_zero(ntile, nn_samples))
+      stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
 
     // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
     // The power / magnitude of every bin goes back into the item's own rows of the exchange buffer (row = slot of
@@ -1003,6 +1045,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 // One CTA per (clip, group of kClampTilesPerCta tiles): the group's tile minima are tested in parallel (one round trip to
 // memory), the tiles that need it are rewritten with 16-byte accesses.
 constexpr int kClampTilesPerCta = 32;
+constexpr int kFillFlag = 0x40000000;   // s_list entry: the tile was skipped by the main kernel (kTileFill), write the threshold without reading
 // clip_tab != null (ragged batch): the clip's own frame count and first tile; `n_frames` stays the (M, T') row stride.
 __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                                             long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft,
@@ -1029,14 +1072,17 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
   const int t0 = blockIdx.x * kClampTilesPerCta;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  if (threadIdx.x < kClampTilesPerCta && t0 + int(threadIdx.x) < tiles_per_clip &&
-      -dec_ordered(tile_min[tile_base + t0 + threadIdx.x]) < thr)   // tile_min holds the negated minimum
-    s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
+  if (threadIdx.x < kClampTilesPerCta && t0 + int(threadIdx.x) < tiles_per_clip) {
+    const int tm = tile_min[tile_base + t0 + threadIdx.x];   // the negated minimum, or kTileFill: a tile of silence the main kernel skipped
+    if (tm == kTileFill) s_list[atomicAdd(&s_count, 1)] = (t0 + threadIdx.x) | kFillFlag;
+    else if (-dec_ordered(tm) < thr) s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
+  }
   __syncthreads();
   const int count = s_count;
   float* o = out + clip * out_clip_stride;
   for (int i = 0; i < count; ++i) {
-    const int t = s_list[i];
+    const bool fill = (s_list[i] & kFillFlag) != 0;   // nothing valid was written there: every value is the floor, i.e. becomes thr
+    const int t = s_list[i] & ~kFillFlag;
     const long long f0 = (long long)t * ft;
     const int rows = int(n_frames - f0 < ft ? n_frames - f0 : ft);
     if (out_mode == OUT_TM && f16) {
@@ -1048,13 +1094,18 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
         const __half2 th2 = __half2half2(th);
         uint4* d4 = reinterpret_cast<uint4*>(d);
         for (int e = threadIdx.x; e < n / 8; e += blockDim.x) {
-          uint4 v = d4[e];
+          uint4 v;
           __half2* h = reinterpret_cast<__half2*>(&v);
-          h[0] = __hmax2(h[0], th2); h[1] = __hmax2(h[1], th2); h[2] = __hmax2(h[2], th2); h[3] = __hmax2(h[3], th2);
+          if (fill) {
+            h[0] = h[1] = h[2] = h[3] = th2;
+          } else {
+            v = d4[e];
+            h[0] = __hmax2(h[0], th2); h[1] = __hmax2(h[1], th2); h[2] = __hmax2(h[2], th2); h[3] = __hmax2(h[3], th2);
+          }
           d4[e] = v;
         }
       } else {
-        for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = __hmax(d[e], th);
+        for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = fill ? th : __hmax(d[e], th);
       }
     } else if (out_mode == OUT_TM) {
       float* d = o + f0 * n_mels;
@@ -1062,19 +1113,22 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
       if ((reinterpret_cast<uintptr_t>(d) & 15) == 0 && (n & 3) == 0) {
         float4* d4 = reinterpret_cast<float4*>(d);
         for (int e = threadIdx.x; e < n / 4; e += blockDim.x) {
-          float4 v = d4[e];
-          v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+          float4 v = make_float4(thr, thr, thr, thr);
+          if (!fill) {
+            v = d4[e];
+            v.x = fmaxf(v.x, thr); v.y = fmaxf(v.y, thr); v.z = fmaxf(v.z, thr); v.w = fmaxf(v.w, thr);
+          }
           d4[e] = v;
         }
       } else {
-        for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = fmaxf(d[e], thr);
+        for (int e = threadIdx.x; e < n; e += blockDim.x) d[e] = fill ? thr : fmaxf(d[e], thr);
       }
     } else {  // OUT_MT: lanes over the tile's (<= 32) frames, warps over the filters -- no per-element division
       const int r = threadIdx.x & 31;
       if (r < rows)
         for (int m = threadIdx.x >> 5; m < n_mels; m += int(blockDim.x >> 5)) {
           float* d = o + (long long)m * mt_stride + f0 + r;
-          *d = fmaxf(*d, thr);
+          *d = fill ? thr : fmaxf(*d, thr);
         }
     }
   }
@@ -1644,8 +1698,12 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false, bool F16 = false>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false, bool F16 = false, bool ZS = false>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
+  if constexpr (!ZS && B2A_SKIP_ZERO_TILES && B2A_RAW_TRACK && POST == POST_WNORM && MEL > 0 && PRE != PRE_KALDI) {
+    // a zero tail (Whisper `padding`): the instantiation that skips the tiles of silence
+    if (a.zero_tail > 0) return launch_plan<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, true>(a, st, launches, err);
+  }
   if (!RAGGED && a.clip_tab != nullptr) {
     // per-clip lengths: the RAGGED instantiation of the run-time-configured kernel of the same plan (and of the Whisper
     // 128-mel kernel, dispatched in launch_frontend), reading the clip table
@@ -1742,10 +1800,10 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     std::lock_guard<std::mutex> lk(info_mu);
     if (!di.ready.load(std::memory_order_relaxed)) {
       int n_sm = 148, per_sm = 1;
-      if ((e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
+      if ((e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
         return cuda_fail(e, "cudaFuncSetAttribute", err);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16>, P::NTHREADS, smem)) != cudaSuccess)
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS>, P::NTHREADS, smem)) != cudaSuccess)
         return cuda_fail(e, "occupancy query", err);
       if (per_sm < 1) {
         if (err) *err = "frontend kernel does not fit on this device";
@@ -1768,7 +1826,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       if ((e = cudaMemsetAsync(a.tile_min, 0x80, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     }
   }
-  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {

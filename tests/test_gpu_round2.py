@@ -286,3 +286,40 @@ int main(int argc, char** argv) {
     assert r.stdout.strip().endswith("launches") and int(r.stdout.split()[0]) >= 2
     got = np.fromfile(fout, np.float32).reshape(want.shape)
     assert_feat_close(got, want, what="compiled C program, golden whisper80")
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+@pytest.mark.parametrize("n,padding", [(16000 * 3 + 37, 480000), (5000, 480000), (16000, 201), (16000, 202), (16000 * 2, 160 * 32 * 3),
+                                       (16000 * 2, 160 * 32 + 399), (480000 // 8, 480000 // 8), (300, 480000)])
+def test_whisper_zero_tail_tiles_are_filled_not_transformed(api, ctx, n_mels, n, padding):
+    # WhisperSTT.swift:139-144: every clip gets 30 s of zeros appended before whisperLogMelSpectrogram.  Tiles that lie entirely in that
+    # zero tail (incl. its reflection at the right edge) are skipped by the main kernel and filled by the clamp kernel with
+    # max(floor, Lmax - 8): the same values the oracle computes from explicit zeros -- fp32, fp16 and 16-bit PCM entries alike.
+    x = synth.pcm(3, n, seed=2101, zero_tail_frac=0.0)
+    want = np.stack([R.whisper_log_mel_spectrogram(c, n_mels, padding=padding) for c in x])
+    got = api.whisperLogMelSpectrogram(x, nMels=n_mels, padding=padding, ctx=ctx)
+    assert got.shape == want.shape
+    assert_feat_close(got, want, what=f"whisper, n = {n}, padding = {padding}")
+    f16 = api.whisperLogMelSpectrogramF16(x, nMels=n_mels, padding=padding, ctx=ctx)
+    assert np.array_equal(_bits(f16), _bits(got.astype(np.float16))), "fp16 entry = cast of the fp32 entry, filled tiles included"
+    # the switch-free check: padding given as explicit zeros (no zero tail for the library to know about) gives the same features
+    xz = np.concatenate([x, np.zeros((3, padding), np.float32)], axis=1)
+    explicit = api.whisperLogMelSpectrogram(xz, nMels=n_mels, ctx=ctx)
+    assert np.array_equal(explicit, got), "virtual zero tail == explicit zeros, bit for bit"
+
+
+def test_whisper_zero_tail_silent_clip_and_ragged(api, ctx):
+    # a clip of digital silence: every value is the log floor ((-10 + 4) / 4 = -1.5), with and without a zero tail
+    z = np.zeros((2, 16000), np.float32)
+    for padding in (0, 480000):
+        got = api.whisperLogMelSpectrogram(z, nMels=80, padding=padding, ctx=ctx)
+        assert np.abs(got + 1.5).max() <= 1e-6
+    # ragged batch with a zero tail: per-clip lengths, tiles of silence per clip
+    lengths = [16000 * 2, 5000, 16000 * 3 + 11, 700]
+    n = max(lengths)
+    x = synth.pcm(len(lengths), n, seed=2102, zero_tail_frac=0.0)
+    got, rows = api.whisperLogMelSpectrogramRagged(x, lengths, nMels=128, padding=48000, ctx=ctx)
+    for b, ln in enumerate(lengths):
+        want = R.whisper_log_mel_spectrogram(x[b, :ln], 128, padding=48000)
+        assert rows[b] == want.shape[0]
+        assert_feat_close(np.asarray(got)[b, :rows[b]], want, what=f"ragged whisper with padding, clip {b}")
