@@ -146,7 +146,11 @@ B2A_API int b2a_reflect_pad(b2a_ctx* ctx, const float* x, int64_t batch, int64_t
 
 /* whisperLogMelSpectrogram STT/Whisper/WhisperAudio.swift:78-137.
  * audio (batch, n_samples) -> out (batch, T', n_mels), T' = b2a_whisper_num_frames(n_samples, padding).
- * The max-8 clamp uses each clip's own global maximum, as the single-clip reference does. */
+ * The max-8 clamp uses each clip's own global maximum, as the single-clip reference does.
+ * `padding` = zeros appended to every clip (the reference's own parameter; WhisperSTT.swift:139-144 concatenates 30 s of zeros before the
+ * call -- pass padding = 480000 instead of concatenating: the zeros are neither stored nor copied, and the frames that lie entirely
+ * inside them are filled with their final value (max(log floor, Lmax - 8)) instead of being transformed; the features are bit-identical
+ * to those of explicit zeros). */
 B2A_API int b2a_whisper_log_mel_spectrogram(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
                                             int n_mels, int64_t padding, float* out, int space);
 /* The same features as IEEE fp16: whisperLogMelSpectrogram(...).asType(.float16), the only form the Whisper encoder ever consumes
