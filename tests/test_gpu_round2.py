@@ -323,3 +323,14 @@ def test_whisper_zero_tail_silent_clip_and_ragged(api, ctx):
         want = R.whisper_log_mel_spectrogram(x[b, :ln], 128, padding=48000)
         assert rows[b] == want.shape[0]
         assert_feat_close(np.asarray(got)[b, :rows[b]], want, what=f"ragged whisper with padding, clip {b}")
+
+
+@pytest.mark.parametrize("n,padding", [(16000 * 2 + 5, 48000), (4000, 160 * 32 * 2 + 201), (16000, 202)])
+def test_chatterbox_log_mel_zero_tail_in_the_mel_major_layout(api, ctx, n, padding):
+    # S3TokenizerUtils.swift:160-208 takes the same `padding`; (M, T') layout: the clamp kernel fills the skipped tiles column-wise
+    x = synth.pcm(2, n, seed=2103, zero_tail_frac=0.0)
+    want = np.stack([R.log_mel_spectrogram_chatterbox(c, 128, padding=padding) for c in x])
+    got = api.logMelSpectrogramChatterbox(x, nMels=128, padding=padding, ctx=ctx)
+    assert_feat_close(got, want, what=f"chatterbox log-mel, n = {n}, padding = {padding}")
+    xz = np.concatenate([x, np.zeros((2, padding), np.float32)], axis=1)
+    assert np.array_equal(api.logMelSpectrogramChatterbox(xz, nMels=128, ctx=ctx), got), "virtual zero tail == explicit zeros, bit for bit"
