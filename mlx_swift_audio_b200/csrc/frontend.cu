@@ -439,14 +439,6 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
   }
 }
 
-// Out-of-line copy for the cold call site (the tile after a skipped tile of silence): the hot loop keeps ONE inlined copy of the staging code
-// (its instruction footprint is at the edge of what the instruction cache serves at full rate)
-template <class P>
-__device__ __noinline__ void stage_pcm_cold(const FrontendParams<P>& prm, float* __restrict__ buf, int clip, int f0, long long n_samples,
-                                            long long n_eff, int tid, int lane, int warp) {
-  stage_pcm<P>(prm, buf, clip, f0, n_samples, n_eff, tid, lane, warp);
-}
-
 // Persistent kernel: grid = MINB CTAs per SM; every CTA loads its tables once and walks tiles
 // blockIdx.x, blockIdx.x + gridDim.x, ...  The next tile's PCM is prefetched (cp.async) into the PCM region as soon as
 // stage A has consumed the current one.
@@ -556,7 +548,29 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     const long long over = j0 + (P::TS - 1) - (ns + zero_tail);   // how far the tile's last sample lies beyond the padded signal
     return over < 0 || prm.pad_mode != PAD_REFLECT || over <= zero_tail - 2;
   };
-  if (clip < n_clips && !tile_zero(tile, n_samples)) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
+  if (ZSKIP) {   // the CTA's first tiles may be tiles of silence too
+    while (clip < n_clips && tile_zero(tile, n_samples)) {
+      if (tid == 0) prm.tile_min[RAGGED ? g : (long long)clip * tpc + tile] = kTileFill;
+      if (RAGGED) {
+        g += gridDim.x;
+        clip = n_clips;
+        if (g < prm.total_tiles) {
+          const int4 t = __ldg(prm.tile_tab + g);
+          clip = t.x;
+          tile = t.y;
+          set_clip(t, g);
+        }
+      } else {
+        clip += step_clip;
+        tile += step_tile;
+        if (tile >= tpc) {
+          tile -= tpc;
+          ++clip;
+        }
+      }
+    }
+  }
+  if (clip < n_clips) stage_pcm<P>(prm, smem, clip, tile * FT, n_samples, n_samples + zero_tail, tid, lane, warp);
   if (LATE_TOP) {   // first tile's PCM and the tables
     cp_async_commit_wait_all();
     __syncthreads();
@@ -581,20 +595,30 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         nn_samples = nt.z;
       }
     }
-
-    // ---- 0. a tile of silence: mark it for the clamp kernel's fill, stage the next tile, publish it like the post-mel barrier would ----
-    if (ZSKIP && tile_zero(tile, n_samples)) {
-      if (tid == 0) prm.tile_min[(RAGGED ? first_tile : clip * tpc) + tile] = kTileFill;
-      if (nclip < n_clips && !tile_zero(ntile, nn_samples)) stage_pcm_cold<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
-      cp_async_commit_wait_all();
-      __syncthreads();
-      clip = nclip;
-      tile = ntile;
-      if (RAGGED) {
-        g += gridDim.x;
-        if (clip < n_clips) set_clip(nt, g);
+    // ZSKIP: the walk passes over tiles of silence (it only marks them for the clamp kernel's fill), so the tile staged behind stage A is
+    // the next tile that is actually transformed -- no barrier, no exposed staging latency for a skipped tile
+    long long ng = g + gridDim.x;   // (RAGGED: launch-wide index of the next tile)
+    if (ZSKIP) {
+      while (nclip < n_clips && tile_zero(ntile, nn_samples)) {
+        if (tid == 0) prm.tile_min[RAGGED ? ng : (long long)nclip * tpc + ntile] = kTileFill;
+        if (RAGGED) {
+          ng += gridDim.x;
+          nclip = n_clips;
+          if (ng < prm.total_tiles) {
+            nt = __ldg(prm.tile_tab + ng);
+            nclip = nt.x;
+            ntile = nt.y;
+            nn_samples = nt.z;
+          }
+        } else {
+          nclip += step_clip;
+          ntile += step_tile;
+          if (ntile >= tpc) {
+            ntile -= tpc;
+            ++nclip;
+          }
+        }
       }
-      continue;
     }
 
     // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
@@ -657,8 +681,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
     __syncthreads();
-    if (EARLY_PREFETCH && nclip < n_clips && !tile_zero(ntile, nn_samples))
-      stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
+    if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
 
     // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
     // The power / magnitude of every bin goes back into the item's own rows of the exchange buffer (row = slot of
@@ -1033,7 +1056,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     clip = nclip;
     tile = ntile;
     if (RAGGED) {
-      g += gridDim.x;
+      g = ng;
       if (clip < n_clips) set_clip(nt, g);
     }
   }
