@@ -6,7 +6,7 @@ python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2f_smoke.log 2>&1; tail -2 gpurun_out/r2f_smoke.log
 python bench.py > gpurun_out/r2f_bench_default.json 2> gpurun_out/r2f_bench_default.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2f_bench_reference.json 2> gpurun_out/r2f_bench_reference.err
-for w in chatterbox128 voice_encoder stft_kokoro stft_hift hift_head whisper_segment whisper128_f16 whisper128_ragged; do
+for w in chatterbox128 voice_encoder stft_kokoro stft_hift hift_head whisper_segment whisper128_f16 whisper128_ragged whisper128_padded; do
   python bench.py --workload $w --steps 20 --warmup 5 --no-e2e > gpurun_out/r2f_bench_$w.json 2> gpurun_out/r2f_bench_$w.err
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches_whisper128.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-secondary > gpurun_out/r2f_ncu_launches.log 2>&1
