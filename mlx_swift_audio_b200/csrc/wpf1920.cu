@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
 
   // ---- tables (once per persistent CTA) ----
   // window: warp-uniform reads of the kernel parameter (a lane-dependent index into the parameter space is served one lane at a time:
-  // measured 16 us for the 1920 taps, 4 % of the 256 x 10 s launch); sample m of the frame belongs to lane (m - rot) mod 32, slot (m - rot) / 32
+  // ncu attributed 4 % of the first version's stall samples to that loop); sample m of the frame belongs to lane (m - rot) mod 32, slot (m - rot) / 32
   for (int m = warp; m < kN; m += NW) {
     const float v = prm.window[m];
     int i = m - rot;
