@@ -229,9 +229,9 @@ int run_batched_bytes(b2a_ctx* c, int space, int64_t batch, const void* in0_v, s
   if (space != B2A_HOST) return fail(c, B2A_E_BAD_ARG, "space must be B2A_HOST or B2A_DEVICE");
   const size_t per_clip = in0_per_clip + in1_per_clip + out0_per_clip + out1_per_clip;
   // bytes per chunk (inputs + outputs).  Measured on the B200 box (tools/gpu/e2e_sweep.sh): the host path is bound by the H2D copies
-  // (~54 GB/s) for any chunk of 32..192 MB; 128 MB keeps fill / drain at a few % of a multi-GB call (ramping the first and last
+  // (~54 GB/s) for any chunk of 32..192 MB; 64 MB keeps fill / drain small (measured on the pcm16 -> fp16 Whisper call: 16 MB 22.97 ms, 32 MB 20.62, 64 MB 19.88, 128 MB 20.30, 256 MB 21.28; ramping the first and last
   // chunks down to 1/8 of the size changed nothing: the step is bound by the duplex PCIe traffic itself).  B2A_HOST_CHUNK_MB overrides.
-  size_t target = size_t(128) << 20;
+  size_t target = size_t(64) << 20;
   if (const char* mb = getenv("B2A_HOST_CHUNK_MB")) target = size_t(std::max(1, atoi(mb))) << 20;
   int64_t chunk = std::max<int64_t>(1, int64_t(target / std::max<size_t>(per_clip, 1)));
   chunk = std::min(std::min(chunk, batch), kMaxClipsPerLaunch);   // (tiny clips: the byte target alone would exceed gridDim.y)
