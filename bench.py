@@ -194,8 +194,10 @@ class GpuWorkload:
         self.seed = seed
         B, n = self.batch, self.n
         U = min(B, UNIQUE_CLIPS)
-        self.pcm16 = None                      # Whisper workloads: unique clips as 16-bit PCM for the e2e headline
+        self.pcm16 = None                      # front ends with a 16-bit PCM entry: unique clips as int16 for the e2e headline
         self.e2e16 = None
+        self.e2e16_entry = None
+        self.out16_dtype = torch.float16       # Whisper: fp16 features out; the other 16-bit PCM entries write fp32
         if name == "whisper_segment":
             frames = 6000                      # mel of 30 s of audio + the 30 s of padding transcribe() appends
             rs = np.random.default_rng(seed)
@@ -281,6 +283,8 @@ class GpuWorkload:
                 self.pcm16 = np.clip(np.rint(xu * 32767.0), -32768, 32767).astype(np.int16)
                 self.e2e16 = lambda c, i, o, sp: lib.b2a_whisper_log_mel_spectrogram_pcm16(c.h, i, B, n, nm, 0, 1, o, sp)
                 self.out16_shape = (B, frames, nm)
+                self.e2e16_entry = ("b2a_whisper_log_mel_spectrogram_pcm16: 16-bit PCM in (x / 32768, as AVAudioFile decodes it), fp16 features out "
+                                    "(asType(.float16), the form the Whisper encoder consumes) -- bit-identical to casting the fp32 entry's result")
             elif name == "chatterbox128":
                 frames = int(lib.b2a_whisper_num_frames(n, 0))   # the last STFT frame is dropped, as in the Whisper front end
                 self.out = torch.empty((B, 128, frames), device=dev)
@@ -297,14 +301,20 @@ class GpuWorkload:
                 rows = int(lib.b2a_lfr_num_rows(frames, 6))
                 self.out = torch.empty((B, rows, 560), device=dev)
                 self.call = lambda c, i, o, sp: lib.b2a_funasr_preprocess_audio(c.h, i[0], B, n, 80, 7, 6, 1, o, sp)
+                self._pcm16_entry(xu, (B, rows, 560), lambda c, i, o, sp: lib.b2a_funasr_preprocess_audio_pcm16(c.h, i, B, n, 80, 7, 6, 1, o, sp),
+                                  "b2a_funasr_preprocess_audio_pcm16")
             elif name == "kaldi":
                 frames = int(lib.b2a_kaldi_num_frames(n, 400, 160))
                 self.out = torch.empty((B, frames, 80), device=dev)
                 self.call = lambda c, i, o, sp: lib.b2a_kaldi_fbank_campplus(c.h, i[0], B, n, 16000, 80, 25.0, 10.0, 1, o, sp)
+                self._pcm16_entry(xu, (B, frames, 80), lambda c, i, o, sp: lib.b2a_kaldi_fbank_campplus_pcm16(c.h, i, B, n, 16000, 80, 25.0, 10.0, 1, o, sp),
+                                  "b2a_kaldi_fbank_campplus_pcm16")
             elif name == "s3gen":
                 frames = int(lib.b2a_s3gen_num_frames(n, 1920, 480))
                 self.out = torch.empty((B, 80, frames), device=dev)
                 self.call = lambda c, i, o, sp: lib.b2a_s3gen_mel_spectrogram(c.h, i[0], B, n, 1920, 80, 24000, 480, 1920, 0, 8000, o, sp)
+                self._pcm16_entry(xu, (B, 80, frames), lambda c, i, o, sp: lib.b2a_s3gen_mel_spectrogram_pcm16(c.h, i, B, n, 1920, 80, 24000, 480, 1920, 0, 8000, o, sp),
+                                  "b2a_s3gen_mel_spectrogram_pcm16")
             else:
                 raise SystemExit(f"unknown workload {name}")
         self.in_bytes = sum(t.numel() * t.element_size() for t in self.inputs)
@@ -316,6 +326,14 @@ class GpuWorkload:
             self.algo_bytes = int(sum(3000 - int(s0) for s0 in self._keep[0])) * 128 * 4 + self.out_bytes
         self.DEV, self.HOST = _lib.B2A_DEVICE, _lib.B2A_HOST
         self.h_in = self.h_out = self.h_in16 = self.h_out16 = None
+
+    def _pcm16_entry(self, xu, out_shape, fn, name):
+        """e2e headline of a front end with a 16-bit PCM entry: int16 samples in (half the host-to-device bytes), fp32 features out."""
+        self.pcm16 = np.clip(np.rint(xu * 32767.0), -32768, 32767).astype(np.int16)
+        self.e2e16 = fn
+        self.out16_shape = out_shape
+        self.out16_dtype = self.torch.float32
+        self.e2e16_entry = name + ": 16-bit PCM in (x / 32768, as AVAudioFile decodes a 16-bit file), fp32 features out -- bit-identical to the fp32 entry on the converted samples"
 
     def close(self):
         self.inputs = self.out = self.h_in = self.h_out = self.h_in16 = self.h_out16 = None
@@ -344,7 +362,7 @@ class GpuWorkload:
             for b0 in range(0, B, u.shape[0]):
                 m = min(u.shape[0], B - b0)
                 self.h_in16[b0:b0 + m].copy_(u[:m])
-            self.h_out16 = torch.empty(self.out16_shape, dtype=torch.float16, pin_memory=True)
+            self.h_out16 = torch.empty(self.out16_shape, dtype=self.out16_dtype, pin_memory=True)
         torch.cuda.synchronize()
 
     def step_host(self):
@@ -353,7 +371,7 @@ class GpuWorkload:
 
     def step_host16(self):
         rc = self.e2e16(self.hctx, C.c_void_p(self.h_in16.data_ptr()), C.c_void_p(self.h_out16.data_ptr()), self.HOST)
-        self._check(self.hctx, rc, "host call (pcm16 -> fp16)")
+        self._check(self.hctx, rc, "host call (16-bit PCM entry)")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -623,12 +641,10 @@ def measure(name, args, env, steps, warmup, e2e_steps, want_cpu, batch=None, det
         e2e = f32
         if wl.e2e16 is not None:
             dt16 = timed(wl.step_host16, e2e_steps)
-            h2d16, d2h16 = wl.h_in16.numel() * 2, wl.h_out16.numel() * 2
+            h2d16, d2h16 = wl.h_in16.numel() * 2, wl.h_out16.numel() * wl.h_out16.element_size()
             e2e = {"value": wl.audio_s * world / dt16, "unit": UNIT, "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h16,
                    "ms_per_step": dt16 * 1e3, "steps": e2e_steps,
-                   "entry": "b2a_whisper_log_mel_spectrogram_pcm16: 16-bit PCM in (x / 32768, as AVAudioFile decodes it), fp16 features out "
-                            "(asType(.float16), the form the Whisper encoder consumes) -- bit-identical to casting the fp32 entry's result",
-                   "fp32_in_fp32_out": f32}
+                   "entry": wl.e2e16_entry, "fp32_in_fp32_out": f32}
         if detail:
             # the copy directions alone (pinned <-> device, no kernels), for the attribution of the e2e ceiling
             def copy_rate(dst, src):

@@ -184,6 +184,11 @@ B2A_API int b2a_apply_cmvn(b2a_ctx* ctx, const float* features, int64_t batch, i
 B2A_API int b2a_funasr_preprocess_audio(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
                                         int n_mels, int lfr_m, int lfr_n, int apply_normalization,
                                         float* out, int space);
+/* The same from 16-bit PCM (sample = int16 / 32768, as AVAudioFile decodes a 16-bit file; exact in fp32): bit-identical to the fp32
+ * entry on the converted samples, half the bytes for a host caller.  Likewise for the two entries below. */
+B2A_API int b2a_funasr_preprocess_audio_pcm16(b2a_ctx* ctx, const int16_t* audio, int64_t batch, int64_t n_samples,
+                                              int n_mels, int lfr_m, int lfr_n, int apply_normalization,
+                                              float* out, int space);
 
 /* kaldiFbankCAMPPlus       Codec/S3Gen/CAMPPlus.swift:32-106.  out (batch, T', num_mel_bins).
  * mean_norm != 0 additionally applies the caller-side `fbank - mean(fbank, axis: 0)` of
@@ -191,6 +196,9 @@ B2A_API int b2a_funasr_preprocess_audio(b2a_ctx* ctx, const float* audio, int64_
 B2A_API int b2a_kaldi_fbank_campplus(b2a_ctx* ctx, const float* audio, int64_t batch, int64_t n_samples,
                                      int sample_rate, int num_mel_bins, float frame_length_ms, float frame_shift_ms,
                                      int mean_norm, float* out, int space);
+B2A_API int b2a_kaldi_fbank_campplus_pcm16(b2a_ctx* ctx, const int16_t* audio, int64_t batch, int64_t n_samples,
+                                           int sample_rate, int num_mel_bins, float frame_length_ms, float frame_shift_ms,
+                                           int mean_norm, float* out, int space);
 
 /* s3genMelSpectrogram      Codec/S3Gen/Mel/S3GenMel.swift:43-102 (wrappers computeMelSpectrogram80
  * CosyVoice2TTS.swift:754-770, CosyVoice3TTS.swift:770-787, melSpectrogramS3Gen ChatterboxTurboModel.swift:545-572).
@@ -198,6 +206,9 @@ B2A_API int b2a_kaldi_fbank_campplus(b2a_ctx* ctx, const float* audio, int64_t b
 B2A_API int b2a_s3gen_mel_spectrogram(b2a_ctx* ctx, const float* y, int64_t batch, int64_t n_samples, int n_fft,
                                       int num_mels, int sampling_rate, int hop_size, int win_size, int fmin, int fmax,
                                       float* out, int space);
+B2A_API int b2a_s3gen_mel_spectrogram_pcm16(b2a_ctx* ctx, const int16_t* y, int64_t batch, int64_t n_samples, int n_fft,
+                                            int num_mels, int sampling_rate, int hop_size, int win_size, int fmin, int fmax,
+                                            float* out, int space);
 
 /* voiceEncoderMelspectrogram TTS/Chatterbox/VoiceEncoder/VoiceEncoderMelspec.swift:17-68 with VoiceEncConfig
  * (Config/ChatterboxConfig.swift:139-156).  out (batch, num_mels, T'). */

@@ -79,6 +79,9 @@ SIGNATURES = {
     "b2a_apply_lfr": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_apply_cmvn": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "b2a_funasr_preprocess_audio": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "b2a_funasr_preprocess_audio_pcm16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "b2a_kaldi_fbank_campplus_pcm16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int]),
+    "b2a_s3gen_mel_spectrogram_pcm16": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_kaldi_fbank_campplus": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int]),
     "b2a_s3gen_mel_spectrogram": (C.c_int, [_ctx, C.c_void_p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "b2a_voice_enc_config_default": (None, [C.POINTER(VoiceEncConfig)]),

@@ -150,6 +150,31 @@ class DevicePtr:
         return self.address
 
 
+def _arr_pcm(audio):
+    """(_Arr, is_int16): 16-bit PCM (NumPy int16 array or torch int16 CUDA tensor) keeps its bytes -- the library converts
+    (sample = int16 / 32768, as AVAudioFile decodes a 16-bit file) on the device; anything else goes through _Arr as float32."""
+    is_t = _is_torch(audio)
+    if is_t:
+        import torch
+        i16 = audio.dtype == torch.int16
+    else:
+        audio = np.asarray(audio)
+        i16 = audio.dtype == np.int16
+    if not i16:
+        return _Arr(audio), False
+    a = _Arr.__new__(_Arr)
+    if is_t:
+        if not audio.is_cuda:
+            raise B2AError(L.B2A_E_BAD_ARG, "torch tensors must live on a CUDA device (use NumPy arrays for host data)")
+        a.t, a.space, a.device = audio.contiguous(), L.B2A_DEVICE, audio.device.index or 0
+        a.ptr = C.c_void_p(a.t.data_ptr())
+    else:
+        a.t, a.space, a.device = np.ascontiguousarray(audio), L.B2A_HOST, None
+        a.ptr = C.c_void_p(a.t.ctypes.data)
+    a.shape = tuple(a.t.shape)
+    return a, True
+
+
 def _ptr(a):
     if _is_torch(a) or isinstance(a, DevicePtr):
         return C.c_void_p(a.data_ptr())
@@ -338,26 +363,7 @@ def whisperLogMelSpectrogramPCM16(audio_i16, nMels: int, padding: int = 0, ctx: 
 
 
 def _whisper_typed(audio, nMels, padding, ctx, out, f16: bool):
-    is_t = _is_torch(audio)
-    if is_t:
-        import torch
-        i16 = audio.dtype == torch.int16
-    else:
-        audio = np.asarray(audio)
-        i16 = audio.dtype == np.int16
-    if i16:
-        a = _Arr.__new__(_Arr)   # 16-bit PCM: same plumbing, no float conversion on the host
-        if is_t:
-            if not audio.is_cuda:
-                raise B2AError(L.B2A_E_BAD_ARG, "torch tensors must live on a CUDA device (use NumPy arrays for host data)")
-            a.t, a.space, a.device = audio.contiguous(), L.B2A_DEVICE, audio.device.index or 0
-            a.ptr = C.c_void_p(a.t.data_ptr())
-        else:
-            a.t, a.space, a.device = np.ascontiguousarray(audio), L.B2A_HOST, None
-            a.ptr = C.c_void_p(a.t.ctypes.data)
-        a.shape = tuple(a.t.shape)
-    else:
-        a = _Arr(audio)
+    a, i16 = _arr_pcm(audio)
     b, n, had = _batched(a, 1)
     c = _ctx_for(a, ctx)
     frames = int(c.lib.b2a_whisper_num_frames(n, padding))
@@ -468,8 +474,8 @@ def applyCMVN(features, cmvnMean=None, cmvnIstd=None, ctx: Context | None = None
 
 def preprocessAudio(audio, nMels: int = 80, lfrM: int = 7, lfrN: int = 6, applyNormalization: bool = True,
                     ctx: Context | None = None, out=None):
-    """STT/FunASR/FunASRAudio.swift:197-216 -> (ceil(T'/lfrN), nMels*lfrM)"""
-    a = _Arr(audio)
+    """STT/FunASR/FunASRAudio.swift:197-216 -> (ceil(T'/lfrN), nMels*lfrM).  ``audio`` may be 16-bit PCM (int16 / 32768)."""
+    a, i16 = _arr_pcm(audio)
     b, n, had = _batched(a, 1)
     c = _ctx_for(a, ctx)
     frames = int(c.lib.b2a_funasr_num_frames(n))
@@ -477,15 +483,16 @@ def preprocessAudio(audio, nMels: int = 80, lfrM: int = 7, lfrN: int = 6, applyN
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
     rows = int(c.lib.b2a_lfr_num_rows(frames, lfrN))
     out = _out_for(a, (b, rows, nMels * lfrM), out)
-    c.check(c.lib.b2a_funasr_preprocess_audio(c.h, a.ptr, b, n, nMels, lfrM, lfrN, int(applyNormalization), _ptr(out), a.space))
+    fn = c.lib.b2a_funasr_preprocess_audio_pcm16 if i16 else c.lib.b2a_funasr_preprocess_audio
+    c.check(fn(c.h, a.ptr, b, n, nMels, lfrM, lfrN, int(applyNormalization), _ptr(out), a.space))
     return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def kaldiFbankCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 80, frameLength: float = 25.0,
                        frameShift: float = 10.0, meanNorm: bool = False, ctx: Context | None = None, out=None):
     """Codec/S3Gen/CAMPPlus.swift:32-106 -> (T', numMelBins).  ``meanNorm`` adds the caller-side
-    ``fbank - mean(fbank, axis: 0)`` of CAMPPlus.inference (:797-802)."""
-    a = _Arr(audio)
+    ``fbank - mean(fbank, axis: 0)`` of CAMPPlus.inference (:797-802).  ``audio`` may be 16-bit PCM (int16 / 32768)."""
+    a, i16 = _arr_pcm(audio)
     b, n, had = _batched(a, 1)
     c = _ctx_for(a, ctx)
     win = int(np.float32(sampleRate) * np.float32(frameLength) / np.float32(1000))
@@ -494,24 +501,24 @@ def kaldiFbankCAMPPlus(audio, sampleRate: int = 16000, numMelBins: int = 80, fra
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "signal shorter than one analysis window")
     out = _out_for(a, (b, frames, numMelBins), out)
-    c.check(c.lib.b2a_kaldi_fbank_campplus(c.h, a.ptr, b, n, sampleRate, numMelBins, frameLength, frameShift, int(meanNorm),
-                                           _ptr(out), a.space))
+    fn = c.lib.b2a_kaldi_fbank_campplus_pcm16 if i16 else c.lib.b2a_kaldi_fbank_campplus
+    c.check(fn(c.h, a.ptr, b, n, sampleRate, numMelBins, frameLength, frameShift, int(meanNorm), _ptr(out), a.space))
     return out if had or isinstance(out, DevicePtr) else out[0]
 
 
 def s3genMelSpectrogram(y, nFft: int = 1920, numMels: int = 80, samplingRate: int = 24000, hopSize: int = 480,
                         winSize: int = 1920, fmin: int = 0, fmax: int = 8000, center: bool = False,
                         ctx: Context | None = None, out=None):
-    """Codec/S3Gen/Mel/S3GenMel.swift:43-102 : (B, T) or (T,) -> (B, numMels, T') or (numMels, T')"""
-    a = _Arr(y)
+    """Codec/S3Gen/Mel/S3GenMel.swift:43-102 : (B, T) or (T,) -> (B, numMels, T') or (numMels, T').  ``y`` may be 16-bit PCM (int16 / 32768)."""
+    a, i16 = _arr_pcm(y)
     b, n, had = _batched(a, 1)
     c = _ctx_for(a, ctx)
     frames = int(c.lib.b2a_s3gen_num_frames(n, nFft, hopSize))
     if frames <= 0:
         _raise(L.B2A_E_TOO_SHORT, "Input is too short for STFT")
     out = _out_for(a, (b, numMels, frames), out)
-    c.check(c.lib.b2a_s3gen_mel_spectrogram(c.h, a.ptr, b, n, nFft, numMels, samplingRate, hopSize, winSize, fmin, fmax,
-                                            _ptr(out), a.space))
+    fn = c.lib.b2a_s3gen_mel_spectrogram_pcm16 if i16 else c.lib.b2a_s3gen_mel_spectrogram
+    c.check(fn(c.h, a.ptr, b, n, nFft, numMels, samplingRate, hopSize, winSize, fmin, fmax, _ptr(out), a.space))
     return out if had or isinstance(out, DevicePtr) else out[0]
 
 

@@ -968,8 +968,9 @@ int b2a_log_mel_spectrogram_chatterbox_ragged(b2a_ctx* c, const float* audio, in
   return whisper_like(c, audio, batch, n_samples, n_mels, padding, out, space, true, lengths, out_frames);
 }
 
-static int funasr_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
-                         int lfr, int norm, float* out, int space, const int64_t* lengths = nullptr, int64_t* out_rows = nullptr) {
+static int funasr_common(b2a_ctx* c, const void* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
+                         int lfr, int norm, float* out, int space, const int64_t* lengths = nullptr, int64_t* out_rows = nullptr,
+                         bool in_i16 = false) {
   int rc = check_common(c, audio, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (n_mels <= 0) return fail(c, B2A_E_BAD_ARG, "n_mels must be positive");
@@ -993,6 +994,7 @@ static int funasr_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t 
     p.lfr_rows = b2a_lfr_num_rows(frames, lfr_n);
     p.post_cmvn = norm;
   }
+  p.in_i16 = in_i16;
   Ragged rg{lengths, [](int64_t len) { return b2a_funasr_num_frames(len); }, out_rows};
   return run_preset(c, p, audio, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
@@ -1004,6 +1006,11 @@ int b2a_funasr_log_mel_spectrogram(b2a_ctx* c, const float* audio, int64_t batch
 int b2a_funasr_preprocess_audio(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
                                 int apply_normalization, float* out, int space) {
   return funasr_common(c, audio, batch, n_samples, n_mels, lfr_m, lfr_n, 1, apply_normalization != 0, out, space);
+}
+
+int b2a_funasr_preprocess_audio_pcm16(b2a_ctx* c, const int16_t* audio, int64_t batch, int64_t n_samples, int n_mels, int lfr_m, int lfr_n,
+                                      int apply_normalization, float* out, int space) {
+  return funasr_common(c, audio, batch, n_samples, n_mels, lfr_m, lfr_n, 1, apply_normalization != 0, out, space, nullptr, nullptr, true);
 }
 
 int b2a_funasr_log_mel_spectrogram_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_mels,
@@ -1073,9 +1080,9 @@ int b2a_apply_cmvn(b2a_ctx* c, const float* features, int64_t batch, int64_t n_r
   return run_batched(c, space, batch, features, size_t(n_rows) * dim, nullptr, 0, out, size_t(n_rows) * dim, nullptr, 0, body);
 }
 
-static int kaldi_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
+static int kaldi_common(b2a_ctx* c, const void* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
                         float frame_length_ms, float frame_shift_ms, int mean_norm, float* out, int space, const int64_t* lengths,
-                        int64_t* out_rows) {
+                        int64_t* out_rows, bool in_i16 = false) {
   int rc = check_common(c, audio, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (sample_rate <= 0 || num_mel_bins <= 0) return fail(c, B2A_E_BAD_ARG, "sample_rate and num_mel_bins must be positive");
@@ -1102,6 +1109,7 @@ static int kaldi_common(b2a_ctx* c, const float* audio, int64_t batch, int64_t n
   p.log_floor = 1.1920929e-07f;
   p.n_frames = frames;
   p.post_mean_norm = mean_norm != 0;
+  p.in_i16 = in_i16;
   Ragged rg{lengths, [&](int64_t len) { return b2a_kaldi_num_frames(len, win_length, hop); }, out_rows};
   return run_preset(c, p, audio, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
@@ -1111,6 +1119,11 @@ int b2a_kaldi_fbank_campplus(b2a_ctx* c, const float* audio, int64_t batch, int6
   return kaldi_common(c, audio, batch, n_samples, sample_rate, num_mel_bins, frame_length_ms, frame_shift_ms, mean_norm, out, space, nullptr, nullptr);
 }
 
+int b2a_kaldi_fbank_campplus_pcm16(b2a_ctx* c, const int16_t* audio, int64_t batch, int64_t n_samples, int sample_rate, int num_mel_bins,
+                                   float frame_length_ms, float frame_shift_ms, int mean_norm, float* out, int space) {
+  return kaldi_common(c, audio, batch, n_samples, sample_rate, num_mel_bins, frame_length_ms, frame_shift_ms, mean_norm, out, space, nullptr, nullptr, true);
+}
+
 int b2a_kaldi_fbank_campplus_ragged(b2a_ctx* c, const float* audio, int64_t batch, int64_t n_samples, const int64_t* lengths, int sample_rate,
                                     int num_mel_bins, float frame_length_ms, float frame_shift_ms, int mean_norm, float* out,
                                     int64_t* out_frames, int space) {
@@ -1118,8 +1131,9 @@ int b2a_kaldi_fbank_campplus_ragged(b2a_ctx* c, const float* audio, int64_t batc
   return kaldi_common(c, audio, batch, n_samples, sample_rate, num_mel_bins, frame_length_ms, frame_shift_ms, mean_norm, out, space, lengths, out_frames);
 }
 
-static int s3gen_common(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
-                        int hop_size, int win_size, int fmin, int fmax, float* out, int space, const int64_t* lengths, int64_t* out_rows) {
+static int s3gen_common(b2a_ctx* c, const void* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
+                        int hop_size, int win_size, int fmin, int fmax, float* out, int space, const int64_t* lengths, int64_t* out_rows,
+                        bool in_i16 = false) {
   int rc = check_common(c, y, out, batch, n_samples);
   if (rc != B2A_OK) return rc;
   if (win_size > n_fft || win_size <= 0) return fail(c, B2A_E_BAD_ARG, "win_size must be in (0, n_fft]");
@@ -1144,6 +1158,7 @@ static int s3gen_common(b2a_ctx* c, const float* y, int64_t batch, int64_t n_sam
   if (lengths)   // reflectPad2D truncates the pad for clips of <= pad samples: one pad_left per launch, so those stay out of ragged batches
     for (int64_t b = 0; b < batch; ++b)
       if (lengths[b] <= pad) return fail(c, B2A_E_UNSUPPORTED, "ragged s3gen mel needs every clip longer than (n_fft - hop) / 2 samples");
+  p.in_i16 = in_i16;
   Ragged rg{lengths, [&](int64_t len) { return b2a_s3gen_num_frames(len, n_fft, hop_size); }, out_rows};
   return run_preset(c, p, y, batch, n_samples, out, space, lengths ? &rg : nullptr);
 }
@@ -1151,6 +1166,12 @@ static int s3gen_common(b2a_ctx* c, const float* y, int64_t batch, int64_t n_sam
 int b2a_s3gen_mel_spectrogram(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
                               int hop_size, int win_size, int fmin, int fmax, float* out, int space) {
   return s3gen_common(c, y, batch, n_samples, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, out, space, nullptr, nullptr);
+}
+
+int b2a_s3gen_mel_spectrogram_pcm16(b2a_ctx* c, const int16_t* y, int64_t batch, int64_t n_samples, int n_fft, int num_mels, int sampling_rate,
+                                    int hop_size, int win_size, int fmin, int fmax, float* out, int space) {
+  if (!frontend_plan_exists(n_fft, hop_size, n_fft)) return fail(c, B2A_E_UNSUPPORTED, "16-bit PCM input is built for the tuned (n_fft, hop) = (1920, 480) / (400, 160)");
+  return s3gen_common(c, y, batch, n_samples, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, out, space, nullptr, nullptr, true);
 }
 
 int b2a_s3gen_mel_spectrogram_ragged(b2a_ctx* c, const float* y, int64_t batch, int64_t n_samples, const int64_t* lengths, int n_fft,

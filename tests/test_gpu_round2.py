@@ -334,3 +334,24 @@ def test_chatterbox_log_mel_zero_tail_in_the_mel_major_layout(api, ctx, n, paddi
     assert_feat_close(got, want, what=f"chatterbox log-mel, n = {n}, padding = {padding}")
     xz = np.concatenate([x, np.zeros((2, padding), np.float32)], axis=1)
     assert np.array_equal(api.logMelSpectrogramChatterbox(xz, nMels=128, ctx=ctx), got), "virtual zero tail == explicit zeros, bit for bit"
+
+
+def test_pcm16_entries_of_the_other_front_ends_are_bit_identical(api, ctx):
+    # 16-bit PCM in (sample = int16 / 32768, exact in fp32): Fun-ASR preprocessAudio, CAM++ Kaldi fbank (+ mean-norm), S3Gen mel -- the same
+    # kernels behind a conversion pass, so the features equal those of the fp32 entry on the converted samples bit for bit (host and device space)
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(2201)
+    for sr, n, fn in ((16000, 16000 * 2 + 7, lambda a: api.preprocessAudio(a, ctx=ctx)),
+                      (16000, 16000 * 2 + 7, lambda a: api.kaldiFbankCAMPPlus(a, meanNorm=True, ctx=ctx)),
+                      (24000, 24000 + 333, lambda a: api.s3genMelSpectrogram(a, ctx=ctx))):
+        i16 = rng.integers(-20000, 20000, (3, n), dtype=np.int16)
+        f32 = i16.astype(np.float32) / np.float32(32768.0)
+        want = fn(f32)
+        got = fn(i16)
+        assert got.dtype == np.float32 and np.array_equal(got, want)
+        got_dev = fn(torch.from_numpy(i16).cuda())
+        assert np.array_equal(got_dev.cpu().numpy(), want)
+    # and against the oracle on the converted samples
+    f32 = (rng.integers(-20000, 20000, (2, 24000 + 333), dtype=np.int16).astype(np.float32) / np.float32(32768.0))
+    i16 = np.rint(f32 * 32768.0).astype(np.int16)
+    assert_feat_close(api.s3genMelSpectrogram(i16, ctx=ctx), R.s3gen_mel_spectrogram(f32), what="s3gen mel from 16-bit PCM")
