@@ -337,6 +337,41 @@ public final class B200Audio {
     return out
   }
 
+  // ---- 16-bit PCM in (sample = int16 / 32768, as AVAudioFile decodes a 16-bit file): half the bytes for a host caller, the same features --
+  /// preprocessAudio (STT/FunASR/FunASRAudio.swift:197-216) of 16-bit PCM
+  public func preprocessAudioPCM16(_ audio: [Int16], nMels: Int = 80, lfrM: Int = 7, lfrN: Int = 6, applyNormalization: Bool = true) -> Tensor {
+    let frames = b2a_funasr_num_frames(Int64(audio.count))
+    if frames <= 0 { fatalError("Input is too short for STFT") }
+    var out = Tensor(zeros: [Int(b2a_lfr_num_rows(frames, Int32(lfrN))), nMels * lfrM])
+    audio.withUnsafeBufferPointer { x in out.data.withUnsafeMutableBufferPointer { o in
+      check(b2a_funasr_preprocess_audio_pcm16(ctx, x.baseAddress, 1, Int64(audio.count), Int32(nMels), Int32(lfrM), Int32(lfrN), applyNormalization ? 1 : 0, o.baseAddress, host))
+    } }
+    return out
+  }
+  /// kaldiFbankCAMPPlus (Codec/S3Gen/CAMPPlus.swift:32-106) of 16-bit PCM; meanNorm adds CAMPPlus.swift:797-802
+  public func kaldiFbankCAMPPlusPCM16(audio: [Int16], sampleRate: Int = 16000, numMelBins: Int = 80, frameLength: Float = 25.0,
+                                      frameShift: Float = 10.0, meanNorm: Bool = false) -> Tensor {
+    let win = Int32(Float(sampleRate) * frameLength / 1000), hop = Int32(Float(sampleRate) * frameShift / 1000)
+    let frames = Int(b2a_kaldi_num_frames(Int64(audio.count), win, hop))
+    if frames <= 0 { fatalError("signal shorter than one analysis window") }
+    var out = Tensor(zeros: [frames, numMelBins])
+    audio.withUnsafeBufferPointer { x in out.data.withUnsafeMutableBufferPointer { o in
+      check(b2a_kaldi_fbank_campplus_pcm16(ctx, x.baseAddress, 1, Int64(audio.count), Int32(sampleRate), Int32(numMelBins), frameLength, frameShift, meanNorm ? 1 : 0, o.baseAddress, host))
+    } }
+    return out
+  }
+  /// s3genMelSpectrogram (Codec/S3Gen/Mel/S3GenMel.swift:43-102) of one 16-bit PCM clip -> (numMels, T')
+  public func s3genMelSpectrogramPCM16(y: [Int16], nFft: Int = 1920, numMels: Int = 80, samplingRate: Int = 24000, hopSize: Int = 480,
+                                       winSize: Int = 1920, fmin: Int = 0, fmax: Int = 8000) -> Tensor {
+    let frames = Int(b2a_s3gen_num_frames(Int64(y.count), Int32(nFft), Int32(hopSize)))
+    if frames <= 0 { fatalError("Input is too short for STFT") }
+    var out = Tensor(zeros: [numMels, frames])
+    y.withUnsafeBufferPointer { x in out.data.withUnsafeMutableBufferPointer { o in
+      check(b2a_s3gen_mel_spectrogram_pcm16(ctx, x.baseAddress, 1, Int64(y.count), Int32(nFft), Int32(numMels), Int32(samplingRate), Int32(hopSize), Int32(winSize), Int32(fmin), Int32(fmax), o.baseAddress, host))
+    } }
+    return out
+  }
+
   // ---- CosyVoice3 / Kokoro vocoder transforms -----------------------------------------------------------------------------------
   /// TTS/CosyVoice3/HiFiGAN/CausalHiFTGenerator.swift:435-460: x (B, T) -> (real, imag) each (B, nFft/2+1, frames), zero padding
   public func cosyVoice3Stft(x: Tensor, nFft: Int, hopLength: Int, window: Tensor) -> (Tensor, Tensor) {

@@ -39,8 +39,6 @@ NOT_BOUND = {
     "b2a_log_mel_spectrogram_chatterbox_ragged": "ragged: bound like whisperLogMelSpectrogramRagged", "b2a_funasr_log_mel_spectrogram_ragged": "ragged",
     "b2a_voice_encoder_melspectrogram_ragged": "ragged", "b2a_funasr_preprocess_audio_ragged": "ragged", "b2a_kaldi_fbank_campplus_ragged": "ragged",
     "b2a_s3gen_mel_spectrogram_ragged": "ragged", "b2a_whisper_log_mel_spectrogram_f16_ragged": "ragged",
-    "b2a_funasr_preprocess_audio_pcm16": "16-bit PCM: bound like whisperLogMelSpectrogramPCM16", "b2a_kaldi_fbank_campplus_pcm16": "16-bit PCM",
-    "b2a_s3gen_mel_spectrogram_pcm16": "16-bit PCM",
 }
 
 
