@@ -637,7 +637,7 @@ def measure(name, args, env, steps, warmup, e2e_steps, want_cpu, batch=None, det
 
         dt32 = timed(wl.step_host, e2e_steps)
         f32 = {"value": wl.audio_s * world / dt32, "unit": UNIT, "h2d_bytes_per_step": wl.in_bytes, "d2h_bytes_per_step": wl.out_bytes,
-               "ms_per_step": dt32 * 1e3, "steps": e2e_steps, "entry": "fp32 PCM in, fp32 features out"}
+               "ms_per_step": dt32 * 1e3, "steps": e2e_steps, "entry": "fp32 inputs in, fp32 results out"}
         e2e = f32
         if wl.e2e16 is not None:
             dt16 = timed(wl.step_host16, e2e_steps)
