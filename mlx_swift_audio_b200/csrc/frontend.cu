@@ -1065,14 +1065,21 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 // Rewrites only the tiles whose minimum lies below the clip's clamp threshold:
 //   (max(L, Lmax - 8) + 4) / 4 == max((L + 4) / 4, (Lmax + 4) / 4 - 2)   (x -> (x+4)/4 is monotone)
 // WhisperAudio.swift:130-134, S3TokenizerUtils.swift:203-205.
-// One CTA per (clip, group of kClampTilesPerCta tiles): the group's tile minima are tested in parallel (one round trip to
+// One CTA per (clip, group of `group` <= kClampTilesPerCta tiles; small launches take smaller groups, down to one tile per CTA: for one 30 s
+// clip three CTAs walking 32 tiles each took 18 us, more than the front-end kernel itself): the group's tile minima are tested in parallel (one round trip to
 // memory), the tiles that need it are rewritten with 16-byte accesses.
 constexpr int kClampTilesPerCta = 32;
+// tiles per CTA of the clamp kernel: enough CTAs to fill the GPU for small launches (one tile per CTA up to ~2000 tiles), kClampTilesPerCta for large ones
+static inline int clamp_group(long long total_tiles) {
+  int g = 1;
+  while (g < kClampTilesPerCta && total_tiles / g > 2048) g *= 2;
+  return g;
+}
 constexpr int kFillFlag = 0x40000000;   // s_list entry: the tile was skipped by the main kernel (kTileFill), write the threshold without reading
 // clip_tab != null (ragged batch): the clip's own frame count and first tile; `n_frames` stays the (M, T') row stride.
 __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                                             long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft,
-                                                            const int4* __restrict__ clip_tab, int f16, float log_floor) {
+                                                            const int4* __restrict__ clip_tab, int f16, float log_floor, int group) {
   __shared__ int s_list[kClampTilesPerCta];
   __shared__ int s_count;
   // launched with programmatic stream serialisation behind the front-end kernel (launch_plan): the blocks may already be resident
@@ -1092,10 +1099,10 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
   // with the expression (and the MUFU) the store loop used for floored values in round 1
   const float norm_floor = log_floor > 0.0f ? fmaf(lg2_ftz(log_floor), 0.25f * 0.30102999566398120f, 1.0f) : -3.0e38f;
   const float thr = fmaxf(dec_ordered(clip_max[clip]) - 2.0f, norm_floor);
-  const int t0 = blockIdx.x * kClampTilesPerCta;
+  const int t0 = blockIdx.x * group;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  if (threadIdx.x < kClampTilesPerCta && t0 + int(threadIdx.x) < tiles_per_clip) {
+  if (int(threadIdx.x) < group && t0 + int(threadIdx.x) < tiles_per_clip) {
     const int tm = tile_min[tile_base + t0 + threadIdx.x];   // the negated minimum, or kTileFill: a tile of silence the main kernel skipped
     if (tm == kTileFill) s_list[atomicAdd(&s_count, 1)] = (t0 + threadIdx.x) | kFillFlag;
     else if (-dec_ordered(tm) < thr) s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
@@ -1856,7 +1863,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     for (long long c0 = 0; c0 < a.batch; c0 += 65535) {   // gridDim.y limit
       const long long nb = std::min<long long>(65535, a.batch - c0);
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(unsigned((prm.tiles_per_clip + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb));
+      const int group = clamp_group(prm.total_tiles);
+      cfg.gridDim = dim3(unsigned((prm.tiles_per_clip + group - 1) / group), unsigned(nb));
       cfg.blockDim = dim3(256);
       cfg.dynamicSmemBytes = 0;
       cfg.stream = st;
@@ -1871,7 +1879,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       const int* c_min = RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip;
       const int4* c_tab = RAGGED ? prm.clip_tab + c0 : nullptr;
       if ((e = cudaLaunchKernelEx(&cfg, whisper_clamp_kernel, c_out, c_max, c_min, prm.tiles_per_clip, (long long)a.n_frames, a.bank.n_mels,
-                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0, clamp_floor)) != cudaSuccess)
+                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0, clamp_floor, group)) != cudaSuccess)
         return cuda_fail(e, "whisper_clamp_kernel launch", err);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
@@ -1886,8 +1894,9 @@ int launch_whisper_clamp(float* out, const int* clip_max, const int* tile_min, i
   const long long stride = n_frames * (long long)n_mels;
   for (long long c0 = 0; c0 < batch; c0 += 65535) {   // gridDim.y limit
     const long long nb = std::min<long long>(65535, batch - c0);
-    whisper_clamp_kernel<<<dim3(unsigned((tiles + kClampTilesPerCta - 1) / kClampTilesPerCta), unsigned(nb)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0, -1.0f);
+    const int group = clamp_group((long long)tiles * batch);
+    whisper_clamp_kernel<<<dim3(unsigned((tiles + group - 1) / group), unsigned(nb)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0, -1.0f, group);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
