@@ -383,7 +383,9 @@ B2A_API int b2a_debug_mel_program_dump(const float* bank, int n_mels, int n_bins
  * process; the environment variable B2A_WHISPER_TC=1 sets the initial state.  Off by default: DESIGN.md section 6. */
 B2A_API int b2a_debug_whisper_tc(int on);
 /* Switches the warp-per-frame n_fft 1920 front end (csrc/wpf1920.cu; on by default, B2A_WPF1920=0 sets the initial state to off) on / off
- * for the process: off = the tiled lane == frame kernel of csrc/frontend.cu runs the S3Gen mel (A/B switch, both are parity-tested). */
+ * for the process: off = the tiled lane == frame kernel of csrc/frontend.cu runs the S3Gen mel (A/B switch, both are parity-tested).
+ * on == 2: the warp-per-frame kernel without its pruned stage B (banks that end at or below bin 640, e.g. S3Gen's fmax 8000 Hz at
+ * 24 kHz, normally skip the ten dead outputs of every 32-point transform; results are bit-identical either way). */
 B2A_API int b2a_debug_wpf1920(int on);
 /* Bring-up hook of the tensor-core Whisper front end (B2A_WHISPER_TC=1): when a device buffer of (batch, T', 201) floats is set, the
  * kernel also leaves the power spectrum |X[k]|^2 of every frame there.  NULL switches it off. */

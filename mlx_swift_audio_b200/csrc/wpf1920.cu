@@ -92,7 +92,18 @@ __device__ __noinline__ void wpf_stage_edge(const float* __restrict__ xc, float*
   }
 }
 
-template <int NW, bool MAG, bool RAGGED>
+// PRUNE: the bank reads no bin above kPruneBins - 1 (S3Gen's 80 filters end at 8 kHz = bin 640 of 961).  Bin k1 + 60 k2 or its mirror
+// image 1920 - k1 - 60 k2 then lies above that limit for k2 = 11..20 in EVERY lane: those ten outputs of the 32-point codelet are never
+// formed (the compiler drops the butterflies that only feed them) and their |X| / store disappear: -6 % instructions per frame.  The mel
+// schedule's 16-byte reads may still touch words above the limit (zero weights): they hold this frame's exchange values or the
+// never-written pad words of the exchange rows, zeroed once per kernel -- finite, so 0 * v == 0.
+constexpr int kPruneBins = 641, kPruneLo = 11, kPruneHi = 20, kPruneDummy = 2848;
+static_assert(kPruneDummy % 32 == 0 && kPruneDummy - 60 * 31 >= kN / 2 + 4 && kPruneDummy + 2 - 60 * (kPruneHi + 1) < kExWords, "dummy mirror stores stay behind the spectrum, inside the warp's buffer");
+static_assert((9 * kExPitch * 2 + 64) / 4 * 4 >= (kPruneBins & ~3) && 14 * kExPitch * 2 + 64 >= kN / 2 + 4, "pad words of rows 9..13 are the ones inside [640, 964)");
+static_assert(60 * kPruneLo >= kPruneBins && kN - 29 - 60 * kPruneHi >= kPruneBins, "pruned outputs are dead in every lane");
+static_assert(60 * (kPruneLo - 1) + 30 < kPruneBins, "kept direct outputs are alive in every lane (no partial prune below the band)");
+
+template <int NW, bool MAG, bool RAGGED, bool PRUNE>
 __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_constant__ WpfParams prm) {
   extern __shared__ __align__(16) float smem[];
   float* s_win = smem;                                              // [lane][60]: window of the lane's samples (rot + 32 n1 + lane) mod 1920
@@ -114,6 +125,8 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
   }
   for (int i = tid; i < 30 * 32; i += NW * 32) s_tw[i] = c_wpf_tw[i];
   for (int i = tid; i < prm.mel_words; i += NW * 32) s_mel[i] = __ldg(prm.mel + i);
+  if (PRUNE)
+    for (int i = lane; i < kExWords; i += 32) s_ex[i] = 0.0f;   // (the pad words of the exchange rows are never written again)
   __syncthreads();
 
   const int M = prm.n_mels, rounds = int(s_mel[1]);
@@ -207,15 +220,29 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
           xr[2 * q] = v.x; xi[2 * q] = v.y; xr[2 * q + 1] = v.z; xi[2 * q + 1] = v.w;
         }
         __syncwarp();   // every lane holds its row: the buffer becomes the spectrum
+        // the pad words of exchange rows 9..13 lie in the pruned band and may hold an edge frame's staged samples: one store keeps them
+        // zero (a NaN sample must not outlive its frame through 0 * NaN in the mel schedule's slack reads)
+        if (PRUNE && lane < 20) s_ex[(9 + (lane >> 2)) * kExPitch * 2 + 64 + (lane & 3)] = 0.0f;
         b2a_cdft32(xr, xi, ur, ui);
         float* pd = s_ex + lane;             // bin lane + 60 k2
         float* pm = s_ex + kN - lane;        // bin 1920 - lane - 60 k2
         const bool direct = lane < 31, mirror = lane >= 1 && lane < 30;
+        if (PRUNE) {
+          // No predicates on the stores (with only two loop-invariant conditions left the compiler builds one copy of stage B per
+          // condition and a warp runs both): lane 31 repeats lane 30's stores word for word, and the three lanes without mirror images
+          // write theirs into the exchange rows behind the spectrum, dead since the row loads (banks 0, 1, 2: the ones lanes 1..29 leave free).
+          pd = s_ex + k1;
+          if (!mirror) pm = s_ex + kPruneDummy + (lane == 0 ? 0 : 32 - lane);
+        }
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2) {
+          if (PRUNE && k2 >= kPruneLo && k2 <= kPruneHi) continue;
           float pw = ur[k2] * ur[k2] + ui[k2] * ui[k2];
           if (MAG) pw = wpf_sqrt(pw);
-          if (k2 < 16) {
+          if (PRUNE) {
+            if (k2 < kPruneLo) pd[60 * k2] = pw;
+            else pm[-60 * k2] = pw;
+          } else if (k2 < 16) {
             if (direct) pd[60 * k2] = pw;
           } else if (k2 == 16) {
             if (lane == 0) s_ex[960] = pw;          // the Nyquist bin belongs to row 0
@@ -270,7 +297,7 @@ int cuda_fail(cudaError_t e, const char* what, std::string* err) {
   return B2A_E_CUDA;
 }
 
-template <int NW, bool MAG, bool RAGGED>
+template <int NW, bool MAG, bool RAGGED, bool PRUNE>
 int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
   constexpr size_t smem = sizeof(float) * size_t(kTableWords + NW * kWarpWords);
   struct DevInfo { std::atomic<int> ready{0}; int n_sm = 0; };
@@ -287,7 +314,7 @@ int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
   if (!di.ready.load(std::memory_order_acquire)) {
     std::lock_guard<std::mutex> lk(mu);
     if (!di.ready.load(std::memory_order_relaxed)) {
-      if ((e = cudaFuncSetAttribute(wpf1920_kernel<NW, MAG, RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
+      if ((e = cudaFuncSetAttribute(wpf1920_kernel<NW, MAG, RAGGED, PRUNE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
         return cuda_fail(e, "cudaFuncSetAttribute", err);
       int n_sm = 148;
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -296,7 +323,7 @@ int launch_t(const WpfParams& prm, cudaStream_t st, std::string* err) {
     }
   }
   const long long blocks = std::min<long long>((prm.total_strips + NW - 1) / NW, di.n_sm);   // one persistent CTA per SM
-  wpf1920_kernel<NW, MAG, RAGGED><<<unsigned(blocks), NW * 32, smem, st>>>(prm);
+  wpf1920_kernel<NW, MAG, RAGGED, PRUNE><<<unsigned(blocks), NW * 32, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "wpf1920_kernel launch", err);
   return B2A_OK;
 }
@@ -317,12 +344,17 @@ int init_wpf1920_tables(std::string* err) {
 
 // On by default; B2A_WPF1920=0 in the environment or b2a_debug_wpf1920(0) keeps the tiled lane == frame kernel of frontend.cu (A/B switch)
 static int g_wpf_enabled = -1;
-void wpf1920_enable(int on) { g_wpf_enabled = on ? 1 : 0; }
+static int g_wpf_prune = 1;   // b2a_debug_wpf1920(2) = warp-per-frame kernel without the pruned stage B (A/B and the parity test of the unpruned path)
+void wpf1920_enable(int on) {
+  g_wpf_enabled = on ? 1 : 0;
+  g_wpf_prune = on == 2 ? 0 : 1;
+}
 
 bool wpf1920_applicable(const FrontendArgs& a) {
   if (g_wpf_enabled < 0) {
     const char* v = getenv("B2A_WPF1920");
     g_wpf_enabled = (v != nullptr && v[0] == '0') ? 0 : 1;
+    if (v != nullptr && v[0] == '2') g_wpf_prune = 0;
   }
   return g_wpf_enabled == 1 && a.n_fft == kN && a.hop == kHop && a.win_len == kN && a.pre_mode == PRE_NONE && a.bank.wpf_mel != nullptr && (a.clip_tab == nullptr || (a.tile_tab != nullptr && a.total_tiles > 0)) &&
          a.bank.n_mels <= kWpfRounds * 32 && !a.whisper_norm && !a.out_f16 && a.out_mode == OUT_MT &&
@@ -356,8 +388,16 @@ int launch_wpf1920(const FrontendArgs& a, void* stream, int* launches, std::stri
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool mag = a.spec_mode == SPEC_MAGNITUDE;
   int rc;
-  if (a.clip_tab) rc = mag ? launch_t<B2A_WPF_WARPS, true, true>(prm, st, err) : launch_t<B2A_WPF_WARPS, false, true>(prm, st, err);
-  else rc = mag ? launch_t<B2A_WPF_WARPS, true, false>(prm, st, err) : launch_t<B2A_WPF_WARPS, false, false>(prm, st, err);
+  // banks that end at or below bin 640 (every S3Gen configuration of the reference: fmax 8000 Hz at 24 kHz) run the pruned stage B
+  const bool prune = g_wpf_prune != 0 && a.bank.n_bins_used > 0 && a.bank.n_bins_used <= kPruneBins;
+  constexpr int W = B2A_WPF_WARPS;
+  if (prune) {
+    if (a.clip_tab) rc = mag ? launch_t<W, true, true, true>(prm, st, err) : launch_t<W, false, true, true>(prm, st, err);
+    else rc = mag ? launch_t<W, true, false, true>(prm, st, err) : launch_t<W, false, false, true>(prm, st, err);
+  } else {
+    if (a.clip_tab) rc = mag ? launch_t<W, true, true, false>(prm, st, err) : launch_t<W, false, true, false>(prm, st, err);
+    else rc = mag ? launch_t<W, true, false, false>(prm, st, err) : launch_t<W, false, false, false>(prm, st, err);
+  }
   if (rc == B2A_OK) *launches += 1;
   return rc;
 }

@@ -131,3 +131,28 @@ def test_s3gen_pure_tone_against_fp64_truth(api, ctx, both_kernels):
     bar = max(1e-4, 4.0 * e32)
     assert err(new) <= bar and err(old) <= bar, (err(new), err(old), e32)
     assert err(new) <= max(1e-4, 2.0 * err(old)), (err(new), err(old))
+
+
+def test_pruned_stage_b_is_bit_identical(api, ctx):
+    # S3Gen's bank ends at bin 639 of 961 (fmax 8000 Hz at 24 kHz), so the kernel skips the ten outputs of every 32-point stage-B transform
+    # that only feed bins 641..960 (wpf1920.cu, PRUNE); b2a_debug_wpf1920(2) runs the same kernel with every bin formed.  Interior frames,
+    # edge frames (staged through the exchange buffer, whose pad words lie in the pruned band) and ragged tiles must agree bit for bit,
+    # and a NaN sample in an edge frame must not leak into later frames of the same warp.
+    x = synth.pcm(5, 24000 * 2 + 123, sample_rate=24000, seed=3007)
+    short = synth.pcm(3, 1441, sample_rate=24000, seed=3008, zero_tail_frac=0.0)
+    lengths = [24000, 480 * 17, 24000 * 2 + 5, 1921, 9600]
+    bad = x.copy()
+    bad[:, 3] = np.nan   # frames 0 and 1 of every clip (reflect pad 720: sample 3 also appears mirrored in frame 0)
+    try:
+        ctx.lib.b2a_debug_wpf1920(1)
+        p = [api.s3genMelSpectrogram(x, ctx=ctx), api.s3genMelSpectrogram(short, ctx=ctx),
+             np.asarray(api.s3genMelSpectrogramRagged(x[:, :24000 * 2 + 5], lengths, ctx=ctx)[0]), api.s3genMelSpectrogram(bad, ctx=ctx)]
+        ctx.lib.b2a_debug_wpf1920(2)
+        u = [api.s3genMelSpectrogram(x, ctx=ctx), api.s3genMelSpectrogram(short, ctx=ctx),
+             np.asarray(api.s3genMelSpectrogramRagged(x[:, :24000 * 2 + 5], lengths, ctx=ctx)[0]), api.s3genMelSpectrogram(bad, ctx=ctx)]
+    finally:
+        ctx.lib.b2a_debug_wpf1920(1)
+    for a, b, name in zip(p, u, ("interior", "short clips", "ragged", "NaN sample")):
+        assert np.array_equal(a, b, equal_nan=True), f"pruned and unpruned stage B differ: {name}"
+    # frames that do not contain sample 3 (frame t covers samples 480 t - 720 .. 480 t + 1199): untouched by the NaN
+    assert np.array_equal(p[3][:, :, 2:], p[0][:, :, 2:])
