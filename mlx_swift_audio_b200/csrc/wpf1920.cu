@@ -70,6 +70,11 @@ struct WpfParams {
   float window[kN];
 };
 
+// L2 prefetch of a 128-byte line (no register, no scoreboard): the next frame's samples are requested one frame (~2.5 us) ahead
+#ifndef B2A_WPF_PREFETCH
+#define B2A_WPF_PREFETCH 1
+#endif
+B2A_DEV void wpf_prefetch(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 B2A_DEV float wpf_sqrt(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -173,6 +178,8 @@ __global__ void __launch_bounds__(NW * 32, 1) wpf1920_kernel(const __grid_consta
 #pragma unroll
         for (int n1 = 0; n1 < kN1 - 1; ++n1) in[n1] = __ldg(p + 32 * n1);
         in[kN1 - 1] = __ldg(p + last_off);
+        // the 480 samples the next frame of this strip adds (15 aligned lines; every line start is a sample of that frame), if that frame is interior too
+        if (B2A_WPF_PREFETCH && f + 1 < nf && lane < 15 && j0 + kHop + kN <= n_samples) wpf_prefetch(xc + j0 + rot + kN + 32 * lane);
       } else {
         wpf_stage_edge(xc, s_ex, p0, prm.pad_left, n_samples, n_samples + prm.zero_tail, prm.pad_mode, rot, lane);
         __syncwarp();
