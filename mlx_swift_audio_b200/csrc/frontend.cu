@@ -186,6 +186,11 @@ struct FrontendParams {
   // Strides (clip_stride, out_clip_stride) stay those of the longest clip.
   const int4* clip_tab;
   const int4* tile_tab;
+  // Dynamic tile walk (equal-length launches of more than two rounds): after its first tile (blockIdx.x) a CTA takes tile
+  // gridDim.x + (atomicAdd(tile_ctr, 1) - tile_ctr_init) instead of the static blockIdx.x + k * gridDim.x -- CTAs that run ahead (an SM with
+  // 7 instead of 8 warps on a scheduler, fewer edge tiles) take more tiles and the launch ends without a tail.  null = static walk.
+  int* tile_ctr;
+  int tile_ctr_init;
   float window[P::WIN];
 };
 
@@ -487,6 +492,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   if (steps_in_smem)
     for (int i = threadIdx.x; i < prm.n_steps; i += P::NTHREADS) s_steps[i] = __ldg(prm.fb_steps + i);
   __shared__ float s_part[PRE == PRE_KALDI ? NW * FT : 1];   // Kaldi: per-warp partial sums of the frame mean
+  __shared__ int s_next;   // dynamic tile walk: the tile the counter handed to this CTA for its next round (published by the post-A barrier)
+  const bool dyn = !RAGGED && !ZS && prm.tile_ctr != nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // frame lane; item / chunk slot of this (half-)warp.  The two half-warps of a 16-frame plan take slots NW apart (not adjacent):
   // their stage-A items then start 16 samples apart, so the 32 lanes' PCM loads (row pitch HOP + 1) fall into 32 different banks
@@ -621,6 +628,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       }
     }
 
+    int next_req = 0;   // dynamic walk, thread 0: the CTA's next tile (the answer is needed behind stage A)
+    if (dyn && tid == 0) next_req = int(gridDim.x) + (atomicAdd(prm.tile_ctr, 1) - prm.tile_ctr_init);
+
     // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
     if (!LATE_TOP) {
       cp_async_commit_wait_all();
@@ -680,7 +690,14 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
+    if (dyn && tid == 0) s_next = next_req;
     __syncthreads();
+    if (dyn) {
+      const int ngd = s_next;
+      nclip = ngd / tpc;
+      ntile = ngd - nclip * tpc;
+      if (ngd >= prm.total_tiles) nclip = n_clips;
+    }
     if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
 
     // ---- 3. stage B: DFTs of size N2 over n2; bins k = k1 + N1*k2 (mirrored above N/2) -------------
@@ -1722,6 +1739,7 @@ bool frontend_plan_exists(int n_fft, int hop, int win_len) {
          (n_fft == 1920 && hop == 480 && win_len == 1920);
 }
 
+bool frontend_dyn_tiles();
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   const PlanShape* ps = plan_shape(n_fft);
   const int ft = ps ? ps->frame_tile : 32;
@@ -1846,7 +1864,20 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   }
   const int n_sm = di.n_sm, per_sm = di.per_sm;
   const long long nblocks = std::min<long long>(prm.total_tiles, (long long)n_sm * per_sm);  // persistent CTAs
-  if (a.whisper_norm) {
+  // dynamic tile walk for launches of more than two rounds; its counter sits behind the clamp tables when there are any (their memset
+  // initialises it too: 0x80808080), otherwise it gets a 4-byte memset of its own
+  prm.tile_ctr = nullptr;
+  prm.tile_ctr_init = 0;
+  if (!RAGGED && !ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > 2 * nblocks) {
+    prm.tile_ctr = a.tile_ctr;
+    if (a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch && a.tile_ctr == a.clip_max + a.batch + prm.total_tiles) {
+      prm.tile_ctr_init = int(0x80808080u);
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + prm.total_tiles + 1), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+    } else {
+      if ((e = cudaMemsetAsync(a.tile_ctr, 0, sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+    }
+  }
+  if (a.whisper_norm && prm.tile_ctr_init == 0) {
     // clip_max and the (negated) tile minima start from the same "very negative" pattern: one memset when the C ABI placed them
     // back to back
     if (reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch) {
@@ -1915,6 +1946,17 @@ int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, co
     return b.id;
   }
   return 0;
+}
+
+// B2A_DYN_TILES=0 in the environment or frontend_dyn_tiles_enable(0): static tile walk everywhere (A/B switch)
+static int g_dyn_tiles = -1;
+void frontend_dyn_tiles_enable(int on) { g_dyn_tiles = on ? 1 : 0; }
+bool frontend_dyn_tiles() {
+  if (g_dyn_tiles < 0) {
+    const char* v = getenv("B2A_DYN_TILES");
+    g_dyn_tiles = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  return g_dyn_tiles == 1;
 }
 
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err) {

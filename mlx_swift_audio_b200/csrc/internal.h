@@ -118,10 +118,12 @@ struct FrontendArgs {
   const void* clip_tab = nullptr;
   const void* tile_tab = nullptr;
   int64_t total_tiles = 0;
+  int* tile_ctr = nullptr;   // one int of device scratch for the dynamic tile walk (behind the clamp tables when whisper_norm is set); null = static walk
 };
 
 // Returns 0 or a b2a_status; sets *launches to the number of kernels enqueued.
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err);
+void frontend_dyn_tiles_enable(int on);
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames);
 int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, const int* chunk_s, int n_chunks, int frame_tile, int n_mels);
 bool frontend_plan_exists(int n_fft, int hop, int win_len);
