@@ -459,7 +459,7 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
       a.clip_max = static_cast<int*>(c->scratch[slot][0].p);
       a.tile_min = reinterpret_cast<float*>(a.clip_max + n);
       a.tile_ctr = a.clip_max + n + n_tiles;   // the dynamic tile walk's counter, initialised by the same memset
-    } else if (!rg) {
+    } else {
       int rc;
       if ((rc = ensure(c, c->scratch[slot][0], sizeof(int))) != B2A_OK) return rc;
       a.tile_ctr = static_cast<int*>(c->scratch[slot][0].p);

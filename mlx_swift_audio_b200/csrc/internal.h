@@ -124,6 +124,7 @@ struct FrontendArgs {
 // Returns 0 or a b2a_status; sets *launches to the number of kernels enqueued.
 int launch_frontend(const FrontendArgs& a, void* stream, int* launches, std::string* err);
 void frontend_dyn_tiles_enable(int on);
+bool frontend_dyn_tiles();
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames);
 int frontend_match_baked(const float* steps, int n_steps, const int* chunk_m, const int* chunk_s, int n_chunks, int frame_tile, int n_mels);
 bool frontend_plan_exists(int n_fft, int hop, int win_len);
