@@ -494,6 +494,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   __shared__ float s_part[PRE == PRE_KALDI ? NW * FT : 1];   // Kaldi: per-warp partial sums of the frame mean
   __shared__ int s_next;   // dynamic tile walk: the tile the counter handed to this CTA for its next round (published by the post-A barrier)
   const bool dyn = !RAGGED && !ZS && prm.tile_ctr != nullptr;
+  // ragged batches: the counter's answer is an index into tile_tab, whose entry has to be loaded a tile ahead of its use -- so the walk is
+  // requested TWO tiles ahead (the CTA's first two tiles are static: blockIdx.x and blockIdx.x + gridDim.x)
+  const bool dyn_r = RAGGED && !ZS && prm.tile_ctr != nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // frame lane; item / chunk slot of this (half-)warp.  The two half-warps of a 16-frame plan take slots NW apart (not adjacent):
   // their stage-A items then start 16 samples apart, so the 32 lanes' PCM loads (row pitch HOP + 1) fall into 32 different banks
@@ -529,6 +532,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   long long n_samples = prm.n_samples, n_frames = prm.n_frames, lfr_rows = prm.lfr_rows;
   const long long zero_tail = prm.n_eff - prm.n_samples;
   long long g = blockIdx.x;    // RAGGED: index of the tile within the launch
+  long long g_next = (long long)blockIdx.x + gridDim.x, g_next2 = 0;   // dyn_r: the next tile's index and the one after it
   int first_tile = 0;
   const int lfr_n = prm.lfr_n > 0 ? prm.lfr_n : 1;
   auto set_clip = [&](const int4& t, long long gg) {   // tile_tab entry -> geometry of its clip
@@ -595,8 +599,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     int4 nt = make_int4(0, 0, 0, 0);    // RAGGED: the next tile's table entry
     if (RAGGED) {
       nclip = n_clips;
-      if (g + gridDim.x < prm.total_tiles) {
-        nt = __ldg(prm.tile_tab + g + gridDim.x);
+      const long long gn = dyn_r ? g_next : g + gridDim.x;
+      if (gn < prm.total_tiles) {
+        nt = __ldg(prm.tile_tab + gn);
         nclip = nt.x;
         ntile = nt.y;
         nn_samples = nt.z;
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     }
     // ZSKIP: the walk passes over tiles of silence (it only marks them for the clamp kernel's fill), so the tile staged behind stage A is
     // the next tile that is actually transformed -- no barrier, no exposed staging latency for a skipped tile
-    long long ng = g + gridDim.x;   // (RAGGED: launch-wide index of the next tile)
+    long long ng = dyn_r ? g_next : g + gridDim.x;   // (RAGGED: launch-wide index of the next tile)
     if (ZSKIP) {
       while (nclip < n_clips && tile_zero(ntile, nn_samples)) {
         if (tid == 0) prm.tile_min[RAGGED ? ng : (long long)nclip * tpc + ntile] = kTileFill;
@@ -630,6 +635,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
     int next_req = 0;   // dynamic walk, thread 0: the CTA's next tile (the answer is needed behind stage A)
     if (dyn && tid == 0) next_req = int(gridDim.x) + (atomicAdd(prm.tile_ctr, 1) - prm.tile_ctr_init);
+    if (dyn_r && tid == 0) next_req = 2 * int(gridDim.x) + (atomicAdd(prm.tile_ctr, 1) - prm.tile_ctr_init);
 
     // ---- 1. this tile's PCM has landed (and every warp is done with the previous tile's staging rows) -------------
     if (!LATE_TOP) {
@@ -690,8 +696,9 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if (dyn && tid == 0) s_next = next_req;
+    if ((dyn || dyn_r) && tid == 0) s_next = next_req;
     __syncthreads();
+    if (dyn_r) g_next2 = s_next;
     if (dyn) {
       const int ngd = s_next;
       nclip = ngd / tpc;
@@ -1074,6 +1081,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     tile = ntile;
     if (RAGGED) {
       g = ng;
+      g_next = g_next2;
       if (clip < n_clips) set_clip(nt, g);
     }
   }
@@ -1868,7 +1876,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   // initialises it too: 0x80808080), otherwise it gets a 4-byte memset of its own
   prm.tile_ctr = nullptr;
   prm.tile_ctr_init = 0;
-  if (!RAGGED && !ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > 2 * nblocks) {
+  if (!ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > (RAGGED ? 3 : 2) * nblocks) {
     prm.tile_ctr = a.tile_ctr;
     if (a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch && a.tile_ctr == a.clip_max + a.batch + prm.total_tiles) {
       prm.tile_ctr_init = int(0x80808080u);
