@@ -191,6 +191,10 @@ struct FrontendParams {
   // 7 instead of 8 warps on a scheduler, fewer edge tiles) take more tiles and the launch ends without a tail.  null = static walk.
   int* tile_ctr;
   int tile_ctr_init;
+  // Tiles [walk_tpc, tiles_per_clip) of every clip are tiles of silence (the caller's zero tail, Whisper's `padding`): the walk runs over the
+  // first walk_tpc tiles of every clip only, and the kernel's prologue marks the rest for the clamp kernel's fill (equal-length launches;
+  // ragged ones and tails the right-edge reflection reaches back out of keep the ZS instantiation's test per tile).
+  int walk_tpc;
   float window[P::WIN];
 };
 
@@ -526,8 +530,16 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
 
   // tile walk: (clip, tile) advances by gridDim.x tiles per iteration without divisions in the loop
   const int tpc = prm.tiles_per_clip, n_clips = prm.n_clips;
-  const int step_clip = int(gridDim.x) / tpc, step_tile = int(gridDim.x) - step_clip * tpc;
-  int clip = int(blockIdx.x) / tpc, tile = int(blockIdx.x) - clip * tpc;
+  const int wtpc = RAGGED ? tpc : prm.walk_tpc;   // tiles per clip the walk visits
+  const int step_clip = int(gridDim.x) / wtpc, step_tile = int(gridDim.x) - step_clip * wtpc;
+  int clip = int(blockIdx.x) / wtpc, tile = int(blockIdx.x) - clip * wtpc;
+  if (POST == POST_WNORM && !RAGGED && wtpc < tpc) {   // the tiles of silence behind the walk: filled by the clamp kernel
+    const int nz = tpc - wtpc;
+    for (long long i = (long long)blockIdx.x * P::NTHREADS + threadIdx.x; i < (long long)n_clips * nz; i += (long long)gridDim.x * P::NTHREADS) {
+      const long long c = i / nz;
+      prm.tile_min[c * tpc + wtpc + (i - c * nz)] = kTileFill;
+    }
+  }
   // geometry of the current clip: launch-wide constants, or (RAGGED) the clip's own row of clip_tab
   long long n_samples = prm.n_samples, n_frames = prm.n_frames, lfr_rows = prm.lfr_rows;
   const long long zero_tail = prm.n_eff - prm.n_samples;
@@ -574,8 +586,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
       } else {
         clip += step_clip;
         tile += step_tile;
-        if (tile >= tpc) {
-          tile -= tpc;
+        if (tile >= wtpc) {
+          tile -= wtpc;
           ++clip;
         }
       }
@@ -591,8 +603,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     const int f0 = tile * FT;
     float* s_r0 = smem;    // PCM tile (plain stft(): later the complex spectrum tile)
     int nclip = clip + step_clip, ntile = tile + step_tile;
-    if (ntile >= tpc) {
-      ntile -= tpc;
+    if (ntile >= wtpc) {
+      ntile -= wtpc;
       ++nclip;
     }
     long long nn_samples = n_samples;   // next tile's clip length
@@ -625,8 +637,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         } else {
           nclip += step_clip;
           ntile += step_tile;
-          if (ntile >= tpc) {
-            ntile -= tpc;
+          if (ntile >= wtpc) {
+            ntile -= wtpc;
             ++nclip;
           }
         }
@@ -701,8 +713,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     if (dyn_r) g_next2 = s_next;
     if (dyn) {
       const int ngd = s_next;
-      nclip = ngd / tpc;
-      ntile = ngd - nclip * tpc;
+      nclip = ngd / wtpc;
+      ntile = ngd - nclip * wtpc;
       if (ngd >= prm.total_tiles) nclip = n_clips;
     }
     if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
@@ -1756,9 +1768,26 @@ int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
 
 template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false, bool F16 = false, bool ZS = false>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
+  int walk_tpc = frontend_tiles_per_clip(P::N, a.n_frames);
   if constexpr (!ZS && B2A_SKIP_ZERO_TILES && B2A_RAW_TRACK && POST == POST_WNORM && MEL > 0 && PRE != PRE_KALDI) {
-    // a zero tail (Whisper `padding`): the instantiation that skips the tiles of silence
-    if (a.zero_tail > 0) return launch_plan<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, true>(a, st, launches, err);
+    // A zero tail (Whisper `padding`).  Equal lengths: the tiles of silence are the last tiles of every clip unless the right-edge
+    // reflection reaches back into the content -- then the walk simply ends in front of them (walk_tpc; the same test as the kernel's
+    // tile_zero).  Otherwise: the instantiation that tests every tile of its walk.
+    if (a.zero_tail > 0) {
+      const int tpc_all = walk_tpc;
+      auto tile_zero = [&](long long tl) {
+        const long long j0 = tl * (P::FT * P::HOP) - a.pad_left;
+        if (j0 < a.n_samples) return false;
+        const long long over = j0 + (P::TS - 1) - (a.n_samples + a.zero_tail);
+        return over < 0 || a.pad_mode != PAD_REFLECT || over <= a.zero_tail - 2;
+      };
+      int z0 = 0;
+      while (z0 < tpc_all && !tile_zero(z0)) ++z0;
+      bool tail_only = !RAGGED && a.clip_tab == nullptr && z0 > 0 && frontend_dyn_tiles();
+      for (int t = z0; t < tpc_all && tail_only; ++t) tail_only = tile_zero(t);
+      if (!tail_only) return launch_plan<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, true>(a, st, launches, err);
+      walk_tpc = z0;
+    }
   }
   if (!RAGGED && a.clip_tab != nullptr) {
     // per-clip lengths: the RAGGED instantiation of the run-time-configured kernel of the same plan (and of the Whisper
@@ -1811,6 +1840,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.clip_max = a.clip_max;
   prm.tile_min = reinterpret_cast<int*>(a.tile_min);
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
+  prm.walk_tpc = RAGGED ? prm.tiles_per_clip : walk_tpc;
   prm.n_clips = int(a.batch);
   prm.clip_tab = static_cast<const int4*>(a.clip_tab);
   prm.tile_tab = static_cast<const int4*>(a.tile_tab);
@@ -1834,7 +1864,8 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
                       (mt_table<P, MEL, OUT>() ? sizeof(int) * size_t(P::NWARPS * mt_slots<P, MEL>()) : 0);
   static_assert((P::R0_WORDS_REAL % 4) == 0 && (P::R0_WORDS_CPLX % 4) == 0 && (P::Y_WORDS % 4) == 0 && (P::N % 4) == 0 && (P::TW_WORDS % 4) == 0,
                 "shared-memory tables must stay 16-byte (window rows) / 8-byte (twiddles) aligned");
-  prm.total_tiles = RAGGED ? (long long)a.total_tiles : (long long)prm.tiles_per_clip * a.batch;
+  prm.total_tiles = RAGGED ? (long long)a.total_tiles : (long long)prm.walk_tpc * a.batch;   // tiles of the walk
+  const long long table_tiles = RAGGED ? (long long)a.total_tiles : (long long)prm.tiles_per_clip * a.batch;   // entries of tile_min
   if (prm.total_tiles <= 0 || prm.total_tiles > 0x7fffffffLL || a.batch > 0x7fffffffLL || a.n_frames > 0x7fffffffLL) {
     if (err) *err = "empty launch";
     return B2A_E_BAD_ARG;
@@ -1878,9 +1909,9 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.tile_ctr_init = 0;
   if (!ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > (RAGGED ? 3 : 2) * nblocks) {
     prm.tile_ctr = a.tile_ctr;
-    if (a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch && a.tile_ctr == a.clip_max + a.batch + prm.total_tiles) {
+    if (a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch && a.tile_ctr == a.clip_max + a.batch + table_tiles) {
       prm.tile_ctr_init = int(0x80808080u);
-      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + prm.total_tiles + 1), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + table_tiles + 1), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     } else {
       if ((e = cudaMemsetAsync(a.tile_ctr, 0, sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     }
@@ -1889,10 +1920,10 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     // clip_max and the (negated) tile minima start from the same "very negative" pattern: one memset when the C ABI placed them
     // back to back
     if (reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch) {
-      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + table_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     } else {
       if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
-      if ((e = cudaMemsetAsync(a.tile_min, 0x80, sizeof(int) * size_t(prm.total_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+      if ((e = cudaMemsetAsync(a.tile_min, 0x80, sizeof(int) * size_t(table_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     }
   }
   frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
@@ -1902,7 +1933,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     for (long long c0 = 0; c0 < a.batch; c0 += 65535) {   // gridDim.y limit
       const long long nb = std::min<long long>(65535, a.batch - c0);
       cudaLaunchConfig_t cfg = {};
-      const int group = clamp_group(prm.total_tiles);
+      const int group = clamp_group(table_tiles);
       cfg.gridDim = dim3(unsigned((prm.tiles_per_clip + group - 1) / group), unsigned(nb));
       cfg.blockDim = dim3(256);
       cfg.dynamicSmemBytes = 0;
