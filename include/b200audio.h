@@ -387,6 +387,10 @@ B2A_API int b2a_debug_whisper_tc(int on);
  * on == 2: the warp-per-frame kernel without its pruned stage B (banks that end at or below bin 640, e.g. S3Gen's fmax 8000 Hz at
  * 24 kHz, normally skip the ten dead outputs of every 32-point transform; results are bit-identical either way). */
 B2A_API int b2a_debug_wpf1920(int on);
+/* Switches the dynamic tile walk of the tiled front-end kernels on / off for the process (on by default; B2A_DYN_TILES=0 sets the initial
+ * state to off): on = after its first tile a persistent CTA takes its next tile from a launch-wide atomic counter, off = the static stride
+ * blockIdx.x + k * gridDim.x.  Results are bit-identical (every tile is computed the same way whoever computes it); A/B switch. */
+B2A_API int b2a_debug_dyn_tiles(int on);
 /* Bring-up hook of the tensor-core Whisper front end (B2A_WHISPER_TC=1): when a device buffer of (batch, T', 201) floats is set, the
  * kernel also leaves the power spectrum |X[k]|^2 of every frame there.  NULL switches it off. */
 B2A_API int b2a_debug_tc_power_buffer(void* device_ptr);

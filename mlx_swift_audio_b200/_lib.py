@@ -117,6 +117,7 @@ SIGNATURES = {
                                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2a_debug_whisper_tc": (C.c_int, [C.c_int]),
     "b2a_debug_wpf1920": (C.c_int, [C.c_int]),
+    "b2a_debug_dyn_tiles": (C.c_int, [C.c_int]),
     "b2a_debug_tc_power_buffer": (C.c_int, [C.c_void_p]),
     "b2a_ctx_enable_timing": (C.c_int, [_ctx, C.c_int]),
     "b2a_ctx_last_kernel_ms": (C.c_int, [_ctx, _f]),

@@ -695,6 +695,11 @@ int b2a_memcpy_d2h(b2a_ctx* c, void* host_dst, const void* device_src, uint64_t 
   return rc != B2A_OK ? rc : cu(c, cudaStreamSynchronize(c->stream), "sync");
 }
 
+int b2a_debug_dyn_tiles(int on) {
+  frontend_dyn_tiles_enable(on);
+  return B2A_OK;
+}
+
 int b2a_debug_whisper_tc(int on) {
   tc_whisper_enable(on);
   return B2A_OK;

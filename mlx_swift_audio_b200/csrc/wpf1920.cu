@@ -19,7 +19,9 @@
 //     contiguous range of frames per warp balances the tail better but measured 7 % slower: 2368 streams 104 KB apart keep as many
 //     DRAM rows open; requesting the next frame's samples ahead of the mel projection spills at 128 registers and measured 7 % slower;
 //     strips handed to the warps by a launch-wide atomic counter -- what the tiled kernels of frontend.cu gain 5 % from -- measured 3 % slower
-//     here, 0.350 vs 0.339 ms: the 16 warps of a CTA then no longer work on 16 neighbouring strips whose frames overlap in the L1);
+//     here, 0.350 vs 0.339 ms: the 16 warps of a CTA then no longer work on 16 neighbouring strips whose frames overlap in the L1; one
+//     contiguous range of strips per CTA with a shared-memory counter for its warps -- neighbours kept, ranges equal to within one strip --
+//     measured the same as the round-robin deal, 0.337 ms either way: the tail is not what bounds this kernel);
 //   * the frame is rotated by rot = pad_left mod 32 samples (x'[m] = x[(m + rot) mod 1920], window rotated alike) so that the 128-byte
 //     lines are aligned: a circular shift changes the phase of X[k] only, and only |X| is used.
 // Reflect / zero padded edge frames (4 of 500) are staged sample by sample through the padding index map (pad_index.cuh).

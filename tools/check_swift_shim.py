@@ -34,7 +34,7 @@ NOT_BOUND = {
     "b2a_version": "diagnostics", "b2a_reflect_pad_index": "index rule used by tests", "b2a_istft_out_length": "shape rule, inlined",
     "b2a_s3tokenizer_plan_segments": "S3Tokenizer windows: INTEGRATION.md section 4", "b2a_s3tokenizer_gather_segments": "see plan_segments",
     "b2a_debug_mel_program_apply": "test hook", "b2a_debug_plan_layout": "test hook", "b2a_debug_mel_program_dump": "build-time generator hook",
-    "b2a_debug_whisper_tc": "experimental switch", "b2a_debug_wpf1920": "A/B switch", "b2a_debug_wpf_mel_apply": "host test hook", "b2a_debug_tc_power_buffer": "bring-up hook", "b2a_ctx_enable_timing": "diagnostics",
+    "b2a_debug_whisper_tc": "experimental switch", "b2a_debug_wpf1920": "A/B switch", "b2a_debug_dyn_tiles": "A/B switch", "b2a_debug_wpf_mel_apply": "host test hook", "b2a_debug_tc_power_buffer": "bring-up hook", "b2a_ctx_enable_timing": "diagnostics",
     "b2a_ctx_last_kernel_ms": "diagnostics", "b2a_resample_poly_filter": "host table used by tests",
     "b2a_log_mel_spectrogram_chatterbox_ragged": "ragged: bound like whisperLogMelSpectrogramRagged", "b2a_funasr_log_mel_spectrogram_ragged": "ragged",
     "b2a_voice_encoder_melspectrogram_ragged": "ragged", "b2a_funasr_preprocess_audio_ragged": "ragged", "b2a_kaldi_fbank_campplus_ragged": "ragged",
