@@ -455,10 +455,11 @@ int run_preset(b2a_ctx* c, const Preset& p, const void* audio, int64_t batch, in
       int rc;
       // clip maxima and tile minima back to back: one memset initialises both (launch_plan)
       const size_t n_tiles = rg ? size_t(a.total_tiles) : size_t(n) * tiles;
-      if ((rc = ensure(c, c->scratch[slot][0], sizeof(int) * (size_t(n) + n_tiles + 1))) != B2A_OK) return rc;
+      if ((rc = ensure(c, c->scratch[slot][0], sizeof(int) * (size_t(n) + 2 * n_tiles + 1))) != B2A_OK) return rc;
       a.clip_max = static_cast<int*>(c->scratch[slot][0].p);
       a.tile_min = reinterpret_cast<float*>(a.clip_max + n);
-      a.tile_ctr = a.clip_max + n + n_tiles;   // the dynamic tile walk's counter, initialised by the same memset
+      a.tile_max = a.clip_max + n + n_tiles;       // per-tile maxima (used by the kernels that track them)
+      a.tile_ctr = a.clip_max + n + 2 * n_tiles;   // the dynamic tile walk's counter, initialised by the same memset
     } else {
       int rc;
       if ((rc = ensure(c, c->scratch[slot][0], sizeof(int))) != B2A_OK) return rc;

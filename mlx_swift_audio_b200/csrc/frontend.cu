@@ -179,6 +179,8 @@ struct FrontendParams {
   float* out;
   int* clip_max;
   int* tile_min;   // per tile: ordered-int encoding of MINUS the minimum normalised value (atomicMax, same 0x80.. initial pattern as clip_max)
+  int* tile_max;   // per tile: the maximum normalised value (floor applied), or null: a tile that lies entirely at or below the clip's clamp
+                   // threshold -- silence -- becomes that constant, which the clamp kernel then writes without reading the tile (RAWT kernels)
   // Ragged batches (per-clip lengths; RAGGED kernels only): clip b = (n_samples, n_frames, lfr_rows, index of its first tile);
   // tile g of the launch = tile_tab[g] = (clip, tile within the clip, the clip's n_samples, n_frames), built on the device from
   // clip_tab (tile_table_kernel): ONE load per tile, issued a tile ahead -- a second, dependent load of the clip's row cost ~1000
@@ -1002,6 +1004,7 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
             const float nmax = fmaf(lg2_ftz(fmaxf(__int_as_float(wmax), log_floor)), 0.25f * 0.30102999566398120f, 1.0f);
             const float nmin = fmaf(lg2_ftz(__int_as_float(wmin)), 0.25f * 0.30102999566398120f, 1.0f);
             red_max_s32(prm.clip_max + clip, enc_ordered(nmax));
+            if (prm.tile_max != nullptr) red_max_s32(prm.tile_max + (tmin_p - prm.tile_min), enc_ordered(nmax));
             red_max_s32(tmin_p, enc_ordered(-nmin));   // the NEGATED minimum, ordered-int encoded: one 0x80 memset initialises clip_max and tile_min alike
           }
         } else {
@@ -1116,7 +1119,8 @@ constexpr int kFillFlag = 0x40000000;   // s_list entry: the tile was skipped by
 // clip_tab != null (ragged batch): the clip's own frame count and first tile; `n_frames` stays the (M, T') row stride.
 __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const int* clip_max, const int* tile_min, int tiles_per_clip,
                                                             long long n_frames, int n_mels, long long out_clip_stride, int out_mode, int ft,
-                                                            const int4* __restrict__ clip_tab, int f16, float log_floor, int group) {
+                                                            const int4* __restrict__ clip_tab, int f16, float log_floor, int group,
+                                                            const int* __restrict__ tile_max) {
   __shared__ int s_list[kClampTilesPerCta];
   __shared__ int s_count;
   // launched with programmatic stream serialisation behind the front-end kernel (launch_plan): the blocks may already be resident
@@ -1141,7 +1145,9 @@ __global__ void __launch_bounds__(256) whisper_clamp_kernel(float* out, const in
   __syncthreads();
   if (int(threadIdx.x) < group && t0 + int(threadIdx.x) < tiles_per_clip) {
     const int tm = tile_min[tile_base + t0 + threadIdx.x];   // the negated minimum, or kTileFill: a tile of silence the main kernel skipped
-    if (tm == kTileFill) s_list[atomicAdd(&s_count, 1)] = (t0 + threadIdx.x) | kFillFlag;
+    // (tile_max: a tile whose largest value does not exceed the threshold becomes the threshold everywhere -- written without reading)
+    if (tm == kTileFill || (tile_max != nullptr && dec_ordered(tile_max[tile_base + t0 + threadIdx.x]) <= thr))
+      s_list[atomicAdd(&s_count, 1)] = (t0 + threadIdx.x) | kFillFlag;
     else if (-dec_ordered(tm) < thr) s_list[atomicAdd(&s_count, 1)] = t0 + threadIdx.x;   // (order within the list is irrelevant)
   }
   __syncthreads();
@@ -1839,6 +1845,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   prm.out = a.out;
   prm.clip_max = a.clip_max;
   prm.tile_min = reinterpret_cast<int*>(a.tile_min);
+  prm.tile_max = nullptr;
   prm.tiles_per_clip = frontend_tiles_per_clip(P::N, a.n_frames);
   prm.walk_tpc = RAGGED ? prm.tiles_per_clip : walk_tpc;
   prm.n_clips = int(a.batch);
@@ -1907,11 +1914,15 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   // initialises it too: 0x80808080), otherwise it gets a 4-byte memset of its own
   prm.tile_ctr = nullptr;
   prm.tile_ctr_init = 0;
+  // per-tile maxima (kernels that track the raw sums): behind the tile minima, same initial pattern
+  const bool contiguous = a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch;
+  if (B2A_RAW_TRACK && POST == POST_WNORM && contiguous && a.tile_max == reinterpret_cast<int*>(a.tile_min) + table_tiles) prm.tile_max = a.tile_max;
+  const long long table_words = a.batch + table_tiles * (prm.tile_max != nullptr ? 2 : 1);   // clip maxima, tile minima (, tile maxima)
   if (!ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > (RAGGED ? 3 : 2) * nblocks) {
     prm.tile_ctr = a.tile_ctr;
-    if (a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch && a.tile_ctr == a.clip_max + a.batch + table_tiles) {
+    if (contiguous && a.tile_ctr == a.clip_max + table_words) {
       prm.tile_ctr_init = int(0x80808080u);
-      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + table_tiles + 1), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(table_words + 1), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     } else {
       if ((e = cudaMemsetAsync(a.tile_ctr, 0, sizeof(int), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     }
@@ -1920,7 +1931,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     // clip_max and the (negated) tile minima start from the same "very negative" pattern: one memset when the C ABI placed them
     // back to back
     if (reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch) {
-      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch + table_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
+      if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(table_words), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     } else {
       if ((e = cudaMemsetAsync(a.clip_max, 0x80, sizeof(int) * size_t(a.batch), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
       if ((e = cudaMemsetAsync(a.tile_min, 0x80, sizeof(int) * size_t(table_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
@@ -1948,8 +1959,9 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       const int* c_max = a.clip_max + c0;
       const int* c_min = RAGGED ? prm.tile_min : prm.tile_min + c0 * prm.tiles_per_clip;
       const int4* c_tab = RAGGED ? prm.clip_tab + c0 : nullptr;
+      const int* c_tmax = prm.tile_max == nullptr ? nullptr : (RAGGED ? prm.tile_max : prm.tile_max + c0 * prm.tiles_per_clip);
       if ((e = cudaLaunchKernelEx(&cfg, whisper_clamp_kernel, c_out, c_max, c_min, prm.tiles_per_clip, (long long)a.n_frames, a.bank.n_mels,
-                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0, clamp_floor, group)) != cudaSuccess)
+                                  prm.out_clip_stride, a.out_mode, int(P::FT), c_tab, F16 ? 1 : 0, clamp_floor, group, c_tmax)) != cudaSuccess)
         return cuda_fail(e, "whisper_clamp_kernel launch", err);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);
@@ -1966,7 +1978,7 @@ int launch_whisper_clamp(float* out, const int* clip_max, const int* tile_min, i
     const long long nb = std::min<long long>(65535, batch - c0);
     const int group = clamp_group((long long)tiles * batch);
     whisper_clamp_kernel<<<dim3(unsigned((tiles + group - 1) / group), unsigned(nb)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0, -1.0f, group);
+        out + c0 * stride, clip_max + c0, tile_min + c0 * tiles, tiles, n_frames, n_mels, stride, OUT_TM, 32, nullptr, 0, -1.0f, group, nullptr);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "whisper_clamp_kernel launch", err);

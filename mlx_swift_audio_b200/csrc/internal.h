@@ -111,6 +111,7 @@ struct FrontendArgs {
   // scratch for the Whisper clamp (device): clip_max (batch) ordered-int encoded, tile_min (batch * tiles)
   int* clip_max = nullptr;
   float* tile_min = nullptr;
+  int* tile_max = nullptr;   // optional: batch * tiles more ints right behind tile_min (per-tile maxima: silent tiles are filled without being read)
   // ragged batch (per-clip lengths): device tables -- clip_tab[b] = int4(n_samples, n_frames, lfr_rows, first tile of the
   // clip), uploaded by the C ABI, and tile_tab[g] = int4(clip, tile, n_samples, n_frames), built from it on the device (launch_tile_table);
   // n_samples / n_frames / lfr_rows above are then those of the longest clip (they give the strides).

@@ -101,3 +101,34 @@ def test_ragged_two_tiles_ahead(api, ctx, both):
                lambda: api.kaldiFbankCAMPPlusRagged(x, lengths, meanNorm=True, ctx=ctx), lambda: api.funASRLogMelSpectrogramRagged(x, lengths, ctx=ctx)):
         (dyn, rows_d), (sta, rows_s) = both(fn)
         assert list(rows_d) == list(rows_s) and np.array_equal(np.asarray(dyn), np.asarray(sta))
+
+
+def test_tiles_below_the_clamp_threshold_are_filled(api, ctx):
+    # whisper_clamp_kernel writes the threshold without reading a tile whose largest value does not exceed it (per-tile maxima from the
+    # main kernel): a loud stretch, a stretch 120 dB quieter (non-zero, every value below Lmax - 8), a stretch of exact zeros, and a loud
+    # burst at the very end so that tiles of all three kinds sit inside the clip.  max(v, thr) == thr exactly, so the features must agree
+    # with the oracle like any other clip, in every layout / type, alone and ragged.
+    rng = np.random.default_rng(5100)
+    n = 16000 * 20
+    x = np.zeros((5, n), np.float32)
+    for b in range(5):
+        loud = (0.3 * rng.standard_normal(n)).astype(np.float32)
+        x[b, :16000 * 6] = loud[:16000 * 6]
+        x[b, 16000 * 6:16000 * 12] = 1e-6 * loud[16000 * 6:16000 * 12]
+        x[b, 16000 * 19:] = loud[16000 * 19:]
+    for n_mels in (128, 80):
+        got = api.whisperLogMelSpectrogram(x, nMels=n_mels, ctx=ctx)
+        for b in (0, 4):
+            want = R.whisper_log_mel_spectrogram(x[b], n_mels)
+            assert_feat_close(got[b], want, what=f"whisper {n_mels}: quiet / silent tiles")
+            thr = want.max() - 2.0
+            assert np.all(got[b, 700:1100] == got[b, 700, 0]) and abs(float(got[b, 700, 0]) - thr) <= 1e-4   # the quiet stretch: one constant
+            assert np.all(got[b, 1300:1800] == got[b, 700, 0])                                               # the zeros: the same constant
+    f16 = api.whisperLogMelSpectrogramF16(x, nMels=128, ctx=ctx)
+    assert np.array_equal(f16.view(np.uint16), api.whisperLogMelSpectrogram(x, nMels=128, ctx=ctx).astype(np.float16).view(np.uint16))
+    mt = api.logMelSpectrogramChatterbox(x, ctx=ctx)
+    assert_feat_close(mt[2], R.log_mel_spectrogram_chatterbox(x[2]), what="chatterbox: quiet / silent tiles")
+    lengths = [n, 16000 * 13, 16000 * 7 + 5, n - 1, 16000 * 12]
+    rg, rows = api.whisperLogMelSpectrogramRagged(x, lengths, nMels=128, ctx=ctx)
+    for b, ln in enumerate(lengths):
+        assert_feat_close(np.asarray(rg)[b, :rows[b]], R.whisper_log_mel_spectrogram(x[b, :ln], 128), what=f"ragged clip {b}: quiet / silent tiles")
