@@ -462,7 +462,7 @@ B2A_DEV void stage_pcm(const FrontendParams<P>& prm, float* __restrict__ buf, in
 // asType(.float16) of the fp32 feature, WhisperSTT.swift:156-157,181-182); clamp bookkeeping stays in fp32.
 // ZS: the launch has a zero tail (Whisper `padding` > 0) -- the instantiation that skips tiles of silence (B2A_SKIP_ZERO_TILES); launches
 // without one keep the kernel without that code (measured: the test alone cost 0.35 - 0.5 % of the unpadded 1024 x 30 s step).
-template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false, bool F16 = false, bool ZS = false>
+template <class P, int PRE, int SPEC, int MEL, int POST, int OUT, bool RAGGED = false, bool F16 = false, bool ZS = false, bool DYN = false>
 __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __grid_constant__ FrontendParams<P> prm) {
   constexpr int N1 = P::N1, N2 = P::N2, H1 = P::H1, FT = P::FT, HOP = P::HOP, NW = P::NWARPS, N = P::N, WIN = P::WIN;
   constexpr bool cplx = SPEC == SK_CPLX;
@@ -498,8 +498,13 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
   if (steps_in_smem)
     for (int i = threadIdx.x; i < prm.n_steps; i += P::NTHREADS) s_steps[i] = __ldg(prm.fb_steps + i);
   __shared__ float s_part[PRE == PRE_KALDI ? NW * FT : 1];   // Kaldi: per-warp partial sums of the frame mean
-  __shared__ int s_next;   // dynamic tile walk: the tile the counter handed to this CTA for its next round (published by the post-A barrier)
-  const bool dyn = !RAGGED && !ZS && prm.tile_ctr != nullptr;
+  // dynamic tile walk (DYN: a compile-time variant of the equal-length kernels -- as a run-time switch its branches and the per-thread
+  // division cost 660 instructions per tile, 6 %): the (clip, tile) the counter handed to this CTA for its next round, worked out by
+  // thread 0 alone and published by the post-A barrier
+  __shared__ int2 s_next2;
+  __shared__ int s_next;   // (ragged batches: the index into the tile table)
+  static_assert(!DYN || (!RAGGED && !ZS), "the compile-time dynamic walk is the equal-length kernels'");
+  constexpr bool dyn = DYN;
   // ragged batches: the counter's answer is an index into tile_tab, whose entry has to be loaded a tile ahead of its use -- so the walk is
   // requested TWO tiles ahead (the CTA's first two tiles are static: blockIdx.x and blockIdx.x + gridDim.x)
   const bool dyn_r = RAGGED && !ZS && prm.tile_ctr != nullptr;
@@ -710,14 +715,17 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
         }
       }
     }
-    if ((dyn || dyn_r) && tid == 0) s_next = next_req;
+    if (dyn_r && tid == 0) s_next = next_req;
+    if (dyn && tid == 0) {
+      const int nc = next_req / wtpc;
+      s_next2 = make_int2(next_req >= prm.total_tiles ? n_clips : nc, next_req - nc * wtpc);
+    }
     __syncthreads();
     if (dyn_r) g_next2 = s_next;
     if (dyn) {
-      const int ngd = s_next;
-      nclip = ngd / wtpc;
-      ntile = ngd - nclip * wtpc;
-      if (ngd >= prm.total_tiles) nclip = n_clips;
+      const int2 v = s_next2;
+      nclip = v.x;
+      ntile = v.y;
     }
     if (EARLY_PREFETCH && nclip < n_clips) stage_pcm<P>(prm, smem, nclip, ntile * FT, nn_samples, nn_samples + zero_tail, tid, lane, warp);
 
@@ -1766,13 +1774,26 @@ bool frontend_plan_exists(int n_fft, int hop, int win_len) {
 }
 
 bool frontend_dyn_tiles();
+static int sm_count() {   // SMs of the current device (cached per device)
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 int frontend_tiles_per_clip(int n_fft, int64_t n_frames) {
   const PlanShape* ps = plan_shape(n_fft);
   const int ft = ps ? ps->frame_tile : 32;
   return int((n_frames + ft - 1) / ft);
 }
 
-template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false, bool F16 = false, bool ZS = false>
+template <class P, int PRE, int SPEC, int MEL = 0, int POST = POST_RUNTIME, int OUT = -1, bool RAGGED = false, bool F16 = false, bool ZS = false, bool DYN = false>
 static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, std::string* err) {
   int walk_tpc = frontend_tiles_per_clip(P::N, a.n_frames);
   if constexpr (!ZS && B2A_SKIP_ZERO_TILES && B2A_RAW_TRACK && POST == POST_WNORM && MEL > 0 && PRE != PRE_KALDI) {
@@ -1801,6 +1822,11 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     if constexpr (MEL == 0 && POST == POST_RUNTIME && OUT == -1 && SPEC != SK_CPLX) return launch_plan<P, PRE, SPEC, 0, POST_RUNTIME, -1, true>(a, st, launches, err);
     if (err) *err = "ragged batches are built for the mel front ends only";
     return B2A_E_UNSUPPORTED;
+  }
+  if constexpr (!DYN && !RAGGED && !ZS && SPEC != SK_CPLX) {
+    // equal-length mel launches of more than two rounds of persistent CTAs: the instantiation with the dynamic tile walk
+    if (a.tile_ctr != nullptr && frontend_dyn_tiles() && (long long)walk_tpc * a.batch > 2LL * sm_count() * P::MINB)
+      return launch_plan<P, PRE, SPEC, MEL, POST, OUT, false, F16, false, true>(a, st, launches, err);
   }
   // (by value on the stack: launches from different contexts / threads share nothing)
   FrontendParams<P> prm;
@@ -1894,10 +1920,10 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
     std::lock_guard<std::mutex> lk(info_mu);
     if (!di.ready.load(std::memory_order_relaxed)) {
       int n_sm = 148, per_sm = 1;
-      if ((e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
+      if ((e = cudaFuncSetAttribute(frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) != cudaSuccess)
         return cuda_fail(e, "cudaFuncSetAttribute", err);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS>, P::NTHREADS, smem)) != cudaSuccess)
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS, DYN>, P::NTHREADS, smem)) != cudaSuccess)
         return cuda_fail(e, "occupancy query", err);
       if (per_sm < 1) {
         if (err) *err = "frontend kernel does not fit on this device";
@@ -1918,7 +1944,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
   const bool contiguous = a.whisper_norm && reinterpret_cast<int*>(a.tile_min) == a.clip_max + a.batch;
   if (B2A_RAW_TRACK && POST == POST_WNORM && contiguous && a.tile_max == reinterpret_cast<int*>(a.tile_min) + table_tiles) prm.tile_max = a.tile_max;
   const long long table_words = a.batch + table_tiles * (prm.tile_max != nullptr ? 2 : 1);   // clip maxima, tile minima (, tile maxima)
-  if (!ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > (RAGGED ? 3 : 2) * nblocks) {
+  if (DYN || (RAGGED && !ZS && a.tile_ctr != nullptr && frontend_dyn_tiles() && prm.total_tiles > 3 * nblocks)) {
     prm.tile_ctr = a.tile_ctr;
     if (contiguous && a.tile_ctr == a.clip_max + table_words) {
       prm.tile_ctr_init = int(0x80808080u);
@@ -1937,7 +1963,7 @@ static int launch_plan(const FrontendArgs& a, cudaStream_t st, int* launches, st
       if ((e = cudaMemsetAsync(a.tile_min, 0x80, sizeof(int) * size_t(table_tiles), st)) != cudaSuccess) return cuda_fail(e, "memset", err);
     }
   }
-  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
+  frontend_kernel<P, PRE, SPEC, MEL, POST, OUT, RAGGED, F16, ZS, DYN><<<unsigned(nblocks), P::NTHREADS, smem, st>>>(prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "frontend_kernel launch", err);
   *launches += 1;
   if (a.whisper_norm) {
