@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(P::NTHREADS, P::MINB) frontend_kernel(const __
     }
   }
 
-  // tile walk: (clip, tile) advances by gridDim.x tiles per iteration without divisions in the loop
+  // tile walk.  Static (launches of at most two rounds, B2A_DYN_TILES=0): (clip, tile) advances by gridDim.x tiles per iteration without
+  // divisions in the loop.  Dynamic (DYN / dyn_r): the first tile is blockIdx.x, every further one comes from the launch-wide counter.
   const int tpc = prm.tiles_per_clip, n_clips = prm.n_clips;
   const int wtpc = RAGGED ? tpc : prm.walk_tpc;   // tiles per clip the walk visits
   const int step_clip = int(gridDim.x) / wtpc, step_tile = int(gridDim.x) - step_clip * wtpc;
