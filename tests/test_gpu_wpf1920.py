@@ -134,7 +134,7 @@ def test_s3gen_pure_tone_against_fp64_truth(api, ctx, both_kernels):
 
 
 def test_pruned_stage_b_is_bit_identical(api, ctx):
-    # S3Gen's bank ends at bin 639 of 961 (fmax 8000 Hz at 24 kHz), so the kernel skips the ten outputs of every 32-point stage-B transform
+    # S3Gen's bank ends at bin 640 of 961 (fmax 8000 Hz at 24 kHz), so the kernel skips the ten outputs of every 32-point stage-B transform
     # that only feed bins 641..960 (wpf1920.cu, PRUNE); b2a_debug_wpf1920(2) runs the same kernel with every bin formed.  Interior frames,
     # edge frames (staged through the exchange buffer, whose pad words lie in the pruned band) and ragged tiles must agree bit for bit,
     # and a NaN sample in an edge frame must not leak into later frames of the same warp.

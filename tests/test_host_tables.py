@@ -304,3 +304,27 @@ def test_wpf_mel_schedule_rejects_what_does_not_fit(built_lib):
     p = np.ones(961, np.float32)
     out = np.zeros(128, np.float32)
     assert built_lib.b2a_debug_wpf_mel_apply(bank.ctypes.data_as(fp), 128, 961, 0, p.ctypes.data_as(fp), out.ctypes.data_as(fp)) == -1
+
+
+def test_process_wide_switches_are_host_only(built_lib):
+    # A/B switches of the kernels' scheduling (dynamic tile walk, warp-per-frame n_fft 1920 kernel and its pruned stage B): plain host state,
+    # settable without a GPU, and none of them may change results (tests/test_gpu_dyn_tiles.py, tests/test_gpu_wpf1920.py compare both sides)
+    for fn, values in ((built_lib.b2a_debug_dyn_tiles, (0, 1)), (built_lib.b2a_debug_wpf1920, (0, 2, 1))):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int]
+        for v in values:
+            assert fn(v) == 0
+
+
+def test_pruned_band_of_the_1920_point_kernel():
+    # wpf1920.cu PRUNE: with a bank that reads no bin above 640, bin k1 + 60 k2 (direct, k2 < 16) or 1920 - k1 - 60 k2 (mirror image, k2 > 16)
+    # of every stage-B row k1 = 0..30 lies above 640 for k2 = 11..20 -- and for no other k2 in EVERY lane; S3Gen's bank ends at bin 640
+    # (8000 Hz at 12.5 Hz per bin: the last filter's falling edge leaves a rounding-sized weight there)
+    dead = []
+    for k2 in range(32):
+        bins = [(k1 + 60 * k2) if k2 < 16 else (960 - k1 if k2 == 16 else 1920 - k1 - 60 * k2) for k1 in range(31)]
+        if all(b > 640 for b in bins):
+            dead.append(k2)
+    assert dead == list(range(11, 21))
+    fb = R.mel_filters(24000, 1920, 80, 0.0, 8000.0)
+    assert int(np.nonzero(fb.any(axis=0))[0].max()) <= 640
